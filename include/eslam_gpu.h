@@ -1,0 +1,179 @@
+/* eslam_gpu.h -- C ABI of libeslam_gpu.so: the B200 implementation of eSLAM's particle-filter
+ * update path.  Plain pointers and sizes only; every call returns an int status (0 = ok) and
+ * never throws.  The host C++ facade (include/eslam/ *.hpp) keeps the reference's class API
+ * (PoseEstimator / ContactModel / EmbodiedSlamFilter / ParticleFilter<PoseParticle>) on top of
+ * these entry points; INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * checkout, liyangSKD/slam-eslam).
+ */
+#ifndef ESLAM_GPU_H
+#define ESLAM_GPU_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESLAM_MAX_CONTACTS 128   /* body contact points per update (Asguard: 4 wheels x 5 feet) */
+#define ESLAM_MAX_CP 8           /* fused contact points reported per pose by the diagnostic call */
+
+enum {
+    ESLAM_OK = 0,
+    ESLAM_ERR_INVALID = 1,       /* bad argument */
+    ESLAM_ERR_CUDA = 2,          /* CUDA runtime failure, see eslam_gpu_last_error */
+    ESLAM_ERR_NO_ENVIRONMENT = 3,/* "No environment attached." src/PoseEstimator.cpp:259-260 */
+    ESLAM_ERR_ZERO_VARIANCE = 4, /* zero measurement variance, src/ContactModel.cpp:122-123 */
+    ESLAM_ERR_EMPTY = 5,         /* empty particle set, assert at src/ParticleFilter.hpp:91 */
+    ESLAM_ERR_COMM = 6           /* collective hook failed */
+};
+
+enum { ESLAM_RESAMPLE_STRATIFIED = 0,   /* reference: src/ParticleFilter.hpp:85-108 */
+       ESLAM_RESAMPLE_SYSTEMATIC = 1 }; /* north_star: one uniform for all strata */
+
+/* Hot-path fields of eslam::Configuration / ContactModelConfiguration
+ * (src/Configuration.hpp:51-111).  eslam_gpu_default_config() fills the reference defaults. */
+typedef struct eslam_gpu_config {
+    uint64_t seed;                       /* :114 seed */
+    uint64_t min_effective;              /* :120 minEffective (size_t) */
+    double measurement_error;            /* :136 */
+    double discount_factor;              /* :141 */
+    double spread_threshold;             /* :146 */
+    double spread_translation_factor;    /* :149 */
+    double spread_rotation_factor;       /* :152 */
+    double slip_factor;                  /* :158 */
+    double max_yaw_deviation;            /* :163 */
+    uint64_t min_contacts;               /* ContactModelConfiguration::minContacts :72 */
+    double contact_likelihood_correction;/* :76 */
+    double contact_point_radius;         /* :80 */
+    int32_t use_slip_update;             /* :64 (inert in the reference, quirk Q5) */
+    int32_t use_shape_update;            /* :67 */
+    int32_t use_hash;                    /* SurfaceHash attached: disables spreading, src/PoseEstimator.cpp:224 */
+    int32_t resample_mode;               /* ESLAM_RESAMPLE_* */
+    int32_t patch_size;                  /* 0: shared map only; P>0: per-particle PxP map patches */
+    int32_t reserved;
+} eslam_gpu_config;
+
+/* Particle shard owned by this context (multi-GPU: one context per rank). */
+typedef struct eslam_gpu_shard {
+    int32_t rank, world;
+    uint64_t global_count;               /* total particles over all ranks */
+} eslam_gpu_shard;
+
+/* Collective hooks used when world > 1; the caller binds them to NCCL (bench.py / tests bind
+ * torch.distributed).  Buffers are DEVICE pointers, calls are stream-ordered on `stream`. */
+typedef int (*eslam_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank, void* stream);
+typedef struct eslam_gpu_comm {
+    void* user;
+    eslam_allgather_fn allgather;
+} eslam_gpu_comm;
+
+/* Per-step inputs of PoseEstimator::project (src/PoseEstimator.cpp:184-194); the facade derives
+ * them from the orientation quaternion and odometry::FootContact. */
+typedef struct eslam_gpu_step {
+    double yaw;            /* base::getYaw(orientation) :186 */
+    double z_delta;        /* (orientation * poseDelta).translation().z() :188-189 */
+    double z_var;          /* odometry.getPositionError()(2,2) * 2 :192 */
+    double delta_mean[3];  /* odometry pose delta mean (x, y, theta) */
+    double delta_sigma[3]; /* std-dev of odometry.getPoseDeltaSample2D() :198 */
+} eslam_gpu_step;
+
+/* odometry::BodyContactPoint after ContactModel::setContactPoints (src/ContactModel.cpp:21-41):
+ * position already rotated by removeYaw(orientation). */
+typedef struct eslam_gpu_contact {
+    double position[3];
+    float contact;         /* contact probability; NaN = unknown (passes the 0.2 gate) */
+    float slip;
+    int32_t group_id;      /* -1 = ungrouped */
+    int32_t pad;
+} eslam_gpu_contact;
+
+/* What PoseEstimator::update leaves behind (src/PoseEstimator.cpp:244-255, 329-351). */
+typedef struct eslam_gpu_update_result {
+    double ess;              /* normalizeWeights() return value */
+    double max_weight;       /* max contact weight, carried into the next project (Q10) */
+    double floating_weight;  /* :329 */
+    double weights_sum;      /* getWeightsSum() before normalising */
+    uint64_t data_particles; /* :307 */
+    uint64_t total_points;   /* :310 */
+    int32_t resampled;       /* eff < minEffective */
+    int32_t status;          /* ESLAM_OK or ESLAM_ERR_ZERO_VARIANCE */
+} eslam_gpu_update_result;
+
+typedef struct eslam_gpu_ctx eslam_gpu_ctx;
+
+void eslam_gpu_default_config(eslam_gpu_config* cfg);                 /* src/Configuration.hpp:53-59,85-111 */
+int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_shard* shard_or_null,
+                     const eslam_gpu_comm* comm_or_null, eslam_gpu_ctx** out);   /* PoseEstimator ctor, src/PoseEstimator.cpp:13-25 */
+void eslam_gpu_destroy(eslam_gpu_ctx* ctx);
+const char* eslam_gpu_last_error(const eslam_gpu_ctx* ctx);
+
+/* PoseEstimator::setEnvironment + GridAccess::setMap (src/PoseEstimator.cpp:47-62, src/PoseEstimator.hpp:68-77):
+ * dense elevation grid, cells[iy*width+ix] = {mean, stdev}, NaN mean = empty cell;
+ * cell index = floor((p - offset)/scale); g2l = row-major 3x4 C_global2local (NULL = identity). */
+int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells_mean_stdev, int width, int height,
+                       double scale_x, double scale_y, double offset_x, double offset_y, const double* g2l);
+
+/* PoseEstimator::init(n, mu, sigma, zpos, zsigma) (src/PoseEstimator.cpp:88-102). n = local shard size. */
+int eslam_gpu_init_gaussian(eslam_gpu_ctx* ctx, uint64_t n, const double mu[3], const double sigma[3],
+                            double zpos, double zsigma);
+/* ParticleFilter::getParticles() (src/ParticleFilter.hpp:150-158) as SoA; NULL pointers are skipped. */
+int eslam_gpu_set_particles(eslam_gpu_ctx* ctx, uint64_t n, const double* x, const double* y, const double* theta,
+                            const double* zpos, const double* zsigma, const double* weight);
+int eslam_gpu_get_particles(eslam_gpu_ctx* ctx, double* x, double* y, double* theta, double* zpos, double* zsigma,
+                            double* weight, double* mprob, uint8_t* floating, uint8_t* n_found);
+uint64_t eslam_gpu_particle_count(const eslam_gpu_ctx* ctx);
+
+/* PoseEstimator::project (src/PoseEstimator.cpp:184-242). */
+int eslam_gpu_project(eslam_gpu_ctx* ctx, const eslam_gpu_step* step);
+/* PoseEstimator::update = updateWeights + normalizeWeights + conditional resample
+ * (src/PoseEstimator.cpp:244-352).  result may be NULL (no host sync). */
+int eslam_gpu_update(eslam_gpu_ctx* ctx, const eslam_gpu_contact* pts, int n_pts, eslam_gpu_update_result* result);
+/* project + update as one fused launch sequence (EmbodiedSlamFilter::update(contact),
+ * src/EmbodiedSlamFilter.cpp:353-369 with the measurement threshold met). */
+int eslam_gpu_step_fused(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const eslam_gpu_contact* pts, int n_pts,
+                         eslam_gpu_update_result* result);
+/* Enqueue `steps` identical fused steps without host synchronisation (benchmark loop; inputs stay
+ * resident).  elapsed_ms (may be NULL) = CUDA-event time of the whole region on the context's stream;
+ * top_kernel_ms (may be NULL) = summed event time of the fused project+weight kernel alone. */
+int eslam_gpu_run_steps(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const eslam_gpu_contact* pts, int n_pts,
+                        int steps, float* elapsed_ms, float* top_kernel_ms, eslam_gpu_update_result* last_result);
+
+/* ParticleFilter::normalizeWeights (src/ParticleFilter.hpp:46-70); returns ESS. */
+int eslam_gpu_normalize_weights(eslam_gpu_ctx* ctx, double* ess);
+/* ParticleFilter::resample -> resample_stratified(N) (src/ParticleFilter.hpp:72-108). */
+int eslam_gpu_resample(eslam_gpu_ctx* ctx);
+/* parity taps: ancestor index of every particle after the last resample; the exact running-sum CDF. */
+int eslam_gpu_get_ancestors(eslam_gpu_ctx* ctx, uint32_t* ancestors);
+int eslam_gpu_get_cdf(eslam_gpu_ctx* ctx, double* cdf);
+
+/* PoseEstimator::getCentroid (src/PoseEstimator.cpp:354-383): out = {x, y, theta, z} weighted means. */
+int eslam_gpu_centroid(eslam_gpu_ctx* ctx, double out[4]);
+/* ParticleFilter::getBestParticleIndex (src/ParticleFilter.hpp:160-173). */
+int eslam_gpu_best_index(eslam_gpu_ctx* ctx, uint64_t* index);
+
+/* ContactModel::evaluatePose + evaluateWeight + updateZPositionEstimate for explicit poses
+ * (src/ContactModel.cpp:117-224,262-340) -- the seam the reference's testContactModel.cpp drives.
+ * All output pointers may be NULL.  cell_index: n*n_pts flat cell indices (iy*width+ix), -1 = not looked up / outside.
+ * cp: n*ESLAM_MAX_CP*5 doubles (point x, y, z, zdiff, zvar) of the fused contact points. */
+int eslam_gpu_evaluate_poses(eslam_gpu_ctx* ctx, uint64_t n, const double* x, const double* y, const double* theta,
+                             const double* zpos, const double* meas_var, const double* z_var_in,
+                             const eslam_gpu_contact* pts, int n_pts,
+                             uint8_t* ok, double* weight, double* z_delta, double* z_var, double* pose_var,
+                             int32_t* n_contacts, double* zpos_out, double* z_var_out,
+                             int32_t* cell_index, double* cp);
+
+/* EmbodiedSlamFilter per-particle map update (src/EmbodiedSlamFilter.cpp:179-232, narrowed by north_star to
+ * writing the fused contact heights of the last update into particle-local PxP grid patches). */
+int eslam_gpu_patch_update(eslam_gpu_ctx* ctx);
+int eslam_gpu_get_patches(eslam_gpu_ctx* ctx, float* cells_mean_stdev, int32_t* origin_xy);
+
+int eslam_gpu_synchronize(eslam_gpu_ctx* ctx);
+/* number of kernels this library has launched on ctx since creation (bench "gpu_launches") */
+uint64_t eslam_gpu_launch_count(const eslam_gpu_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESLAM_GPU_H */

@@ -1,0 +1,360 @@
+// eslam_math.h -- host/device arithmetic shared by the CUDA kernels and by the CPU oracle's
+// "shared" arithmetic policy.
+//
+// Every function here is built ONLY from IEEE-754 correctly rounded primitives
+// (+ - * / sqrt fma, int<->fp conversions, bit moves), with every contraction written
+// out as an explicit fma().  Compile device code with `-fmad=false` and host code with
+// `-ffp-contract=off` and the two sides produce bit-identical doubles.  That is what lets
+// the GPU path be compared bit-for-bit with the oracle instead of "within libm ulps".
+//
+// Nothing in this file is taken from the reference; the reference leans on boost / libm
+// (src/ContactModel.cpp:104-115, src/PoseEstimator.cpp:64-73) whose transcendental
+// implementations are neither vendored nor pinned.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define ESLAM_HD __host__ __device__ __forceinline__
+#else
+#define ESLAM_HD static inline __attribute__((always_inline))
+#endif
+
+namespace eslam_math {
+
+// ---------------------------------------------------------------- bit moves / fma
+ESLAM_HD uint64_t d2u(double x) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(x);
+#else
+    uint64_t u; __builtin_memcpy(&u, &x, 8); return u;
+#endif
+}
+ESLAM_HD double u2d(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double x; __builtin_memcpy(&x, &u, 8); return x;
+#endif
+}
+ESLAM_HD uint32_t f2u(float x) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(x);
+#else
+    uint32_t u; __builtin_memcpy(&u, &x, 4); return u;
+#endif
+}
+ESLAM_HD float u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float x; __builtin_memcpy(&x, &u, 4); return x;
+#endif
+}
+ESLAM_HD double fma_(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return __builtin_fma(a, b, c);
+#endif
+}
+ESLAM_HD float fmaf_(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return __builtin_fmaf(a, b, c);
+#endif
+}
+ESLAM_HD double sqrt_(double x) {
+#if defined(__CUDA_ARCH__)
+    return __dsqrt_rn(x);
+#else
+    return __builtin_sqrt(x);
+#endif
+}
+// round to nearest even integer, |x| < 2^51
+ESLAM_HD double rint_(double x) {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+    return (x + magic) - magic;
+}
+ESLAM_HD bool isnan_(double x) { return x != x; }
+
+// exact 2^k for k in [-1022, 1023]
+ESLAM_HD double pow2i(int k) { return u2d((uint64_t)(k + 1023) << 52); }
+
+// ---------------------------------------------------------------- Philox4x32-10
+// Counter-based RNG (Salmon et al., SC'11).  north_star: "counter-based Philox RNG".
+struct Philox4 { uint32_t v[4]; };
+
+ESLAM_HD void philox_mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b; hi = __umulhi(a, b);
+#else
+    uint64_t p = (uint64_t)a * (uint64_t)b; lo = (uint32_t)p; hi = (uint32_t)(p >> 32);
+#endif
+}
+
+ESLAM_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                               uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        philox_mulhilo(M0, c0, hi0, lo0);
+        philox_mulhilo(M1, c2, hi1, lo1);
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    Philox4 o; o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3; return o;
+}
+
+// RNG streams (counter word 3).  Counter layout: (index, step, slot, stream); key = seed.
+enum { STREAM_INIT = 0, STREAM_PROJECT = 1, STREAM_RESAMPLE = 2, STREAM_TERRAIN = 3 };
+
+// [0,1): 53 bits, like boost::uniform_real<>(0,1) over a full-range engine
+ESLAM_HD double u01(uint32_t hi, uint32_t lo) {
+    uint64_t x = ((uint64_t)hi << 32) | lo;
+    return (double)(x >> 11) * 1.1102230246251565e-16;  // 2^-53
+}
+// (0,1): 52 bits + half, safe for log()
+ESLAM_HD double u01_open(uint32_t hi, uint32_t lo) {
+    uint64_t x = ((uint64_t)hi << 32) | lo;
+    return ((double)(x >> 12) + 0.5) * 2.220446049250313e-16;  // 2^-52
+}
+
+// ---------------------------------------------------------------- exp
+// exp(x) to ~1 ulp: x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor in r (tail 4e-18).
+ESLAM_HD double exp_(double x) {
+    if (isnan_(x)) return x;
+    if (x > 709.782712893384) return u2d(0x7FF0000000000000ull);
+    if (x < -745.2) return 0.0;
+    const double L2E = 1.4426950408889634, LN2_HI = 6.93147180369123816490e-01,
+                 LN2_LO = 1.90821492927058770002e-10;
+    double k = rint_(x * L2E);
+    double r = fma_(-k, LN2_HI, x);
+    r = fma_(-k, LN2_LO, r);
+    double p = 1.6059043836821613e-10;               // 1/13!
+    p = fma_(p, r, 2.08767569878681e-09);            // 1/12!
+    p = fma_(p, r, 2.505210838544172e-08);           // 1/11!
+    p = fma_(p, r, 2.755731922398589e-07);           // 1/10!
+    p = fma_(p, r, 2.7557319223985893e-06);          // 1/9!
+    p = fma_(p, r, 2.48015873015873e-05);            // 1/8!
+    p = fma_(p, r, 0.0001984126984126984);           // 1/7!
+    p = fma_(p, r, 0.001388888888888889);            // 1/6!
+    p = fma_(p, r, 0.008333333333333333);            // 1/5!
+    p = fma_(p, r, 0.041666666666666664);            // 1/4!
+    p = fma_(p, r, 0.16666666666666666);             // 1/3!
+    p = fma_(p, r, 0.5);
+    p = fma_(p, r, 1.0);
+    p = fma_(p, r, 1.0);
+    int ki = (int)k;
+    int k1 = ki / 2, k2 = ki - k1;                    // both in [-538, 512]
+    return (p * pow2i(k1)) * pow2i(k2);
+}
+
+// ---------------------------------------------------------------- log
+// log(x), x > 0 finite normal or subnormal; ~1-2 ulp.  x = 2^k m, m in [sqrt(1/2), sqrt 2),
+// log m = 2 atanh(s), s = (m-1)/(m+1).
+ESLAM_HD double log_(double x) {
+    if (isnan_(x) || x < 0.0) return u2d(0x7FF8000000000000ull);
+    if (x == 0.0) return u2d(0xFFF0000000000000ull);
+    uint64_t u = d2u(x);
+    int k = 0;
+    if ((u >> 52) == 0) { x *= 18014398509481984.0; u = d2u(x); k = -54; }  // subnormal
+    if ((u >> 52) == 0x7FF) return x;
+    k += (int)(u >> 52) - 1023;
+    u = (u & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull;   // m in [1,2)
+    double m = u2d(u);
+    if (m > 1.4142135623730951) { m *= 0.5; k += 1; }
+    double f = m - 1.0;
+    double s = f / (m + 1.0);
+    double z = s * s;
+    double p = 0.047619047619047616;                  // 1/21
+    p = fma_(p, z, 0.05263157894736842);              // 1/19
+    p = fma_(p, z, 0.058823529411764705);             // 1/17
+    p = fma_(p, z, 0.06666666666666667);              // 1/15
+    p = fma_(p, z, 0.07692307692307693);              // 1/13
+    p = fma_(p, z, 0.09090909090909091);              // 1/11
+    p = fma_(p, z, 0.1111111111111111);               // 1/9
+    p = fma_(p, z, 0.14285714285714285);              // 1/7
+    p = fma_(p, z, 0.2);                              // 1/5
+    p = fma_(p, z, 0.3333333333333333);               // 1/3
+    // log m = 2s + 2s z p
+    double s2 = s + s;
+    double lm = fma_(s2 * z, p, s2);
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    double dk = (double)k;
+    return fma_(dk, LN2_HI, fma_(dk, LN2_LO, lm));
+}
+
+// ---------------------------------------------------------------- sin / cos kernels, |a| <= pi/4
+ESLAM_HD double sin_kernel(double a) {
+    double z = a * a;
+    double p = -8.22063524662433e-18;                 // -1/19!
+    p = fma_(p, z, 2.8114572543455206e-15);           //  1/17!
+    p = fma_(p, z, -7.647163731819816e-13);           // -1/15!
+    p = fma_(p, z, 1.6059043836821613e-10);           //  1/13!
+    p = fma_(p, z, -2.505210838544172e-08);           // -1/11!
+    p = fma_(p, z, 2.7557319223985893e-06);           //  1/9!
+    p = fma_(p, z, -0.0001984126984126984);           // -1/7!
+    p = fma_(p, z, 0.008333333333333333);             //  1/5!
+    p = fma_(p, z, -0.16666666666666666);             // -1/3!
+    return fma_(a * z, p, a);
+}
+ESLAM_HD double cos_kernel(double a) {
+    double z = a * a;
+    double p = 4.110317623312165e-19;                 //  1/20!
+    p = fma_(p, z, -1.5619206968586225e-16);          // -1/18!
+    p = fma_(p, z, 4.779477332387385e-14);            //  1/16!
+    p = fma_(p, z, -1.1470745597729725e-11);          // -1/14!
+    p = fma_(p, z, 2.08767569878681e-09);             //  1/12!
+    p = fma_(p, z, -2.755731922398589e-07);           // -1/10!
+    p = fma_(p, z, 2.48015873015873e-05);             //  1/8!
+    p = fma_(p, z, -0.001388888888888889);            // -1/6!
+    p = fma_(p, z, 0.041666666666666664);             //  1/4!
+    p = fma_(p, z, -0.5);
+    return fma_(z, p, 1.0);
+}
+ESLAM_HD void quadrant_(int q, double sk, double ck, double& s, double& c) {
+    switch (q & 3) {
+        case 0: s = sk;  c = ck;  break;
+        case 1: s = ck;  c = -sk; break;
+        case 2: s = -sk; c = -ck; break;
+        default: s = -ck; c = sk; break;
+    }
+}
+// sin/cos(2 pi u), u in [0,1): exact quadrant reduction (Box-Muller angle)
+ESLAM_HD void sincos_2pi(double u, double& s, double& c) {
+    double q = rint_(u * 4.0);          // 0..4
+    double r = u - q * 0.25;            // exact, |r| <= 1/8
+    double a = r * 6.283185307179586;
+    quadrant_((int)q, sin_kernel(a), cos_kernel(a), s, c);
+}
+// sin/cos(theta), three-part Cody-Waite reduction; full accuracy for |theta| < ~1e5,
+// graceful beyond (headings are un-wrapped sums of small deltas, src/PoseEstimator.cpp:206)
+ESLAM_HD void sincos_(double t, double& s, double& c) {
+    const double TWO_OVER_PI = 0.6366197723675814;
+    const double P1 = 1.57079632673412561417e+00, P2 = 6.07710050650619224932e-11,
+                 P3 = 2.02226624879595063154e-21;
+    double k = rint_(t * TWO_OVER_PI);
+    double r = fma_(-k, P1, t);
+    r = fma_(-k, P2, r);
+    r = fma_(-k, P3, r);
+    long long ki = (long long)k;
+    quadrant_((int)(ki & 3), sin_kernel(r), cos_kernel(r), s, c);
+}
+
+// ---------------------------------------------------------------- normals
+// Box-Muller on two open uniforms -> two independent N(0,1)
+ESLAM_HD void box_muller(double u1, double u2, double& n0, double& n1) {
+    double r = sqrt_(-2.0 * log_(u1));
+    double s, c; sincos_2pi(u2, s, c);
+    n0 = r * c; n1 = r * s;
+}
+
+// ---------------------------------------------------------------- 1/sqrt
+// ~1.5 ulp, deterministic: fp32 magic seed + 3 fp32 Newton steps + one fp64 Halley step.
+ESLAM_HD double rsqrt_(double x) {
+    if (!(x > 1e-30 && x < 1e30)) return 1.0 / sqrt_(x);
+    float xf = (float)x;
+    float y = u2f(0x5f3759dfu - (f2u(xf) >> 1));
+    float hx = 0.5f * xf;
+    float t;
+    t = y * y; t = fmaf_(-hx, t, 1.5f); y = y * t;
+    t = y * y; t = fmaf_(-hx, t, 1.5f); y = y * t;
+    t = y * y; t = fmaf_(-hx, t, 1.5f); y = y * t;
+    double yd = (double)y;
+    double h = x * yd;
+    double e = fma_(-h, yd, 1.0);
+    double p = fma_(0.375, e, 0.5);
+    return fma_(yd, e * p, yd);
+}
+
+// ---------------------------------------------------------------- inverse Mills ratio h(t) = phi(t)/Phi(t)
+// The reference computes pdf(n,z)/cdf(n,z) with n = Normal(0, sigma*corr)
+// (src/ContactModel.cpp:104-115) = h(z/s)/s, s = sigma*corr.  h is tabulated on
+// [-H_TMAX, H_TMAX) in H_NINT intervals of width 1/H_PER_UNIT as degree-5 polynomials in the
+// centred local coordinate (tools/gen_h_table.py; relative error <= 1e-10 everywhere a contact
+// can matter, <= 1e-12 for t <= 4).  Layout: tab[q*H_NINT + j] = (c[2q], c[2q+1]) so that
+// neighbouring intervals are neighbouring 16-byte words (shared-memory bank friendly).
+#define ESLAM_H_TMAX 10.0
+#define ESLAM_H_PER_UNIT 32
+#define ESLAM_H_NINT 640
+#define ESLAM_H_TABLE_DOUBLES (ESLAM_H_NINT * 6)
+
+struct dbl2 { double x, y; };
+
+ESLAM_HD double h_slow(double t) {
+    if (isnan_(t)) return t;
+    if (t > 0.0) {
+        // Phi(t) = 1 - O(1e-23) for t >= 10
+        return exp_(-0.5 * t * t) * 0.3989422804014327;
+    }
+    // 1/Mills(x) = x + 1/(x + 2/(x + 3/(x + ...))), x >= 10: Laplace continued fraction
+    double x = -t;
+    double f = x;
+    for (int k = 24; k >= 1; --k) f = x + (double)k / f;
+    return f;
+}
+
+ESLAM_HD double h_ratio(double t, const dbl2* tab) {
+    if (!(t >= -ESLAM_H_TMAX && t < ESLAM_H_TMAX)) return h_slow(t);
+    double fi = fma_(t, (double)ESLAM_H_PER_UNIT, ESLAM_H_TMAX * ESLAM_H_PER_UNIT);
+    int j = (int)fi;                      // fi >= 0: truncation == floor
+    if (j > ESLAM_H_NINT - 1) j = ESLAM_H_NINT - 1;
+    double z = (fi - (double)j) - 0.5;
+    dbl2 c01 = tab[j], c23 = tab[ESLAM_H_NINT + j], c45 = tab[2 * ESLAM_H_NINT + j];
+    double p = c45.y;
+    p = fma_(p, z, c45.x);
+    p = fma_(p, z, c23.y);
+    p = fma_(p, z, c23.x);
+    p = fma_(p, z, c01.y);
+    p = fma_(p, z, c01.x);
+    return p;
+}
+
+// contact likelihood ratio pdf/cdf for N(0, sqrt(zvar)*corr) at zdiff (src/ContactModel.cpp:104-115,170)
+// inv_corr = 1.0 / contactLikelihoodCorrection
+ESLAM_HD double likelihood_ratio(double zdiff, double zvar, double inv_corr, const dbl2* tab) {
+    double qc = rsqrt_(zvar) * inv_corr;   // 1 / (sigma * corr)
+    double t = zdiff * qc;
+    return h_ratio(t, tab) * qc;
+}
+
+// ---------------------------------------------------------------- powers
+// w^(1/n) as in pow(weight, 1.0/found_points) (src/PoseEstimator.cpp:309), w >= 0
+ESLAM_HD double root_n(double w, unsigned long long n) {
+    if (n == 1) return w;
+    if (n == 2) return sqrt_(w);
+    if (n == 4) return sqrt_(sqrt_(w));
+    if (w == 0.0) return 0.0;
+    if (n == 0) return (w == 1.0) ? 1.0 : (w < 1.0 ? 0.0 : u2d(0x7FF0000000000000ull));  // pow(w, inf)
+    return exp_(log_(w) / (double)n);
+}
+// x^e for the size_t exponent 4 - cpoints.size() (src/PoseEstimator.cpp:336), x >= 0.
+// e wraps to ~1.8e19 when more than 4 contacts were found (quirk Q2).
+ESLAM_HD double pow_u64(double x, unsigned long long e) {
+    if (e <= 16) {
+        double r = 1.0;
+        for (unsigned long long i = 0; i < e; ++i) r *= x;
+        return r;
+    }
+    if (isnan_(x)) return x;
+    if (x == 1.0) return 1.0;
+    return (x < 1.0) ? 0.0 : u2d(0x7FF0000000000000ull);
+}
+
+// ---------------------------------------------------------------- grid cell index
+// floor((x - offset) / scale) as envire's GridBase::toGrid does it (un-vendored).
+// Returns false when outside [0, n).  The device fast path multiplies by a reciprocal and only
+// falls back to this exact division when the quotient is within 2^-18 of an integer.
+ESLAM_HD bool cell_index_exact(double x, double offset, double scale, int n, int& idx) {
+    double q = floor((x - offset) / scale);
+    if (!(q >= 0.0 && q < (double)n)) return false;
+    idx = (int)q; return true;
+}
+
+}  // namespace eslam_math
