@@ -1,0 +1,584 @@
+// eslam_gpu.cu -- C ABI of libeslam_gpu.so (include/eslam_gpu.h): context, memory and launch sequencing.
+// All arithmetic lives in eslam_kernels.cuh; there is no CPU implementation of any step in this library.
+#include "eslam_kernels.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+static const em::dbl2 H_TABLE_HOST[ESLAM_H_NINT * 3] = {
+#include "eslam_h_table.inc"
+};
+
+struct eslam_gpu_ctx {
+    eslam_gpu_config cfg;
+    eslam_gpu_shard shard;
+    eslam_gpu_comm comm; bool has_comm;
+    int device;
+    cudaStream_t stream;
+    std::string error;
+    uint64_t launches;
+
+    // particles
+    uint64_t n, cap;
+    StateBufs st;
+    DevScalars* sc; DevScalars* sc_host;          // sc_host: pinned staging
+    uint32_t* ancestors; double* cdf;
+    // tiles
+    unsigned n_tiles, tile_cap;
+    TilePartA* part_a; double *tile_sum, *tile_sq, *tile_prefix, *scratch_a, *scratch_b, *tile_sin, *sb, *cent_part, *best_w;
+    unsigned long long* best_idx;
+    TileDesc* desc; int* tile_bofs; SegF* tile_pre;
+    // map
+    float2* cells; MapParams map; bool has_map;
+    em::dbl2* htab;
+    int max_smem_optin, sm_count;
+    uint32_t project_step;
+    // step staging
+    std::vector<cudaEvent_t> events;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char buf__[256];                                                                       \
+            snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            ctx->error = buf__;                                                                    \
+            return ESLAM_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+#define LAUNCHED() do { ctx->launches++; CK(cudaGetLastError()); } while (0)
+
+template <class T> static cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T)); }
+
+static void free_particles(eslam_gpu_ctx* ctx) {
+    for (int b = 0; b < 2; ++b) {
+        for (int f = 0; f < 7; ++f) { cudaFree(ctx->st.f[b][f]); ctx->st.f[b][f] = nullptr; }
+        for (int f = 0; f < 2; ++f) { cudaFree(ctx->st.b[b][f]); ctx->st.b[b][f] = nullptr; }
+    }
+    cudaFree(ctx->ancestors); cudaFree(ctx->cdf); ctx->ancestors = nullptr; ctx->cdf = nullptr;
+    cudaFree(ctx->part_a); cudaFree(ctx->tile_sum); cudaFree(ctx->tile_sq); cudaFree(ctx->tile_prefix);
+    cudaFree(ctx->scratch_a); cudaFree(ctx->scratch_b); cudaFree(ctx->tile_sin); cudaFree(ctx->sb);
+    cudaFree(ctx->cent_part); cudaFree(ctx->best_w); cudaFree(ctx->best_idx);
+    cudaFree(ctx->desc); cudaFree(ctx->tile_bofs); cudaFree(ctx->tile_pre);
+    ctx->part_a = nullptr; ctx->tile_sum = ctx->tile_sq = ctx->tile_prefix = ctx->scratch_a = ctx->scratch_b = nullptr;
+    ctx->tile_sin = ctx->sb = ctx->cent_part = ctx->best_w = nullptr; ctx->best_idx = nullptr;
+    ctx->desc = nullptr; ctx->tile_bofs = nullptr; ctx->tile_pre = nullptr;
+    ctx->cap = 0; ctx->tile_cap = 0;
+}
+
+static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
+    if (n == 0) return ESLAM_ERR_EMPTY;
+    if (n > 0xFFFFFFFFull) { ctx->error = "more than 2^32 particles per shard"; return ESLAM_ERR_INVALID; }
+    if (n > ctx->cap) {
+        free_particles(ctx);
+        for (int b = 0; b < 2; ++b) {
+            for (int f = 0; f < 7; ++f) CK(dalloc(&ctx->st.f[b][f], n));
+            for (int f = 0; f < 2; ++f) CK(dalloc(&ctx->st.b[b][f], n));
+        }
+        CK(dalloc(&ctx->ancestors, n)); CK(dalloc(&ctx->cdf, n));
+        const unsigned t = (unsigned)((n + TILE - 1) / TILE);
+        CK(dalloc(&ctx->part_a, t)); CK(dalloc(&ctx->tile_sum, t)); CK(dalloc(&ctx->tile_sq, t));
+        CK(dalloc(&ctx->tile_prefix, t)); CK(dalloc(&ctx->scratch_a, t)); CK(dalloc(&ctx->scratch_b, t));
+        CK(dalloc(&ctx->tile_sin, t)); CK(dalloc(&ctx->sb, (size_t)MAX_BND_TOTAL)); CK(dalloc(&ctx->cent_part, 5 * (size_t)t));
+        CK(dalloc(&ctx->best_w, t)); CK(dalloc(&ctx->best_idx, t));
+        CK(dalloc(&ctx->desc, t)); CK(dalloc(&ctx->tile_bofs, t)); CK(dalloc(&ctx->tile_pre, t));
+        ctx->cap = n; ctx->tile_cap = t;
+    }
+    ctx->n = n; ctx->n_tiles = (unsigned)((n + TILE - 1) / TILE);
+    return ESLAM_OK;
+}
+
+static inline uint64_t global_count(const eslam_gpu_ctx* ctx) {
+    return ctx->shard.world > 1 ? ctx->shard.global_count : ctx->n;
+}
+static inline uint64_t base_index(const eslam_gpu_ctx* ctx) {
+    return ctx->shard.world > 1 ? (uint64_t)ctx->shard.rank * ctx->n : 0;
+}
+static inline double scan_eps(const eslam_gpu_ctx* ctx) {
+    // |sequential fp64 running sum - approximate parallel prefix| <= N 2^-53 (relative); 8x margin, floor 2^-40
+    const double e = ldexp((double)global_count(ctx), -50);
+    return e > ldexp(1.0, -40) ? e : ldexp(1.0, -40);
+}
+
+static ModelParams model_params(const eslam_gpu_ctx* ctx) {
+    const eslam_gpu_config& c = ctx->cfg;
+    ModelParams m;
+    m.k0 = (uint32_t)c.seed; m.k1 = (uint32_t)(c.seed >> 32);
+    m.slip_factor = c.slip_factor; m.max_yaw_dev = c.max_yaw_deviation; m.spread_thr = c.spread_threshold;
+    m.spread_tf = c.spread_translation_factor; m.spread_rf = c.spread_rotation_factor;
+    m.merr2 = c.measurement_error * c.measurement_error;
+    m.inv_corr = 1.0 / c.contact_likelihood_correction;
+    m.discount = c.discount_factor;
+    m.min_contacts = c.min_contacts; m.use_shape = c.use_shape_update; m.use_hash = c.use_hash;
+    return m;
+}
+
+// ContactModel::setContactPoints bookkeeping (src/ContactModel.cpp:21-41 + the group logic of :136,153-154,194-197)
+static int build_contact_set(eslam_gpu_ctx* ctx, const eslam_gpu_contact* pts, int n, ContactSet* cs) {
+    if (!pts || n < 0 || n > ESLAM_MAX_CONTACTS) { ctx->error = "contact point count out of range"; return ESLAM_ERR_INVALID; }
+    memset(cs, 0, sizeof(*cs));
+    cs->n = n;
+    const double contact_threshold = 0.2;                                 // src/ContactModel.cpp:136
+    for (int i = 0; i < n; ++i) {
+        cs->px[i] = pts[i].position[0]; cs->py[i] = pts[i].position[1];
+        cs->pzr[i] = pts[i].position[2] - ctx->cfg.contact_point_radius;  // :147
+        const float contactProbability = pts[i].contact;                  // :153
+        unsigned f = 0;
+        if (!(contactProbability < contact_threshold)) f |= 1u;           // :154 (NaN passes)
+        const int gid = pts[i].group_id;
+        if (gid == -1 || i + 1 == n || gid != pts[i + 1].group_id) f |= 2u;   // :195-197
+        cs->flags[i] = (uint8_t)f;
+    }
+    return ESLAM_OK;
+}
+
+static size_t weight_smem_bytes(const eslam_gpu_ctx* ctx) {
+    return HTAB_BYTES + 1024 + 256 + (size_t)ctx->map.tile_w * ctx->map.tile_h * sizeof(float2);
+}
+
+extern "C" {
+
+void eslam_gpu_default_config(eslam_gpu_config* c) {
+    if (!c) return;
+    memset(c, 0, sizeof(*c));
+    c->seed = 42u; c->min_effective = 50;                                 // src/Configuration.hpp:86-88
+    c->measurement_error = 0.1; c->discount_factor = 0.9; c->spread_threshold = 0.9;
+    c->spread_translation_factor = 0.1; c->spread_rotation_factor = 0.05; c->slip_factor = 0.05;
+    c->max_yaw_deviation = 15 * M_PI / 180.0;
+    c->min_contacts = 3; c->contact_likelihood_correction = 0.33; c->contact_point_radius = 0.01;   // :55-59
+    c->use_slip_update = 0; c->use_shape_update = 1; c->use_hash = 0;
+    c->resample_mode = ESLAM_RESAMPLE_STRATIFIED; c->patch_size = 0;
+}
+
+int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_shard* shard, const eslam_gpu_comm* comm,
+                     eslam_gpu_ctx** out) {
+    if (!cfg || !out) return ESLAM_ERR_INVALID;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ESLAM_ERR_CUDA;
+    eslam_gpu_ctx* ctx = new eslam_gpu_ctx();
+    ctx->cfg = *cfg;
+    ctx->shard.rank = 0; ctx->shard.world = 1; ctx->shard.global_count = 0;
+    if (shard) ctx->shard = *shard;
+    ctx->has_comm = comm != nullptr;
+    if (comm) ctx->comm = *comm;
+    ctx->device = device; ctx->launches = 0; ctx->n = ctx->cap = 0; ctx->n_tiles = ctx->tile_cap = 0;
+    memset(&ctx->st, 0, sizeof(ctx->st));
+    ctx->ancestors = nullptr; ctx->cdf = nullptr; ctx->part_a = nullptr;
+    ctx->tile_sum = ctx->tile_sq = ctx->tile_prefix = ctx->scratch_a = ctx->scratch_b = ctx->tile_sin = ctx->sb = nullptr;
+    ctx->cent_part = ctx->best_w = nullptr; ctx->best_idx = nullptr; ctx->desc = nullptr; ctx->tile_bofs = nullptr;
+    ctx->tile_pre = nullptr; ctx->cells = nullptr; ctx->has_map = false; ctx->project_step = 0;
+    memset(&ctx->map, 0, sizeof(ctx->map));
+    *out = ctx;
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CK(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CK(dalloc(&ctx->sc, 1));
+    CK(cudaMemsetAsync(ctx->sc, 0, sizeof(DevScalars), ctx->stream));
+    CK(cudaMallocHost((void**)&ctx->sc_host, sizeof(DevScalars)));
+    CK(dalloc(&ctx->htab, (size_t)ESLAM_H_NINT * 3));
+    CK(cudaMemcpyAsync(ctx->htab, H_TABLE_HOST, sizeof(H_TABLE_HOST), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainSmem)));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ESLAM_OK;
+}
+
+void eslam_gpu_destroy(eslam_gpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_particles(ctx);
+    cudaFree(ctx->sc); cudaFreeHost(ctx->sc_host); cudaFree(ctx->htab); cudaFree(ctx->cells);
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* eslam_gpu_last_error(const eslam_gpu_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+uint64_t eslam_gpu_launch_count(const eslam_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t eslam_gpu_particle_count(const eslam_gpu_ctx* ctx) { return ctx ? ctx->n : 0; }
+
+int eslam_gpu_synchronize(eslam_gpu_ctx* ctx) {
+    if (!ctx) return ESLAM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ESLAM_OK;
+}
+
+int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int height, double sx, double sy, double ox,
+                       double oy, const double* g2l) {
+    if (!ctx || !cells || width <= 0 || height <= 0 || !(sx > 0) || !(sy > 0)) return ESLAM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->cells); ctx->cells = nullptr;
+    const size_t count = (size_t)width * height;
+    CK(dalloc(&ctx->cells, count));
+    CK(cudaMemcpyAsync(ctx->cells, cells, count * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    MapParams& m = ctx->map;
+    m.cells = ctx->cells; m.W = width; m.H = height; m.sx = sx; m.sy = sy; m.ox = ox; m.oy = oy;
+    m.inv_sx = 1.0 / sx; m.inv_sy = 1.0 / sy;
+    m.identity = g2l == nullptr;
+    for (int i = 0; i < 8; ++i) m.g2l[i] = g2l ? g2l[i] : (i == 0 || i == 5 ? 1.0 : 0.0);
+    // shared-memory map tile: as many cells as fit next to the h-table
+    const size_t avail = (size_t)ctx->max_smem_optin - (HTAB_BYTES + 1024 + 256);
+    int side = (int)floor(sqrt((double)(avail / sizeof(float2))));
+    m.tile_w = width < side ? width : side;
+    m.tile_h = (int)((avail / sizeof(float2)) / (size_t)m.tile_w);
+    if (m.tile_h > height) m.tile_h = height;
+    const int bytes = (int)weight_smem_bytes(ctx);
+    CK(cudaFuncSetAttribute(k_project_weight<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_project_weight<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->has_map = true;
+    return ESLAM_OK;
+}
+
+int eslam_gpu_init_gaussian(eslam_gpu_ctx* ctx, uint64_t n, const double mu[3], const double sigma[3], double zpos,
+                            double zsigma) {
+    if (!ctx || !mu || !sigma) return ESLAM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int st = ensure_capacity(ctx, n);
+    if (st != ESLAM_OK) return st;
+    DevScalars init; memset(&init, 0, sizeof(init));
+    init.tile_cx = mu[0]; init.tile_cy = mu[1];
+    *ctx->sc_host = init;
+    CK(cudaMemcpyAsync(ctx->sc, ctx->sc_host, sizeof(DevScalars), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->project_step = 0;
+    const ModelParams mp = model_params(ctx);
+    k_init_gaussian<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->st, ctx->sc, n, base_index(ctx), mp.k0, mp.k1,
+                                                                         mu[0], mu[1], mu[2], sigma[0], sigma[1], sigma[2],
+                                                                         zpos, zsigma);
+    LAUNCHED();
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ESLAM_OK;
+}
+
+static int read_scalars(eslam_gpu_ctx* ctx) {
+    CK(cudaMemcpyAsync(ctx->sc_host, ctx->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ESLAM_OK;
+}
+
+int eslam_gpu_set_particles(eslam_gpu_ctx* ctx, uint64_t n, const double* x, const double* y, const double* theta,
+                            const double* zpos, const double* zsigma, const double* weight) {
+    if (!ctx) return ESLAM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const bool fresh = n != ctx->n;
+    int st = ensure_capacity(ctx, n);
+    if (st != ESLAM_OK) return st;
+    st = read_scalars(ctx);
+    if (st != ESLAM_OK) return st;
+    const int cur = ctx->sc_host->cur;
+    if (fresh) {
+        for (int f = 0; f < 7; ++f) CK(cudaMemsetAsync(ctx->st.f[cur][f], 0, n * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(ctx->st.b[cur][B_FLOAT], 1, n, ctx->stream));
+        CK(cudaMemsetAsync(ctx->st.b[cur][B_NF], 0, n, ctx->stream));
+    }
+    const double* src[6] = {x, y, theta, zpos, zsigma, weight};
+    for (int f = 0; f < 6; ++f)
+        if (src[f]) CK(cudaMemcpyAsync(ctx->st.f[cur][f], src[f], n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ESLAM_OK;
+}
+
+int eslam_gpu_get_particles(eslam_gpu_ctx* ctx, double* x, double* y, double* theta, double* zpos, double* zsigma,
+                            double* weight, double* mprob, uint8_t* floating, uint8_t* n_found) {
+    if (!ctx) return ESLAM_ERR_INVALID;
+    if (ctx->n == 0) return ESLAM_ERR_EMPTY;
+    CK(cudaSetDevice(ctx->device));
+    int st = read_scalars(ctx);
+    if (st != ESLAM_OK) return st;
+    const int cur = ctx->sc_host->cur;
+    double* dst[7] = {x, y, theta, zpos, zsigma, weight, mprob};
+    for (int f = 0; f < 7; ++f)
+        if (dst[f]) CK(cudaMemcpyAsync(dst[f], ctx->st.f[cur][f], ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (floating) CK(cudaMemcpyAsync(floating, ctx->st.b[cur][B_FLOAT], ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_found) CK(cudaMemcpyAsync(n_found, ctx->st.b[cur][B_NF], ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ESLAM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- launch sequences
+static void fill_weight_params(eslam_gpu_ctx* ctx, WeightParams* P, const eslam_gpu_step* step, const ContactSet* cs) {
+    memset(P, 0, sizeof(*P));
+    P->st = ctx->st; P->sc = ctx->sc; P->part = ctx->part_a; P->map = ctx->map; P->mp = model_params(ctx);
+    P->htab = ctx->htab; P->n = ctx->n; P->base = base_index(ctx); P->project_step = ctx->project_step;
+    if (step) {
+        P->yaw = step->yaw; P->z_delta = step->z_delta; P->z_var = step->z_var;
+        for (int i = 0; i < 3; ++i) { P->dmean[i] = step->delta_mean[i]; P->dsigma[i] = step->delta_sigma[i]; }
+    }
+    if (cs) P->cs = *cs;
+}
+
+static unsigned weight_grid(const eslam_gpu_ctx* ctx) {
+    return ctx->n_tiles < (unsigned)ctx->sm_count ? ctx->n_tiles : (unsigned)ctx->sm_count;
+}
+
+// normalise + (optional) resample tail shared by update / normalize_weights / resample.
+// mode: 0 = do_resample := force, 1 = decide from ESS (update), 2 = ESS only
+static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int mode, int force) {
+    const unsigned T = ctx->n_tiles;
+    const uint64_t n = ctx->n, ng = global_count(ctx);
+    const double eps = scan_eps(ctx);
+    if (apply_loop_b) k_loop_b<true><<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->tile_sum);
+    else k_loop_b<false><<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->tile_sum);
+    LAUNCHED();
+    k_reduce_b<<<1, 1024, 0, ctx->stream>>>(ctx->tile_sum, T, n, ctx->sc, ctx->scratch_a, ctx->scratch_b, ctx->tile_prefix, normalise);
+    LAUNCHED();
+    k_norm_scan<<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ng, ctx->tile_prefix, ctx->tile_sq, ctx->desc, normalise, eps);
+    LAUNCHED();
+    const int decide = mode == 0 ? 0 : 1;
+    k_chain<<<1, 1024, sizeof(ChainSmem), ctx->stream>>>(ctx->desc, T, ctx->tile_sq, ctx->sc, ctx->scratch_a, ctx->scratch_b,
+                                                         ctx->tile_bofs, ctx->tile_pre, ctx->tile_sin, ctx->sb,
+                                                         mode == 2 ? 0ull : ctx->cfg.min_effective, decide, force);
+    LAUNCHED();
+    if (mode == 2) return ESLAM_OK;
+    k_cdf<<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->tile_prefix, ctx->tile_bofs, ctx->tile_sin, ctx->sb, ctx->cdf, eps);
+    LAUNCHED();
+    k_cdf_sequential<<<1, 1, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->cdf);
+    LAUNCHED();
+    const ModelParams mp = model_params(ctx);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    k_search<<<blocks, 256, 0, ctx->stream>>>(ctx->sc, ctx->cdf, n, ng, base_index(ctx), mp.k0, mp.k1,
+                                              ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC, ctx->ancestors);
+    LAUNCHED();
+    k_gather<<<blocks, 256, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->ancestors);
+    LAUNCHED();
+    k_after_resample<<<1, 1, 0, ctx->stream>>>(ctx->sc);
+    LAUNCHED();
+    return ESLAM_OK;
+}
+
+static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null, const ContactSet* cs,
+                         cudaEvent_t ev0, cudaEvent_t ev1) {
+    WeightParams P;
+    fill_weight_params(ctx, &P, step_or_null, cs);
+    const size_t smem = weight_smem_bytes(ctx);
+    if (ev0) CK(cudaEventRecord(ev0, ctx->stream));
+    if (step_or_null) { k_project_weight<true, true><<<weight_grid(ctx), WT_THREADS, smem, ctx->stream>>>(P); ctx->project_step++; }
+    else k_project_weight<false, true><<<weight_grid(ctx), WT_THREADS, smem, ctx->stream>>>(P);
+    LAUNCHED();
+    if (ev1) CK(cudaEventRecord(ev1, ctx->stream));
+    k_reduce_a<<<1, 1024, 0, ctx->stream>>>(ctx->part_a, ctx->n_tiles, ctx->n, ctx->sc, ctx->scratch_a, ctx->scratch_b,
+                                            ctx->cfg.discount_factor);
+    LAUNCHED();
+    return launch_tail(ctx, true, 1, 1, 0);
+}
+
+static int fetch_result(eslam_gpu_ctx* ctx, eslam_gpu_update_result* r) {
+    int st = read_scalars(ctx);
+    if (st != ESLAM_OK) return st;
+    const DevScalars& s = *ctx->sc_host;
+    r->ess = s.ess; r->max_weight = s.max_weight; r->floating_weight = s.floating_weight; r->weights_sum = s.sum_w;
+    r->data_particles = s.data_particles; r->total_points = s.total_points; r->resampled = s.do_resample;
+    r->status = ESLAM_OK;
+    if (s.error_flags & ERR_ZERO_VARIANCE_BIT) {
+        r->status = ESLAM_ERR_ZERO_VARIANCE;
+        ctx->error = "using a zero measurement variance leads to singularities";
+        CK(cudaMemsetAsync(&ctx->sc->error_flags, 0, sizeof(int), ctx->stream));
+    }
+    return r->status;
+}
+
+static int check_ready(eslam_gpu_ctx* ctx, bool need_map) {
+    if (!ctx) return ESLAM_ERR_INVALID;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return ESLAM_ERR_CUDA;
+    if (ctx->n == 0) { ctx->error = "empty particle set"; return ESLAM_ERR_EMPTY; }
+    if (need_map && !ctx->has_map) { ctx->error = "No environment attached."; return ESLAM_ERR_NO_ENVIRONMENT; }
+    return ESLAM_OK;
+}
+
+int eslam_gpu_project(eslam_gpu_ctx* ctx, const eslam_gpu_step* step) {
+    int st = check_ready(ctx, false);
+    if (st != ESLAM_OK) return st;
+    if (!step) return ESLAM_ERR_INVALID;
+    WeightParams P;
+    fill_weight_params(ctx, &P, step, nullptr);
+    k_project_weight<true, false><<<weight_grid(ctx), WT_THREADS, 0, ctx->stream>>>(P);
+    ctx->project_step++;
+    LAUNCHED();
+    return ESLAM_OK;
+}
+
+int eslam_gpu_update(eslam_gpu_ctx* ctx, const eslam_gpu_contact* pts, int n_pts, eslam_gpu_update_result* result) {
+    int st = check_ready(ctx, true);
+    if (st != ESLAM_OK) return st;
+    ContactSet cs;
+    st = build_contact_set(ctx, pts, n_pts, &cs);
+    if (st != ESLAM_OK) return st;
+    st = launch_update(ctx, nullptr, &cs, nullptr, nullptr);
+    if (st != ESLAM_OK) return st;
+    return result ? fetch_result(ctx, result) : ESLAM_OK;
+}
+
+int eslam_gpu_step_fused(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const eslam_gpu_contact* pts, int n_pts,
+                         eslam_gpu_update_result* result) {
+    int st = check_ready(ctx, true);
+    if (st != ESLAM_OK) return st;
+    if (!step) return ESLAM_ERR_INVALID;
+    ContactSet cs;
+    st = build_contact_set(ctx, pts, n_pts, &cs);
+    if (st != ESLAM_OK) return st;
+    st = launch_update(ctx, step, &cs, nullptr, nullptr);
+    if (st != ESLAM_OK) return st;
+    return result ? fetch_result(ctx, result) : ESLAM_OK;
+}
+
+int eslam_gpu_run_steps(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const eslam_gpu_contact* pts, int n_pts, int steps,
+                        float* elapsed_ms, float* top_kernel_ms, eslam_gpu_update_result* last_result) {
+    int st = check_ready(ctx, true);
+    if (st != ESLAM_OK) return st;
+    if (!step || steps <= 0) return ESLAM_ERR_INVALID;
+    ContactSet cs;
+    st = build_contact_set(ctx, pts, n_pts, &cs);
+    if (st != ESLAM_OK) return st;
+    const size_t need = 2 + 2 * (size_t)steps;
+    while (ctx->events.size() < need) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->events.push_back(e); }
+    CK(cudaEventRecord(ctx->events[0], ctx->stream));
+    for (int s = 0; s < steps; ++s) {
+        st = launch_update(ctx, step, &cs, ctx->events[2 + 2 * s], ctx->events[3 + 2 * s]);
+        if (st != ESLAM_OK) return st;
+    }
+    CK(cudaEventRecord(ctx->events[1], ctx->stream));
+    CK(cudaEventSynchronize(ctx->events[1]));
+    if (elapsed_ms) CK(cudaEventElapsedTime(elapsed_ms, ctx->events[0], ctx->events[1]));
+    if (top_kernel_ms) {
+        float tot = 0;
+        for (int s = 0; s < steps; ++s) { float t = 0; CK(cudaEventElapsedTime(&t, ctx->events[2 + 2 * s], ctx->events[3 + 2 * s])); tot += t; }
+        *top_kernel_ms = tot;
+    }
+    return last_result ? fetch_result(ctx, last_result) : ESLAM_OK;
+}
+
+int eslam_gpu_normalize_weights(eslam_gpu_ctx* ctx, double* ess) {
+    int st = check_ready(ctx, false);
+    if (st != ESLAM_OK) return st;
+    st = launch_tail(ctx, false, 1, 2, 0);
+    if (st != ESLAM_OK) return st;
+    if (ess) { st = read_scalars(ctx); if (st != ESLAM_OK) return st; *ess = ctx->sc_host->ess; }
+    return ESLAM_OK;
+}
+
+int eslam_gpu_resample(eslam_gpu_ctx* ctx) {
+    int st = check_ready(ctx, false);
+    if (st != ESLAM_OK) return st;
+    return launch_tail(ctx, false, 0, 0, 1);
+}
+
+int eslam_gpu_get_ancestors(eslam_gpu_ctx* ctx, uint32_t* a) {
+    int st = check_ready(ctx, false);
+    if (st != ESLAM_OK) return st;
+    if (!a) return ESLAM_ERR_INVALID;
+    CK(cudaMemcpyAsync(a, ctx->ancestors, ctx->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ESLAM_OK;
+}
+
+int eslam_gpu_get_cdf(eslam_gpu_ctx* ctx, double* c) {
+    int st = check_ready(ctx, false);
+    if (st != ESLAM_OK) return st;
+    if (!c) return ESLAM_ERR_INVALID;
+    CK(cudaMemcpyAsync(c, ctx->cdf, ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ESLAM_OK;
+}
+
+static int launch_centroid(eslam_gpu_ctx* ctx) {
+    k_centroid_tiles<<<ctx->n_tiles, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->n, ctx->cent_part, ctx->n_tiles,
+                                                            ctx->best_idx, ctx->best_w);
+    LAUNCHED();
+    k_centroid_final<<<1, 1024, 0, ctx->stream>>>(ctx->cent_part, ctx->n_tiles, ctx->scratch_b, ctx->best_idx, ctx->best_w, ctx->sc);
+    LAUNCHED();
+    return read_scalars(ctx);
+}
+
+int eslam_gpu_centroid(eslam_gpu_ctx* ctx, double out[4]) {
+    int st = check_ready(ctx, false);
+    if (st != ESLAM_OK) return st;
+    if (!out) return ESLAM_ERR_INVALID;
+    st = launch_tail(ctx, false, 1, 2, 0);                        // normalizeWeights(), src/PoseEstimator.cpp:356
+    if (st != ESLAM_OK) return st;
+    st = launch_centroid(ctx);
+    if (st != ESLAM_OK) return st;
+    const double* c = ctx->sc_host->centroid;
+    for (int i = 0; i < 4; ++i) out[i] = c[i] / c[4];             // :373-375
+    return ESLAM_OK;
+}
+
+int eslam_gpu_best_index(eslam_gpu_ctx* ctx, uint64_t* index) {
+    int st = check_ready(ctx, false);
+    if (st != ESLAM_OK) return st;
+    if (!index) return ESLAM_ERR_INVALID;
+    st = launch_centroid(ctx);
+    if (st != ESLAM_OK) return st;
+    *index = ctx->sc_host->best_index;
+    return ESLAM_OK;
+}
+
+int eslam_gpu_evaluate_poses(eslam_gpu_ctx* ctx, uint64_t n, const double* x, const double* y, const double* theta,
+                             const double* zpos, const double* meas_var, const double* z_var_in,
+                             const eslam_gpu_contact* pts, int n_pts,
+                             uint8_t* ok, double* weight, double* z_delta, double* z_var, double* pose_var,
+                             int32_t* n_contacts, double* zpos_out, double* z_var_out, int32_t* cell_index, double* cp) {
+    if (!ctx || n == 0 || !x || !y || !theta || !zpos || !meas_var) return ESLAM_ERR_INVALID;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return ESLAM_ERR_CUDA;
+    if (!ctx->has_map) { ctx->error = "No environment attached."; return ESLAM_ERR_NO_ENVIRONMENT; }
+    EvalParams P; memset(&P, 0, sizeof(P));
+    int st = build_contact_set(ctx, pts, n_pts, &P.cs);
+    if (st != ESLAM_OK) return st;
+    const size_t nd = n * sizeof(double);
+    double* din = nullptr; double* dout = nullptr; int32_t* dint = nullptr; uint8_t* dok = nullptr; int* derr = nullptr;
+    const size_t cpn = n * ESLAM_MAX_CP * 5, celln = n * (size_t)(n_pts > 0 ? n_pts : 1);
+    CK(dalloc(&din, 6 * n)); CK(dalloc(&dout, 6 * n + cpn)); CK(dalloc(&dint, n + celln)); CK(dalloc(&dok, n)); CK(dalloc(&derr, 1));
+    const double* src[6] = {x, y, theta, zpos, meas_var, z_var_in};
+    for (int i = 0; i < 6; ++i)
+        if (src[i]) CK(cudaMemcpyAsync(din + i * n, src[i], nd, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(derr, 0, sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(dout, 0, (6 * n + cpn) * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(dint, 0xFF, (n + celln) * sizeof(int32_t), ctx->stream));
+    CK(cudaMemsetAsync(dok, 0, n, ctx->stream));
+    P.n = n; P.x = din; P.y = din + n; P.th = din + 2 * n; P.z = din + 3 * n; P.mv = din + 4 * n;
+    P.zvin = z_var_in ? din + 5 * n : nullptr;
+    P.map = ctx->map; P.map.tile_w = 0; P.map.tile_h = 0; P.htab = ctx->htab;
+    const ModelParams mp = model_params(ctx);
+    P.inv_corr = mp.inv_corr; P.min_contacts = mp.min_contacts; P.use_shape = mp.use_shape;
+    P.ok = dok; P.weight = dout; P.zdelta = dout + n; P.zvar = dout + 2 * n; P.posevar = dout + 3 * n;
+    P.zout = dout + 4 * n; P.zvout = dout + 5 * n; P.cp = dout + 6 * n; P.ncont = dint; P.cells = dint + n; P.err = derr;
+    k_evaluate_poses<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(P);
+    LAUNCHED();
+    int herr = 0;
+    CK(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    double* dst[6] = {weight, z_delta, z_var, pose_var, zpos_out, z_var_out};
+    for (int i = 0; i < 6; ++i)
+        if (dst[i]) CK(cudaMemcpyAsync(dst[i], dout + i * n, nd, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cp) CK(cudaMemcpyAsync(cp, dout + 6 * n, cpn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ok) CK(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_contacts) CK(cudaMemcpyAsync(n_contacts, dint, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (cell_index && n_pts > 0) CK(cudaMemcpyAsync(cell_index, dint + n, celln * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(din); cudaFree(dout); cudaFree(dint); cudaFree(dok); cudaFree(derr);
+    if (herr & ERR_ZERO_VARIANCE_BIT) {
+        ctx->error = "using a zero measurement variance leads to singularities";
+        return ESLAM_ERR_ZERO_VARIANCE;
+    }
+    return ESLAM_OK;
+}
+
+int eslam_gpu_patch_update(eslam_gpu_ctx* ctx) {
+    if (!ctx) return ESLAM_ERR_INVALID;
+    ctx->error = "per-particle map patches are not enabled in this context (patch_size == 0)";
+    return ESLAM_ERR_INVALID;
+}
+
+int eslam_gpu_get_patches(eslam_gpu_ctx* ctx, float*, int32_t*) {
+    if (!ctx) return ESLAM_ERR_INVALID;
+    ctx->error = "per-particle map patches are not enabled in this context (patch_size == 0)";
+    return ESLAM_ERR_INVALID;
+}
+
+}  // extern "C"

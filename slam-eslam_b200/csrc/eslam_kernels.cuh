@@ -1,0 +1,978 @@
+// eslam_kernels.cuh -- sm_100a kernels of the eSLAM particle-filter update path.
+//
+// Reference functions replaced (paths relative to liyangSKD/slam-eslam):
+//   k_init_gaussian      PoseEstimator::init                      src/PoseEstimator.cpp:88-102
+//   k_project_weight     PoseEstimator::project                   src/PoseEstimator.cpp:184-242
+//                        + updateWeights loop A                   src/PoseEstimator.cpp:276-327
+//                        + ContactModel::evaluatePose/evaluateWeight/updateZPositionEstimate
+//                                                                 src/ContactModel.cpp:117-224,262-340
+//                        + GridAccess::get                        src/PoseEstimator.hpp:97-105
+//   k_reduce_a           floating_weight, max_weight              src/PoseEstimator.cpp:329,347-348
+//   k_loop_b             updateWeights loop B                     src/PoseEstimator.cpp:332-345
+//   k_reduce_b,k_norm_scan,k_chain   ParticleFilter::normalizeWeights  src/ParticleFilter.hpp:46-70
+//   k_norm_scan,k_chain,k_cdf        running sum of resample_stratified src/ParticleFilter.hpp:95,102
+//   k_search             the stratified walk                      src/ParticleFilter.hpp:96-105
+//   k_gather             xi_kp.push_back(xi_k[idx]); swap         src/ParticleFilter.hpp:104-107
+//   k_centroid,k_best    getCentroid / getBestParticleIndex       src/PoseEstimator.cpp:354-383, src/ParticleFilter.hpp:160-173
+//
+// Arithmetic is that of eslam_math.h (compile with -fmad=false); all global sums are pairwise over the
+// index-aligned binary tree, so results do not depend on grid size, SM count or number of GPUs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "eslam_math.h"
+#include "../../include/eslam_gpu.h"
+
+namespace em = eslam_math;
+
+#define TILE 1024                // particles per reduction tile (fixed: defines the summation tree)
+#define WT_THREADS 512           // threads of the fused project+weight kernel (2 particles each per tile)
+#define MAX_BND_PER_TILE 8       // boundary elements a tile descriptor can hold
+#define MAX_BND_TOTAL 2048       // boundary elements the chain kernel can walk
+#define BIN_NONE (-100000)       // "no binade": piece made of zero / sub-quarter-ulp weights only
+#define ERR_ZERO_VARIANCE_BIT 1
+#define ERR_CDF_FALLBACK_BIT 2
+
+struct StateBufs {               // SoA particle state, double buffered (src/PoseParticle.hpp:52-86 hot fields)
+    double* f[2][7];             // x, y, theta, zPos, zSigma, weight, mprob
+    uint8_t* b[2][2];            // floating, n_found (= cpoints.size())
+};
+enum { F_X = 0, F_Y, F_TH, F_Z, F_ZS, F_W, F_MP };
+enum { B_FLOAT = 0, B_NF };
+
+struct DevScalars {              // device-resident scalars of one context
+    double max_weight;           // PoseEstimator::max_weight, carried to the next project (Q10)
+    double floating_weight;
+    double sum_w;                // getWeightsSum()
+    double ess;
+    double pow_table[6];         // pow(discount*floating_weight, 4 - n), n = 0..4, [5] = wrapped exponent (Q2)
+    double tile_cx, tile_cy;     // world position the shared-memory map tile is centred on
+    double centroid[5];          // sum x w, y w, theta w, z w, w
+    unsigned long long data_particles, total_points;
+    unsigned long long best_index;
+    unsigned int resample_step;
+    int cur;                     // which state buffer is current
+    int do_resample;
+    int uniform;                 // sum of weights <= 0 -> 1/N (Q8)
+    int error_flags;
+    int n_boundaries;
+};
+
+struct TilePartA {               // per-tile partials of loop A
+    double sum_pw, max_w, sum_x, sum_y;
+    unsigned int cnt, pts;
+};
+
+struct ContactSet {              // odometry::BodyContactState after setContactPoints, as kernel parameters
+    int n;
+    int pad;
+    double px[ESLAM_MAX_CONTACTS], py[ESLAM_MAX_CONTACTS], pzr[ESLAM_MAX_CONTACTS];   // pzr = z - contactPointRadius
+    uint8_t flags[ESLAM_MAX_CONTACTS];   // bit0: passes !(contact < 0.2); bit1: last point of its group
+};
+
+struct MapParams {
+    const float2* cells; int W, H;
+    double sx, sy, ox, oy, inv_sx, inv_sy;
+    double g2l[8];               // rows 0 and 1 of C_global2local
+    int identity;
+    int tile_w, tile_h;          // shared-memory tile (cells)
+};
+
+struct ModelParams {             // eslam::Configuration hot fields
+    uint32_t k0, k1;
+    double slip_factor, max_yaw_dev, spread_thr, spread_tf, spread_rf;
+    double merr2, inv_corr, discount;
+    unsigned long long min_contacts;
+    int use_shape, use_hash;
+};
+
+struct WeightParams {
+    StateBufs st; DevScalars* sc; TilePartA* part;
+    MapParams map; ModelParams mp;
+    const em::dbl2* htab;
+    unsigned long long n, base;  // local particle count, global index of local particle 0
+    uint32_t project_step;
+    double yaw, z_delta, z_var, dmean[3], dsigma[3];
+    ContactSet cs;
+};
+
+struct TileDesc {                // what a tile contributes to the exact running sum (see DESIGN.md "exact CDF")
+    int n_bnd, overflow;
+    int head_b, pad;
+    long long head_d0, head_d1;  // rounding function of the elements before the tile's first boundary element
+    struct { double w; int idx, b; long long d0, d1; } bnd[MAX_BND_PER_TILE];
+};
+
+struct SegF { long long d0, d1; int b; int pad; };   // 2-state rounding function of a run of interior elements
+
+// ------------------------------------------------------------------------------------------------ small helpers
+__device__ __forceinline__ uint32_t stream_word(uint32_t stream, unsigned long long idx) {
+    return stream ^ ((uint32_t)(idx >> 32) << 8);
+}
+
+__device__ __forceinline__ double warp_tree_sum(double v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;   // xor butterfly = balanced binary tree over lane order; every lane holds the total
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Tree sum over the 1024 leaves of a tile held one per thread (blockDim.x == 1024). red: >= 32 doubles.
+__device__ __forceinline__ double tile_tree_sum_1024(double v, double* red) {
+    v = warp_tree_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = red[threadIdx.x & 31];
+    return warp_tree_sum(t);
+}
+
+// Pairwise tree over n values in global memory, continuing the per-tile trees; one CTA; a/b ping-pong.
+__device__ double block_tree_reduce(double* a, double* b, unsigned n) {
+    while (n > 1) {
+        unsigned h = (n + 1) >> 1;
+        for (unsigned i = threadIdx.x; i < h; i += blockDim.x)
+            b[i] = (2 * i + 1 < n) ? a[2 * i] + a[2 * i + 1] : a[2 * i];
+        __syncthreads();
+        double* t = a; a = b; b = t; n = h;
+    }
+    return n ? a[0] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------ map lookup
+struct MapTile { const float2* s; int x0, y0, w, h; };
+
+#define IDX_FRAC_BITS 18
+__device__ __forceinline__ bool axis_index(double g, double off, double scale, double inv, int n, int& idx) {
+    // floor((g - off)/scale) without the division: multiply by the reciprocal, take the floor from the low mantissa
+    // bits after adding 1.5*2^34 (18 fractional bits), and only when that fixed-point value is an exact integer
+    // (the quotient is within 2^-19 of a cell border) fall back to the exact IEEE division of eslam_math.h.
+    const double q = g - off;
+    const double m = q * inv + 25769803776.0;            // 1.5 * 2^34
+    const uint64_t u = em::d2u(m);
+    const int k = (int)(uint32_t)u;
+    const uint32_t hi = (uint32_t)(u >> 32);
+    if (((hi - 0x4217FFFFu) <= 1u) && ((k & ((1 << IDX_FRAC_BITS) - 1)) != 0)) {
+        idx = k >> IDX_FRAC_BITS;
+        return (unsigned)idx < (unsigned)n;
+    }
+    return em::cell_index_exact(g, off, scale, n, idx);
+}
+
+__device__ __forceinline__ bool cell_lookup(const MapParams& M, const MapTile& mt, double wx, double wy, double wz,
+                                            float2& cell, int& flat) {
+    double gx = wx, gy = wy;
+    if (!M.identity) {
+        gx = em::fma_(M.g2l[0], wx, em::fma_(M.g2l[1], wy, em::fma_(M.g2l[2], wz, M.g2l[3])));
+        gy = em::fma_(M.g2l[4], wx, em::fma_(M.g2l[5], wy, em::fma_(M.g2l[6], wz, M.g2l[7])));
+    }
+    int ix, iy;
+    if (!axis_index(gx, M.ox, M.sx, M.inv_sx, M.W, ix)) return false;
+    if (!axis_index(gy, M.oy, M.sy, M.inv_sy, M.H, iy)) return false;
+    flat = iy * M.W + ix;
+    const unsigned lx = (unsigned)(ix - mt.x0), ly = (unsigned)(iy - mt.y0);
+    if (lx < (unsigned)mt.w && ly < (unsigned)mt.h) cell = mt.s[ly * mt.w + lx];
+    else cell = __ldg(&M.cells[flat]);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ contact model
+struct PoseEval { int n_found; double d1, d2, A, poseVar; };
+
+// ContactModel::evaluatePose (src/ContactModel.cpp:117-224) for one pose; SHARED arithmetic policy.
+template <bool TAP>
+__device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapParams& M, const MapTile& mt,
+                                             const em::dbl2* htab, double inv_corr,
+                                             double x, double y, double z, double s, double c, double mv,
+                                             PoseEval& out, int32_t* tap_cells, double* tap_cp) {
+    bool valid = false, group_valid = true;
+    double acc_d = 0, acc_v = 0, acc_r = 0, acc_p = 0;
+    double pt_x = 0, pt_y = 0, pt_z = 0;
+    out.n_found = 0; out.d1 = 0; out.d2 = 0; out.A = 0; out.poseVar = 0;
+    const int n = cs.n;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        const unsigned f = cs.flags[i];
+        if (TAP) tap_cells[i] = -1;
+        if ((f & 1u) && group_valid) {                                    // :154
+            const double px = cs.px[i], py = cs.py[i];
+            const double wx = em::fma_(c, px, em::fma_(-s, py, x));      // :147
+            const double wy = em::fma_(s, px, em::fma_(c, py, y));
+            const double wz = z + cs.pzr[i];
+            float2 cell; int flat = -1;
+            bool hit = cell_lookup(M, mt, wx, wy, wz, cell, flat);       // :156
+            if (TAP) tap_cells[i] = flat;
+            if (hit) {
+                hit = false;
+                if (cell.x == cell.x) {                                  // NaN mean = empty cell
+                    const double d = wz - (double)cell.x;                // :160
+                    const double sp2 = (double)cell.y * (double)cell.y;  // :166
+                    const double zvar = sp2 + mv;                        // :167
+                    if (d * d < 9.0 * zvar) {                            // 3-sigma patch gate of MLSMap::getPatch
+                        hit = true;
+                        const double ratio = em::likelihood_ratio(d, zvar, inv_corr, htab);   // :170
+                        if (!valid) {                                    // :172-177
+                            acc_d = d * ratio; acc_v = zvar * ratio; acc_r = ratio; acc_p = sp2 * ratio;
+                            if (TAP) { pt_x = wx; pt_y = wy; pt_z = (double)cell.x; }
+                        } else {                                         // :178-184
+                            acc_d = em::fma_(d, ratio, acc_d); acc_v = em::fma_(zvar, ratio, acc_v);
+                            acc_r += ratio; acc_p = em::fma_(sp2, ratio, acc_p);
+                        }
+                        valid = true;
+                    }
+                }
+            }
+            if (!hit) group_valid = false;                               // :189-190
+        }
+        if (valid && (f & 2u)) {                                         // :194-197 end of group
+            if (group_valid && acc_r > 1e-9) {                           // :199
+                const double zd = acc_d / acc_r, zv = acc_v / acc_r;     // :201-202
+                out.poseVar += acc_p / acc_r;                            // :203
+                const double e = zd / zv;
+                out.d1 += e; out.d2 += 1.0 / zv; out.A = em::fma_(zd, e, out.A);
+                if (TAP && out.n_found < ESLAM_MAX_CP) {
+                    double* o = tap_cp + out.n_found * 5;
+                    o[0] = pt_x; o[1] = pt_y; o[2] = pt_z; o[3] = zd; o[4] = zv;
+                }
+                out.n_found++;
+            }
+            group_valid = true; valid = false;                           // :210-213 (only when valid: Q4)
+            acc_d = acc_v = acc_r = acc_p = 0;
+        }
+    }
+}
+
+// ContactModel::evaluateWeight (src/ContactModel.cpp:262-317), three-sum form
+__device__ __forceinline__ void evaluate_weight(const PoseEval& e, int use_shape, double& weight, double& z_delta,
+                                                double& z_var) {
+    const double delta = e.d1 / e.d2;
+    double pz = 1.0;
+    if (use_shape) {
+        double q = em::fma_(-e.d1, delta, e.A);
+        if (!(q > 0.0)) q = 0.0;
+        pz = em::exp_(-0.5 * q);
+    }
+    weight = pz; z_delta = -delta; z_var = 1.0 / e.d2;
+}
+
+// ContactModel::updateZPositionEstimate (src/ContactModel.cpp:319-340)
+__device__ __forceinline__ bool update_z(const PoseEval& e, double m_zDelta, double m_zVar, double& z_pos, double& z_var) {
+    const double pose_var = e.poseVar / (double)e.n_found;
+    double delta_var = z_var - pose_var;
+    if (delta_var < 1e-9) delta_var = 1e-9;                              // std::max(z_var - pose_var, 1e-9)
+    if (fabs(m_zDelta / em::sqrt_(delta_var)) > 1.0) return false;      // 1 sigma (Q6)
+    const double gain = z_var / (z_var + m_zVar);
+    z_pos += gain * m_zDelta;
+    const double var_gain = delta_var / (delta_var + m_zVar);
+    delta_var = (1.0 - var_gain) * delta_var;
+    z_var = pose_var + delta_var;
+    return true;
+}
+
+__device__ __forceinline__ double weighting_function(double x, double alpha, double beta, double gamma) {
+    if (x < alpha) return 1.0;                                           // src/PoseEstimator.cpp:114-128
+    if (x < beta) {
+        const double a = (1.0 - gamma) / (alpha - beta);
+        const double b = 1.0 - alpha * a;
+        return a * x + b;
+    }
+    if (x >= beta) return gamma;
+    return 0.0;
+}
+
+__device__ __forceinline__ void normal_pair(const em::Philox4& p, double& n0, double& n1) {
+    em::box_muller(em::u01_open(p.v[0], p.v[1]), em::u01_open(p.v[2], p.v[3]), n0, n1);
+}
+
+// ------------------------------------------------------------------------------------------------ init
+__global__ void k_init_gaussian(StateBufs st, DevScalars* sc, unsigned long long n, unsigned long long base,
+                                uint32_t k0, uint32_t k1, double mx, double my, double mt, double sgx, double sgy,
+                                double sgt, double zpos, double zsigma) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cur = sc->cur;
+    const unsigned long long gi = base + i;
+    const uint32_t sw = stream_word(em::STREAM_INIT, gi);
+    em::Philox4 a = em::philox4x32_10((uint32_t)gi, 0, 0, sw, k0, k1);
+    em::Philox4 b = em::philox4x32_10((uint32_t)gi, 0, 1, sw, k0, k1);
+    double nx, ny, nt, unused;
+    normal_pair(a, nx, ny);
+    normal_pair(b, nt, unused);
+    st.f[cur][F_X][i] = nx * sgx + mx;                                   // src/PoseEstimator.cpp:69-72
+    st.f[cur][F_Y][i] = ny * sgy + my;
+    st.f[cur][F_TH][i] = nt * sgt + mt;
+    st.f[cur][F_Z][i] = zpos; st.f[cur][F_ZS][i] = zsigma;
+    st.f[cur][F_W][i] = 0.0; st.f[cur][F_MP][i] = 0.0;                   // weight(0): src/PoseParticle.hpp:56 (Q9)
+    st.b[cur][B_FLOAT][i] = 1; st.b[cur][B_NF][i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ fused project + weight
+#define HTAB_BYTES (ESLAM_H_NINT * 3 * 16)
+
+template <bool DO_PROJECT, bool DO_WEIGHT>
+__global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_constant__ WeightParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    em::dbl2* htab = reinterpret_cast<em::dbl2*>(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw + HTAB_BYTES);             // 4 x 32 doubles
+    unsigned* redu = reinterpret_cast<unsigned*>(smem_raw + HTAB_BYTES + 1024); // 2 x 32 unsigned
+    float2* tile = reinterpret_cast<float2*>(smem_raw + HTAB_BYTES + 1024 + 256);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DevScalars* sc = P.sc;
+    const int cur = sc->cur;
+    MapTile mt; mt.s = tile; mt.w = 0; mt.h = 0; mt.x0 = 0; mt.y0 = 0;
+    if (DO_WEIGHT) {
+        for (int i = tid; i < ESLAM_H_NINT * 3; i += WT_THREADS) htab[i] = P.htab[i];
+        if (P.map.tile_w > 0) {
+            // stage the map tile around the particle cloud into shared memory
+            mt.w = P.map.tile_w; mt.h = P.map.tile_h;
+            double cx = (sc->tile_cx - P.map.ox) * P.map.inv_sx, cy = (sc->tile_cy - P.map.oy) * P.map.inv_sy;
+            if (!(cx > -1e9 && cx < 1e9)) cx = 0;
+            if (!(cy > -1e9 && cy < 1e9)) cy = 0;
+            int x0 = (int)cx - mt.w / 2, y0 = (int)cy - mt.h / 2;
+            x0 = max(0, min(x0, P.map.W - mt.w)); y0 = max(0, min(y0, P.map.H - mt.h));
+            mt.x0 = x0; mt.y0 = y0;
+            const int cells = mt.w * mt.h;
+            for (int i = tid; i < cells; i += WT_THREADS) {
+                const int r = i / mt.w, cc = i - r * mt.w;
+                tile[i] = __ldg(&P.map.cells[(size_t)(y0 + r) * P.map.W + x0 + cc]);
+            }
+        }
+        __syncthreads();
+    }
+    double spread = 0.0;
+    if (DO_PROJECT) spread = weighting_function(sc->max_weight, 0.0, P.mp.spread_thr, 0.0);   // :194
+
+    double* X = P.st.f[cur][F_X]; double* Y = P.st.f[cur][F_Y]; double* TH = P.st.f[cur][F_TH];
+    double* Z = P.st.f[cur][F_Z]; double* ZS = P.st.f[cur][F_ZS]; double* WG = P.st.f[cur][F_W];
+    double* MPB = P.st.f[cur][F_MP];
+    uint8_t* FL = P.st.b[cur][B_FLOAT]; uint8_t* NF = P.st.b[cur][B_NF];
+
+    const unsigned n_tiles = (unsigned)((P.n + TILE - 1) / TILE);
+    for (unsigned t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        double r_pw[2], r_mx[2], r_x[2], r_y[2]; unsigned r_cnt[2], r_pts[2];
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+            const unsigned long long i = (unsigned long long)t * TILE + r * WT_THREADS + tid;
+            double v_pw = 0, v_mx = 0, v_x = 0, v_y = 0; unsigned v_cnt = 0, v_pts = 0;
+            if (i < P.n) {
+                double x = X[i], y = Y[i], th = TH[i], z = Z[i], zs = ZS[i], w = WG[i];
+                if (DO_PROJECT) {                                                    // :196-237
+                    const unsigned long long gi = P.base + i;
+                    const uint32_t sw = stream_word(em::STREAM_PROJECT, gi);
+                    double n0, n1, n2, unused;
+                    normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 0, sw, P.mp.k0, P.mp.k1), n0, n1);
+                    normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 1, sw, P.mp.k0, P.mp.k1), n2, unused);
+                    const double dx = P.dmean[0] + P.dsigma[0] * n0;                 // :198
+                    double dy = P.dmean[1] + P.dsigma[1] * n1;
+                    const double dth = P.dmean[2] + P.dsigma[2] * n2;
+                    const em::Philox4 u = em::philox4x32_10((uint32_t)gi, P.project_step, 2, sw, P.mp.k0, P.mp.k1);
+                    if (em::u01(u.v[0], u.v[1]) < P.mp.slip_factor) dy *= em::u01(u.v[2], u.v[3]);   // :199-202
+                    double s, c; em::sincos_(th, s, c);
+                    x += c * dx - s * dy;                                            // :205
+                    y += s * dx + c * dy;
+                    th += dth;                                                       // :206
+                    if (P.mp.max_yaw_dev > 0.0) {                                    // :208-216
+                        if (fabs(th - P.yaw) > P.mp.max_yaw_dev) w *= 0.7;
+                    }
+                    z += P.z_delta;                                                  // :218
+                    zs = em::sqrt_(zs * zs + P.z_var);                               // :219
+                    if (spread > 0 && !P.mp.use_hash) {                              // :224-236
+                        const double trans_fac = P.mp.spread_tf * spread, rot_fac = P.mp.spread_rf * spread;
+                        double sx, sy, sth;
+                        normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 3, sw, P.mp.k0, P.mp.k1), sx, sy);
+                        normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 4, sw, P.mp.k0, P.mp.k1), sth, unused);
+                        x += sx * trans_fac + 0.0;
+                        y += sy * trans_fac + 0.0;
+                        th += sth * rot_fac + 0.0;
+                    }
+                    X[i] = x; Y[i] = y; TH[i] = th;
+                    if (!DO_WEIGHT) { Z[i] = z; ZS[i] = zs; WG[i] = w; }
+                }
+                if (DO_WEIGHT) {                                                     // :276-327
+                    double s, c; em::sincos_(th, s, c);
+                    const double mv = zs * zs + P.mp.merr2;                          // :290
+                    if (mv == 0) atomicOr(&P.sc->error_flags, ERR_ZERO_VARIANCE_BIT);   // src/ContactModel.cpp:122-123
+                    PoseEval ev;
+                    contact_eval<false>(P.cs, P.map, mt, htab, P.mp.inv_corr, x, y, z, s, c, mv, ev, nullptr, nullptr);
+                    double mprob = 1.0; uint8_t floating = 1;                        // :316-317
+                    if ((unsigned long long)ev.n_found >= P.mp.min_contacts) {                     // ContactModel.cpp:217
+                        double weight, zdl, zvr;
+                        evaluate_weight(ev, P.mp.use_shape, weight, zdl, zvr);
+                        double zVar = zs * zs;                                       // :294
+                        update_z(ev, zdl, zvr, z, zVar);                             // :295
+                        zs = em::sqrt_(zVar);                                        // :296
+                        w *= weight;                                                 // :300 (Q1: first application)
+                        mprob = weight; floating = 0;
+                        v_mx = weight; v_cnt = 1; v_pts = (unsigned)ev.n_found;      // :305-310
+                        v_pw = em::root_n(weight, (unsigned long long)ev.n_found);   // :309
+                    }
+                    Z[i] = z; ZS[i] = zs; WG[i] = w; MPB[i] = mprob;
+                    FL[i] = floating; NF[i] = (uint8_t)min(ev.n_found, 255);         // :322 cpoints.size()
+                    v_x = x; v_y = y;
+                }
+            }
+            r_pw[r] = v_pw; r_mx[r] = v_mx; r_x[r] = v_x; r_y[r] = v_y; r_cnt[r] = v_cnt; r_pts[r] = v_pts;
+        }
+        if (DO_WEIGHT) {
+            // tile tree: leaf index = r*512 + tid; warp partial g = r*16 + warp covers leaves [32g, 32g+32)
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const double a = warp_tree_sum(r_pw[r]), b = warp_max(r_mx[r]);
+                const double cx = warp_tree_sum(r_x[r]), cy = warp_tree_sum(r_y[r]);
+                const unsigned c1 = warp_sum_u(r_cnt[r]), c2 = warp_sum_u(r_pts[r]);
+                if (lane == 0) {
+                    const int g = r * (WT_THREADS / 32) + warp;
+                    red[g] = a; red[32 + g] = b; red[64 + g] = cx; red[96 + g] = cy; redu[g] = c1; redu[32 + g] = c2;
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const double a = warp_tree_sum(red[lane]), b = warp_max(red[32 + lane]);
+                const double cx = warp_tree_sum(red[64 + lane]), cy = warp_tree_sum(red[96 + lane]);
+                const unsigned c1 = warp_sum_u(redu[lane]), c2 = warp_sum_u(redu[32 + lane]);
+                if (lane == 0) {
+                    TilePartA o; o.sum_pw = a; o.max_w = b; o.sum_x = cx; o.sum_y = cy; o.cnt = c1; o.pts = c2;
+                    P.part[t] = o;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ reduce A (one CTA)
+// floating_weight (:329), max_weight (:305, :347-348), the loop-B power table, next step's map tile centre
+__global__ void __launch_bounds__(1024, 1) k_reduce_a(const TilePartA* part, unsigned n_tiles, unsigned long long n,
+                                                      DevScalars* sc, double* scratch_a, double* scratch_b,
+                                                      double discount) {
+    __shared__ double red[32];
+    __shared__ unsigned long long redull[64];
+    double mx = 0, sx = 0, sy = 0; unsigned long long cnt = 0, pts = 0;
+    for (unsigned i = threadIdx.x; i < n_tiles; i += blockDim.x) {
+        const TilePartA p = part[i];
+        scratch_a[i] = p.sum_pw;
+        mx = fmax(mx, p.max_w); sx += p.sum_x; sy += p.sum_y; cnt += p.cnt; pts += p.pts;
+    }
+    __syncthreads();
+    const double sum_pw = block_tree_reduce(scratch_a, scratch_b, n_tiles);
+    mx = warp_max(mx); sx = warp_tree_sum(sx); sy = warp_tree_sum(sy);
+    for (int o = 1; o < 32; o <<= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); pts += __shfl_xor_sync(0xffffffffu, pts, o); }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = mx; redull[threadIdx.x >> 5] = cnt; redull[32 + (threadIdx.x >> 5)] = pts; }
+    __syncthreads();
+    double smx = 0; unsigned long long scnt = 0, spts = 0;
+    if (threadIdx.x == 0) { for (int i = 0; i < 32; ++i) { smx = fmax(smx, red[i]); scnt += redull[i]; spts += redull[32 + i]; } }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sx;
+    __syncthreads();
+    double tsx = 0; if (threadIdx.x == 0) for (int i = 0; i < 32; ++i) tsx += red[i];
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sy;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tsy = 0; for (int i = 0; i < 32; ++i) tsy += red[i];
+        const double last_max = sc->max_weight;                                       // :268
+        const double fw = scnt > 0 ? sum_pw / (double)scnt : 1.0;                     // :329
+        sc->floating_weight = fw;
+        sc->data_particles = scnt; sc->total_points = spts;
+        sc->max_weight = (spts == 0) ? last_max * discount : smx;                     // :347-348
+        const double xb = discount * fw;
+        for (int k = 0; k <= 4; ++k) sc->pow_table[k] = em::pow_u64(xb, (unsigned long long)(4 - k));   // :336
+        sc->pow_table[5] = em::pow_u64(xb, ~0ull);                                    // wrapped size_t exponent (Q2)
+        if (n > 0) { sc->tile_cx = tsx / (double)n; sc->tile_cy = tsy / (double)n; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ loop B + raw sums
+// weight *= mprob * pow(discount*floating_weight, 4 - cpoints.size())  (:332-345); per-tile sums of the result
+template <bool APPLY>
+__global__ void __launch_bounds__(1024, 1) k_loop_b(StateBufs st, const DevScalars* sc, unsigned long long n,
+                                                    double* tile_sum) {
+    __shared__ double red[32];
+    const int cur = sc->cur;
+    const unsigned long long i = (unsigned long long)blockIdx.x * TILE + threadIdx.x;
+    double w = 0.0;
+    if (i < n) {
+        w = st.f[cur][F_W][i];
+        if (APPLY) {
+            const unsigned nf = st.b[cur][B_NF][i];
+            const double factor = st.f[cur][F_MP][i] * sc->pow_table[nf > 4 ? 5 : nf];
+            w *= factor;                                                              // Q1: second application
+            st.f[cur][F_W][i] = w;
+        }
+    }
+    const double s = tile_tree_sum_1024(w, red);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = s;
+}
+
+// ------------------------------------------------------------------------------------------------ reduce B (one CTA)
+// getWeightsSum (src/ParticleFilter.hpp:34-39) and approximate per-tile prefixes of the (normalised) weights
+__global__ void __launch_bounds__(1024, 1) k_reduce_b(const double* tile_sum, unsigned n_tiles, unsigned long long n,
+                                                      DevScalars* sc, double* scratch_a, double* scratch_b,
+                                                      double* tile_prefix, int normalise) {
+    __shared__ double sh[1024];
+    for (unsigned i = threadIdx.x; i < n_tiles; i += blockDim.x) scratch_a[i] = tile_sum[i];
+    __syncthreads();
+    const double total = block_tree_reduce(scratch_a, scratch_b, n_tiles);
+    const int uniform = normalise && (total <= 0.0);                                 // :51 (Q8)
+    if (threadIdx.x == 0) { if (normalise) sc->sum_w = total; sc->uniform = uniform; }
+    // exclusive scan of the per-tile masses (approximate is enough: only used to classify elements)
+    const unsigned per = (n_tiles + blockDim.x - 1) / blockDim.x;
+    const unsigned lo = threadIdx.x * per, hi = min(lo + per, n_tiles);
+    auto mass = [&](unsigned t) -> double {
+        if (uniform) { const unsigned long long c = min((unsigned long long)TILE, n - (unsigned long long)t * TILE); return (double)c / (double)n; }
+        return normalise ? tile_sum[t] / total : tile_sum[t];
+    };
+    double local = 0;
+    for (unsigned t = lo; t < hi; ++t) local += mass(t);
+    sh[threadIdx.x] = local;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const double v = (threadIdx.x >= (unsigned)o) ? sh[threadIdx.x - o] : 0.0;
+        __syncthreads();
+        sh[threadIdx.x] += v;
+        __syncthreads();
+    }
+    double run = sh[threadIdx.x] - local;
+    for (unsigned t = lo; t < hi; ++t) { tile_prefix[t] = run; run += mass(t); }
+}
+
+// ------------------------------------------------------------------------------------------------ exact running sum
+// Element classes for the exact emulation of  sum_w += xi_k[idx].weight  (src/ParticleFilter.hpp:95,102):
+//   neutral  : adding it never changes the running sum (zero, or below a quarter ulp of the sum)
+//   interior : the sum stays inside one binade 2^b across this add -> the add is an integer add of
+//              rne(w / ulp_b), with ties depending only on the parity of the sum: a 2-state function (d0, d1)
+//   boundary : anything else (first element, binade crossings, ambiguous cases): added in real fp64 by the chain
+struct ElemClass { int kind; int b; long long d0, d1; };   // kind: 0 neutral, 1 interior, 2 boundary
+
+__device__ __forceinline__ ElemClass classify_elem(double w, double a_prev, double a_cur, double eps) {
+    ElemClass c; c.kind = 0; c.b = BIN_NONE; c.d0 = 0; c.d1 = 0;
+    if (w == 0.0) return c;
+    c.kind = 2;
+    if (!(w > 0.0) || !(a_cur < 1.7e308)) return c;                    // negative / NaN / inf: let the chain add it
+    const double lo = em::fma_(-a_prev, eps, a_prev), hi = em::fma_(a_cur, eps, a_cur);
+    const uint64_t ulo = em::d2u(lo), uhi = em::d2u(hi), uw = em::d2u(w);
+    if (!(lo > 0.0) || (ulo >> 52) == 0) return c;
+    const int blo = (int)(ulo >> 52) - 1023, bhi = (int)(uhi >> 52) - 1023;
+    const int ew = ((uw >> 52) == 0) ? -1023 : (int)(uw >> 52) - 1023;
+    if (ew + 1 <= blo - 54) { c.kind = 0; return c; }                   // w < 2^(blo-54): under a quarter ulp
+    if (blo != bhi || (uw >> 52) == 0) return c;
+    const int k = blo - ew;
+    if (k < 0) return c;
+    const uint64_t M = (uw & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
+    c.kind = 1; c.b = blo;
+    if (k == 0) { c.d0 = c.d1 = (long long)M; return c; }
+    const uint64_t fl = M >> k, frac = M & ((1ull << k) - 1), half = 1ull << (k - 1);
+    const long long up = frac > half ? 1 : 0;
+    const bool tie = frac == half;
+    c.d0 = (long long)fl + up + ((tie && (fl & 1)) ? 1 : 0);
+    c.d1 = (long long)fl + up + ((tie && !(fl & 1)) ? 1 : 0);
+    return c;
+}
+
+__device__ __forceinline__ SegF segf_identity() { SegF f; f.d0 = 0; f.d1 = 0; f.b = BIN_NONE; f.pad = 0; return f; }
+// a then b.  pad carries a "binade mismatch" flag (must never happen; triggers the sequential fallback)
+__device__ __forceinline__ SegF segf_compose(const SegF& a, const SegF& b) {
+    SegF c;
+    c.b = (b.b != BIN_NONE) ? b.b : a.b;
+    c.pad = a.pad | b.pad | ((a.b != BIN_NONE && b.b != BIN_NONE && a.b != b.b) ? 1 : 0);
+    c.d0 = a.d0 + ((a.d0 & 1) ? b.d1 : b.d0);
+    c.d1 = a.d1 + (((1 + a.d1) & 1) ? b.d1 : b.d0);
+    return c;
+}
+__device__ __forceinline__ double segf_apply(double S, const SegF& f, int& bad) {
+    if (f.pad) bad = 1;
+    if (f.b == BIN_NONE) return S;
+    const uint64_t u = em::d2u(S);
+    if ((int)(u >> 52) - 1023 != f.b) { bad = 1; return S; }
+    return em::u2d(u + (uint64_t)((u & 1) ? f.d1 : f.d0));
+}
+
+struct SegE { SegF f; int head; };   // scan element: function since the last boundary at or before (head = its index, -1 none)
+__device__ __forceinline__ SegE sege_combine(const SegE& L, const SegE& R) {
+    if (R.head >= 0) return R;
+    SegE o; o.head = L.head; o.f = segf_compose(L.f, R.f); return o;
+}
+__device__ __forceinline__ SegE sege_shfl_up(const SegE& v, int o) {
+    SegE r;
+    r.f.d0 = __shfl_up_sync(0xffffffffu, v.f.d0, o); r.f.d1 = __shfl_up_sync(0xffffffffu, v.f.d1, o);
+    r.f.b = __shfl_up_sync(0xffffffffu, v.f.b, o); r.f.pad = __shfl_up_sync(0xffffffffu, v.f.pad, o);
+    r.head = __shfl_up_sync(0xffffffffu, v.head, o);
+    return r;
+}
+
+struct TileScan {          // per-thread results of the tile-local scans
+    ElemClass cls;
+    SegE inc;              // inclusive segmented function
+    int bnd_before;        // boundary elements strictly before this one in the tile
+    int bnd_total;
+};
+
+// Shared scratch for tile_scan: 32 doubles + 32 SegE + 32 ints
+struct TileScanSmem { double d[32]; SegE e[32]; int c[32]; };
+
+// Tile-local approximate inclusive prefix + classification + segmented function scan. blockDim.x == 1024.
+__device__ __forceinline__ TileScan tile_scan(double w, bool active, double tile_prefix, double eps, TileScanSmem& sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // approximate inclusive prefix (fixed order -> k_norm_scan and k_cdf see identical bits)
+    double a = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, a, o); if (lane >= o) a += v; }
+    __syncthreads();
+    if (lane == 31) sm.d[warp] = a;
+    __syncthreads();
+    double wp = sm.d[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, wp, o); if (lane >= o) wp += v; }
+    const double warp_excl = __shfl_sync(0xffffffffu, wp, max(warp - 1, 0));
+    const double a_cur = tile_prefix + ((warp > 0 ? warp_excl : 0.0) + a);
+    double a_prev = __shfl_up_sync(0xffffffffu, a_cur, 1);
+    if (lane == 0) a_prev = tile_prefix + (warp > 0 ? warp_excl : 0.0);
+
+    TileScan r;
+    r.cls = classify_elem(active ? w : 0.0, a_prev, a_cur, eps);
+    SegE e; e.f = segf_identity(); e.head = -1;
+    if (r.cls.kind == 1) { e.f.d0 = r.cls.d0; e.f.d1 = r.cls.d1; e.f.b = r.cls.b; }
+    if (r.cls.kind == 2) e.head = (int)threadIdx.x;
+    int cnt = (r.cls.kind == 2) ? 1 : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const SegE v = sege_shfl_up(e, o); const int cv = __shfl_up_sync(0xffffffffu, cnt, o);
+        if (lane >= o) { e = sege_combine(v, e); cnt += cv; }
+    }
+    __syncthreads();
+    if (lane == 31) { sm.e[warp] = e; sm.c[warp] = cnt; }
+    __syncthreads();
+    SegE we = sm.e[lane]; int wc = sm.c[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const SegE v = sege_shfl_up(we, o); const int cv = __shfl_up_sync(0xffffffffu, wc, o);
+        if (lane >= o) { we = sege_combine(v, we); wc += cv; }
+    }
+    const int src = max(warp - 1, 0);
+    SegE pe; pe.f.d0 = __shfl_sync(0xffffffffu, we.f.d0, src); pe.f.d1 = __shfl_sync(0xffffffffu, we.f.d1, src);
+    pe.f.b = __shfl_sync(0xffffffffu, we.f.b, src); pe.f.pad = __shfl_sync(0xffffffffu, we.f.pad, src);
+    pe.head = __shfl_sync(0xffffffffu, we.head, src);
+    const int pc = __shfl_sync(0xffffffffu, wc, src);
+    r.bnd_total = __shfl_sync(0xffffffffu, wc, 31);
+    if (warp > 0) { e = sege_combine(pe, e); cnt += pc; }
+    r.inc = e;
+    r.bnd_before = cnt - ((r.cls.kind == 2) ? 1 : 0);
+    return r;
+}
+
+// normalise (src/ParticleFilter.hpp:51-67), per-tile sum of w^2, and the tile descriptors of the exact running sum
+__global__ void __launch_bounds__(1024, 1) k_norm_scan(StateBufs st, const DevScalars* sc, unsigned long long n,
+                                                       unsigned long long n_global, const double* tile_prefix,
+                                                       double* tile_sq, TileDesc* desc, int normalise, double eps) {
+    __shared__ TileScanSmem sm;
+    __shared__ double red[32];
+    __shared__ int slot_of[TILE];
+    const int cur = sc->cur;
+    const unsigned long long i = (unsigned long long)blockIdx.x * TILE + threadIdx.x;
+    const bool active = i < n;
+    double w = 0.0;
+    if (active) {
+        w = st.f[cur][F_W][i];
+        if (normalise) {
+            if (sc->uniform) w = 1.0 / (double)n_global;                              // :55
+            else w /= sc->sum_w;                                                     // :64
+            st.f[cur][F_W][i] = w;
+        }
+    }
+    const double sq = tile_tree_sum_1024(w * w, red);                                 // effective += w*w
+    if (threadIdx.x == 0) tile_sq[blockIdx.x] = sq;
+
+    const TileScan ts = tile_scan(w, active, tile_prefix[blockIdx.x], eps, sm);
+    TileDesc* D = &desc[blockIdx.x];
+    slot_of[threadIdx.x] = ts.bnd_before;
+    if (threadIdx.x == 0) {
+        D->n_bnd = ts.bnd_total; D->overflow = ts.bnd_total > MAX_BND_PER_TILE;
+        D->head_b = BIN_NONE; D->head_d0 = 0; D->head_d1 = 0; D->pad = 0;
+    }
+    __syncthreads();
+    if (ts.bnd_total <= MAX_BND_PER_TILE) {
+        if (ts.cls.kind == 2) { D->bnd[ts.bnd_before].w = w; D->bnd[ts.bnd_before].idx = (int)threadIdx.x; }
+        // piece ends: the next element is a boundary, or this is the last element of the tile
+        const int next_kind = __shfl_down_sync(0xffffffffu, ts.cls.kind, 1);
+        __shared__ int first_kind[32];
+        if ((threadIdx.x & 31) == 0) first_kind[threadIdx.x >> 5] = ts.cls.kind;
+        __syncthreads();
+        int nk = next_kind;
+        if ((threadIdx.x & 31) == 31) nk = (threadIdx.x == TILE - 1) ? 2 : first_kind[(threadIdx.x >> 5) + 1];
+        if (nk == 2) {
+            if (ts.inc.head < 0) { D->head_b = ts.inc.f.b; D->head_d0 = ts.inc.f.d0; D->head_d1 = ts.inc.f.d1; D->pad = ts.inc.f.pad; }
+            else {
+                const int s = slot_of[ts.inc.head];
+                D->bnd[s].b = ts.inc.f.b; D->bnd[s].d0 = ts.inc.f.d0; D->bnd[s].d1 = ts.inc.f.d1;
+                if (ts.inc.f.pad) D->overflow = 1;
+            }
+        }
+    }
+}
+
+// one CTA: ESS, resample decision, and the exact value of the running sum at every tile start / boundary element
+struct ChainSmem { double bw[MAX_BND_TOTAL]; SegF seg[MAX_BND_TOTAL]; };
+
+__global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, unsigned n_tiles, const double* tile_sq,
+                                                   DevScalars* sc, double* scratch_a, double* scratch_b,
+                                                   int* tile_bofs, SegF* tile_pre, double* tile_sin, double* sb_out,
+                                                   unsigned long long min_effective, int decide, int force) {
+    extern __shared__ __align__(16) unsigned char chain_raw[];
+    ChainSmem& cs = *reinterpret_cast<ChainSmem*>(chain_raw);
+    __shared__ int sh_i[1024];
+    __shared__ SegE sh_e[1024];
+    __shared__ int s_total, s_bad, s_go;
+    const unsigned tid = threadIdx.x;
+    if (decide) {
+        for (unsigned i = tid; i < n_tiles; i += blockDim.x) scratch_a[i] = tile_sq[i];
+        __syncthreads();
+        const double eff = block_tree_reduce(scratch_a, scratch_b, n_tiles);
+        if (tid == 0) {
+            const double ess = 1.0 / eff;                                             // src/ParticleFilter.hpp:69
+            sc->ess = ess;
+            sc->do_resample = (force || ess < (double)min_effective) ? 1 : 0;         // src/PoseEstimator.cpp:249
+        }
+    } else if (tid == 0) sc->do_resample = force ? 1 : 0;
+    if (tid == 0) { s_bad = 0; }
+    __syncthreads();
+    if (tid == 0) s_go = sc->do_resample;
+    __syncthreads();
+    if (!s_go) return;
+
+    // exclusive prefix of boundary counts + segmented exclusive scan of tile functions
+    const unsigned per = (n_tiles + blockDim.x - 1) / blockDim.x;
+    const unsigned lo = tid * per, hi = min(lo + per, n_tiles);
+    int cnt = 0; SegE agg; agg.f = segf_identity(); agg.head = -1; int bad = 0;
+    for (unsigned t = lo; t < hi; ++t) {
+        const TileDesc& D = desc[t];
+        if (D.overflow) bad = 1;
+        cnt += D.n_bnd;
+        SegE e;
+        if (D.n_bnd > 0 && !D.overflow) {
+            const int l = D.n_bnd - 1; e.head = (int)t; e.f.b = D.bnd[l].b; e.f.d0 = D.bnd[l].d0; e.f.d1 = D.bnd[l].d1; e.f.pad = 0;
+        } else { e.head = -1; e.f.b = D.head_b; e.f.d0 = D.head_d0; e.f.d1 = D.head_d1; e.f.pad = D.pad; }
+        agg = sege_combine(agg, e);
+    }
+    sh_i[tid] = cnt; sh_e[tid] = agg;
+    if (bad) atomicOr(&s_bad, 1);
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int ci = 0; SegE ce; ce.f = segf_identity(); ce.head = -1;
+        const bool has = tid >= (unsigned)o;
+        if (has) { ci = sh_i[tid - o]; ce = sh_e[tid - o]; }
+        __syncthreads();
+        if (has) { sh_i[tid] += ci; sh_e[tid] = sege_combine(ce, sh_e[tid]); }
+        __syncthreads();
+    }
+    if (tid == 1023) s_total = sh_i[1023];
+    int run_c = sh_i[tid] - cnt;
+    SegE run_e; run_e.f = segf_identity(); run_e.head = -1;
+    if (tid > 0) run_e = sh_e[tid - 1];
+    __syncthreads();
+    const int total = s_total;
+    if (total > MAX_BND_TOTAL) { if (tid == 0) s_bad = 1; }
+    __syncthreads();
+    if (s_bad) { if (tid == 0) { atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT); sc->n_boundaries = total; } return; }
+    for (unsigned t = lo; t < hi; ++t) {
+        const TileDesc& D = desc[t];
+        tile_bofs[t] = run_c; tile_pre[t] = run_e.f;
+        // boundary k = run_c + j: weight, and the function of the segment that follows it
+        for (int j = 0; j < D.n_bnd; ++j) {
+            cs.bw[run_c + j] = D.bnd[j].w;
+            if (j + 1 < D.n_bnd) { SegF f; f.b = D.bnd[j].b; f.d0 = D.bnd[j].d0; f.d1 = D.bnd[j].d1; f.pad = 0; cs.seg[run_c + j] = f; }
+        }
+        if (D.n_bnd > 0 && run_c > 0) {
+            // segment after boundary run_c-1 ends with this tile's head piece
+            SegF hf; hf.b = D.head_b; hf.d0 = D.head_d0; hf.d1 = D.head_d1; hf.pad = D.pad;
+            cs.seg[run_c - 1] = segf_compose(run_e.f, hf);
+        }
+        SegE e;
+        if (D.n_bnd > 0) { const int l = D.n_bnd - 1; e.head = (int)t; e.f.b = D.bnd[l].b; e.f.d0 = D.bnd[l].d0; e.f.d1 = D.bnd[l].d1; e.f.pad = 0; }
+        else { e.head = -1; e.f.b = D.head_b; e.f.d0 = D.head_d0; e.f.d1 = D.head_d1; e.f.pad = D.pad; }
+        run_e = sege_combine(run_e, e);
+        run_c += D.n_bnd;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // the sequential part: one real fp64 add per boundary element, one integer add per segment
+        double S = 0.0; int b2 = 0;
+        for (int k = 0; k < total; ++k) {
+            S = S + cs.bw[k];
+            cs.bw[k] = S;
+            if (k + 1 < total) S = segf_apply(S, cs.seg[k], b2);
+        }
+        if (b2) { s_bad = 1; atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT); }
+        sc->n_boundaries = total;
+    }
+    __syncthreads();
+    if (s_bad) return;
+    for (unsigned k = tid; k < (unsigned)total; k += blockDim.x) sb_out[k] = cs.bw[k];
+    int b3 = 0;
+    for (unsigned t = lo; t < hi; ++t) {
+        const int ofs = tile_bofs[t];
+        const double S0 = ofs > 0 ? cs.bw[ofs - 1] : 0.0;
+        tile_sin[t] = segf_apply(S0, tile_pre[t], b3);
+    }
+    if (b3) atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT);
+}
+
+// exact running sum of every element: cdf[i] == the reference's sum_w after adding xi_k[i].weight
+__global__ void __launch_bounds__(1024, 1) k_cdf(StateBufs st, DevScalars* sc, unsigned long long n,
+                                                 const double* tile_prefix, const int* tile_bofs, const double* tile_sin,
+                                                 const double* sb, double* cdf, double eps) {
+    __shared__ TileScanSmem sm;
+    __shared__ int slot_of[TILE];
+    if (!sc->do_resample || (sc->error_flags & ERR_CDF_FALLBACK_BIT)) return;
+    const int cur = sc->cur;
+    const unsigned long long i = (unsigned long long)blockIdx.x * TILE + threadIdx.x;
+    const bool active = i < n;
+    const double w = active ? st.f[cur][F_W][i] : 0.0;
+    const TileScan ts = tile_scan(w, active, tile_prefix[blockIdx.x], eps, sm);
+    slot_of[threadIdx.x] = ts.bnd_before;
+    __syncthreads();
+    int bad = 0;
+    double S;
+    const int ofs = tile_bofs[blockIdx.x];
+    if (ts.cls.kind == 2) S = sb[ofs + ts.bnd_before];
+    else if (ts.inc.head < 0) S = segf_apply(tile_sin[blockIdx.x], ts.inc.f, bad);
+    else S = segf_apply(sb[ofs + slot_of[ts.inc.head]], ts.inc.f, bad);
+    if (bad) atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT);
+    if (active) cdf[i] = S;
+}
+
+// fallback: literal left-to-right running sum by one thread (only when the tile descriptors overflowed)
+__global__ void k_cdf_sequential(StateBufs st, DevScalars* sc, unsigned long long n, double* cdf) {
+    if (!sc->do_resample || !(sc->error_flags & ERR_CDF_FALLBACK_BIT)) return;
+    const double* w = st.f[sc->cur][F_W];
+    double s = 0.0;
+    for (unsigned long long i = 0; i < n; ++i) { s = (i == 0) ? w[0] : s + w[i]; cdf[i] = s; }
+    sc->error_flags &= ~ERR_CDF_FALLBACK_BIT;
+}
+
+// ------------------------------------------------------------------------------------------------ resample
+// the stratified walk (src/ParticleFilter.hpp:96-105) as a lower-bound search: ancestor[k] = first idx with !(cdf[idx] < sum_r)
+__global__ void k_search(const DevScalars* sc, const double* __restrict__ cdf, unsigned long long n,
+                         unsigned long long n_global, unsigned long long base, uint32_t k0, uint32_t k1,
+                         int systematic, uint32_t* ancestors) {
+    if (!sc->do_resample) return;
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const unsigned long long gk = systematic ? 0ull : base + k;
+    const em::Philox4 r = em::philox4x32_10((uint32_t)gk, sc->resample_step, 0, stream_word(em::STREAM_RESAMPLE, gk), k0, k1);
+    const double u = em::u01(r.v[0], r.v[1]);
+    const double sum_r = ((double)(base + k) + u) / (double)n_global;                // :98
+    unsigned long long lo = 0, hi = n;                                               // first idx in [0,n) with cdf >= sum_r
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if (__ldg(&cdf[mid]) < sum_r) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= n) lo = n - 1;                      // the reference walks off the end here; we stop at the last particle
+    ancestors[k] = (uint32_t)lo;
+}
+
+__global__ void k_gather(StateBufs st, const DevScalars* sc, unsigned long long n, const uint32_t* __restrict__ anc) {
+    if (!sc->do_resample) return;
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int cur = sc->cur, nxt = cur ^ 1;
+    const uint32_t a = anc[k];
+#pragma unroll
+    for (int f = 0; f < 7; ++f) st.f[nxt][f][k] = st.f[cur][f][a];                    // :104 copy keeps the weight (Q3)
+    st.b[nxt][0][k] = st.b[cur][0][a]; st.b[nxt][1][k] = st.b[cur][1][a];
+}
+
+__global__ void k_after_resample(DevScalars* sc) {
+    if (!sc->do_resample) return;
+    sc->cur ^= 1;                                                                    // xi_k.swap(xi_kp) :107
+    sc->resample_step += 1;
+}
+
+// ------------------------------------------------------------------------------------------------ outputs
+__global__ void __launch_bounds__(1024, 1) k_centroid_tiles(StateBufs st, const DevScalars* sc, unsigned long long n,
+                                                            double* part /* 5 x n_tiles */, unsigned n_tiles,
+                                                            unsigned long long* best_idx, double* best_w) {
+    __shared__ double red[32];
+    __shared__ unsigned long long bi[32];
+    const int cur = sc->cur;
+    const unsigned long long i = (unsigned long long)blockIdx.x * TILE + threadIdx.x;
+    double x = 0, y = 0, th = 0, z = 0, w = 0;
+    if (i < n) { w = st.f[cur][F_W][i]; x = st.f[cur][F_X][i] * w; y = st.f[cur][F_Y][i] * w; th = st.f[cur][F_TH][i] * w; z = st.f[cur][F_Z][i] * w; }
+    const double sx = tile_tree_sum_1024(x, red), sy = tile_tree_sum_1024(y, red);
+    const double st_ = tile_tree_sum_1024(th, red), sz = tile_tree_sum_1024(z, red), sw = tile_tree_sum_1024(w, red);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = sx; part[n_tiles + blockIdx.x] = sy; part[2 * n_tiles + blockIdx.x] = st_;
+        part[3 * n_tiles + blockIdx.x] = sz; part[4 * n_tiles + blockIdx.x] = sw;
+    }
+    // first index of the strict maximum (src/ParticleFilter.hpp:160-173)
+    double bw = (i < n) ? st.f[cur][F_W][i] : -INFINITY; unsigned long long bidx = (i < n) ? i : ~0ull;
+    if (!(bw == bw)) bw = -INFINITY;   // NaN never wins the > comparison
+    for (int o = 1; o < 32; o <<= 1) {
+        const double ow = __shfl_xor_sync(0xffffffffu, bw, o); const unsigned long long oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ow > bw || (ow == bw && oi < bidx)) { bw = ow; bidx = oi; }
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = bw; bi[threadIdx.x >> 5] = bidx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 32; ++k) if (red[k] > bw || (red[k] == bw && bi[k] < bidx)) { bw = red[k]; bidx = bi[k]; }
+        best_idx[blockIdx.x] = bidx; best_w[blockIdx.x] = bw;
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1) k_centroid_final(double* part, unsigned n_tiles, double* scratch_b,
+                                                            const unsigned long long* best_idx, const double* best_w,
+                                                            DevScalars* sc) {
+    for (int q = 0; q < 5; ++q) {
+        const double v = block_tree_reduce(part + (size_t)q * n_tiles, scratch_b, n_tiles);
+        if (threadIdx.x == 0) sc->centroid[q] = v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double bw = -INFINITY; unsigned long long bi = 0;
+        for (unsigned t = 0; t < n_tiles; ++t) if (best_w[t] > bw) { bw = best_w[t]; bi = best_idx[t]; }
+        sc->best_index = (bi == ~0ull) ? 0 : bi;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ diagnostic seam
+// ContactModel::evaluatePose / evaluateWeight / updateZPositionEstimate for explicit poses
+// (the seam test/testContactModel.cpp drives); same device functions as the fused kernel.
+struct EvalParams {
+    unsigned long long n;
+    const double *x, *y, *th, *z, *mv, *zvin;
+    MapParams map; const em::dbl2* htab;
+    double inv_corr; unsigned long long min_contacts; int use_shape;
+    uint8_t* ok; double *weight, *zdelta, *zvar, *posevar; int32_t* ncont; double *zout, *zvout;
+    int32_t* cells; double* cp; int* err;
+    ContactSet cs;
+};
+
+__global__ void k_evaluate_poses(const __grid_constant__ EvalParams P) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    MapTile mt; mt.s = nullptr; mt.w = 0; mt.h = 0; mt.x0 = 0; mt.y0 = 0;
+    double s, c; em::sincos_(P.th[i], s, c);
+    const double mv = P.mv[i];
+    if (mv == 0) { atomicOr(P.err, ERR_ZERO_VARIANCE_BIT); return; }
+    PoseEval ev;
+    contact_eval<true>(P.cs, P.map, mt, P.htab, P.inv_corr, P.x[i], P.y[i], P.z[i], s, c, mv, ev,
+                       P.cells + i * P.cs.n, P.cp + i * ESLAM_MAX_CP * 5);
+    const bool ok = (unsigned long long)ev.n_found >= P.min_contacts;
+    double weight = 0, zdl = 0, zvr = 0, z = P.z[i], zv = P.zvin ? P.zvin[i] : 0.0;
+    if (ok) {
+        evaluate_weight(ev, P.use_shape, weight, zdl, zvr);
+        if (P.zvin) update_z(ev, zdl, zvr, z, zv);
+    }
+    P.ok[i] = ok; P.weight[i] = weight; P.zdelta[i] = zdl; P.zvar[i] = zvr; P.posevar[i] = ev.poseVar;
+    P.ncont[i] = ev.n_found; P.zout[i] = z; P.zvout[i] = zv;
+}

@@ -1,0 +1,281 @@
+"""Parity of the CUDA path (through the C ABI, libeslam_gpu.so) against the CPU oracle on identical inputs and
+identical Philox noise.  Bars (north_star): ancestor indices and map-cell indices bit-exact; poses 1e-6 m / rad and
+normalised weights 1e-5 relative against the LITERAL restatement.  Against the SHARED-arithmetic oracle the CUDA path
+is expected to be bit-identical in every double, and these tests require exactly that."""
+import numpy as np
+import pytest
+
+from helpers import assert_particles_equal, kat_config, kat_contacts, load_kat, quadrant_grid
+from slam_eslam_b200 import abi, synthetic
+
+pytestmark = pytest.mark.gpu
+KAT = load_kat()
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from slam_eslam_b200 import GpuPoseEstimator
+    return GpuPoseEstimator
+
+
+def pair(gpu, oracle, workload, n=None, policy=None, **cfg):
+    g = gpu(abi.default_config(**cfg))
+    o = oracle.OraclePoseEstimator(abi.default_config(**cfg), policy=oracle.SHARED if policy is None else policy)
+    contacts, step = synthetic.setup_filter(g, workload, n=n)
+    synthetic.setup_filter(o, workload, n=n)
+    return g, o, contacts, step
+
+
+# ---------------------------------------------------------------------------------- reference KATs on the GPU
+@pytest.mark.parametrize("name", ["K2_nogroup_flat", "K3_nogroup_uncertain"])
+def test_reference_kat_nogroup(gpu, name):
+    case = KAT[name]
+    g = gpu(kat_config(case))
+    g.setEnvironment(*quadrant_grid(case["z"], case["stddev"], case.get("res")))
+    out = g.evaluatePoses([0.0], [0.0], [0.0], [0.0], [case["meas_var"]], kat_contacts(case))
+    assert out["ok"][0] and out["n_contacts"][0] == case["expect_contacts"]
+    for i, p in enumerate(case["points"]):
+        assert np.allclose(out["cp"][0, i, :3], [p[0], p[1], case["z"][i]], atol=1e-6)
+    rel = case["rel_tol_percent"] / 100.0
+    assert abs(out["z_delta"][0]) < case["z_delta_abs_max"]
+    assert abs(out["z_var"][0] - case["z_var"]) <= rel * case["z_var"]
+    assert abs(out["weight"][0] - case["weight"]) <= rel * case["weight"]
+
+
+def test_reference_kat_accessor_positions(gpu):
+    """K1: the map is queried at pose * contact_point (test/testContactModel.cpp:89-124): here seen as the cell
+    each contact lands in on a 1 m grid centred on the expected positions."""
+    case = KAT["K1_accessor_positions"]
+    g = gpu(kat_config(case))
+    cells = np.zeros((8, 8, 2), dtype=np.float32)
+    g.setEnvironment(cells, (0.5, 0.5), (-2.0, -2.0))
+    for pose in case["poses"]:
+        x, y, z = pose["xyz"]
+        out = g.evaluatePoses([x], [y], [pose["theta"]], [z], [case["meas_var"]], kat_contacts(case))
+        for got, want in zip(out["cell_index"][0], pose["expected_queries"]):
+            ix, iy = int(np.floor((want[0] + 2.0) / 0.5)), int(np.floor((want[1] + 2.0) / 0.5))
+            assert got == iy * 8 + ix
+
+
+def test_reference_kat_map_absence(gpu):
+    case = KAT["K5_map_absence_group"]
+    g = gpu(kat_config(case))
+    g.setEnvironment(*quadrant_grid(case["z"], case["stddev"], case["res"]))
+    out = g.evaluatePoses([0.0], [0.0], [0.0], [0.0], [case["meas_var"]], kat_contacts(case))
+    assert out["ok"][0] and out["n_contacts"][0] == 1
+
+
+def test_kats_bit_identical_to_shared_oracle(gpu, oracle):
+    for name in ("K2_nogroup_flat", "K3_nogroup_uncertain", "K2_default_radius", "K5_map_absence_group",
+                 "STALE_updatePose_group"):
+        case = KAT[name]
+        g = gpu(kat_config(case))
+        o = oracle.OraclePoseEstimator(kat_config(case), policy=oracle.SHARED)
+        for f in (g, o):
+            f.setEnvironment(*quadrant_grid(case["z"], case["stddev"], case.get("res")))
+        args = ([0.0], [0.0], [0.0], [0.0], [case["meas_var"]], kat_contacts(case))
+        a, b = g.evaluatePoses(*args, z_var_in=[0.5]), o.evaluatePoses(*args, z_var_in=[0.5])
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (name, k, a[k], b[k])
+
+
+# ---------------------------------------------------------------------------------- errors
+def test_error_conventions(gpu):
+    g = gpu()
+    g.init(16, (0, 0, 0), (0.1, 0.1, 0.1), 0.0, 1.0)
+    with pytest.raises(RuntimeError, match="No environment attached"):
+        g.update(kat_contacts(KAT["K2_nogroup_flat"]))
+    case = KAT["K2_nogroup_flat"]
+    g.setEnvironment(*quadrant_grid(case["z"], case["stddev"]))
+    with pytest.raises(RuntimeError, match="zero measurement variance"):
+        g.evaluatePoses([0.0], [0.0], [0.0], [0.0], [0.0], kat_contacts(case))
+    g2 = gpu(abi.default_config(measurement_error=0.0))
+    g2.setEnvironment(*quadrant_grid(case["z"], case["stddev"]))
+    g2.init(16, (0, 0, 0), (0.1, 0.1, 0.1), 0.0, 0.0)
+    with pytest.raises(RuntimeError, match="zero measurement variance"):
+        g2.update(kat_contacts(case))
+
+
+# ---------------------------------------------------------------------------------- stage: init / project
+def test_init_and_project_bit_identical(gpu, oracle):
+    g, o, contacts, step = pair(gpu, oracle, "C2")
+    assert_particles_equal(g.getParticles(), o.getParticles())
+    for _ in range(3):
+        g.project(step)
+        o.project(step)
+        assert_particles_equal(g.getParticles(), o.getParticles())
+
+
+def test_spread_and_yaw_penalty_paths(gpu, oracle):
+    """max_weight = 0 after init -> spread = 1 (src/PoseEstimator.cpp:194,224-236); yaw far away -> weight *= 0.7."""
+    g, o, contacts, step = pair(gpu, oracle, "C1", slip_factor=0.5)
+    far = abi.make_step(yaw=2.0, z_delta=0.01, z_var=1e-4, delta_mean=(0.05, 0.01, 0.02), delta_sigma=(0.01, 0.01, 0.01))
+    for f in (g, o):
+        f.setParticles(weight=np.full(250, 1.0 / 250))
+        f.project(far)
+    a, b = g.getParticles(), o.getParticles()
+    assert_particles_equal(a, b)
+    assert np.allclose(a["weight"], 0.7 / 250)
+
+
+# ---------------------------------------------------------------------------------- stage: contact model
+def test_evaluate_poses_bit_identical_and_cells_exact(gpu, oracle):
+    """Random poses on the C2 terrain, 64 contact points: every output double and every map-cell index."""
+    g, o, _, _ = pair(gpu, oracle, "C2", n=16)
+    lit = oracle.OraclePoseEstimator(abi.default_config(), policy=oracle.LITERAL)
+    synthetic.setup_filter(lit, "C2", n=16)
+    contacts = synthetic.make_contact_points(64)
+    rng = np.random.default_rng(11)
+    n = 4000
+    x, y = rng.uniform(-13.5, 13.5, (2, n))          # partly off the 25.6 m map
+    th = rng.uniform(-7, 7, n)
+    z = 0.19 + rng.normal(0, 0.2, n)
+    zs = 10 ** rng.uniform(-2, 0.2, n)
+    mv = zs * zs + 0.01
+    a = g.evaluatePoses(x, y, th, z, mv, contacts, z_var_in=zs * zs)
+    b = o.evaluatePoses(x, y, th, z, mv, contacts, z_var_in=zs * zs)
+    c = lit.evaluatePoses(x, y, th, z, mv, contacts, z_var_in=zs * zs)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    # against the line-by-line restatement: cells bit-exact, floats within north_star's tolerance
+    assert np.array_equal(a["cell_index"], c["cell_index"])
+    assert np.array_equal(a["ok"], c["ok"]) and np.array_equal(a["n_contacts"], c["n_contacts"])
+    np.testing.assert_allclose(a["weight"], c["weight"], rtol=1e-5, atol=1e-300)
+    np.testing.assert_allclose(a["zpos_out"], c["zpos_out"], rtol=0, atol=1e-6)
+    assert a["ok"].sum() > n // 10 and (a["cell_index"] < 0).any()
+
+
+# ---------------------------------------------------------------------------------- end to end trajectories
+@pytest.mark.parametrize("workload,steps,cfg", [
+    ("C1", 40, {}),                                        # reference defaults: resample when ESS < 50
+    ("C1", 12, {"min_effective": 251}),                    # resample every step
+    ("C1", 12, {"min_effective": 251, "resample_mode": abi.RESAMPLE_SYSTEMATIC}),
+    ("C2", 8, {"min_effective": 10001}),
+])
+def test_trajectory_bit_identical_to_shared_oracle(gpu, oracle, workload, steps, cfg):
+    g, o, contacts, step = pair(gpu, oracle, workload, **cfg)
+    resampled = 0
+    for i in range(steps):
+        g.project(step)
+        o.project(step)
+        ra, rb = g.update(contacts), o.update(contacts)
+        assert ra.as_dict() == rb.as_dict(), "step %d: %r vs %r" % (i, ra.as_dict(), rb.as_dict())
+        if ra.resampled:
+            resampled += 1
+            assert np.array_equal(g.getAncestors(), o.getAncestors()), "ancestors, step %d" % i
+            assert np.array_equal(g.getCdf(), o.getCdf()), "running sum, step %d" % i
+        assert_particles_equal(g.getParticles(), o.getParticles())
+    assert resampled > 0
+    assert np.array_equal(g.getCentroid(), o.getCentroid())
+    assert g.getBestParticleIndex() == o.getBestParticleIndex()
+
+
+def test_fused_step_equals_project_then_update(gpu):
+    g1, g2 = gpu(abi.default_config(min_effective=10001)), gpu(abi.default_config(min_effective=10001))
+    contacts, step = synthetic.setup_filter(g1, "C2")
+    synthetic.setup_filter(g2, "C2")
+    for _ in range(3):
+        g1.project(step)
+        r1 = g1.update(contacts)
+        r2 = g2.stepFused(step, contacts)
+        assert r1.as_dict() == r2.as_dict()
+    assert_particles_equal(g1.getParticles(), g2.getParticles())
+
+
+def test_trajectory_within_tolerance_of_literal_oracle(gpu, oracle):
+    """GPU vs the line-by-line restatement (libm, reference expression order) over 25 steps of C1."""
+    g, o, contacts, step = pair(gpu, oracle, "C1", policy=oracle.LITERAL)
+    for i in range(25):
+        g.project(step)
+        o.project(step)
+        ra, rb = g.update(contacts), o.update(contacts)
+        assert ra.resampled == rb.resampled and ra.data_particles == rb.data_particles
+        if ra.resampled:
+            assert np.array_equal(g.getAncestors(), o.getAncestors())        # bit-exact indices
+        a, b = g.getParticles(), o.getParticles()
+        np.testing.assert_allclose(a["weight"], b["weight"], rtol=1e-5, atol=0)
+        for k in ("x", "y", "theta", "zpos"):
+            np.testing.assert_allclose(a[k], b[k], rtol=0, atol=1e-6)
+        assert np.array_equal(a["n_found"], b["n_found"])
+
+
+# ---------------------------------------------------------------------------------- stage: resampling (exact running sum)
+def weight_cases(n, rng):
+    yield "uniform", np.full(n, 1.0 / n)
+    w = rng.random(n); yield "random", w / w.sum()
+    w = rng.random(n) ** 20; yield "peaked", w / w.sum()
+    w = np.exp(rng.normal(size=n) * 8); yield "lognormal", w / w.sum()
+    w = rng.random(n); w[rng.random(n) < 0.5] = 0; w[0] = 0; yield "half zeros", w / w.sum()
+    w = 2.0 ** -rng.integers(1, 60, size=n).astype(float); yield "dyadic (ties)", w / 2 ** np.ceil(np.log2(w.sum()))
+    w = rng.random(n) * 1e-18; w[n // 2] = 1.0; yield "one heavy", w
+    w = rng.random(n); yield "unnormalised", w * 3.7
+    w = np.full(n, 2.0 ** -53); w[0] = 0.5; yield "all ties at a binade edge (sequential fallback)", w
+    w = np.zeros(n); yield "all zero", w
+
+
+@pytest.mark.parametrize("n", [1, 2, 250, 1024, 1025, 5000, 200000])
+def test_resample_stage_bit_exact(gpu, oracle, n):
+    """Identical weights in -> the reference's left-to-right running sum, bit for bit, and identical ancestors."""
+    rng = np.random.default_rng(n)
+    for name, w in weight_cases(n, rng):
+        g = gpu()
+        o = oracle.OraclePoseEstimator(abi.default_config(), policy=oracle.LITERAL)
+        z = np.zeros(n)
+        xs = np.arange(n, dtype=np.float64)
+        for f in (g, o):
+            f.setParticles(x=xs, y=z, theta=z, zpos=z, zsigma=z + 1, weight=w)
+            f.resample()
+        assert np.array_equal(g.getCdf(), np.cumsum(w)), "%s: running sum" % name      # numpy cumsum is sequential
+        anc = g.getAncestors()
+        assert np.array_equal(anc, o.getAncestors()), "%s: ancestors" % name
+        p = g.getParticles()
+        assert np.array_equal(p["x"], xs[anc]) and np.array_equal(p["weight"], w[anc])  # copies keep their weight (Q3)
+
+
+def test_normalize_centroid_best_index(gpu, oracle):
+    n = 3000
+    rng = np.random.default_rng(5)
+    x, y, th, z = rng.normal(size=(4, n))
+    w = rng.random(n); w[1234] = 3.0
+    g, o = gpu(), oracle.OraclePoseEstimator(abi.default_config(), policy=oracle.SHARED)
+    for f in (g, o):
+        f.setParticles(x=x, y=y, theta=th, zpos=z, zsigma=np.ones(n), weight=w)
+    assert g.getBestParticleIndex() == o.getBestParticleIndex() == 1234
+    assert g.normalizeWeights() == o.normalizeWeights()
+    assert np.array_equal(g.getParticles()["weight"], o.getParticles()["weight"])
+    assert np.array_equal(g.getCentroid(), o.getCentroid())
+    # all-zero weights -> uniform (Q8)
+    g.setParticles(weight=np.zeros(n))
+    assert g.normalizeWeights() == pytest.approx(n)
+    assert np.all(g.getParticles()["weight"] == 1.0 / n)
+
+
+# ---------------------------------------------------------------------------------- BASELINE full size (C3)
+def test_full_size_step_matches_oracle_and_properties(gpu, oracle):
+    """One step of C3 (1,048,576 particles x 64 contact points, 2048^2 grid, resampling forced): every particle
+    bit-identical to the SHARED oracle; then size-independent properties on further steps."""
+    n = synthetic.WORKLOADS["C3"]["n"]
+    g, o, contacts, step = pair(gpu, oracle, "C3", min_effective=n + 1)
+    ra, rb = g.stepFused(step, contacts), None
+    o.project(step)
+    rb = o.update(contacts)
+    assert ra.as_dict() == rb.as_dict()
+    assert ra.resampled == 1
+    anc = g.getAncestors()
+    assert np.array_equal(anc, o.getAncestors())
+    assert_particles_equal(g.getParticles(), o.getParticles())
+    for _ in range(3):
+        before_w = None
+        r = g.stepFused(step, contacts)
+        assert r.resampled == 1 and 1.0 <= r.ess <= n
+        anc = g.getAncestors().astype(np.int64)
+        assert np.all(np.diff(anc) >= 0) and anc[0] >= 0 and anc[-1] < n       # sortedness
+        cdf = g.getCdf()
+        assert np.all(np.diff(cdf) >= 0) and abs(cdf[-1] - 1.0) < 1e-9          # normalised running sum
+        counts = np.bincount(anc, minlength=n)
+        w = np.diff(np.concatenate(([0.0], cdf))) * n
+        assert np.all(counts <= np.ceil(w) + 1) and np.all(counts >= np.floor(w) - 1)   # stratified offspring bounds
+        assert counts.sum() == n
