@@ -170,6 +170,9 @@ int eslam_gpu_patch_update(eslam_gpu_ctx* ctx);
 int eslam_gpu_get_patches(eslam_gpu_ctx* ctx, float* cells_mean_stdev, int32_t* origin_xy);
 
 int eslam_gpu_synchronize(eslam_gpu_ctx* ctx);
+/* diagnostics of the exact running-sum machinery: out = {sequential-fallback runs, boundary elements of the last
+ * resample, pending error flags, resamples done} */
+int eslam_gpu_debug_counters(eslam_gpu_ctx* ctx, uint64_t out[4]);
 /* number of kernels this library has launched on ctx since creation (bench "gpu_launches") */
 uint64_t eslam_gpu_launch_count(const eslam_gpu_ctx* ctx);
 

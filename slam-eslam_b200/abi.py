@@ -140,6 +140,7 @@ GPU_ONLY = {
     "run_steps": (C.c_int, [C.c_void_p, C.POINTER(Step), C.POINTER(Contact), C.c_int, C.c_int,
                             C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(UpdateResult)]),
     "synchronize": (C.c_int, [C.c_void_p]),
+    "debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "launch_count": (C.c_uint64, [C.c_void_p]),
 }
 

@@ -30,7 +30,7 @@ struct eslam_gpu_ctx {
     unsigned n_tiles, tile_cap;
     TilePartA* part_a; double *tile_sum, *tile_sq, *tile_prefix, *scratch_a, *scratch_b, *tile_sin, *sb, *cent_part, *best_w;
     unsigned long long* best_idx;
-    TileDesc* desc; int* tile_bofs; SegF* tile_pre;
+    TileDesc* desc; BndEntry* pool; int* tile_bofs; SegF* tile_pre;
     // map
     float2* cells; MapParams map; bool has_map;
     em::dbl2* htab;
@@ -64,7 +64,7 @@ static void free_particles(eslam_gpu_ctx* ctx) {
     cudaFree(ctx->part_a); cudaFree(ctx->tile_sum); cudaFree(ctx->tile_sq); cudaFree(ctx->tile_prefix);
     cudaFree(ctx->scratch_a); cudaFree(ctx->scratch_b); cudaFree(ctx->tile_sin); cudaFree(ctx->sb);
     cudaFree(ctx->cent_part); cudaFree(ctx->best_w); cudaFree(ctx->best_idx);
-    cudaFree(ctx->desc); cudaFree(ctx->tile_bofs); cudaFree(ctx->tile_pre);
+    cudaFree(ctx->desc); cudaFree(ctx->pool); cudaFree(ctx->tile_bofs); cudaFree(ctx->tile_pre); ctx->pool = nullptr;
     ctx->part_a = nullptr; ctx->tile_sum = ctx->tile_sq = ctx->tile_prefix = ctx->scratch_a = ctx->scratch_b = nullptr;
     ctx->tile_sin = ctx->sb = ctx->cent_part = ctx->best_w = nullptr; ctx->best_idx = nullptr;
     ctx->desc = nullptr; ctx->tile_bofs = nullptr; ctx->tile_pre = nullptr;
@@ -86,7 +86,7 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
         CK(dalloc(&ctx->tile_prefix, t)); CK(dalloc(&ctx->scratch_a, t)); CK(dalloc(&ctx->scratch_b, t));
         CK(dalloc(&ctx->tile_sin, t)); CK(dalloc(&ctx->sb, (size_t)MAX_BND_TOTAL)); CK(dalloc(&ctx->cent_part, 5 * (size_t)t));
         CK(dalloc(&ctx->best_w, t)); CK(dalloc(&ctx->best_idx, t));
-        CK(dalloc(&ctx->desc, t)); CK(dalloc(&ctx->tile_bofs, t)); CK(dalloc(&ctx->tile_pre, t));
+        CK(dalloc(&ctx->desc, t)); CK(dalloc(&ctx->pool, (size_t)MAX_BND_TOTAL)); CK(dalloc(&ctx->tile_bofs, t)); CK(dalloc(&ctx->tile_pre, t));
         ctx->cap = n; ctx->tile_cap = t;
     }
     ctx->n = n; ctx->n_tiles = (unsigned)((n + TILE - 1) / TILE);
@@ -170,7 +170,7 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     memset(&ctx->st, 0, sizeof(ctx->st));
     ctx->ancestors = nullptr; ctx->cdf = nullptr; ctx->part_a = nullptr;
     ctx->tile_sum = ctx->tile_sq = ctx->tile_prefix = ctx->scratch_a = ctx->scratch_b = ctx->tile_sin = ctx->sb = nullptr;
-    ctx->cent_part = ctx->best_w = nullptr; ctx->best_idx = nullptr; ctx->desc = nullptr; ctx->tile_bofs = nullptr;
+    ctx->cent_part = ctx->best_w = nullptr; ctx->best_idx = nullptr; ctx->desc = nullptr; ctx->pool = nullptr; ctx->tile_bofs = nullptr;
     ctx->tile_pre = nullptr; ctx->cells = nullptr; ctx->has_map = false; ctx->project_step = 0;
     memset(&ctx->map, 0, sizeof(ctx->map));
     *out = ctx;
@@ -330,10 +330,10 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     LAUNCHED();
     k_reduce_b<<<1, 1024, 0, ctx->stream>>>(ctx->tile_sum, T, n, ctx->sc, ctx->scratch_a, ctx->scratch_b, ctx->tile_prefix, normalise);
     LAUNCHED();
-    k_norm_scan<<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ng, ctx->tile_prefix, ctx->tile_sq, ctx->desc, normalise, eps);
+    k_norm_scan<<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ng, ctx->tile_prefix, ctx->tile_sq, ctx->desc, ctx->pool, ctx->sc, normalise, eps);
     LAUNCHED();
     const int decide = mode == 0 ? 0 : 1;
-    k_chain<<<1, 1024, sizeof(ChainSmem), ctx->stream>>>(ctx->desc, T, ctx->tile_sq, ctx->sc, ctx->scratch_a, ctx->scratch_b,
+    k_chain<<<1, 1024, sizeof(ChainSmem), ctx->stream>>>(ctx->desc, ctx->pool, T, ctx->tile_sq, ctx->sc, ctx->scratch_a, ctx->scratch_b,
                                                          ctx->tile_bofs, ctx->tile_pre, ctx->tile_sin, ctx->sb,
                                                          mode == 2 ? 0ull : ctx->cfg.min_effective, decide, force);
     LAUNCHED();
@@ -566,6 +566,16 @@ int eslam_gpu_evaluate_poses(eslam_gpu_ctx* ctx, uint64_t n, const double* x, co
         ctx->error = "using a zero measurement variance leads to singularities";
         return ESLAM_ERR_ZERO_VARIANCE;
     }
+    return ESLAM_OK;
+}
+
+int eslam_gpu_debug_counters(eslam_gpu_ctx* ctx, uint64_t out[4]) {
+    if (!ctx || !out) return ESLAM_ERR_INVALID;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return ESLAM_ERR_CUDA;
+    int st = read_scalars(ctx);
+    if (st != ESLAM_OK) return st;
+    out[0] = ctx->sc_host->fallbacks; out[1] = (uint64_t)ctx->sc_host->n_boundaries;
+    out[2] = (uint64_t)ctx->sc_host->error_flags; out[3] = ctx->sc_host->resample_step;
     return ESLAM_OK;
 }
 

@@ -27,8 +27,7 @@ namespace em = eslam_math;
 
 #define TILE 1024                // particles per reduction tile (fixed: defines the summation tree)
 #define WT_THREADS 512           // threads of the fused project+weight kernel (2 particles each per tile)
-#define MAX_BND_PER_TILE 8       // boundary elements a tile descriptor can hold
-#define MAX_BND_TOTAL 2048       // boundary elements the chain kernel can walk
+#define MAX_BND_TOTAL 2048       // boundary elements per resample (pool + chain capacity); more -> sequential fallback
 #define BIN_NONE (-100000)       // "no binade": piece made of zero / sub-quarter-ulp weights only
 #define ERR_ZERO_VARIANCE_BIT 1
 #define ERR_CDF_FALLBACK_BIT 2
@@ -56,6 +55,8 @@ struct DevScalars {              // device-resident scalars of one context
     int uniform;                 // sum of weights <= 0 -> 1/N (Q8)
     int error_flags;
     int n_boundaries;
+    int pool_count;              // boundary-element pool allocator (reset by k_reduce_b)
+    unsigned int fallbacks;      // times the sequential CDF fallback ran
 };
 
 struct TilePartA {               // per-tile partials of loop A
@@ -96,11 +97,12 @@ struct WeightParams {
     ContactSet cs;
 };
 
+struct BndEntry { double w; int idx, b; long long d0, d1; };   // a boundary element and the rounding function of the run after it
 struct TileDesc {                // what a tile contributes to the exact running sum (see DESIGN.md "exact CDF")
     int n_bnd, overflow;
     int head_b, pad;
     long long head_d0, head_d1;  // rounding function of the elements before the tile's first boundary element
-    struct { double w; int idx, b; long long d0, d1; } bnd[MAX_BND_PER_TILE];
+    int bnd_base, pad2;          // the tile's n_bnd boundary elements live at pool[bnd_base ..]
 };
 
 struct SegF { long long d0, d1; int b; int pad; };   // 2-state rounding function of a run of interior elements
@@ -524,7 +526,7 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_b(const double* tile_sum, un
     __syncthreads();
     const double total = block_tree_reduce(scratch_a, scratch_b, n_tiles);
     const int uniform = normalise && (total <= 0.0);                                 // :51 (Q8)
-    if (threadIdx.x == 0) { if (normalise) sc->sum_w = total; sc->uniform = uniform; }
+    if (threadIdx.x == 0) { if (normalise) sc->sum_w = total; sc->uniform = uniform; sc->pool_count = 0; }
     // exclusive scan of the per-tile masses (approximate is enough: only used to classify elements)
     const unsigned per = (n_tiles + blockDim.x - 1) / blockDim.x;
     const unsigned lo = threadIdx.x * per, hi = min(lo + per, n_tiles);
@@ -673,10 +675,12 @@ __device__ __forceinline__ TileScan tile_scan(double w, bool active, double tile
 // normalise (src/ParticleFilter.hpp:51-67), per-tile sum of w^2, and the tile descriptors of the exact running sum
 __global__ void __launch_bounds__(1024, 1) k_norm_scan(StateBufs st, const DevScalars* sc, unsigned long long n,
                                                        unsigned long long n_global, const double* tile_prefix,
-                                                       double* tile_sq, TileDesc* desc, int normalise, double eps) {
+                                                       double* tile_sq, TileDesc* desc, BndEntry* pool, DevScalars* scw, int normalise,
+                                                       double eps) {
     __shared__ TileScanSmem sm;
     __shared__ double red[32];
     __shared__ int slot_of[TILE];
+    __shared__ int s_base;
     const int cur = sc->cur;
     const unsigned long long i = (unsigned long long)blockIdx.x * TILE + threadIdx.x;
     const bool active = i < n;
@@ -696,12 +700,16 @@ __global__ void __launch_bounds__(1024, 1) k_norm_scan(StateBufs st, const DevSc
     TileDesc* D = &desc[blockIdx.x];
     slot_of[threadIdx.x] = ts.bnd_before;
     if (threadIdx.x == 0) {
-        D->n_bnd = ts.bnd_total; D->overflow = ts.bnd_total > MAX_BND_PER_TILE;
+        int base = 0;
+        if (ts.bnd_total > 0) base = atomicAdd(&scw->pool_count, ts.bnd_total);
+        s_base = base;
+        D->n_bnd = ts.bnd_total; D->overflow = (base + ts.bnd_total > MAX_BND_TOTAL) ? 1 : 0; D->bnd_base = base; D->pad2 = 0;
         D->head_b = BIN_NONE; D->head_d0 = 0; D->head_d1 = 0; D->pad = 0;
     }
     __syncthreads();
-    if (ts.bnd_total <= MAX_BND_PER_TILE) {
-        if (ts.cls.kind == 2) { D->bnd[ts.bnd_before].w = w; D->bnd[ts.bnd_before].idx = (int)threadIdx.x; }
+    if (s_base + ts.bnd_total <= MAX_BND_TOTAL) {
+        BndEntry* B = pool + s_base;
+        if (ts.cls.kind == 2) { B[ts.bnd_before].w = w; B[ts.bnd_before].idx = (int)threadIdx.x; }
         // piece ends: the next element is a boundary, or this is the last element of the tile
         const int next_kind = __shfl_down_sync(0xffffffffu, ts.cls.kind, 1);
         __shared__ int first_kind[32];
@@ -713,7 +721,7 @@ __global__ void __launch_bounds__(1024, 1) k_norm_scan(StateBufs st, const DevSc
             if (ts.inc.head < 0) { D->head_b = ts.inc.f.b; D->head_d0 = ts.inc.f.d0; D->head_d1 = ts.inc.f.d1; D->pad = ts.inc.f.pad; }
             else {
                 const int s = slot_of[ts.inc.head];
-                D->bnd[s].b = ts.inc.f.b; D->bnd[s].d0 = ts.inc.f.d0; D->bnd[s].d1 = ts.inc.f.d1;
+                B[s].b = ts.inc.f.b; B[s].d0 = ts.inc.f.d0; B[s].d1 = ts.inc.f.d1;
                 if (ts.inc.f.pad) D->overflow = 1;
             }
         }
@@ -723,7 +731,7 @@ __global__ void __launch_bounds__(1024, 1) k_norm_scan(StateBufs st, const DevSc
 // one CTA: ESS, resample decision, and the exact value of the running sum at every tile start / boundary element
 struct ChainSmem { double bw[MAX_BND_TOTAL]; SegF seg[MAX_BND_TOTAL]; };
 
-__global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, unsigned n_tiles, const double* tile_sq,
+__global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, const BndEntry* pool, unsigned n_tiles, const double* tile_sq,
                                                    DevScalars* sc, double* scratch_a, double* scratch_b,
                                                    int* tile_bofs, SegF* tile_pre, double* tile_sin, double* sb_out,
                                                    unsigned long long min_effective, int decide, int force) {
@@ -759,7 +767,8 @@ __global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, unsigne
         cnt += D.n_bnd;
         SegE e;
         if (D.n_bnd > 0 && !D.overflow) {
-            const int l = D.n_bnd - 1; e.head = (int)t; e.f.b = D.bnd[l].b; e.f.d0 = D.bnd[l].d0; e.f.d1 = D.bnd[l].d1; e.f.pad = 0;
+            const BndEntry& L = pool[D.bnd_base + D.n_bnd - 1];
+            e.head = (int)t; e.f.b = L.b; e.f.d0 = L.d0; e.f.d1 = L.d1; e.f.pad = 0;
         } else { e.head = -1; e.f.b = D.head_b; e.f.d0 = D.head_d0; e.f.d1 = D.head_d1; e.f.pad = D.pad; }
         agg = sege_combine(agg, e);
     }
@@ -787,9 +796,10 @@ __global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, unsigne
         const TileDesc& D = desc[t];
         tile_bofs[t] = run_c; tile_pre[t] = run_e.f;
         // boundary k = run_c + j: weight, and the function of the segment that follows it
+        const BndEntry* B = pool + D.bnd_base;
         for (int j = 0; j < D.n_bnd; ++j) {
-            cs.bw[run_c + j] = D.bnd[j].w;
-            if (j + 1 < D.n_bnd) { SegF f; f.b = D.bnd[j].b; f.d0 = D.bnd[j].d0; f.d1 = D.bnd[j].d1; f.pad = 0; cs.seg[run_c + j] = f; }
+            cs.bw[run_c + j] = B[j].w;
+            if (j + 1 < D.n_bnd) { SegF f; f.b = B[j].b; f.d0 = B[j].d0; f.d1 = B[j].d1; f.pad = 0; cs.seg[run_c + j] = f; }
         }
         if (D.n_bnd > 0 && run_c > 0) {
             // segment after boundary run_c-1 ends with this tile's head piece
@@ -797,7 +807,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, unsigne
             cs.seg[run_c - 1] = segf_compose(run_e.f, hf);
         }
         SegE e;
-        if (D.n_bnd > 0) { const int l = D.n_bnd - 1; e.head = (int)t; e.f.b = D.bnd[l].b; e.f.d0 = D.bnd[l].d0; e.f.d1 = D.bnd[l].d1; e.f.pad = 0; }
+        if (D.n_bnd > 0) { const BndEntry& L = B[D.n_bnd - 1]; e.head = (int)t; e.f.b = L.b; e.f.d0 = L.d0; e.f.d1 = L.d1; e.f.pad = 0; }
         else { e.head = -1; e.f.b = D.head_b; e.f.d0 = D.head_d0; e.f.d1 = D.head_d1; e.f.pad = D.pad; }
         run_e = sege_combine(run_e, e);
         run_c += D.n_bnd;
@@ -857,6 +867,7 @@ __global__ void k_cdf_sequential(StateBufs st, DevScalars* sc, unsigned long lon
     double s = 0.0;
     for (unsigned long long i = 0; i < n; ++i) { s = (i == 0) ? w[0] : s + w[i]; cdf[i] = s; }
     sc->error_flags &= ~ERR_CDF_FALLBACK_BIT;
+    sc->fallbacks += 1;
 }
 
 // ------------------------------------------------------------------------------------------------ resample

@@ -208,5 +208,11 @@ class GpuPoseEstimator(FilterBase):
     def synchronize(self):
         self._check(self._lib.eslam_gpu_synchronize(self._ctx))
 
+    def debugCounters(self):
+        """{fallbacks, boundaries, error_flags, resamples} of the exact running-sum machinery."""
+        out = (C.c_uint64 * 4)()
+        self._check(self._lib.eslam_gpu_debug_counters(self._ctx, out))
+        return dict(fallbacks=int(out[0]), boundaries=int(out[1]), error_flags=int(out[2]), resamples=int(out[3]))
+
     def launchCount(self):
         return int(self._lib.eslam_gpu_launch_count(self._ctx))

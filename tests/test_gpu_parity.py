@@ -208,7 +208,8 @@ def weight_cases(n, rng):
     w = rng.random(n); yield "random", w / w.sum()
     w = rng.random(n) ** 20; yield "peaked", w / w.sum()
     w = np.exp(rng.normal(size=n) * 8); yield "lognormal", w / w.sum()
-    w = rng.random(n); w[rng.random(n) < 0.5] = 0; w[0] = 0; yield "half zeros", w / w.sum()
+    w = rng.random(n); w[rng.random(n) < 0.5] = 0; w[0] = 0
+    if w.sum() > 0: yield "half zeros", w / w.sum()
     w = 2.0 ** -rng.integers(1, 60, size=n).astype(float); yield "dyadic (ties)", w / 2 ** np.ceil(np.log2(w.sum()))
     w = rng.random(n) * 1e-18; w[n // 2] = 1.0; yield "one heavy", w
     w = rng.random(n); yield "unnormalised", w * 3.7
@@ -233,6 +234,10 @@ def test_resample_stage_bit_exact(gpu, oracle, n):
         assert np.array_equal(anc, o.getAncestors()), "%s: ancestors" % name
         p = g.getParticles()
         assert np.array_equal(p["x"], xs[anc]) and np.array_equal(p["weight"], w[anc])  # copies keep their weight (Q3)
+        if name in ("uniform", "random", "peaked", "lognormal", "half zeros", "unnormalised", "one heavy"):
+            assert g.debugCounters()["fallbacks"] == 0, "%s took the sequential fallback (%r)" % (name, g.debugCounters())
+        if "fallback" in name and n > 4096:
+            assert g.debugCounters()["fallbacks"] == 1
 
 
 def test_normalize_centroid_best_index(gpu, oracle):
@@ -279,3 +284,4 @@ def test_full_size_step_matches_oracle_and_properties(gpu, oracle):
         w = np.diff(np.concatenate(([0.0], cdf))) * n
         assert np.all(counts <= np.ceil(w) + 1) and np.all(counts >= np.floor(w) - 1)   # stratified offspring bounds
         assert counts.sum() == n
+    assert g.debugCounters()["fallbacks"] == 0 and g.debugCounters()["resamples"] == 4
