@@ -26,7 +26,7 @@
 namespace em = eslam_math;
 
 #define TILE 1024                // particles per reduction tile (fixed: defines the summation tree)
-#define WT_THREADS 512           // threads of the fused project+weight kernel (2 particles each per tile)
+#define WT_THREADS 1024          // threads of the fused project+weight kernel (one particle each per tile)
 #define MAX_BND_TOTAL 2048       // boundary elements per resample (pool + chain capacity); more -> sequential fallback
 #define BIN_NONE (-100000)       // "no binade": piece made of zero / sub-quarter-ulp weights only
 #define ERR_ZERO_VARIANCE_BIT 1
@@ -191,6 +191,8 @@ __device__ __forceinline__ bool cell_lookup(const MapParams& M, const MapTile& m
 struct PoseEval { int n_found; double d1, d2, A, poseVar; };
 
 // ContactModel::evaluatePose (src/ContactModel.cpp:117-224) for one pose; SHARED arithmetic policy.
+// Written straight-line: every lane computes every evaluated contact, lanes whose group is already invalid are masked
+// out of the accumulation; the rare cases (cell-border quotient, variance or t outside the table) take one slow branch.
 template <bool TAP>
 __device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapParams& M, const MapTile& mt,
                                              const em::dbl2* htab, double inv_corr,
@@ -201,54 +203,72 @@ __device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapPara
     double pt_x = 0, pt_y = 0, pt_z = 0;
     out.n_found = 0; out.d1 = 0; out.d2 = 0; out.A = 0; out.poseVar = 0;
     const int n = cs.n;
+    const double MAGIC = 25769803776.0;                                  // 1.5 * 2^34: 18 fractional bits
+    const int FRAC_MASK = (1 << IDX_FRAC_BITS) - 1;
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
         const unsigned f = cs.flags[i];
         if (TAP) tap_cells[i] = -1;
-        if ((f & 1u) && group_valid) {                                    // :154
+        if (f & 1u) {                                                    // :154 !(contact < 0.2): warp-uniform
             const double px = cs.px[i], py = cs.py[i];
             const double wx = em::fma_(c, px, em::fma_(-s, py, x));      // :147
             const double wy = em::fma_(s, px, em::fma_(c, py, y));
             const double wz = z + cs.pzr[i];
-            float2 cell; int flat = -1;
-            bool hit = cell_lookup(M, mt, wx, wy, wz, cell, flat);       // :156
-            if (TAP) tap_cells[i] = flat;
-            if (hit) {
-                hit = false;
-                if (cell.x == cell.x) {                                  // NaN mean = empty cell
-                    const double d = wz - (double)cell.x;                // :160
-                    const double sp2 = (double)cell.y * (double)cell.y;  // :166
-                    const double zvar = sp2 + mv;                        // :167
-                    if (d * d < 9.0 * zvar) {                            // 3-sigma patch gate of MLSMap::getPatch
-                        hit = true;
-                        const double ratio = em::likelihood_ratio(d, zvar, inv_corr, htab);   // :170
-                        if (!valid) {                                    // :172-177
-                            acc_d = d * ratio; acc_v = zvar * ratio; acc_r = ratio; acc_p = sp2 * ratio;
-                            if (TAP) { pt_x = wx; pt_y = wy; pt_z = (double)cell.x; }
-                        } else {                                         // :178-184
-                            acc_d = em::fma_(d, ratio, acc_d); acc_v = em::fma_(zvar, ratio, acc_v);
-                            acc_r += ratio; acc_p = em::fma_(sp2, ratio, acc_p);
-                        }
-                        valid = true;
-                    }
-                }
+            double gx = wx, gy = wy;
+            if (!M.identity) {                                           // C_global2local, src/PoseEstimator.hpp:101
+                gx = em::fma_(M.g2l[0], wx, em::fma_(M.g2l[1], wy, em::fma_(M.g2l[2], wz, M.g2l[3])));
+                gy = em::fma_(M.g2l[4], wx, em::fma_(M.g2l[5], wy, em::fma_(M.g2l[6], wz, M.g2l[7])));
             }
-            if (!hit) group_valid = false;                               // :189-190
+            // cell index floor((g - offset)/scale): reciprocal multiply + floor from the mantissa (see axis_index)
+            const uint64_t ux = em::d2u((gx - M.ox) * M.inv_sx + MAGIC), uy = em::d2u((gy - M.oy) * M.inv_sy + MAGIC);
+            const int kx = (int)(uint32_t)ux, ky = (int)(uint32_t)uy;
+            int ix = kx >> IDX_FRAC_BITS, iy = ky >> IDX_FRAC_BITS;
+            const bool fast = (((uint32_t)(ux >> 32) - 0x4217FFFFu) <= 1u) & ((kx & FRAC_MASK) != 0) &
+                              (((uint32_t)(uy >> 32) - 0x4217FFFFu) <= 1u) & ((ky & FRAC_MASK) != 0);
+            bool inb = ((unsigned)ix < (unsigned)M.W) & ((unsigned)iy < (unsigned)M.H);
+            if (!fast) {                                                 // rare: exact IEEE division
+                inb = em::cell_index_exact(gx, M.ox, M.sx, M.W, ix);
+                if (inb) inb = em::cell_index_exact(gy, M.oy, M.sy, M.H, iy);
+            }
+            const int flat = inb ? iy * M.W + ix : 0;
+            const unsigned lx = (unsigned)(ix - mt.x0), ly = (unsigned)(iy - mt.y0);
+            const bool in_tile = inb & (lx < (unsigned)mt.w) & (ly < (unsigned)mt.h);
+            const float2* src = in_tile ? (mt.s + ly * mt.w + lx) : (M.cells + flat);
+            const float2 cell = *src;                                    // generic load: shared tile or global (L2)
+            if (TAP) tap_cells[i] = (inb && group_valid) ? flat : -1;
+            const double d = wz - (double)cell.x;                        // :160
+            const double sp2 = (double)cell.y * (double)cell.y;          // :166
+            const double zvar = sp2 + mv;                                // :167
+            // map hit: inside the grid, cell not empty (NaN mean), 3-sigma patch gate of MLSMap::getPatch
+            const bool use = group_valid & inb & (cell.x == cell.x) & (d * d < 9.0 * zvar);
+            bool rare;
+            double ratio = em::likelihood_ratio_fast(d, zvar, inv_corr, htab, rare);           // :170
+            if (rare & use) ratio = em::likelihood_ratio(d, zvar, inv_corr, htab);
+            if (use) {                                                   // :172-185
+                if (TAP && !valid) { pt_x = wx; pt_y = wy; pt_z = (double)cell.x; }
+                acc_d = em::fma_(d, ratio, acc_d); acc_v = em::fma_(zvar, ratio, acc_v);
+                acc_r += ratio; acc_p = em::fma_(sp2, ratio, acc_p);
+                valid = true;
+            } else {
+                group_valid = false;                                     // :189-190 (stays false if it already was)
+            }
         }
-        if (valid && (f & 2u)) {                                         // :194-197 end of group
-            if (group_valid && acc_r > 1e-9) {                           // :199
-                const double zd = acc_d / acc_r, zv = acc_v / acc_r;     // :201-202
-                out.poseVar += acc_p / acc_r;                            // :203
-                const double e = zd / zv;
-                out.d1 += e; out.d2 += 1.0 / zv; out.A = em::fma_(zd, e, out.A);
-                if (TAP && out.n_found < ESLAM_MAX_CP) {
-                    double* o = tap_cp + out.n_found * 5;
-                    o[0] = pt_x; o[1] = pt_y; o[2] = pt_z; o[3] = zd; o[4] = zv;
+        if (f & 2u) {                                                    // :194-197 end of group: warp-uniform
+            if (valid) {
+                if (group_valid && acc_r > 1e-9) {                       // :199
+                    const double zd = acc_d / acc_r, zv = acc_v / acc_r; // :201-202
+                    out.poseVar += acc_p / acc_r;                        // :203
+                    const double e = zd / zv;
+                    out.d1 += e; out.d2 += 1.0 / zv; out.A = em::fma_(zd, e, out.A);
+                    if (TAP && out.n_found < ESLAM_MAX_CP) {
+                        double* o = tap_cp + out.n_found * 5;
+                        o[0] = pt_x; o[1] = pt_y; o[2] = pt_z; o[3] = zd; o[4] = zv;
+                    }
+                    out.n_found++;
                 }
-                out.n_found++;
+                group_valid = true; valid = false;                       // :210-213 (only when valid: Q4)
+                acc_d = acc_v = acc_r = acc_p = 0;
             }
-            group_valid = true; valid = false;                           // :210-213 (only when valid: Q4)
-            acc_d = acc_v = acc_r = acc_p = 0;
         }
     }
 }
@@ -360,90 +380,80 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_c
 
     const unsigned n_tiles = (unsigned)((P.n + TILE - 1) / TILE);
     for (unsigned t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        double r_pw[2], r_mx[2], r_x[2], r_y[2]; unsigned r_cnt[2], r_pts[2];
-#pragma unroll 1
-        for (int r = 0; r < 2; ++r) {
-            const unsigned long long i = (unsigned long long)t * TILE + r * WT_THREADS + tid;
-            double v_pw = 0, v_mx = 0, v_x = 0, v_y = 0; unsigned v_cnt = 0, v_pts = 0;
-            if (i < P.n) {
-                double x = X[i], y = Y[i], th = TH[i], z = Z[i], zs = ZS[i], w = WG[i];
-                if (DO_PROJECT) {                                                    // :196-237
-                    const unsigned long long gi = P.base + i;
-                    const uint32_t sw = stream_word(em::STREAM_PROJECT, gi);
-                    double n0, n1, n2, unused;
-                    normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 0, sw, P.mp.k0, P.mp.k1), n0, n1);
-                    normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 1, sw, P.mp.k0, P.mp.k1), n2, unused);
-                    const double dx = P.dmean[0] + P.dsigma[0] * n0;                 // :198
-                    double dy = P.dmean[1] + P.dsigma[1] * n1;
-                    const double dth = P.dmean[2] + P.dsigma[2] * n2;
-                    const em::Philox4 u = em::philox4x32_10((uint32_t)gi, P.project_step, 2, sw, P.mp.k0, P.mp.k1);
-                    if (em::u01(u.v[0], u.v[1]) < P.mp.slip_factor) dy *= em::u01(u.v[2], u.v[3]);   // :199-202
-                    double s, c; em::sincos_(th, s, c);
-                    x += c * dx - s * dy;                                            // :205
-                    y += s * dx + c * dy;
-                    th += dth;                                                       // :206
-                    if (P.mp.max_yaw_dev > 0.0) {                                    // :208-216
-                        if (fabs(th - P.yaw) > P.mp.max_yaw_dev) w *= 0.7;
-                    }
-                    z += P.z_delta;                                                  // :218
-                    zs = em::sqrt_(zs * zs + P.z_var);                               // :219
-                    if (spread > 0 && !P.mp.use_hash) {                              // :224-236
-                        const double trans_fac = P.mp.spread_tf * spread, rot_fac = P.mp.spread_rf * spread;
-                        double sx, sy, sth;
-                        normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 3, sw, P.mp.k0, P.mp.k1), sx, sy);
-                        normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 4, sw, P.mp.k0, P.mp.k1), sth, unused);
-                        x += sx * trans_fac + 0.0;
-                        y += sy * trans_fac + 0.0;
-                        th += sth * rot_fac + 0.0;
-                    }
-                    X[i] = x; Y[i] = y; TH[i] = th;
-                    if (!DO_WEIGHT) { Z[i] = z; ZS[i] = zs; WG[i] = w; }
+        // one particle per thread: leaf index of the tile's summation tree == threadIdx.x
+        const unsigned long long i = (unsigned long long)t * TILE + tid;
+        double v_pw = 0, v_mx = 0, v_x = 0, v_y = 0; unsigned v_cnt = 0, v_pts = 0;
+        if (i < P.n) {
+            double x = X[i], y = Y[i], th = TH[i], z = Z[i], zs = ZS[i], w = WG[i];
+            if (DO_PROJECT) {                                                    // :196-237
+                const unsigned long long gi = P.base + i;
+                const uint32_t sw = stream_word(em::STREAM_PROJECT, gi);
+                double n0, n1, n2, unused;
+                normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 0, sw, P.mp.k0, P.mp.k1), n0, n1);
+                normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 1, sw, P.mp.k0, P.mp.k1), n2, unused);
+                const double dx = P.dmean[0] + P.dsigma[0] * n0;                 // :198
+                double dy = P.dmean[1] + P.dsigma[1] * n1;
+                const double dth = P.dmean[2] + P.dsigma[2] * n2;
+                const em::Philox4 u = em::philox4x32_10((uint32_t)gi, P.project_step, 2, sw, P.mp.k0, P.mp.k1);
+                if (em::u01(u.v[0], u.v[1]) < P.mp.slip_factor) dy *= em::u01(u.v[2], u.v[3]);   // :199-202
+                double s, c; em::sincos_(th, s, c);
+                x += c * dx - s * dy;                                            // :205
+                y += s * dx + c * dy;
+                th += dth;                                                       // :206
+                if (P.mp.max_yaw_dev > 0.0) {                                    // :208-216
+                    if (fabs(th - P.yaw) > P.mp.max_yaw_dev) w *= 0.7;
                 }
-                if (DO_WEIGHT) {                                                     // :276-327
-                    double s, c; em::sincos_(th, s, c);
-                    const double mv = zs * zs + P.mp.merr2;                          // :290
-                    if (mv == 0) atomicOr(&P.sc->error_flags, ERR_ZERO_VARIANCE_BIT);   // src/ContactModel.cpp:122-123
-                    PoseEval ev;
-                    contact_eval<false>(P.cs, P.map, mt, htab, P.mp.inv_corr, x, y, z, s, c, mv, ev, nullptr, nullptr);
-                    double mprob = 1.0; uint8_t floating = 1;                        // :316-317
-                    if ((unsigned long long)ev.n_found >= P.mp.min_contacts) {                     // ContactModel.cpp:217
-                        double weight, zdl, zvr;
-                        evaluate_weight(ev, P.mp.use_shape, weight, zdl, zvr);
-                        double zVar = zs * zs;                                       // :294
-                        update_z(ev, zdl, zvr, z, zVar);                             // :295
-                        zs = em::sqrt_(zVar);                                        // :296
-                        w *= weight;                                                 // :300 (Q1: first application)
-                        mprob = weight; floating = 0;
-                        v_mx = weight; v_cnt = 1; v_pts = (unsigned)ev.n_found;      // :305-310
-                        v_pw = em::root_n(weight, (unsigned long long)ev.n_found);   // :309
-                    }
-                    Z[i] = z; ZS[i] = zs; WG[i] = w; MPB[i] = mprob;
-                    FL[i] = floating; NF[i] = (uint8_t)min(ev.n_found, 255);         // :322 cpoints.size()
-                    v_x = x; v_y = y;
+                z += P.z_delta;                                                  // :218
+                zs = em::sqrt_(zs * zs + P.z_var);                               // :219
+                if (spread > 0 && !P.mp.use_hash) {                              // :224-236
+                    const double trans_fac = P.mp.spread_tf * spread, rot_fac = P.mp.spread_rf * spread;
+                    double sx, sy, sth;
+                    normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 3, sw, P.mp.k0, P.mp.k1), sx, sy);
+                    normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 4, sw, P.mp.k0, P.mp.k1), sth, unused);
+                    x += sx * trans_fac + 0.0;
+                    y += sy * trans_fac + 0.0;
+                    th += sth * rot_fac + 0.0;
                 }
+                X[i] = x; Y[i] = y; TH[i] = th;
+                if (!DO_WEIGHT) { Z[i] = z; ZS[i] = zs; WG[i] = w; }
             }
-            r_pw[r] = v_pw; r_mx[r] = v_mx; r_x[r] = v_x; r_y[r] = v_y; r_cnt[r] = v_cnt; r_pts[r] = v_pts;
+            if (DO_WEIGHT) {                                                     // :276-327
+                double s, c; em::sincos_(th, s, c);
+                const double mv = zs * zs + P.mp.merr2;                          // :290
+                if (mv == 0) atomicOr(&P.sc->error_flags, ERR_ZERO_VARIANCE_BIT);   // src/ContactModel.cpp:122-123
+                PoseEval ev;
+                contact_eval<false>(P.cs, P.map, mt, htab, P.mp.inv_corr, x, y, z, s, c, mv, ev, nullptr, nullptr);
+                double mprob = 1.0; uint8_t floating = 1;                        // :316-317
+                if ((unsigned long long)ev.n_found >= P.mp.min_contacts) {       // ContactModel.cpp:217
+                    double weight, zdl, zvr;
+                    evaluate_weight(ev, P.mp.use_shape, weight, zdl, zvr);
+                    double zVar = zs * zs;                                       // :294
+                    update_z(ev, zdl, zvr, z, zVar);                             // :295
+                    zs = em::sqrt_(zVar);                                        // :296
+                    w *= weight;                                                 // :300 (Q1: first application)
+                    mprob = weight; floating = 0;
+                    v_mx = weight; v_cnt = 1; v_pts = (unsigned)ev.n_found;      // :305-310
+                    v_pw = em::root_n(weight, (unsigned long long)ev.n_found);   // :309
+                }
+                Z[i] = z; ZS[i] = zs; WG[i] = w; MPB[i] = mprob;
+                FL[i] = floating; NF[i] = (uint8_t)min(ev.n_found, 255);         // :322 cpoints.size()
+                v_x = x; v_y = y;
+            }
         }
         if (DO_WEIGHT) {
-            // tile tree: leaf index = r*512 + tid; warp partial g = r*16 + warp covers leaves [32g, 32g+32)
+            // tile tree: xor butterfly in the warp (levels 0-4), then over the 32 warp partials (levels 5-9)
+            const double a = warp_tree_sum(v_pw), b = warp_max(v_mx);
+            const double cx = warp_tree_sum(v_x), cy = warp_tree_sum(v_y);
+            const unsigned c1 = warp_sum_u(v_cnt), c2 = warp_sum_u(v_pts);
             __syncthreads();
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const double a = warp_tree_sum(r_pw[r]), b = warp_max(r_mx[r]);
-                const double cx = warp_tree_sum(r_x[r]), cy = warp_tree_sum(r_y[r]);
-                const unsigned c1 = warp_sum_u(r_cnt[r]), c2 = warp_sum_u(r_pts[r]);
-                if (lane == 0) {
-                    const int g = r * (WT_THREADS / 32) + warp;
-                    red[g] = a; red[32 + g] = b; red[64 + g] = cx; red[96 + g] = cy; redu[g] = c1; redu[32 + g] = c2;
-                }
-            }
+            if (lane == 0) { red[warp] = a; red[32 + warp] = b; red[64 + warp] = cx; red[96 + warp] = cy; redu[warp] = c1; redu[32 + warp] = c2; }
             __syncthreads();
             if (warp == 0) {
-                const double a = warp_tree_sum(red[lane]), b = warp_max(red[32 + lane]);
-                const double cx = warp_tree_sum(red[64 + lane]), cy = warp_tree_sum(red[96 + lane]);
-                const unsigned c1 = warp_sum_u(redu[lane]), c2 = warp_sum_u(redu[32 + lane]);
+                const double a2 = warp_tree_sum(red[lane]), b2 = warp_max(red[32 + lane]);
+                const double cx2 = warp_tree_sum(red[64 + lane]), cy2 = warp_tree_sum(red[96 + lane]);
+                const unsigned c12 = warp_sum_u(redu[lane]), c22 = warp_sum_u(redu[32 + lane]);
                 if (lane == 0) {
-                    TilePartA o; o.sum_pw = a; o.max_w = b; o.sum_x = cx; o.sum_y = cy; o.cnt = c1; o.pts = c2;
+                    TilePartA o; o.sum_pw = a2; o.max_w = b2; o.sum_x = cx2; o.sum_y = cy2; o.cnt = c12; o.pts = c22;
                     P.part[t] = o;
                 }
             }

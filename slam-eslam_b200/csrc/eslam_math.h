@@ -257,8 +257,8 @@ ESLAM_HD void box_muller(double u1, double u2, double& n0, double& n1) {
 
 // ---------------------------------------------------------------- 1/sqrt
 // ~1.5 ulp, deterministic: fp32 magic seed + 3 fp32 Newton steps + one fp64 Halley step.
-ESLAM_HD double rsqrt_(double x) {
-    if (!(x > 1e-30 && x < 1e30)) return 1.0 / sqrt_(x);
+// rsqrt_core is valid for x in (1e-30, 1e30); rsqrt_ adds the out-of-range fallback.
+ESLAM_HD double rsqrt_core(double x) {
     float xf = (float)x;
     float y = u2f(0x5f3759dfu - (f2u(xf) >> 1));
     float hx = 0.5f * xf;
@@ -271,6 +271,11 @@ ESLAM_HD double rsqrt_(double x) {
     double e = fma_(-h, yd, 1.0);
     double p = fma_(0.375, e, 0.5);
     return fma_(yd, e * p, yd);
+}
+ESLAM_HD bool rsqrt_in_range(double x) { return x > 1e-30 && x < 1e30; }
+ESLAM_HD double rsqrt_(double x) {
+    if (!rsqrt_in_range(x)) return 1.0 / sqrt_(x);
+    return rsqrt_core(x);
 }
 
 // ---------------------------------------------------------------- inverse Mills ratio h(t) = phi(t)/Phi(t)
@@ -300,13 +305,16 @@ ESLAM_HD double h_slow(double t) {
     return f;
 }
 
-ESLAM_HD double h_ratio(double t, const dbl2* tab) {
-    if (!(t >= -ESLAM_H_TMAX && t < ESLAM_H_TMAX)) return h_slow(t);
-    double fi = fma_(t, (double)ESLAM_H_PER_UNIT, ESLAM_H_TMAX * ESLAM_H_PER_UNIT);
-    int j = (int)fi;                      // fi >= 0: truncation == floor
-    if (j > ESLAM_H_NINT - 1) j = ESLAM_H_NINT - 1;
-    double z = (fi - (double)j) - 0.5;
-    dbl2 c01 = tab[j], c23 = tab[ESLAM_H_NINT + j], c45 = tab[2 * ESLAM_H_NINT + j];
+ESLAM_HD bool h_in_range(double t) { return t >= -ESLAM_H_TMAX && t < ESLAM_H_TMAX; }
+// table evaluation, valid for h_in_range(t) (any other input reads a clamped interval: garbage, never out of bounds).
+// interval index and centred coordinate come from one magic-number rounding: no int<->double conversions.
+ESLAM_HD double h_core(double t, const dbl2* tab) {
+    const double t32 = fma_(t, (double)ESLAM_H_PER_UNIT, ESLAM_H_TMAX * ESLAM_H_PER_UNIT - 0.5);   // 32 t + 319.5
+    const double m = t32 + 6755399441055744.0;      // 1.5 * 2^52: low mantissa bits = rne(t32) = interval index
+    int j = (int)(uint32_t)d2u(m);
+    j = j < 0 ? 0 : (j > ESLAM_H_NINT - 1 ? ESLAM_H_NINT - 1 : j);
+    const double z = t32 - (m - 6755399441055744.0);   // in [-0.5, 0.5]
+    const dbl2 c01 = tab[j], c23 = tab[ESLAM_H_NINT + j], c45 = tab[2 * ESLAM_H_NINT + j];
     double p = c45.y;
     p = fma_(p, z, c45.x);
     p = fma_(p, z, c23.y);
@@ -315,6 +323,10 @@ ESLAM_HD double h_ratio(double t, const dbl2* tab) {
     p = fma_(p, z, c01.x);
     return p;
 }
+ESLAM_HD double h_ratio(double t, const dbl2* tab) {
+    if (!h_in_range(t)) return h_slow(t);
+    return h_core(t, tab);
+}
 
 // contact likelihood ratio pdf/cdf for N(0, sqrt(zvar)*corr) at zdiff (src/ContactModel.cpp:104-115,170)
 // inv_corr = 1.0 / contactLikelihoodCorrection
@@ -322,6 +334,13 @@ ESLAM_HD double likelihood_ratio(double zdiff, double zvar, double inv_corr, con
     double qc = rsqrt_(zvar) * inv_corr;   // 1 / (sigma * corr)
     double t = zdiff * qc;
     return h_ratio(t, tab) * qc;
+}
+// the same value on the common path without branches; *rare is set when the generic function must be used instead
+ESLAM_HD double likelihood_ratio_fast(double zdiff, double zvar, double inv_corr, const dbl2* tab, bool& rare) {
+    const double qc = rsqrt_core(zvar) * inv_corr;
+    const double t = zdiff * qc;
+    rare = !(rsqrt_in_range(zvar) && h_in_range(t));
+    return h_core(t, tab) * qc;
 }
 
 // ---------------------------------------------------------------- powers
