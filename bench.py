@@ -159,8 +159,9 @@ def main():
     comm = dist.init(world, rank, local_rank) if world > 1 else None
     n_global = n_local * world
     cfg = abi.default_config(min_effective=n_global + 1)          # resample every step (ESS <= N always)
-    shard = abi.Shard(rank=rank, world=world, global_count=n_global) if world > 1 else None
-    g = GpuPoseEstimator(cfg, device=local_rank, shard=shard, comm=None if comm is None else comm.hooks)
+    g = GpuPoseEstimator(cfg, device=local_rank, shard=comm.shard(n_local) if comm else None)
+    if comm:
+        comm.connect(g)
     contacts, step = synthetic.setup_filter(g, args.workload, n=n_local)
 
     # warm-up, then K timed steps with inputs resident (events on the library's stream)
@@ -205,6 +206,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "particles_per_gpu": n_local, "particles": n_global, "contact_points": c,
                    "grid": "%dx%d float2, replicated" % (w["grid"], w["grid"]), "resample": "stratified, every step",
+                   "sharding": "contiguous particle ranges, exact-global resampling (ancestors identical to 1 GPU)" if world > 1 else "none",
                    "timing": "inputs larger than L2: particle state 2 x %.0f MB + scan buffers stream from HBM every "
                              "step; the %.0f MB map is L2-resident by design" % (n_local * 58 / 1e6, w["grid"] ** 2 * 8 / 1e6),
                    "step_algorithmic_bytes": step_bytes,

@@ -61,14 +61,6 @@ typedef struct eslam_gpu_shard {
     uint64_t global_count;               /* total particles over all ranks */
 } eslam_gpu_shard;
 
-/* Collective hooks used when world > 1; the caller binds them to NCCL (bench.py / tests bind
- * torch.distributed).  Buffers are DEVICE pointers, calls are stream-ordered on `stream`. */
-typedef int (*eslam_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank, void* stream);
-typedef struct eslam_gpu_comm {
-    void* user;
-    eslam_allgather_fn allgather;
-} eslam_gpu_comm;
-
 /* Per-step inputs of PoseEstimator::project (src/PoseEstimator.cpp:184-194); the facade derives
  * them from the orientation quaternion and odometry::FootContact. */
 typedef struct eslam_gpu_step {
@@ -105,7 +97,13 @@ typedef struct eslam_gpu_ctx eslam_gpu_ctx;
 
 void eslam_gpu_default_config(eslam_gpu_config* cfg);                 /* src/Configuration.hpp:53-59,85-111 */
 int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_shard* shard_or_null,
-                     const eslam_gpu_comm* comm_or_null, eslam_gpu_ctx** out);   /* PoseEstimator ctor, src/PoseEstimator.cpp:13-25 */
+                     eslam_gpu_ctx** out);                            /* PoseEstimator ctor, src/PoseEstimator.cpp:13-25 */
+/* Sharded filter (one context per GPU / rank; shards are equal multiples of 1024 particles): rank 0 creates a NCCL
+ * unique id, the launcher broadcasts the 128 bytes, every rank joins.  The library resolves NCCL at run time
+ * (dlopen of the libnccl.so.2 already in the process) and issues the exchange steps on its own stream:
+ * all-gathers of per-tile partials / scan descriptors and contiguous-range send/recv for resampling. */
+int eslam_gpu_nccl_unique_id(uint8_t out[128]);
+int eslam_gpu_comm_init(eslam_gpu_ctx* ctx, const uint8_t unique_id[128]);
 void eslam_gpu_destroy(eslam_gpu_ctx* ctx);
 const char* eslam_gpu_last_error(const eslam_gpu_ctx* ctx);
 

@@ -56,13 +56,6 @@ class Shard(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("global_count", C.c_uint64)]
 
 
-ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
-
-
-class Comm(C.Structure):
-    _fields_ = [("user", C.c_void_p), ("allgather", ALLGATHER_FN)]
-
-
 class Step(C.Structure):
     _fields_ = [("yaw", C.c_double), ("z_delta", C.c_double), ("z_var", C.c_double),
                 ("delta_mean", C.c_double * 3), ("delta_sigma", C.c_double * 3)]
@@ -133,7 +126,9 @@ SIGNATURES = {
 
 GPU_ONLY = {
     "default_config": (None, [C.POINTER(Config)]),
-    "create": (C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(Shard), C.POINTER(Comm), C.POINTER(C.c_void_p)]),
+    "create": (C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(Shard), C.POINTER(C.c_void_p)]),
+    "nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "comm_init": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8)]),
     "destroy": (None, [C.c_void_p]),
     "last_error": (C.c_char_p, [C.c_void_p]),
     "step_fused": (C.c_int, [C.c_void_p, C.POINTER(Step), C.POINTER(Contact), C.c_int, C.POINTER(UpdateResult)]),

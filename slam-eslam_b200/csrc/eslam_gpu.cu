@@ -1,10 +1,13 @@
-// eslam_gpu.cu -- C ABI of libeslam_gpu.so (include/eslam_gpu.h): context, memory and launch sequencing.
-// All arithmetic lives in eslam_kernels.cuh; there is no CPU implementation of any step in this library.
+// eslam_gpu.cu -- C ABI of libeslam_gpu.so (include/eslam_gpu.h): context, memory, launch sequencing and the
+// exchange steps of the sharded (multi-GPU) filter.  All arithmetic lives in eslam_kernels.cuh; there is no CPU
+// implementation of any step in this library.
 #include "eslam_kernels.cuh"
+#include "eslam_nccl.h"
 
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -12,31 +15,36 @@ static const em::dbl2 H_TABLE_HOST[ESLAM_H_NINT * 3] = {
 #include "eslam_h_table.inc"
 };
 
+static NcclApi g_nccl;
+
 struct eslam_gpu_ctx {
     eslam_gpu_config cfg;
     eslam_gpu_shard shard;
-    eslam_gpu_comm comm; bool has_comm;
     int device;
     cudaStream_t stream;
     std::string error;
     uint64_t launches;
+    eslam_ncclComm_t comm; bool has_comm;
 
-    // particles
+    // particles (local shard)
     uint64_t n, cap;
     StateBufs st;
     DevScalars* sc; DevScalars* sc_host;          // sc_host: pinned staging
     uint32_t* ancestors; double* cdf;
-    // tiles
-    unsigned n_tiles, tile_cap;
-    TilePartA* part_a; double *tile_sum, *tile_sq, *tile_prefix, *scratch_a, *scratch_b, *tile_sin, *sb, *cent_part, *best_w;
-    unsigned long long* best_idx;
-    TileDesc* desc; BndEntry* pool; int* tile_bofs; SegF* tile_pre;
+    // per-tile arrays: l_* cover the local tiles, g_* all tiles of all ranks (aliases of l_* when world == 1)
+    unsigned t_local, t_global, t_cap;
+    TilePartA *l_part_a, *g_part_a; double *l_tile_sum, *g_tile_sum, *l_tile_sq, *g_tile_sq;
+    TileDesc *l_desc, *g_desc; BndEntry *l_pool, *g_pool;
+    double *l_cent, *g_cent, *l_best_w, *g_best_w; unsigned long long *l_best_idx, *g_best_idx;
+    double *tile_prefix, *scratch_a, *scratch_b, *tile_sin, *sb; int* tile_bofs; SegF* tile_pre;
+    double* tile_sin_host;                        // pinned, t_global
+    // resampling window fetched from the owning ranks (world > 1)
+    uint64_t win_cap; double* win_cdf; double* win_f[7]; uint8_t* win_b[2];
     // map
     float2* cells; MapParams map; bool has_map;
     em::dbl2* htab;
     int max_smem_optin, sm_count;
     uint32_t project_step;
-    // step staging
     std::vector<cudaEvent_t> events;
 };
 
@@ -51,29 +59,57 @@ struct eslam_gpu_ctx {
         }                                                                                          \
     } while (0)
 
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        int r__ = (call);                                                                          \
+        if (r__ != 0) {                                                                            \
+            char buf__[256];                                                                       \
+            snprintf(buf__, sizeof buf__, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "?"); \
+            ctx->error = buf__;                                                                    \
+            return ESLAM_ERR_COMM;                                                                 \
+        }                                                                                          \
+    } while (0)
+
 #define LAUNCHED() do { ctx->launches++; CK(cudaGetLastError()); } while (0)
 
 template <class T> static cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T)); }
+template <class T> static void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+static inline bool sharded(const eslam_gpu_ctx* ctx) { return ctx->shard.world > 1; }
 
 static void free_particles(eslam_gpu_ctx* ctx) {
     for (int b = 0; b < 2; ++b) {
-        for (int f = 0; f < 7; ++f) { cudaFree(ctx->st.f[b][f]); ctx->st.f[b][f] = nullptr; }
-        for (int f = 0; f < 2; ++f) { cudaFree(ctx->st.b[b][f]); ctx->st.b[b][f] = nullptr; }
+        for (int f = 0; f < 7; ++f) dfree(ctx->st.f[b][f]);
+        for (int f = 0; f < 2; ++f) dfree(ctx->st.b[b][f]);
     }
-    cudaFree(ctx->ancestors); cudaFree(ctx->cdf); ctx->ancestors = nullptr; ctx->cdf = nullptr;
-    cudaFree(ctx->part_a); cudaFree(ctx->tile_sum); cudaFree(ctx->tile_sq); cudaFree(ctx->tile_prefix);
-    cudaFree(ctx->scratch_a); cudaFree(ctx->scratch_b); cudaFree(ctx->tile_sin); cudaFree(ctx->sb);
-    cudaFree(ctx->cent_part); cudaFree(ctx->best_w); cudaFree(ctx->best_idx);
-    cudaFree(ctx->desc); cudaFree(ctx->pool); cudaFree(ctx->tile_bofs); cudaFree(ctx->tile_pre); ctx->pool = nullptr;
-    ctx->part_a = nullptr; ctx->tile_sum = ctx->tile_sq = ctx->tile_prefix = ctx->scratch_a = ctx->scratch_b = nullptr;
-    ctx->tile_sin = ctx->sb = ctx->cent_part = ctx->best_w = nullptr; ctx->best_idx = nullptr;
-    ctx->desc = nullptr; ctx->tile_bofs = nullptr; ctx->tile_pre = nullptr;
-    ctx->cap = 0; ctx->tile_cap = 0;
+    dfree(ctx->ancestors); dfree(ctx->cdf);
+    const bool sh = ctx->g_part_a != ctx->l_part_a;
+    if (sh) { dfree(ctx->g_part_a); dfree(ctx->g_tile_sum); dfree(ctx->g_tile_sq); dfree(ctx->g_desc); dfree(ctx->g_pool);
+              dfree(ctx->g_cent); dfree(ctx->g_best_w); dfree(ctx->g_best_idx); }
+    dfree(ctx->l_part_a); dfree(ctx->l_tile_sum); dfree(ctx->l_tile_sq); dfree(ctx->l_desc); dfree(ctx->l_pool);
+    dfree(ctx->l_cent); dfree(ctx->l_best_w); dfree(ctx->l_best_idx);
+    ctx->g_part_a = nullptr; ctx->g_tile_sum = ctx->g_tile_sq = nullptr; ctx->g_desc = nullptr; ctx->g_pool = nullptr;
+    ctx->g_cent = ctx->g_best_w = nullptr; ctx->g_best_idx = nullptr;
+    dfree(ctx->tile_prefix); dfree(ctx->scratch_a); dfree(ctx->scratch_b); dfree(ctx->tile_sin); dfree(ctx->sb);
+    dfree(ctx->tile_bofs); dfree(ctx->tile_pre);
+    if (ctx->tile_sin_host) { cudaFreeHost(ctx->tile_sin_host); ctx->tile_sin_host = nullptr; }
+    ctx->cap = 0; ctx->t_cap = 0;
+}
+
+static void free_window(eslam_gpu_ctx* ctx) {
+    dfree(ctx->win_cdf);
+    for (int f = 0; f < 7; ++f) dfree(ctx->win_f[f]);
+    for (int f = 0; f < 2; ++f) dfree(ctx->win_b[f]);
+    ctx->win_cap = 0;
 }
 
 static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
     if (n == 0) return ESLAM_ERR_EMPTY;
     if (n > 0xFFFFFFFFull) { ctx->error = "more than 2^32 particles per shard"; return ESLAM_ERR_INVALID; }
+    const int G = sharded(ctx) ? ctx->shard.world : 1;
+    if (G > 1 && (n % TILE != 0 || ctx->shard.global_count != n * (uint64_t)G)) {
+        ctx->error = "sharded contexts need equal shards that are multiples of 1024 particles"; return ESLAM_ERR_INVALID;
+    }
     if (n > ctx->cap) {
         free_particles(ctx);
         for (int b = 0; b < 2; ++b) {
@@ -81,29 +117,46 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
             for (int f = 0; f < 2; ++f) CK(dalloc(&ctx->st.b[b][f], n));
         }
         CK(dalloc(&ctx->ancestors, n)); CK(dalloc(&ctx->cdf, n));
-        const unsigned t = (unsigned)((n + TILE - 1) / TILE);
-        CK(dalloc(&ctx->part_a, t)); CK(dalloc(&ctx->tile_sum, t)); CK(dalloc(&ctx->tile_sq, t));
-        CK(dalloc(&ctx->tile_prefix, t)); CK(dalloc(&ctx->scratch_a, t)); CK(dalloc(&ctx->scratch_b, t));
-        CK(dalloc(&ctx->tile_sin, t)); CK(dalloc(&ctx->sb, (size_t)MAX_BND_TOTAL)); CK(dalloc(&ctx->cent_part, 5 * (size_t)t));
-        CK(dalloc(&ctx->best_w, t)); CK(dalloc(&ctx->best_idx, t));
-        CK(dalloc(&ctx->desc, t)); CK(dalloc(&ctx->pool, (size_t)MAX_BND_TOTAL)); CK(dalloc(&ctx->tile_bofs, t)); CK(dalloc(&ctx->tile_pre, t));
-        ctx->cap = n; ctx->tile_cap = t;
+        const size_t t = (size_t)((n + TILE - 1) / TILE), tg = t * G;
+        CK(dalloc(&ctx->l_part_a, t)); CK(dalloc(&ctx->l_tile_sum, t)); CK(dalloc(&ctx->l_tile_sq, t));
+        CK(dalloc(&ctx->l_desc, t)); CK(dalloc(&ctx->l_pool, (size_t)MAX_BND_TOTAL));
+        CK(dalloc(&ctx->l_cent, 5 * t)); CK(dalloc(&ctx->l_best_w, t)); CK(dalloc(&ctx->l_best_idx, t));
+        if (G > 1) {
+            CK(dalloc(&ctx->g_part_a, tg)); CK(dalloc(&ctx->g_tile_sum, tg)); CK(dalloc(&ctx->g_tile_sq, tg));
+            CK(dalloc(&ctx->g_desc, tg)); CK(dalloc(&ctx->g_pool, (size_t)MAX_BND_TOTAL * G));
+            CK(dalloc(&ctx->g_cent, 5 * tg)); CK(dalloc(&ctx->g_best_w, tg)); CK(dalloc(&ctx->g_best_idx, tg));
+        } else {
+            ctx->g_part_a = ctx->l_part_a; ctx->g_tile_sum = ctx->l_tile_sum; ctx->g_tile_sq = ctx->l_tile_sq;
+            ctx->g_desc = ctx->l_desc; ctx->g_pool = ctx->l_pool; ctx->g_cent = ctx->l_cent;
+            ctx->g_best_w = ctx->l_best_w; ctx->g_best_idx = ctx->l_best_idx;
+        }
+        CK(dalloc(&ctx->tile_prefix, tg)); CK(dalloc(&ctx->scratch_a, tg)); CK(dalloc(&ctx->scratch_b, tg));
+        CK(dalloc(&ctx->tile_sin, tg)); CK(dalloc(&ctx->sb, (size_t)MAX_BND_TOTAL));
+        CK(dalloc(&ctx->tile_bofs, tg)); CK(dalloc(&ctx->tile_pre, tg));
+        CK(cudaMallocHost((void**)&ctx->tile_sin_host, tg * sizeof(double)));
+        ctx->cap = n; ctx->t_cap = (unsigned)t;
     }
-    ctx->n = n; ctx->n_tiles = (unsigned)((n + TILE - 1) / TILE);
+    ctx->n = n; ctx->t_local = (unsigned)((n + TILE - 1) / TILE); ctx->t_global = ctx->t_local * G;
     return ESLAM_OK;
 }
 
-static inline uint64_t global_count(const eslam_gpu_ctx* ctx) {
-    return ctx->shard.world > 1 ? ctx->shard.global_count : ctx->n;
-}
-static inline uint64_t base_index(const eslam_gpu_ctx* ctx) {
-    return ctx->shard.world > 1 ? (uint64_t)ctx->shard.rank * ctx->n : 0;
-}
+static inline uint64_t global_count(const eslam_gpu_ctx* ctx) { return sharded(ctx) ? ctx->shard.global_count : ctx->n; }
+static inline uint64_t base_index(const eslam_gpu_ctx* ctx) { return sharded(ctx) ? (uint64_t)ctx->shard.rank * ctx->n : 0; }
+static inline unsigned tile_ofs(const eslam_gpu_ctx* ctx) { return sharded(ctx) ? (unsigned)ctx->shard.rank * ctx->t_local : 0; }
 static inline double scan_eps(const eslam_gpu_ctx* ctx) {
     // |sequential fp64 running sum - approximate parallel prefix| <= N 2^-53 (relative); 8x margin, floor 2^-40
     const double e = ldexp((double)global_count(ctx), -50);
     return e > ldexp(1.0, -40) ? e : ldexp(1.0, -40);
 }
+
+// all-gather of equal-sized per-rank blocks (device pointers, stream ordered); identity on one GPU
+static int allgather(eslam_gpu_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank) {
+    if (!sharded(ctx)) return ESLAM_OK;
+    if (!ctx->has_comm) { ctx->error = "sharded context without a communicator (call eslam_gpu_comm_init)"; return ESLAM_ERR_COMM; }
+    NK(g_nccl.AllGather(send, recv, bytes_per_rank, ESLAM_NCCL_UINT8, ctx->comm, ctx->stream));
+    return ESLAM_OK;
+}
+#define AG(send, recv, bytes) do { int s__ = allgather(ctx, send, recv, bytes); if (s__ != ESLAM_OK) return s__; } while (0)
 
 static ModelParams model_params(const eslam_gpu_ctx* ctx) {
     const eslam_gpu_config& c = ctx->cfg;
@@ -141,6 +194,12 @@ static size_t weight_smem_bytes(const eslam_gpu_ctx* ctx) {
     return HTAB_BYTES + 1024 + 256 + (size_t)ctx->map.tile_w * ctx->map.tile_h * sizeof(float2);
 }
 
+static int read_scalars(eslam_gpu_ctx* ctx) {
+    CK(cudaMemcpyAsync(ctx->sc_host, ctx->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ESLAM_OK;
+}
+
 extern "C" {
 
 void eslam_gpu_default_config(eslam_gpu_config* c) {
@@ -155,23 +214,27 @@ void eslam_gpu_default_config(eslam_gpu_config* c) {
     c->resample_mode = ESLAM_RESAMPLE_STRATIFIED; c->patch_size = 0;
 }
 
-int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_shard* shard, const eslam_gpu_comm* comm,
-                     eslam_gpu_ctx** out) {
+int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_shard* shard, eslam_gpu_ctx** out) {
     if (!cfg || !out) return ESLAM_ERR_INVALID;
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ESLAM_ERR_CUDA;
     eslam_gpu_ctx* ctx = new eslam_gpu_ctx();
+    memset(&ctx->st, 0, sizeof(ctx->st));
     ctx->cfg = *cfg;
     ctx->shard.rank = 0; ctx->shard.world = 1; ctx->shard.global_count = 0;
     if (shard) ctx->shard = *shard;
-    ctx->has_comm = comm != nullptr;
-    if (comm) ctx->comm = *comm;
-    ctx->device = device; ctx->launches = 0; ctx->n = ctx->cap = 0; ctx->n_tiles = ctx->tile_cap = 0;
-    memset(&ctx->st, 0, sizeof(ctx->st));
-    ctx->ancestors = nullptr; ctx->cdf = nullptr; ctx->part_a = nullptr;
-    ctx->tile_sum = ctx->tile_sq = ctx->tile_prefix = ctx->scratch_a = ctx->scratch_b = ctx->tile_sin = ctx->sb = nullptr;
-    ctx->cent_part = ctx->best_w = nullptr; ctx->best_idx = nullptr; ctx->desc = nullptr; ctx->pool = nullptr; ctx->tile_bofs = nullptr;
-    ctx->tile_pre = nullptr; ctx->cells = nullptr; ctx->has_map = false; ctx->project_step = 0;
+    ctx->comm = nullptr; ctx->has_comm = false;
+    ctx->device = device; ctx->launches = 0; ctx->n = ctx->cap = 0; ctx->t_local = ctx->t_global = ctx->t_cap = 0;
+    ctx->ancestors = nullptr; ctx->cdf = nullptr;
+    ctx->l_part_a = ctx->g_part_a = nullptr; ctx->l_tile_sum = ctx->g_tile_sum = ctx->l_tile_sq = ctx->g_tile_sq = nullptr;
+    ctx->l_desc = ctx->g_desc = nullptr; ctx->l_pool = ctx->g_pool = nullptr;
+    ctx->l_cent = ctx->g_cent = ctx->l_best_w = ctx->g_best_w = nullptr; ctx->l_best_idx = ctx->g_best_idx = nullptr;
+    ctx->tile_prefix = ctx->scratch_a = ctx->scratch_b = ctx->tile_sin = ctx->sb = nullptr;
+    ctx->tile_bofs = nullptr; ctx->tile_pre = nullptr; ctx->tile_sin_host = nullptr;
+    ctx->win_cap = 0; ctx->win_cdf = nullptr;
+    for (int f = 0; f < 7; ++f) ctx->win_f[f] = nullptr;
+    for (int f = 0; f < 2; ++f) ctx->win_b[f] = nullptr;
+    ctx->cells = nullptr; ctx->has_map = false; ctx->project_step = 0;
     memset(&ctx->map, 0, sizeof(ctx->map));
     *out = ctx;
     CK(cudaSetDevice(device));
@@ -192,7 +255,8 @@ void eslam_gpu_destroy(eslam_gpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    free_particles(ctx);
+    if (ctx->has_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    free_particles(ctx); free_window(ctx);
     cudaFree(ctx->sc); cudaFreeHost(ctx->sc_host); cudaFree(ctx->htab); cudaFree(ctx->cells);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
@@ -202,6 +266,25 @@ void eslam_gpu_destroy(eslam_gpu_ctx* ctx) {
 const char* eslam_gpu_last_error(const eslam_gpu_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
 uint64_t eslam_gpu_launch_count(const eslam_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 uint64_t eslam_gpu_particle_count(const eslam_gpu_ctx* ctx) { return ctx ? ctx->n : 0; }
+
+int eslam_gpu_nccl_unique_id(uint8_t out[128]) {
+    if (!out || !g_nccl.load()) return ESLAM_ERR_COMM;
+    eslam_ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != 0) return ESLAM_ERR_COMM;
+    memcpy(out, id.internal, 128);
+    return ESLAM_OK;
+}
+
+int eslam_gpu_comm_init(eslam_gpu_ctx* ctx, const uint8_t id_bytes[128]) {
+    if (!ctx || !id_bytes) return ESLAM_ERR_INVALID;
+    if (!sharded(ctx)) return ESLAM_OK;
+    if (!g_nccl.load()) { ctx->error = "libnccl.so.2 not found"; return ESLAM_ERR_COMM; }
+    CK(cudaSetDevice(ctx->device));
+    eslam_ncclUniqueId id; memcpy(id.internal, id_bytes, 128);
+    NK(g_nccl.CommInitRank(&ctx->comm, ctx->shard.world, id, ctx->shard.rank));
+    ctx->has_comm = true;
+    return ESLAM_OK;
+}
 
 int eslam_gpu_synchronize(eslam_gpu_ctx* ctx) {
     if (!ctx) return ESLAM_ERR_INVALID;
@@ -222,6 +305,7 @@ int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int he
     MapParams& m = ctx->map;
     m.cells = ctx->cells; m.W = width; m.H = height; m.sx = sx; m.sy = sy; m.ox = ox; m.oy = oy;
     m.inv_sx = 1.0 / sx; m.inv_sy = 1.0 / sy;
+    m.c0x = 25769803776.0 - ox * m.inv_sx; m.c0y = 25769803776.0 - oy * m.inv_sy;   // 1.5 * 2^34 - offset/scale
     m.identity = g2l == nullptr;
     for (int i = 0; i < 8; ++i) m.g2l[i] = g2l ? g2l[i] : (i == 0 || i == 5 ? 1.0 : 0.0);
     // shared-memory map tile: as many cells as fit next to the h-table
@@ -254,12 +338,6 @@ int eslam_gpu_init_gaussian(eslam_gpu_ctx* ctx, uint64_t n, const double mu[3], 
                                                                          mu[0], mu[1], mu[2], sigma[0], sigma[1], sigma[2],
                                                                          zpos, zsigma);
     LAUNCHED();
-    CK(cudaStreamSynchronize(ctx->stream));
-    return ESLAM_OK;
-}
-
-static int read_scalars(eslam_gpu_ctx* ctx) {
-    CK(cudaMemcpyAsync(ctx->sc_host, ctx->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return ESLAM_OK;
 }
@@ -303,10 +381,12 @@ int eslam_gpu_get_particles(eslam_gpu_ctx* ctx, double* x, double* y, double* th
     return ESLAM_OK;
 }
 
+}  // extern "C"
+
 // ---------------------------------------------------------------------------------------------- launch sequences
 static void fill_weight_params(eslam_gpu_ctx* ctx, WeightParams* P, const eslam_gpu_step* step, const ContactSet* cs) {
     memset(P, 0, sizeof(*P));
-    P->st = ctx->st; P->sc = ctx->sc; P->part = ctx->part_a; P->map = ctx->map; P->mp = model_params(ctx);
+    P->st = ctx->st; P->sc = ctx->sc; P->part = ctx->l_part_a; P->map = ctx->map; P->mp = model_params(ctx);
     P->htab = ctx->htab; P->n = ctx->n; P->base = base_index(ctx); P->project_step = ctx->project_step;
     if (step) {
         P->yaw = step->yaw; P->z_delta = step->z_delta; P->z_var = step->z_var;
@@ -316,38 +396,124 @@ static void fill_weight_params(eslam_gpu_ctx* ctx, WeightParams* P, const eslam_
 }
 
 static unsigned weight_grid(const eslam_gpu_ctx* ctx) {
-    return ctx->n_tiles < (unsigned)ctx->sm_count ? ctx->n_tiles : (unsigned)ctx->sm_count;
+    return ctx->t_local < (unsigned)ctx->sm_count ? ctx->t_local : (unsigned)ctx->sm_count;
+}
+
+// Sharded resampling, exact-global mode: every rank knows the exact running sum at every tile start (k_chain ran on
+// the all-gathered descriptors), so every rank can tell which contiguous element range holds the ancestors of each
+// rank's strata; the owners send exactly those ranges (running sum + particle state), then search and gather run on
+// the received window.  Ancestor indices are global and identical to the one-GPU run.
+static int resample_exchange(eslam_gpu_ctx* ctx) {
+    int st = read_scalars(ctx);                                         // host needs: resample? which buffer? fallback?
+    if (st != ESLAM_OK) return st;
+    if (!ctx->sc_host->do_resample) return ESLAM_OK;
+    if (ctx->sc_host->error_flags & ERR_CDF_FALLBACK_BIT) {
+        ctx->error = "exact running sum needs the sequential fallback, which is not available across shards";
+        return ESLAM_ERR_COMM;
+    }
+    const int G = ctx->shard.world, me = ctx->shard.rank, cur = ctx->sc_host->cur;
+    const uint64_t n = ctx->n, N = ctx->shard.global_count;
+    const unsigned T = ctx->t_global;
+    CK(cudaMemcpyAsync(ctx->tile_sin_host, ctx->tile_sin, T * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const double* S = ctx->tile_sin_host;                               // exact running sum before each tile
+    auto last_tile_below = [&](double thr) -> unsigned {                // max t with S[t] < thr (0 if none)
+        unsigned lo = 0, hi = T;                                        // first t with !(S[t] < thr)
+        while (lo < hi) { unsigned mid = (lo + hi) / 2; if (S[mid] < thr) lo = mid + 1; else hi = mid; }
+        return lo == 0 ? 0 : lo - 1;
+    };
+    std::vector<uint64_t> wb(G), we(G);                                 // window [wb, we) of every rank
+    for (int r = 0; r < G; ++r) {
+        const double lo_thr = (double)((uint64_t)r * n) / (double)N, hi_thr = (double)((uint64_t)(r + 1) * n) / (double)N;
+        const unsigned tlo = last_tile_below(lo_thr), thi = last_tile_below(hi_thr);
+        wb[r] = (uint64_t)tlo * TILE; we[r] = std::min<uint64_t>(((uint64_t)thi + 1) * TILE, N);
+    }
+    const uint64_t wlen = we[me] - wb[me];
+    if (wlen > ctx->win_cap) {
+        free_window(ctx);
+        CK(dalloc(&ctx->win_cdf, wlen));
+        for (int f = 0; f < 7; ++f) CK(dalloc(&ctx->win_f[f], wlen));
+        for (int f = 0; f < 2; ++f) CK(dalloc(&ctx->win_b[f], wlen));
+        ctx->win_cap = wlen;
+    }
+    // arrays to move: running sum, 7 doubles, 2 bytes
+    const void* src[10]; void* dst[10]; size_t esz[10];
+    src[0] = ctx->cdf; dst[0] = ctx->win_cdf; esz[0] = 8;
+    for (int f = 0; f < 7; ++f) { src[1 + f] = ctx->st.f[cur][f]; dst[1 + f] = ctx->win_f[f]; esz[1 + f] = 8; }
+    for (int f = 0; f < 2; ++f) { src[8 + f] = ctx->st.b[cur][f]; dst[8 + f] = ctx->win_b[f]; esz[8 + f] = 1; }
+    const uint64_t my_lo = (uint64_t)me * n, my_hi = my_lo + n;
+    NK(g_nccl.GroupStart());
+    for (int q = 0; q < G; ++q) {
+        const uint64_t s_lo = std::max(wb[q], my_lo), s_hi = std::min(we[q], my_hi);      // what q needs from me
+        const uint64_t q_lo = (uint64_t)q * n, q_hi = q_lo + n;
+        const uint64_t r_lo = std::max(wb[me], q_lo), r_hi = std::min(we[me], q_hi);      // what I need from q
+        for (int a = 0; a < 10; ++a) {
+            if (q == me) {
+                if (r_hi > r_lo)
+                    CK(cudaMemcpyAsync((char*)dst[a] + (r_lo - wb[me]) * esz[a], (const char*)src[a] + (r_lo - my_lo) * esz[a],
+                                       (r_hi - r_lo) * esz[a], cudaMemcpyDeviceToDevice, ctx->stream));
+                continue;
+            }
+            if (s_hi > s_lo)
+                NK(g_nccl.Send((const char*)src[a] + (s_lo - my_lo) * esz[a], (s_hi - s_lo) * esz[a], ESLAM_NCCL_UINT8, q, ctx->comm, ctx->stream));
+            if (r_hi > r_lo)
+                NK(g_nccl.Recv((char*)dst[a] + (r_lo - wb[me]) * esz[a], (r_hi - r_lo) * esz[a], ESLAM_NCCL_UINT8, q, ctx->comm, ctx->stream));
+        }
+    }
+    NK(g_nccl.GroupEnd());
+    const ModelParams mp = model_params(ctx);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    k_search<<<blocks, 256, 0, ctx->stream>>>(ctx->sc, ctx->win_cdf, wlen, wb[me], n, N, base_index(ctx), mp.k0, mp.k1,
+                                              ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC, ctx->ancestors);
+    LAUNCHED();
+    GatherSrc gs; memset(&gs, 0, sizeof(gs));
+    for (int f = 0; f < 7; ++f) gs.f[f] = ctx->win_f[f];
+    for (int f = 0; f < 2; ++f) gs.b[f] = ctx->win_b[f];
+    gs.base = wb[me]; gs.use_window = 1;
+    k_gather<<<blocks, 256, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->ancestors, gs);
+    LAUNCHED();
+    k_after_resample<<<1, 1, 0, ctx->stream>>>(ctx->sc);
+    LAUNCHED();
+    return ESLAM_OK;
 }
 
 // normalise + (optional) resample tail shared by update / normalize_weights / resample.
 // mode: 0 = do_resample := force, 1 = decide from ESS (update), 2 = ESS only
 static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int mode, int force) {
-    const unsigned T = ctx->n_tiles;
+    const unsigned T = ctx->t_local, TG = ctx->t_global;
     const uint64_t n = ctx->n, ng = global_count(ctx);
     const double eps = scan_eps(ctx);
-    if (apply_loop_b) k_loop_b<true><<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->tile_sum);
-    else k_loop_b<false><<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->tile_sum);
+    if (apply_loop_b) k_loop_b<true><<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->l_tile_sum);
+    else k_loop_b<false><<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->l_tile_sum);
     LAUNCHED();
-    k_reduce_b<<<1, 1024, 0, ctx->stream>>>(ctx->tile_sum, T, n, ctx->sc, ctx->scratch_a, ctx->scratch_b, ctx->tile_prefix, normalise);
+    AG(ctx->l_tile_sum, ctx->g_tile_sum, T * sizeof(double));
+    k_reduce_b<<<1, 1024, 0, ctx->stream>>>(ctx->g_tile_sum, TG, ng, ctx->sc, ctx->scratch_a, ctx->scratch_b, ctx->tile_prefix, normalise);
     LAUNCHED();
-    k_norm_scan<<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ng, ctx->tile_prefix, ctx->tile_sq, ctx->desc, ctx->pool, ctx->sc, normalise, eps);
+    k_norm_scan<<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ng, ctx->tile_prefix, ctx->l_tile_sq, ctx->l_desc, ctx->l_pool,
+                                             ctx->sc, normalise, eps, tile_ofs(ctx));
     LAUNCHED();
+    AG(ctx->l_tile_sq, ctx->g_tile_sq, T * sizeof(double));
+    AG(ctx->l_desc, ctx->g_desc, T * sizeof(TileDesc));
+    AG(ctx->l_pool, ctx->g_pool, (size_t)MAX_BND_TOTAL * sizeof(BndEntry));
     const int decide = mode == 0 ? 0 : 1;
-    k_chain<<<1, 1024, sizeof(ChainSmem), ctx->stream>>>(ctx->desc, ctx->pool, T, ctx->tile_sq, ctx->sc, ctx->scratch_a, ctx->scratch_b,
-                                                         ctx->tile_bofs, ctx->tile_pre, ctx->tile_sin, ctx->sb,
-                                                         mode == 2 ? 0ull : ctx->cfg.min_effective, decide, force);
+    k_chain<<<1, 1024, sizeof(ChainSmem), ctx->stream>>>(ctx->g_desc, ctx->g_pool, TG, ctx->g_tile_sq, ctx->sc, ctx->scratch_a,
+                                                         ctx->scratch_b, ctx->tile_bofs, ctx->tile_pre, ctx->tile_sin, ctx->sb,
+                                                         mode == 2 ? 0ull : ctx->cfg.min_effective, decide, force, T);
     LAUNCHED();
     if (mode == 2) return ESLAM_OK;
-    k_cdf<<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->tile_prefix, ctx->tile_bofs, ctx->tile_sin, ctx->sb, ctx->cdf, eps);
+    k_cdf<<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->tile_prefix, ctx->tile_bofs, ctx->tile_sin, ctx->sb, ctx->cdf, eps,
+                                       tile_ofs(ctx));
     LAUNCHED();
+    if (sharded(ctx)) return resample_exchange(ctx);
     k_cdf_sequential<<<1, 1, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->cdf);
     LAUNCHED();
     const ModelParams mp = model_params(ctx);
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    k_search<<<blocks, 256, 0, ctx->stream>>>(ctx->sc, ctx->cdf, n, ng, base_index(ctx), mp.k0, mp.k1,
+    k_search<<<blocks, 256, 0, ctx->stream>>>(ctx->sc, ctx->cdf, n, 0, n, ng, 0, mp.k0, mp.k1,
                                               ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC, ctx->ancestors);
     LAUNCHED();
-    k_gather<<<blocks, 256, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->ancestors);
+    GatherSrc gs; memset(&gs, 0, sizeof(gs));
+    k_gather<<<blocks, 256, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->ancestors, gs);
     LAUNCHED();
     k_after_resample<<<1, 1, 0, ctx->stream>>>(ctx->sc);
     LAUNCHED();
@@ -364,7 +530,8 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
     else k_project_weight<false, true><<<weight_grid(ctx), WT_THREADS, smem, ctx->stream>>>(P);
     LAUNCHED();
     if (ev1) CK(cudaEventRecord(ev1, ctx->stream));
-    k_reduce_a<<<1, 1024, 0, ctx->stream>>>(ctx->part_a, ctx->n_tiles, ctx->n, ctx->sc, ctx->scratch_a, ctx->scratch_b,
+    AG(ctx->l_part_a, ctx->g_part_a, ctx->t_local * sizeof(TilePartA));
+    k_reduce_a<<<1, 1024, 0, ctx->stream>>>(ctx->g_part_a, ctx->t_global, global_count(ctx), ctx->sc, ctx->scratch_a, ctx->scratch_b,
                                             ctx->cfg.discount_factor);
     LAUNCHED();
     return launch_tail(ctx, true, 1, 1, 0);
@@ -392,6 +559,21 @@ static int check_ready(eslam_gpu_ctx* ctx, bool need_map) {
     if (need_map && !ctx->has_map) { ctx->error = "No environment attached."; return ESLAM_ERR_NO_ENVIRONMENT; }
     return ESLAM_OK;
 }
+
+static int launch_centroid(eslam_gpu_ctx* ctx) {
+    k_centroid_tiles<<<ctx->t_local, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->n, base_index(ctx), ctx->l_cent,
+                                                            ctx->l_best_idx, ctx->l_best_w);
+    LAUNCHED();
+    AG(ctx->l_cent, ctx->g_cent, ctx->t_local * 5 * sizeof(double));
+    AG(ctx->l_best_idx, ctx->g_best_idx, ctx->t_local * sizeof(unsigned long long));
+    AG(ctx->l_best_w, ctx->g_best_w, ctx->t_local * sizeof(double));
+    k_centroid_final<<<1, 1024, 0, ctx->stream>>>(ctx->g_cent, ctx->t_global, ctx->scratch_a, ctx->scratch_b, ctx->g_best_idx,
+                                                  ctx->g_best_w, ctx->sc);
+    LAUNCHED();
+    return read_scalars(ctx);
+}
+
+extern "C" {
 
 int eslam_gpu_project(eslam_gpu_ctx* ctx, const eslam_gpu_step* step) {
     int st = check_ready(ctx, false);
@@ -486,15 +668,6 @@ int eslam_gpu_get_cdf(eslam_gpu_ctx* ctx, double* c) {
     CK(cudaMemcpyAsync(c, ctx->cdf, ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return ESLAM_OK;
-}
-
-static int launch_centroid(eslam_gpu_ctx* ctx) {
-    k_centroid_tiles<<<ctx->n_tiles, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->n, ctx->cent_part, ctx->n_tiles,
-                                                            ctx->best_idx, ctx->best_w);
-    LAUNCHED();
-    k_centroid_final<<<1, 1024, 0, ctx->stream>>>(ctx->cent_part, ctx->n_tiles, ctx->scratch_b, ctx->best_idx, ctx->best_w, ctx->sc);
-    LAUNCHED();
-    return read_scalars(ctx);
 }
 
 int eslam_gpu_centroid(eslam_gpu_ctx* ctx, double out[4]) {

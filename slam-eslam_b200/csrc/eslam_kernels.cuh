@@ -74,6 +74,7 @@ struct ContactSet {              // odometry::BodyContactState after setContactP
 struct MapParams {
     const float2* cells; int W, H;
     double sx, sy, ox, oy, inv_sx, inv_sy;
+    double c0x, c0y;             // 1.5*2^34 - offset*inv_scale (fixed-point cell index, see contact_eval)
     double g2l[8];               // rows 0 and 1 of C_global2local
     int identity;
     int tile_w, tile_h;          // shared-memory tile (cells)
@@ -153,58 +154,42 @@ __device__ double block_tree_reduce(double* a, double* b, unsigned n) {
 // ------------------------------------------------------------------------------------------------ map lookup
 struct MapTile { const float2* s; int x0, y0, w, h; };
 
-#define IDX_FRAC_BITS 18
-__device__ __forceinline__ bool axis_index(double g, double off, double scale, double inv, int n, int& idx) {
-    // floor((g - off)/scale) without the division: multiply by the reciprocal, take the floor from the low mantissa
-    // bits after adding 1.5*2^34 (18 fractional bits), and only when that fixed-point value is an exact integer
-    // (the quotient is within 2^-19 of a cell border) fall back to the exact IEEE division of eslam_math.h.
-    const double q = g - off;
-    const double m = q * inv + 25769803776.0;            // 1.5 * 2^34
-    const uint64_t u = em::d2u(m);
-    const int k = (int)(uint32_t)u;
-    const uint32_t hi = (uint32_t)(u >> 32);
-    if (((hi - 0x4217FFFFu) <= 1u) && ((k & ((1 << IDX_FRAC_BITS) - 1)) != 0)) {
-        idx = k >> IDX_FRAC_BITS;
-        return (unsigned)idx < (unsigned)n;
-    }
-    return em::cell_index_exact(g, off, scale, n, idx);
-}
-
-__device__ __forceinline__ bool cell_lookup(const MapParams& M, const MapTile& mt, double wx, double wy, double wz,
-                                            float2& cell, int& flat) {
-    double gx = wx, gy = wy;
-    if (!M.identity) {
-        gx = em::fma_(M.g2l[0], wx, em::fma_(M.g2l[1], wy, em::fma_(M.g2l[2], wz, M.g2l[3])));
-        gy = em::fma_(M.g2l[4], wx, em::fma_(M.g2l[5], wy, em::fma_(M.g2l[6], wz, M.g2l[7])));
-    }
-    int ix, iy;
-    if (!axis_index(gx, M.ox, M.sx, M.inv_sx, M.W, ix)) return false;
-    if (!axis_index(gy, M.oy, M.sy, M.inv_sy, M.H, iy)) return false;
-    flat = iy * M.W + ix;
-    const unsigned lx = (unsigned)(ix - mt.x0), ly = (unsigned)(iy - mt.y0);
-    if (lx < (unsigned)mt.w && ly < (unsigned)mt.h) cell = mt.s[ly * mt.w + lx];
-    else cell = __ldg(&M.cells[flat]);
-    return true;
-}
+#define IDX_FRAC_BITS 18         // fractional bits of the fixed-point cell quotient (see contact_eval)
 
 // ------------------------------------------------------------------------------------------------ contact model
 struct PoseEval { int n_found; double d1, d2, A, poseVar; };
 
+// One map cell from the shared-memory tile or from global memory (L2), predicated: no branch, no generic pointer.
+__device__ __forceinline__ float2 load_cell(bool in_tile, uint32_t tile_saddr, const float2* gptr) {
+    float2 v;
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " setp.ne.s32 p, %4, 0;\n"
+        " @p ld.shared.v2.f32 {%0, %1}, [%2];\n"
+        " @!p ld.global.nc.v2.f32 {%0, %1}, [%3];\n"
+        "}\n"
+        : "=f"(v.x), "=f"(v.y)
+        : "r"(tile_saddr), "l"(gptr), "r"((int)in_tile));
+    return v;
+}
+
 // ContactModel::evaluatePose (src/ContactModel.cpp:117-224) for one pose; SHARED arithmetic policy.
-// Written straight-line: every lane computes every evaluated contact, lanes whose group is already invalid are masked
-// out of the accumulation; the rare cases (cell-border quotient, variance or t outside the table) take one slow branch.
+// Written straight-line: every lane computes every evaluated contact; lanes whose group is already invalid, or whose
+// lookup misses, contribute a zero ratio.  The rare cases (quotient within 2^-18 of a cell border, variance or t
+// outside the table) take one slow branch each.
 template <bool TAP>
 __device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapParams& M, const MapTile& mt,
                                              const em::dbl2* htab, double inv_corr,
                                              double x, double y, double z, double s, double c, double mv,
                                              PoseEval& out, int32_t* tap_cells, double* tap_cp) {
-    bool valid = false, group_valid = true;
+    int valid = 0, gvalid = 1;                                           // :134-135
     double acc_d = 0, acc_v = 0, acc_r = 0, acc_p = 0;
     double pt_x = 0, pt_y = 0, pt_z = 0;
     out.n_found = 0; out.d1 = 0; out.d2 = 0; out.A = 0; out.poseVar = 0;
     const int n = cs.n;
-    const double MAGIC = 25769803776.0;                                  // 1.5 * 2^34: 18 fractional bits
     const int FRAC_MASK = (1 << IDX_FRAC_BITS) - 1;
+    const uint32_t tile_sa = (uint32_t)__cvta_generic_to_shared(mt.s);
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
         const unsigned f = cs.flags[i];
@@ -219,43 +204,45 @@ __device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapPara
                 gx = em::fma_(M.g2l[0], wx, em::fma_(M.g2l[1], wy, em::fma_(M.g2l[2], wz, M.g2l[3])));
                 gy = em::fma_(M.g2l[4], wx, em::fma_(M.g2l[5], wy, em::fma_(M.g2l[6], wz, M.g2l[7])));
             }
-            // cell index floor((g - offset)/scale): reciprocal multiply + floor from the mantissa (see axis_index)
-            const uint64_t ux = em::d2u((gx - M.ox) * M.inv_sx + MAGIC), uy = em::d2u((gy - M.oy) * M.inv_sy + MAGIC);
+            // cell index floor((g - offset)/scale): g*inv + (1.5*2^34 - offset*inv) puts the quotient with 18 fractional
+            // bits into the low mantissa word (error < 2^-18); when the fraction is within one step of an integer
+            // (or the quotient is out of the fixed-point range) the exact IEEE division of eslam_math.h decides.
+            const uint64_t ux = em::d2u(em::fma_(gx, M.inv_sx, M.c0x)), uy = em::d2u(em::fma_(gy, M.inv_sy, M.c0y));
             const int kx = (int)(uint32_t)ux, ky = (int)(uint32_t)uy;
             int ix = kx >> IDX_FRAC_BITS, iy = ky >> IDX_FRAC_BITS;
-            const bool fast = (((uint32_t)(ux >> 32) - 0x4217FFFFu) <= 1u) & ((kx & FRAC_MASK) != 0) &
-                              (((uint32_t)(uy >> 32) - 0x4217FFFFu) <= 1u) & ((ky & FRAC_MASK) != 0);
+            const bool fast = (((uint32_t)(ux >> 32) - 0x4217FFFFu) <= 1u) & (((kx + 1) & FRAC_MASK) > 2) &
+                              (((uint32_t)(uy >> 32) - 0x4217FFFFu) <= 1u) & (((ky + 1) & FRAC_MASK) > 2);
             bool inb = ((unsigned)ix < (unsigned)M.W) & ((unsigned)iy < (unsigned)M.H);
-            if (!fast) {                                                 // rare: exact IEEE division
+            if (!fast) {                                                 // rare
                 inb = em::cell_index_exact(gx, M.ox, M.sx, M.W, ix);
                 if (inb) inb = em::cell_index_exact(gy, M.oy, M.sy, M.H, iy);
             }
             const int flat = inb ? iy * M.W + ix : 0;
             const unsigned lx = (unsigned)(ix - mt.x0), ly = (unsigned)(iy - mt.y0);
             const bool in_tile = inb & (lx < (unsigned)mt.w) & (ly < (unsigned)mt.h);
-            const float2* src = in_tile ? (mt.s + ly * mt.w + lx) : (M.cells + flat);
-            const float2 cell = *src;                                    // generic load: shared tile or global (L2)
-            if (TAP) tap_cells[i] = (inb && group_valid) ? flat : -1;
-            const double d = wz - (double)cell.x;                        // :160
-            const double sp2 = (double)cell.y * (double)cell.y;          // :166
+            const float2 cell = load_cell(in_tile, tile_sa + (ly * mt.w + lx) * 8u, M.cells + flat);
+            if (TAP) tap_cells[i] = (inb && gvalid) ? flat : -1;
+            // candidate lanes: group still valid, inside the grid, cell not empty (NaN mean; a NaN stdev misses too).
+            // Non-candidate lanes compute on zeros so that everything below stays finite for them.
+            const bool cand = (gvalid != 0) & inb & (cell.x == cell.x) & (cell.y == cell.y);
+            const float cm = cand ? cell.x : 0.0f, csd = cand ? cell.y : 0.0f;
+            const double d = wz - (double)cm;                            // :160
+            const double sp2 = (double)csd * (double)csd;                // :166
             const double zvar = sp2 + mv;                                // :167
-            // map hit: inside the grid, cell not empty (NaN mean), 3-sigma patch gate of MLSMap::getPatch
-            const bool use = group_valid & inb & (cell.x == cell.x) & (d * d < 9.0 * zvar);
+            const bool use = cand & (d * d < 9.0 * zvar);                // 3-sigma patch gate of MLSMap::getPatch
             bool rare;
             double ratio = em::likelihood_ratio_fast(d, zvar, inv_corr, htab, rare);           // :170
             if (rare & use) ratio = em::likelihood_ratio(d, zvar, inv_corr, htab);
-            if (use) {                                                   // :172-185
-                if (TAP && !valid) { pt_x = wx; pt_y = wy; pt_z = (double)cell.x; }
-                acc_d = em::fma_(d, ratio, acc_d); acc_v = em::fma_(zvar, ratio, acc_v);
-                acc_r += ratio; acc_p = em::fma_(sp2, ratio, acc_p);
-                valid = true;
-            } else {
-                group_valid = false;                                     // :189-190 (stays false if it already was)
-            }
+            const double r_eff = use ? ratio : 0.0;
+            if (TAP && use && !valid) { pt_x = wx; pt_y = wy; pt_z = (double)cell.x; }
+            acc_d = em::fma_(d, r_eff, acc_d); acc_v = em::fma_(zvar, r_eff, acc_v);           // :172-184
+            acc_r += r_eff; acc_p = em::fma_(sp2, r_eff, acc_p);
+            valid |= (int)use;                                           // :185
+            gvalid &= (int)use;                                          // :189-190
         }
         if (f & 2u) {                                                    // :194-197 end of group: warp-uniform
             if (valid) {
-                if (group_valid && acc_r > 1e-9) {                       // :199
+                if (gvalid && acc_r > 1e-9) {                            // :199
                     const double zd = acc_d / acc_r, zv = acc_v / acc_r; // :201-202
                     out.poseVar += acc_p / acc_r;                        // :203
                     const double e = zd / zv;
@@ -266,7 +253,7 @@ __device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapPara
                     }
                     out.n_found++;
                 }
-                group_valid = true; valid = false;                       // :210-213 (only when valid: Q4)
+                gvalid = 1; valid = 0;                                   // :210-213 (only when valid: Q4)
                 acc_d = acc_v = acc_r = acc_p = 0;
             }
         }
@@ -686,7 +673,7 @@ __device__ __forceinline__ TileScan tile_scan(double w, bool active, double tile
 __global__ void __launch_bounds__(1024, 1) k_norm_scan(StateBufs st, const DevScalars* sc, unsigned long long n,
                                                        unsigned long long n_global, const double* tile_prefix,
                                                        double* tile_sq, TileDesc* desc, BndEntry* pool, DevScalars* scw, int normalise,
-                                                       double eps) {
+                                                       double eps, unsigned tile_ofs) {
     __shared__ TileScanSmem sm;
     __shared__ double red[32];
     __shared__ int slot_of[TILE];
@@ -706,7 +693,7 @@ __global__ void __launch_bounds__(1024, 1) k_norm_scan(StateBufs st, const DevSc
     const double sq = tile_tree_sum_1024(w * w, red);                                 // effective += w*w
     if (threadIdx.x == 0) tile_sq[blockIdx.x] = sq;
 
-    const TileScan ts = tile_scan(w, active, tile_prefix[blockIdx.x], eps, sm);
+    const TileScan ts = tile_scan(w, active, tile_prefix[tile_ofs + blockIdx.x], eps, sm);
     TileDesc* D = &desc[blockIdx.x];
     slot_of[threadIdx.x] = ts.bnd_before;
     if (threadIdx.x == 0) {
@@ -744,7 +731,8 @@ struct ChainSmem { double bw[MAX_BND_TOTAL]; SegF seg[MAX_BND_TOTAL]; };
 __global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, const BndEntry* pool, unsigned n_tiles, const double* tile_sq,
                                                    DevScalars* sc, double* scratch_a, double* scratch_b,
                                                    int* tile_bofs, SegF* tile_pre, double* tile_sin, double* sb_out,
-                                                   unsigned long long min_effective, int decide, int force) {
+                                                   unsigned long long min_effective, int decide, int force,
+                                                   unsigned tiles_per_rank) {
     extern __shared__ __align__(16) unsigned char chain_raw[];
     ChainSmem& cs = *reinterpret_cast<ChainSmem*>(chain_raw);
     __shared__ int sh_i[1024];
@@ -777,7 +765,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, const B
         cnt += D.n_bnd;
         SegE e;
         if (D.n_bnd > 0 && !D.overflow) {
-            const BndEntry& L = pool[D.bnd_base + D.n_bnd - 1];
+            const BndEntry& L = pool[(size_t)(t / tiles_per_rank) * MAX_BND_TOTAL + D.bnd_base + D.n_bnd - 1];
             e.head = (int)t; e.f.b = L.b; e.f.d0 = L.d0; e.f.d1 = L.d1; e.f.pad = 0;
         } else { e.head = -1; e.f.b = D.head_b; e.f.d0 = D.head_d0; e.f.d1 = D.head_d1; e.f.pad = D.pad; }
         agg = sege_combine(agg, e);
@@ -806,7 +794,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, const B
         const TileDesc& D = desc[t];
         tile_bofs[t] = run_c; tile_pre[t] = run_e.f;
         // boundary k = run_c + j: weight, and the function of the segment that follows it
-        const BndEntry* B = pool + D.bnd_base;
+        const BndEntry* B = pool + (size_t)(t / tiles_per_rank) * MAX_BND_TOTAL + D.bnd_base;
         for (int j = 0; j < D.n_bnd; ++j) {
             cs.bw[run_c + j] = B[j].w;
             if (j + 1 < D.n_bnd) { SegF f; f.b = B[j].b; f.d0 = B[j].d0; f.d1 = B[j].d1; f.pad = 0; cs.seg[run_c + j] = f; }
@@ -849,7 +837,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, const B
 // exact running sum of every element: cdf[i] == the reference's sum_w after adding xi_k[i].weight
 __global__ void __launch_bounds__(1024, 1) k_cdf(StateBufs st, DevScalars* sc, unsigned long long n,
                                                  const double* tile_prefix, const int* tile_bofs, const double* tile_sin,
-                                                 const double* sb, double* cdf, double eps) {
+                                                 const double* sb, double* cdf, double eps, unsigned tile_ofs) {
     __shared__ TileScanSmem sm;
     __shared__ int slot_of[TILE];
     if (!sc->do_resample || (sc->error_flags & ERR_CDF_FALLBACK_BIT)) return;
@@ -857,14 +845,15 @@ __global__ void __launch_bounds__(1024, 1) k_cdf(StateBufs st, DevScalars* sc, u
     const unsigned long long i = (unsigned long long)blockIdx.x * TILE + threadIdx.x;
     const bool active = i < n;
     const double w = active ? st.f[cur][F_W][i] : 0.0;
-    const TileScan ts = tile_scan(w, active, tile_prefix[blockIdx.x], eps, sm);
+    const unsigned gt = tile_ofs + blockIdx.x;
+    const TileScan ts = tile_scan(w, active, tile_prefix[gt], eps, sm);
     slot_of[threadIdx.x] = ts.bnd_before;
     __syncthreads();
     int bad = 0;
     double S;
-    const int ofs = tile_bofs[blockIdx.x];
+    const int ofs = tile_bofs[gt];
     if (ts.cls.kind == 2) S = sb[ofs + ts.bnd_before];
-    else if (ts.inc.head < 0) S = segf_apply(tile_sin[blockIdx.x], ts.inc.f, bad);
+    else if (ts.inc.head < 0) S = segf_apply(tile_sin[gt], ts.inc.f, bad);
     else S = segf_apply(sb[ofs + slot_of[ts.inc.head]], ts.inc.f, bad);
     if (bad) atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT);
     if (active) cdf[i] = S;
@@ -881,10 +870,12 @@ __global__ void k_cdf_sequential(StateBufs st, DevScalars* sc, unsigned long lon
 }
 
 // ------------------------------------------------------------------------------------------------ resample
-// the stratified walk (src/ParticleFilter.hpp:96-105) as a lower-bound search: ancestor[k] = first idx with !(cdf[idx] < sum_r)
-__global__ void k_search(const DevScalars* sc, const double* __restrict__ cdf, unsigned long long n,
-                         unsigned long long n_global, unsigned long long base, uint32_t k0, uint32_t k1,
-                         int systematic, uint32_t* ancestors) {
+// the stratified walk (src/ParticleFilter.hpp:96-105) as a lower-bound search: ancestor[k] = first idx with
+// !(cdf[idx] < sum_r).  cdf_win holds the exact running sum of global elements [win_base, win_base + win_len)
+// (the whole local array on one GPU; the window fetched from the owning ranks otherwise).
+__global__ void k_search(const DevScalars* sc, const double* __restrict__ cdf_win, unsigned long long win_len,
+                         unsigned long long win_base, unsigned long long n, unsigned long long n_global,
+                         unsigned long long base, uint32_t k0, uint32_t k1, int systematic, uint32_t* ancestors) {
     if (!sc->do_resample) return;
     const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -892,24 +883,35 @@ __global__ void k_search(const DevScalars* sc, const double* __restrict__ cdf, u
     const em::Philox4 r = em::philox4x32_10((uint32_t)gk, sc->resample_step, 0, stream_word(em::STREAM_RESAMPLE, gk), k0, k1);
     const double u = em::u01(r.v[0], r.v[1]);
     const double sum_r = ((double)(base + k) + u) / (double)n_global;                // :98
-    unsigned long long lo = 0, hi = n;                                               // first idx in [0,n) with cdf >= sum_r
+    unsigned long long lo = 0, hi = win_len;
     while (lo < hi) {
         const unsigned long long mid = (lo + hi) >> 1;
-        if (__ldg(&cdf[mid]) < sum_r) lo = mid + 1; else hi = mid;
+        if (__ldg(&cdf_win[mid]) < sum_r) lo = mid + 1; else hi = mid;
     }
-    if (lo >= n) lo = n - 1;                      // the reference walks off the end here; we stop at the last particle
+    lo += win_base;
+    if (lo >= n_global) lo = n_global - 1;        // the reference walks off the end here; we stop at the last particle
     ancestors[k] = (uint32_t)lo;
 }
 
-__global__ void k_gather(StateBufs st, const DevScalars* sc, unsigned long long n, const uint32_t* __restrict__ anc) {
+struct GatherSrc { const double* f[7]; const uint8_t* b[2]; unsigned long long base; int use_window; };
+
+__global__ void k_gather(StateBufs st, const DevScalars* sc, unsigned long long n, const uint32_t* __restrict__ anc,
+                         GatherSrc src) {
     if (!sc->do_resample) return;
     const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int cur = sc->cur, nxt = cur ^ 1;
-    const uint32_t a = anc[k];
+    const unsigned long long a = (unsigned long long)anc[k] - src.base;
 #pragma unroll
-    for (int f = 0; f < 7; ++f) st.f[nxt][f][k] = st.f[cur][f][a];                    // :104 copy keeps the weight (Q3)
-    st.b[nxt][0][k] = st.b[cur][0][a]; st.b[nxt][1][k] = st.b[cur][1][a];
+    for (int f = 0; f < 7; ++f) {
+        const double* in = src.use_window ? src.f[f] : st.f[cur][f];
+        st.f[nxt][f][k] = in[a];                                                     // :104 copy keeps the weight (Q3)
+    }
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+        const uint8_t* in = src.use_window ? src.b[f] : st.b[cur][f];
+        st.b[nxt][f][k] = in[a];
+    }
 }
 
 __global__ void k_after_resample(DevScalars* sc) {
@@ -920,7 +922,7 @@ __global__ void k_after_resample(DevScalars* sc) {
 
 // ------------------------------------------------------------------------------------------------ outputs
 __global__ void __launch_bounds__(1024, 1) k_centroid_tiles(StateBufs st, const DevScalars* sc, unsigned long long n,
-                                                            double* part /* 5 x n_tiles */, unsigned n_tiles,
+                                                            unsigned long long base, double* part /* n_tiles x 5 */,
                                                             unsigned long long* best_idx, double* best_w) {
     __shared__ double red[32];
     __shared__ unsigned long long bi[32];
@@ -931,11 +933,11 @@ __global__ void __launch_bounds__(1024, 1) k_centroid_tiles(StateBufs st, const 
     const double sx = tile_tree_sum_1024(x, red), sy = tile_tree_sum_1024(y, red);
     const double st_ = tile_tree_sum_1024(th, red), sz = tile_tree_sum_1024(z, red), sw = tile_tree_sum_1024(w, red);
     if (threadIdx.x == 0) {
-        part[blockIdx.x] = sx; part[n_tiles + blockIdx.x] = sy; part[2 * n_tiles + blockIdx.x] = st_;
-        part[3 * n_tiles + blockIdx.x] = sz; part[4 * n_tiles + blockIdx.x] = sw;
+        double* o = part + (size_t)blockIdx.x * 5;
+        o[0] = sx; o[1] = sy; o[2] = st_; o[3] = sz; o[4] = sw;
     }
     // first index of the strict maximum (src/ParticleFilter.hpp:160-173)
-    double bw = (i < n) ? st.f[cur][F_W][i] : -INFINITY; unsigned long long bidx = (i < n) ? i : ~0ull;
+    double bw = (i < n) ? st.f[cur][F_W][i] : -INFINITY; unsigned long long bidx = (i < n) ? base + i : ~0ull;
     if (!(bw == bw)) bw = -INFINITY;   // NaN never wins the > comparison
     for (int o = 1; o < 32; o <<= 1) {
         const double ow = __shfl_xor_sync(0xffffffffu, bw, o); const unsigned long long oi = __shfl_xor_sync(0xffffffffu, bidx, o);
@@ -950,11 +952,13 @@ __global__ void __launch_bounds__(1024, 1) k_centroid_tiles(StateBufs st, const 
     }
 }
 
-__global__ void __launch_bounds__(1024, 1) k_centroid_final(double* part, unsigned n_tiles, double* scratch_b,
-                                                            const unsigned long long* best_idx, const double* best_w,
-                                                            DevScalars* sc) {
+__global__ void __launch_bounds__(1024, 1) k_centroid_final(const double* part, unsigned n_tiles, double* scratch_a,
+                                                            double* scratch_b, const unsigned long long* best_idx,
+                                                            const double* best_w, DevScalars* sc) {
     for (int q = 0; q < 5; ++q) {
-        const double v = block_tree_reduce(part + (size_t)q * n_tiles, scratch_b, n_tiles);
+        for (unsigned t = threadIdx.x; t < n_tiles; t += blockDim.x) scratch_a[t] = part[(size_t)t * 5 + q];
+        __syncthreads();
+        const double v = block_tree_reduce(scratch_a, scratch_b, n_tiles);
         if (threadIdx.x == 0) sc->centroid[q] = v;
         __syncthreads();
     }

@@ -257,7 +257,7 @@ ESLAM_HD void box_muller(double u1, double u2, double& n0, double& n1) {
 
 // ---------------------------------------------------------------- 1/sqrt
 // ~1.5 ulp, deterministic: fp32 magic seed + 3 fp32 Newton steps + one fp64 Halley step.
-// rsqrt_core is valid for x in (1e-30, 1e30); rsqrt_ adds the out-of-range fallback.
+// rsqrt_core is valid for x in [2^-100, 2^100); rsqrt_ adds the out-of-range fallback.
 ESLAM_HD double rsqrt_core(double x) {
     float xf = (float)x;
     float y = u2f(0x5f3759dfu - (f2u(xf) >> 1));
@@ -272,7 +272,8 @@ ESLAM_HD double rsqrt_core(double x) {
     double p = fma_(0.375, e, 0.5);
     return fma_(yd, e * p, yd);
 }
-ESLAM_HD bool rsqrt_in_range(double x) { return x > 1e-30 && x < 1e30; }
+// 2^-100 <= x < 2^100 (and positive, finite), decided on the exponent bits
+ESLAM_HD bool rsqrt_in_range(double x) { return ((uint32_t)(d2u(x) >> 52) - 923u) < 200u; }
 ESLAM_HD double rsqrt_(double x) {
     if (!rsqrt_in_range(x)) return 1.0 / sqrt_(x);
     return rsqrt_core(x);
@@ -305,7 +306,7 @@ ESLAM_HD double h_slow(double t) {
     return f;
 }
 
-ESLAM_HD bool h_in_range(double t) { return t >= -ESLAM_H_TMAX && t < ESLAM_H_TMAX; }
+ESLAM_HD bool h_in_range(double t) { return fabs(t) < ESLAM_H_TMAX; }
 // table evaluation, valid for h_in_range(t) (any other input reads a clamped interval: garbage, never out of bounds).
 // interval index and centred coordinate come from one magic-number rounding: no int<->double conversions.
 ESLAM_HD double h_core(double t, const dbl2* tab) {

@@ -159,13 +159,12 @@ class FilterBase:
 class GpuPoseEstimator(FilterBase):
     """eslam::PoseEstimator on one B200 (one context per GPU / rank)."""
 
-    def __init__(self, config=None, device=0, shard=None, comm=None):
+    def __init__(self, config=None, device=0, shard=None):
         lib = abi.load_library()
         cfg = config if config is not None else abi.default_config()
         ctx = C.c_void_p()
-        self._keepalive = (cfg, shard, comm)
-        st = lib.eslam_gpu_create(C.byref(cfg), int(device), None if shard is None else C.byref(shard),
-                                  None if comm is None else C.byref(comm), C.byref(ctx))
+        self._keepalive = (cfg, shard)
+        st = lib.eslam_gpu_create(C.byref(cfg), int(device), None if shard is None else C.byref(shard), C.byref(ctx))
         if st != abi.OK:
             raise RuntimeError("eslam_gpu_create failed with status %d (is a CUDA device visible?)" % st)
         super().__init__(lib, "eslam_gpu_", ctx)
@@ -174,6 +173,11 @@ class GpuPoseEstimator(FilterBase):
     def _detail(self):
         msg = self._lib.eslam_gpu_last_error(self._ctx)
         return (": " + msg.decode()) if msg else ""
+
+    def commInit(self, unique_id):
+        """Join the NCCL communicator of a sharded filter; unique_id = 128 bytes from abi nccl_unique_id()."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self._lib.eslam_gpu_comm_init(self._ctx, buf))
 
     def close(self):
         if self._ctx:

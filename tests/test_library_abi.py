@@ -59,7 +59,7 @@ def test_no_cpu_fallback(lib_path):
     lib = abi.load_library(lib_path)
     ctx = ctypes.c_void_p()
     cfg = abi.default_config()
-    assert lib.eslam_gpu_create(ctypes.byref(cfg), 0, None, None, ctypes.byref(ctx)) == abi.ERR_CUDA
+    assert lib.eslam_gpu_create(ctypes.byref(cfg), 0, None, ctypes.byref(ctx)) == abi.ERR_CUDA
     with pytest.raises(RuntimeError):
         from slam_eslam_b200 import GpuPoseEstimator
         GpuPoseEstimator()
