@@ -104,6 +104,10 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
  * all-gathers of per-tile partials / scan descriptors and contiguous-range send/recv for resampling. */
 int eslam_gpu_nccl_unique_id(uint8_t out[128]);
 int eslam_gpu_comm_init(eslam_gpu_ctx* ctx, const uint8_t unique_id[128]);
+/* Host-only planning step of sharded resampling: element range [begin[r], end[r]) that holds every possible ancestor
+ * of rank r's strata, from the exact running sum before each 1024-particle tile (n_tiles = world * n_local / 1024). */
+int eslam_gpu_plan_windows(const double* tile_start_sum, unsigned n_tiles, uint64_t n_local, int world,
+                           uint64_t* begin, uint64_t* end);
 void eslam_gpu_destroy(eslam_gpu_ctx* ctx);
 const char* eslam_gpu_last_error(const eslam_gpu_ctx* ctx);
 

@@ -129,6 +129,7 @@ GPU_ONLY = {
     "create": (C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(Shard), C.POINTER(C.c_void_p)]),
     "nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "comm_init": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8)]),
+    "plan_windows": (C.c_int, [_dp, C.c_uint, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "destroy": (None, [C.c_void_p]),
     "last_error": (C.c_char_p, [C.c_void_p]),
     "step_fused": (C.c_int, [C.c_void_p, C.POINTER(Step), C.POINTER(Contact), C.c_int, C.POINTER(UpdateResult)]),

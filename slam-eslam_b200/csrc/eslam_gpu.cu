@@ -399,6 +399,29 @@ static unsigned weight_grid(const eslam_gpu_ctx* ctx) {
     return ctx->t_local < (unsigned)ctx->sm_count ? ctx->t_local : (unsigned)ctx->sm_count;
 }
 
+// Pure host logic (no device needed): which contiguous element range [begin, end) holds every possible ancestor of the
+// strata owned by each rank, given the exact running sum before each 1024-particle tile.  Stratum k draws
+// sum_r = (k + u)/N with u in [0,1), so rank r's draws lie in [r n/N, (r+1) n/N); the ancestor of sum_r is the first
+// element whose running sum is >= sum_r, which lies in the last tile whose starting sum is still below sum_r.
+extern "C" int eslam_gpu_plan_windows(const double* tile_start_sum, unsigned n_tiles, uint64_t n_local, int world,
+                                      uint64_t* begin, uint64_t* end) {
+    if (!tile_start_sum || !begin || !end || world <= 0 || n_tiles == 0) return ESLAM_ERR_INVALID;
+    const uint64_t N = n_local * (uint64_t)world;
+    auto last_tile_below = [&](double thr) -> unsigned {                // max t with S[t] < thr (0 if none)
+        unsigned lo = 0, hi = n_tiles;                                  // first t with !(S[t] < thr)
+        while (lo < hi) { unsigned mid = (lo + hi) / 2; if (tile_start_sum[mid] < thr) lo = mid + 1; else hi = mid; }
+        return lo == 0 ? 0 : lo - 1;
+    };
+    for (int r = 0; r < world; ++r) {
+        const double lo_thr = (double)((uint64_t)r * n_local) / (double)N;
+        const double hi_thr = (double)((uint64_t)(r + 1) * n_local) / (double)N;
+        const unsigned tlo = last_tile_below(lo_thr), thi = last_tile_below(hi_thr);
+        begin[r] = (uint64_t)tlo * TILE;
+        end[r] = std::min<uint64_t>(((uint64_t)thi + 1) * TILE, N);
+    }
+    return ESLAM_OK;
+}
+
 // Sharded resampling, exact-global mode: every rank knows the exact running sum at every tile start (k_chain ran on
 // the all-gathered descriptors), so every rank can tell which contiguous element range holds the ancestors of each
 // rank's strata; the owners send exactly those ranges (running sum + particle state), then search and gather run on
@@ -416,18 +439,8 @@ static int resample_exchange(eslam_gpu_ctx* ctx) {
     const unsigned T = ctx->t_global;
     CK(cudaMemcpyAsync(ctx->tile_sin_host, ctx->tile_sin, T * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    const double* S = ctx->tile_sin_host;                               // exact running sum before each tile
-    auto last_tile_below = [&](double thr) -> unsigned {                // max t with S[t] < thr (0 if none)
-        unsigned lo = 0, hi = T;                                        // first t with !(S[t] < thr)
-        while (lo < hi) { unsigned mid = (lo + hi) / 2; if (S[mid] < thr) lo = mid + 1; else hi = mid; }
-        return lo == 0 ? 0 : lo - 1;
-    };
     std::vector<uint64_t> wb(G), we(G);                                 // window [wb, we) of every rank
-    for (int r = 0; r < G; ++r) {
-        const double lo_thr = (double)((uint64_t)r * n) / (double)N, hi_thr = (double)((uint64_t)(r + 1) * n) / (double)N;
-        const unsigned tlo = last_tile_below(lo_thr), thi = last_tile_below(hi_thr);
-        wb[r] = (uint64_t)tlo * TILE; we[r] = std::min<uint64_t>(((uint64_t)thi + 1) * TILE, N);
-    }
+    eslam_gpu_plan_windows(ctx->tile_sin_host, T, n, G, wb.data(), we.data());
     const uint64_t wlen = we[me] - wb[me];
     if (wlen > ctx->win_cap) {
         free_window(ctx);
