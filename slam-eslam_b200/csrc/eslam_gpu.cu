@@ -6,7 +6,9 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <chrono>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -427,7 +429,16 @@ extern "C" int eslam_gpu_plan_windows(const double* tile_start_sum, unsigned n_t
 // rank's strata; the owners send exactly those ranges (running sum + particle state), then search and gather run on
 // the received window.  Ancestor indices are global and identical to the one-GPU run.
 static int resample_exchange(eslam_gpu_ctx* ctx) {
+    const bool trace = getenv("ESLAM_GPU_TRACE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[eslam rank %d] %s: %.1f us\n", ctx->shard.rank, what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+        t0 = t1;
+    };
     int st = read_scalars(ctx);                                         // host needs: resample? which buffer? fallback?
+    lap("wait for the step so far + scalars");
     if (st != ESLAM_OK) return st;
     if (!ctx->sc_host->do_resample) return ESLAM_OK;
     if (ctx->sc_host->error_flags & ERR_CDF_FALLBACK_BIT) {
@@ -441,14 +452,19 @@ static int resample_exchange(eslam_gpu_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     std::vector<uint64_t> wb(G), we(G);                                 // window [wb, we) of every rank
     eslam_gpu_plan_windows(ctx->tile_sin_host, T, n, G, wb.data(), we.data());
+    lap("tile sums to host + plan");
     const uint64_t wlen = we[me] - wb[me];
-    if (wlen > ctx->win_cap) {
+    if (wlen > ctx->win_cap) {                                          // grow with headroom: windows move by tiles
         free_window(ctx);
-        CK(dalloc(&ctx->win_cdf, wlen));
-        for (int f = 0; f < 7; ++f) CK(dalloc(&ctx->win_f[f], wlen));
-        for (int f = 0; f < 2; ++f) CK(dalloc(&ctx->win_b[f], wlen));
-        ctx->win_cap = wlen;
+        const uint64_t cap = std::max<uint64_t>(wlen + wlen / 4, n + 8 * TILE);
+        CK(dalloc(&ctx->win_cdf, cap));
+        for (int f = 0; f < 7; ++f) CK(dalloc(&ctx->win_f[f], cap));
+        for (int f = 0; f < 2; ++f) CK(dalloc(&ctx->win_b[f], cap));
+        ctx->win_cap = cap;
     }
+    if (getenv("ESLAM_GPU_TRACE"))
+        fprintf(stderr, "[eslam rank %d] window [%llu, %llu) = %llu elements (own %llu)\n", me,
+                (unsigned long long)wb[me], (unsigned long long)we[me], (unsigned long long)wlen, (unsigned long long)n);
     // arrays to move: running sum, 7 doubles, 2 bytes
     const void* src[10]; void* dst[10]; size_t esz[10];
     src[0] = ctx->cdf; dst[0] = ctx->win_cdf; esz[0] = 8;
@@ -474,6 +490,7 @@ static int resample_exchange(eslam_gpu_ctx* ctx) {
         }
     }
     NK(g_nccl.GroupEnd());
+    lap("enqueue range exchange");
     const ModelParams mp = model_params(ctx);
     const unsigned blocks = (unsigned)((n + 255) / 256);
     k_search<<<blocks, 256, 0, ctx->stream>>>(ctx->sc, ctx->win_cdf, wlen, wb[me], n, N, base_index(ctx), mp.k0, mp.k1,
