@@ -91,6 +91,7 @@ struct Vec3 { double x, y, z; };
 
 struct ContactPoint {          // src/PoseParticle.hpp:20-43
     Vec3 point; double zdiff, zvar, prob;
+    int cell_ix, cell_iy;      // map cell of `point` (used by the per-particle patch write)
 };
 
 struct PoseParticle {          // src/PoseParticle.hpp:52-86 (hot fields)
@@ -155,7 +156,6 @@ struct eslam_oracle_ctx {
     double sh_d1 = 0, sh_d2 = 0, sh_A = 0;
     // per-particle patches
     std::vector<float> patches; std::vector<int32_t> patch_origin;
-    std::vector<ContactPoint> last_cps; std::vector<uint8_t> last_ncp;
 
     eslam_oracle_ctx(const eslam_gpu_config& c, int pol) : cfg(c), policy(pol), noise(c.seed) {
         shard.rank = 0; shard.world = 1; shard.global_count = 0;
@@ -163,8 +163,9 @@ struct eslam_oracle_ctx {
 
     // --- map seam: GridAccess::get -> MLSMap::getPatch(C_global2local*pos, patch, 3.0)  src/PoseEstimator.hpp:97-105
     template <class A>
-    bool map_get(const Vec3& pos, SurfacePatch& patch, double measVar, int32_t* cell_out) {
+    bool map_get(const Vec3& pos, SurfacePatch& patch, double measVar, int32_t* cell_out, long particle, int* cix, int* ciy) {
         if (cell_out) *cell_out = -1;
+        *cix = *ciy = -1;
         if (fake.active) {                                      // test/testContactModel.cpp:18-37
             fake.points.push_back(pos);
             int index = 0;
@@ -194,8 +195,32 @@ struct eslam_oracle_ctx {
         if (!em::cell_index_exact(gy, grid.oy, grid.sy, grid.h, iy)) return false;
         const size_t cell = (size_t)iy * grid.w + ix;
         if (cell_out) *cell_out = (int32_t)cell;
-        const float mean = grid.cells[2 * cell], stdev = grid.cells[2 * cell + 1];
-        if (std::isnan(mean)) return false;                     // empty cell
+        *cix = ix; *ciy = iy;
+        float mean = grid.cells[2 * cell], stdev = grid.cells[2 * cell + 1];
+        // per-particle map first (MLSMap::getPatch walks the newest grid first): the particle-local patch overlays
+        // the shared grid; its cell is used when it holds a surface that passes the 3-sigma gate
+        if (particle >= 0 && cfg.patch_size > 0 && !patches.empty()) {
+            const int P = cfg.patch_size;
+            const int32_t* org = &patch_origin[2 * particle];
+            if (org[0] != INT32_MIN) {
+                const int lx = ix - org[0], ly = iy - org[1];
+                if (lx >= 0 && lx < P && ly >= 0 && ly < P) {
+                    const float* pc = &patches[((size_t)particle * P * P + (size_t)ly * P + lx) * 2];
+                    if (!std::isnan(pc[0]) && !std::isnan(pc[1])) {
+                        bool pass;
+                        if (A::shared) {
+                            const double d = patch.mean - (double)pc[0];
+                            pass = d * d < 9.0 * ((double)pc[1] * (double)pc[1] + measVar);
+                        } else {
+                            const double interval = std::sqrt(patch.stdev * patch.stdev + (double)pc[1] * (double)pc[1]) * 3.0;
+                            pass = std::fabs(patch.mean - (double)pc[0]) < interval;
+                        }
+                        if (pass) { patch.mean = pc[0]; patch.stdev = pc[1]; return true; }
+                    }
+                }
+            }
+        }
+        if (std::isnan(mean) || std::isnan(stdev)) return false;   // empty cell
         // MLSGrid::get(pos, patch, sigma_threshold = 3.0): |mean - query| < 3 sqrt(stdev_q^2 + stdev_p^2)
         if (A::shared) {
             const double d = patch.mean - (double)mean;
@@ -211,7 +236,7 @@ struct eslam_oracle_ctx {
 
     // --- ContactModel::evaluatePose  src/ContactModel.cpp:117-224
     template <class A>
-    bool evaluatePose(double tx, double ty, double tz, double theta, double measVar, int32_t* cells) {
+    bool evaluatePose(double tx, double ty, double tz, double theta, double measVar, int32_t* cells, long particle = -1) {
         if (measVar == 0) throw std::string("using a zero measurement variance leads to singularities");  // :122-123
         contact_points.clear();                                 // :126
         double s, c; A::sincos(theta, s, c);
@@ -243,14 +268,15 @@ struct eslam_oracle_ctx {
             const float contactProbability = contactPoints[i].contact;   // :153
             if (cells) cells[i] = -1;
             if (group_valid && !(contactProbability < contact_threshold)) {   // :154
-                if (map_get<A>(w, patch, measVar, cells ? &cells[i] : nullptr)) {   // :156
+                int cix, ciy;
+                if (map_get<A>(w, patch, measVar, cells ? &cells[i] : nullptr, particle, &cix, &ciy)) {   // :156
                     const double zdiff = w.z - patch.mean;      // :160
                     const double pose_var = patch.stdev * patch.stdev;           // :166
                     const double zvar = patch.stdev * patch.stdev + measVar;      // :167
                     const Vec3 surface_point = {w.x, w.y, patch.mean};           // :168
                     const double ratio = A::likelihood_ratio(zdiff, zvar, cfg.contact_likelihood_correction);  // :170
                     if (!valid) {                               // :172-177
-                        p.point = surface_point; p.prob = 1.0;
+                        p.point = surface_point; p.prob = 1.0; p.cell_ix = cix; p.cell_iy = ciy;
                         p.zdiff = zdiff * ratio; p.zvar = zvar * ratio;
                         contact_ratio = ratio;
                         pose_var_avg = pose_var * ratio;
@@ -326,6 +352,38 @@ struct eslam_oracle_ctx {
         m_weight = pz;                                          // :299-301
         m_zDelta = -delta;
         m_zVar = 1.0 / d2;
+    }
+
+    // --- per-particle map write (north_star's contact-height variant of EmbodiedSlamFilter::processMap,
+    //     src/EmbodiedSlamFilter.cpp:209-227; definition in DESIGN.md "particle-local patches"): every fused contact of
+    //     the particle's last evaluation writes {height = point.z + zdiff, stdev = sqrt(zvar)} into the particle's own
+    //     P x P patch, Kalman-merged (float arithmetic) with what the cell already holds.
+    void patch_write(size_t i, double px, double py) {
+        const int P = cfg.patch_size;
+        int32_t* org = &patch_origin[2 * i];
+        if (org[0] == INT32_MIN) {                              // anchor the patch on the particle's own cell
+            int ix, iy;
+            double gx = px, gy = py;
+            if (!grid.identity) { const double* g = grid.g2l; gx = em::fma_(g[0], px, em::fma_(g[1], py, g[3])); gy = em::fma_(g[4], px, em::fma_(g[5], py, g[7])); }
+            if (!em::cell_index_exact(gx, grid.ox, grid.sx, grid.w, ix) || !em::cell_index_exact(gy, grid.oy, grid.sy, grid.h, iy)) return;
+            org[0] = ix - P / 2; org[1] = iy - P / 2;
+        }
+        const size_t ncp = std::min<size_t>(contact_points.size(), ESLAM_MAX_CP);
+        for (size_t k = 0; k < ncp; k++) {
+            const ContactPoint& q = contact_points[k];
+            const int lx = q.cell_ix - org[0], ly = q.cell_iy - org[1];
+            if (lx < 0 || lx >= P || ly < 0 || ly >= P) continue;
+            float* cell = &patches[(i * P * P + (size_t)ly * P + lx) * 2];
+            const float zm = (float)(q.point.z + q.zdiff);      // contact height
+            const float sd = (float)std::sqrt(q.zvar);
+            if (std::isnan(cell[0]) || std::isnan(cell[1])) { cell[0] = zm; cell[1] = sd; }
+            else {                                              // Kalman merge of two height estimates
+                const float v0 = cell[1] * cell[1], v1 = sd * sd;
+                const float kg = v0 / (v0 + v1);
+                cell[0] = cell[0] + kg * (zm - cell[0]);
+                cell[1] = std::sqrt((1.0f - kg) * v0);
+            }
+        }
     }
 
     // --- ContactModel::updateZPositionEstimate  src/ContactModel.cpp:319-340
@@ -440,13 +498,13 @@ struct eslam_oracle_ctx {
         data_weights.reserve(xi_k.size());
         double last_max_weight = max_weight;                    // :268-269
         max_weight = 0;
-        const bool keep_cps = cfg.patch_size > 0;
-        if (keep_cps) { last_cps.assign(xi_k.size() * ESLAM_MAX_CP, ContactPoint()); last_ncp.assign(xi_k.size(), 0); }
+        const bool keep_cps = cfg.patch_size > 0 && !patches.empty();
         for (size_t i = 0; i < xi_k.size(); i++) {              // :276
             PoseParticle& pose(xi_k[i]);
             const double measVar = pose.zSigma * pose.zSigma + cfg.measurement_error * cfg.measurement_error;  // :290
             bool ok;
-            try { ok = evaluatePose<A>(pose.px, pose.py, pose.zPos, pose.orientation, measVar, nullptr); }     // :288-291
+            const double eval_x = pose.px, eval_y = pose.py;
+            try { ok = evaluatePose<A>(pose.px, pose.py, pose.zPos, pose.orientation, measVar, nullptr, (long)i); }     // :288-291
             catch (std::string&) { return ESLAM_ERR_ZERO_VARIANCE; }
             if (ok) {
                 double zVar = pose.zSigma * pose.zSigma;        // :294
@@ -467,10 +525,7 @@ struct eslam_oracle_ctx {
                 if (A::shared) data_weights.push_back(0.0);     // keeps the pairwise tree index-aligned
             }
             pose.n_cpoints = contact_points.size();             // :322 cpoints.swap(contact_points)
-            if (keep_cps) {
-                last_ncp[i] = (uint8_t)std::min<size_t>(contact_points.size(), ESLAM_MAX_CP);
-                for (size_t k = 0; k < last_ncp[i]; k++) last_cps[i * ESLAM_MAX_CP + k] = contact_points[k];
-            }
+            if (keep_cps) patch_write(i, eval_x, eval_y);       // per-particle map write, before any resampling
         }
         const double sum_data_weights = A::sum(data_weights);
         const double floating_weight = data_particles > 0 ? sum_data_weights / data_particles : 1.0;   // :329
@@ -802,36 +857,8 @@ int eslam_oracle_lowest_points(const eslam_gpu_contact* pts, int n_pts, int upda
 // per-particle patch write (north_star's contact-height variant of EmbodiedSlamFilter::processMap,
 // src/EmbodiedSlamFilter.cpp:209-227): see DESIGN.md "particle-local patches" for the definition.
 int eslam_oracle_patch_update(eslam_oracle_ctx* ctx) {
+    // the write is part of update() (after each particle's evaluation, before resampling); nothing left to do here
     if (!ctx || ctx->cfg.patch_size <= 0) return ESLAM_ERR_INVALID;
-    const int P = ctx->cfg.patch_size;
-    const Grid& g = ctx->grid;
-    for (size_t i = 0; i < ctx->xi_k.size(); i++) {
-        const PoseParticle& p = ctx->xi_k[i];
-        int32_t* org = &ctx->patch_origin[2 * i];
-        if (org[0] == INT32_MIN) {                              // anchor the patch on the particle's own cell
-            int ix, iy;
-            if (!em::cell_index_exact(p.px, g.ox, g.sx, g.w, ix) || !em::cell_index_exact(p.py, g.oy, g.sy, g.h, iy)) continue;
-            org[0] = ix - P / 2; org[1] = iy - P / 2;
-        }
-        if (i >= ctx->last_ncp.size()) continue;
-        for (int k = 0; k < ctx->last_ncp[i]; k++) {
-            const ContactPoint& q = ctx->last_cps[i * ESLAM_MAX_CP + k];
-            int ix, iy;
-            if (!em::cell_index_exact(q.point.x, g.ox, g.sx, g.w, ix) || !em::cell_index_exact(q.point.y, g.oy, g.sy, g.h, iy)) continue;
-            const int lx = ix - org[0], ly = iy - org[1];
-            if (lx < 0 || lx >= P || ly < 0 || ly >= P) continue;
-            float* cell = &ctx->patches[(i * P * P + (size_t)ly * P + lx) * 2];
-            const float zm = (float)(q.point.z + q.zdiff);      // contact height
-            const float sd = (float)std::sqrt(q.zvar);
-            if (std::isnan(cell[0])) { cell[0] = zm; cell[1] = sd; }
-            else {                                              // Kalman merge of two height estimates
-                const float v0 = cell[1] * cell[1], v1 = sd * sd;
-                const float k = v0 / (v0 + v1);
-                cell[0] = cell[0] + k * (zm - cell[0]);
-                cell[1] = std::sqrt((1.0f - k) * v0);
-            }
-        }
-    }
     return ESLAM_OK;
 }
 

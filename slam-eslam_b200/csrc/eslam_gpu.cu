@@ -33,6 +33,7 @@ struct eslam_gpu_ctx {
     StateBufs st;
     DevScalars* sc; DevScalars* sc_host;          // sc_host: pinned staging
     uint32_t* ancestors; double* cdf;
+    float2* patch[2]; int* porigin[2];            // per-particle map patches (cfg.patch_size > 0), double buffered
     // per-tile arrays: l_* cover the local tiles, g_* all tiles of all ranks (aliases of l_* when world == 1)
     unsigned t_local, t_global, t_cap;
     TilePartA *l_part_a, *g_part_a; double *l_tile_sum, *g_tile_sum, *l_tile_sq, *g_tile_sq;
@@ -85,6 +86,7 @@ static void free_particles(eslam_gpu_ctx* ctx) {
         for (int f = 0; f < 2; ++f) dfree(ctx->st.b[b][f]);
     }
     dfree(ctx->ancestors); dfree(ctx->cdf);
+    for (int b = 0; b < 2; ++b) { dfree(ctx->patch[b]); dfree(ctx->porigin[b]); }
     const bool sh = ctx->g_part_a != ctx->l_part_a;
     if (sh) { dfree(ctx->g_part_a); dfree(ctx->g_tile_sum); dfree(ctx->g_tile_sq); dfree(ctx->g_desc); dfree(ctx->g_pool);
               dfree(ctx->g_cent); dfree(ctx->g_best_w); dfree(ctx->g_best_idx); }
@@ -109,6 +111,7 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
     if (n == 0) return ESLAM_ERR_EMPTY;
     if (n > 0xFFFFFFFFull) { ctx->error = "more than 2^32 particles per shard"; return ESLAM_ERR_INVALID; }
     const int G = sharded(ctx) ? ctx->shard.world : 1;
+    if (G > 1 && ctx->cfg.patch_size > 0) { ctx->error = "per-particle map patches are not supported on sharded contexts yet"; return ESLAM_ERR_INVALID; }
     if (G > 1 && (n % TILE != 0 || ctx->shard.global_count != n * (uint64_t)G)) {
         ctx->error = "sharded contexts need equal shards that are multiples of 1024 particles"; return ESLAM_ERR_INVALID;
     }
@@ -119,6 +122,10 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
             for (int f = 0; f < 2; ++f) CK(dalloc(&ctx->st.b[b][f], n));
         }
         CK(dalloc(&ctx->ancestors, n)); CK(dalloc(&ctx->cdf, n));
+        if (ctx->cfg.patch_size > 0) {
+            const size_t pp = (size_t)ctx->cfg.patch_size * ctx->cfg.patch_size;
+            for (int b = 0; b < 2; ++b) { CK(dalloc(&ctx->patch[b], n * pp)); CK(dalloc(&ctx->porigin[b], 2 * n)); }
+        }
         const size_t t = (size_t)((n + TILE - 1) / TILE), tg = t * G;
         CK(dalloc(&ctx->l_part_a, t)); CK(dalloc(&ctx->l_tile_sum, t)); CK(dalloc(&ctx->l_tile_sq, t));
         CK(dalloc(&ctx->l_desc, t)); CK(dalloc(&ctx->l_pool, (size_t)MAX_BND_TOTAL));
@@ -196,6 +203,19 @@ static size_t weight_smem_bytes(const eslam_gpu_ctx* ctx) {
     return HTAB_BYTES + 1024 + 256 + (size_t)ctx->map.tile_w * ctx->map.tile_h * sizeof(float2);
 }
 
+// empty maps for every particle: NaN cells (0xFF bytes), un-anchored origins
+static int reset_patches(eslam_gpu_ctx* ctx) {
+    if (ctx->cfg.patch_size <= 0) return ESLAM_OK;
+    const size_t pp = (size_t)ctx->cfg.patch_size * ctx->cfg.patch_size;
+    for (int b = 0; b < 2; ++b) {
+        CK(cudaMemsetAsync(ctx->patch[b], 0xFF, ctx->n * pp * sizeof(float2), ctx->stream));
+        k_fill_i32<<<(unsigned)((2 * ctx->n + 255) / 256), 256, 0, ctx->stream>>>(ctx->porigin[b], 2 * ctx->n, INT_MIN);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    return ESLAM_OK;
+}
+
 static int read_scalars(eslam_gpu_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->sc_host, ctx->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -228,6 +248,7 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     ctx->comm = nullptr; ctx->has_comm = false;
     ctx->device = device; ctx->launches = 0; ctx->n = ctx->cap = 0; ctx->t_local = ctx->t_global = ctx->t_cap = 0;
     ctx->ancestors = nullptr; ctx->cdf = nullptr;
+    for (int b = 0; b < 2; ++b) { ctx->patch[b] = nullptr; ctx->porigin[b] = nullptr; }
     ctx->l_part_a = ctx->g_part_a = nullptr; ctx->l_tile_sum = ctx->g_tile_sum = ctx->l_tile_sq = ctx->g_tile_sq = nullptr;
     ctx->l_desc = ctx->g_desc = nullptr; ctx->l_pool = ctx->g_pool = nullptr;
     ctx->l_cent = ctx->g_cent = ctx->l_best_w = ctx->g_best_w = nullptr; ctx->l_best_idx = ctx->g_best_idx = nullptr;
@@ -317,8 +338,10 @@ int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int he
     m.tile_h = (int)((avail / sizeof(float2)) / (size_t)m.tile_w);
     if (m.tile_h > height) m.tile_h = height;
     const int bytes = (int)weight_smem_bytes(ctx);
-    CK(cudaFuncSetAttribute(k_project_weight<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_project_weight<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_project_weight<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_project_weight<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_project_weight<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_project_weight<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->has_map = true;
     return ESLAM_OK;
@@ -335,6 +358,8 @@ int eslam_gpu_init_gaussian(eslam_gpu_ctx* ctx, uint64_t n, const double mu[3], 
     *ctx->sc_host = init;
     CK(cudaMemcpyAsync(ctx->sc, ctx->sc_host, sizeof(DevScalars), cudaMemcpyHostToDevice, ctx->stream));
     ctx->project_step = 0;
+    st = reset_patches(ctx);
+    if (st != ESLAM_OK) return st;
     const ModelParams mp = model_params(ctx);
     k_init_gaussian<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->st, ctx->sc, n, base_index(ctx), mp.k0, mp.k1,
                                                                          mu[0], mu[1], mu[2], sigma[0], sigma[1], sigma[2],
@@ -358,6 +383,8 @@ int eslam_gpu_set_particles(eslam_gpu_ctx* ctx, uint64_t n, const double* x, con
         for (int f = 0; f < 7; ++f) CK(cudaMemsetAsync(ctx->st.f[cur][f], 0, n * sizeof(double), ctx->stream));
         CK(cudaMemsetAsync(ctx->st.b[cur][B_FLOAT], 1, n, ctx->stream));
         CK(cudaMemsetAsync(ctx->st.b[cur][B_NF], 0, n, ctx->stream));
+        st = reset_patches(ctx);
+        if (st != ESLAM_OK) return st;
     }
     const double* src[6] = {x, y, theta, zpos, zsigma, weight};
     for (int f = 0; f < 6; ++f)
@@ -390,6 +417,8 @@ static void fill_weight_params(eslam_gpu_ctx* ctx, WeightParams* P, const eslam_
     memset(P, 0, sizeof(*P));
     P->st = ctx->st; P->sc = ctx->sc; P->part = ctx->l_part_a; P->map = ctx->map; P->mp = model_params(ctx);
     P->htab = ctx->htab; P->n = ctx->n; P->base = base_index(ctx); P->project_step = ctx->project_step;
+    P->patch_size = ctx->cfg.patch_size > 0 ? ctx->cfg.patch_size : 0;
+    for (int b = 0; b < 2; ++b) { P->patch[b] = ctx->patch[b]; P->porigin[b] = ctx->porigin[b]; }
     if (step) {
         P->yaw = step->yaw; P->z_delta = step->z_delta; P->z_var = step->z_var;
         for (int i = 0; i < 3; ++i) { P->dmean[i] = step->delta_mean[i]; P->dsigma[i] = step->delta_sigma[i]; }
@@ -545,6 +574,11 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     GatherSrc gs; memset(&gs, 0, sizeof(gs));
     k_gather<<<blocks, 256, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->ancestors, gs);
     LAUNCHED();
+    if (ctx->cfg.patch_size > 0) {
+        k_gather_patches<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->sc, n, ctx->ancestors, ctx->cfg.patch_size,
+                                                                                  ctx->patch[0], ctx->patch[1], ctx->porigin[0], ctx->porigin[1]);
+        LAUNCHED();
+    }
     k_after_resample<<<1, 1, 0, ctx->stream>>>(ctx->sc);
     LAUNCHED();
     return ESLAM_OK;
@@ -556,8 +590,13 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
     fill_weight_params(ctx, &P, step_or_null, cs);
     const size_t smem = weight_smem_bytes(ctx);
     if (ev0) CK(cudaEventRecord(ev0, ctx->stream));
-    if (step_or_null) { k_project_weight<true, true><<<weight_grid(ctx), WT_THREADS, smem, ctx->stream>>>(P); ctx->project_step++; }
-    else k_project_weight<false, true><<<weight_grid(ctx), WT_THREADS, smem, ctx->stream>>>(P);
+    const bool patches = ctx->cfg.patch_size > 0;
+    if (step_or_null) {
+        if (patches) k_project_weight<true, true, true><<<weight_grid(ctx), WT_THREADS, smem, ctx->stream>>>(P);
+        else k_project_weight<true, true, false><<<weight_grid(ctx), WT_THREADS, smem, ctx->stream>>>(P);
+        ctx->project_step++;
+    } else if (patches) k_project_weight<false, true, true><<<weight_grid(ctx), WT_THREADS, smem, ctx->stream>>>(P);
+    else k_project_weight<false, true, false><<<weight_grid(ctx), WT_THREADS, smem, ctx->stream>>>(P);
     LAUNCHED();
     if (ev1) CK(cudaEventRecord(ev1, ctx->stream));
     AG(ctx->l_part_a, ctx->g_part_a, ctx->t_local * sizeof(TilePartA));
@@ -611,7 +650,7 @@ int eslam_gpu_project(eslam_gpu_ctx* ctx, const eslam_gpu_step* step) {
     if (!step) return ESLAM_ERR_INVALID;
     WeightParams P;
     fill_weight_params(ctx, &P, step, nullptr);
-    k_project_weight<true, false><<<weight_grid(ctx), WT_THREADS, 0, ctx->stream>>>(P);
+    k_project_weight<true, false, false><<<weight_grid(ctx), WT_THREADS, 0, ctx->stream>>>(P);
     ctx->project_step++;
     LAUNCHED();
     return ESLAM_OK;
@@ -784,14 +823,28 @@ int eslam_gpu_debug_counters(eslam_gpu_ctx* ctx, uint64_t out[4]) {
 
 int eslam_gpu_patch_update(eslam_gpu_ctx* ctx) {
     if (!ctx) return ESLAM_ERR_INVALID;
-    ctx->error = "per-particle map patches are not enabled in this context (patch_size == 0)";
-    return ESLAM_ERR_INVALID;
+    if (ctx->cfg.patch_size <= 0) {
+        ctx->error = "per-particle map patches are not enabled in this context (patch_size == 0)";
+        return ESLAM_ERR_INVALID;
+    }
+    return ESLAM_OK;   // the write is part of update(): after each particle's evaluation, before resampling
 }
 
-int eslam_gpu_get_patches(eslam_gpu_ctx* ctx, float*, int32_t*) {
+int eslam_gpu_get_patches(eslam_gpu_ctx* ctx, float* cells, int32_t* origin_xy) {
     if (!ctx) return ESLAM_ERR_INVALID;
-    ctx->error = "per-particle map patches are not enabled in this context (patch_size == 0)";
-    return ESLAM_ERR_INVALID;
+    if (ctx->cfg.patch_size <= 0 || ctx->n == 0) {
+        ctx->error = "per-particle map patches are not enabled in this context (patch_size == 0)";
+        return ESLAM_ERR_INVALID;
+    }
+    CK(cudaSetDevice(ctx->device));
+    int st = read_scalars(ctx);
+    if (st != ESLAM_OK) return st;
+    const int cur = ctx->sc_host->cur;
+    const size_t pp = (size_t)ctx->cfg.patch_size * ctx->cfg.patch_size;
+    if (cells) CK(cudaMemcpyAsync(cells, ctx->patch[cur], ctx->n * pp * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    if (origin_xy) CK(cudaMemcpyAsync(origin_xy, ctx->porigin[cur], 2 * ctx->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ESLAM_OK;
 }
 
 }  // extern "C"

@@ -19,6 +19,7 @@
 // index-aligned binary tree, so results do not depend on grid size, SM count or number of GPUs.
 #pragma once
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 #include "eslam_math.h"
 #include "../../include/eslam_gpu.h"
@@ -94,6 +95,8 @@ struct WeightParams {
     const em::dbl2* htab;
     unsigned long long n, base;  // local particle count, global index of local particle 0
     uint32_t project_step;
+    int patch_size;              // P (0: no per-particle patches)
+    float2* patch[2]; int* porigin[2];   // double buffered with the particle state: [N][P][P] cells, [N][2] origins
     double yaw, z_delta, z_var, dmean[3], dsigma[3];
     ContactSet cs;
 };
@@ -178,14 +181,21 @@ __device__ __forceinline__ float2 load_cell(bool in_tile, uint32_t tile_saddr, c
 // Written straight-line: every lane computes every evaluated contact; lanes whose group is already invalid, or whose
 // lookup misses, contribute a zero ratio.  The rare cases (quotient within 2^-18 of a cell border, variance or t
 // outside the table) take one slow branch each.
-template <bool TAP>
+// PATCH: the particle owns a P x P overlay of the shared grid (north_star's per-particle map patches); its cells are
+// looked up first (MLSMap::getPatch walks the newest grid first) and the fused contacts are recorded for the write.
+struct PatchRef { const float2* cells; int ox, oy, P; };                 // ox == INT_MIN: not anchored yet
+struct CpRec { int ix[ESLAM_MAX_CP], iy[ESLAM_MAX_CP]; double h[ESLAM_MAX_CP], zv[ESLAM_MAX_CP]; };
+
+template <bool TAP, bool PATCH>
 __device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapParams& M, const MapTile& mt,
                                              const em::dbl2* htab, double inv_corr,
                                              double x, double y, double z, double s, double c, double mv,
-                                             PoseEval& out, int32_t* tap_cells, double* tap_cp) {
+                                             PoseEval& out, int32_t* tap_cells, double* tap_cp,
+                                             const PatchRef& pr, CpRec* rec) {
     int valid = 0, gvalid = 1;                                           // :134-135
     double acc_d = 0, acc_v = 0, acc_r = 0, acc_p = 0;
     double pt_x = 0, pt_y = 0, pt_z = 0;
+    int pt_ix = 0, pt_iy = 0;
     out.n_found = 0; out.d1 = 0; out.d2 = 0; out.A = 0; out.poseVar = 0;
     const int n = cs.n;
     const int FRAC_MASK = (1 << IDX_FRAC_BITS) - 1;
@@ -220,8 +230,18 @@ __device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapPara
             const int flat = inb ? iy * M.W + ix : 0;
             const unsigned lx = (unsigned)(ix - mt.x0), ly = (unsigned)(iy - mt.y0);
             const bool in_tile = inb & (lx < (unsigned)mt.w) & (ly < (unsigned)mt.h);
-            const float2 cell = load_cell(in_tile, tile_sa + (ly * mt.w + lx) * 8u, M.cells + flat);
+            float2 cell = load_cell(in_tile, tile_sa + (ly * mt.w + lx) * 8u, M.cells + flat);
             if (TAP) tap_cells[i] = (inb && gvalid) ? flat : -1;
+            if (PATCH) {
+                const unsigned plx = (unsigned)(ix - pr.ox), ply = (unsigned)(iy - pr.oy);
+                if (inb && pr.ox != INT_MIN && plx < (unsigned)pr.P && ply < (unsigned)pr.P) {
+                    const float2 pc = pr.cells[ply * pr.P + plx];
+                    if (pc.x == pc.x && pc.y == pc.y) {
+                        const double dp = wz - (double)pc.x;
+                        if (dp * dp < 9.0 * ((double)pc.y * (double)pc.y + mv)) cell = pc;
+                    }
+                }
+            }
             // candidate lanes: group still valid, inside the grid, cell not empty (NaN mean; a NaN stdev misses too).
             // Non-candidate lanes compute on zeros so that everything below stays finite for them.
             const bool cand = (gvalid != 0) & inb & (cell.x == cell.x) & (cell.y == cell.y);
@@ -234,7 +254,7 @@ __device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapPara
             double ratio = em::likelihood_ratio_fast(d, zvar, inv_corr, htab, rare);           // :170
             if (rare & use) ratio = em::likelihood_ratio(d, zvar, inv_corr, htab);
             const double r_eff = use ? ratio : 0.0;
-            if (TAP && use && !valid) { pt_x = wx; pt_y = wy; pt_z = (double)cell.x; }
+            if ((TAP || PATCH) && use && !valid) { pt_x = wx; pt_y = wy; pt_z = (double)cell.x; pt_ix = ix; pt_iy = iy; }
             acc_d = em::fma_(d, r_eff, acc_d); acc_v = em::fma_(zvar, r_eff, acc_v);           // :172-184
             acc_r += r_eff; acc_p = em::fma_(sp2, r_eff, acc_p);
             valid |= (int)use;                                           // :185
@@ -250,6 +270,10 @@ __device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapPara
                     if (TAP && out.n_found < ESLAM_MAX_CP) {
                         double* o = tap_cp + out.n_found * 5;
                         o[0] = pt_x; o[1] = pt_y; o[2] = pt_z; o[3] = zd; o[4] = zv;
+                    }
+                    if (PATCH && out.n_found < ESLAM_MAX_CP) {
+                        rec->ix[out.n_found] = pt_ix; rec->iy[out.n_found] = pt_iy;
+                        rec->h[out.n_found] = pt_z + zd; rec->zv[out.n_found] = zv;
                     }
                     out.n_found++;
                 }
@@ -285,6 +309,42 @@ __device__ __forceinline__ bool update_z(const PoseEval& e, double m_zDelta, dou
     delta_var = (1.0 - var_gain) * delta_var;
     z_var = pose_var + delta_var;
     return true;
+}
+
+// Per-particle map write (north_star's contact-height variant of EmbodiedSlamFilter::processMap,
+// src/EmbodiedSlamFilter.cpp:209-227): each fused contact writes {height, sqrt(zvar)} into the particle's own patch,
+// Kalman-merged in float with what the cell holds.  The patch is anchored on the particle's cell at its first write.
+__device__ __forceinline__ void patch_write(const MapParams& M, float2* cells, int* origin, int P, double x, double y,
+                                            int n_found, const CpRec& rec) {
+    int ox = origin[0], oy = origin[1];
+    if (ox == INT_MIN) {
+        double gx = x, gy = y;
+        if (!M.identity) {
+            gx = em::fma_(M.g2l[0], x, em::fma_(M.g2l[1], y, M.g2l[3]));
+            gy = em::fma_(M.g2l[4], x, em::fma_(M.g2l[5], y, M.g2l[7]));
+        }
+        int ix, iy;
+        if (!em::cell_index_exact(gx, M.ox, M.sx, M.W, ix) || !em::cell_index_exact(gy, M.oy, M.sy, M.H, iy)) return;
+        ox = ix - P / 2; oy = iy - P / 2;
+        origin[0] = ox; origin[1] = oy;
+    }
+    const int ncp = n_found < ESLAM_MAX_CP ? n_found : ESLAM_MAX_CP;
+    for (int k = 0; k < ncp; ++k) {
+        const int lx = rec.ix[k] - ox, ly = rec.iy[k] - oy;
+        if (lx < 0 || lx >= P || ly < 0 || ly >= P) continue;
+        float2* cell = cells + ly * P + lx;
+        const float zm = (float)rec.h[k];
+        const float sd = (float)em::sqrt_(rec.zv[k]);
+        float2 cv = *cell;
+        if (!(cv.x == cv.x) || !(cv.y == cv.y)) { cv.x = zm; cv.y = sd; }
+        else {
+            const float v0 = cv.y * cv.y, v1 = sd * sd;
+            const float kg = __fdiv_rn(v0, v0 + v1);
+            cv.x = cv.x + kg * (zm - cv.x);
+            cv.y = __fsqrt_rn((1.0f - kg) * v0);
+        }
+        *cell = cv;
+    }
 }
 
 __device__ __forceinline__ double weighting_function(double x, double alpha, double beta, double gamma) {
@@ -327,7 +387,7 @@ __global__ void k_init_gaussian(StateBufs st, DevScalars* sc, unsigned long long
 // ------------------------------------------------------------------------------------------------ fused project + weight
 #define HTAB_BYTES (ESLAM_H_NINT * 3 * 16)
 
-template <bool DO_PROJECT, bool DO_WEIGHT>
+template <bool DO_PROJECT, bool DO_WEIGHT, bool PATCH>
 __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_constant__ WeightParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     em::dbl2* htab = reinterpret_cast<em::dbl2*>(smem_raw);
@@ -409,7 +469,18 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_c
                 const double mv = zs * zs + P.mp.merr2;                          // :290
                 if (mv == 0) atomicOr(&P.sc->error_flags, ERR_ZERO_VARIANCE_BIT);   // src/ContactModel.cpp:122-123
                 PoseEval ev;
-                contact_eval<false>(P.cs, P.map, mt, htab, P.mp.inv_corr, x, y, z, s, c, mv, ev, nullptr, nullptr);
+                PatchRef pr; pr.cells = nullptr; pr.ox = INT_MIN; pr.oy = 0; pr.P = 0;
+                CpRec rec;
+                if (PATCH) {
+                    const size_t pp = (size_t)P.patch_size * P.patch_size;
+                    pr.cells = P.patch[cur] + i * pp; pr.P = P.patch_size;
+                    pr.ox = P.porigin[cur][2 * i]; pr.oy = P.porigin[cur][2 * i + 1];
+                }
+                contact_eval<false, PATCH>(P.cs, P.map, mt, htab, P.mp.inv_corr, x, y, z, s, c, mv, ev, nullptr, nullptr,
+                                           pr, &rec);
+                if (PATCH)
+                    patch_write(P.map, P.patch[cur] + i * (size_t)P.patch_size * P.patch_size, P.porigin[cur] + 2 * i,
+                                P.patch_size, x, y, ev.n_found, rec);
                 double mprob = 1.0; uint8_t floating = 1;                        // :316-317
                 if ((unsigned long long)ev.n_found >= P.mp.min_contacts) {       // ContactModel.cpp:217
                     double weight, zdl, zvr;
@@ -914,6 +985,25 @@ __global__ void k_gather(StateBufs st, const DevScalars* sc, unsigned long long 
     }
 }
 
+// cloneMaps (src/PoseEstimator.cpp:31-45): every copy of a particle owns a copy of its map patch. One warp per particle.
+__global__ void k_gather_patches(const DevScalars* sc, unsigned long long n, const uint32_t* __restrict__ anc, int P,
+                                 float2* p0, float2* p1, int* o0, int* o1) {
+    if (!sc->do_resample) return;
+    const unsigned long long k = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int cur = sc->cur;
+    const float2* src = (cur ? p1 : p0) + (size_t)anc[k] * P * P;
+    float2* dst = (cur ? p0 : p1) + k * (size_t)P * P;
+    for (int c = lane; c < P * P; c += 32) dst[c] = src[c];
+    if (lane < 2) (cur ? o0 : o1)[2 * k + lane] = (cur ? o1 : o0)[2 * (size_t)anc[k] + lane];
+}
+
+__global__ void k_fill_i32(int* p, size_t count, int v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) p[i] = v;
+}
+
 __global__ void k_after_resample(DevScalars* sc) {
     if (!sc->do_resample) return;
     sc->cur ^= 1;                                                                    // xi_k.swap(xi_kp) :107
@@ -990,8 +1080,9 @@ __global__ void k_evaluate_poses(const __grid_constant__ EvalParams P) {
     const double mv = P.mv[i];
     if (mv == 0) { atomicOr(P.err, ERR_ZERO_VARIANCE_BIT); return; }
     PoseEval ev;
-    contact_eval<true>(P.cs, P.map, mt, P.htab, P.inv_corr, P.x[i], P.y[i], P.z[i], s, c, mv, ev,
-                       P.cells + i * P.cs.n, P.cp + i * ESLAM_MAX_CP * 5);
+    PatchRef pr; pr.cells = nullptr; pr.ox = INT_MIN; pr.oy = 0; pr.P = 0;
+    contact_eval<true, false>(P.cs, P.map, mt, P.htab, P.inv_corr, P.x[i], P.y[i], P.z[i], s, c, mv, ev,
+                              P.cells + i * P.cs.n, P.cp + i * ESLAM_MAX_CP * 5, pr, nullptr);
     const bool ok = (unsigned long long)ev.n_found >= P.min_contacts;
     double weight = 0, zdl = 0, zvr = 0, z = P.z[i], zv = P.zvin ? P.zvin[i] : 0.0;
     if (ok) {

@@ -285,3 +285,46 @@ def test_full_size_step_matches_oracle_and_properties(gpu, oracle):
         assert np.all(counts <= np.ceil(w) + 1) and np.all(counts >= np.floor(w) - 1)   # stratified offspring bounds
         assert counts.sum() == n
     assert g.debugCounters()["fallbacks"] == 0 and g.debugCounters()["resamples"] == 4
+
+
+# ---------------------------------------------------------------------------------- per-particle map patches (C4)
+@pytest.mark.parametrize("n,steps", [(250, 10), (20000, 4)])
+def test_patches_bit_identical_to_shared_oracle(gpu, oracle, n, steps):
+    """EmbodiedSlamFilter per-particle map update (contact heights into particle-local 16x16 patches), patch-first
+    lookup, and cloneMaps through resampling: particles AND every patch cell / origin identical to the oracle."""
+    P = 16
+    g, o, contacts, step = pair(gpu, oracle, "C1", n=n, patch_size=P, min_effective=n + 1)
+    still = abi.make_step(delta_sigma=(0.001, 0.001, 0.0005))
+    for i in range(steps):
+        st = step if i % 2 == 0 else still               # small motion: written cells are hit again
+        g.project(st)
+        o.project(st)
+        ra, rb = g.update(contacts), o.update(contacts)
+        assert ra.as_dict() == rb.as_dict(), i
+        assert np.array_equal(g.getAncestors(), o.getAncestors())
+        assert_particles_equal(g.getParticles(), o.getParticles())
+        ca, oa = g.getPatches(P)
+        cb, ob = o.getPatches(P)
+        assert np.array_equal(oa, ob), "patch origins, step %d" % i
+        assert np.array_equal(ca, cb, equal_nan=True), "patch cells, step %d" % i
+    assert (~np.isnan(ca[..., 0])).sum() > n // 2
+    g.patchUpdate()                                       # kept for the ABI: the write is part of update()
+
+
+def test_patches_change_the_result_only_through_written_cells(gpu):
+    P = 16
+    a = gpu(abi.default_config(patch_size=P, min_effective=0))
+    b = gpu(abi.default_config(min_effective=0))
+    contacts, step = synthetic.setup_filter(a, "C1")
+    synthetic.setup_filter(b, "C1")
+    for f in (a, b):
+        f.project(step)
+        f.update(contacts)
+    assert np.array_equal(a.getParticles()["weight"], b.getParticles()["weight"])      # empty patches: same as shared map
+    still = abi.make_step()
+    for f in (a, b):
+        f.project(still)
+        f.update(contacts)
+    assert not np.array_equal(a.getParticles()["weight"], b.getParticles()["weight"])
+    with pytest.raises(RuntimeError):
+        b.getPatches(P)
