@@ -1,0 +1,84 @@
+// PoseEstimator.hpp -- eslam::PoseEstimator (src/PoseEstimator.hpp:119-155) over libeslam_gpu.so: same constructor,
+// init / project / update / setEnvironment / getCentroid, same exceptions.  Every step is a device call.
+#ifndef ESLAM_FACADE_POSEESTIMATOR_HPP
+#define ESLAM_FACADE_POSEESTIMATOR_HPP
+#include "ContactModel.hpp"
+
+namespace eslam {
+
+class PoseEstimator : public ParticleFilter<PoseParticle> {
+public:
+    PoseEstimator(odometry::FootContact& odometry, const eslam::Configuration& config)      // src/PoseEstimator.cpp:13-25
+        : ParticleFilter<Particle>(toGpuConfig(config)), config(config), odometry(odometry), max_weight(0), haveEnv(false) {}
+    ~PoseEstimator() {}
+
+    void init(int numParticles, const base::Pose2D& mu, const base::Pose2D& sigma, double zpos = 0, double zsigma = 0) {   // :88-102
+        const double m[3] = {mu.position.x(), mu.position.y(), mu.orientation};
+        const double s[3] = {sigma.position.x(), sigma.position.y(), sigma.orientation};
+        gpu_check(gpu, eslam_gpu_init_gaussian(gpu, (uint64_t)numParticles, m, s, zpos, zsigma));
+        deviceChanged();
+    }
+
+    void setEnvironment(const DenseGrid& map, const double* C_global2local = 0) {            // :47-62
+        attachGrid(gpu, map, C_global2local); haveEnv = true;
+    }
+
+    void project(const odometry::BodyContactState& /*state*/, const base::Quaterniond& orientation) {   // :184-242
+        flush();
+        eslam_gpu_step s;
+        s.yaw = base::getYaw(orientation);                                                   // :186
+        zCompensatedOrientation = base::removeYaw(orientation);                              // :187
+        const base::Pose d = odometry.getPoseDelta();
+        s.z_delta = (orientation * d.position).z();                                          // :188-189
+        s.z_var = odometry.getPositionErrorZZ() * 2.0;                                       // :192
+        s.delta_mean[0] = d.position.x(); s.delta_mean[1] = d.position.y(); s.delta_mean[2] = base::getYaw(d.orientation);
+        for (int i = 0; i < 3; i++) s.delta_sigma[i] = odometry.getSampleSigma()[i];        // :198
+        gpu_check(gpu, eslam_gpu_project(gpu, &s));
+        deviceChanged();
+    }
+
+    void update(const odometry::BodyContactState& state, const base::Quaterniond& orientation,
+                const std::vector<terrain_estimator::TerrainClassification>& ltc) {          // :244-255
+        flush();
+        if (!haveEnv) throw std::runtime_error("No environment attached.");                 // :259-260
+        contactModel.setTerrainClassification(ltc);
+        contactModel.setContactPoints(state, orientation);                                   // :262
+        std::vector<eslam_gpu_contact> pts = toAbi(contactModel.getContactState());
+        gpu_check(gpu, eslam_gpu_update(gpu, pts.data(), (int)pts.size(), &lastResult));
+        max_weight = lastResult.max_weight;
+        deviceChanged();
+    }
+
+    base::Pose getCentroid() {                                                               // :354-383
+        flush();
+        double c[4]; gpu_check(gpu, eslam_gpu_centroid(gpu, c));
+        deviceChanged();                                                                     // getCentroid re-normalises (:356)
+        return base::Pose(base::Vector3d(c[0], c[1], c[3]), base::Quaterniond::fromYaw(c[2]) * zCompensatedOrientation);
+    }
+
+    const eslam_gpu_update_result& getLastUpdate() const { return lastResult; }
+
+private:
+    // the reference's ContactModel member (src/PoseEstimator.hpp:145) is only used for its host bookkeeping here
+    struct HostContactModel {
+        odometry::BodyContactState contactState;
+        void setTerrainClassification(const std::vector<terrain_estimator::TerrainClassification>&) {}
+        void setContactPoints(const odometry::BodyContactState& state, const base::Quaterniond& orientation) {
+            contactState = state;
+            const base::Quaterniond yc = base::removeYaw(orientation);
+            for (size_t i = 0; i < contactState.points.size(); i++) contactState.points[i].position = yc * contactState.points[i].position;
+        }
+        const odometry::BodyContactState& getContactState() const { return contactState; }
+    };
+
+    eslam::Configuration config;
+    HostContactModel contactModel;
+    odometry::FootContact& odometry;
+    base::Quaterniond zCompensatedOrientation;
+    double max_weight;
+    bool haveEnv;
+    eslam_gpu_update_result lastResult;
+};
+
+}  // namespace eslam
+#endif

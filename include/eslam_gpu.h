@@ -142,6 +142,8 @@ int eslam_gpu_step_fused(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const e
 int eslam_gpu_run_steps(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const eslam_gpu_contact* pts, int n_pts,
                         int steps, float* elapsed_ms, float* top_kernel_ms, eslam_gpu_update_result* last_result);
 
+/* ParticleFilter::getWeightsSum (src/ParticleFilter.hpp:34-39). */
+int eslam_gpu_weights_sum(eslam_gpu_ctx* ctx, double* sum);
 /* ParticleFilter::normalizeWeights (src/ParticleFilter.hpp:46-70); returns ESS. */
 int eslam_gpu_normalize_weights(eslam_gpu_ctx* ctx, double* ess);
 /* ParticleFilter::resample -> resample_stratified(N) (src/ParticleFilter.hpp:72-108). */

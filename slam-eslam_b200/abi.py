@@ -136,6 +136,7 @@ GPU_ONLY = {
     "run_steps": (C.c_int, [C.c_void_p, C.POINTER(Step), C.POINTER(Contact), C.c_int, C.c_int,
                             C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(UpdateResult)]),
     "synchronize": (C.c_int, [C.c_void_p]),
+    "weights_sum": (C.c_int, [C.c_void_p, _dp]),
     "debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "launch_count": (C.c_uint64, [C.c_void_p]),
 }

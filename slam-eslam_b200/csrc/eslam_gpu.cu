@@ -706,6 +706,22 @@ int eslam_gpu_run_steps(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const es
     return last_result ? fetch_result(ctx, last_result) : ESLAM_OK;
 }
 
+int eslam_gpu_weights_sum(eslam_gpu_ctx* ctx, double* sum) {
+    int st = check_ready(ctx, false);
+    if (st != ESLAM_OK) return st;
+    if (!sum) return ESLAM_ERR_INVALID;
+    k_loop_b<false><<<ctx->t_local, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->n, ctx->l_tile_sum);
+    LAUNCHED();
+    AG(ctx->l_tile_sum, ctx->g_tile_sum, ctx->t_local * sizeof(double));
+    k_reduce_b<<<1, 1024, 0, ctx->stream>>>(ctx->g_tile_sum, ctx->t_global, global_count(ctx), ctx->sc, ctx->scratch_a, ctx->scratch_b,
+                                            ctx->tile_prefix, 0);
+    LAUNCHED();
+    st = read_scalars(ctx);
+    if (st != ESLAM_OK) return st;
+    *sum = ctx->sc_host->sum_w;
+    return ESLAM_OK;
+}
+
 int eslam_gpu_normalize_weights(eslam_gpu_ctx* ctx, double* ess) {
     int st = check_ready(ctx, false);
     if (st != ESLAM_OK) return st;

@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_b(const double* tile_sum, un
     __syncthreads();
     const double total = block_tree_reduce(scratch_a, scratch_b, n_tiles);
     const int uniform = normalise && (total <= 0.0);                                 // :51 (Q8)
-    if (threadIdx.x == 0) { if (normalise) sc->sum_w = total; sc->uniform = uniform; sc->pool_count = 0; }
+    if (threadIdx.x == 0) { sc->sum_w = total; sc->uniform = uniform; sc->pool_count = 0; }
     // exclusive scan of the per-tile masses (approximate is enough: only used to classify elements)
     const unsigned per = (n_tiles + blockDim.x - 1) / blockDim.x;
     const unsigned lo = threadIdx.x * per, hi = min(lo + per, n_tiles);
