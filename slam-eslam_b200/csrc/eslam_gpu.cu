@@ -522,14 +522,14 @@ static int resample_exchange(eslam_gpu_ctx* ctx) {
     lap("enqueue range exchange");
     const ModelParams mp = model_params(ctx);
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    k_search<<<blocks, 256, 0, ctx->stream>>>(ctx->sc, ctx->win_cdf, wlen, wb[me], n, N, base_index(ctx), mp.k0, mp.k1,
-                                              ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC, ctx->ancestors);
-    LAUNCHED();
     GatherSrc gs; memset(&gs, 0, sizeof(gs));
     for (int f = 0; f < 7; ++f) gs.f[f] = ctx->win_f[f];
     for (int f = 0; f < 2; ++f) gs.b[f] = ctx->win_b[f];
     gs.base = wb[me]; gs.use_window = 1;
-    k_gather<<<blocks, 256, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->ancestors, gs);
+    k_resample<<<blocks, 256, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->win_cdf, ctx->tile_sin + wb[me] / TILE,
+                                                (unsigned)((wlen + TILE - 1) / TILE), wlen, wb[me], n, N, base_index(ctx),
+                                                mp.k0, mp.k1, ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC,
+                                                ctx->ancestors, gs);
     LAUNCHED();
     k_after_resample<<<1, 1, 0, ctx->stream>>>(ctx->sc);
     LAUNCHED();
@@ -542,13 +542,13 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     const unsigned T = ctx->t_local, TG = ctx->t_global;
     const uint64_t n = ctx->n, ng = global_count(ctx);
     const double eps = scan_eps(ctx);
-    if (apply_loop_b) k_loop_b<true><<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->l_tile_sum);
-    else k_loop_b<false><<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->l_tile_sum);
+    if (apply_loop_b) k_loop_b<true><<<T, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->l_tile_sum);
+    else k_loop_b<false><<<T, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->l_tile_sum);
     LAUNCHED();
     AG(ctx->l_tile_sum, ctx->g_tile_sum, T * sizeof(double));
     k_reduce_b<<<1, 1024, 0, ctx->stream>>>(ctx->g_tile_sum, TG, ng, ctx->sc, ctx->scratch_a, ctx->scratch_b, ctx->tile_prefix, normalise);
     LAUNCHED();
-    k_norm_scan<<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ng, ctx->tile_prefix, ctx->l_tile_sq, ctx->l_desc, ctx->l_pool,
+    k_norm_scan<<<T, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ng, ctx->tile_prefix, ctx->l_tile_sq, ctx->l_desc, ctx->l_pool,
                                              ctx->sc, normalise, eps, tile_ofs(ctx));
     LAUNCHED();
     AG(ctx->l_tile_sq, ctx->g_tile_sq, T * sizeof(double));
@@ -560,19 +560,17 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
                                                          mode == 2 ? 0ull : ctx->cfg.min_effective, decide, force, T);
     LAUNCHED();
     if (mode == 2) return ESLAM_OK;
-    k_cdf<<<T, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->tile_prefix, ctx->tile_bofs, ctx->tile_sin, ctx->sb, ctx->cdf, eps,
+    k_cdf<<<T, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->tile_prefix, ctx->tile_bofs, ctx->tile_sin, ctx->sb, ctx->cdf, eps,
                                        tile_ofs(ctx));
     LAUNCHED();
     if (sharded(ctx)) return resample_exchange(ctx);
-    k_cdf_sequential<<<1, 1, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->cdf);
+    k_cdf_sequential<<<1, 1, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->cdf, ctx->tile_sin);
     LAUNCHED();
     const ModelParams mp = model_params(ctx);
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    k_search<<<blocks, 256, 0, ctx->stream>>>(ctx->sc, ctx->cdf, n, 0, n, ng, 0, mp.k0, mp.k1,
-                                              ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC, ctx->ancestors);
-    LAUNCHED();
     GatherSrc gs; memset(&gs, 0, sizeof(gs));
-    k_gather<<<blocks, 256, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->ancestors, gs);
+    k_resample<<<blocks, 256, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->cdf, ctx->tile_sin, T, n, 0, n, ng, 0, mp.k0, mp.k1,
+                                                ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC, ctx->ancestors, gs);
     LAUNCHED();
     if (ctx->cfg.patch_size > 0) {
         k_gather_patches<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->sc, n, ctx->ancestors, ctx->cfg.patch_size,
@@ -710,7 +708,7 @@ int eslam_gpu_weights_sum(eslam_gpu_ctx* ctx, double* sum) {
     int st = check_ready(ctx, false);
     if (st != ESLAM_OK) return st;
     if (!sum) return ESLAM_ERR_INVALID;
-    k_loop_b<false><<<ctx->t_local, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->n, ctx->l_tile_sum);
+    k_loop_b<false><<<ctx->t_local, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->n, ctx->l_tile_sum);
     LAUNCHED();
     AG(ctx->l_tile_sum, ctx->g_tile_sum, ctx->t_local * sizeof(double));
     k_reduce_b<<<1, 1024, 0, ctx->stream>>>(ctx->g_tile_sum, ctx->t_global, global_count(ctx), ctx->sc, ctx->scratch_a, ctx->scratch_b,

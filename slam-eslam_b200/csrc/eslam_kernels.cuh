@@ -563,24 +563,62 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_a(const TilePartA* part, uns
 }
 
 // ------------------------------------------------------------------------------------------------ loop B + raw sums
+#define SCAN_THREADS 256         // scan-type kernels: 256 threads x 4 consecutive elements = one 1024-tile
+#define EPT 4
+
+// Tree sum over the 1024 leaves of a tile held 4 consecutive per thread (blockDim.x == 256): same tree as
+// tile_tree_sum_1024 (levels 0-1 in the thread, 2-6 by the warp butterfly, 7-9 over the 8 warp partials). red: >= 8.
+__device__ __forceinline__ double tile_tree_sum4(const double v[EPT], double* red) {
+    double t = (v[0] + v[1]) + (v[2] + v[3]);
+    t = warp_tree_sum(t);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    double r = red[threadIdx.x & 7];
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    return r;
+}
+
 // weight *= mprob * pow(discount*floating_weight, 4 - cpoints.size())  (:332-345); per-tile sums of the result
 template <bool APPLY>
-__global__ void __launch_bounds__(1024, 1) k_loop_b(StateBufs st, const DevScalars* sc, unsigned long long n,
-                                                    double* tile_sum) {
-    __shared__ double red[32];
+__global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, const DevScalars* sc, unsigned long long n,
+                                                         double* tile_sum) {
+    __shared__ double red[8];
     const int cur = sc->cur;
-    const unsigned long long i = (unsigned long long)blockIdx.x * TILE + threadIdx.x;
-    double w = 0.0;
-    if (i < n) {
-        w = st.f[cur][F_W][i];
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
+    double w[EPT];
+    double* W = st.f[cur][F_W];
+    if (i0 + EPT <= n) {
+        const double2 a = *reinterpret_cast<const double2*>(W + i0), b = *reinterpret_cast<const double2*>(W + i0 + 2);
+        w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
         if (APPLY) {
-            const unsigned nf = st.b[cur][B_NF][i];
-            const double factor = st.f[cur][F_MP][i] * sc->pow_table[nf > 4 ? 5 : nf];
-            w *= factor;                                                              // Q1: second application
-            st.f[cur][F_W][i] = w;
+            const double2 ma = *reinterpret_cast<const double2*>(st.f[cur][F_MP] + i0), mb = *reinterpret_cast<const double2*>(st.f[cur][F_MP] + i0 + 2);
+            const uchar4 nf = *reinterpret_cast<const uchar4*>(st.b[cur][B_NF] + i0);
+            const double mp[EPT] = {ma.x, ma.y, mb.x, mb.y};
+            const unsigned nfv[EPT] = {nf.x, nf.y, nf.z, nf.w};
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) { const double factor = mp[j] * sc->pow_table[nfv[j] > 4 ? 5 : nfv[j]]; w[j] *= factor; }   // Q1: second application
+            *reinterpret_cast<double2*>(W + i0) = make_double2(w[0], w[1]);
+            *reinterpret_cast<double2*>(W + i0 + 2) = make_double2(w[2], w[3]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            w[j] = 0.0;
+            if (i0 + j < n) {
+                w[j] = W[i0 + j];
+                if (APPLY) {
+                    const unsigned nf = st.b[cur][B_NF][i0 + j];
+                    const double factor = st.f[cur][F_MP][i0 + j] * sc->pow_table[nf > 4 ? 5 : nf];
+                    w[j] *= factor;
+                    W[i0 + j] = w[j];
+                }
+            }
         }
     }
-    const double s = tile_tree_sum_1024(w, red);
+    const double s = tile_tree_sum4(w, red);
     if (threadIdx.x == 0) tile_sum[blockIdx.x] = s;
 }
 
@@ -680,117 +718,167 @@ __device__ __forceinline__ SegE sege_shfl_up(const SegE& v, int o) {
     return r;
 }
 
-struct TileScan {          // per-thread results of the tile-local scans
-    ElemClass cls;
-    SegE inc;              // inclusive segmented function
-    int bnd_before;        // boundary elements strictly before this one in the tile
+struct TileScan {          // per-thread results of the tile-local scans (EPT consecutive elements per thread)
+    ElemClass cls[EPT];
+    SegE inc[EPT];         // inclusive segmented function
+    int bnd_before[EPT];   // boundary elements strictly before this one in the tile
     int bnd_total;
 };
 
-// Shared scratch for tile_scan: 32 doubles + 32 SegE + 32 ints
-struct TileScanSmem { double d[32]; SegE e[32]; int c[32]; };
+// Shared scratch for tile_scan: one entry per warp (8 warps)
+struct TileScanSmem { double d[8]; SegE e[8]; int c[8]; };
 
-// Tile-local approximate inclusive prefix + classification + segmented function scan. blockDim.x == 1024.
-__device__ __forceinline__ TileScan tile_scan(double w, bool active, double tile_prefix, double eps, TileScanSmem& sm) {
+__device__ __forceinline__ SegE sege_identity() { SegE e; e.f = segf_identity(); e.head = -1; return e; }
+__device__ __forceinline__ SegE sege_shfl(const SegE& v, int src) {
+    SegE r;
+    r.f.d0 = __shfl_sync(0xffffffffu, v.f.d0, src); r.f.d1 = __shfl_sync(0xffffffffu, v.f.d1, src);
+    r.f.b = __shfl_sync(0xffffffffu, v.f.b, src); r.f.pad = __shfl_sync(0xffffffffu, v.f.pad, src);
+    r.head = __shfl_sync(0xffffffffu, v.head, src);
+    return r;
+}
+
+// Tile-local approximate inclusive prefix + classification + segmented function scan.
+// blockDim.x == SCAN_THREADS; thread t holds elements 4t .. 4t+3 of the tile (inactive ones as w = 0).
+// The order of the floating-point adds is fixed, so k_norm_scan and k_cdf see identical bits.
+__device__ __forceinline__ void tile_scan(const double w[EPT], double tile_prefix, double eps, TileScanSmem& sm, TileScan& r) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // approximate inclusive prefix (fixed order -> k_norm_scan and k_cdf see identical bits)
-    double a = w;
+    // approximate prefix: local inclusive sums, warp scan of the thread totals, scan of the 8 warp totals
+    double l[EPT];
+    l[0] = w[0]; l[1] = l[0] + w[1]; l[2] = l[1] + w[2]; l[3] = l[2] + w[3];
+    double a = l[3];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, a, o); if (lane >= o) a += v; }
     __syncthreads();
     if (lane == 31) sm.d[warp] = a;
     __syncthreads();
-    double wp = sm.d[lane];
+    double wp = sm.d[lane & 7];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, wp, o); if (lane >= o) wp += v; }
+    for (int o = 1; o < 8; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, wp, o); if ((lane & 7) >= o) wp += v; }
     const double warp_excl = __shfl_sync(0xffffffffu, wp, max(warp - 1, 0));
-    const double a_cur = tile_prefix + ((warp > 0 ? warp_excl : 0.0) + a);
-    double a_prev = __shfl_up_sync(0xffffffffu, a_cur, 1);
-    if (lane == 0) a_prev = tile_prefix + (warp > 0 ? warp_excl : 0.0);
+    double lane_excl = __shfl_up_sync(0xffffffffu, a, 1);
+    if (lane == 0) lane_excl = 0.0;
+    const double base = tile_prefix + ((warp > 0 ? warp_excl : 0.0) + lane_excl);
 
-    TileScan r;
-    r.cls = classify_elem(active ? w : 0.0, a_prev, a_cur, eps);
-    SegE e; e.f = segf_identity(); e.head = -1;
-    if (r.cls.kind == 1) { e.f.d0 = r.cls.d0; e.f.d1 = r.cls.d1; e.f.b = r.cls.b; }
-    if (r.cls.kind == 2) e.head = (int)threadIdx.x;
-    int cnt = (r.cls.kind == 2) ? 1 : 0;
+    SegE loc[EPT]; int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        const double a_prev = (j == 0) ? base : base + l[j - 1], a_cur = base + l[j];
+        r.cls[j] = classify_elem(w[j], a_prev, a_cur, eps);
+        SegE e = sege_identity();
+        if (r.cls[j].kind == 1) { e.f.d0 = r.cls[j].d0; e.f.d1 = r.cls[j].d1; e.f.b = r.cls[j].b; }
+        if (r.cls[j].kind == 2) e.head = (int)threadIdx.x * EPT + j;
+        loc[j] = (j == 0) ? e : sege_combine(loc[j - 1], e);
+        r.bnd_before[j] = cnt;
+        cnt += (r.cls[j].kind == 2) ? 1 : 0;
+    }
+    // scan of the per-thread aggregates
+    SegE agg = loc[EPT - 1]; int c = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const SegE v = sege_shfl_up(e, o); const int cv = __shfl_up_sync(0xffffffffu, cnt, o);
-        if (lane >= o) { e = sege_combine(v, e); cnt += cv; }
+        const SegE v = sege_shfl_up(agg, o); const int cv = __shfl_up_sync(0xffffffffu, c, o);
+        if (lane >= o) { agg = sege_combine(v, agg); c += cv; }
     }
     __syncthreads();
-    if (lane == 31) { sm.e[warp] = e; sm.c[warp] = cnt; }
+    if (lane == 31) { sm.e[warp] = agg; sm.c[warp] = c; }
     __syncthreads();
-    SegE we = sm.e[lane]; int wc = sm.c[lane];
+    SegE we = sm.e[lane & 7]; int wc = sm.c[lane & 7];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
+    for (int o = 1; o < 8; o <<= 1) {
         const SegE v = sege_shfl_up(we, o); const int cv = __shfl_up_sync(0xffffffffu, wc, o);
-        if (lane >= o) { we = sege_combine(v, we); wc += cv; }
+        if ((lane & 7) >= o) { we = sege_combine(v, we); wc += cv; }
     }
-    const int src = max(warp - 1, 0);
-    SegE pe; pe.f.d0 = __shfl_sync(0xffffffffu, we.f.d0, src); pe.f.d1 = __shfl_sync(0xffffffffu, we.f.d1, src);
-    pe.f.b = __shfl_sync(0xffffffffu, we.f.b, src); pe.f.pad = __shfl_sync(0xffffffffu, we.f.pad, src);
-    pe.head = __shfl_sync(0xffffffffu, we.head, src);
-    const int pc = __shfl_sync(0xffffffffu, wc, src);
-    r.bnd_total = __shfl_sync(0xffffffffu, wc, 31);
-    if (warp > 0) { e = sege_combine(pe, e); cnt += pc; }
-    r.inc = e;
-    r.bnd_before = cnt - ((r.cls.kind == 2) ? 1 : 0);
-    return r;
+    r.bnd_total = __shfl_sync(0xffffffffu, wc, 7);
+    const SegE wpre = sege_shfl(we, max(warp - 1, 0)); const int wcpre = __shfl_sync(0xffffffffu, wc, max(warp - 1, 0));
+    SegE excl = sege_shfl_up(agg, 1); int cexcl = __shfl_up_sync(0xffffffffu, c, 1);
+    if (lane == 0) { excl = sege_identity(); cexcl = 0; }
+    if (warp > 0) { excl = sege_combine(wpre, excl); cexcl += wcpre; }
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) { r.inc[j] = sege_combine(excl, loc[j]); r.bnd_before[j] += cexcl; }
+}
+
+__device__ __forceinline__ void load4(const double* p, unsigned long long i0, unsigned long long n, double w[EPT]) {
+    if (i0 + EPT <= n) {
+        const double2 a = *reinterpret_cast<const double2*>(p + i0), b = *reinterpret_cast<const double2*>(p + i0 + 2);
+        w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) w[j] = (i0 + j < n) ? p[i0 + j] : 0.0;
+    }
+}
+__device__ __forceinline__ void store4(double* p, unsigned long long i0, unsigned long long n, const double w[EPT]) {
+    if (i0 + EPT <= n) {
+        *reinterpret_cast<double2*>(p + i0) = make_double2(w[0], w[1]);
+        *reinterpret_cast<double2*>(p + i0 + 2) = make_double2(w[2], w[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) if (i0 + j < n) p[i0 + j] = w[j];
+    }
 }
 
 // normalise (src/ParticleFilter.hpp:51-67), per-tile sum of w^2, and the tile descriptors of the exact running sum
-__global__ void __launch_bounds__(1024, 1) k_norm_scan(StateBufs st, const DevScalars* sc, unsigned long long n,
-                                                       unsigned long long n_global, const double* tile_prefix,
-                                                       double* tile_sq, TileDesc* desc, BndEntry* pool, DevScalars* scw, int normalise,
-                                                       double eps, unsigned tile_ofs) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_norm_scan(StateBufs st, const DevScalars* sc, unsigned long long n,
+                                                            unsigned long long n_global, const double* tile_prefix,
+                                                            double* tile_sq, TileDesc* desc, BndEntry* pool, DevScalars* scw,
+                                                            int normalise, double eps, unsigned tile_ofs) {
     __shared__ TileScanSmem sm;
-    __shared__ double red[32];
+    __shared__ double red[8];
     __shared__ int slot_of[TILE];
+    __shared__ int first_kind[SCAN_THREADS / 32 + 1];
     __shared__ int s_base;
     const int cur = sc->cur;
-    const unsigned long long i = (unsigned long long)blockIdx.x * TILE + threadIdx.x;
-    const bool active = i < n;
-    double w = 0.0;
-    if (active) {
-        w = st.f[cur][F_W][i];
-        if (normalise) {
-            if (sc->uniform) w = 1.0 / (double)n_global;                              // :55
-            else w /= sc->sum_w;                                                     // :64
-            st.f[cur][F_W][i] = w;
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
+    double w[EPT];
+    load4(st.f[cur][F_W], i0, n, w);
+    if (normalise) {
+        const int uniform = sc->uniform; const double sum_w = sc->sum_w;
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            if (i0 + j < n) {
+                if (uniform) w[j] = 1.0 / (double)n_global;                           // :55
+                else w[j] /= sum_w;                                                  // :64
+            }
         }
+        store4(st.f[cur][F_W], i0, n, w);
     }
-    const double sq = tile_tree_sum_1024(w * w, red);                                 // effective += w*w
+    double q[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) q[j] = w[j] * w[j];                                 // effective += w*w
+    const double sq = tile_tree_sum4(q, red);
     if (threadIdx.x == 0) tile_sq[blockIdx.x] = sq;
 
-    const TileScan ts = tile_scan(w, active, tile_prefix[tile_ofs + blockIdx.x], eps, sm);
+    TileScan ts;
+    tile_scan(w, tile_prefix[tile_ofs + blockIdx.x], eps, sm, ts);
     TileDesc* D = &desc[blockIdx.x];
-    slot_of[threadIdx.x] = ts.bnd_before;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) slot_of[threadIdx.x * EPT + j] = ts.bnd_before[j];
+    if ((threadIdx.x & 31) == 0) first_kind[threadIdx.x >> 5] = ts.cls[0].kind;
     if (threadIdx.x == 0) {
         int base = 0;
         if (ts.bnd_total > 0) base = atomicAdd(&scw->pool_count, ts.bnd_total);
         s_base = base;
         D->n_bnd = ts.bnd_total; D->overflow = (base + ts.bnd_total > MAX_BND_TOTAL) ? 1 : 0; D->bnd_base = base; D->pad2 = 0;
         D->head_b = BIN_NONE; D->head_d0 = 0; D->head_d1 = 0; D->pad = 0;
+        first_kind[SCAN_THREADS / 32] = 2;                                           // past the tile end: closes the last piece
     }
     __syncthreads();
     if (s_base + ts.bnd_total <= MAX_BND_TOTAL) {
         BndEntry* B = pool + s_base;
-        if (ts.cls.kind == 2) { B[ts.bnd_before].w = w; B[ts.bnd_before].idx = (int)threadIdx.x; }
-        // piece ends: the next element is a boundary, or this is the last element of the tile
-        const int next_kind = __shfl_down_sync(0xffffffffu, ts.cls.kind, 1);
-        __shared__ int first_kind[32];
-        if ((threadIdx.x & 31) == 0) first_kind[threadIdx.x >> 5] = ts.cls.kind;
-        __syncthreads();
-        int nk = next_kind;
-        if ((threadIdx.x & 31) == 31) nk = (threadIdx.x == TILE - 1) ? 2 : first_kind[(threadIdx.x >> 5) + 1];
-        if (nk == 2) {
-            if (ts.inc.head < 0) { D->head_b = ts.inc.f.b; D->head_d0 = ts.inc.f.d0; D->head_d1 = ts.inc.f.d1; D->pad = ts.inc.f.pad; }
-            else {
-                const int s = slot_of[ts.inc.head];
-                B[s].b = ts.inc.f.b; B[s].d0 = ts.inc.f.d0; B[s].d1 = ts.inc.f.d1;
-                if (ts.inc.f.pad) D->overflow = 1;
+        // kind of the element after this thread's last one
+        int next_first = __shfl_down_sync(0xffffffffu, ts.cls[0].kind, 1);
+        if ((threadIdx.x & 31) == 31) next_first = first_kind[(threadIdx.x >> 5) + 1];
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            if (ts.cls[j].kind == 2) { B[ts.bnd_before[j]].w = w[j]; B[ts.bnd_before[j]].idx = (int)threadIdx.x * EPT + j; }
+            // piece ends: the next element is a boundary, or this is the last element of the tile
+            const int nk = (j + 1 < EPT) ? ts.cls[(j + 1) & (EPT - 1)].kind : next_first;
+            if (nk == 2) {
+                const SegE& e = ts.inc[j];
+                if (e.head < 0) { D->head_b = e.f.b; D->head_d0 = e.f.d0; D->head_d1 = e.f.d1; D->pad = e.f.pad; }
+                else {
+                    const int sl = slot_of[e.head];
+                    B[sl].b = e.f.b; B[sl].d0 = e.f.d0; B[sl].d1 = e.f.d1;
+                    if (e.f.pad) D->overflow = 1;
+                }
             }
         }
     }
@@ -906,47 +994,64 @@ __global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, const B
 }
 
 // exact running sum of every element: cdf[i] == the reference's sum_w after adding xi_k[i].weight
-__global__ void __launch_bounds__(1024, 1) k_cdf(StateBufs st, DevScalars* sc, unsigned long long n,
-                                                 const double* tile_prefix, const int* tile_bofs, const double* tile_sin,
-                                                 const double* sb, double* cdf, double eps, unsigned tile_ofs) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_cdf(StateBufs st, DevScalars* sc, unsigned long long n,
+                                                      const double* tile_prefix, const int* tile_bofs, const double* tile_sin,
+                                                      const double* sb, double* cdf, double eps, unsigned tile_ofs) {
     __shared__ TileScanSmem sm;
     __shared__ int slot_of[TILE];
     if (!sc->do_resample || (sc->error_flags & ERR_CDF_FALLBACK_BIT)) return;
     const int cur = sc->cur;
-    const unsigned long long i = (unsigned long long)blockIdx.x * TILE + threadIdx.x;
-    const bool active = i < n;
-    const double w = active ? st.f[cur][F_W][i] : 0.0;
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
+    double w[EPT];
+    load4(st.f[cur][F_W], i0, n, w);
     const unsigned gt = tile_ofs + blockIdx.x;
-    const TileScan ts = tile_scan(w, active, tile_prefix[gt], eps, sm);
-    slot_of[threadIdx.x] = ts.bnd_before;
+    TileScan ts;
+    tile_scan(w, tile_prefix[gt], eps, sm, ts);
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) slot_of[threadIdx.x * EPT + j] = ts.bnd_before[j];
     __syncthreads();
     int bad = 0;
-    double S;
+    double S[EPT];
     const int ofs = tile_bofs[gt];
-    if (ts.cls.kind == 2) S = sb[ofs + ts.bnd_before];
-    else if (ts.inc.head < 0) S = segf_apply(tile_sin[gt], ts.inc.f, bad);
-    else S = segf_apply(sb[ofs + slot_of[ts.inc.head]], ts.inc.f, bad);
+    const double s_in = tile_sin[gt];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        if (ts.cls[j].kind == 2) S[j] = sb[ofs + ts.bnd_before[j]];
+        else if (ts.inc[j].head < 0) S[j] = segf_apply(s_in, ts.inc[j].f, bad);
+        else S[j] = segf_apply(sb[ofs + slot_of[ts.inc[j].head]], ts.inc[j].f, bad);
+    }
     if (bad) atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT);
-    if (active) cdf[i] = S;
+    store4(cdf, i0, n, S);
 }
 
 // fallback: literal left-to-right running sum by one thread (only when the tile descriptors overflowed)
-__global__ void k_cdf_sequential(StateBufs st, DevScalars* sc, unsigned long long n, double* cdf) {
+__global__ void k_cdf_sequential(StateBufs st, DevScalars* sc, unsigned long long n, double* cdf, double* tile_sin) {
     if (!sc->do_resample || !(sc->error_flags & ERR_CDF_FALLBACK_BIT)) return;
     const double* w = st.f[sc->cur][F_W];
     double s = 0.0;
-    for (unsigned long long i = 0; i < n; ++i) { s = (i == 0) ? w[0] : s + w[i]; cdf[i] = s; }
+    for (unsigned long long i = 0; i < n; ++i) {
+        if ((i & (TILE - 1)) == 0) tile_sin[i / TILE] = s;
+        s = (i == 0) ? w[0] : s + w[i]; cdf[i] = s;
+    }
     sc->error_flags &= ~ERR_CDF_FALLBACK_BIT;
     sc->fallbacks += 1;
 }
 
 // ------------------------------------------------------------------------------------------------ resample
-// the stratified walk (src/ParticleFilter.hpp:96-105) as a lower-bound search: ancestor[k] = first idx with
-// !(cdf[idx] < sum_r).  cdf_win holds the exact running sum of global elements [win_base, win_base + win_len)
-// (the whole local array on one GPU; the window fetched from the owning ranks otherwise).
-__global__ void k_search(const DevScalars* sc, const double* __restrict__ cdf_win, unsigned long long win_len,
-                         unsigned long long win_base, unsigned long long n, unsigned long long n_global,
-                         unsigned long long base, uint32_t k0, uint32_t k1, int systematic, uint32_t* ancestors) {
+// The stratified walk (src/ParticleFilter.hpp:96-105) as a lower-bound search, fused with the copy (:104):
+// ancestor[k] = first idx with !(cdf[idx] < sum_r); out[k] = in[ancestor[k]].
+// cdf_win holds the exact running sum of global elements [win_base, win_base + win_len) (the whole local array on one
+// GPU; the window fetched from the owning ranks otherwise) and tile_start[t] the exact sum before the window's t-th
+// 1024-tile, so the search is two-level: 10 steps over the tile starts (8 KB, cache resident), then 10 steps inside one
+// tile.  Correct because tile_start[t] == cdf[1024 t - 1]: everything before the last tile whose start is below sum_r
+// is below sum_r too, and the next tile's start is not.
+struct GatherSrc { const double* f[7]; const uint8_t* b[2]; unsigned long long base; int use_window; };
+
+__global__ void __launch_bounds__(256) k_resample(StateBufs st, const DevScalars* sc, const double* __restrict__ cdf_win,
+                                                  const double* __restrict__ tile_start, unsigned n_tiles_win,
+                                                  unsigned long long win_len, unsigned long long win_base,
+                                                  unsigned long long n, unsigned long long n_global, unsigned long long base,
+                                                  uint32_t k0, uint32_t k1, int systematic, uint32_t* ancestors, GatherSrc src) {
     if (!sc->do_resample) return;
     const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -954,25 +1059,19 @@ __global__ void k_search(const DevScalars* sc, const double* __restrict__ cdf_wi
     const em::Philox4 r = em::philox4x32_10((uint32_t)gk, sc->resample_step, 0, stream_word(em::STREAM_RESAMPLE, gk), k0, k1);
     const double u = em::u01(r.v[0], r.v[1]);
     const double sum_r = ((double)(base + k) + u) / (double)n_global;                // :98
-    unsigned long long lo = 0, hi = win_len;
+    unsigned tlo = 0, thi = n_tiles_win;                                             // first tile with !(start < sum_r)
+    while (tlo < thi) { const unsigned mid = (tlo + thi) >> 1; if (__ldg(&tile_start[mid]) < sum_r) tlo = mid + 1; else thi = mid; }
+    const unsigned t = tlo == 0 ? 0 : tlo - 1;
+    unsigned long long lo = (unsigned long long)t * TILE, hi = min(lo + TILE, win_len);
     while (lo < hi) {
         const unsigned long long mid = (lo + hi) >> 1;
         if (__ldg(&cdf_win[mid]) < sum_r) lo = mid + 1; else hi = mid;
     }
-    lo += win_base;
-    if (lo >= n_global) lo = n_global - 1;        // the reference walks off the end here; we stop at the last particle
-    ancestors[k] = (uint32_t)lo;
-}
-
-struct GatherSrc { const double* f[7]; const uint8_t* b[2]; unsigned long long base; int use_window; };
-
-__global__ void k_gather(StateBufs st, const DevScalars* sc, unsigned long long n, const uint32_t* __restrict__ anc,
-                         GatherSrc src) {
-    if (!sc->do_resample) return;
-    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    unsigned long long a = lo;                    // window-relative
+    if (a + win_base >= n_global) a = n_global - 1 - win_base;   // the reference walks off the end here; we stop at the last particle
+    if (a >= win_len) a = win_len - 1;
+    ancestors[k] = (uint32_t)(a + win_base);
     const int cur = sc->cur, nxt = cur ^ 1;
-    const unsigned long long a = (unsigned long long)anc[k] - src.base;
 #pragma unroll
     for (int f = 0; f < 7; ++f) {
         const double* in = src.use_window ? src.f[f] : st.f[cur][f];
