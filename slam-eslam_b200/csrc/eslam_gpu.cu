@@ -32,6 +32,7 @@ struct eslam_gpu_ctx {
     uint64_t n, cap;
     StateBufs st;
     DevScalars* sc; DevScalars* sc_host;          // sc_host: pinned staging
+    double* tile_hint;                            // pinned {cx, cy}: cloud centre, refreshed asynchronously after every update
     uint32_t* ancestors; double* cdf;
     float2* patch[2]; int* porigin[2];            // per-particle map patches (cfg.patch_size > 0), double buffered
     // per-tile arrays: l_* cover the local tiles, g_* all tiles of all ranks (aliases of l_* when world == 1)
@@ -45,6 +46,7 @@ struct eslam_gpu_ctx {
     uint64_t win_cap; double* win_cdf; double* win_f[7]; uint8_t* win_b[2];
     // map
     float2* cells; MapParams map; bool has_map;
+    CUtensorMap tmap; bool has_tmap;              // TMA descriptor of the grid for the shared-memory tile
     em::dbl2* htab;
     int max_smem_optin, sm_count;
     uint32_t project_step;
@@ -200,7 +202,7 @@ static int build_contact_set(eslam_gpu_ctx* ctx, const eslam_gpu_contact* pts, i
 }
 
 static size_t weight_smem_bytes(const eslam_gpu_ctx* ctx) {
-    return HTAB_BYTES + 1024 + 256 + (size_t)ctx->map.tile_w * ctx->map.tile_h * sizeof(float2);
+    return HTAB_BYTES + WT_SCRATCH_BYTES + (size_t)ctx->map.tile_w * ctx->map.tile_h * sizeof(float2);
 }
 
 // empty maps for every particle: NaN cells (0xFF bytes), un-anchored origins
@@ -257,7 +259,7 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     ctx->win_cap = 0; ctx->win_cdf = nullptr;
     for (int f = 0; f < 7; ++f) ctx->win_f[f] = nullptr;
     for (int f = 0; f < 2; ++f) ctx->win_b[f] = nullptr;
-    ctx->cells = nullptr; ctx->has_map = false; ctx->project_step = 0;
+    ctx->cells = nullptr; ctx->has_map = false; ctx->has_tmap = false; ctx->project_step = 0;
     memset(&ctx->map, 0, sizeof(ctx->map));
     *out = ctx;
     CK(cudaSetDevice(device));
@@ -267,6 +269,8 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     CK(dalloc(&ctx->sc, 1));
     CK(cudaMemsetAsync(ctx->sc, 0, sizeof(DevScalars), ctx->stream));
     CK(cudaMallocHost((void**)&ctx->sc_host, sizeof(DevScalars)));
+    CK(cudaMallocHost((void**)&ctx->tile_hint, 2 * sizeof(double)));
+    ctx->tile_hint[0] = ctx->tile_hint[1] = 0.0;
     CK(dalloc(&ctx->htab, (size_t)ESLAM_H_NINT * 3));
     CK(cudaMemcpyAsync(ctx->htab, H_TABLE_HOST, sizeof(H_TABLE_HOST), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainSmem)));
@@ -280,7 +284,7 @@ void eslam_gpu_destroy(eslam_gpu_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->has_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     free_particles(ctx); free_window(ctx);
-    cudaFree(ctx->sc); cudaFreeHost(ctx->sc_host); cudaFree(ctx->htab); cudaFree(ctx->cells);
+    cudaFree(ctx->sc); cudaFreeHost(ctx->sc_host); cudaFreeHost(ctx->tile_hint); cudaFree(ctx->htab); cudaFree(ctx->cells);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -332,11 +336,33 @@ int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int he
     m.identity = g2l == nullptr;
     for (int i = 0; i < 8; ++i) m.g2l[i] = g2l ? g2l[i] : (i == 0 || i == 5 ? 1.0 : 0.0);
     // shared-memory map tile: as many cells as fit next to the h-table
-    const size_t avail = (size_t)ctx->max_smem_optin - (HTAB_BYTES + 1024 + 256);
+    const size_t avail = (size_t)ctx->max_smem_optin - (HTAB_BYTES + WT_SCRATCH_BYTES);
     int side = (int)floor(sqrt((double)(avail / sizeof(float2))));
     m.tile_w = width < side ? width : side;
     m.tile_h = (int)((avail / sizeof(float2)) / (size_t)m.tile_w);
     if (m.tile_h > height) m.tile_h = height;
+    if (m.tile_w > 256) m.tile_w = 256;                           // TMA box limit per dimension
+    if (m.tile_h > 256) m.tile_h = 256;
+    // TMA descriptor: 2-D tensor of 8-byte cells, box = the tile.  Needs 16-byte multiples for the row pitch and the
+    // box's inner extent; otherwise the kernel stages the tile with ordinary loads.
+    ctx->has_tmap = false;
+    if ((width % 2) == 0 && (m.tile_w % 2) == 0) {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+            qres == cudaDriverEntryPointSuccess) {
+            const cuuint64_t gdim[2] = {(cuuint64_t)width, (cuuint64_t)height};
+            const cuuint64_t gstride[1] = {(cuuint64_t)width * sizeof(float2)};
+            const cuuint32_t box[2] = {(cuuint32_t)m.tile_w, (cuuint32_t)m.tile_h};
+            const cuuint32_t estr[2] = {1, 1};
+            const CUresult r = ((EncodeFn)fn)(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)ctx->cells, gdim, gstride, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            ctx->has_tmap = (r == CUDA_SUCCESS);
+        }
+    }
     const int bytes = (int)weight_smem_bytes(ctx);
     CK(cudaFuncSetAttribute(k_project_weight<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_project_weight<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -355,6 +381,7 @@ int eslam_gpu_init_gaussian(eslam_gpu_ctx* ctx, uint64_t n, const double mu[3], 
     if (st != ESLAM_OK) return st;
     DevScalars init; memset(&init, 0, sizeof(init));
     init.tile_cx = mu[0]; init.tile_cy = mu[1];
+    ctx->tile_hint[0] = mu[0]; ctx->tile_hint[1] = mu[1];
     *ctx->sc_host = init;
     CK(cudaMemcpyAsync(ctx->sc, ctx->sc_host, sizeof(DevScalars), cudaMemcpyHostToDevice, ctx->stream));
     ctx->project_step = 0;
@@ -418,12 +445,21 @@ static void fill_weight_params(eslam_gpu_ctx* ctx, WeightParams* P, const eslam_
     P->st = ctx->st; P->sc = ctx->sc; P->part = ctx->l_part_a; P->map = ctx->map; P->mp = model_params(ctx);
     P->htab = ctx->htab; P->n = ctx->n; P->base = base_index(ctx); P->project_step = ctx->project_step;
     P->patch_size = ctx->cfg.patch_size > 0 ? ctx->cfg.patch_size : 0;
+    P->use_tma = ctx->has_tmap && !getenv("ESLAM_GPU_NO_TMA");
+    if (ctx->has_tmap) P->tmap = ctx->tmap;
     for (int b = 0; b < 2; ++b) { P->patch[b] = ctx->patch[b]; P->porigin[b] = ctx->porigin[b]; }
     if (step) {
         P->yaw = step->yaw; P->z_delta = step->z_delta; P->z_var = step->z_var;
         for (int i = 0; i < 3; ++i) { P->dmean[i] = step->delta_mean[i]; P->dsigma[i] = step->delta_sigma[i]; }
     }
     if (cs) P->cs = *cs;
+    // where to put the shared-memory map tile: around the cloud centre the device reported last (a hint: it may be a
+    // few steps old when steps are enqueued without synchronisation; results do not depend on it)
+    volatile double* hint = ctx->tile_hint;
+    double cx = (hint[0] - ctx->map.ox) * ctx->map.inv_sx, cy = (hint[1] - ctx->map.oy) * ctx->map.inv_sy;
+    if (!(cx > -1e9 && cx < 1e9)) cx = 0;
+    if (!(cy > -1e9 && cy < 1e9)) cy = 0;
+    P->map.tile_x0 = (int)cx - ctx->map.tile_w / 2; P->map.tile_y0 = (int)cy - ctx->map.tile_h / 2;
 }
 
 static unsigned weight_grid(const eslam_gpu_ctx* ctx) {
@@ -601,6 +637,7 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
     k_reduce_a<<<1, 1024, 0, ctx->stream>>>(ctx->g_part_a, ctx->t_global, global_count(ctx), ctx->sc, ctx->scratch_a, ctx->scratch_b,
                                             ctx->cfg.discount_factor);
     LAUNCHED();
+    CK(cudaMemcpyAsync(ctx->tile_hint, &ctx->sc->tile_cx, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return launch_tail(ctx, true, 1, 1, 0);
 }
 

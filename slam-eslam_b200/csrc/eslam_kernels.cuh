@@ -18,6 +18,7 @@
 // Arithmetic is that of eslam_math.h (compile with -fmad=false); all global sums are pairwise over the
 // index-aligned binary tree, so results do not depend on grid size, SM count or number of GPUs.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <limits.h>
 #include <stdint.h>
@@ -79,6 +80,7 @@ struct MapParams {
     double g2l[8];               // rows 0 and 1 of C_global2local
     int identity;
     int tile_w, tile_h;          // shared-memory tile (cells)
+    int tile_x0, tile_y0;        // its origin: a placement hint from the host (any value gives the same results)
 };
 
 struct ModelParams {             // eslam::Configuration hot fields
@@ -96,6 +98,8 @@ struct WeightParams {
     unsigned long long n, base;  // local particle count, global index of local particle 0
     uint32_t project_step;
     int patch_size;              // P (0: no per-particle patches)
+    int use_tma;                 // the map tile is staged by one TMA bulk tensor copy (tmap valid)
+    alignas(64) CUtensorMap tmap;  // 2-D tensor map of the elevation grid (8-byte cells), box = the shared-memory tile
     float2* patch[2]; int* porigin[2];   // double buffered with the particle state: [N][P][P] cells, [N][2] origins
     double yaw, z_delta, z_var, dmean[3], dsigma[3];
     ContactSet cs;
@@ -142,8 +146,27 @@ __device__ __forceinline__ double tile_tree_sum_1024(double v, double* red) {
     return warp_tree_sum(t);
 }
 
-// Pairwise tree over n values in global memory, continuing the per-tile trees; one CTA; a/b ping-pong.
-__device__ double block_tree_reduce(double* a, double* b, unsigned n) {
+// Pairwise tree over n values in global memory, continuing the per-tile trees; one CTA.  With shared scratch
+// (sa: TREE_SMEM doubles, sb: TREE_SMEM/2) and n <= 2*TREE_SMEM all levels but the first run in shared memory;
+// otherwise the levels ping-pong between the global arrays a and b.  Same tree either way.
+#define TREE_SMEM 2048
+__device__ double block_tree_reduce(double* a, double* b, unsigned n, double* sa = nullptr, double* sb = nullptr) {
+    if (sa && n > 1 && ((n + 1) >> 1) <= TREE_SMEM) {
+        unsigned h = (n + 1) >> 1;
+        for (unsigned i = threadIdx.x; i < h; i += blockDim.x) sa[i] = (2 * i + 1 < n) ? a[2 * i] + a[2 * i + 1] : a[2 * i];
+        __syncthreads();
+        n = h;
+        double *x = sa, *y = sb;
+        while (n > 1) {
+            h = (n + 1) >> 1;
+            for (unsigned i = threadIdx.x; i < h; i += blockDim.x) y[i] = (2 * i + 1 < n) ? x[2 * i] + x[2 * i + 1] : x[2 * i];
+            __syncthreads();
+            double* t = x; x = y; y = t; n = h;
+        }
+        const double r = x[0];
+        __syncthreads();
+        return r;
+    }
     while (n > 1) {
         unsigned h = (n + 1) >> 1;
         for (unsigned i = threadIdx.x; i < h; i += blockDim.x)
@@ -386,36 +409,67 @@ __global__ void k_init_gaussian(StateBufs st, DevScalars* sc, unsigned long long
 
 // ------------------------------------------------------------------------------------------------ fused project + weight
 #define HTAB_BYTES (ESLAM_H_NINT * 3 * 16)
+#define WT_SCRATCH_BYTES (1024 + 256 + 128)   // tile-reduction scratch (doubles, unsigned) + the TMA mbarrier (padded to 128 B)
+
+// TMA (cp.async.bulk.tensor) + mbarrier helpers: one thread arms the barrier with the byte count and issues the copy,
+// everyone waits on the barrier's phase before reading the tile.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t mbar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(mbar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t phase) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(mbar), "r"(phase) : "memory");
+    } while (!ok);
+}
 
 template <bool DO_PROJECT, bool DO_WEIGHT, bool PATCH>
 __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_constant__ WeightParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     em::dbl2* htab = reinterpret_cast<em::dbl2*>(smem_raw);
     double* red = reinterpret_cast<double*>(smem_raw + HTAB_BYTES);             // 4 x 32 doubles
     unsigned* redu = reinterpret_cast<unsigned*>(smem_raw + HTAB_BYTES + 1024); // 2 x 32 unsigned
-    float2* tile = reinterpret_cast<float2*>(smem_raw + HTAB_BYTES + 1024 + 256);
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(smem_raw + HTAB_BYTES + 1024 + 256);
+    float2* tile = reinterpret_cast<float2*>(smem_raw + HTAB_BYTES + WT_SCRATCH_BYTES);   // 128-byte aligned
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevScalars* sc = P.sc;
     const int cur = sc->cur;
     MapTile mt; mt.s = tile; mt.w = 0; mt.h = 0; mt.x0 = 0; mt.y0 = 0;
     if (DO_WEIGHT) {
-        for (int i = tid; i < ESLAM_H_NINT * 3; i += WT_THREADS) htab[i] = P.htab[i];
+        const bool tma = P.use_tma && P.map.tile_w > 0;
         if (P.map.tile_w > 0) {
             // stage the map tile around the particle cloud into shared memory
             mt.w = P.map.tile_w; mt.h = P.map.tile_h;
-            double cx = (sc->tile_cx - P.map.ox) * P.map.inv_sx, cy = (sc->tile_cy - P.map.oy) * P.map.inv_sy;
-            if (!(cx > -1e9 && cx < 1e9)) cx = 0;
-            if (!(cy > -1e9 && cy < 1e9)) cy = 0;
-            int x0 = (int)cx - mt.w / 2, y0 = (int)cy - mt.h / 2;
-            x0 = max(0, min(x0, P.map.W - mt.w)); y0 = max(0, min(y0, P.map.H - mt.h));
+            const int x0 = max(0, min(P.map.tile_x0, P.map.W - mt.w)), y0 = max(0, min(P.map.tile_y0, P.map.H - mt.h));
             mt.x0 = x0; mt.y0 = y0;
-            const int cells = mt.w * mt.h;
-            for (int i = tid; i < cells; i += WT_THREADS) {
-                const int r = i / mt.w, cc = i - r * mt.w;
-                tile[i] = __ldg(&P.map.cells[(size_t)(y0 + r) * P.map.W + x0 + cc]);
+            if (tma) {
+                // one TMA bulk tensor copy: box (tile_w x tile_h cells) at (x0, y0) of the 2-D grid -> shared memory
+                if (tid == 0) mbar_init(mbar, 1);
+                __syncthreads();
+                if (tid == 0) {
+                    mbar_expect_tx(mbar, (uint32_t)(mt.w * mt.h) * (uint32_t)sizeof(float2));
+                    tma_load_2d((uint32_t)__cvta_generic_to_shared(tile), &P.tmap, mbar, x0, y0);
+                }
+            } else {
+                const int cells = mt.w * mt.h;
+                for (int i = tid; i < cells; i += WT_THREADS) {
+                    const int r = i / mt.w, cc = i - r * mt.w;
+                    tile[i] = __ldg(&P.map.cells[(size_t)(y0 + r) * P.map.W + x0 + cc]);
+                }
             }
         }
+        for (int i = tid; i < ESLAM_H_NINT * 3; i += WT_THREADS) htab[i] = P.htab[i];   // overlaps the TMA copy
         __syncthreads();
+        if (tma) mbar_wait(mbar, 0);
     }
     double spread = 0.0;
     if (DO_PROJECT) spread = weighting_function(sc->max_weight, 0.0, P.mp.spread_thr, 0.0);   // :194
@@ -461,12 +515,12 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_c
                     y += sy * trans_fac + 0.0;
                     th += sth * rot_fac + 0.0;
                 }
-                X[i] = x; Y[i] = y; TH[i] = th;
-                if (!DO_WEIGHT) { Z[i] = z; ZS[i] = zs; WG[i] = w; }
+                X[i] = x; Y[i] = y; TH[i] = th; Z[i] = z; ZS[i] = zs; WG[i] = w;   // everything project changed
             }
             if (DO_WEIGHT) {                                                     // :276-327
                 double s, c; em::sincos_(th, s, c);
-                const double mv = zs * zs + P.mp.merr2;                          // :290
+                const double zs2 = zs * zs;
+                const double mv = zs2 + P.mp.merr2;                              // :290
                 if (mv == 0) atomicOr(&P.sc->error_flags, ERR_ZERO_VARIANCE_BIT);   // src/ContactModel.cpp:122-123
                 PoseEval ev;
                 PatchRef pr; pr.cells = nullptr; pr.ox = INT_MIN; pr.oy = 0; pr.P = 0;
@@ -485,15 +539,15 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_c
                 if ((unsigned long long)ev.n_found >= P.mp.min_contacts) {       // ContactModel.cpp:217
                     double weight, zdl, zvr;
                     evaluate_weight(ev, P.mp.use_shape, weight, zdl, zvr);
-                    double zVar = zs * zs;                                       // :294
+                    double zVar = zs2;                                           // :294
                     update_z(ev, zdl, zvr, z, zVar);                             // :295
-                    zs = em::sqrt_(zVar);                                        // :296
-                    w *= weight;                                                 // :300 (Q1: first application)
+                    Z[i] = z; ZS[i] = em::sqrt_(zVar);                           // :296
+                    WG[i] = WG[i] * weight;                                      // :300 (Q1: first application)
                     mprob = weight; floating = 0;
                     v_mx = weight; v_cnt = 1; v_pts = (unsigned)ev.n_found;      // :305-310
                     v_pw = em::root_n(weight, (unsigned long long)ev.n_found);   // :309
                 }
-                Z[i] = z; ZS[i] = zs; WG[i] = w; MPB[i] = mprob;
+                MPB[i] = mprob;
                 FL[i] = floating; NF[i] = (uint8_t)min(ev.n_found, 255);         // :322 cpoints.size()
                 v_x = x; v_y = y;
             }
@@ -526,6 +580,7 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_a(const TilePartA* part, uns
                                                       double discount) {
     __shared__ double red[32];
     __shared__ unsigned long long redull[64];
+    __shared__ double tree_a[TREE_SMEM], tree_b[TREE_SMEM / 2];
     double mx = 0, sx = 0, sy = 0; unsigned long long cnt = 0, pts = 0;
     for (unsigned i = threadIdx.x; i < n_tiles; i += blockDim.x) {
         const TilePartA p = part[i];
@@ -533,7 +588,7 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_a(const TilePartA* part, uns
         mx = fmax(mx, p.max_w); sx += p.sum_x; sy += p.sum_y; cnt += p.cnt; pts += p.pts;
     }
     __syncthreads();
-    const double sum_pw = block_tree_reduce(scratch_a, scratch_b, n_tiles);
+    const double sum_pw = block_tree_reduce(scratch_a, scratch_b, n_tiles, tree_a, tree_b);
     mx = warp_max(mx); sx = warp_tree_sum(sx); sy = warp_tree_sum(sy);
     for (int o = 1; o < 32; o <<= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); pts += __shfl_xor_sync(0xffffffffu, pts, o); }
     __syncthreads();
@@ -628,9 +683,10 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_b(const double* tile_sum, un
                                                       DevScalars* sc, double* scratch_a, double* scratch_b,
                                                       double* tile_prefix, int normalise) {
     __shared__ double sh[1024];
+    __shared__ double tree_a[TREE_SMEM], tree_b[TREE_SMEM / 2];
     for (unsigned i = threadIdx.x; i < n_tiles; i += blockDim.x) scratch_a[i] = tile_sum[i];
     __syncthreads();
-    const double total = block_tree_reduce(scratch_a, scratch_b, n_tiles);
+    const double total = block_tree_reduce(scratch_a, scratch_b, n_tiles, tree_a, tree_b);
     const int uniform = normalise && (total <= 0.0);                                 // :51 (Q8)
     if (threadIdx.x == 0) { sc->sum_w = total; sc->uniform = uniform; sc->pool_count = 0; }
     // exclusive scan of the per-tile masses (approximate is enough: only used to classify elements)
@@ -901,7 +957,8 @@ __global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, const B
     if (decide) {
         for (unsigned i = tid; i < n_tiles; i += blockDim.x) scratch_a[i] = tile_sq[i];
         __syncthreads();
-        const double eff = block_tree_reduce(scratch_a, scratch_b, n_tiles);
+        const double eff = block_tree_reduce(scratch_a, scratch_b, n_tiles, reinterpret_cast<double*>(chain_raw),
+                                             reinterpret_cast<double*>(chain_raw) + TREE_SMEM);
         if (tid == 0) {
             const double ess = 1.0 / eff;                                             // src/ParticleFilter.hpp:69
             sc->ess = ess;
@@ -1144,10 +1201,11 @@ __global__ void __launch_bounds__(1024, 1) k_centroid_tiles(StateBufs st, const 
 __global__ void __launch_bounds__(1024, 1) k_centroid_final(const double* part, unsigned n_tiles, double* scratch_a,
                                                             double* scratch_b, const unsigned long long* best_idx,
                                                             const double* best_w, DevScalars* sc) {
+    __shared__ double tree_a[TREE_SMEM], tree_b[TREE_SMEM / 2];
     for (int q = 0; q < 5; ++q) {
         for (unsigned t = threadIdx.x; t < n_tiles; t += blockDim.x) scratch_a[t] = part[(size_t)t * 5 + q];
         __syncthreads();
-        const double v = block_tree_reduce(scratch_a, scratch_b, n_tiles);
+        const double v = block_tree_reduce(scratch_a, scratch_b, n_tiles, tree_a, tree_b);
         if (threadIdx.x == 0) sc->centroid[q] = v;
         __syncthreads();
     }
