@@ -46,7 +46,7 @@ struct eslam_gpu_ctx {
     uint64_t win_cap; double* win_cdf; double* win_f[7]; uint8_t* win_b[2];
     // map
     float2* cells; MapParams map; bool has_map;
-    CUtensorMap tmap; bool has_tmap;              // TMA descriptor of the grid for the shared-memory tile
+    CUtensorMap tmap; CUtensorMap* d_tmap; bool has_tmap;   // TMA descriptor of the grid (host copy, device copy)
     em::dbl2* htab;
     int max_smem_optin, sm_count;
     uint32_t project_step;
@@ -259,7 +259,7 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     ctx->win_cap = 0; ctx->win_cdf = nullptr;
     for (int f = 0; f < 7; ++f) ctx->win_f[f] = nullptr;
     for (int f = 0; f < 2; ++f) ctx->win_b[f] = nullptr;
-    ctx->cells = nullptr; ctx->has_map = false; ctx->has_tmap = false; ctx->project_step = 0;
+    ctx->cells = nullptr; ctx->has_map = false; ctx->has_tmap = false; ctx->d_tmap = nullptr; ctx->project_step = 0;
     memset(&ctx->map, 0, sizeof(ctx->map));
     *out = ctx;
     CK(cudaSetDevice(device));
@@ -284,7 +284,7 @@ void eslam_gpu_destroy(eslam_gpu_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->has_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     free_particles(ctx); free_window(ctx);
-    cudaFree(ctx->sc); cudaFreeHost(ctx->sc_host); cudaFreeHost(ctx->tile_hint); cudaFree(ctx->htab); cudaFree(ctx->cells);
+    cudaFree(ctx->sc); cudaFreeHost(ctx->sc_host); cudaFreeHost(ctx->tile_hint); cudaFree(ctx->d_tmap); cudaFree(ctx->htab); cudaFree(ctx->cells);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -338,8 +338,10 @@ int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int he
     // shared-memory map tile: as many cells as fit next to the h-table
     const size_t avail = (size_t)ctx->max_smem_optin - (HTAB_BYTES + WT_SCRATCH_BYTES);
     int side = (int)floor(sqrt((double)(avail / sizeof(float2))));
+    if (getenv("ESLAM_GPU_TILE")) side = atoi(getenv("ESLAM_GPU_TILE"));
     m.tile_w = width < side ? width : side;
     m.tile_h = (int)((avail / sizeof(float2)) / (size_t)m.tile_w);
+    if (getenv("ESLAM_GPU_TILE")) m.tile_h = atoi(getenv("ESLAM_GPU_TILE"));
     if (m.tile_h > height) m.tile_h = height;
     if (m.tile_w > 256) m.tile_w = 256;                           // TMA box limit per dimension
     if (m.tile_h > 256) m.tile_h = 256;
@@ -361,6 +363,16 @@ int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int he
                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             ctx->has_tmap = (r == CUDA_SUCCESS);
+            if (getenv("ESLAM_GPU_TRACE")) {
+                const unsigned long long* q = reinterpret_cast<const unsigned long long*>(&ctx->tmap);
+                fprintf(stderr, "[eslam] tensor map encode=%d cells=%p W=%d H=%d box=%dx%d:", (int)r, (void*)ctx->cells, width, height, m.tile_w, m.tile_h);
+                for (int i = 0; i < 16; ++i) fprintf(stderr, " %016llx", q[i]);
+                fprintf(stderr, "\n");
+            }
+            if (ctx->has_tmap) {
+                if (!ctx->d_tmap) CK(cudaMalloc((void**)&ctx->d_tmap, sizeof(CUtensorMap)));
+                CK(cudaMemcpyAsync(ctx->d_tmap, &ctx->tmap, sizeof(CUtensorMap), cudaMemcpyHostToDevice, ctx->stream));
+            }
         }
     }
     const int bytes = (int)weight_smem_bytes(ctx);
@@ -446,7 +458,7 @@ static void fill_weight_params(eslam_gpu_ctx* ctx, WeightParams* P, const eslam_
     P->htab = ctx->htab; P->n = ctx->n; P->base = base_index(ctx); P->project_step = ctx->project_step;
     P->patch_size = ctx->cfg.patch_size > 0 ? ctx->cfg.patch_size : 0;
     P->use_tma = ctx->has_tmap && !getenv("ESLAM_GPU_NO_TMA");
-    if (ctx->has_tmap) P->tmap = ctx->tmap;
+    P->tmap = ctx->d_tmap;
     for (int b = 0; b < 2; ++b) { P->patch[b] = ctx->patch[b]; P->porigin[b] = ctx->porigin[b]; }
     if (step) {
         P->yaw = step->yaw; P->z_delta = step->z_delta; P->z_var = step->z_var;

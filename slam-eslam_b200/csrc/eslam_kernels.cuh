@@ -99,7 +99,7 @@ struct WeightParams {
     uint32_t project_step;
     int patch_size;              // P (0: no per-particle patches)
     int use_tma;                 // the map tile is staged by one TMA bulk tensor copy (tmap valid)
-    alignas(64) CUtensorMap tmap;  // 2-D tensor map of the elevation grid (8-byte cells), box = the shared-memory tile
+    const CUtensorMap* tmap;     // device copy of the 2-D tensor map of the elevation grid (8-byte cells, box = the tile)
     float2* patch[2]; int* porigin[2];   // double buffered with the particle state: [N][P][P] cells, [N][2] origins
     double yaw, z_delta, z_var, dmean[3], dsigma[3];
     ContactSet cs;
@@ -449,7 +449,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_c
         if (P.map.tile_w > 0) {
             // stage the map tile around the particle cloud into shared memory
             mt.w = P.map.tile_w; mt.h = P.map.tile_h;
-            const int x0 = max(0, min(P.map.tile_x0, P.map.W - mt.w)), y0 = max(0, min(P.map.tile_y0, P.map.H - mt.h));
+            // TMA needs a 16-byte aligned box start: an even x0 for 8-byte cells (W and tile_w are even when TMA is on)
+            const int x0 = max(0, min(P.map.tile_x0, P.map.W - mt.w)) & ~1, y0 = max(0, min(P.map.tile_y0, P.map.H - mt.h));
             mt.x0 = x0; mt.y0 = y0;
             if (tma) {
                 // one TMA bulk tensor copy: box (tile_w x tile_h cells) at (x0, y0) of the 2-D grid -> shared memory
@@ -457,9 +458,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_c
                 __syncthreads();
                 if (tid == 0) {
                     mbar_expect_tx(mbar, (uint32_t)(mt.w * mt.h) * (uint32_t)sizeof(float2));
-                    tma_load_2d((uint32_t)__cvta_generic_to_shared(tile), &P.tmap, mbar, x0, y0);
+                    tma_load_2d((uint32_t)__cvta_generic_to_shared(tile), P.tmap, mbar, x0, y0);
                 }
-            } else {
+            }
+            if (!tma) {
                 const int cells = mt.w * mt.h;
                 for (int i = tid; i < cells; i += WT_THREADS) {
                     const int r = i / mt.w, cc = i - r * mt.w;
