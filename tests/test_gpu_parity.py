@@ -328,3 +328,27 @@ def test_patches_change_the_result_only_through_written_cells(gpu):
     assert not np.array_equal(a.getParticles()["weight"], b.getParticles()["weight"])
     with pytest.raises(RuntimeError):
         b.getPatches(P)
+
+
+# ---------------------------------------------------------------------------------- larger sets (more tiles than threads)
+def test_four_million_particles_resample_stage(gpu):
+    """4,194,304 particles = 4096 tiles: the single-CTA kernels walk several tiles per thread and the tree reductions
+    leave shared memory; the running sum must still be the sequential one and the ancestors its lower bounds."""
+    n = 1 << 22
+    rng = np.random.default_rng(22)
+    w = rng.random(n) ** 3
+    w /= w.sum()
+    g = gpu()
+    z = np.zeros(n)
+    g.setParticles(x=np.arange(n, dtype=np.float64), y=z, theta=z, zpos=z, zsigma=z + 1, weight=w)
+    g.resample()
+    cdf = np.cumsum(w)
+    assert np.array_equal(g.getCdf(), cdf)
+    anc = g.getAncestors().astype(np.int64)
+    assert np.all(np.diff(anc) >= 0)
+    # lower-bound property against the exact running sum: cdf[a-1] < (k+u)/n <= cdf[a] for some u in [0,1)
+    k = np.arange(n)
+    lo = np.where(anc > 0, cdf[np.maximum(anc - 1, 0)], 0.0)
+    assert np.all(lo < (k + 1.0) / n) and np.all(cdf[anc] >= k / n)
+    assert g.debugCounters()["fallbacks"] == 0
+    assert g.normalizeWeights() == pytest.approx(1.0 / np.sum((w[anc] / w[anc].sum()) ** 2), rel=1e-12)
