@@ -44,6 +44,8 @@ struct eslam_gpu_ctx {
     double* tile_sin_host;                        // pinned, t_global
     // resampling window fetched from the owning ranks (world > 1)
     uint64_t win_cap; double* win_cdf; double* win_f[7]; uint8_t* win_b[2];
+    // peer-mapped buffers of the other ranks (CUDA IPC over NVLink): resampling reads ancestors in place
+    PeerTable peers; bool has_peers; std::vector<void*> ipc_opened; int* d_barrier_send; int* d_barrier_recv;
     // map
     float2* cells; MapParams map; bool has_map;
     CUtensorMap tmap; CUtensorMap* d_tmap; bool has_tmap;   // TMA descriptor of the grid (host copy, device copy)
@@ -109,6 +111,43 @@ static void free_window(eslam_gpu_ctx* ctx) {
     ctx->win_cap = 0;
 }
 
+// Exchange CUDA IPC handles of the running-sum and state buffers and map every peer's buffers into this process.
+static int allgather(eslam_gpu_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank);
+static int setup_peers(eslam_gpu_ctx* ctx) {
+    const int G = ctx->shard.world, me = ctx->shard.rank;
+    if (G > ESLAM_MAX_RANKS) { ctx->error = "more ranks than ESLAM_MAX_RANKS"; return ESLAM_ERR_INVALID; }
+    if (!ctx->has_comm) { ctx->error = "sharded context without a communicator (call eslam_gpu_comm_init before init)"; return ESLAM_ERR_COMM; }
+    const int NH = 19;                                                  // cdf + 2 x 7 doubles + 2 x 2 bytes
+    void* mine[NH]; int k = 0;
+    mine[k++] = ctx->cdf;
+    for (int b = 0; b < 2; ++b) for (int f = 0; f < 7; ++f) mine[k++] = ctx->st.f[b][f];
+    for (int b = 0; b < 2; ++b) for (int f = 0; f < 2; ++f) mine[k++] = ctx->st.b[b][f];
+    std::vector<cudaIpcMemHandle_t> h_mine(NH), h_all((size_t)NH * G);
+    for (int i = 0; i < NH; ++i) CK(cudaIpcGetMemHandle(&h_mine[i], mine[i]));
+    cudaIpcMemHandle_t *d_send = nullptr, *d_recv = nullptr;
+    CK(dalloc(&d_send, (size_t)NH)); CK(dalloc(&d_recv, (size_t)NH * G));
+    CK(cudaMemcpyAsync(d_send, h_mine.data(), NH * sizeof(cudaIpcMemHandle_t), cudaMemcpyHostToDevice, ctx->stream));
+    int st = allgather(ctx, d_send, d_recv, NH * sizeof(cudaIpcMemHandle_t));
+    if (st != ESLAM_OK) return st;
+    CK(cudaMemcpyAsync(h_all.data(), d_recv, (size_t)NH * G * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_send); cudaFree(d_recv);
+    for (int q = 0; q < G; ++q) {
+        void* p[NH];
+        for (int i = 0; i < NH; ++i) {
+            if (q == me) p[i] = mine[i];
+            else { CK(cudaIpcOpenMemHandle(&p[i], h_all[(size_t)q * NH + i], cudaIpcMemLazyEnablePeerAccess)); ctx->ipc_opened.push_back(p[i]); }
+        }
+        int j = 0;
+        ctx->peers.cdf[q] = (const double*)p[j++];
+        for (int b = 0; b < 2; ++b) for (int f = 0; f < 7; ++f) ctx->peers.f[q][b][f] = (const double*)p[j++];
+        for (int b = 0; b < 2; ++b) for (int f = 0; f < 2; ++f) ctx->peers.b[q][b][f] = (const uint8_t*)p[j++];
+    }
+    if (!ctx->d_barrier_send) { CK(dalloc(&ctx->d_barrier_send, 1)); CK(dalloc(&ctx->d_barrier_recv, (size_t)ESLAM_MAX_RANKS)); }
+    ctx->has_peers = true;
+    return ESLAM_OK;
+}
+
 static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
     if (n == 0) return ESLAM_ERR_EMPTY;
     if (n > 0xFFFFFFFFull) { ctx->error = "more than 2^32 particles per shard"; return ESLAM_ERR_INVALID; }
@@ -118,6 +157,8 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
         ctx->error = "sharded contexts need equal shards that are multiples of 1024 particles"; return ESLAM_ERR_INVALID;
     }
     if (n > ctx->cap) {
+        for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);   // peer mappings of the old buffers are stale
+        ctx->ipc_opened.clear(); ctx->has_peers = false;
         free_particles(ctx);
         for (int b = 0; b < 2; ++b) {
             for (int f = 0; f < 7; ++f) CK(dalloc(&ctx->st.f[b][f], n));
@@ -148,6 +189,7 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
         ctx->cap = n; ctx->t_cap = (unsigned)t;
     }
     ctx->n = n; ctx->t_local = (unsigned)((n + TILE - 1) / TILE); ctx->t_global = ctx->t_local * G;
+    if (G > 1 && !ctx->has_peers && !getenv("ESLAM_GPU_NO_P2P")) return setup_peers(ctx);
     return ESLAM_OK;
 }
 
@@ -256,7 +298,8 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     ctx->l_cent = ctx->g_cent = ctx->l_best_w = ctx->g_best_w = nullptr; ctx->l_best_idx = ctx->g_best_idx = nullptr;
     ctx->tile_prefix = ctx->scratch_a = ctx->scratch_b = ctx->tile_sin = ctx->sb = nullptr;
     ctx->tile_bofs = nullptr; ctx->tile_pre = nullptr; ctx->tile_sin_host = nullptr;
-    ctx->win_cap = 0; ctx->win_cdf = nullptr;
+    ctx->win_cap = 0; ctx->win_cdf = nullptr; ctx->has_peers = false; ctx->d_barrier_send = ctx->d_barrier_recv = nullptr;
+    memset(&ctx->peers, 0, sizeof(ctx->peers));
     for (int f = 0; f < 7; ++f) ctx->win_f[f] = nullptr;
     for (int f = 0; f < 2; ++f) ctx->win_b[f] = nullptr;
     ctx->cells = nullptr; ctx->has_map = false; ctx->has_tmap = false; ctx->d_tmap = nullptr; ctx->project_step = 0;
@@ -283,7 +326,9 @@ void eslam_gpu_destroy(eslam_gpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->has_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
     free_particles(ctx); free_window(ctx);
+    cudaFree(ctx->d_barrier_send); cudaFree(ctx->d_barrier_recv);
     cudaFree(ctx->sc); cudaFreeHost(ctx->sc_host); cudaFreeHost(ctx->tile_hint); cudaFree(ctx->d_tmap); cudaFree(ctx->htab); cudaFree(ctx->cells);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
@@ -611,6 +656,20 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     k_cdf<<<T, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->tile_prefix, ctx->tile_bofs, ctx->tile_sin, ctx->sb, ctx->cdf, eps,
                                        tile_ofs(ctx));
     LAUNCHED();
+    if (sharded(ctx) && ctx->has_peers) {
+        // all ranks must have finished their k_cdf before anyone reads running sums / state through peer pointers:
+        // a 4-byte all-gather on the streams is that barrier (the next step's all-gathers protect the buffers that are
+        // still being read from being overwritten)
+        AG(ctx->d_barrier_send, ctx->d_barrier_recv, sizeof(int));
+        const ModelParams mp = model_params(ctx);
+        k_resample_p2p<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->tile_sin, TG, T, n, ng, base_index(ctx),
+                                                                            mp.k0, mp.k1, ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC,
+                                                                            ctx->ancestors, ctx->peers);
+        LAUNCHED();
+        k_after_resample<<<1, 1, 0, ctx->stream>>>(ctx->sc);
+        LAUNCHED();
+        return ESLAM_OK;
+    }
     if (sharded(ctx)) return resample_exchange(ctx);
     k_cdf_sequential<<<1, 1, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->cdf, ctx->tile_sin);
     LAUNCHED();
@@ -660,6 +719,10 @@ static int fetch_result(eslam_gpu_ctx* ctx, eslam_gpu_update_result* r) {
     r->ess = s.ess; r->max_weight = s.max_weight; r->floating_weight = s.floating_weight; r->weights_sum = s.sum_w;
     r->data_particles = s.data_particles; r->total_points = s.total_points; r->resampled = s.do_resample;
     r->status = ESLAM_OK;
+    if (sharded(ctx) && (s.error_flags & ERR_CDF_FALLBACK_BIT)) {
+        r->status = ESLAM_ERR_COMM;
+        ctx->error = "exact running sum needs the sequential fallback, which is not available across shards";
+    }
     if (s.error_flags & ERR_ZERO_VARIANCE_BIT) {
         r->status = ESLAM_ERR_ZERO_VARIANCE;
         ctx->error = "using a zero measurement variance leads to singularities";

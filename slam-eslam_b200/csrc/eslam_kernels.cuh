@@ -1143,6 +1143,54 @@ __global__ void __launch_bounds__(256) k_resample(StateBufs st, const DevScalars
     }
 }
 
+// Sharded resampling over NVLink peer memory (exact-global mode).  Every rank holds, after the all-gathered k_chain, the
+// exact running sum before every 1024-tile of EVERY rank (tile_start, global).  Stratum k of this rank searches that
+// table, then searches inside the one tile that holds its ancestor -- reading the owner's running sum through its
+// peer-mapped pointer -- and copies the ancestor's state straight from the owner's current buffers.  No host step, no
+// staging: remote ancestors cost NVLink reads, local ones (the vast majority when weights are balanced) HBM reads.
+#define ESLAM_MAX_RANKS 8
+struct PeerTable {
+    const double* cdf[ESLAM_MAX_RANKS];
+    const double* f[ESLAM_MAX_RANKS][2][7];
+    const uint8_t* b[ESLAM_MAX_RANKS][2][2];
+};
+
+__global__ void __launch_bounds__(256) k_resample_p2p(StateBufs st, DevScalars* sc, const double* __restrict__ tile_start,
+                                                      unsigned n_tiles_global, unsigned tiles_per_rank, unsigned long long n,
+                                                      unsigned long long n_global, unsigned long long base, uint32_t k0,
+                                                      uint32_t k1, int systematic, uint32_t* ancestors,
+                                                      const __grid_constant__ PeerTable peers) {
+    if (!sc->do_resample) return;
+    if (sc->error_flags & ERR_CDF_FALLBACK_BIT) return;     // reported through the update status; state is left as is
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const unsigned long long gk = systematic ? 0ull : base + k;
+    const em::Philox4 r = em::philox4x32_10((uint32_t)gk, sc->resample_step, 0, stream_word(em::STREAM_RESAMPLE, gk), k0, k1);
+    const double u = em::u01(r.v[0], r.v[1]);
+    const double sum_r = ((double)(base + k) + u) / (double)n_global;                // :98
+    unsigned tlo = 0, thi = n_tiles_global;                                          // first tile with !(start < sum_r)
+    while (tlo < thi) { const unsigned mid = (tlo + thi) >> 1; if (__ldg(&tile_start[mid]) < sum_r) tlo = mid + 1; else thi = mid; }
+    const unsigned t = tlo == 0 ? 0 : tlo - 1;
+    const unsigned q = t / tiles_per_rank;                                           // owner of the ancestor
+    const double* cdf_q = peers.cdf[q];
+    unsigned long long lo = (unsigned long long)(t - q * tiles_per_rank) * TILE, hi = min(lo + TILE, n);   // owner-local
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if (cdf_q[mid] < sum_r) lo = mid + 1; else hi = mid;
+    }
+    unsigned owner = q;
+    if (lo >= n) {                                  // past the end of the owner's tile range
+        if (q + 1 < (unsigned)(n_global / n)) { owner = q + 1; lo = 0; }   // cannot happen (tile_start[t+1] >= sum_r); kept safe
+        else lo = n - 1;                            // the reference walks off the end here; we stop at the last particle
+    }
+    ancestors[k] = (uint32_t)((unsigned long long)owner * n + lo);
+    const int cur = sc->cur, nxt = cur ^ 1;
+#pragma unroll
+    for (int f = 0; f < 7; ++f) st.f[nxt][f][k] = peers.f[owner][cur][f][lo];        // :104 copy keeps the weight (Q3)
+#pragma unroll
+    for (int f = 0; f < 2; ++f) st.b[nxt][f][k] = peers.b[owner][cur][f][lo];
+}
+
 // cloneMaps (src/PoseEstimator.cpp:31-45): every copy of a particle owns a copy of its map patch. One warp per particle.
 __global__ void k_gather_patches(const DevScalars* sc, unsigned long long n, const uint32_t* __restrict__ anc, int P,
                                  float2* p0, float2* p1, int* o0, int* o1) {
@@ -1164,6 +1212,7 @@ __global__ void k_fill_i32(int* p, size_t count, int v) {
 
 __global__ void k_after_resample(DevScalars* sc) {
     if (!sc->do_resample) return;
+    if (sc->error_flags & ERR_CDF_FALLBACK_BIT) return;   // sharded run that could not resample: state left as is
     sc->cur ^= 1;                                                                    // xi_k.swap(xi_kp) :107
     sc->resample_step += 1;
 }
