@@ -158,7 +158,8 @@ def main():
     torch.cuda.set_device(local_rank)
     comm = dist.init(world, rank, local_rank) if world > 1 else None
     n_global = n_local * world
-    cfg = abi.default_config(min_effective=n_global + 1)          # resample every step (ESS <= N always)
+    patch = 16 if args.workload == "C4" else 0                       # C4: EmbodiedSlamFilter per-particle map patches
+    cfg = abi.default_config(min_effective=n_global + 1, patch_size=patch)   # resample every step (ESS <= N always)
     g = GpuPoseEstimator(cfg, device=local_rank, shard=comm.shard(n_local) if comm else None)
     if comm:
         comm.connect(g)
@@ -174,6 +175,7 @@ def main():
     torch.cuda.synchronize()
     if comm: comm.barrier()
     launches = g.launchCount() - launches0
+    paths = g.pathCounters()
     if comm:
         ms = comm.max_float(ms)
         top_ms = comm.max_float(top_ms)
@@ -205,13 +207,14 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "particles_per_gpu": n_local, "particles": n_global, "contact_points": c,
-                   "grid": "%dx%d float2, replicated" % (w["grid"], w["grid"]), "resample": "stratified, every step",
+                   "grid": "%dx%d float2, replicated" % (w["grid"], w["grid"]), "resample": "stratified, every step", "patch_size": patch,
                    "sharding": "contiguous particle ranges, exact-global resampling (ancestors identical to 1 GPU)" if world > 1 else "none",
                    "timing": "inputs larger than L2: particle state 2 x %.0f MB + scan buffers stream from HBM every "
                              "step; the %.0f MB map is L2-resident by design" % (n_local * 58 / 1e6, w["grid"] ** 2 * 8 / 1e6),
                    "step_algorithmic_bytes": step_bytes,
                    "step_hbm_frac": step_bytes / (ms * 1e-3 / args.steps) / 1e9 / peak,
-                   "resampled_last_step": res.resampled, "ess_last_step": res.ess},
+                   "resampled_last_step": res.resampled, "ess_last_step": res.ess,
+                   "deferred_last_step": paths["deferred"]},
         "roofline": {"bound": "hbm", "kernel": "k_project_weight<true,true>", "achieved": achieved, "peak": peak,
                      "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None,

@@ -177,6 +177,9 @@ int eslam_gpu_synchronize(eslam_gpu_ctx* ctx);
 /* diagnostics of the exact running-sum machinery: out = {sequential-fallback runs, boundary elements of the last
  * resample, pending error flags, resamples done} */
 int eslam_gpu_debug_counters(eslam_gpu_ctx* ctx, uint64_t out[4]);
+/* which weight kernel did the work in the last update: out = {local particles, particles the lean kernel
+ * (footprint inside the shared-memory map tile, every decision safely away from its threshold) handed to the generic one} */
+int eslam_gpu_path_counters(eslam_gpu_ctx* ctx, uint64_t out[2]);
 /* number of kernels this library has launched on ctx since creation (bench "gpu_launches") */
 uint64_t eslam_gpu_launch_count(const eslam_gpu_ctx* ctx);
 

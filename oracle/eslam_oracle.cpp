@@ -298,7 +298,10 @@ struct eslam_oracle_ctx {
                 if (group_valid && contact_ratio > 1e-9) {      // :199
                     p.zdiff /= contact_ratio;                   // :201-203
                     p.zvar /= contact_ratio;
-                    m_poseVar += pose_var_avg / contact_ratio;
+                    // SHARED: sum(stdev^2 r)/sum(r) == sum(zvar r)/sum(r) - measVar (measVar is constant over the
+                    // particle), so the fourth running sum is not carried
+                    if (A::shared) m_poseVar += p.zvar - measVar;
+                    else m_poseVar += pose_var_avg / contact_ratio;
                     contact_points.push_back(p);                // :205
                     if (A::shared) {                            // running sums for evaluateWeight
                         const double e = p.zdiff / p.zvar;

@@ -138,6 +138,7 @@ GPU_ONLY = {
     "synchronize": (C.c_int, [C.c_void_p]),
     "weights_sum": (C.c_int, [C.c_void_p, _dp]),
     "debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "path_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "launch_count": (C.c_uint64, [C.c_void_p]),
 }
 

@@ -34,6 +34,10 @@ struct eslam_gpu_ctx {
     DevScalars* sc; DevScalars* sc_host;          // sc_host: pinned staging
     double* tile_hint;                            // pinned {cx, cy}: cloud centre, refreshed asynchronously after every update
     uint32_t* ancestors; double* cdf;
+    uint32_t* defer_list;                         // particles the lean weight kernel hands to the generic one (n entries)
+    double* hint; unsigned hint_n;                // per-CTA sums of x, y (tile placement hint), entries written by the last update
+    int fast_threads;                             // CTA size of the lean kernel (ESLAM_GPU_FAST_THREADS = 512 | 1024)
+    bool grid_sane;                               // every stdev of the grid is NaN or |stdev| < 2^49 (lean path precondition)
     float2* patch[2]; int* porigin[2];            // per-particle map patches (cfg.patch_size > 0), double buffered
     // per-tile arrays: l_* cover the local tiles, g_* all tiles of all ranks (aliases of l_* when world == 1)
     unsigned t_local, t_global, t_cap;
@@ -89,7 +93,7 @@ static void free_particles(eslam_gpu_ctx* ctx) {
         for (int f = 0; f < 7; ++f) dfree(ctx->st.f[b][f]);
         for (int f = 0; f < 2; ++f) dfree(ctx->st.b[b][f]);
     }
-    dfree(ctx->ancestors); dfree(ctx->cdf);
+    dfree(ctx->ancestors); dfree(ctx->cdf); dfree(ctx->defer_list);
     for (int b = 0; b < 2; ++b) { dfree(ctx->patch[b]); dfree(ctx->porigin[b]); }
     const bool sh = ctx->g_part_a != ctx->l_part_a;
     if (sh) { dfree(ctx->g_part_a); dfree(ctx->g_tile_sum); dfree(ctx->g_tile_sq); dfree(ctx->g_desc); dfree(ctx->g_pool);
@@ -164,7 +168,7 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
             for (int f = 0; f < 7; ++f) CK(dalloc(&ctx->st.f[b][f], n));
             for (int f = 0; f < 2; ++f) CK(dalloc(&ctx->st.b[b][f], n));
         }
-        CK(dalloc(&ctx->ancestors, n)); CK(dalloc(&ctx->cdf, n));
+        CK(dalloc(&ctx->ancestors, n)); CK(dalloc(&ctx->cdf, n)); CK(dalloc(&ctx->defer_list, n));
         if (ctx->cfg.patch_size > 0) {
             const size_t pp = (size_t)ctx->cfg.patch_size * ctx->cfg.patch_size;
             for (int b = 0; b < 2; ++b) { CK(dalloc(&ctx->patch[b], n * pp)); CK(dalloc(&ctx->porigin[b], 2 * n)); }
@@ -244,7 +248,7 @@ static int build_contact_set(eslam_gpu_ctx* ctx, const eslam_gpu_contact* pts, i
 }
 
 static size_t weight_smem_bytes(const eslam_gpu_ctx* ctx) {
-    return HTAB_BYTES + WT_SCRATCH_BYTES + (size_t)ctx->map.tile_w * ctx->map.tile_h * sizeof(float2);
+    return WT_HEAD_BYTES + (size_t)ctx->map.tile_w * ctx->map.tile_h * sizeof(float2);
 }
 
 // empty maps for every particle: NaN cells (0xFF bytes), un-anchored origins
@@ -291,7 +295,9 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     if (shard) ctx->shard = *shard;
     ctx->comm = nullptr; ctx->has_comm = false;
     ctx->device = device; ctx->launches = 0; ctx->n = ctx->cap = 0; ctx->t_local = ctx->t_global = ctx->t_cap = 0;
-    ctx->ancestors = nullptr; ctx->cdf = nullptr;
+    ctx->ancestors = nullptr; ctx->cdf = nullptr; ctx->defer_list = nullptr; ctx->hint = nullptr; ctx->hint_n = 0;
+    ctx->grid_sane = false;
+    ctx->fast_threads = getenv("ESLAM_GPU_FAST_THREADS") ? atoi(getenv("ESLAM_GPU_FAST_THREADS")) : 1024;
     for (int b = 0; b < 2; ++b) { ctx->patch[b] = nullptr; ctx->porigin[b] = nullptr; }
     ctx->l_part_a = ctx->g_part_a = nullptr; ctx->l_tile_sum = ctx->g_tile_sum = ctx->l_tile_sq = ctx->g_tile_sq = nullptr;
     ctx->l_desc = ctx->g_desc = nullptr; ctx->l_pool = ctx->g_pool = nullptr;
@@ -314,6 +320,8 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     CK(cudaMallocHost((void**)&ctx->sc_host, sizeof(DevScalars)));
     CK(cudaMallocHost((void**)&ctx->tile_hint, 2 * sizeof(double)));
     ctx->tile_hint[0] = ctx->tile_hint[1] = 0.0;
+    CK(dalloc(&ctx->hint, (size_t)2 * ctx->sm_count));
+    CK(cudaMemsetAsync(ctx->hint, 0, 2 * ctx->sm_count * sizeof(double), ctx->stream));
     CK(dalloc(&ctx->htab, (size_t)ESLAM_H_NINT * 3));
     CK(cudaMemcpyAsync(ctx->htab, H_TABLE_HOST, sizeof(H_TABLE_HOST), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainSmem)));
@@ -329,7 +337,7 @@ void eslam_gpu_destroy(eslam_gpu_ctx* ctx) {
     for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
     free_particles(ctx); free_window(ctx);
     cudaFree(ctx->d_barrier_send); cudaFree(ctx->d_barrier_recv);
-    cudaFree(ctx->sc); cudaFreeHost(ctx->sc_host); cudaFreeHost(ctx->tile_hint); cudaFree(ctx->d_tmap); cudaFree(ctx->htab); cudaFree(ctx->cells);
+    cudaFree(ctx->sc); cudaFreeHost(ctx->sc_host); cudaFreeHost(ctx->tile_hint); cudaFree(ctx->d_tmap); cudaFree(ctx->htab); cudaFree(ctx->cells); cudaFree(ctx->hint);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -374,6 +382,12 @@ int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int he
     const size_t count = (size_t)width * height;
     CK(dalloc(&ctx->cells, count));
     CK(cudaMemcpyAsync(ctx->cells, cells, count * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    // lean-path precondition: stdev^2 + measVar stays inside rsqrt_core's validated range (see k_weight_fast)
+    ctx->grid_sane = true;
+    for (size_t i = 0; i < count; ++i) {
+        const float sd = cells[2 * i + 1];
+        if (sd == sd && !(fabsf(sd) < 5.6e14f)) { ctx->grid_sane = false; break; }   // 2^49 = 5.63e14
+    }
     MapParams& m = ctx->map;
     m.cells = ctx->cells; m.W = width; m.H = height; m.sx = sx; m.sy = sy; m.ox = ox; m.oy = oy;
     m.inv_sx = 1.0 / sx; m.inv_sy = 1.0 / sy;
@@ -381,7 +395,7 @@ int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int he
     m.identity = g2l == nullptr;
     for (int i = 0; i < 8; ++i) m.g2l[i] = g2l ? g2l[i] : (i == 0 || i == 5 ? 1.0 : 0.0);
     // shared-memory map tile: as many cells as fit next to the h-table
-    const size_t avail = (size_t)ctx->max_smem_optin - (HTAB_BYTES + WT_SCRATCH_BYTES);
+    const size_t avail = (size_t)ctx->max_smem_optin - WT_HEAD_BYTES;
     int side = (int)floor(sqrt((double)(avail / sizeof(float2))));
     if (getenv("ESLAM_GPU_TILE")) side = atoi(getenv("ESLAM_GPU_TILE"));
     m.tile_w = width < side ? width : side;
@@ -421,10 +435,15 @@ int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int he
         }
     }
     const int bytes = (int)weight_smem_bytes(ctx);
-    CK(cudaFuncSetAttribute(k_project_weight<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_project_weight<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_project_weight<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_project_weight<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_project_weight<true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_project_weight<false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_project_weight<true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_project_weight<false, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_project_weight<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_weight_fast<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_weight_fast<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_weight_fast<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_weight_fast<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->has_map = true;
     return ESLAM_OK;
@@ -497,26 +516,73 @@ int eslam_gpu_get_particles(eslam_gpu_ctx* ctx, double* x, double* y, double* th
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------- launch sequences
+// where to put the shared-memory map tile: around the cloud centre the device reported last (a hint: it may be a few
+// steps old when steps are enqueued without synchronisation; results do not depend on it).  Inside the grid, x0 even
+// (TMA needs a 16-byte aligned box start for 8-byte cells).
+static void place_tile(const eslam_gpu_ctx* ctx, MapParams* m) {
+    volatile double* hint = ctx->tile_hint;
+    double cx = (hint[0] - ctx->map.ox) * ctx->map.inv_sx, cy = (hint[1] - ctx->map.oy) * ctx->map.inv_sy;
+    if (!(cx > -1e9 && cx < 1e9)) cx = 0;
+    if (!(cy > -1e9 && cy < 1e9)) cy = 0;
+    const int x0 = (int)cx - m->tile_w / 2, y0 = (int)cy - m->tile_h / 2;
+    m->tile_x0 = std::max(0, std::min(x0, m->W - m->tile_w)) & ~1;
+    m->tile_y0 = std::max(0, std::min(y0, m->H - m->tile_h));
+}
+
 static void fill_weight_params(eslam_gpu_ctx* ctx, WeightParams* P, const eslam_gpu_step* step, const ContactSet* cs) {
     memset(P, 0, sizeof(*P));
-    P->st = ctx->st; P->sc = ctx->sc; P->part = ctx->l_part_a; P->map = ctx->map; P->mp = model_params(ctx);
+    P->st = ctx->st; P->sc = ctx->sc; P->map = ctx->map; P->mp = model_params(ctx);
     P->htab = ctx->htab; P->n = ctx->n; P->base = base_index(ctx); P->project_step = ctx->project_step;
     P->patch_size = ctx->cfg.patch_size > 0 ? ctx->cfg.patch_size : 0;
     P->use_tma = ctx->has_tmap && !getenv("ESLAM_GPU_NO_TMA");
     P->tmap = ctx->d_tmap;
+    P->defer_list = ctx->defer_list; P->hint = ctx->hint;
     for (int b = 0; b < 2; ++b) { P->patch[b] = ctx->patch[b]; P->porigin[b] = ctx->porigin[b]; }
     if (step) {
         P->yaw = step->yaw; P->z_delta = step->z_delta; P->z_var = step->z_var;
         for (int i = 0; i < 3; ++i) { P->dmean[i] = step->delta_mean[i]; P->dsigma[i] = step->delta_sigma[i]; }
     }
     if (cs) P->cs = *cs;
-    // where to put the shared-memory map tile: around the cloud centre the device reported last (a hint: it may be a
-    // few steps old when steps are enqueued without synchronisation; results do not depend on it)
-    volatile double* hint = ctx->tile_hint;
-    double cx = (hint[0] - ctx->map.ox) * ctx->map.inv_sx, cy = (hint[1] - ctx->map.oy) * ctx->map.inv_sy;
-    if (!(cx > -1e9 && cx < 1e9)) cx = 0;
-    if (!(cy > -1e9 && cy < 1e9)) cy = 0;
-    P->map.tile_x0 = (int)cx - ctx->map.tile_w / 2; P->map.tile_y0 = (int)cy - ctx->map.tile_h / 2;
+    place_tile(ctx, &P->map);
+}
+
+static inline uint32_t hi_word(double v) { uint64_t u; memcpy(&u, &v, 8); return (uint32_t)(u >> 32); }
+
+// The lean kernel's inputs (k_weight_fast).  Returns false when the lean path does not apply to this context / update:
+// per-particle patches, a non-identity C_global2local, no shared-memory tile, a grid with out-of-range deviations.
+static bool fill_fast_params(eslam_gpu_ctx* ctx, FastParams* F, const WeightParams& P, const ContactSet& cs) {
+    if (getenv("ESLAM_GPU_NO_FAST")) return false;
+    if (ctx->cfg.patch_size > 0 || !ctx->map.identity || !ctx->grid_sane || P.map.tile_w <= 0 || P.map.tile_h <= 0) return false;
+    memset(F, 0, sizeof(*F));
+    WeightCommon& c = F->c;
+    c.st = P.st; c.sc = P.sc; c.map = P.map; c.mp = P.mp; c.htab = P.htab; c.n = P.n; c.base = P.base;
+    c.project_step = P.project_step; c.use_tma = P.use_tma; c.tmap = P.tmap; c.defer_list = P.defer_list; c.hint = P.hint;
+    c.yaw = P.yaw; c.z_delta = P.z_delta; c.z_var = P.z_var;
+    for (int i = 0; i < 3; ++i) { c.dmean[i] = P.dmean[i]; c.dsigma[i] = P.dsigma[i]; }
+    FastContacts& fc = F->fc;
+    double r2 = 0; int last_end = 0;
+    for (int i = 0; i < cs.n; ++i) {
+        if (cs.flags[i] & 1u) {
+            fc.px[fc.n_eval] = cs.px[i]; fc.py[fc.n_eval] = cs.py[i]; fc.pzr[fc.n_eval] = cs.pzr[i]; fc.n_eval++;
+            const double q = cs.px[i] * cs.px[i] + cs.py[i] * cs.py[i];
+            if (!(q < 1e12)) return false;                                // NaN / absurd contact positions: generic path
+            if (q > r2) r2 = q;
+        }
+        if ((cs.flags[i] & 2u) && fc.n_eval > last_end) { fc.gend[fc.n_groups++] = (uint8_t)fc.n_eval; last_end = fc.n_eval; }
+    }
+    const double inv_max = std::max(P.map.inv_sx, P.map.inv_sy);
+    const double mc = ceil(sqrt(r2) * inv_max) + 2.0;
+    if (!(mc * 2 + 1 < P.map.tile_w && mc * 2 + 1 < P.map.tile_h)) return false;
+    fc.margin = (int)mc;
+    // 3-sigma gate d^2 < 9 zvar  <=>  |t| < 3/corr with t = d / (sigma corr); decided on the high word of |t|
+    const double T = 3.0 * P.mp.inv_corr;
+    if (!(T > 0.0) || !(T < 1e300)) return false;
+    const uint32_t hiT = hi_word(T), hi10 = hi_word(ESLAM_H_TMAX);
+    fc.gate_lo = std::min(hiT, hi10) - 1u;                                // also keeps t inside the table
+    fc.gate_span = (hiT + 1u) - fc.gate_lo;
+    fc.c0x = (402653184.0 - (double)P.map.tile_x0) - P.map.ox * P.map.inv_sx;   // 1.5 * 2^28
+    fc.c0y = (402653184.0 - (double)P.map.tile_y0) - P.map.oy * P.map.inv_sy;
+    return true;
 }
 
 static unsigned weight_grid(const eslam_gpu_ctx* ctx) {
@@ -694,19 +760,38 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
     WeightParams P;
     fill_weight_params(ctx, &P, step_or_null, cs);
     const size_t smem = weight_smem_bytes(ctx);
+    const unsigned grid = weight_grid(ctx);
     if (ev0) CK(cudaEventRecord(ev0, ctx->stream));
     const bool patches = ctx->cfg.patch_size > 0;
-    if (step_or_null) {
-        if (patches) k_project_weight<true, true, true><<<weight_grid(ctx), WT_THREADS, smem, ctx->stream>>>(P);
-        else k_project_weight<true, true, false><<<weight_grid(ctx), WT_THREADS, smem, ctx->stream>>>(P);
-        ctx->project_step++;
-    } else if (patches) k_project_weight<false, true, true><<<weight_grid(ctx), WT_THREADS, smem, ctx->stream>>>(P);
-    else k_project_weight<false, true, false><<<weight_grid(ctx), WT_THREADS, smem, ctx->stream>>>(P);
-    LAUNCHED();
+    static FastParams F;                                                  // large (lists of 128 contacts): not on the stack
+    if (fill_fast_params(ctx, &F, P, *cs)) {
+        // lean kernel for the particles whose footprint lies inside the tile, generic kernel for the rest
+        const bool wide = ctx->fast_threads == 512;                      // 512 threads x 128 registers or 1024 x 64
+        if (step_or_null) {
+            if (wide) k_weight_fast<true, 512><<<grid, 512, smem, ctx->stream>>>(F);
+            else k_weight_fast<true, 1024><<<grid, 1024, smem, ctx->stream>>>(F);
+            ctx->project_step++;
+        } else if (wide) k_weight_fast<false, 512><<<grid, 512, smem, ctx->stream>>>(F);
+        else k_weight_fast<false, 1024><<<grid, 1024, smem, ctx->stream>>>(F);
+        LAUNCHED();
+        k_project_weight<false, true, false, true><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
+        LAUNCHED();
+    } else {
+        if (step_or_null) {
+            if (patches) k_project_weight<true, true, true, false><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
+            else k_project_weight<true, true, false, false><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
+            ctx->project_step++;
+        } else if (patches) k_project_weight<false, true, true, false><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
+        else k_project_weight<false, true, false, false><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
+        LAUNCHED();
+    }
     if (ev1) CK(cudaEventRecord(ev1, ctx->stream));
+    ctx->hint_n = grid;
+    k_tile_part<<<ctx->t_local, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->n, ctx->l_part_a);
+    LAUNCHED();
     AG(ctx->l_part_a, ctx->g_part_a, ctx->t_local * sizeof(TilePartA));
-    k_reduce_a<<<1, 1024, 0, ctx->stream>>>(ctx->g_part_a, ctx->t_global, global_count(ctx), ctx->sc, ctx->scratch_a, ctx->scratch_b,
-                                            ctx->cfg.discount_factor);
+    k_reduce_a<<<1, 1024, 0, ctx->stream>>>(ctx->g_part_a, ctx->t_global, ctx->n, ctx->sc, ctx->scratch_a, ctx->scratch_b,
+                                            ctx->cfg.discount_factor, ctx->hint, ctx->hint_n);
     LAUNCHED();
     CK(cudaMemcpyAsync(ctx->tile_hint, &ctx->sc->tile_cx, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return launch_tail(ctx, true, 1, 1, 0);
@@ -760,7 +845,7 @@ int eslam_gpu_project(eslam_gpu_ctx* ctx, const eslam_gpu_step* step) {
     if (!step) return ESLAM_ERR_INVALID;
     WeightParams P;
     fill_weight_params(ctx, &P, step, nullptr);
-    k_project_weight<true, false, false><<<weight_grid(ctx), WT_THREADS, 0, ctx->stream>>>(P);
+    k_project_weight<true, false, false, false><<<weight_grid(ctx), WT_THREADS, 0, ctx->stream>>>(P);
     ctx->project_step++;
     LAUNCHED();
     return ESLAM_OK;
@@ -944,6 +1029,15 @@ int eslam_gpu_debug_counters(eslam_gpu_ctx* ctx, uint64_t out[4]) {
     if (st != ESLAM_OK) return st;
     out[0] = ctx->sc_host->fallbacks; out[1] = (uint64_t)ctx->sc_host->n_boundaries;
     out[2] = (uint64_t)ctx->sc_host->error_flags; out[3] = ctx->sc_host->resample_step;
+    return ESLAM_OK;
+}
+
+int eslam_gpu_path_counters(eslam_gpu_ctx* ctx, uint64_t out[2]) {
+    if (!ctx || !out) return ESLAM_ERR_INVALID;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return ESLAM_ERR_CUDA;
+    int st = read_scalars(ctx);
+    if (st != ESLAM_OK) return st;
+    out[0] = ctx->n; out[1] = ctx->sc_host->defer_last;
     return ESLAM_OK;
 }
 

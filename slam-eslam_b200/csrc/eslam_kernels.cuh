@@ -28,7 +28,7 @@
 namespace em = eslam_math;
 
 #define TILE 1024                // particles per reduction tile (fixed: defines the summation tree)
-#define WT_THREADS 1024          // threads of the fused project+weight kernel (one particle each per tile)
+#define WT_THREADS 1024          // threads of the generic project+weight kernel
 #define MAX_BND_TOTAL 2048       // boundary elements per resample (pool + chain capacity); more -> sequential fallback
 #define BIN_NONE (-100000)       // "no binade": piece made of zero / sub-quarter-ulp weights only
 #define ERR_ZERO_VARIANCE_BIT 1
@@ -59,10 +59,12 @@ struct DevScalars {              // device-resident scalars of one context
     int n_boundaries;
     int pool_count;              // boundary-element pool allocator (reset by k_reduce_b)
     unsigned int fallbacks;      // times the sequential CDF fallback ran
+    unsigned int defer_count;    // particles the lean weight kernel handed to the generic one (live counter)
+    unsigned int defer_last;     // its value at the end of the last update (diagnostics)
 };
 
 struct TilePartA {               // per-tile partials of loop A
-    double sum_pw, max_w, sum_x, sum_y;
+    double sum_pw, max_w;
     unsigned int cnt, pts;
 };
 
@@ -80,7 +82,8 @@ struct MapParams {
     double g2l[8];               // rows 0 and 1 of C_global2local
     int identity;
     int tile_w, tile_h;          // shared-memory tile (cells)
-    int tile_x0, tile_y0;        // its origin: a placement hint from the host (any value gives the same results)
+    int tile_x0, tile_y0;        // its origin (inside the grid, x0 even): a placement choice of the host, any value
+                                 // gives the same results
 };
 
 struct ModelParams {             // eslam::Configuration hot fields
@@ -91,8 +94,34 @@ struct ModelParams {             // eslam::Configuration hot fields
     int use_shape, use_hash;
 };
 
+// The lean weight kernel's view of one update: only the contact points that pass !(contact < 0.2)
+// (src/ContactModel.cpp:154), grouped (:194-197), and the integer thresholds of the 3-sigma gate on t = zdiff/(sigma corr).
+struct FastContacts {
+    int n_eval, n_groups;
+    int margin;                  // cells: every contact of a particle whose own cell is >= margin inside the tile is in the tile
+    uint32_t gate_lo, gate_span; // high word of |t|: below gate_lo -> inside the gate; within [gate_lo, gate_lo+gate_span] -> undecided
+    double c0x, c0y;             // 1.5*2^28 - offset/scale - tile origin: tile-relative cell quotient with 24 fractional bits
+    uint8_t gend[ESLAM_MAX_CONTACTS];   // one past the last evaluated contact of each group (groups without any are dropped)
+    double px[ESLAM_MAX_CONTACTS], py[ESLAM_MAX_CONTACTS], pzr[ESLAM_MAX_CONTACTS];
+};
+
+struct WeightCommon {
+    StateBufs st; DevScalars* sc;
+    MapParams map; ModelParams mp;
+    const em::dbl2* htab;
+    unsigned long long n, base;  // local particle count, global index of local particle 0
+    uint32_t project_step;
+    int use_tma;                 // the map tile is staged by one TMA bulk tensor copy (tmap valid)
+    const CUtensorMap* tmap;     // device copy of the 2-D tensor map of the elevation grid (8-byte cells, box = the tile)
+    uint32_t* defer_list;        // particles the lean kernel could not decide (order irrelevant)
+    double* hint;                // [gridDim.x][2]: sums of x and y over the particles a CTA handled (tile placement hint)
+    double yaw, z_delta, z_var, dmean[3], dsigma[3];
+};
+
+struct FastParams { WeightCommon c; FastContacts fc; };
+
 struct WeightParams {
-    StateBufs st; DevScalars* sc; TilePartA* part;
+    StateBufs st; DevScalars* sc;
     MapParams map; ModelParams mp;
     const em::dbl2* htab;
     unsigned long long n, base;  // local particle count, global index of local particle 0
@@ -101,6 +130,8 @@ struct WeightParams {
     int use_tma;                 // the map tile is staged by one TMA bulk tensor copy (tmap valid)
     const CUtensorMap* tmap;     // device copy of the 2-D tensor map of the elevation grid (8-byte cells, box = the tile)
     float2* patch[2]; int* porigin[2];   // double buffered with the particle state: [N][P][P] cells, [N][2] origins
+    uint32_t* defer_list;        // LIST mode: the particles to evaluate (count = sc->defer_count)
+    double* hint;                // [gridDim.x][2]: sums of x and y over the particles a CTA handled (tile placement hint)
     double yaw, z_delta, z_var, dmean[3], dsigma[3];
     ContactSet cs;
 };
@@ -177,6 +208,24 @@ __device__ double block_tree_reduce(double* a, double* b, unsigned n, double* sa
     return n ? a[0] : 0.0;
 }
 
+#define SCAN_THREADS 256         // scan-type kernels: 256 threads x 4 consecutive elements = one 1024-tile
+#define EPT 4
+
+// Tree sum over the 1024 leaves of a tile held 4 consecutive per thread (blockDim.x == 256): same tree as
+// tile_tree_sum_1024 (levels 0-1 in the thread, 2-6 by the warp butterfly, 7-9 over the 8 warp partials). red: >= 8.
+__device__ __forceinline__ double tile_tree_sum4(const double v[EPT], double* red) {
+    double t = (v[0] + v[1]) + (v[2] + v[3]);
+    t = warp_tree_sum(t);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    double r = red[threadIdx.x & 7];
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------ map lookup
 struct MapTile { const float2* s; int x0, y0, w, h; };
 
@@ -216,7 +265,7 @@ __device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapPara
                                              PoseEval& out, int32_t* tap_cells, double* tap_cp,
                                              const PatchRef& pr, CpRec* rec) {
     int valid = 0, gvalid = 1;                                           // :134-135
-    double acc_d = 0, acc_v = 0, acc_r = 0, acc_p = 0;
+    double acc_d = 0, acc_v = 0, acc_r = 0;
     double pt_x = 0, pt_y = 0, pt_z = 0;
     int pt_ix = 0, pt_iy = 0;
     out.n_found = 0; out.d1 = 0; out.d2 = 0; out.A = 0; out.poseVar = 0;
@@ -270,8 +319,7 @@ __device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapPara
             const bool cand = (gvalid != 0) & inb & (cell.x == cell.x) & (cell.y == cell.y);
             const float cm = cand ? cell.x : 0.0f, csd = cand ? cell.y : 0.0f;
             const double d = wz - (double)cm;                            // :160
-            const double sp2 = (double)csd * (double)csd;                // :166
-            const double zvar = sp2 + mv;                                // :167
+            const double zvar = em::fma_((double)csd, (double)csd, mv);  // :166-167 (the product of two floats is exact)
             const bool use = cand & (d * d < 9.0 * zvar);                // 3-sigma patch gate of MLSMap::getPatch
             bool rare;
             double ratio = em::likelihood_ratio_fast(d, zvar, inv_corr, htab, rare);           // :170
@@ -279,7 +327,7 @@ __device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapPara
             const double r_eff = use ? ratio : 0.0;
             if ((TAP || PATCH) && use && !valid) { pt_x = wx; pt_y = wy; pt_z = (double)cell.x; pt_ix = ix; pt_iy = iy; }
             acc_d = em::fma_(d, r_eff, acc_d); acc_v = em::fma_(zvar, r_eff, acc_v);           // :172-184
-            acc_r += r_eff; acc_p = em::fma_(sp2, r_eff, acc_p);
+            acc_r += r_eff;
             valid |= (int)use;                                           // :185
             gvalid &= (int)use;                                          // :189-190
         }
@@ -287,7 +335,7 @@ __device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapPara
             if (valid) {
                 if (gvalid && acc_r > 1e-9) {                            // :199
                     const double zd = acc_d / acc_r, zv = acc_v / acc_r; // :201-202
-                    out.poseVar += acc_p / acc_r;                        // :203
+                    out.poseVar += zv - mv;                              // :203 sum(stdev^2 r)/sum(r) = sum(zvar r)/sum(r) - measVar
                     const double e = zd / zv;
                     out.d1 += e; out.d2 += 1.0 / zv; out.A = em::fma_(zd, e, out.A);
                     if (TAP && out.n_found < ESLAM_MAX_CP) {
@@ -301,7 +349,7 @@ __device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapPara
                     out.n_found++;
                 }
                 gvalid = 1; valid = 0;                                   // :210-213 (only when valid: Q4)
-                acc_d = acc_v = acc_r = acc_p = 0;
+                acc_d = acc_v = acc_r = 0;
             }
         }
     }
@@ -407,9 +455,12 @@ __global__ void k_init_gaussian(StateBufs st, DevScalars* sc, unsigned long long
     st.b[cur][B_FLOAT][i] = 1; st.b[cur][B_NF][i] = 0;
 }
 
-// ------------------------------------------------------------------------------------------------ fused project + weight
+// ------------------------------------------------------------------------------------------------ project + weight
+// Shared-memory layout of the weight kernels: [h table | lean contact list | scratch | map tile (128-byte aligned)]
 #define HTAB_BYTES (ESLAM_H_NINT * 3 * 16)
-#define WT_SCRATCH_BYTES (1024 + 256 + 128)   // tile-reduction scratch (doubles, unsigned) + the TMA mbarrier (padded to 128 B)
+#define WT_CONTACT_BYTES (ESLAM_MAX_CONTACTS * 32)         // {px, py, pzr, -} per evaluated contact
+#define WT_SCRATCH_BYTES 1024                              // hint reduction (2 x 32 doubles), TMA mbarrier
+#define WT_HEAD_BYTES ((HTAB_BYTES + WT_CONTACT_BYTES + WT_SCRATCH_BYTES + 127) / 128 * 128)
 
 // TMA (cp.async.bulk.tensor) + mbarrier helpers: one thread arms the barrier with the byte count and issues the copy,
 // everyone waits on the barrier's phase before reading the tile.
@@ -432,181 +483,370 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t phase) {
     } while (!ok);
 }
 
-template <bool DO_PROJECT, bool DO_WEIGHT, bool PATCH>
-__global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_constant__ WeightParams P) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+// Stage the map tile (one TMA bulk tensor copy: box tile_w x tile_h cells at (tile_x0, tile_y0) of the 2-D grid, or
+// ordinary loads when the grid cannot be described to TMA) and the pdf/cdf table into shared memory.  All threads call.
+__device__ __forceinline__ MapTile stage_tile_and_table(const MapParams& M, int use_tma, const CUtensorMap* tmap,
+                                                        const em::dbl2* htab_g, unsigned char* smem_raw) {
     em::dbl2* htab = reinterpret_cast<em::dbl2*>(smem_raw);
-    double* red = reinterpret_cast<double*>(smem_raw + HTAB_BYTES);             // 4 x 32 doubles
-    unsigned* redu = reinterpret_cast<unsigned*>(smem_raw + HTAB_BYTES + 1024); // 2 x 32 unsigned
-    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(smem_raw + HTAB_BYTES + 1024 + 256);
-    float2* tile = reinterpret_cast<float2*>(smem_raw + HTAB_BYTES + WT_SCRATCH_BYTES);   // 128-byte aligned
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const DevScalars* sc = P.sc;
-    const int cur = sc->cur;
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(smem_raw + HTAB_BYTES + WT_CONTACT_BYTES + 512);
+    float2* tile = reinterpret_cast<float2*>(smem_raw + WT_HEAD_BYTES);
+    const int tid = threadIdx.x;
     MapTile mt; mt.s = tile; mt.w = 0; mt.h = 0; mt.x0 = 0; mt.y0 = 0;
-    if (DO_WEIGHT) {
-        const bool tma = P.use_tma && P.map.tile_w > 0;
-        if (P.map.tile_w > 0) {
-            // stage the map tile around the particle cloud into shared memory
-            mt.w = P.map.tile_w; mt.h = P.map.tile_h;
-            // TMA needs a 16-byte aligned box start: an even x0 for 8-byte cells (W and tile_w are even when TMA is on)
-            const int x0 = max(0, min(P.map.tile_x0, P.map.W - mt.w)) & ~1, y0 = max(0, min(P.map.tile_y0, P.map.H - mt.h));
-            mt.x0 = x0; mt.y0 = y0;
-            if (tma) {
-                // one TMA bulk tensor copy: box (tile_w x tile_h cells) at (x0, y0) of the 2-D grid -> shared memory
-                if (tid == 0) mbar_init(mbar, 1);
-                __syncthreads();
-                if (tid == 0) {
-                    mbar_expect_tx(mbar, (uint32_t)(mt.w * mt.h) * (uint32_t)sizeof(float2));
-                    tma_load_2d((uint32_t)__cvta_generic_to_shared(tile), P.tmap, mbar, x0, y0);
-                }
+    const bool tma = use_tma && M.tile_w > 0;
+    if (M.tile_w > 0) {
+        mt.w = M.tile_w; mt.h = M.tile_h; mt.x0 = M.tile_x0; mt.y0 = M.tile_y0;
+        if (tma) {
+            if (tid == 0) mbar_init(mbar, 1);
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(mbar, (uint32_t)(mt.w * mt.h) * (uint32_t)sizeof(float2));
+                tma_load_2d((uint32_t)__cvta_generic_to_shared(tile), tmap, mbar, mt.x0, mt.y0);
             }
-            if (!tma) {
-                const int cells = mt.w * mt.h;
-                for (int i = tid; i < cells; i += WT_THREADS) {
-                    const int r = i / mt.w, cc = i - r * mt.w;
-                    tile[i] = __ldg(&P.map.cells[(size_t)(y0 + r) * P.map.W + x0 + cc]);
+        } else {
+            const int cells = mt.w * mt.h;
+            for (int i = tid; i < cells; i += blockDim.x) {
+                const int r = i / mt.w, cc = i - r * mt.w;
+                tile[i] = __ldg(&M.cells[(size_t)(mt.y0 + r) * M.W + mt.x0 + cc]);
+            }
+        }
+    }
+    for (int i = tid; i < ESLAM_H_NINT * 3; i += blockDim.x) htab[i] = htab_g[i];   // overlaps the TMA copy
+    __syncthreads();
+    if (tma) mbar_wait(mbar, 0);
+    return mt;
+}
+
+// PoseEstimator::project for one particle (src/PoseEstimator.cpp:196-237)
+template <class PP>
+__device__ __forceinline__ void project_particle(const PP& P, unsigned long long gi, double spread, double& x, double& y,
+                                                 double& th, double& z, double& zs, double& w) {
+    const uint32_t sw = stream_word(em::STREAM_PROJECT, gi);
+    double n0, n1, n2, unused;
+    normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 0, sw, P.mp.k0, P.mp.k1), n0, n1);
+    normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 1, sw, P.mp.k0, P.mp.k1), n2, unused);
+    const double dx = P.dmean[0] + P.dsigma[0] * n0;                     // :198
+    double dy = P.dmean[1] + P.dsigma[1] * n1;
+    const double dth = P.dmean[2] + P.dsigma[2] * n2;
+    const em::Philox4 u = em::philox4x32_10((uint32_t)gi, P.project_step, 2, sw, P.mp.k0, P.mp.k1);
+    if (em::u01(u.v[0], u.v[1]) < P.mp.slip_factor) dy *= em::u01(u.v[2], u.v[3]);   // :199-202
+    double s, c; em::sincos_(th, s, c);
+    x += c * dx - s * dy;                                                // :205
+    y += s * dx + c * dy;
+    th += dth;                                                           // :206
+    if (P.mp.max_yaw_dev > 0.0) {                                        // :208-216
+        if (fabs(th - P.yaw) > P.mp.max_yaw_dev) w *= 0.7;
+    }
+    z += P.z_delta;                                                      // :218
+    zs = em::sqrt_(zs * zs + P.z_var);                                   // :219
+    if (spread > 0 && !P.mp.use_hash) {                                  // :224-236
+        const double trans_fac = P.mp.spread_tf * spread, rot_fac = P.mp.spread_rf * spread;
+        double sx, sy, sth;
+        normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 3, sw, P.mp.k0, P.mp.k1), sx, sy);
+        normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 4, sw, P.mp.k0, P.mp.k1), sth, unused);
+        x += sx * trans_fac + 0.0;
+        y += sy * trans_fac + 0.0;
+        th += sth * rot_fac + 0.0;
+    }
+}
+
+// The per-particle tail of updateWeights loop A (src/PoseEstimator.cpp:293-322) once the contact model has run.
+template <class PP>
+__device__ __forceinline__ void finish_particle(const PP& P, int cur, unsigned long long i, const PoseEval& ev, double z,
+                                                double zs2, double w) {
+    double mprob = 1.0; uint8_t floating = 1;                            // :316-317
+    if ((unsigned long long)ev.n_found >= P.mp.min_contacts) {           // ContactModel.cpp:217
+        double weight, zdl, zvr;
+        evaluate_weight(ev, P.mp.use_shape, weight, zdl, zvr);
+        double zVar = zs2;                                               // :294
+        update_z(ev, zdl, zvr, z, zVar);                                 // :295
+        P.st.f[cur][F_Z][i] = z; P.st.f[cur][F_ZS][i] = em::sqrt_(zVar); // :296
+        P.st.f[cur][F_W][i] = w * weight;                                // :300 (Q1: first application)
+        mprob = weight; floating = 0;
+    }
+    P.st.f[cur][F_MP][i] = mprob;
+    P.st.b[cur][B_FLOAT][i] = floating; P.st.b[cur][B_NF][i] = (uint8_t)min(ev.n_found, 255);   // :322 cpoints.size()
+}
+
+// sums of x, y over the particles this CTA handled -> hint[blockIdx.x] (only steers where the next tile is put)
+__device__ __forceinline__ void write_hint(double hx, double hy, double* red, double* hint) {
+    hx = warp_tree_sum(hx); hy = warp_tree_sum(hy);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { red[warp] = hx; red[32 + warp] = hy; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        const double a = warp_tree_sum(lane < nw ? red[lane] : 0.0), b = warp_tree_sum(lane < nw ? red[32 + lane] : 0.0);
+        if (lane == 0) { hint[2 * blockIdx.x] = a; hint[2 * blockIdx.x + 1] = b; }
+    }
+}
+
+// Warp-chunk schedule shared by the weight kernels: chunk c = 32 consecutive work items; warp w of CTA b takes chunks
+// it*(G*W) + w*G + b, so a partly filled last round is spread over all SMs instead of filling a few of them.
+__device__ __forceinline__ unsigned long long first_chunk() { return (unsigned long long)(threadIdx.x >> 5) * gridDim.x + blockIdx.x; }
+__device__ __forceinline__ unsigned long long chunk_stride() { return (unsigned long long)(blockDim.x >> 5) * gridDim.x; }
+
+// ---- the lean path ------------------------------------------------------------------------------------------------
+// ContactModel::evaluatePose for a particle whose whole footprint lies inside the shared-memory tile ("interior").
+// Same arithmetic as contact_eval for everything that reaches the result (zdiff, zvar, 1/sqrt, table, running sums,
+// group fusion); what differs is HOW two decisions are taken:
+//   * cell index: one fused fixed-point quotient per axis (tile-relative, 24 fractional bits) instead of transform +
+//     divide; if the fraction is within 4 steps of a cell border the decision is not trusted;
+//   * 3-sigma gate d^2 < 9 zvar: decided on the high word of |t| = |zdiff| / (sigma corr) against 3/corr; within one
+//     high-word step (2^-20 relative) of the threshold the decision is not trusted.
+// An untrusted decision makes the function return false and the particle is re-evaluated by contact_eval (exact
+// division, exact gate): results are bit-identical to the generic path by construction.
+__device__ __forceinline__ bool fast_eval(const FastContacts& F, const double* fcs /* smem {px,py,pzr,-} */, uint32_t tile_sa,
+                                          int tile_w, const em::dbl2* htab, double inv_sx, double inv_sy, double inv_corr,
+                                          double ucx, double ucy, double s, double c, double z, double mv, PoseEval& out) {
+    const double axx = c * inv_sx, axy = -s * inv_sx, ayx = s * inv_sy, ayy = c * inv_sy;
+    const uint32_t gate_lo = F.gate_lo;
+    // Flags as integers (no loop-carried predicates): pass = -1 while every evaluated contact since the last reset was
+    // inside the gate (gvalid of :135,:189-190: once a contact misses, nothing is used until the next reset); n_used
+    // counts the contacts used since the last reset (valid of :134,:185 == n_used > 0).  border_min / gate_min keep the
+    // minimum distance of any decision from its threshold; both are examined once, after the loop.
+    int pass = -1, n_used = 0;
+    uint32_t border_min = 0xFFFFFFFFu, gate_min = 0xFFFFFFFFu;
+    double acc_d = 0, acc_v = 0, acc_r = 0;
+    out.n_found = 0; out.d1 = 0; out.d2 = 0; out.A = 0; out.poseVar = 0;
+    const int ng = F.n_groups;
+    int i = 0;
+#pragma unroll 1
+    for (int g = 0; g < ng; ++g) {
+        const int e = F.gend[g];
+#pragma unroll 2
+        for (; i < e; ++i) {
+            const double2 pxy = *reinterpret_cast<const double2*>(fcs + 4 * i);
+            const double pzr = fcs[4 * i + 2];
+            const uint64_t ux = em::d2u(em::fma_(axx, pxy.x, em::fma_(axy, pxy.y, ucx)));
+            const uint64_t uy = em::d2u(em::fma_(ayx, pxy.x, em::fma_(ayy, pxy.y, ucy)));
+            const uint32_t kx = (uint32_t)ux, ky = (uint32_t)uy;
+            // (k + 4) << 8 drops the cell bits: below 8 << 8 when the fraction is within 4/2^24 of a cell border
+            border_min = min(border_min, min(kx * 256u + 1024u, ky * 256u + 1024u));
+            const uint32_t cell_sa = tile_sa + ((ky >> 24) * (uint32_t)tile_w + (kx >> 24)) * 8u;
+            float2 cell;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cell.x), "=f"(cell.y) : "r"(cell_sa));
+            const double d = (z + pzr) - (double)cell.x;                 // :147,:160
+            const double zvar = em::fma_((double)cell.y, (double)cell.y, mv);   // :166-167
+            const double qc = em::rsqrt_core(zvar) * inv_corr;           // 1 / (sigma corr)  :109,:170
+            const double t = d * qc;
+            const uint32_t dlt = ((uint32_t)(em::d2u(t) >> 32) & 0x7FFFFFFFu) - gate_lo;   // < 0: inside the gate
+            gate_min = min(gate_min, dlt);                               // NaN cells (empty): |t| high word >= 0x7FF00000, a miss
+            pass &= (int)dlt >> 31;                                      // use = gvalid && inside; gvalid = use  :154,:189-190
+            n_used -= pass;                                              // :185
+            const double ratio = em::h_core(t, htab) * qc;               // :111-112
+            // :172-184, unconditionally: once a contact of the group has missed (pass == 0) the group can no longer be
+            // pushed (:199 needs gvalid) and the sums are cleared or never read again, so what they hold does not matter
+            acc_d = em::fma_(d, ratio, acc_d); acc_v = em::fma_(zvar, ratio, acc_v); acc_r += ratio;
+        }
+        if (n_used > 0) {                                                // :194-197 (the group's last evaluated point)
+            if (pass && acc_r > 1e-9) {                                  // :199
+                const double zd = acc_d / acc_r, zv = acc_v / acc_r;     // :201-202
+                out.poseVar += zv - mv;                                  // :203
+                const double q = zd / zv;
+                out.d1 += q; out.d2 += 1.0 / zv; out.A = em::fma_(zd, q, out.A);
+                out.n_found++;
+            }
+            pass = -1; n_used = 0;                                       // :210-213 (only when valid: Q4)
+            acc_d = acc_v = acc_r = 0;
+        }
+    }
+    // an index or gate decision too close to its threshold: the generic kernel decides (a decision taken while the group
+    // was already invalid cannot matter, but is sent over as well: it is rare)
+    return border_min >= 2048u && gate_min > F.gate_span;
+}
+
+template <bool DO_PROJECT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_weight_fast(const __grid_constant__ FastParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const WeightCommon& C = P.c;
+    const em::dbl2* htab = reinterpret_cast<const em::dbl2*>(smem_raw);
+    double* fcs = reinterpret_cast<double*>(smem_raw + HTAB_BYTES);
+    double* red = reinterpret_cast<double*>(smem_raw + HTAB_BYTES + WT_CONTACT_BYTES);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const DevScalars* sc = C.sc;
+    const int cur = sc->cur;
+    for (int i = tid; i < P.fc.n_eval; i += THREADS) {
+        fcs[4 * i] = P.fc.px[i]; fcs[4 * i + 1] = P.fc.py[i]; fcs[4 * i + 2] = P.fc.pzr[i]; fcs[4 * i + 3] = 0.0;
+    }
+    const MapTile mt = stage_tile_and_table(C.map, C.use_tma, C.tmap, C.htab, smem_raw);   // ends with a barrier
+    const uint32_t tile_sa = (uint32_t)__cvta_generic_to_shared(mt.s);
+    double spread = 0.0;
+    if (DO_PROJECT) spread = weighting_function(sc->max_weight, 0.0, C.mp.spread_thr, 0.0);   // :194
+
+    double* X = C.st.f[cur][F_X]; double* Y = C.st.f[cur][F_Y]; double* TH = C.st.f[cur][F_TH];
+    double* Z = C.st.f[cur][F_Z]; double* ZS = C.st.f[cur][F_ZS]; double* WG = C.st.f[cur][F_W];
+    const unsigned long long n_chunks = (C.n + 31) >> 5;
+    const uint32_t margin = (uint32_t)P.fc.margin;
+    const uint32_t span_x = (uint32_t)max(mt.w - 2 * P.fc.margin, 0), span_y = (uint32_t)max(mt.h - 2 * P.fc.margin, 0);
+    double hx = 0, hy = 0;
+    for (unsigned long long ch = first_chunk(); ch < n_chunks; ch += chunk_stride()) {
+        const unsigned long long i = (ch << 5) + lane;
+        bool defer = false;
+        if (i < C.n) {
+            double x = X[i], y = Y[i], th = TH[i], z = Z[i], zs = ZS[i], w = WG[i];
+            if (DO_PROJECT) {
+                project_particle(C, C.base + i, spread, x, y, th, z, zs, w);
+                X[i] = x; Y[i] = y; TH[i] = th; Z[i] = z; ZS[i] = zs; WG[i] = w;   // everything project changed
+            }
+            hx += x; hy += y;
+            double s, c; em::sincos_(th, s, c);                          // :279-282
+            const double zs2 = zs * zs;
+            const double mv = zs2 + C.mp.merr2;                          // :290
+            if (mv == 0) atomicOr(&C.sc->error_flags, ERR_ZERO_VARIANCE_BIT);   // src/ContactModel.cpp:122-123
+            // interior: the particle's own cell (tile-relative, 24-bit fraction fixed point) at least `margin` cells
+            // inside the tile on every side, the quotient inside the fixed-point range, measVar inside rsqrt_core's range
+            const uint64_t ucx = em::d2u(em::fma_(x, C.map.inv_sx, P.fc.c0x)), ucy = em::d2u(em::fma_(y, C.map.inv_sy, P.fc.c0y));
+            const bool interior = ((uint32_t)(ucx >> 32) == 0x41B80000u) & ((uint32_t)(ucy >> 32) == 0x41B80000u) &
+                                  ((((uint32_t)ucx >> 24) - margin) < span_x) & ((((uint32_t)ucy >> 24) - margin) < span_y) &
+                                  (((uint32_t)(em::d2u(mv) >> 52) - 923u) < 199u);
+            defer = true;
+            if (interior) {
+                PoseEval ev;
+                if (fast_eval(P.fc, fcs, tile_sa, mt.w, htab, C.map.inv_sx, C.map.inv_sy, C.mp.inv_corr, em::u2d(ucx), em::u2d(ucy),
+                              s, c, z, mv, ev)) {
+                    finish_particle(C, cur, i, ev, z, zs2, w);
+                    defer = false;
                 }
             }
         }
-        for (int i = tid; i < ESLAM_H_NINT * 3; i += WT_THREADS) htab[i] = P.htab[i];   // overlaps the TMA copy
-        __syncthreads();
-        if (tma) mbar_wait(mbar, 0);
+        // hand the undecided particles to the generic kernel (warp-aggregated append)
+        const unsigned m = __ballot_sync(0xffffffffu, defer);
+        if (m) {
+            unsigned slot = 0;
+            if (lane == (__ffs(m) - 1)) slot = atomicAdd(&C.sc->defer_count, (unsigned)__popc(m));
+            slot = __shfl_sync(0xffffffffu, slot, __ffs(m) - 1);
+            if (defer) C.defer_list[slot + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+        }
     }
+    write_hint(hx, hy, red, C.hint);
+}
+
+// ---- the generic path ---------------------------------------------------------------------------------------------
+// Any particle, any map (tile + L2 fallback, exact cell index, per-particle patches, C_global2local).  LIST: evaluate
+// the particles the lean kernel handed over (already projected); otherwise all particles.
+template <bool DO_PROJECT, bool DO_WEIGHT, bool PATCH, bool LIST>
+__global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_constant__ WeightParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const em::dbl2* htab = reinterpret_cast<const em::dbl2*>(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw + HTAB_BYTES + WT_CONTACT_BYTES);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const DevScalars* sc = P.sc;
+    const int cur = sc->cur;
+    const unsigned long long count = LIST ? (unsigned long long)sc->defer_count : P.n;
+    const unsigned long long n_chunks = (count + 31) >> 5;
+    if (LIST && (unsigned long long)blockIdx.x >= n_chunks) return;     // nothing for this CTA (its warp 0 would be the first to get work)
+    MapTile mt; mt.s = nullptr; mt.w = 0; mt.h = 0; mt.x0 = 0; mt.y0 = 0;
+    if (DO_WEIGHT) mt = stage_tile_and_table(P.map, P.use_tma, P.tmap, P.htab, smem_raw);
     double spread = 0.0;
     if (DO_PROJECT) spread = weighting_function(sc->max_weight, 0.0, P.mp.spread_thr, 0.0);   // :194
 
     double* X = P.st.f[cur][F_X]; double* Y = P.st.f[cur][F_Y]; double* TH = P.st.f[cur][F_TH];
     double* Z = P.st.f[cur][F_Z]; double* ZS = P.st.f[cur][F_ZS]; double* WG = P.st.f[cur][F_W];
-    double* MPB = P.st.f[cur][F_MP];
-    uint8_t* FL = P.st.b[cur][B_FLOAT]; uint8_t* NF = P.st.b[cur][B_NF];
+    double hx = 0, hy = 0;
+    for (unsigned long long ch = first_chunk(); ch < n_chunks; ch += chunk_stride()) {
+        const unsigned long long k = (ch << 5) + lane;
+        if (k >= count) continue;
+        const unsigned long long i = LIST ? (unsigned long long)P.defer_list[k] : k;
+        double x = X[i], y = Y[i], th = TH[i], z = Z[i], zs = ZS[i], w = WG[i];
+        if (DO_PROJECT) {                                                        // :196-237
+            project_particle(P, P.base + i, spread, x, y, th, z, zs, w);
+            X[i] = x; Y[i] = y; TH[i] = th; Z[i] = z; ZS[i] = zs; WG[i] = w;     // everything project changed
+        }
+        hx += x; hy += y;
+        if (DO_WEIGHT) {                                                         // :276-327
+            double s, c; em::sincos_(th, s, c);
+            const double zs2 = zs * zs;
+            const double mv = zs2 + P.mp.merr2;                                  // :290
+            if (!LIST && mv == 0) atomicOr(&P.sc->error_flags, ERR_ZERO_VARIANCE_BIT);   // src/ContactModel.cpp:122-123
+            PoseEval ev;
+            PatchRef pr; pr.cells = nullptr; pr.ox = INT_MIN; pr.oy = 0; pr.P = 0;
+            CpRec rec;
+            if (PATCH) {
+                const size_t pp = (size_t)P.patch_size * P.patch_size;
+                pr.cells = P.patch[cur] + i * pp; pr.P = P.patch_size;
+                pr.ox = P.porigin[cur][2 * i]; pr.oy = P.porigin[cur][2 * i + 1];
+            }
+            contact_eval<false, PATCH>(P.cs, P.map, mt, htab, P.mp.inv_corr, x, y, z, s, c, mv, ev, nullptr, nullptr,
+                                       pr, &rec);
+            if (PATCH)
+                patch_write(P.map, P.patch[cur] + i * (size_t)P.patch_size * P.patch_size, P.porigin[cur] + 2 * i,
+                            P.patch_size, x, y, ev.n_found, rec);
+            finish_particle(P, cur, i, ev, z, zs2, w);
+        }
+    }
+    if (!LIST && DO_WEIGHT) write_hint(hx, hy, red, P.hint);
+}
 
-    const unsigned n_tiles = (unsigned)((P.n + TILE - 1) / TILE);
-    for (unsigned t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        // one particle per thread: leaf index of the tile's summation tree == threadIdx.x
-        const unsigned long long i = (unsigned long long)t * TILE + tid;
-        double v_pw = 0, v_mx = 0, v_x = 0, v_y = 0; unsigned v_cnt = 0, v_pts = 0;
-        if (i < P.n) {
-            double x = X[i], y = Y[i], th = TH[i], z = Z[i], zs = ZS[i], w = WG[i];
-            if (DO_PROJECT) {                                                    // :196-237
-                const unsigned long long gi = P.base + i;
-                const uint32_t sw = stream_word(em::STREAM_PROJECT, gi);
-                double n0, n1, n2, unused;
-                normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 0, sw, P.mp.k0, P.mp.k1), n0, n1);
-                normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 1, sw, P.mp.k0, P.mp.k1), n2, unused);
-                const double dx = P.dmean[0] + P.dsigma[0] * n0;                 // :198
-                double dy = P.dmean[1] + P.dsigma[1] * n1;
-                const double dth = P.dmean[2] + P.dsigma[2] * n2;
-                const em::Philox4 u = em::philox4x32_10((uint32_t)gi, P.project_step, 2, sw, P.mp.k0, P.mp.k1);
-                if (em::u01(u.v[0], u.v[1]) < P.mp.slip_factor) dy *= em::u01(u.v[2], u.v[3]);   // :199-202
-                double s, c; em::sincos_(th, s, c);
-                x += c * dx - s * dy;                                            // :205
-                y += s * dx + c * dy;
-                th += dth;                                                       // :206
-                if (P.mp.max_yaw_dev > 0.0) {                                    // :208-216
-                    if (fabs(th - P.yaw) > P.mp.max_yaw_dev) w *= 0.7;
-                }
-                z += P.z_delta;                                                  // :218
-                zs = em::sqrt_(zs * zs + P.z_var);                               // :219
-                if (spread > 0 && !P.mp.use_hash) {                              // :224-236
-                    const double trans_fac = P.mp.spread_tf * spread, rot_fac = P.mp.spread_rf * spread;
-                    double sx, sy, sth;
-                    normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 3, sw, P.mp.k0, P.mp.k1), sx, sy);
-                    normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 4, sw, P.mp.k0, P.mp.k1), sth, unused);
-                    x += sx * trans_fac + 0.0;
-                    y += sy * trans_fac + 0.0;
-                    th += sth * rot_fac + 0.0;
-                }
-                X[i] = x; Y[i] = y; TH[i] = th; Z[i] = z; ZS[i] = zs; WG[i] = w;   // everything project changed
-            }
-            if (DO_WEIGHT) {                                                     // :276-327
-                double s, c; em::sincos_(th, s, c);
-                const double zs2 = zs * zs;
-                const double mv = zs2 + P.mp.merr2;                              // :290
-                if (mv == 0) atomicOr(&P.sc->error_flags, ERR_ZERO_VARIANCE_BIT);   // src/ContactModel.cpp:122-123
-                PoseEval ev;
-                PatchRef pr; pr.cells = nullptr; pr.ox = INT_MIN; pr.oy = 0; pr.P = 0;
-                CpRec rec;
-                if (PATCH) {
-                    const size_t pp = (size_t)P.patch_size * P.patch_size;
-                    pr.cells = P.patch[cur] + i * pp; pr.P = P.patch_size;
-                    pr.ox = P.porigin[cur][2 * i]; pr.oy = P.porigin[cur][2 * i + 1];
-                }
-                contact_eval<false, PATCH>(P.cs, P.map, mt, htab, P.mp.inv_corr, x, y, z, s, c, mv, ev, nullptr, nullptr,
-                                           pr, &rec);
-                if (PATCH)
-                    patch_write(P.map, P.patch[cur] + i * (size_t)P.patch_size * P.patch_size, P.porigin[cur] + 2 * i,
-                                P.patch_size, x, y, ev.n_found, rec);
-                double mprob = 1.0; uint8_t floating = 1;                        // :316-317
-                if ((unsigned long long)ev.n_found >= P.mp.min_contacts) {       // ContactModel.cpp:217
-                    double weight, zdl, zvr;
-                    evaluate_weight(ev, P.mp.use_shape, weight, zdl, zvr);
-                    double zVar = zs2;                                           // :294
-                    update_z(ev, zdl, zvr, z, zVar);                             // :295
-                    Z[i] = z; ZS[i] = em::sqrt_(zVar);                           // :296
-                    WG[i] = WG[i] * weight;                                      // :300 (Q1: first application)
-                    mprob = weight; floating = 0;
-                    v_mx = weight; v_cnt = 1; v_pts = (unsigned)ev.n_found;      // :305-310
-                    v_pw = em::root_n(weight, (unsigned long long)ev.n_found);   // :309
-                }
-                MPB[i] = mprob;
-                FL[i] = floating; NF[i] = (uint8_t)min(ev.n_found, 255);         // :322 cpoints.size()
-                v_x = x; v_y = y;
-            }
+// ------------------------------------------------------------------------------------------------ loop A partials
+// data_particles, total_points, max_weight and the terms pow(w, 1/found) of sum_data_weights (src/PoseEstimator.cpp:
+// 305-310) per 1024-particle tile, from what the weight kernels left per particle (mprob, floating, cpoints.size()).
+__global__ void __launch_bounds__(SCAN_THREADS) k_tile_part(StateBufs st, const DevScalars* sc, unsigned long long n,
+                                                            TilePartA* part) {
+    __shared__ double red[8];
+    __shared__ double redm[8];
+    __shared__ unsigned redu[16];
+    const int cur = sc->cur;
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
+    double mp[EPT]; unsigned nf[EPT], fl[EPT];
+    if (i0 + EPT <= n) {
+        const double2 a = *reinterpret_cast<const double2*>(st.f[cur][F_MP] + i0), b = *reinterpret_cast<const double2*>(st.f[cur][F_MP] + i0 + 2);
+        const uchar4 f = *reinterpret_cast<const uchar4*>(st.b[cur][B_FLOAT] + i0), c = *reinterpret_cast<const uchar4*>(st.b[cur][B_NF] + i0);
+        mp[0] = a.x; mp[1] = a.y; mp[2] = b.x; mp[3] = b.y;
+        fl[0] = f.x; fl[1] = f.y; fl[2] = f.z; fl[3] = f.w; nf[0] = c.x; nf[1] = c.y; nf[2] = c.z; nf[3] = c.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            const bool in = i0 + j < n;
+            mp[j] = in ? st.f[cur][F_MP][i0 + j] : 0.0; fl[j] = in ? st.b[cur][B_FLOAT][i0 + j] : 1u; nf[j] = in ? st.b[cur][B_NF][i0 + j] : 0u;
         }
-        if (DO_WEIGHT) {
-            // tile tree: xor butterfly in the warp (levels 0-4), then over the 32 warp partials (levels 5-9)
-            const double a = warp_tree_sum(v_pw), b = warp_max(v_mx);
-            const double cx = warp_tree_sum(v_x), cy = warp_tree_sum(v_y);
-            const unsigned c1 = warp_sum_u(v_cnt), c2 = warp_sum_u(v_pts);
-            __syncthreads();
-            if (lane == 0) { red[warp] = a; red[32 + warp] = b; red[64 + warp] = cx; red[96 + warp] = cy; redu[warp] = c1; redu[32 + warp] = c2; }
-            __syncthreads();
-            if (warp == 0) {
-                const double a2 = warp_tree_sum(red[lane]), b2 = warp_max(red[32 + lane]);
-                const double cx2 = warp_tree_sum(red[64 + lane]), cy2 = warp_tree_sum(red[96 + lane]);
-                const unsigned c12 = warp_sum_u(redu[lane]), c22 = warp_sum_u(redu[32 + lane]);
-                if (lane == 0) {
-                    TilePartA o; o.sum_pw = a2; o.max_w = b2; o.sum_x = cx2; o.sum_y = cy2; o.cnt = c12; o.pts = c22;
-                    P.part[t] = o;
-                }
-            }
+    }
+    double pw[EPT], mx = 0; unsigned cnt = 0, pts = 0;
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        pw[j] = 0.0;
+        if (!fl[j]) {
+            pw[j] = em::root_n(mp[j], (unsigned long long)nf[j]);        // :309
+            mx = fmax(mx, mp[j]); cnt += 1; pts += nf[j];                // :305-310
         }
+    }
+    const double s = tile_tree_sum4(pw, red);
+    mx = warp_max(mx); cnt = warp_sum_u(cnt); pts = warp_sum_u(pts);
+    if ((threadIdx.x & 31) == 0) { redm[threadIdx.x >> 5] = mx; redu[threadIdx.x >> 5] = cnt; redu[8 + (threadIdx.x >> 5)] = pts; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        TilePartA o; o.sum_pw = s; o.max_w = 0; o.cnt = 0; o.pts = 0;
+        for (int k = 0; k < SCAN_THREADS / 32; ++k) { o.max_w = fmax(o.max_w, redm[k]); o.cnt += redu[k]; o.pts += redu[8 + k]; }
+        part[blockIdx.x] = o;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ reduce A (one CTA)
 // floating_weight (:329), max_weight (:305, :347-348), the loop-B power table, next step's map tile centre
-__global__ void __launch_bounds__(1024, 1) k_reduce_a(const TilePartA* part, unsigned n_tiles, unsigned long long n,
+__global__ void __launch_bounds__(1024, 1) k_reduce_a(const TilePartA* part, unsigned n_tiles, unsigned long long n_local,
                                                       DevScalars* sc, double* scratch_a, double* scratch_b,
-                                                      double discount) {
+                                                      double discount, const double* hint, unsigned n_hint) {
     __shared__ double red[32];
     __shared__ unsigned long long redull[64];
     __shared__ double tree_a[TREE_SMEM], tree_b[TREE_SMEM / 2];
-    double mx = 0, sx = 0, sy = 0; unsigned long long cnt = 0, pts = 0;
+    double mx = 0; unsigned long long cnt = 0, pts = 0;
     for (unsigned i = threadIdx.x; i < n_tiles; i += blockDim.x) {
         const TilePartA p = part[i];
         scratch_a[i] = p.sum_pw;
-        mx = fmax(mx, p.max_w); sx += p.sum_x; sy += p.sum_y; cnt += p.cnt; pts += p.pts;
+        mx = fmax(mx, p.max_w); cnt += p.cnt; pts += p.pts;
     }
     __syncthreads();
     const double sum_pw = block_tree_reduce(scratch_a, scratch_b, n_tiles, tree_a, tree_b);
-    mx = warp_max(mx); sx = warp_tree_sum(sx); sy = warp_tree_sum(sy);
+    mx = warp_max(mx);
     for (int o = 1; o < 32; o <<= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); pts += __shfl_xor_sync(0xffffffffu, pts, o); }
     __syncthreads();
     if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = mx; redull[threadIdx.x >> 5] = cnt; redull[32 + (threadIdx.x >> 5)] = pts; }
     __syncthreads();
-    double smx = 0; unsigned long long scnt = 0, spts = 0;
-    if (threadIdx.x == 0) { for (int i = 0; i < 32; ++i) { smx = fmax(smx, red[i]); scnt += redull[i]; spts += redull[32 + i]; } }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sx;
-    __syncthreads();
-    double tsx = 0; if (threadIdx.x == 0) for (int i = 0; i < 32; ++i) tsx += red[i];
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sy;
-    __syncthreads();
     if (threadIdx.x == 0) {
-        double tsy = 0; for (int i = 0; i < 32; ++i) tsy += red[i];
+        double smx = 0; unsigned long long scnt = 0, spts = 0;
+        for (int i = 0; i < 32; ++i) { smx = fmax(smx, red[i]); scnt += redull[i]; spts += redull[32 + i]; }
+        double tsx = 0, tsy = 0;
+        for (unsigned i = 0; i < n_hint; ++i) { tsx += hint[2 * i]; tsy += hint[2 * i + 1]; }
         const double last_max = sc->max_weight;                                       // :268
         const double fw = scnt > 0 ? sum_pw / (double)scnt : 1.0;                     // :329
         sc->floating_weight = fw;
@@ -615,29 +855,12 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_a(const TilePartA* part, uns
         const double xb = discount * fw;
         for (int k = 0; k <= 4; ++k) sc->pow_table[k] = em::pow_u64(xb, (unsigned long long)(4 - k));   // :336
         sc->pow_table[5] = em::pow_u64(xb, ~0ull);                                    // wrapped size_t exponent (Q2)
-        if (n > 0) { sc->tile_cx = tsx / (double)n; sc->tile_cy = tsy / (double)n; }
+        if (n_local > 0 && n_hint > 0) { sc->tile_cx = tsx / (double)n_local; sc->tile_cy = tsy / (double)n_local; }
+        sc->defer_last = sc->defer_count; sc->defer_count = 0;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ loop B + raw sums
-#define SCAN_THREADS 256         // scan-type kernels: 256 threads x 4 consecutive elements = one 1024-tile
-#define EPT 4
-
-// Tree sum over the 1024 leaves of a tile held 4 consecutive per thread (blockDim.x == 256): same tree as
-// tile_tree_sum_1024 (levels 0-1 in the thread, 2-6 by the warp butterfly, 7-9 over the 8 warp partials). red: >= 8.
-__device__ __forceinline__ double tile_tree_sum4(const double v[EPT], double* red) {
-    double t = (v[0] + v[1]) + (v[2] + v[3]);
-    t = warp_tree_sum(t);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
-    __syncthreads();
-    double r = red[threadIdx.x & 7];
-    r += __shfl_xor_sync(0xffffffffu, r, 1);
-    r += __shfl_xor_sync(0xffffffffu, r, 2);
-    r += __shfl_xor_sync(0xffffffffu, r, 4);
-    return r;
-}
-
 // weight *= mprob * pow(discount*floating_weight, 4 - cpoints.size())  (:332-345); per-tile sums of the result
 template <bool APPLY>
 __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, const DevScalars* sc, unsigned long long n,

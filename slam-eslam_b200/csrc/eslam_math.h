@@ -256,14 +256,14 @@ ESLAM_HD void box_muller(double u1, double u2, double& n0, double& n1) {
 }
 
 // ---------------------------------------------------------------- 1/sqrt
-// ~1.5 ulp, deterministic: fp32 magic seed + 3 fp32 Newton steps + one fp64 Halley step.
+// ~1 ulp, deterministic: fp32 magic seed (3.4e-2) + 2 fp32 Newton steps (1.8e-3, 4.7e-6) + one fp64 Halley step
+// (cubic: residual 5/16 (2 * 4.7e-6)^3 = 3e-16).
 // rsqrt_core is valid for x in [2^-100, 2^100); rsqrt_ adds the out-of-range fallback.
 ESLAM_HD double rsqrt_core(double x) {
     float xf = (float)x;
     float y = u2f(0x5f3759dfu - (f2u(xf) >> 1));
     float hx = 0.5f * xf;
     float t;
-    t = y * y; t = fmaf_(-hx, t, 1.5f); y = y * t;
     t = y * y; t = fmaf_(-hx, t, 1.5f); y = y * t;
     t = y * y; t = fmaf_(-hx, t, 1.5f); y = y * t;
     double yd = (double)y;
@@ -282,13 +282,13 @@ ESLAM_HD double rsqrt_(double x) {
 // ---------------------------------------------------------------- inverse Mills ratio h(t) = phi(t)/Phi(t)
 // The reference computes pdf(n,z)/cdf(n,z) with n = Normal(0, sigma*corr)
 // (src/ContactModel.cpp:104-115) = h(z/s)/s, s = sigma*corr.  h is tabulated on
-// [-H_TMAX, H_TMAX) in H_NINT intervals of width 1/H_PER_UNIT as degree-5 polynomials in the
-// centred local coordinate (tools/gen_h_table.py; relative error <= 1e-10 everywhere a contact
+// [-H_TMAX, H_TMAX] in H_NINT intervals of width 1/H_PER_UNIT (centred on the multiples of 1/H_PER_UNIT) as degree-5
+// polynomials in the centred local coordinate (tools/gen_h_table.py; relative error <= 1e-10 everywhere a contact
 // can matter, <= 1e-12 for t <= 4).  Layout: tab[q*H_NINT + j] = (c[2q], c[2q+1]) so that
 // neighbouring intervals are neighbouring 16-byte words (shared-memory bank friendly).
 #define ESLAM_H_TMAX 10.0
 #define ESLAM_H_PER_UNIT 32
-#define ESLAM_H_NINT 640
+#define ESLAM_H_NINT 641
 #define ESLAM_H_TABLE_DOUBLES (ESLAM_H_NINT * 6)
 
 struct dbl2 { double x, y; };
@@ -308,13 +308,15 @@ ESLAM_HD double h_slow(double t) {
 
 ESLAM_HD bool h_in_range(double t) { return fabs(t) < ESLAM_H_TMAX; }
 // table evaluation, valid for h_in_range(t) (any other input reads a clamped interval: garbage, never out of bounds).
-// interval index and centred coordinate come from one magic-number rounding: no int<->double conversions.
+// Interval j is centred on t = (j - 320)/32; index and centred coordinate come from one magic-number rounding:
+// m = 32 t + (1.5 2^52 + 320) has rne(32 t) + 320 in its low mantissa word, m - magic = rne(32 t) exactly,
+// z = 32 t - rne(32 t) in [-0.5, 0.5] with a single rounding.  No int<->double conversions.
+#define ESLAM_H_MAGIC 6755399441056064.0   /* 1.5 * 2^52 + 320 */
 ESLAM_HD double h_core(double t, const dbl2* tab) {
-    const double t32 = fma_(t, (double)ESLAM_H_PER_UNIT, ESLAM_H_TMAX * ESLAM_H_PER_UNIT - 0.5);   // 32 t + 319.5
-    const double m = t32 + 6755399441055744.0;      // 1.5 * 2^52: low mantissa bits = rne(t32) = interval index
-    int j = (int)(uint32_t)d2u(m);
-    j = j < 0 ? 0 : (j > ESLAM_H_NINT - 1 ? ESLAM_H_NINT - 1 : j);
-    const double z = t32 - (m - 6755399441055744.0);   // in [-0.5, 0.5]
+    const double m = fma_(t, (double)ESLAM_H_PER_UNIT, ESLAM_H_MAGIC);
+    uint32_t j = (uint32_t)d2u(m);
+    j = j > (uint32_t)(ESLAM_H_NINT - 1) ? (uint32_t)(ESLAM_H_NINT - 1) : j;   // also catches "negative" (wrapped) indices
+    const double z = fma_(t, (double)ESLAM_H_PER_UNIT, -(m - ESLAM_H_MAGIC));
     const dbl2 c01 = tab[j], c23 = tab[ESLAM_H_NINT + j], c45 = tab[2 * ESLAM_H_NINT + j];
     double p = c45.y;
     p = fma_(p, z, c45.x);
