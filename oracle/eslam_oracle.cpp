@@ -16,7 +16,7 @@
 
 namespace em = eslam_math;
 
-static const em::dbl2 H_TABLE[ESLAM_H_NINT * 3] = {
+static const em::dbl2 H_TABLE[ESLAM_H_TABLE_ENTRIES] = {
 #include "../slam-eslam_b200/csrc/eslam_h_table.inc"
 };
 
@@ -296,16 +296,22 @@ struct eslam_oracle_ctx {
             if (valid && (groupId == -1 || i + 1 == contactPoints.size()
                           || groupId != contactPoints[i + 1].group_id)) {          // :194-197
                 if (group_valid && contact_ratio > 1e-9) {      // :199
-                    p.zdiff /= contact_ratio;                   // :201-203
-                    p.zvar /= contact_ratio;
+                    if (A::shared) {                            // one reciprocal instead of two divisions
+                        const double ir = 1.0 / contact_ratio;
+                        p.zdiff *= ir; p.zvar *= ir;
+                    } else {
+                        p.zdiff /= contact_ratio;               // :201-203
+                        p.zvar /= contact_ratio;
+                    }
                     // SHARED: sum(stdev^2 r)/sum(r) == sum(zvar r)/sum(r) - measVar (measVar is constant over the
                     // particle), so the fourth running sum is not carried
                     if (A::shared) m_poseVar += p.zvar - measVar;
                     else m_poseVar += pose_var_avg / contact_ratio;
                     contact_points.push_back(p);                // :205
                     if (A::shared) {                            // running sums for evaluateWeight
-                        const double e = p.zdiff / p.zvar;
-                        sh_d1 += e; sh_d2 += 1.0 / p.zvar; sh_A = em::fma_(p.zdiff, e, sh_A);
+                        const double iv = 1.0 / p.zvar;
+                        const double e = p.zdiff * iv;
+                        sh_d1 += e; sh_d2 += iv; sh_A = em::fma_(p.zdiff, e, sh_A);
                     }
                     // :207-208 p.prob *= matchTerrain(...) happens after the push_back: inert (quirk Q5)
                 }

@@ -13,7 +13,7 @@
 #include <string>
 #include <vector>
 
-static const em::dbl2 H_TABLE_HOST[ESLAM_H_NINT * 3] = {
+static const em::dbl2 H_TABLE_HOST[ESLAM_H_TABLE_ENTRIES] = {
 #include "eslam_h_table.inc"
 };
 
@@ -36,7 +36,8 @@ struct eslam_gpu_ctx {
     uint32_t* ancestors; double* cdf;
     uint32_t* defer_list;                         // particles the lean weight kernel hands to the generic one (n entries)
     double* hint; unsigned hint_n;                // per-CTA sums of x, y (tile placement hint), entries written by the last update
-    int fast_threads;                             // CTA size of the lean kernel (ESLAM_GPU_FAST_THREADS = 512 | 1024)
+    int lean_threads;                             // CTA size of the lean kernel: 1024 x 64 registers or 512 x 128 (ESLAM_GPU_LEAN_THREADS)
+    int* bin_count; uint2* keys; uint32_t* bin_list; unsigned* bin_offs; unsigned* bin_next; int* cta_bin;   // lean path: bins, per-bin lists, chunk counters
     bool grid_sane;                               // every stdev of the grid is NaN or |stdev| < 2^49 (lean path precondition)
     float2* patch[2]; int* porigin[2];            // per-particle map patches (cfg.patch_size > 0), double buffered
     // per-tile arrays: l_* cover the local tiles, g_* all tiles of all ranks (aliases of l_* when world == 1)
@@ -93,7 +94,7 @@ static void free_particles(eslam_gpu_ctx* ctx) {
         for (int f = 0; f < 7; ++f) dfree(ctx->st.f[b][f]);
         for (int f = 0; f < 2; ++f) dfree(ctx->st.b[b][f]);
     }
-    dfree(ctx->ancestors); dfree(ctx->cdf); dfree(ctx->defer_list);
+    dfree(ctx->ancestors); dfree(ctx->cdf); dfree(ctx->defer_list); dfree(ctx->keys); dfree(ctx->bin_list);
     for (int b = 0; b < 2; ++b) { dfree(ctx->patch[b]); dfree(ctx->porigin[b]); }
     const bool sh = ctx->g_part_a != ctx->l_part_a;
     if (sh) { dfree(ctx->g_part_a); dfree(ctx->g_tile_sum); dfree(ctx->g_tile_sq); dfree(ctx->g_desc); dfree(ctx->g_pool);
@@ -169,6 +170,7 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
             for (int f = 0; f < 2; ++f) CK(dalloc(&ctx->st.b[b][f], n));
         }
         CK(dalloc(&ctx->ancestors, n)); CK(dalloc(&ctx->cdf, n)); CK(dalloc(&ctx->defer_list, n));
+        CK(dalloc(&ctx->keys, n)); CK(dalloc(&ctx->bin_list, n));
         if (ctx->cfg.patch_size > 0) {
             const size_t pp = (size_t)ctx->cfg.patch_size * ctx->cfg.patch_size;
             for (int b = 0; b < 2; ++b) { CK(dalloc(&ctx->patch[b], n * pp)); CK(dalloc(&ctx->porigin[b], 2 * n)); }
@@ -297,7 +299,8 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     ctx->device = device; ctx->launches = 0; ctx->n = ctx->cap = 0; ctx->t_local = ctx->t_global = ctx->t_cap = 0;
     ctx->ancestors = nullptr; ctx->cdf = nullptr; ctx->defer_list = nullptr; ctx->hint = nullptr; ctx->hint_n = 0;
     ctx->grid_sane = false;
-    ctx->fast_threads = getenv("ESLAM_GPU_FAST_THREADS") ? atoi(getenv("ESLAM_GPU_FAST_THREADS")) : 1024;
+    ctx->lean_threads = getenv("ESLAM_GPU_LEAN_THREADS") ? atoi(getenv("ESLAM_GPU_LEAN_THREADS")) : 1024;
+    ctx->bin_count = nullptr; ctx->keys = nullptr; ctx->bin_list = nullptr; ctx->bin_offs = nullptr; ctx->bin_next = nullptr; ctx->cta_bin = nullptr;
     for (int b = 0; b < 2; ++b) { ctx->patch[b] = nullptr; ctx->porigin[b] = nullptr; }
     ctx->l_part_a = ctx->g_part_a = nullptr; ctx->l_tile_sum = ctx->g_tile_sum = ctx->l_tile_sq = ctx->g_tile_sq = nullptr;
     ctx->l_desc = ctx->g_desc = nullptr; ctx->l_pool = ctx->g_pool = nullptr;
@@ -320,9 +323,13 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     CK(cudaMallocHost((void**)&ctx->sc_host, sizeof(DevScalars)));
     CK(cudaMallocHost((void**)&ctx->tile_hint, 2 * sizeof(double)));
     ctx->tile_hint[0] = ctx->tile_hint[1] = 0.0;
+    CK(dalloc(&ctx->bin_count, (size_t)MAX_BINS)); CK(dalloc(&ctx->bin_offs, (size_t)MAX_BINS)); CK(dalloc(&ctx->bin_next, (size_t)MAX_BINS));
+    CK(dalloc(&ctx->cta_bin, (size_t)ctx->sm_count));
+    CK(cudaMemsetAsync(ctx->bin_count, 0, MAX_BINS * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->bin_next, 0, MAX_BINS * sizeof(unsigned), ctx->stream));
     CK(dalloc(&ctx->hint, (size_t)2 * ctx->sm_count));
     CK(cudaMemsetAsync(ctx->hint, 0, 2 * ctx->sm_count * sizeof(double), ctx->stream));
-    CK(dalloc(&ctx->htab, (size_t)ESLAM_H_NINT * 3));
+    CK(dalloc(&ctx->htab, (size_t)ESLAM_H_TABLE_ENTRIES));
     CK(cudaMemcpyAsync(ctx->htab, H_TABLE_HOST, sizeof(H_TABLE_HOST), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainSmem)));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -337,7 +344,7 @@ void eslam_gpu_destroy(eslam_gpu_ctx* ctx) {
     for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
     free_particles(ctx); free_window(ctx);
     cudaFree(ctx->d_barrier_send); cudaFree(ctx->d_barrier_recv);
-    cudaFree(ctx->sc); cudaFreeHost(ctx->sc_host); cudaFreeHost(ctx->tile_hint); cudaFree(ctx->d_tmap); cudaFree(ctx->htab); cudaFree(ctx->cells); cudaFree(ctx->hint);
+    cudaFree(ctx->sc); cudaFreeHost(ctx->sc_host); cudaFreeHost(ctx->tile_hint); cudaFree(ctx->d_tmap); cudaFree(ctx->htab); cudaFree(ctx->cells); cudaFree(ctx->hint); cudaFree(ctx->bin_count); cudaFree(ctx->bin_offs); cudaFree(ctx->bin_next); cudaFree(ctx->cta_bin);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -440,10 +447,8 @@ int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int he
     CK(cudaFuncSetAttribute(k_project_weight<true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_project_weight<false, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_project_weight<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_weight_fast<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_weight_fast<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_weight_fast<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_weight_fast<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_weight_lean<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_weight_lean<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->has_map = true;
     return ESLAM_OK;
@@ -570,18 +575,27 @@ static bool fill_fast_params(eslam_gpu_ctx* ctx, FastParams* F, const WeightPara
         }
         if ((cs.flags[i] & 2u) && fc.n_eval > last_end) { fc.gend[fc.n_groups++] = (uint8_t)fc.n_eval; last_end = fc.n_eval; }
     }
+    // bins: tile cores on a lattice; a particle whose own cell is in a core has its whole footprint (contact offsets
+    // <= R, +1 cell for the approximate own cell, +1 for rounding) inside that bin's tile.  Even margin and core width
+    // keep the tile origins even (TMA: 16-byte aligned box start).
     const double inv_max = std::max(P.map.inv_sx, P.map.inv_sy);
     const double mc = ceil(sqrt(r2) * inv_max) + 2.0;
-    if (!(mc * 2 + 1 < P.map.tile_w && mc * 2 + 1 < P.map.tile_h)) return false;
-    fc.margin = (int)mc;
+    if (!(mc < 100.0)) return false;
+    fc.margin = ((int)mc + 1) & ~1;
+    if ((P.map.W & 1) || (P.map.tile_w & 1)) return false;
+    fc.bsx = (P.map.tile_w - 2 * fc.margin) & ~1; fc.bsy = P.map.tile_h - 2 * fc.margin;
+    if (fc.bsx < 8 || fc.bsy < 8) return false;
+    fc.nbx = (P.map.W + fc.bsx - 1) / fc.bsx; fc.nby = (P.map.H + fc.bsy - 1) / fc.bsy;
+    fc.nb = fc.nbx * fc.nby;
+    if (fc.nb > MAX_BINS || P.map.W > 16000 || P.map.H > 16000) return false;
     // 3-sigma gate d^2 < 9 zvar  <=>  |t| < 3/corr with t = d / (sigma corr); decided on the high word of |t|
     const double T = 3.0 * P.mp.inv_corr;
     if (!(T > 0.0) || !(T < 1e300)) return false;
     const uint32_t hiT = hi_word(T), hi10 = hi_word(ESLAM_H_TMAX);
     fc.gate_lo = std::min(hiT, hi10) - 1u;                                // also keeps t inside the table
     fc.gate_span = (hiT + 1u) - fc.gate_lo;
-    fc.c0x = (402653184.0 - (double)P.map.tile_x0) - P.map.ox * P.map.inv_sx;   // 1.5 * 2^28
-    fc.c0y = (402653184.0 - (double)P.map.tile_y0) - P.map.oy * P.map.inv_sy;
+    fc.c0x = 402653184.0 - P.map.ox * P.map.inv_sx;                       // 1.5 * 2^28 - offset/scale
+    fc.c0y = 402653184.0 - P.map.oy * P.map.inv_sy;
     return true;
 }
 
@@ -765,17 +779,22 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
     const bool patches = ctx->cfg.patch_size > 0;
     static FastParams F;                                                  // large (lists of 128 contacts): not on the stack
     if (fill_fast_params(ctx, &F, P, *cs)) {
-        // lean kernel for the particles whose footprint lies inside the tile, generic kernel for the rest
-        const bool wide = ctx->fast_threads == 512;                      // 512 threads x 128 registers or 1024 x 64
-        if (step_or_null) {
-            if (wide) k_weight_fast<true, 512><<<grid, 512, smem, ctx->stream>>>(F);
-            else k_weight_fast<true, 1024><<<grid, 1024, smem, ctx->stream>>>(F);
-            ctx->project_step++;
-        } else if (wide) k_weight_fast<false, 512><<<grid, 512, smem, ctx->stream>>>(F);
-        else k_weight_fast<false, 1024><<<grid, 1024, smem, ctx->stream>>>(F);
+        // bin the particles by map tile, evaluate bin by bin from shared memory; the generic kernel takes what is left
+        // (footprints that leave the map, out-of-range values)
+        const unsigned T = ctx->t_local;
+        if (step_or_null) { k_project_bin<true><<<T, 1024, 0, ctx->stream>>>(F, ctx->bin_count, ctx->keys); ctx->project_step++; }
+        else k_project_bin<false><<<T, 1024, 0, ctx->stream>>>(F, ctx->bin_count, ctx->keys);
+        LAUNCHED();
+        k_bin_scatter<<<T, 1024, 0, ctx->stream>>>(ctx->bin_count, F.fc.nb, ctx->keys, ctx->n, ctx->bin_list, ctx->bin_offs, ctx->cta_bin, ctx->sm_count);
+        LAUNCHED();
+        if (ctx->lean_threads == 512)
+            k_weight_lean<512><<<(unsigned)ctx->sm_count, 512, smem, ctx->stream>>>(F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin);
+        else
+            k_weight_lean<1024><<<(unsigned)ctx->sm_count, 1024, smem, ctx->stream>>>(F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin);
         LAUNCHED();
         k_project_weight<false, true, false, true><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
         LAUNCHED();
+        ctx->hint_n = 0;
     } else {
         if (step_or_null) {
             if (patches) k_project_weight<true, true, true, false><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
@@ -784,14 +803,14 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
         } else if (patches) k_project_weight<false, true, true, false><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
         else k_project_weight<false, true, false, false><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
         LAUNCHED();
+        ctx->hint_n = grid;
     }
     if (ev1) CK(cudaEventRecord(ev1, ctx->stream));
-    ctx->hint_n = grid;
     k_tile_part<<<ctx->t_local, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->n, ctx->l_part_a);
     LAUNCHED();
     AG(ctx->l_part_a, ctx->g_part_a, ctx->t_local * sizeof(TilePartA));
     k_reduce_a<<<1, 1024, 0, ctx->stream>>>(ctx->g_part_a, ctx->t_global, ctx->n, ctx->sc, ctx->scratch_a, ctx->scratch_b,
-                                            ctx->cfg.discount_factor, ctx->hint, ctx->hint_n);
+                                            ctx->cfg.discount_factor, ctx->hint, ctx->hint_n, ctx->bin_count, ctx->bin_next);
     LAUNCHED();
     CK(cudaMemcpyAsync(ctx->tile_hint, &ctx->sc->tile_cx, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return launch_tail(ctx, true, 1, 1, 0);

@@ -100,7 +100,8 @@ struct FastContacts {
     int n_eval, n_groups;
     int margin;                  // cells: every contact of a particle whose own cell is >= margin inside the tile is in the tile
     uint32_t gate_lo, gate_span; // high word of |t|: below gate_lo -> inside the gate; within [gate_lo, gate_lo+gate_span] -> undecided
-    double c0x, c0y;             // 1.5*2^28 - offset/scale - tile origin: tile-relative cell quotient with 24 fractional bits
+    double c0x, c0y;             // 1.5*2^28 - offset/scale: cell quotient with 24 fractional bits (minus the tile origin: tile-relative)
+    int bsx, bsy, nbx, nby, nb;  // bins: a lattice of tile cores (tile minus the margin on every side), bsx x bsy cells each
     uint8_t gend[ESLAM_MAX_CONTACTS];   // one past the last evaluated contact of each group (groups without any are dropped)
     double px[ESLAM_MAX_CONTACTS], py[ESLAM_MAX_CONTACTS], pzr[ESLAM_MAX_CONTACTS];
 };
@@ -334,10 +335,12 @@ __device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapPara
         if (f & 2u) {                                                    // :194-197 end of group: warp-uniform
             if (valid) {
                 if (gvalid && acc_r > 1e-9) {                            // :199
-                    const double zd = acc_d / acc_r, zv = acc_v / acc_r; // :201-202
+                    const double ir = 1.0 / acc_r;
+                    const double zd = acc_d * ir, zv = acc_v * ir;       // :201-202
                     out.poseVar += zv - mv;                              // :203 sum(stdev^2 r)/sum(r) = sum(zvar r)/sum(r) - measVar
-                    const double e = zd / zv;
-                    out.d1 += e; out.d2 += 1.0 / zv; out.A = em::fma_(zd, e, out.A);
+                    const double iv = 1.0 / zv;
+                    const double e = zd * iv;
+                    out.d1 += e; out.d2 += iv; out.A = em::fma_(zd, e, out.A);
                     if (TAP && out.n_found < ESLAM_MAX_CP) {
                         double* o = tap_cp + out.n_found * 5;
                         o[0] = pt_x; o[1] = pt_y; o[2] = pt_z; o[3] = zd; o[4] = zv;
@@ -457,7 +460,7 @@ __global__ void k_init_gaussian(StateBufs st, DevScalars* sc, unsigned long long
 
 // ------------------------------------------------------------------------------------------------ project + weight
 // Shared-memory layout of the weight kernels: [h table | lean contact list | scratch | map tile (128-byte aligned)]
-#define HTAB_BYTES (ESLAM_H_NINT * 3 * 16)
+#define HTAB_BYTES ((ESLAM_H_TABLE_ENTRIES * 16 + 127) / 128 * 128)
 #define WT_CONTACT_BYTES (ESLAM_MAX_CONTACTS * 32)         // {px, py, pzr, -} per evaluated contact
 #define WT_SCRATCH_BYTES 1024                              // hint reduction (2 x 32 doubles), TMA mbarrier
 #define WT_HEAD_BYTES ((HTAB_BYTES + WT_CONTACT_BYTES + WT_SCRATCH_BYTES + 127) / 128 * 128)
@@ -510,7 +513,7 @@ __device__ __forceinline__ MapTile stage_tile_and_table(const MapParams& M, int 
             }
         }
     }
-    for (int i = tid; i < ESLAM_H_NINT * 3; i += blockDim.x) htab[i] = htab_g[i];   // overlaps the TMA copy
+    for (int i = tid; i < ESLAM_H_TABLE_ENTRIES; i += blockDim.x) htab[i] = htab_g[i];   // overlaps the TMA copy
     __syncthreads();
     if (tma) mbar_wait(mbar, 0);
     return mt;
@@ -587,24 +590,151 @@ __device__ __forceinline__ unsigned long long first_chunk() { return (unsigned l
 __device__ __forceinline__ unsigned long long chunk_stride() { return (unsigned long long)(blockDim.x >> 5) * gridDim.x; }
 
 // ---- the lean path ------------------------------------------------------------------------------------------------
-// ContactModel::evaluatePose for a particle whose whole footprint lies inside the shared-memory tile ("interior").
-// Same arithmetic as contact_eval for everything that reaches the result (zdiff, zvar, 1/sqrt, table, running sums,
-// group fusion); what differs is HOW two decisions are taken:
+// Particles are binned by the map tile that holds their whole footprint (k_project_bin), listed per bin
+// (k_bin_scatter), and evaluated bin by bin from shared memory (k_weight_lean): every CTA stages the tile of the bin
+// it is working on with one TMA bulk tensor copy, so the lookups never leave the SM wherever the cloud lies.
+//
+// ContactModel::evaluatePose for a particle whose footprint lies inside the staged tile uses the same arithmetic as
+// contact_eval for everything that reaches the result (zdiff, zvar, 1/sqrt, table, running sums, group fusion); what
+// differs is HOW two decisions are taken:
 //   * cell index: one fused fixed-point quotient per axis (tile-relative, 24 fractional bits) instead of transform +
 //     divide; if the fraction is within 4 steps of a cell border the decision is not trusted;
 //   * 3-sigma gate d^2 < 9 zvar: decided on the high word of |t| = |zdiff| / (sigma corr) against 3/corr; within one
 //     high-word step (2^-20 relative) of the threshold the decision is not trusted.
-// An untrusted decision makes the function return false and the particle is re-evaluated by contact_eval (exact
-// division, exact gate): results are bit-identical to the generic path by construction.
-__device__ __forceinline__ bool fast_eval(const FastContacts& F, const double* fcs /* smem {px,py,pzr,-} */, uint32_t tile_sa,
-                                          int tile_w, const em::dbl2* htab, double inv_sx, double inv_sy, double inv_corr,
-                                          double ucx, double ucy, double s, double c, double z, double mv, PoseEval& out) {
-    const double axx = c * inv_sx, axy = -s * inv_sx, ayx = s * inv_sy, ayy = c * inv_sy;
+// An untrusted decision is taken again for that contact by lean_contact_exact (IEEE division, the gate as written):
+// results are bit-identical to the generic path by construction.
+#define MAX_BINS 4096
+
+__device__ __forceinline__ void bin_origin(const MapParams& M, const FastContacts& F, int b, int& x0, int& y0) {
+    const int by = b / F.nbx, bx = b - by * F.nbx;
+    x0 = max(0, min(bx * F.bsx - F.margin, M.W - M.tile_w)) & ~1;        // W - tile_w is even when the lean path is on
+    y0 = max(0, min(by * F.bsy - F.margin, M.H - M.tile_h));
+}
+
+// project (optional) + which bin.  One particle per thread, one 1024-particle index tile per CTA: ranks inside a bin are
+// handed out through a shared-memory histogram, one global atomic per (CTA, non-empty bin).
+template <bool DO_PROJECT>
+__global__ void __launch_bounds__(1024, 1) k_project_bin(const __grid_constant__ FastParams P, int* __restrict__ bin_count,
+                                                         uint2* __restrict__ keys) {
+    __shared__ int hist[MAX_BINS], gbase[MAX_BINS];
+    const WeightCommon& C = P.c; const FastContacts& F = P.fc;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cur = C.sc->cur;
+    for (int b = tid; b < F.nb; b += 1024) hist[b] = 0;
+    __syncthreads();
+    const unsigned long long i = (unsigned long long)blockIdx.x * 1024 + tid;
+    int bin = -1, rank = 0; bool defer = false;
+    if (i < C.n) {
+        double x = C.st.f[cur][F_X][i], y = C.st.f[cur][F_Y][i], zs = C.st.f[cur][F_ZS][i];
+        if (DO_PROJECT) {
+            double th = C.st.f[cur][F_TH][i], z = C.st.f[cur][F_Z][i], w = C.st.f[cur][F_W][i];
+            const double spread = weighting_function(C.sc->max_weight, 0.0, C.mp.spread_thr, 0.0);   // :194
+            project_particle(C, C.base + i, spread, x, y, th, z, zs, w);
+            C.st.f[cur][F_X][i] = x; C.st.f[cur][F_Y][i] = y; C.st.f[cur][F_TH][i] = th;
+            C.st.f[cur][F_Z][i] = z; C.st.f[cur][F_ZS][i] = zs; C.st.f[cur][F_W][i] = w;   // everything project changed
+        }
+        const double mv = zs * zs + C.mp.merr2;                          // :290 (zero or out of range: generic kernel)
+        // the particle's own cell (grid-relative fixed point, 18 fractional bits; may be off by one cell: the margin
+        // has room for that), its bin, and whether its footprint is inside that bin's tile
+        const uint64_t ux = em::d2u(em::fma_(x, C.map.inv_sx, C.map.c0x)), uy = em::d2u(em::fma_(y, C.map.inv_sy, C.map.c0y));
+        const int cx = (int)(uint32_t)ux >> IDX_FRAC_BITS, cy = (int)(uint32_t)uy >> IDX_FRAC_BITS;
+        bool ok = (((uint32_t)(ux >> 32) - 0x4217FFFFu) <= 1u) & (((uint32_t)(uy >> 32) - 0x4217FFFFu) <= 1u) &
+                  ((unsigned)cx < (unsigned)C.map.W) & ((unsigned)cy < (unsigned)C.map.H) &
+                  (((uint32_t)(em::d2u(mv) >> 52) - 923u) < 199u);       // measVar inside rsqrt_core's range
+        if (ok) {
+            const int b = (cy / F.bsy) * F.nbx + cx / F.bsx;
+            int x0, y0; bin_origin(C.map, F, b, x0, y0);
+            ok = ((unsigned)(cx - x0 - F.margin) < (unsigned)(C.map.tile_w - 2 * F.margin)) &
+                 ((unsigned)(cy - y0 - F.margin) < (unsigned)(C.map.tile_h - 2 * F.margin));
+            if (ok) { bin = b; rank = atomicAdd(&hist[b], 1); }
+        }
+        defer = !ok;
+    }
+    // particles the lean kernel cannot take (map border, out of range): the generic kernel's list
+    const unsigned m = __ballot_sync(0xffffffffu, defer);
+    if (m) {
+        unsigned slot = 0;
+        if (lane == (__ffs(m) - 1)) slot = atomicAdd(&C.sc->defer_count, (unsigned)__popc(m));
+        slot = __shfl_sync(0xffffffffu, slot, __ffs(m) - 1);
+        if (defer) C.defer_list[slot + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+    }
+    __syncthreads();
+    for (int b = tid; b < F.nb; b += 1024) { const int c = hist[b]; if (c > 0) gbase[b] = atomicAdd(&bin_count[b], c); }
+    __syncthreads();
+    if (i < C.n) keys[i] = make_uint2((unsigned)bin, bin >= 0 ? (unsigned)(gbase[bin] + rank) : 0u);
+}
+
+// bin-sorted particle list, the offset of every bin in it, and the bin each CTA of the lean kernel starts on
+// (CTA c starts where sorted position c*M/G lies: CTAs per bin in proportion to the bin's particles)
+__global__ void __launch_bounds__(1024, 1) k_bin_scatter(const int* __restrict__ bin_count, int nb, const uint2* __restrict__ keys,
+                                                         unsigned long long n, uint32_t* __restrict__ list, unsigned* __restrict__ bin_offs,
+                                                         int* __restrict__ cta_bin, int n_cta) {
+    __shared__ unsigned offs[MAX_BINS + 1];
+    __shared__ unsigned wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // exclusive scan over the bins (4 consecutive bins per thread)
+    unsigned c[4], lo = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int b = tid * 4 + j; c[j] = b < nb ? (unsigned)bin_count[b] : 0u; lo += c[j]; }
+    unsigned so = lo;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned a = __shfl_up_sync(0xffffffffu, so, o); if (lane >= o) so += a; }
+    if (lane == 31) wsum[warp] = so;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned a = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned x = __shfl_up_sync(0xffffffffu, a, o); if (lane >= o) a += x; }
+        wsum[lane] = a;
+    }
+    __syncthreads();
+    unsigned eo = so - lo + (warp ? wsum[warp - 1] : 0u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { offs[tid * 4 + j] = eo; eo += c[j]; }
+    if (tid == 1023) offs[MAX_BINS] = eo;
+    __syncthreads();
+    const unsigned long long i = (unsigned long long)blockIdx.x * 1024 + tid;
+    if (i < n) { const uint2 k = keys[i]; if ((int)k.x >= 0) list[offs[k.x] + k.y] = (uint32_t)i; }
+    if (blockIdx.x == 0) {
+        for (int b = tid; b < nb; b += 1024) bin_offs[b] = offs[b];
+        const unsigned M = offs[MAX_BINS];
+        if (tid < n_cta) {
+            const unsigned p = (unsigned)(((unsigned long long)tid * M) / (unsigned)n_cta);
+            int lo_b = 0, hi_b = nb;                      // last bin whose offset is <= p: it holds p when it is not empty
+            while (hi_b - lo_b > 1) { const int mid = (lo_b + hi_b) >> 1; if (offs[mid] <= p) lo_b = mid; else hi_b = mid; }
+            cta_bin[tid] = lo_b;
+        }
+    }
+}
+
+// h(t) outside the table (|t| >= 10): kept out of line, it is never on a hot path
+__device__ __noinline__ double h_slow_call(double t) { return em::h_slow(t); }
+
+// shared-memory reads by 32-bit shared address (pure: the staged data do not change while they are read, so the
+// compiler may schedule these freely)
+__device__ __forceinline__ void lds_f64x2(uint32_t sa, double& a, double& b) { asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(sa)); }
+__device__ __forceinline__ void lds_f32x4(uint32_t sa, float& a, float& b, float& c, float& d) {
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(sa));
+}
+__device__ __forceinline__ double lds_f64(uint32_t sa) { double a; asm("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(sa)); return a; }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t sa) { float2 v; asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(sa)); return v; }
+
+struct LeanTile { uint32_t sa; int w, x0, y0; double c0x, c0y; };
+
+// EXACT == false: the lean decisions; returns false when one of them was too close to its threshold to be trusted.
+// EXACT == true: every decision as contact_eval takes it (cell index through the IEEE division, the gate as
+// d^2 < 9 zvar); always returns true.  Everything that reaches the result is the same arithmetic in both.
+template <bool EXACT, int UNROLL>
+__device__ __forceinline__ bool lean_eval(const FastContacts& F, const MapParams& M, const LeanTile& T,
+                                          uint32_t htab_sa, double inv_corr, double x, double y, double s, double c,
+                                          double z, double mv, PoseEval& out) {
+    const double axx = c * M.inv_sx, axy = -s * M.inv_sx, ayx = s * M.inv_sy, ayy = c * M.inv_sy;
+    const double ucx = em::fma_(x, M.inv_sx, T.c0x), ucy = em::fma_(y, M.inv_sy, T.c0y);
     const uint32_t gate_lo = F.gate_lo;
     // Flags as integers (no loop-carried predicates): pass = -1 while every evaluated contact since the last reset was
     // inside the gate (gvalid of :135,:189-190: once a contact misses, nothing is used until the next reset); n_used
     // counts the contacts used since the last reset (valid of :134,:185 == n_used > 0).  border_min / gate_min keep the
-    // minimum distance of any decision from its threshold; both are examined once, after the loop.
+    // minimum distance of any lean decision from its threshold; both are examined once, after the loop.
     int pass = -1, n_used = 0;
     uint32_t border_min = 0xFFFFFFFFu, gate_min = 0xFFFFFFFFu;
     double acc_d = 0, acc_v = 0, acc_r = 0;
@@ -614,112 +744,178 @@ __device__ __forceinline__ bool fast_eval(const FastContacts& F, const double* f
 #pragma unroll 1
     for (int g = 0; g < ng; ++g) {
         const int e = F.gend[g];
-#pragma unroll 2
+#pragma unroll UNROLL
         for (; i < e; ++i) {
-            const double2 pxy = *reinterpret_cast<const double2*>(fcs + 4 * i);
-            const double pzr = fcs[4 * i + 2];
-            const uint64_t ux = em::d2u(em::fma_(axx, pxy.x, em::fma_(axy, pxy.y, ucx)));
-            const uint64_t uy = em::d2u(em::fma_(ayx, pxy.x, em::fma_(ayy, pxy.y, ucy)));
-            const uint32_t kx = (uint32_t)ux, ky = (uint32_t)uy;
-            // (k + 4) << 8 drops the cell bits: below 8 << 8 when the fraction is within 4/2^24 of a cell border
-            border_min = min(border_min, min(kx * 256u + 1024u, ky * 256u + 1024u));
-            const uint32_t cell_sa = tile_sa + ((ky >> 24) * (uint32_t)tile_w + (kx >> 24)) * 8u;
-            float2 cell;
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(cell.x), "=f"(cell.y) : "r"(cell_sa));
-            const double d = (z + pzr) - (double)cell.x;                 // :147,:160
-            const double zvar = em::fma_((double)cell.y, (double)cell.y, mv);   // :166-167
-            const double qc = em::rsqrt_core(zvar) * inv_corr;           // 1 / (sigma corr)  :109,:170
-            const double t = d * qc;
-            const uint32_t dlt = ((uint32_t)(em::d2u(t) >> 32) & 0x7FFFFFFFu) - gate_lo;   // < 0: inside the gate
-            gate_min = min(gate_min, dlt);                               // NaN cells (empty): |t| high word >= 0x7FF00000, a miss
-            pass &= (int)dlt >> 31;                                      // use = gvalid && inside; gvalid = use  :154,:189-190
+            const double px = F.px[i], py = F.py[i];                     // warp-uniform: constant bank, not the shared-memory pipe
+            const double wz = z + F.pzr[i];                              // :147
+            double d, zvar, ratio; int inside;
+            if (!EXACT) {
+                const uint64_t ux = em::d2u(em::fma_(axx, px, em::fma_(axy, py, ucx)));
+                const uint64_t uy = em::d2u(em::fma_(ayx, px, em::fma_(ayy, py, ucy)));
+                const uint32_t kx = (uint32_t)ux, ky = (uint32_t)uy;
+                // (k + 4) << 8 drops the cell bits: below 8 << 8 when the fraction is within 4/2^24 of a cell border
+                border_min = min(border_min, min(kx * 256u + 1024u, ky * 256u + 1024u));
+                const float2 cell = lds_f32x2(T.sa + ((ky >> 24) * (uint32_t)T.w + (kx >> 24)) * 8u);
+                d = wz - (double)cell.x;                                 // :160
+                zvar = em::fma_((double)cell.y, (double)cell.y, mv);     // :166-167
+                const double qc = em::rsqrt_core(zvar) * inv_corr;       // 1 / (sigma corr)  :109,:170
+                const double t = d * qc;
+                const uint32_t dlt = ((uint32_t)(em::d2u(t) >> 32) & 0x7FFFFFFFu) - gate_lo;   // < 0: inside the gate
+                gate_min = min(gate_min, dlt);                           // NaN cells (empty): |t| high word >= 0x7FF00000, a miss
+                inside = (int)dlt >> 31;
+                uint32_t j; double zc; em::h_index(t, j, zc);
+                double c0, c1; float c2, c3, c4, c5;
+                lds_f64x2(htab_sa + 16u * j, c0, c1); lds_f32x4(htab_sa + 16u * (ESLAM_H_NINT + j), c2, c3, c4, c5);
+                ratio = em::h_poly(zc, c0, c1, c2, c3, c4, c5) * qc;     // :111-112
+            } else {
+                const double wx = em::fma_(c, px, em::fma_(-s, py, x));  // :147
+                const double wy = em::fma_(s, px, em::fma_(c, py, y));
+                int ix = 0, iy = 0;
+                bool inb = em::cell_index_exact(wx, M.ox, M.sx, M.W, ix);
+                if (inb) inb = em::cell_index_exact(wy, M.oy, M.sy, M.H, iy);
+                const unsigned lx = (unsigned)(ix - T.x0), ly = (unsigned)(iy - T.y0);
+                inb = inb & (lx < (unsigned)M.tile_w) & (ly < (unsigned)M.tile_h);   // always true for a binned particle
+                float2 cl = make_float2(0.f, 0.f);
+                if (inb) cl = lds_f32x2(T.sa + (ly * (unsigned)M.tile_w + lx) * 8u);
+                d = wz - (double)cl.x;
+                zvar = em::fma_((double)cl.y, (double)cl.y, mv);
+                const bool hit = inb & (cl.x == cl.x) & (cl.y == cl.y) & (d * d < 9.0 * zvar);
+                ratio = 0.0;
+                if (hit) {                                               // em::likelihood_ratio
+                    const double q2 = (em::rsqrt_in_range(zvar) ? em::rsqrt_core(zvar) : 1.0 / em::sqrt_(zvar)) * inv_corr;
+                    const double t2 = d * q2;
+                    double hv;
+                    if (em::h_in_range(t2)) {
+                        uint32_t j; double zc; em::h_index(t2, j, zc);
+                        double c0, c1; float c2, c3, c4, c5;
+                        lds_f64x2(htab_sa + 16u * j, c0, c1); lds_f32x4(htab_sa + 16u * (ESLAM_H_NINT + j), c2, c3, c4, c5);
+                        hv = em::h_poly(zc, c0, c1, c2, c3, c4, c5);
+                    } else hv = h_slow_call(t2);
+                    ratio = hv * q2;
+                }
+                inside = hit ? -1 : 0;
+            }
+            pass &= inside;                                              // use = gvalid && hit; gvalid = use  :154,:189-190
             n_used -= pass;                                              // :185
-            const double ratio = em::h_core(t, htab) * qc;               // :111-112
             // :172-184, unconditionally: once a contact of the group has missed (pass == 0) the group can no longer be
             // pushed (:199 needs gvalid) and the sums are cleared or never read again, so what they hold does not matter
             acc_d = em::fma_(d, ratio, acc_d); acc_v = em::fma_(zvar, ratio, acc_v); acc_r += ratio;
         }
         if (n_used > 0) {                                                // :194-197 (the group's last evaluated point)
             if (pass && acc_r > 1e-9) {                                  // :199
-                const double zd = acc_d / acc_r, zv = acc_v / acc_r;     // :201-202
+                const double ir = 1.0 / acc_r;
+                const double zd = acc_d * ir, zv = acc_v * ir;           // :201-202
                 out.poseVar += zv - mv;                                  // :203
-                const double q = zd / zv;
-                out.d1 += q; out.d2 += 1.0 / zv; out.A = em::fma_(zd, q, out.A);
+                const double iv = 1.0 / zv;
+                const double q = zd * iv;
+                out.d1 += q; out.d2 += iv; out.A = em::fma_(zd, q, out.A);
                 out.n_found++;
             }
             pass = -1; n_used = 0;                                       // :210-213 (only when valid: Q4)
             acc_d = acc_v = acc_r = 0;
         }
     }
-    // an index or gate decision too close to its threshold: the generic kernel decides (a decision taken while the group
-    // was already invalid cannot matter, but is sent over as well: it is rare)
-    return border_min >= 2048u && gate_min > F.gate_span;
+    // a decision taken while the group was already invalid cannot matter but is counted as well: it is rare
+    return EXACT || (border_min >= 2048u && gate_min > F.gate_span);
 }
 
-template <bool DO_PROJECT, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) k_weight_fast(const __grid_constant__ FastParams P) {
+// the whole particle again with exact decisions (~2e-4 of the particles); out of line so that it costs the lean loop no registers
+__device__ __noinline__ void lean_redo_exact(const FastParams* P, const LeanTile* T, uint32_t htab_sa, int cur,
+                                             unsigned long long i, PoseEval* out) {
+    const WeightCommon& C = P->c;
+    const double x = C.st.f[cur][F_X][i], y = C.st.f[cur][F_Y][i], th = C.st.f[cur][F_TH][i];
+    const double z = C.st.f[cur][F_Z][i], zs = C.st.f[cur][F_ZS][i];
+    double s, c; em::sincos_(th, s, c);
+    lean_eval<true, 1>(P->fc, C.map, *T, htab_sa, C.mp.inv_corr, x, y, s, c, z, zs * zs + C.mp.merr2, *out);
+}
+
+// Work distribution: a chunk is 32 consecutive entries of a bin's list.  Every CTA works on one bin at a time (its tile
+// is what the CTA has in shared memory); its warps pull chunks from the bin's global counter, so all CTAs on a bin finish
+// it together.  A CTA whose bin is exhausted joins the bin with the most chunks left (restaging the tile) or exits.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_weight_lean(const __grid_constant__ FastParams P, const uint32_t* __restrict__ list,
+                                                            const int* __restrict__ bin_count, const unsigned* __restrict__ bin_offs,
+                                                            unsigned* __restrict__ bin_next, const int* __restrict__ cta_bin) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const WeightCommon& C = P.c;
-    const em::dbl2* htab = reinterpret_cast<const em::dbl2*>(smem_raw);
-    double* fcs = reinterpret_cast<double*>(smem_raw + HTAB_BYTES);
-    double* red = reinterpret_cast<double*>(smem_raw + HTAB_BYTES + WT_CONTACT_BYTES);
+    em::dbl2* htab = reinterpret_cast<em::dbl2*>(smem_raw);
+    const uint32_t htab_sa = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t mbar = htab_sa + HTAB_BYTES + WT_CONTACT_BYTES + 512;
+    int* s_pick = reinterpret_cast<int*>(smem_raw + HTAB_BYTES + WT_CONTACT_BYTES);          // [0] best remaining, [1] its bin, [2] the chunk claimed for the CTA (-1: none)
+    float2* tile = reinterpret_cast<float2*>(smem_raw + WT_HEAD_BYTES);
     const int tid = threadIdx.x, lane = tid & 31;
-    const DevScalars* sc = C.sc;
-    const int cur = sc->cur;
-    for (int i = tid; i < P.fc.n_eval; i += THREADS) {
-        fcs[4 * i] = P.fc.px[i]; fcs[4 * i + 1] = P.fc.py[i]; fcs[4 * i + 2] = P.fc.pzr[i]; fcs[4 * i + 3] = 0.0;
-    }
-    const MapTile mt = stage_tile_and_table(C.map, C.use_tma, C.tmap, C.htab, smem_raw);   // ends with a barrier
-    const uint32_t tile_sa = (uint32_t)__cvta_generic_to_shared(mt.s);
-    double spread = 0.0;
-    if (DO_PROJECT) spread = weighting_function(sc->max_weight, 0.0, C.mp.spread_thr, 0.0);   // :194
-
-    double* X = C.st.f[cur][F_X]; double* Y = C.st.f[cur][F_Y]; double* TH = C.st.f[cur][F_TH];
-    double* Z = C.st.f[cur][F_Z]; double* ZS = C.st.f[cur][F_ZS]; double* WG = C.st.f[cur][F_W];
-    const unsigned long long n_chunks = (C.n + 31) >> 5;
-    const uint32_t margin = (uint32_t)P.fc.margin;
-    const uint32_t span_x = (uint32_t)max(mt.w - 2 * P.fc.margin, 0), span_y = (uint32_t)max(mt.h - 2 * P.fc.margin, 0);
-    double hx = 0, hy = 0;
-    for (unsigned long long ch = first_chunk(); ch < n_chunks; ch += chunk_stride()) {
-        const unsigned long long i = (ch << 5) + lane;
-        bool defer = false;
-        if (i < C.n) {
-            double x = X[i], y = Y[i], th = TH[i], z = Z[i], zs = ZS[i], w = WG[i];
-            if (DO_PROJECT) {
-                project_particle(C, C.base + i, spread, x, y, th, z, zs, w);
-                X[i] = x; Y[i] = y; TH[i] = th; Z[i] = z; ZS[i] = zs; WG[i] = w;   // everything project changed
+    const int cur = C.sc->cur;
+    const int nb = P.fc.nb;
+    for (int i = tid; i < ESLAM_H_TABLE_ENTRIES; i += THREADS) htab[i] = C.htab[i];
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    LeanTile T; T.sa = (uint32_t)__cvta_generic_to_shared(tile); T.w = C.map.tile_w; T.x0 = 0; T.y0 = 0; T.c0x = 0; T.c0y = 0;
+    int bin = cta_bin[blockIdx.x];
+    uint32_t phase = 0;
+    while (true) {
+        const unsigned cnt = (unsigned)bin_count[bin], nch = (cnt + 31u) >> 5, base = bin_offs[bin];
+        // one thread claims a first chunk for the CTA: the tile is only staged when there really is work left
+        if (tid == 0) { const unsigned c0 = atomicAdd(&bin_next[bin], 1u); s_pick[2] = c0 < nch ? (int)c0 : -1; }
+        __syncthreads();
+        const int first = s_pick[2];
+        if (first >= 0) {
+            bin_origin(C.map, P.fc, bin, T.x0, T.y0);
+            T.c0x = P.fc.c0x - (double)T.x0; T.c0y = P.fc.c0y - (double)T.y0;   // exact
+            if (C.use_tma) {
+                if (tid == 0) {
+                    mbar_expect_tx(mbar, (uint32_t)(C.map.tile_w * C.map.tile_h) * (uint32_t)sizeof(float2));
+                    tma_load_2d(T.sa, C.tmap, mbar, T.x0, T.y0);
+                }
+                mbar_wait(mbar, phase); phase ^= 1u;
+            } else {
+                const int cells = C.map.tile_w * C.map.tile_h;
+                for (int i = tid; i < cells; i += THREADS) {
+                    const int rr = i / C.map.tile_w, cc = i - rr * C.map.tile_w;
+                    tile[i] = __ldg(&C.map.cells[(size_t)(T.y0 + rr) * C.map.W + T.x0 + cc]);
+                }
+                __syncthreads();
             }
-            hx += x; hy += y;
-            double s, c; em::sincos_(th, s, c);                          // :279-282
-            const double zs2 = zs * zs;
-            const double mv = zs2 + C.mp.merr2;                          // :290
-            if (mv == 0) atomicOr(&C.sc->error_flags, ERR_ZERO_VARIANCE_BIT);   // src/ContactModel.cpp:122-123
-            // interior: the particle's own cell (tile-relative, 24-bit fraction fixed point) at least `margin` cells
-            // inside the tile on every side, the quotient inside the fixed-point range, measVar inside rsqrt_core's range
-            const uint64_t ucx = em::d2u(em::fma_(x, C.map.inv_sx, P.fc.c0x)), ucy = em::d2u(em::fma_(y, C.map.inv_sy, P.fc.c0y));
-            const bool interior = ((uint32_t)(ucx >> 32) == 0x41B80000u) & ((uint32_t)(ucy >> 32) == 0x41B80000u) &
-                                  ((((uint32_t)ucx >> 24) - margin) < span_x) & ((((uint32_t)ucy >> 24) - margin) < span_y) &
-                                  (((uint32_t)(em::d2u(mv) >> 52) - 923u) < 199u);
-            defer = true;
-            if (interior) {
-                PoseEval ev;
-                if (fast_eval(P.fc, fcs, tile_sa, mt.w, htab, C.map.inv_sx, C.map.inv_sy, C.mp.inv_corr, em::u2d(ucx), em::u2d(ucy),
-                              s, c, z, mv, ev)) {
-                    finish_particle(C, cur, i, ev, z, zs2, w);
-                    defer = false;
+            bool have_first = tid < 32;                                  // warp 0 starts with the claimed chunk
+            while (true) {
+                unsigned ch = (unsigned)first;
+                if (!have_first) {
+                    if (lane == 0) ch = atomicAdd(&bin_next[bin], 1u);
+                    ch = __shfl_sync(0xffffffffu, ch, 0);
+                }
+                have_first = false;
+                if (ch >= nch) break;
+                const unsigned k = (ch << 5) + lane;
+                if (k < cnt) {
+                    const unsigned long long i = list[base + k];
+                    const double z = C.st.f[cur][F_Z][i], zs = C.st.f[cur][F_ZS][i];
+                    const double zs2 = zs * zs;
+                    PoseEval ev;
+                    {
+                        const double x = C.st.f[cur][F_X][i], y = C.st.f[cur][F_Y][i], th = C.st.f[cur][F_TH][i];
+                        double s, c; em::sincos_(th, s, c);              // :279-282
+                        if (!lean_eval<false, 2>(P.fc, C.map, T, htab_sa, C.mp.inv_corr, x, y, s, c, z, zs2 + C.mp.merr2 /* :290 */, ev))
+                            lean_redo_exact(&P, &T, htab_sa, cur, i, &ev);
+                    }
+                    finish_particle(C, cur, i, ev, z, zs2, C.st.f[cur][F_W][i]);
                 }
             }
         }
-        // hand the undecided particles to the generic kernel (warp-aggregated append)
-        const unsigned m = __ballot_sync(0xffffffffu, defer);
-        if (m) {
-            unsigned slot = 0;
-            if (lane == (__ffs(m) - 1)) slot = atomicAdd(&C.sc->defer_count, (unsigned)__popc(m));
-            slot = __shfl_sync(0xffffffffu, slot, __ffs(m) - 1);
-            if (defer) C.defer_list[slot + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+        // everyone is done with this tile; pick the bin with the most chunks left
+        if (tid == 0) { s_pick[0] = 0; s_pick[1] = -1; }
+        __syncthreads();
+        int best = 0, best_bin = -1;
+        for (int b = tid; b < nb; b += THREADS) {
+            const int left = (int)(((unsigned)bin_count[b] + 31u) >> 5) - (int)min(bin_next[b], 0x7FFFFFFFu);
+            if (left > best) { best = left; best_bin = b; }
         }
+        if (best > 0) atomicMax(&s_pick[0], best);
+        __syncthreads();
+        if (best > 0 && best == s_pick[0]) s_pick[1] = best_bin;         // any of the ties
+        __syncthreads();
+        bin = s_pick[1];
+        if (bin < 0) break;
+        __syncthreads();
     }
-    write_hint(hx, hy, red, C.hint);
 }
 
 // ---- the generic path ---------------------------------------------------------------------------------------------
@@ -758,7 +954,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_c
             double s, c; em::sincos_(th, s, c);
             const double zs2 = zs * zs;
             const double mv = zs2 + P.mp.merr2;                                  // :290
-            if (!LIST && mv == 0) atomicOr(&P.sc->error_flags, ERR_ZERO_VARIANCE_BIT);   // src/ContactModel.cpp:122-123
+            if (mv == 0) atomicOr(&P.sc->error_flags, ERR_ZERO_VARIANCE_BIT);   // src/ContactModel.cpp:122-123
             PoseEval ev;
             PatchRef pr; pr.cells = nullptr; pr.ox = INT_MIN; pr.oy = 0; pr.P = 0;
             CpRec rec;
@@ -825,7 +1021,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_part(StateBufs st, const 
 // floating_weight (:329), max_weight (:305, :347-348), the loop-B power table, next step's map tile centre
 __global__ void __launch_bounds__(1024, 1) k_reduce_a(const TilePartA* part, unsigned n_tiles, unsigned long long n_local,
                                                       DevScalars* sc, double* scratch_a, double* scratch_b,
-                                                      double discount, const double* hint, unsigned n_hint) {
+                                                      double discount, const double* hint, unsigned n_hint, int* bin_count,
+                                                      unsigned* bin_next) {
+    for (int b = threadIdx.x; b < MAX_BINS; b += blockDim.x) { bin_count[b] = 0; bin_next[b] = 0; }   // for the next update's lean path
     __shared__ double red[32];
     __shared__ unsigned long long redull[64];
     __shared__ double tree_a[TREE_SMEM], tree_b[TREE_SMEM / 2];

@@ -260,16 +260,19 @@ ESLAM_HD void box_muller(double u1, double u2, double& n0, double& n1) {
 // (cubic: residual 5/16 (2 * 4.7e-6)^3 = 3e-16).
 // rsqrt_core is valid for x in [2^-100, 2^100); rsqrt_ adds the out-of-range fallback.
 ESLAM_HD double rsqrt_core(double x) {
-    float xf = (float)x;
-    float y = u2f(0x5f3759dfu - (f2u(xf) >> 1));
-    float hx = 0.5f * xf;
+    // x -> float by bit moves (exponent rebias 1023 -> 127, top 23 mantissa bits: truncation) and the float result ->
+    // double by bit moves (exact): both stay off the conversion unit, which is the scarcest pipe of the lean kernel
+    const uint32_t xb = (uint32_t)(d2u(x) >> 29) - (896u << 23);
+    const float xf = u2f(xb);
+    float y = u2f(0x5f3759dfu - (xb >> 1));
+    const float hx = 0.5f * xf;
     float t;
     t = y * y; t = fmaf_(-hx, t, 1.5f); y = y * t;
     t = y * y; t = fmaf_(-hx, t, 1.5f); y = y * t;
-    double yd = (double)y;
-    double h = x * yd;
-    double e = fma_(-h, yd, 1.0);
-    double p = fma_(0.375, e, 0.5);
+    const double yd = u2d(((uint64_t)f2u(y) << 29) + (896ull << 52));
+    const double h = x * yd;
+    const double e = fma_(-h, yd, 1.0);
+    const double p = fma_(0.375, e, 0.5);
     return fma_(yd, e * p, yd);
 }
 // 2^-100 <= x < 2^100 (and positive, finite), decided on the exponent bits
@@ -283,13 +286,13 @@ ESLAM_HD double rsqrt_(double x) {
 // The reference computes pdf(n,z)/cdf(n,z) with n = Normal(0, sigma*corr)
 // (src/ContactModel.cpp:104-115) = h(z/s)/s, s = sigma*corr.  h is tabulated on
 // [-H_TMAX, H_TMAX] in H_NINT intervals of width 1/H_PER_UNIT (centred on the multiples of 1/H_PER_UNIT) as degree-5
-// polynomials in the centred local coordinate (tools/gen_h_table.py; relative error <= 1e-10 everywhere a contact
+// polynomials (c0, c1 double; c2..c5 float) in the centred local coordinate (tools/gen_h_table.py; relative error <= 1e-10 everywhere a contact
 // can matter, <= 1e-12 for t <= 4).  Layout: tab[q*H_NINT + j] = (c[2q], c[2q+1]) so that
 // neighbouring intervals are neighbouring 16-byte words (shared-memory bank friendly).
 #define ESLAM_H_TMAX 10.0
 #define ESLAM_H_PER_UNIT 32
 #define ESLAM_H_NINT 641
-#define ESLAM_H_TABLE_DOUBLES (ESLAM_H_NINT * 6)
+#define ESLAM_H_TABLE_ENTRIES (ESLAM_H_NINT * 2)   /* 16-byte entries */
 
 struct dbl2 { double x, y; };
 
@@ -312,19 +315,32 @@ ESLAM_HD bool h_in_range(double t) { return fabs(t) < ESLAM_H_TMAX; }
 // m = 32 t + (1.5 2^52 + 320) has rne(32 t) + 320 in its low mantissa word, m - magic = rne(32 t) exactly,
 // z = 32 t - rne(32 t) in [-0.5, 0.5] with a single rounding.  No int<->double conversions.
 #define ESLAM_H_MAGIC 6755399441056064.0   /* 1.5 * 2^52 + 320 */
-ESLAM_HD double h_core(double t, const dbl2* tab) {
+// interval index j (clamped) and centred coordinate z of t
+ESLAM_HD void h_index(double t, uint32_t& j, double& z) {
     const double m = fma_(t, (double)ESLAM_H_PER_UNIT, ESLAM_H_MAGIC);
-    uint32_t j = (uint32_t)d2u(m);
+    j = (uint32_t)d2u(m);
     j = j > (uint32_t)(ESLAM_H_NINT - 1) ? (uint32_t)(ESLAM_H_NINT - 1) : j;   // also catches "negative" (wrapped) indices
-    const double z = fma_(t, (double)ESLAM_H_PER_UNIT, -(m - ESLAM_H_MAGIC));
-    const dbl2 c01 = tab[j], c23 = tab[ESLAM_H_NINT + j], c45 = tab[2 * ESLAM_H_NINT + j];
-    double p = c45.y;
-    p = fma_(p, z, c45.x);
-    p = fma_(p, z, c23.y);
-    p = fma_(p, z, c23.x);
-    p = fma_(p, z, c01.y);
-    p = fma_(p, z, c01.x);
-    return p;
+    z = fma_(t, (double)ESLAM_H_PER_UNIT, -(m - ESLAM_H_MAGIC));
+}
+// c0 + c1 z + z^2 q(z), q = c2 + c3 z + c4 z^2 + c5 z^3 evaluated in fp32: with |z| <= 1/2 and intervals 1/32 wide the
+// z^2 q term is below 1e-2 of the value, so its fp32 rounding (6e-8) stays below 1e-9 relative (tests/test_math.py).
+// The shared-memory table is what bounds the lean kernel: 32 bytes per lookup instead of 48.
+ESLAM_HD double h_poly(double z, double c0, double c1, float c2, float c3, float c4, float c5) {
+    const float zf = (float)z;
+    const float q = fmaf_(fmaf_(fmaf_(c5, zf, c4), zf, c3), zf, c2);
+    return fma_(z * z, (double)q, fma_(c1, z, c0));
+}
+// layout: tab[j] = (c0, c1) as doubles, tab[H_NINT + j] = (c2, c3, c4, c5) as floats in the same 16 bytes
+ESLAM_HD void h_unpack(const dbl2& hi, float& c2, float& c3, float& c4, float& c5) {
+    const uint64_t a = d2u(hi.x), b = d2u(hi.y);
+    c2 = u2f((uint32_t)a); c3 = u2f((uint32_t)(a >> 32)); c4 = u2f((uint32_t)b); c5 = u2f((uint32_t)(b >> 32));
+}
+ESLAM_HD double h_core(double t, const dbl2* tab) {
+    uint32_t j; double z;
+    h_index(t, j, z);
+    const dbl2 c01 = tab[j];
+    float c2, c3, c4, c5; h_unpack(tab[ESLAM_H_NINT + j], c2, c3, c4, c5);
+    return h_poly(z, c01.x, c01.y, c2, c3, c4, c5);
 }
 ESLAM_HD double h_ratio(double t, const dbl2* tab) {
     if (!h_in_range(t)) return h_slow(t);

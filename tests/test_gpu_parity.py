@@ -173,12 +173,9 @@ def test_trajectory_bit_identical_to_shared_oracle(gpu, oracle, workload, steps,
     assert g.getBestParticleIndex() == o.getBestParticleIndex()
 
 
-@pytest.mark.parametrize("threads", ["1024", "512"])
-def test_lean_and_generic_weight_kernels_agree(gpu, monkeypatch, threads):
-    """The lean kernel (footprint inside the shared-memory tile, fused fixed-point cell index, gate on the high word
-    of t) and the generic kernel (exact division, exact gate) must leave bit-identical particles; with a 2 m cloud
-    both take a share of the particles."""
-    monkeypatch.setenv("ESLAM_GPU_FAST_THREADS", threads)
+def test_lean_and_generic_weight_kernels_agree(gpu, monkeypatch):
+    """The lean path (particles binned by map tile, fused fixed-point cell index, gate on the high word of t) and the
+    generic kernel (exact division, exact gate) must leave bit-identical particles."""
     n = 131072
     lean = gpu(abi.default_config(min_effective=n + 1))
     monkeypatch.setenv("ESLAM_GPU_NO_FAST", "1")
@@ -193,7 +190,7 @@ def test_lean_and_generic_weight_kernels_agree(gpu, monkeypatch, threads):
         ra = lean.stepFused(step, contacts)
         assert ra.as_dict() == rb.as_dict(), "step %d" % i
         pc, pg = lean.pathCounters(), generic.pathCounters()
-        assert pg["deferred"] == 0 and 0 < pc["deferred"] < n, (pc, pg)
+        assert pg["deferred"] == 0 and pc["deferred"] < n // 100, (pc, pg)
         assert np.array_equal(lean.getAncestors(), generic.getAncestors())
         assert_particles_equal(lean.getParticles(), generic.getParticles())
 

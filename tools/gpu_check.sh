@@ -13,14 +13,11 @@ PY
 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err || { tail -20 gpurun_out/bench.err; exit 1; }
 summ gpurun_out/bench.json
 if [[ "$*" == *sweep* ]]; then
-  for t in 512 1024; do
-    ESLAM_GPU_FAST_THREADS=$t python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_t$t.json 2>> gpurun_out/bench.err && { echo "threads $t"; summ gpurun_out/bench_t$t.json; }
-  done
   ESLAM_GPU_NO_FAST=1 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_nofast.json 2>> gpurun_out/bench.err && { echo "generic only"; summ gpurun_out/bench_nofast.json; }
 fi
 if [[ "$*" == *ncu* ]]; then
   python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:k_weight_fast -s 4 -c 1 -f -o gpurun_out/prof_fast python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_w.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:k_weight_lean -s 4 -c 1 -f -o gpurun_out/prof_lean python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_w.log 2>&1
   python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
-  ncu --metrics gpu__time_duration.sum --clock-control none -s 36 -c 39 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_l.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -s 45 -c 45 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_l.log 2>&1
 fi
