@@ -138,7 +138,8 @@ int eslam_gpu_step_fused(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const e
                          eslam_gpu_update_result* result);
 /* Enqueue `steps` identical fused steps without host synchronisation (benchmark loop; inputs stay
  * resident).  elapsed_ms (may be NULL) = CUDA-event time of the whole region on the context's stream;
- * top_kernel_ms (may be NULL) = summed event time of the fused project+weight kernel alone. */
+ * top_kernel_ms (may be NULL) = summed event time of the dominant kernel alone (k_weight_lean; k_project_weight when
+ * the lean path does not apply). */
 int eslam_gpu_run_steps(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const eslam_gpu_contact* pts, int n_pts,
                         int steps, float* elapsed_ms, float* top_kernel_ms, eslam_gpu_update_result* last_result);
 
@@ -177,8 +178,8 @@ int eslam_gpu_synchronize(eslam_gpu_ctx* ctx);
 /* diagnostics of the exact running-sum machinery: out = {sequential-fallback runs, boundary elements of the last
  * resample, pending error flags, resamples done} */
 int eslam_gpu_debug_counters(eslam_gpu_ctx* ctx, uint64_t out[4]);
-/* which weight kernel did the work in the last update: out = {local particles, particles the lean kernel
- * (footprint inside the shared-memory map tile, every decision safely away from its threshold) handed to the generic one} */
+/* which weight kernel did the work in the last update: out = {particles binned for the lean kernel (0: the update
+ * ran on the generic kernel alone), particles evaluated by the generic kernel (map border, out-of-range values)} */
 int eslam_gpu_path_counters(eslam_gpu_ctx* ctx, uint64_t out[2]);
 /* number of kernels this library has launched on ctx since creation (bench "gpu_launches") */
 uint64_t eslam_gpu_launch_count(const eslam_gpu_ctx* ctx);

@@ -36,6 +36,7 @@ struct eslam_gpu_ctx {
     uint32_t* ancestors; double* cdf;
     uint32_t* defer_list;                         // particles the lean weight kernel hands to the generic one (n entries)
     double* hint; unsigned hint_n;                // per-CTA sums of x, y (tile placement hint), entries written by the last update
+    bool last_lean;                               // the last update went through the lean path
     int lean_threads;                             // CTA size of the lean kernel: 1024 x 64 registers or 512 x 128 (ESLAM_GPU_LEAN_THREADS)
     int* bin_count; uint2* keys; uint32_t* bin_list; unsigned* bin_offs; unsigned* bin_next; int* cta_bin;   // lean path: bins, per-bin lists, chunk counters
     bool grid_sane;                               // every stdev of the grid is NaN or |stdev| < 2^49 (lean path precondition)
@@ -299,6 +300,7 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     ctx->device = device; ctx->launches = 0; ctx->n = ctx->cap = 0; ctx->t_local = ctx->t_global = ctx->t_cap = 0;
     ctx->ancestors = nullptr; ctx->cdf = nullptr; ctx->defer_list = nullptr; ctx->hint = nullptr; ctx->hint_n = 0;
     ctx->grid_sane = false;
+    ctx->last_lean = false;
     ctx->lean_threads = getenv("ESLAM_GPU_LEAN_THREADS") ? atoi(getenv("ESLAM_GPU_LEAN_THREADS")) : 1024;
     ctx->bin_count = nullptr; ctx->keys = nullptr; ctx->bin_list = nullptr; ctx->bin_offs = nullptr; ctx->bin_next = nullptr; ctx->cta_bin = nullptr;
     for (int b = 0; b < 2; ++b) { ctx->patch[b] = nullptr; ctx->porigin[b] = nullptr; }
@@ -775,10 +777,11 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
     fill_weight_params(ctx, &P, step_or_null, cs);
     const size_t smem = weight_smem_bytes(ctx);
     const unsigned grid = weight_grid(ctx);
-    if (ev0) CK(cudaEventRecord(ev0, ctx->stream));
     const bool patches = ctx->cfg.patch_size > 0;
     static FastParams F;                                                  // large (lists of 128 contacts): not on the stack
-    if (fill_fast_params(ctx, &F, P, *cs)) {
+    const bool lean = fill_fast_params(ctx, &F, P, *cs);
+    if (!lean && ev0) CK(cudaEventRecord(ev0, ctx->stream));
+    if (lean) {
         // bin the particles by map tile, evaluate bin by bin from shared memory; the generic kernel takes what is left
         // (footprints that leave the map, out-of-range values)
         const unsigned T = ctx->t_local;
@@ -787,11 +790,13 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
         LAUNCHED();
         k_bin_scatter<<<T, 1024, 0, ctx->stream>>>(ctx->bin_count, F.fc.nb, ctx->keys, ctx->n, ctx->bin_list, ctx->bin_offs, ctx->cta_bin, ctx->sm_count);
         LAUNCHED();
+        if (ev0) CK(cudaEventRecord(ev0, ctx->stream));                  // the events bracket the dominant kernel alone
         if (ctx->lean_threads == 512)
             k_weight_lean<512><<<(unsigned)ctx->sm_count, 512, smem, ctx->stream>>>(F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin);
         else
             k_weight_lean<1024><<<(unsigned)ctx->sm_count, 1024, smem, ctx->stream>>>(F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin);
         LAUNCHED();
+        if (ev1) CK(cudaEventRecord(ev1, ctx->stream));
         k_project_weight<false, true, false, true><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
         LAUNCHED();
         ctx->hint_n = 0;
@@ -804,8 +809,9 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
         else k_project_weight<false, true, false, false><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
         LAUNCHED();
         ctx->hint_n = grid;
+        if (ev1) CK(cudaEventRecord(ev1, ctx->stream));
     }
-    if (ev1) CK(cudaEventRecord(ev1, ctx->stream));
+    ctx->last_lean = lean;
     k_tile_part<<<ctx->t_local, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->n, ctx->l_part_a);
     LAUNCHED();
     AG(ctx->l_part_a, ctx->g_part_a, ctx->t_local * sizeof(TilePartA));
@@ -1056,7 +1062,7 @@ int eslam_gpu_path_counters(eslam_gpu_ctx* ctx, uint64_t out[2]) {
     if (cudaSetDevice(ctx->device) != cudaSuccess) return ESLAM_ERR_CUDA;
     int st = read_scalars(ctx);
     if (st != ESLAM_OK) return st;
-    out[0] = ctx->n; out[1] = ctx->sc_host->defer_last;
+    out[0] = ctx->last_lean ? ctx->n : 0; out[1] = ctx->last_lean ? ctx->sc_host->defer_last : ctx->n;
     return ESLAM_OK;
 }
 

@@ -103,7 +103,7 @@ struct FastContacts {
     double c0x, c0y;             // 1.5*2^28 - offset/scale: cell quotient with 24 fractional bits (minus the tile origin: tile-relative)
     int bsx, bsy, nbx, nby, nb;  // bins: a lattice of tile cores (tile minus the margin on every side), bsx x bsy cells each
     uint8_t gend[ESLAM_MAX_CONTACTS];   // one past the last evaluated contact of each group (groups without any are dropped)
-    double px[ESLAM_MAX_CONTACTS], py[ESLAM_MAX_CONTACTS], pzr[ESLAM_MAX_CONTACTS];
+    double px[ESLAM_MAX_CONTACTS + 1], py[ESLAM_MAX_CONTACTS + 1], pzr[ESLAM_MAX_CONTACTS + 1];   // [n_eval] = 0: read ahead by the loop
 };
 
 struct WeightCommon {
@@ -740,22 +740,31 @@ __device__ __forceinline__ bool lean_eval(const FastContacts& F, const MapParams
     double acc_d = 0, acc_v = 0, acc_r = 0;
     out.n_found = 0; out.d1 = 0; out.d2 = 0; out.A = 0; out.poseVar = 0;
     const int ng = F.n_groups;
+    // Software pipeline of the lean loop: the cell of contact i+1 is looked up (constant-bank read of the contact, fused
+    // index, shared-memory load) while contact i goes through its dependent chain (1/sqrt, table, sums).  The look-up of
+    // contact n_eval (zeros: the particle's own cell) is issued and dropped.
+    float2 cell_n = make_float2(0.f, 0.f); double wz_n = 0.0;
+    auto look_up = [&](int j) {
+        const double px = F.px[j], py = F.py[j];                         // warp-uniform: constant bank, not the shared-memory pipe
+        wz_n = z + F.pzr[j];                                             // :147
+        const uint64_t ux = em::d2u(em::fma_(axx, px, em::fma_(axy, py, ucx)));
+        const uint64_t uy = em::d2u(em::fma_(ayx, px, em::fma_(ayy, py, ucy)));
+        const uint32_t kx = (uint32_t)ux, ky = (uint32_t)uy;
+        // (k + 4) << 8 drops the cell bits: below 8 << 8 when the fraction is within 4/2^24 of a cell border
+        border_min = min(border_min, min(kx * 256u + 1024u, ky * 256u + 1024u));
+        cell_n = lds_f32x2(T.sa + ((ky >> 24) * (uint32_t)T.w + (kx >> 24)) * 8u);
+    };
     int i = 0;
+    if (!EXACT) look_up(0);
 #pragma unroll 1
     for (int g = 0; g < ng; ++g) {
         const int e = F.gend[g];
 #pragma unroll UNROLL
         for (; i < e; ++i) {
-            const double px = F.px[i], py = F.py[i];                     // warp-uniform: constant bank, not the shared-memory pipe
-            const double wz = z + F.pzr[i];                              // :147
             double d, zvar, ratio; int inside;
             if (!EXACT) {
-                const uint64_t ux = em::d2u(em::fma_(axx, px, em::fma_(axy, py, ucx)));
-                const uint64_t uy = em::d2u(em::fma_(ayx, px, em::fma_(ayy, py, ucy)));
-                const uint32_t kx = (uint32_t)ux, ky = (uint32_t)uy;
-                // (k + 4) << 8 drops the cell bits: below 8 << 8 when the fraction is within 4/2^24 of a cell border
-                border_min = min(border_min, min(kx * 256u + 1024u, ky * 256u + 1024u));
-                const float2 cell = lds_f32x2(T.sa + ((ky >> 24) * (uint32_t)T.w + (kx >> 24)) * 8u);
+                const float2 cell = cell_n; const double wz = wz_n;
+                look_up(i + 1);
                 d = wz - (double)cell.x;                                 // :160
                 zvar = em::fma_((double)cell.y, (double)cell.y, mv);     // :166-167
                 const double qc = em::rsqrt_core(zvar) * inv_corr;       // 1 / (sigma corr)  :109,:170
@@ -768,7 +777,9 @@ __device__ __forceinline__ bool lean_eval(const FastContacts& F, const MapParams
                 lds_f64x2(htab_sa + 16u * j, c0, c1); lds_f32x4(htab_sa + 16u * (ESLAM_H_NINT + j), c2, c3, c4, c5);
                 ratio = em::h_poly(zc, c0, c1, c2, c3, c4, c5) * qc;     // :111-112
             } else {
-                const double wx = em::fma_(c, px, em::fma_(-s, py, x));  // :147
+                const double px = F.px[i], py = F.py[i];
+                const double wz = z + F.pzr[i];                          // :147
+                const double wx = em::fma_(c, px, em::fma_(-s, py, x));
                 const double wy = em::fma_(s, px, em::fma_(c, py, y));
                 int ix = 0, iy = 0;
                 bool inb = em::cell_index_exact(wx, M.ox, M.sx, M.W, ix);

@@ -219,10 +219,10 @@ class GpuPoseEstimator(FilterBase):
         return dict(fallbacks=int(out[0]), boundaries=int(out[1]), error_flags=int(out[2]), resamples=int(out[3]))
 
     def pathCounters(self):
-        """{particles, deferred}: how many particles of the last update the lean weight kernel handed to the generic one."""
+        """{lean, deferred}: particles binned for the lean weight kernel / evaluated by the generic one in the last update."""
         out = (C.c_uint64 * 2)()
         self._check(self._lib.eslam_gpu_path_counters(self._ctx, out))
-        return dict(particles=int(out[0]), deferred=int(out[1]))
+        return dict(lean=int(out[0]), deferred=int(out[1]))
 
     def launchCount(self):
         return int(self._lib.eslam_gpu_launch_count(self._ctx))

@@ -1,5 +1,6 @@
 """Synthetic terrain, contact points and odometry streams for the configurations of BASELINE.json
 (SURVEY.md §8d).  Inputs only -- nothing here is on the measured path."""
+import functools
 import math
 
 import numpy as np
@@ -7,6 +8,7 @@ import numpy as np
 from . import abi
 
 
+@functools.lru_cache(maxsize=4)
 def make_terrain(width, height, scale=0.05, seed=1234, empty_fraction=0.01):
     """Dense elevation grid: mean = 0.25 sin(2 pi x/5) cos(2 pi y/7) + 0.05 n, stdev = 0.01 + 0.02 u,
     `empty_fraction` of the cells empty (NaN mean).  Returns (cells[h,w,2] float32, scale(2), offset(2))."""

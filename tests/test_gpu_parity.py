@@ -190,7 +190,7 @@ def test_lean_and_generic_weight_kernels_agree(gpu, monkeypatch):
         ra = lean.stepFused(step, contacts)
         assert ra.as_dict() == rb.as_dict(), "step %d" % i
         pc, pg = lean.pathCounters(), generic.pathCounters()
-        assert pg["deferred"] == 0 and pc["deferred"] < n // 100, (pc, pg)
+        assert pg["lean"] == 0 and pg["deferred"] == n and pc["lean"] == n and pc["deferred"] < n // 100, (pc, pg)
         assert np.array_equal(lean.getAncestors(), generic.getAncestors())
         assert_particles_equal(lean.getParticles(), generic.getParticles())
 

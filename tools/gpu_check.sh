@@ -7,7 +7,7 @@ if [[ "$*" == *tests* ]]; then python -m pytest tests -m gpu -x -q 2>&1 | tail -
 summ() { python - "$1" <<'PY'
 import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print("ms/step %.4f  value %.4g  kernel_ms %.4f  step_frac %.4f  e2e_ms %.4f launches %d deferred %s" % (d["ms_per_step"], d["value"], d["roofline"]["kernel_ms"], d["config"]["step_hbm_frac"], d["e2e"]["ms_per_step"], d["gpu_launches"], d["config"].get("deferred_last_step")))
+print("ms/step %.4f  value %.4g  kernel_ms %.4f  step_frac %.4f  e2e_ms %.4f launches %d deferred %s" % (d["ms_per_step"], d["value"], d["roofline"]["kernel_ms"], d["config"]["step_hbm_frac"], d["e2e"]["ms_per_step"], d["gpu_launches"], d["config"].get("generic_path_particles")))
 PY
 }
 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err || { tail -20 gpurun_out/bench.err; exit 1; }

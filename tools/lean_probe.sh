@@ -8,7 +8,7 @@ for t in 1024 512; do
   python - gpurun_out/bench_t$t.json <<'PY'
 import json,sys,os
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print("threads %s: ms/step %.4f kernel_ms %.4f deferred %s" % (os.environ["ESLAM_GPU_LEAN_THREADS"], d["ms_per_step"], d["roofline"]["kernel_ms"], d["config"].get("deferred_last_step")))
+print("threads %s: ms/step %.4f kernel_ms %.4f deferred %s" % (os.environ["ESLAM_GPU_LEAN_THREADS"], d["ms_per_step"], d["roofline"]["kernel_ms"], d["config"].get("generic_path_particles")))
 PY
   ncu --metrics $M --clock-control none -k regex:"k_weight_lean|k_project_bin|k_bin_scatter" -s 9 -c 3 --csv --log-file gpurun_out/probe_t$t.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
   python - gpurun_out/probe_t$t.csv <<'PY'
