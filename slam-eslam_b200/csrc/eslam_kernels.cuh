@@ -857,9 +857,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_weight_lean(const __grid_constan
     const int tid = threadIdx.x, lane = tid & 31;
     const int cur = C.sc->cur;
     const int nb = P.fc.nb;
-    for (int i = tid; i < ESLAM_H_TABLE_ENTRIES; i += THREADS) htab[i] = C.htab[i];
     if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
+    for (int i = tid; i < ESLAM_H_TABLE_ENTRIES; i += THREADS) htab[i] = C.htab[i];   // visible after the barrier below
     LeanTile T; T.sa = (uint32_t)__cvta_generic_to_shared(tile); T.w = C.map.tile_w; T.x0 = 0; T.y0 = 0; T.c0x = 0; T.c0y = 0;
     int bin = cta_bin[blockIdx.x];
     uint32_t phase = 0;
