@@ -11,6 +11,7 @@
 #include <chrono>
 #include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 static const em::dbl2 H_TABLE_HOST[ESLAM_H_TABLE_ENTRIES] = {
@@ -32,10 +33,12 @@ struct eslam_gpu_ctx {
     uint64_t n, cap;
     StateBufs st;
     DevScalars* sc; DevScalars* sc_host;          // sc_host: pinned staging
-    double* tile_hint;                            // pinned {cx, cy}: cloud centre, refreshed asynchronously after every update
+    DevScalars* sc_async;                         // pinned mirror refreshed after every update on a side stream (never waited for)
+    cudaStream_t side; cudaEvent_t side_ev;
     uint32_t* ancestors; double* cdf;
     uint32_t* defer_list;                         // particles the lean weight kernel hands to the generic one (n entries)
     double* hint; unsigned hint_n;                // per-CTA sums of x, y (tile placement hint), entries written by the last update
+    unsigned* ticket;                             // "last CTA" counter of k_resample_local
     bool last_lean;                               // the last update went through the lean path
     int lean_threads;                             // CTA size of the lean kernel: 1024 x 64 registers or 512 x 128 (ESLAM_GPU_LEAN_THREADS)
     int* bin_count; uint2* keys; uint32_t* bin_list; unsigned* bin_offs; unsigned* bin_next; int* cta_bin;   // lean path: bins, per-bin lists, chunk counters
@@ -59,7 +62,45 @@ struct eslam_gpu_ctx {
     int max_smem_optin, sm_count;
     uint32_t project_step;
     std::vector<cudaEvent_t> events;
+    bool use_pdl;                                 // programmatic dependent launch between the kernels of a step (ESLAM_GPU_NO_PDL=1: off)
+    bool timing; std::vector<std::pair<int, cudaEvent_t> > marks; size_t marks_used;
 };
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(eslam_gpu_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+static void timing_mark(eslam_gpu_ctx* ctx, int line) {
+    if (ctx->marks_used == ctx->marks.size()) { cudaEvent_t e; cudaEventCreate(&e); ctx->marks.push_back(std::make_pair(line, e)); }
+    ctx->marks[ctx->marks_used].first = line;
+    cudaEventRecord(ctx->marks[ctx->marks_used].second, ctx->stream);
+    ctx->marks_used++;
+}
+static void timing_report(eslam_gpu_ctx* ctx) {
+    if (!ctx->timing || ctx->marks_used < 2) return;
+    cudaEventSynchronize(ctx->marks[ctx->marks_used - 1].second);
+    std::vector<std::pair<int, std::pair<double, int> > > acc;
+    for (size_t i = 1; i < ctx->marks_used; ++i) {
+        float ms = 0; cudaEventElapsedTime(&ms, ctx->marks[i - 1].second, ctx->marks[i].second);
+        size_t j = 0; for (; j < acc.size(); ++j) if (acc[j].first == ctx->marks[i].first) break;
+        if (j == acc.size()) acc.push_back(std::make_pair(ctx->marks[i].first, std::make_pair(0.0, 0)));
+        acc[j].second.first += ms; acc[j].second.second++;
+    }
+    double tot = 0;
+    for (size_t j = 0; j < acc.size(); ++j) {
+        fprintf(stderr, "[eslam timing] line %4d: %8.2f us x %d\n", acc[j].first, 1e3 * acc[j].second.first / acc[j].second.second, acc[j].second.second);
+        tot += 1e3 * acc[j].second.first / acc[j].second.second;
+    }
+    fprintf(stderr, "[eslam timing] sum of means %.2f us\n", tot);
+    ctx->marks_used = 0;
+}
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -83,8 +124,17 @@ struct eslam_gpu_ctx {
         }                                                                                          \
     } while (0)
 
-#define LAUNCHED() do { ctx->launches++; CK(cudaGetLastError()); } while (0)
+// ESLAM_GPU_TIMING=1: an event after every launch; eslam_gpu_run_steps prints the mean time between consecutive events
+// (kernel + the gap before it) per launch site to stderr.  Development aid; off by default.
+#define LAUNCHED() do { ctx->launches++; CK(cudaGetLastError()); if (ctx->timing) timing_mark(ctx, __LINE__); } while (0)
 
+struct eslam_gpu_ctx;
+static void timing_mark(eslam_gpu_ctx* ctx, int line);
+// Launch with programmatic dependent launch allowed: the kernel's CTAs may be scheduled while the previous kernel of the
+// stream is still draining; every kernel of the step starts with pdl_start() (griddepcontrol.launch_dependents + .wait), so
+// nothing is read before the previous kernel has completed and flushed.  Hides the launch latency of the step's ~13 kernels.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(eslam_gpu_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args);
 template <class T> static cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T)); }
 template <class T> static void dfree(T*& p) { if (p) cudaFree(p); p = nullptr; }
 
@@ -300,7 +350,9 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     ctx->device = device; ctx->launches = 0; ctx->n = ctx->cap = 0; ctx->t_local = ctx->t_global = ctx->t_cap = 0;
     ctx->ancestors = nullptr; ctx->cdf = nullptr; ctx->defer_list = nullptr; ctx->hint = nullptr; ctx->hint_n = 0;
     ctx->grid_sane = false;
-    ctx->last_lean = false;
+    ctx->last_lean = false; ctx->ticket = nullptr;
+    ctx->timing = getenv("ESLAM_GPU_TIMING") != nullptr; ctx->marks_used = 0;
+    ctx->use_pdl = getenv("ESLAM_GPU_NO_PDL") == nullptr;
     ctx->lean_threads = getenv("ESLAM_GPU_LEAN_THREADS") ? atoi(getenv("ESLAM_GPU_LEAN_THREADS")) : 1024;
     ctx->bin_count = nullptr; ctx->keys = nullptr; ctx->bin_list = nullptr; ctx->bin_offs = nullptr; ctx->bin_next = nullptr; ctx->cta_bin = nullptr;
     for (int b = 0; b < 2; ++b) { ctx->patch[b] = nullptr; ctx->porigin[b] = nullptr; }
@@ -323,8 +375,11 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     CK(dalloc(&ctx->sc, 1));
     CK(cudaMemsetAsync(ctx->sc, 0, sizeof(DevScalars), ctx->stream));
     CK(cudaMallocHost((void**)&ctx->sc_host, sizeof(DevScalars)));
-    CK(cudaMallocHost((void**)&ctx->tile_hint, 2 * sizeof(double)));
-    ctx->tile_hint[0] = ctx->tile_hint[1] = 0.0;
+    CK(cudaMallocHost((void**)&ctx->sc_async, sizeof(DevScalars)));
+    memset(ctx->sc_async, 0, sizeof(DevScalars));
+    CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->side_ev, cudaEventDisableTiming));
+    CK(dalloc(&ctx->ticket, 1)); CK(cudaMemsetAsync(ctx->ticket, 0, sizeof(unsigned), ctx->stream));
     CK(dalloc(&ctx->bin_count, (size_t)MAX_BINS)); CK(dalloc(&ctx->bin_offs, (size_t)MAX_BINS)); CK(dalloc(&ctx->bin_next, (size_t)MAX_BINS));
     CK(dalloc(&ctx->cta_bin, (size_t)ctx->sm_count));
     CK(cudaMemsetAsync(ctx->bin_count, 0, MAX_BINS * sizeof(int), ctx->stream));
@@ -346,7 +401,8 @@ void eslam_gpu_destroy(eslam_gpu_ctx* ctx) {
     for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
     free_particles(ctx); free_window(ctx);
     cudaFree(ctx->d_barrier_send); cudaFree(ctx->d_barrier_recv);
-    cudaFree(ctx->sc); cudaFreeHost(ctx->sc_host); cudaFreeHost(ctx->tile_hint); cudaFree(ctx->d_tmap); cudaFree(ctx->htab); cudaFree(ctx->cells); cudaFree(ctx->hint); cudaFree(ctx->bin_count); cudaFree(ctx->bin_offs); cudaFree(ctx->bin_next); cudaFree(ctx->cta_bin);
+    cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); cudaEventDestroy(ctx->side_ev); cudaFreeHost(ctx->sc_async);
+    cudaFree(ctx->sc); cudaFreeHost(ctx->sc_host); cudaFree(ctx->d_tmap); cudaFree(ctx->htab); cudaFree(ctx->cells); cudaFree(ctx->hint); cudaFree(ctx->ticket); cudaFree(ctx->bin_count); cudaFree(ctx->bin_offs); cudaFree(ctx->bin_next); cudaFree(ctx->cta_bin);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -464,7 +520,8 @@ int eslam_gpu_init_gaussian(eslam_gpu_ctx* ctx, uint64_t n, const double mu[3], 
     if (st != ESLAM_OK) return st;
     DevScalars init; memset(&init, 0, sizeof(init));
     init.tile_cx = mu[0]; init.tile_cy = mu[1];
-    ctx->tile_hint[0] = mu[0]; ctx->tile_hint[1] = mu[1];
+    CK(cudaStreamSynchronize(ctx->side));
+    *ctx->sc_async = init;
     *ctx->sc_host = init;
     CK(cudaMemcpyAsync(ctx->sc, ctx->sc_host, sizeof(DevScalars), cudaMemcpyHostToDevice, ctx->stream));
     ctx->project_step = 0;
@@ -527,8 +584,8 @@ int eslam_gpu_get_particles(eslam_gpu_ctx* ctx, double* x, double* y, double* th
 // steps old when steps are enqueued without synchronisation; results do not depend on it).  Inside the grid, x0 even
 // (TMA needs a 16-byte aligned box start for 8-byte cells).
 static void place_tile(const eslam_gpu_ctx* ctx, MapParams* m) {
-    volatile double* hint = ctx->tile_hint;
-    double cx = (hint[0] - ctx->map.ox) * ctx->map.inv_sx, cy = (hint[1] - ctx->map.oy) * ctx->map.inv_sy;
+    volatile DevScalars* as = ctx->sc_async;                          // as of the last update that has reached the host
+    double cx = (as->tile_cx - ctx->map.ox) * ctx->map.inv_sx, cy = (as->tile_cy - ctx->map.oy) * ctx->map.inv_sy;
     if (!(cx > -1e9 && cx < 1e9)) cx = 0;
     if (!(cy > -1e9 && cy < 1e9)) cy = 0;
     const int x0 = (int)cx - m->tile_w / 2, y0 = (int)cy - m->tile_h / 2;
@@ -701,12 +758,12 @@ static int resample_exchange(eslam_gpu_ctx* ctx) {
     for (int f = 0; f < 7; ++f) gs.f[f] = ctx->win_f[f];
     for (int f = 0; f < 2; ++f) gs.b[f] = ctx->win_b[f];
     gs.base = wb[me]; gs.use_window = 1;
-    k_resample<<<blocks, 256, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->win_cdf, ctx->tile_sin + wb[me] / TILE,
+    CK(launch_pdl(ctx, k_resample, blocks, 256, 0, ctx->st, ctx->sc, ctx->win_cdf, ctx->tile_sin + wb[me] / TILE,
                                                 (unsigned)((wlen + TILE - 1) / TILE), wlen, wb[me], n, N, base_index(ctx),
                                                 mp.k0, mp.k1, ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC,
-                                                ctx->ancestors, gs);
+                                                ctx->ancestors, gs));
     LAUNCHED();
-    k_after_resample<<<1, 1, 0, ctx->stream>>>(ctx->sc);
+    CK(launch_pdl(ctx, k_after_resample, 1, 1, 0, ctx->sc));
     LAUNCHED();
     return ESLAM_OK;
 }
@@ -717,26 +774,26 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     const unsigned T = ctx->t_local, TG = ctx->t_global;
     const uint64_t n = ctx->n, ng = global_count(ctx);
     const double eps = scan_eps(ctx);
-    if (apply_loop_b) k_loop_b<true><<<T, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->l_tile_sum);
-    else k_loop_b<false><<<T, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->l_tile_sum);
+    if (apply_loop_b) CK(launch_pdl(ctx, k_loop_b<true>, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, ctx->l_tile_sum));
+    else CK(launch_pdl(ctx, k_loop_b<false>, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, ctx->l_tile_sum));
     LAUNCHED();
     AG(ctx->l_tile_sum, ctx->g_tile_sum, T * sizeof(double));
-    k_reduce_b<<<1, 1024, 0, ctx->stream>>>(ctx->g_tile_sum, TG, ng, ctx->sc, ctx->scratch_a, ctx->scratch_b, ctx->tile_prefix, normalise);
+    CK(launch_pdl(ctx, k_reduce_b, 1, 1024, 0, ctx->g_tile_sum, TG, ng, ctx->sc, ctx->scratch_a, ctx->scratch_b, ctx->tile_prefix, normalise));
     LAUNCHED();
-    k_norm_scan<<<T, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ng, ctx->tile_prefix, ctx->l_tile_sq, ctx->l_desc, ctx->l_pool,
-                                             ctx->sc, normalise, eps, tile_ofs(ctx));
+    CK(launch_pdl(ctx, k_norm_scan, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, ng, ctx->tile_prefix, ctx->l_tile_sq, ctx->l_desc, ctx->l_pool,
+                                             ctx->sc, normalise, eps, tile_ofs(ctx)));
     LAUNCHED();
     AG(ctx->l_tile_sq, ctx->g_tile_sq, T * sizeof(double));
     AG(ctx->l_desc, ctx->g_desc, T * sizeof(TileDesc));
     AG(ctx->l_pool, ctx->g_pool, (size_t)MAX_BND_TOTAL * sizeof(BndEntry));
     const int decide = mode == 0 ? 0 : 1;
-    k_chain<<<1, 1024, sizeof(ChainSmem), ctx->stream>>>(ctx->g_desc, ctx->g_pool, TG, ctx->g_tile_sq, ctx->sc, ctx->scratch_a,
+    CK(launch_pdl(ctx, k_chain, 1, 1024, sizeof(ChainSmem), ctx->g_desc, ctx->g_pool, TG, ctx->g_tile_sq, ctx->sc, ctx->scratch_a,
                                                          ctx->scratch_b, ctx->tile_bofs, ctx->tile_pre, ctx->tile_sin, ctx->sb,
-                                                         mode == 2 ? 0ull : ctx->cfg.min_effective, decide, force, T);
+                                                         mode == 2 ? 0ull : ctx->cfg.min_effective, decide, force, T));
     LAUNCHED();
     if (mode == 2) return ESLAM_OK;
-    k_cdf<<<T, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->tile_prefix, ctx->tile_bofs, ctx->tile_sin, ctx->sb, ctx->cdf, eps,
-                                       tile_ofs(ctx));
+    CK(launch_pdl(ctx, k_cdf, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, ctx->tile_prefix, ctx->tile_bofs, ctx->tile_sin, ctx->sb, ctx->cdf, eps,
+                                       tile_ofs(ctx)));
     LAUNCHED();
     if (sharded(ctx) && ctx->has_peers) {
         // all ranks must have finished their k_cdf before anyone reads running sums / state through peer pointers:
@@ -744,29 +801,37 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
         // still being read from being overwritten)
         AG(ctx->d_barrier_send, ctx->d_barrier_recv, sizeof(int));
         const ModelParams mp = model_params(ctx);
-        k_resample_p2p<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->tile_sin, TG, T, n, ng, base_index(ctx),
+        CK(launch_pdl(ctx, k_resample_p2p, (unsigned)((n + 255) / 256), 256, 0, ctx->st, ctx->sc, ctx->tile_sin, TG, T, n, ng, base_index(ctx),
                                                                             mp.k0, mp.k1, ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC,
-                                                                            ctx->ancestors, ctx->peers);
+                                                                            ctx->ancestors, ctx->peers));
         LAUNCHED();
-        k_after_resample<<<1, 1, 0, ctx->stream>>>(ctx->sc);
+        CK(launch_pdl(ctx, k_after_resample, 1, 1, 0, ctx->sc));
         LAUNCHED();
         return ESLAM_OK;
     }
     if (sharded(ctx)) return resample_exchange(ctx);
-    k_cdf_sequential<<<1, 1, 0, ctx->stream>>>(ctx->st, ctx->sc, n, ctx->cdf, ctx->tile_sin);
+    CK(launch_pdl(ctx, k_cdf_sequential, 1, 1, 0, ctx->st, ctx->sc, n, ctx->cdf, ctx->tile_sin));
     LAUNCHED();
     const ModelParams mp = model_params(ctx);
+    if (ctx->cfg.patch_size <= 0 && !getenv("ESLAM_GPU_NO_LOCAL_RESAMPLE")) {
+        // search in shared memory, copy and buffer swap in one kernel
+        CK(launch_pdl(ctx, k_resample_local, (unsigned)((n + 1023) / 1024), 1024, 0, ctx->st, ctx->sc, ctx->cdf, ctx->tile_sin, T, n, mp.k0, mp.k1,
+                                                                              ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC,
+                                                                              ctx->ancestors, ctx->ticket));
+        LAUNCHED();
+        return ESLAM_OK;
+    }
     const unsigned blocks = (unsigned)((n + 255) / 256);
     GatherSrc gs; memset(&gs, 0, sizeof(gs));
-    k_resample<<<blocks, 256, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->cdf, ctx->tile_sin, T, n, 0, n, ng, 0, mp.k0, mp.k1,
-                                                ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC, ctx->ancestors, gs);
+    CK(launch_pdl(ctx, k_resample, blocks, 256, 0, ctx->st, ctx->sc, ctx->cdf, ctx->tile_sin, T, n, 0, n, ng, 0, mp.k0, mp.k1,
+                                                ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC, ctx->ancestors, gs));
     LAUNCHED();
     if (ctx->cfg.patch_size > 0) {
-        k_gather_patches<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->sc, n, ctx->ancestors, ctx->cfg.patch_size,
-                                                                                  ctx->patch[0], ctx->patch[1], ctx->porigin[0], ctx->porigin[1]);
+        CK(launch_pdl(ctx, k_gather_patches, (unsigned)((n * 32 + 255) / 256), 256, 0, ctx->sc, n, ctx->ancestors, ctx->cfg.patch_size,
+                                                                                  ctx->patch[0], ctx->patch[1], ctx->porigin[0], ctx->porigin[1]));
         LAUNCHED();
     }
-    k_after_resample<<<1, 1, 0, ctx->stream>>>(ctx->sc);
+    CK(launch_pdl(ctx, k_after_resample, 1, 1, 0, ctx->sc));
     LAUNCHED();
     return ESLAM_OK;
 }
@@ -785,40 +850,47 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
         // bin the particles by map tile, evaluate bin by bin from shared memory; the generic kernel takes what is left
         // (footprints that leave the map, out-of-range values)
         const unsigned T = ctx->t_local;
-        if (step_or_null) { k_project_bin<true><<<T, 1024, 0, ctx->stream>>>(F, ctx->bin_count, ctx->keys); ctx->project_step++; }
-        else k_project_bin<false><<<T, 1024, 0, ctx->stream>>>(F, ctx->bin_count, ctx->keys);
+        if (step_or_null) { CK(launch_pdl(ctx, k_project_bin<true>, T, 1024, 0, F, ctx->bin_count, ctx->keys)); ctx->project_step++; }
+        else CK(launch_pdl(ctx, k_project_bin<false>, T, 1024, 0, F, ctx->bin_count, ctx->keys));
         LAUNCHED();
-        k_bin_scatter<<<T, 1024, 0, ctx->stream>>>(ctx->bin_count, F.fc.nb, ctx->keys, ctx->n, ctx->bin_list, ctx->bin_offs, ctx->cta_bin, ctx->sm_count);
+        CK(launch_pdl(ctx, k_bin_scatter, T, 1024, 0, ctx->bin_count, F.fc.nb, ctx->keys, ctx->n, ctx->bin_list, ctx->bin_offs, ctx->cta_bin, ctx->sm_count));
         LAUNCHED();
         if (ev0) CK(cudaEventRecord(ev0, ctx->stream));                  // the events bracket the dominant kernel alone
         if (ctx->lean_threads == 512)
-            k_weight_lean<512><<<(unsigned)ctx->sm_count, 512, smem, ctx->stream>>>(F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin);
+            CK(launch_pdl(ctx, k_weight_lean<512>, (unsigned)ctx->sm_count, 512, smem, F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin));
         else
-            k_weight_lean<1024><<<(unsigned)ctx->sm_count, 1024, smem, ctx->stream>>>(F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin);
+            CK(launch_pdl(ctx, k_weight_lean<1024>, (unsigned)ctx->sm_count, 1024, smem, F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin));
         LAUNCHED();
         if (ev1) CK(cudaEventRecord(ev1, ctx->stream));
-        k_project_weight<false, true, false, true><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
+        // the generic kernel on the list: sized by the list length an earlier update reported (a hint: any grid is correct)
+        const unsigned est = ((volatile DevScalars*)ctx->sc_async)->defer_last;
+        const unsigned lgrid = std::min(grid, est / 1024u + 2u);
+        CK(launch_pdl(ctx, (k_project_weight<false, true, false, true>), lgrid, WT_THREADS, smem, P));
         LAUNCHED();
         ctx->hint_n = 0;
     } else {
         if (step_or_null) {
-            if (patches) k_project_weight<true, true, true, false><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
-            else k_project_weight<true, true, false, false><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
+            if (patches) CK(launch_pdl(ctx, (k_project_weight<true, true, true, false>), grid, WT_THREADS, smem, P));
+            else CK(launch_pdl(ctx, (k_project_weight<true, true, false, false>), grid, WT_THREADS, smem, P));
             ctx->project_step++;
-        } else if (patches) k_project_weight<false, true, true, false><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
-        else k_project_weight<false, true, false, false><<<grid, WT_THREADS, smem, ctx->stream>>>(P);
+        } else if (patches) CK(launch_pdl(ctx, (k_project_weight<false, true, true, false>), grid, WT_THREADS, smem, P));
+        else CK(launch_pdl(ctx, (k_project_weight<false, true, false, false>), grid, WT_THREADS, smem, P));
         LAUNCHED();
         ctx->hint_n = grid;
         if (ev1) CK(cudaEventRecord(ev1, ctx->stream));
     }
     ctx->last_lean = lean;
-    k_tile_part<<<ctx->t_local, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->n, ctx->l_part_a);
+    CK(launch_pdl(ctx, k_tile_part, ctx->t_local, SCAN_THREADS, 0, ctx->st, ctx->sc, ctx->n, ctx->l_part_a));
     LAUNCHED();
     AG(ctx->l_part_a, ctx->g_part_a, ctx->t_local * sizeof(TilePartA));
-    k_reduce_a<<<1, 1024, 0, ctx->stream>>>(ctx->g_part_a, ctx->t_global, ctx->n, ctx->sc, ctx->scratch_a, ctx->scratch_b,
-                                            ctx->cfg.discount_factor, ctx->hint, ctx->hint_n, ctx->bin_count, ctx->bin_next);
+    CK(launch_pdl(ctx, k_reduce_a, 1, 1024, 0, ctx->g_part_a, ctx->t_global, ctx->n, ctx->sc, ctx->scratch_a, ctx->scratch_b,
+                                            ctx->cfg.discount_factor, ctx->hint, ctx->hint_n, ctx->bin_count, ctx->bin_next));
     LAUNCHED();
-    CK(cudaMemcpyAsync(ctx->tile_hint, &ctx->sc->tile_cx, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    // cloud centre (tile placement of the generic path) and the generic-list length (its launch size): copied to the host
+    // on a side stream, read by later launches without waiting -- both are hints
+    CK(cudaEventRecord(ctx->side_ev, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->side, ctx->side_ev, 0));
+    CK(cudaMemcpyAsync(ctx->sc_async, ctx->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->side));
     return launch_tail(ctx, true, 1, 1, 0);
 }
 
@@ -911,12 +983,14 @@ int eslam_gpu_run_steps(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const es
     const size_t need = 2 + 2 * (size_t)steps;
     while (ctx->events.size() < need) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->events.push_back(e); }
     CK(cudaEventRecord(ctx->events[0], ctx->stream));
+    ctx->marks_used = 0;
     for (int s = 0; s < steps; ++s) {
         st = launch_update(ctx, step, &cs, ctx->events[2 + 2 * s], ctx->events[3 + 2 * s]);
         if (st != ESLAM_OK) return st;
     }
     CK(cudaEventRecord(ctx->events[1], ctx->stream));
     CK(cudaEventSynchronize(ctx->events[1]));
+    timing_report(ctx);
     if (elapsed_ms) CK(cudaEventElapsedTime(elapsed_ms, ctx->events[0], ctx->events[1]));
     if (top_kernel_ms) {
         float tot = 0;

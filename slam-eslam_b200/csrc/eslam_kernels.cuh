@@ -148,6 +148,13 @@ struct TileDesc {                // what a tile contributes to the exact running
 struct SegF { long long d0, d1; int b; int pad; };   // 2-state rounding function of a run of interior elements
 
 // ------------------------------------------------------------------------------------------------ small helpers
+// First statement of every kernel of a filter step (see launch_pdl in eslam_gpu.cu): let the next kernel of the stream
+// be scheduled early, then wait until everything launched before this kernel has completed and is visible.
+__device__ __forceinline__ void pdl_start() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t stream_word(uint32_t stream, unsigned long long idx) {
     return stream ^ ((uint32_t)(idx >> 32) << 8);
 }
@@ -616,6 +623,7 @@ __device__ __forceinline__ void bin_origin(const MapParams& M, const FastContact
 template <bool DO_PROJECT>
 __global__ void __launch_bounds__(1024, 1) k_project_bin(const __grid_constant__ FastParams P, int* __restrict__ bin_count,
                                                          uint2* __restrict__ keys) {
+    pdl_start();
     __shared__ int hist[MAX_BINS], gbase[MAX_BINS];
     const WeightCommon& C = P.c; const FastContacts& F = P.fc;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -669,6 +677,7 @@ __global__ void __launch_bounds__(1024, 1) k_project_bin(const __grid_constant__
 __global__ void __launch_bounds__(1024, 1) k_bin_scatter(const int* __restrict__ bin_count, int nb, const uint2* __restrict__ keys,
                                                          unsigned long long n, uint32_t* __restrict__ list, unsigned* __restrict__ bin_offs,
                                                          int* __restrict__ cta_bin, int n_cta) {
+    pdl_start();
     __shared__ unsigned offs[MAX_BINS + 1];
     __shared__ unsigned wsum[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -847,6 +856,7 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_weight_lean(const __grid_constant__ FastParams P, const uint32_t* __restrict__ list,
                                                             const int* __restrict__ bin_count, const unsigned* __restrict__ bin_offs,
                                                             unsigned* __restrict__ bin_next, const int* __restrict__ cta_bin) {
+    pdl_start();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const WeightCommon& C = P.c;
     em::dbl2* htab = reinterpret_cast<em::dbl2*>(smem_raw);
@@ -934,6 +944,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_weight_lean(const __grid_constan
 // the particles the lean kernel handed over (already projected); otherwise all particles.
 template <bool DO_PROJECT, bool DO_WEIGHT, bool PATCH, bool LIST>
 __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_constant__ WeightParams P) {
+    pdl_start();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const em::dbl2* htab = reinterpret_cast<const em::dbl2*>(smem_raw);
     double* red = reinterpret_cast<double*>(smem_raw + HTAB_BYTES + WT_CONTACT_BYTES);
@@ -990,6 +1001,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_c
 // 305-310) per 1024-particle tile, from what the weight kernels left per particle (mprob, floating, cpoints.size()).
 __global__ void __launch_bounds__(SCAN_THREADS) k_tile_part(StateBufs st, const DevScalars* sc, unsigned long long n,
                                                             TilePartA* part) {
+    pdl_start();
     __shared__ double red[8];
     __shared__ double redm[8];
     __shared__ unsigned redu[16];
@@ -1034,6 +1046,7 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_a(const TilePartA* part, uns
                                                       DevScalars* sc, double* scratch_a, double* scratch_b,
                                                       double discount, const double* hint, unsigned n_hint, int* bin_count,
                                                       unsigned* bin_next) {
+    pdl_start();
     for (int b = threadIdx.x; b < MAX_BINS; b += blockDim.x) { bin_count[b] = 0; bin_next[b] = 0; }   // for the next update's lean path
     __shared__ double red[32];
     __shared__ unsigned long long redull[64];
@@ -1074,6 +1087,7 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_a(const TilePartA* part, uns
 template <bool APPLY>
 __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, const DevScalars* sc, unsigned long long n,
                                                          double* tile_sum) {
+    pdl_start();
     __shared__ double red[8];
     const int cur = sc->cur;
     const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
@@ -1116,6 +1130,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, const Dev
 __global__ void __launch_bounds__(1024, 1) k_reduce_b(const double* tile_sum, unsigned n_tiles, unsigned long long n,
                                                       DevScalars* sc, double* scratch_a, double* scratch_b,
                                                       double* tile_prefix, int normalise) {
+    pdl_start();
     __shared__ double sh[1024];
     __shared__ double tree_a[TREE_SMEM], tree_b[TREE_SMEM / 2];
     for (unsigned i = threadIdx.x; i < n_tiles; i += blockDim.x) scratch_a[i] = tile_sum[i];
@@ -1310,6 +1325,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_norm_scan(StateBufs st, const 
                                                             unsigned long long n_global, const double* tile_prefix,
                                                             double* tile_sq, TileDesc* desc, BndEntry* pool, DevScalars* scw,
                                                             int normalise, double eps, unsigned tile_ofs) {
+    pdl_start();
     __shared__ TileScanSmem sm;
     __shared__ double red[8];
     __shared__ int slot_of[TILE];
@@ -1382,6 +1398,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, const B
                                                    int* tile_bofs, SegF* tile_pre, double* tile_sin, double* sb_out,
                                                    unsigned long long min_effective, int decide, int force,
                                                    unsigned tiles_per_rank) {
+    pdl_start();
     extern __shared__ __align__(16) unsigned char chain_raw[];
     ChainSmem& cs = *reinterpret_cast<ChainSmem*>(chain_raw);
     __shared__ int sh_i[1024];
@@ -1488,6 +1505,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, const B
 __global__ void __launch_bounds__(SCAN_THREADS) k_cdf(StateBufs st, DevScalars* sc, unsigned long long n,
                                                       const double* tile_prefix, const int* tile_bofs, const double* tile_sin,
                                                       const double* sb, double* cdf, double eps, unsigned tile_ofs) {
+    pdl_start();
     __shared__ TileScanSmem sm;
     __shared__ int slot_of[TILE];
     if (!sc->do_resample || (sc->error_flags & ERR_CDF_FALLBACK_BIT)) return;
@@ -1517,6 +1535,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_cdf(StateBufs st, DevScalars* 
 
 // fallback: literal left-to-right running sum by one thread (only when the tile descriptors overflowed)
 __global__ void k_cdf_sequential(StateBufs st, DevScalars* sc, unsigned long long n, double* cdf, double* tile_sin) {
+    pdl_start();
     if (!sc->do_resample || !(sc->error_flags & ERR_CDF_FALLBACK_BIT)) return;
     const double* w = st.f[sc->cur][F_W];
     double s = 0.0;
@@ -1543,6 +1562,7 @@ __global__ void __launch_bounds__(256) k_resample(StateBufs st, const DevScalars
                                                   unsigned long long win_len, unsigned long long win_base,
                                                   unsigned long long n, unsigned long long n_global, unsigned long long base,
                                                   uint32_t k0, uint32_t k1, int systematic, uint32_t* ancestors, GatherSrc src) {
+    pdl_start();
     if (!sc->do_resample) return;
     const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -1575,6 +1595,71 @@ __global__ void __launch_bounds__(256) k_resample(StateBufs st, const DevScalars
     }
 }
 
+// One-GPU variant with the search in shared memory.  A CTA owns 1024 consecutive strata; their draws lie in
+// [k0/N, (k0+1024)/N), so their ancestors lie in the tiles from the last one starting below k0/N to the last one starting
+// below (k0+1024)/N: with balanced weights one or two tiles.  When that is at most RS_TILES tiles the CTA copies their exact
+// running sums into shared memory (coalesced) and every thread searches there; otherwise the two-level global search runs.
+// Fused with the copy (:104) and with xi_k.swap(xi_kp) (:107): the last CTA to finish flips the current buffer.
+#define RS_TILES 3
+__global__ void __launch_bounds__(1024, 2) k_resample_local(StateBufs st, DevScalars* sc, const double* __restrict__ cdf,
+                                                            const double* __restrict__ tile_start, unsigned n_tiles,
+                                                            unsigned long long n, uint32_t k0key, uint32_t k1key, int systematic,
+                                                            uint32_t* ancestors, unsigned* ticket) {
+    pdl_start();
+    __shared__ double s_cdf[RS_TILES * TILE];
+    __shared__ unsigned s_t[2];
+    if (!sc->do_resample) return;
+    const unsigned tid = threadIdx.x;
+    const unsigned long long kb = (unsigned long long)blockIdx.x * 1024, k = kb + tid;
+    if (tid < 2) {
+        const double thr = (double)(kb + (tid ? 1024ull : 0ull)) / (double)n;   // monotone bounds of every sum_r of this CTA
+        unsigned lo = 0, hi = n_tiles;                                           // first tile with !(start < thr)
+        while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (__ldg(&tile_start[mid]) < thr) lo = mid + 1; else hi = mid; }
+        s_t[tid] = lo == 0 ? 0u : lo - 1;
+    }
+    __syncthreads();
+    const unsigned t_lo = s_t[0], t_hi = s_t[1];
+    const bool in_smem = (t_hi - t_lo) < RS_TILES;
+    const unsigned long long w0 = (unsigned long long)t_lo * TILE;
+    const unsigned long long w1 = min(((unsigned long long)t_hi + 1) * TILE, n);   // window [w0, w1)
+    if (in_smem) {
+        for (unsigned long long j = w0 + tid; j < w1; j += 1024) s_cdf[j - w0] = cdf[j];
+        __syncthreads();
+    }
+    if (k < n) {
+        const unsigned long long gk = systematic ? 0ull : k;
+        const em::Philox4 r = em::philox4x32_10((uint32_t)gk, sc->resample_step, 0, stream_word(em::STREAM_RESAMPLE, gk), k0key, k1key);
+        const double u = em::u01(r.v[0], r.v[1]);
+        const double sum_r = ((double)k + u) / (double)n;                            // :98
+        unsigned long long a;
+        if (in_smem) {
+            unsigned lo = 0, hi = (unsigned)(w1 - w0);                               // first element with !(cdf < sum_r)
+            while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (s_cdf[mid] < sum_r) lo = mid + 1; else hi = mid; }
+            a = w0 + lo;
+        } else {
+            unsigned tlo = 0, thi = n_tiles;
+            while (tlo < thi) { const unsigned mid = (tlo + thi) >> 1; if (__ldg(&tile_start[mid]) < sum_r) tlo = mid + 1; else thi = mid; }
+            const unsigned t = tlo == 0 ? 0 : tlo - 1;
+            unsigned long long lo = (unsigned long long)t * TILE, hi = min(lo + TILE, n);
+            while (lo < hi) { const unsigned long long mid = (lo + hi) >> 1; if (__ldg(&cdf[mid]) < sum_r) lo = mid + 1; else hi = mid; }
+            a = lo;
+        }
+        if (a >= n) a = n - 1;               // the reference walks off the end here; we stop at the last particle
+        ancestors[k] = (uint32_t)a;
+        const int cur = sc->cur, nxt = cur ^ 1;
+#pragma unroll
+        for (int f = 0; f < 7; ++f) st.f[nxt][f][k] = st.f[cur][f][a];               // :104 copy keeps the weight (Q3)
+#pragma unroll
+        for (int f = 0; f < 2; ++f) st.b[nxt][f][k] = st.b[cur][f][a];
+    }
+    // xi_k.swap(xi_kp) :107 by the last CTA (every CTA has read sc->cur by then)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0; sc->cur ^= 1; sc->resample_step += 1; }
+    }
+}
+
 // Sharded resampling over NVLink peer memory (exact-global mode).  Every rank holds, after the all-gathered k_chain, the
 // exact running sum before every 1024-tile of EVERY rank (tile_start, global).  Stratum k of this rank searches that
 // table, then searches inside the one tile that holds its ancestor -- reading the owner's running sum through its
@@ -1592,6 +1677,7 @@ __global__ void __launch_bounds__(256) k_resample_p2p(StateBufs st, DevScalars* 
                                                       unsigned long long n_global, unsigned long long base, uint32_t k0,
                                                       uint32_t k1, int systematic, uint32_t* ancestors,
                                                       const __grid_constant__ PeerTable peers) {
+    pdl_start();
     if (!sc->do_resample) return;
     if (sc->error_flags & ERR_CDF_FALLBACK_BIT) return;     // reported through the update status; state is left as is
     const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1626,6 +1712,7 @@ __global__ void __launch_bounds__(256) k_resample_p2p(StateBufs st, DevScalars* 
 // cloneMaps (src/PoseEstimator.cpp:31-45): every copy of a particle owns a copy of its map patch. One warp per particle.
 __global__ void k_gather_patches(const DevScalars* sc, unsigned long long n, const uint32_t* __restrict__ anc, int P,
                                  float2* p0, float2* p1, int* o0, int* o1) {
+    pdl_start();
     if (!sc->do_resample) return;
     const unsigned long long k = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (k >= n) return;
@@ -1643,6 +1730,7 @@ __global__ void k_fill_i32(int* p, size_t count, int v) {
 }
 
 __global__ void k_after_resample(DevScalars* sc) {
+    pdl_start();
     if (!sc->do_resample) return;
     if (sc->error_flags & ERR_CDF_FALLBACK_BIT) return;   // sharded run that could not resample: state left as is
     sc->cur ^= 1;                                                                    // xi_k.swap(xi_kp) :107
