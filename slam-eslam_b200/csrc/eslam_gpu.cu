@@ -47,7 +47,8 @@ struct eslam_gpu_ctx {
     // per-tile arrays: l_* cover the local tiles, g_* all tiles of all ranks (aliases of l_* when world == 1)
     unsigned t_local, t_global, t_cap;
     TilePartA *l_part_a, *g_part_a; double *l_tile_sum, *g_tile_sum, *l_tile_sq, *g_tile_sq;
-    TileDesc *l_desc, *g_desc; BndEntry *l_pool, *g_pool;
+    TileDesc *l_desc; BndEntry *l_pool;           // l_tile_sq, l_desc, l_pool point into l_pack
+    unsigned char *l_pack, *g_pack; size_t pack_bytes;   // [sum w^2 per tile | tile descriptors | boundary pool] per rank: one all-gather
     double *l_cent, *g_cent, *l_best_w, *g_best_w; unsigned long long *l_best_idx, *g_best_idx;
     double *tile_prefix, *scratch_a, *scratch_b, *tile_sin, *sb; int* tile_bofs; SegF* tile_pre;
     double* tile_sin_host;                        // pinned, t_global
@@ -148,11 +149,12 @@ static void free_particles(eslam_gpu_ctx* ctx) {
     dfree(ctx->ancestors); dfree(ctx->cdf); dfree(ctx->defer_list); dfree(ctx->keys); dfree(ctx->bin_list);
     for (int b = 0; b < 2; ++b) { dfree(ctx->patch[b]); dfree(ctx->porigin[b]); }
     const bool sh = ctx->g_part_a != ctx->l_part_a;
-    if (sh) { dfree(ctx->g_part_a); dfree(ctx->g_tile_sum); dfree(ctx->g_tile_sq); dfree(ctx->g_desc); dfree(ctx->g_pool);
+    if (sh) { dfree(ctx->g_part_a); dfree(ctx->g_tile_sum); dfree(ctx->g_pack);
               dfree(ctx->g_cent); dfree(ctx->g_best_w); dfree(ctx->g_best_idx); }
-    dfree(ctx->l_part_a); dfree(ctx->l_tile_sum); dfree(ctx->l_tile_sq); dfree(ctx->l_desc); dfree(ctx->l_pool);
+    dfree(ctx->l_part_a); dfree(ctx->l_tile_sum); dfree(ctx->l_pack);
+    ctx->l_tile_sq = nullptr; ctx->l_desc = nullptr; ctx->l_pool = nullptr; ctx->g_pack = nullptr;
     dfree(ctx->l_cent); dfree(ctx->l_best_w); dfree(ctx->l_best_idx);
-    ctx->g_part_a = nullptr; ctx->g_tile_sum = ctx->g_tile_sq = nullptr; ctx->g_desc = nullptr; ctx->g_pool = nullptr;
+    ctx->g_part_a = nullptr; ctx->g_tile_sum = ctx->g_tile_sq = nullptr;
     ctx->g_cent = ctx->g_best_w = nullptr; ctx->g_best_idx = nullptr;
     dfree(ctx->tile_prefix); dfree(ctx->scratch_a); dfree(ctx->scratch_b); dfree(ctx->tile_sin); dfree(ctx->sb);
     dfree(ctx->tile_bofs); dfree(ctx->tile_pre);
@@ -227,16 +229,19 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
             for (int b = 0; b < 2; ++b) { CK(dalloc(&ctx->patch[b], n * pp)); CK(dalloc(&ctx->porigin[b], 2 * n)); }
         }
         const size_t t = (size_t)((n + TILE - 1) / TILE), tg = t * G;
-        CK(dalloc(&ctx->l_part_a, t)); CK(dalloc(&ctx->l_tile_sum, t)); CK(dalloc(&ctx->l_tile_sq, t));
-        CK(dalloc(&ctx->l_desc, t)); CK(dalloc(&ctx->l_pool, (size_t)MAX_BND_TOTAL));
+        CK(dalloc(&ctx->l_part_a, t)); CK(dalloc(&ctx->l_tile_sum, t));
+        ctx->pack_bytes = t * (sizeof(double) + sizeof(TileDesc)) + (size_t)MAX_BND_TOTAL * sizeof(BndEntry);
+        CK(dalloc(&ctx->l_pack, ctx->pack_bytes));
+        ctx->l_tile_sq = reinterpret_cast<double*>(ctx->l_pack);
+        ctx->l_desc = reinterpret_cast<TileDesc*>(ctx->l_pack + t * sizeof(double));
+        ctx->l_pool = reinterpret_cast<BndEntry*>(ctx->l_pack + t * (sizeof(double) + sizeof(TileDesc)));
         CK(dalloc(&ctx->l_cent, 5 * t)); CK(dalloc(&ctx->l_best_w, t)); CK(dalloc(&ctx->l_best_idx, t));
         if (G > 1) {
-            CK(dalloc(&ctx->g_part_a, tg)); CK(dalloc(&ctx->g_tile_sum, tg)); CK(dalloc(&ctx->g_tile_sq, tg));
-            CK(dalloc(&ctx->g_desc, tg)); CK(dalloc(&ctx->g_pool, (size_t)MAX_BND_TOTAL * G));
+            CK(dalloc(&ctx->g_part_a, tg)); CK(dalloc(&ctx->g_tile_sum, tg)); CK(dalloc(&ctx->g_pack, ctx->pack_bytes * G));
             CK(dalloc(&ctx->g_cent, 5 * tg)); CK(dalloc(&ctx->g_best_w, tg)); CK(dalloc(&ctx->g_best_idx, tg));
         } else {
-            ctx->g_part_a = ctx->l_part_a; ctx->g_tile_sum = ctx->l_tile_sum; ctx->g_tile_sq = ctx->l_tile_sq;
-            ctx->g_desc = ctx->l_desc; ctx->g_pool = ctx->l_pool; ctx->g_cent = ctx->l_cent;
+            ctx->g_part_a = ctx->l_part_a; ctx->g_tile_sum = ctx->l_tile_sum; ctx->g_pack = ctx->l_pack;
+            ctx->g_cent = ctx->l_cent;
             ctx->g_best_w = ctx->l_best_w; ctx->g_best_idx = ctx->l_best_idx;
         }
         CK(dalloc(&ctx->tile_prefix, tg)); CK(dalloc(&ctx->scratch_a, tg)); CK(dalloc(&ctx->scratch_b, tg));
@@ -357,7 +362,7 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     ctx->bin_count = nullptr; ctx->keys = nullptr; ctx->bin_list = nullptr; ctx->bin_offs = nullptr; ctx->bin_next = nullptr; ctx->cta_bin = nullptr;
     for (int b = 0; b < 2; ++b) { ctx->patch[b] = nullptr; ctx->porigin[b] = nullptr; }
     ctx->l_part_a = ctx->g_part_a = nullptr; ctx->l_tile_sum = ctx->g_tile_sum = ctx->l_tile_sq = ctx->g_tile_sq = nullptr;
-    ctx->l_desc = ctx->g_desc = nullptr; ctx->l_pool = ctx->g_pool = nullptr;
+    ctx->l_desc = nullptr; ctx->l_pool = nullptr; ctx->l_pack = ctx->g_pack = nullptr; ctx->pack_bytes = 0;
     ctx->l_cent = ctx->g_cent = ctx->l_best_w = ctx->g_best_w = nullptr; ctx->l_best_idx = ctx->g_best_idx = nullptr;
     ctx->tile_prefix = ctx->scratch_a = ctx->scratch_b = ctx->tile_sin = ctx->sb = nullptr;
     ctx->tile_bofs = nullptr; ctx->tile_pre = nullptr; ctx->tile_sin_host = nullptr;
@@ -783,13 +788,12 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     CK(launch_pdl(ctx, k_norm_scan, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, ng, ctx->tile_prefix, ctx->l_tile_sq, ctx->l_desc, ctx->l_pool,
                                              ctx->sc, normalise, eps, tile_ofs(ctx)));
     LAUNCHED();
-    AG(ctx->l_tile_sq, ctx->g_tile_sq, T * sizeof(double));
-    AG(ctx->l_desc, ctx->g_desc, T * sizeof(TileDesc));
-    AG(ctx->l_pool, ctx->g_pool, (size_t)MAX_BND_TOTAL * sizeof(BndEntry));
+    AG(ctx->l_pack, ctx->g_pack, ctx->pack_bytes);                     // sum w^2, descriptors and boundary pool in one exchange
+    ChainPack pk; pk.base = ctx->g_pack; pk.pack_bytes = ctx->pack_bytes; pk.tiles_per_rank = T;
     const int decide = mode == 0 ? 0 : 1;
-    CK(launch_pdl(ctx, k_chain, 1, 1024, sizeof(ChainSmem), ctx->g_desc, ctx->g_pool, TG, ctx->g_tile_sq, ctx->sc, ctx->scratch_a,
+    CK(launch_pdl(ctx, k_chain, 1, 1024, sizeof(ChainSmem), pk, TG, ctx->sc, ctx->scratch_a,
                                                          ctx->scratch_b, ctx->tile_bofs, ctx->tile_pre, ctx->tile_sin, ctx->sb,
-                                                         mode == 2 ? 0ull : ctx->cfg.min_effective, decide, force, T));
+                                                         mode == 2 ? 0ull : ctx->cfg.min_effective, decide, force));
     LAUNCHED();
     if (mode == 2) return ESLAM_OK;
     CK(launch_pdl(ctx, k_cdf, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, ctx->tile_prefix, ctx->tile_bofs, ctx->tile_sin, ctx->sb, ctx->cdf, eps,

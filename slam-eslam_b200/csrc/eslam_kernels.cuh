@@ -190,6 +190,37 @@ __device__ __forceinline__ double tile_tree_sum_1024(double v, double* red) {
 // otherwise the levels ping-pong between the global arrays a and b.  Same tree either way.
 #define TREE_SMEM 2048
 __device__ double block_tree_reduce(double* a, double* b, unsigned n, double* sa = nullptr, double* sb = nullptr) {
+    if (sa && ((n + 1) >> 1) > TREE_SMEM && n <= 16u * TREE_SMEM) {
+        // many tiles (sharded runs: all ranks' tiles): the first L levels of the same tree run in registers, 2^L consecutive
+        // leaves per thread (a missing right operand passes the left one through, as below), the rest in shared memory
+        unsigned L = 1; while ((((n + (1u << L) - 1) >> L) + 1) >> 1 > TREE_SMEM) ++L;
+        const unsigned groups = (n + (1u << L) - 1) >> L;                 // <= 2 * TREE_SMEM values left
+        for (unsigned g = threadIdx.x; g < ((groups + 1) >> 1); g += blockDim.x) {
+            double pair[2]; unsigned have = 0;
+            for (unsigned h = 0; h < 2; ++h) {
+                const unsigned gi = 2 * g + h;
+                if (gi >= groups) break;
+                double v[16]; unsigned m = 0;
+                const unsigned base = gi << L;
+                for (unsigned j = 0; j < (1u << L) && base + j < n; ++j) v[m++] = a[base + j];
+                while (m > 1) { const unsigned hh = (m + 1) >> 1; for (unsigned j = 0; j < hh; ++j) v[j] = (2 * j + 1 < m) ? v[2 * j] + v[2 * j + 1] : v[2 * j]; m = hh; }
+                pair[have++] = v[0];
+            }
+            sa[g] = have == 2 ? pair[0] + pair[1] : pair[0];              // one more level: sa holds ceil(groups/2) values
+        }
+        __syncthreads();
+        unsigned m = (groups + 1) >> 1;
+        double *x = sa, *y = sb;
+        while (m > 1) {
+            const unsigned h = (m + 1) >> 1;
+            for (unsigned i = threadIdx.x; i < h; i += blockDim.x) y[i] = (2 * i + 1 < m) ? x[2 * i] + x[2 * i + 1] : x[2 * i];
+            __syncthreads();
+            double* t = x; x = y; y = t; m = h;
+        }
+        const double r = x[0];
+        __syncthreads();
+        return r;
+    }
     if (sa && n > 1 && ((n + 1) >> 1) <= TREE_SMEM) {
         unsigned h = (n + 1) >> 1;
         for (unsigned i = threadIdx.x; i < h; i += blockDim.x) sa[i] = (2 * i + 1 < n) ? a[2 * i] + a[2 * i + 1] : a[2 * i];
@@ -1393,12 +1424,29 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_norm_scan(StateBufs st, const 
 // one CTA: ESS, resample decision, and the exact value of the running sum at every tile start / boundary element
 struct ChainSmem { double bw[MAX_BND_TOTAL]; SegF seg[MAX_BND_TOTAL]; };
 
-__global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, const BndEntry* pool, unsigned n_tiles, const double* tile_sq,
+// What a rank contributes to the chain, packed so that ONE all-gather moves it: [sum of w^2 per tile | tile descriptors |
+// boundary pool]; pack_bytes is the size of one rank's block, tiles_per_rank the number of tiles in it.
+struct ChainPack {
+    const unsigned char* base; size_t pack_bytes; unsigned tiles_per_rank;
+    __device__ __forceinline__ const unsigned char* rank(unsigned r) const { return base + (size_t)r * pack_bytes; }
+    __device__ __forceinline__ double tile_sq(unsigned t) const {
+        const unsigned r = t / tiles_per_rank; return reinterpret_cast<const double*>(rank(r))[t - r * tiles_per_rank];
+    }
+    __device__ __forceinline__ const TileDesc& desc(unsigned t) const {
+        const unsigned r = t / tiles_per_rank;
+        return reinterpret_cast<const TileDesc*>(rank(r) + (size_t)tiles_per_rank * sizeof(double))[t - r * tiles_per_rank];
+    }
+    __device__ __forceinline__ const BndEntry* pool(unsigned r) const {
+        return reinterpret_cast<const BndEntry*>(rank(r) + (size_t)tiles_per_rank * (sizeof(double) + sizeof(TileDesc)));
+    }
+};
+
+__global__ void __launch_bounds__(1024, 1) k_chain(ChainPack pk, unsigned n_tiles,
                                                    DevScalars* sc, double* scratch_a, double* scratch_b,
                                                    int* tile_bofs, SegF* tile_pre, double* tile_sin, double* sb_out,
-                                                   unsigned long long min_effective, int decide, int force,
-                                                   unsigned tiles_per_rank) {
+                                                   unsigned long long min_effective, int decide, int force) {
     pdl_start();
+    const unsigned tiles_per_rank = pk.tiles_per_rank;
     extern __shared__ __align__(16) unsigned char chain_raw[];
     ChainSmem& cs = *reinterpret_cast<ChainSmem*>(chain_raw);
     __shared__ int sh_i[1024];
@@ -1406,7 +1454,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, const B
     __shared__ int s_total, s_bad, s_go;
     const unsigned tid = threadIdx.x;
     if (decide) {
-        for (unsigned i = tid; i < n_tiles; i += blockDim.x) scratch_a[i] = tile_sq[i];
+        for (unsigned i = tid; i < n_tiles; i += blockDim.x) scratch_a[i] = pk.tile_sq(i);
         __syncthreads();
         const double eff = block_tree_reduce(scratch_a, scratch_b, n_tiles, reinterpret_cast<double*>(chain_raw),
                                              reinterpret_cast<double*>(chain_raw) + TREE_SMEM);
@@ -1427,12 +1475,12 @@ __global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, const B
     const unsigned lo = tid * per, hi = min(lo + per, n_tiles);
     int cnt = 0; SegE agg; agg.f = segf_identity(); agg.head = -1; int bad = 0;
     for (unsigned t = lo; t < hi; ++t) {
-        const TileDesc& D = desc[t];
+        const TileDesc& D = pk.desc(t);
         if (D.overflow) bad = 1;
         cnt += D.n_bnd;
         SegE e;
         if (D.n_bnd > 0 && !D.overflow) {
-            const BndEntry& L = pool[(size_t)(t / tiles_per_rank) * MAX_BND_TOTAL + D.bnd_base + D.n_bnd - 1];
+            const BndEntry& L = pk.pool(t / tiles_per_rank)[D.bnd_base + D.n_bnd - 1];
             e.head = (int)t; e.f.b = L.b; e.f.d0 = L.d0; e.f.d1 = L.d1; e.f.pad = 0;
         } else { e.head = -1; e.f.b = D.head_b; e.f.d0 = D.head_d0; e.f.d1 = D.head_d1; e.f.pad = D.pad; }
         agg = sege_combine(agg, e);
@@ -1458,10 +1506,10 @@ __global__ void __launch_bounds__(1024, 1) k_chain(const TileDesc* desc, const B
     __syncthreads();
     if (s_bad) { if (tid == 0) { atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT); sc->n_boundaries = total; } return; }
     for (unsigned t = lo; t < hi; ++t) {
-        const TileDesc& D = desc[t];
+        const TileDesc& D = pk.desc(t);
         tile_bofs[t] = run_c; tile_pre[t] = run_e.f;
         // boundary k = run_c + j: weight, and the function of the segment that follows it
-        const BndEntry* B = pool + (size_t)(t / tiles_per_rank) * MAX_BND_TOTAL + D.bnd_base;
+        const BndEntry* B = pk.pool(t / tiles_per_rank) + D.bnd_base;
         for (int j = 0; j < D.n_bnd; ++j) {
             cs.bw[run_c + j] = B[j].w;
             if (j + 1 < D.n_bnd) { SegF f; f.b = B[j].b; f.d0 = B[j].d0; f.d1 = B[j].d1; f.pad = 0; cs.seg[run_c + j] = f; }
@@ -1607,18 +1655,19 @@ __global__ void __launch_bounds__(1024, 2) k_resample_local(StateBufs st, DevSca
                                                             uint32_t* ancestors, unsigned* ticket) {
     pdl_start();
     __shared__ double s_cdf[RS_TILES * TILE];
-    __shared__ unsigned s_t[2];
     if (!sc->do_resample) return;
     const unsigned tid = threadIdx.x;
     const unsigned long long kb = (unsigned long long)blockIdx.x * 1024, k = kb + tid;
-    if (tid < 2) {
-        const double thr = (double)(kb + (tid ? 1024ull : 0ull)) / (double)n;   // monotone bounds of every sum_r of this CTA
-        unsigned lo = 0, hi = n_tiles;                                           // first tile with !(start < thr)
-        while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (__ldg(&tile_start[mid]) < thr) lo = mid + 1; else hi = mid; }
-        s_t[tid] = lo == 0 ? 0u : lo - 1;
+    // the tile starts are non-decreasing, so "the last tile starting below thr" is a count: one coalesced read of the table and
+    // two block-wide counts instead of two dependent binary searches.  thr_lo / thr_hi bound every sum_r of this CTA.
+    const double thr_lo = (double)kb / (double)n, thr_hi = (double)(kb + 1024ull) / (double)n;
+    unsigned c_lo = 0, c_hi = 0;
+    for (unsigned t0 = 0; t0 < n_tiles; t0 += 1024) {
+        const double ts = (t0 + tid < n_tiles) ? __ldg(&tile_start[t0 + tid]) : 1.7e308;
+        c_lo += (unsigned)__syncthreads_count(ts < thr_lo);
+        c_hi += (unsigned)__syncthreads_count(ts < thr_hi);
     }
-    __syncthreads();
-    const unsigned t_lo = s_t[0], t_hi = s_t[1];
+    const unsigned t_lo = c_lo == 0 ? 0u : c_lo - 1, t_hi = c_hi == 0 ? 0u : c_hi - 1;
     const bool in_smem = (t_hi - t_lo) < RS_TILES;
     const unsigned long long w0 = (unsigned long long)t_lo * TILE;
     const unsigned long long w1 = min(((unsigned long long)t_hi + 1) * TILE, n);   // window [w0, w1)

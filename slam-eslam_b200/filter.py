@@ -212,6 +212,12 @@ class GpuPoseEstimator(FilterBase):
     def synchronize(self):
         self._check(self._lib.eslam_gpu_synchronize(self._ctx))
 
+    def getWeightsSum(self):
+        """ParticleFilter::getWeightsSum (src/ParticleFilter.hpp:34-39)."""
+        v = C.c_double()
+        self._check(self._lib.eslam_gpu_weights_sum(self._ctx, C.byref(v)))
+        return v.value
+
     def debugCounters(self):
         """{fallbacks, boundaries, error_flags, resamples} of the exact running-sum machinery."""
         out = (C.c_uint64 * 4)()

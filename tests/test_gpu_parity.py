@@ -353,16 +353,30 @@ def test_patches_change_the_result_only_through_written_cells(gpu):
 
 
 # ---------------------------------------------------------------------------------- larger sets (more tiles than threads)
-def test_four_million_particles_resample_stage(gpu):
-    """4,194,304 particles = 4096 tiles: the single-CTA kernels walk several tiles per thread and the tree reductions
-    leave shared memory; the running sum must still be the sequential one and the ancestors its lower bounds."""
-    n = 1 << 22
+def tree_sum(v):
+    """Pairwise sum over the index-aligned binary tree (a missing right operand passes the left one through)."""
+    a = np.array(v, dtype=np.float64)
+    while a.size > 1:
+        if a.size % 2:
+            a = np.concatenate([a[:-1:2] + a[1::2], a[-1:]])
+        else:
+            a = a[0::2] + a[1::2]
+    return float(a[0])
+
+
+@pytest.mark.parametrize("n", [1 << 22, 5 << 20])
+def test_millions_of_particles_resample_stage(gpu, n):
+    """4,194,304 particles = 4096 tiles, 5,242,880 = 5120 tiles: the single-CTA kernels walk several tiles per thread and
+    the tree reductions run their first levels in registers (as they do for the all-ranks tile arrays of sharded runs);
+    the sums must still be the index-aligned tree's, the running sum the sequential one and the ancestors its lower
+    bounds."""
     rng = np.random.default_rng(22)
     w = rng.random(n) ** 3
     w /= w.sum()
     g = gpu()
     z = np.zeros(n)
     g.setParticles(x=np.arange(n, dtype=np.float64), y=z, theta=z, zpos=z, zsigma=z + 1, weight=w)
+    assert g.getWeightsSum() == tree_sum(w)
     g.resample()
     cdf = np.cumsum(w)
     assert np.array_equal(g.getCdf(), cdf)
