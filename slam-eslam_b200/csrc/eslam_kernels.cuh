@@ -31,6 +31,7 @@ namespace em = eslam_math;
 #define WT_THREADS 1024          // threads of the generic project+weight kernel
 #define MAX_BND_TOTAL 2048       // boundary elements per resample (pool + chain capacity); more -> sequential fallback
 #define BIN_NONE (-100000)       // "no binade": piece made of zero / sub-quarter-ulp weights only
+#define ESLAM_MAX_RANKS 8        // GPUs of one box
 #define ERR_ZERO_VARIANCE_BIT 1
 #define ERR_CDF_FALLBACK_BIT 2
 
@@ -153,6 +154,45 @@ struct SegF { long long d0, d1; int b; int pad; };   // 2-state rounding functio
 __device__ __forceinline__ void pdl_start() {
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ peer exchange
+// The small per-step exchanges of the sharded filter (loop-A tile partials, raw tile sums, chain inputs, the barrier in
+// front of the peer-memory resampling) go over NVLink peer memory instead of a collective library: every rank PUSHES its
+// block into the same slot of every peer's buffer (k_publish: one CTA per peer, plain stores to the peer-mapped pointer,
+// then a system-scope release of an epoch flag in the peer's memory); the consuming kernel polls its OWN flags (local
+// memory) until all ranks' epoch has arrived.  One launch + one NVLink write + a local poll instead of a collective's
+// latency; ordering between steps is the same as with collectives (a rank cannot publish step s+1 before every peer has
+// published the last exchange of step s, which it does after consuming the earlier ones).
+struct PublishArgs {
+    void* dst[ESLAM_MAX_RANKS];            // peer q's buffer region + my slot
+    unsigned* flag[ESLAM_MAX_RANKS];       // peer q's epoch flag for (this exchange, my rank)
+    const void* src; unsigned long long bytes;   // multiple of 8
+    unsigned epoch; int world;
+};
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__global__ void __launch_bounds__(256) k_publish(const __grid_constant__ PublishArgs A) {
+    pdl_start();
+    const int q = blockIdx.x;
+    if (q >= A.world) return;
+    const unsigned long long words = A.bytes >> 3;
+    const unsigned long long* s = reinterpret_cast<const unsigned long long*>(A.src);
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(A.dst[q]);
+    for (unsigned long long i = threadIdx.x; i < words; i += blockDim.x) d[i] = s[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(A.flag[q], A.epoch);
+}
+// consumer side: wait until every rank's block of this exchange and epoch has landed in this GPU's memory
+__device__ __forceinline__ void peer_wait(const unsigned* flags, unsigned epoch, int world) {
+    if (world <= 1 || flags == nullptr) return;
+    if ((int)threadIdx.x < world) { while ((int)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) __nanosleep(40); }
+    __syncthreads();
 }
 
 __device__ __forceinline__ uint32_t stream_word(uint32_t stream, unsigned long long idx) {
@@ -1076,8 +1116,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_part(StateBufs st, const 
 __global__ void __launch_bounds__(1024, 1) k_reduce_a(const TilePartA* part, unsigned n_tiles, unsigned long long n_local,
                                                       DevScalars* sc, double* scratch_a, double* scratch_b,
                                                       double discount, const double* hint, unsigned n_hint, int* bin_count,
-                                                      unsigned* bin_next) {
+                                                      unsigned* bin_next, const unsigned* xflags, unsigned epoch, int world) {
     pdl_start();
+    peer_wait(xflags, epoch, world);
     for (int b = threadIdx.x; b < MAX_BINS; b += blockDim.x) { bin_count[b] = 0; bin_next[b] = 0; }   // for the next update's lean path
     __shared__ double red[32];
     __shared__ unsigned long long redull[64];
@@ -1160,8 +1201,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, const Dev
 // getWeightsSum (src/ParticleFilter.hpp:34-39) and approximate per-tile prefixes of the (normalised) weights
 __global__ void __launch_bounds__(1024, 1) k_reduce_b(const double* tile_sum, unsigned n_tiles, unsigned long long n,
                                                       DevScalars* sc, double* scratch_a, double* scratch_b,
-                                                      double* tile_prefix, int normalise) {
+                                                      double* tile_prefix, int normalise, const unsigned* xflags, unsigned epoch, int world) {
     pdl_start();
+    peer_wait(xflags, epoch, world);
     __shared__ double sh[1024];
     __shared__ double tree_a[TREE_SMEM], tree_b[TREE_SMEM / 2];
     for (unsigned i = threadIdx.x; i < n_tiles; i += blockDim.x) scratch_a[i] = tile_sum[i];
@@ -1444,8 +1486,10 @@ struct ChainPack {
 __global__ void __launch_bounds__(1024, 1) k_chain(ChainPack pk, unsigned n_tiles,
                                                    DevScalars* sc, double* scratch_a, double* scratch_b,
                                                    int* tile_bofs, SegF* tile_pre, double* tile_sin, double* sb_out,
-                                                   unsigned long long min_effective, int decide, int force) {
+                                                   unsigned long long min_effective, int decide, int force,
+                                                   const unsigned* xflags, unsigned epoch, int world) {
     pdl_start();
+    peer_wait(xflags, epoch, world);
     const unsigned tiles_per_rank = pk.tiles_per_rank;
     extern __shared__ __align__(16) unsigned char chain_raw[];
     ChainSmem& cs = *reinterpret_cast<ChainSmem*>(chain_raw);
@@ -1714,7 +1758,6 @@ __global__ void __launch_bounds__(1024, 2) k_resample_local(StateBufs st, DevSca
 // table, then searches inside the one tile that holds its ancestor -- reading the owner's running sum through its
 // peer-mapped pointer -- and copies the ancestor's state straight from the owner's current buffers.  No host step, no
 // staging: remote ancestors cost NVLink reads, local ones (the vast majority when weights are balanced) HBM reads.
-#define ESLAM_MAX_RANKS 8
 struct PeerTable {
     const double* cdf[ESLAM_MAX_RANKS];
     const double* f[ESLAM_MAX_RANKS][2][7];
@@ -1725,10 +1768,12 @@ __global__ void __launch_bounds__(256) k_resample_p2p(StateBufs st, DevScalars* 
                                                       unsigned n_tiles_global, unsigned tiles_per_rank, unsigned long long n,
                                                       unsigned long long n_global, unsigned long long base, uint32_t k0,
                                                       uint32_t k1, int systematic, uint32_t* ancestors,
-                                                      const __grid_constant__ PeerTable peers) {
+                                                      const __grid_constant__ PeerTable peers, const unsigned* xflags,
+                                                      unsigned epoch, int world) {
     pdl_start();
     if (!sc->do_resample) return;
     if (sc->error_flags & ERR_CDF_FALLBACK_BIT) return;     // reported through the update status; state is left as is
+    peer_wait(xflags, epoch, world);                        // every rank's running sum is final before anyone reads a peer
     const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const unsigned long long gk = systematic ? 0ull : base + k;
