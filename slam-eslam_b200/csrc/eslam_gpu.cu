@@ -669,6 +669,7 @@ static inline uint32_t hi_word(double v) { uint64_t u; memcpy(&u, &v, 8); return
 static bool fill_fast_params(eslam_gpu_ctx* ctx, FastParams* F, const WeightParams& P, const ContactSet& cs) {
     if (getenv("ESLAM_GPU_NO_FAST")) return false;
     if (ctx->cfg.patch_size > 0 || !ctx->map.identity || !ctx->grid_sane || P.map.tile_w <= 0 || P.map.tile_h <= 0) return false;
+    if (ctx->n >= 0x80000000ull) return false;                            // bit 31 of a list entry flags the particle
     memset(F, 0, sizeof(*F));
     WeightCommon& c = F->c;
     c.st = P.st; c.sc = P.sc; c.map = P.map; c.mp = P.mp; c.htab = P.htab; c.n = P.n; c.base = P.base;
@@ -686,6 +687,9 @@ static bool fill_fast_params(eslam_gpu_ctx* ctx, FastParams* F, const WeightPara
         }
         if ((cs.flags[i] & 2u) && fc.n_eval > last_end) { fc.gend[fc.n_groups++] = (uint8_t)fc.n_eval; last_end = fc.n_eval; }
     }
+    fc.n = fc.n_eval;
+    for (int i = 0; i < fc.n_eval; ++i) fc.flags[i] = 1u;
+    for (int g = 0; g < fc.n_groups; ++g) fc.flags[fc.gend[g] - 1] |= 2u;   // the compact list in the ContactSet convention
     // bins: tile cores on a lattice; a particle whose own cell is in a core has its whole footprint (contact offsets
     // <= R, +1 cell for the approximate own cell, +1 for rounding) inside that bin's tile.  Even margin and core width
     // keep the tile origins even (TMA: 16-byte aligned box start).
@@ -900,8 +904,8 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
     const bool lean = fill_fast_params(ctx, &F, P, *cs);
     if (!lean && ev0) CK(cudaEventRecord(ev0, ctx->stream));
     if (lean) {
-        // bin the particles by map tile, evaluate bin by bin from shared memory; the generic kernel takes what is left
-        // (footprints that leave the map, out-of-range values)
+        // bin the particles by map tile, evaluate bin by bin from shared memory (particles whose footprint leaves the map or
+        // whose values are out of range are flagged and go through contact_eval inside the same kernel)
         const unsigned T = ctx->t_local;
         if (step_or_null) { CK(launch_pdl(ctx, k_project_bin<true>, T, 1024, 0, F, ctx->bin_count, ctx->keys)); ctx->project_step++; }
         else CK(launch_pdl(ctx, k_project_bin<false>, T, 1024, 0, F, ctx->bin_count, ctx->keys));
@@ -915,11 +919,6 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
             CK(launch_pdl(ctx, k_weight_lean<1024>, (unsigned)ctx->sm_count, 1024, smem, F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin));
         LAUNCHED();
         if (ev1) CK(cudaEventRecord(ev1, ctx->stream));
-        // the generic kernel on the list: sized by the list length an earlier update reported (a hint: any grid is correct)
-        const unsigned est = ((volatile DevScalars*)ctx->sc_async)->defer_last;
-        const unsigned lgrid = std::min(grid, est / 1024u + 2u);
-        CK(launch_pdl(ctx, (k_project_weight<false, true, false, true>), lgrid, WT_THREADS, smem, P));
-        LAUNCHED();
         ctx->hint_n = 0;
     } else {
         if (step_or_null) {

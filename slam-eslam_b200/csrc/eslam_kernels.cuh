@@ -98,12 +98,14 @@ struct ModelParams {             // eslam::Configuration hot fields
 // The lean weight kernel's view of one update: only the contact points that pass !(contact < 0.2)
 // (src/ContactModel.cpp:154), grouped (:194-197), and the integer thresholds of the 3-sigma gate on t = zdiff/(sigma corr).
 struct FastContacts {
+    int n;                       // == n_eval: with px/py/pzr/flags below the compact list reads like a ContactSet (contact_eval)
     int n_eval, n_groups;
     int margin;                  // cells: every contact of a particle whose own cell is >= margin inside the tile is in the tile
     uint32_t gate_lo, gate_span; // high word of |t|: below gate_lo -> inside the gate; within [gate_lo, gate_lo+gate_span] -> undecided
     double c0x, c0y;             // 1.5*2^28 - offset/scale: cell quotient with 24 fractional bits (minus the tile origin: tile-relative)
     int bsx, bsy, nbx, nby, nb;  // bins: a lattice of tile cores (tile minus the margin on every side), bsx x bsy cells each
     uint8_t gend[ESLAM_MAX_CONTACTS];   // one past the last evaluated contact of each group (groups without any are dropped)
+    uint8_t flags[ESLAM_MAX_CONTACTS];  // per compact contact: bit0 = 1 (evaluated), bit1 = last of its group
     double px[ESLAM_MAX_CONTACTS + 1], py[ESLAM_MAX_CONTACTS + 1], pzr[ESLAM_MAX_CONTACTS + 1];   // [n_eval] = 0: read ahead by the loop
 };
 
@@ -337,8 +339,8 @@ __device__ __forceinline__ float2 load_cell(bool in_tile, uint32_t tile_saddr, c
 struct PatchRef { const float2* cells; int ox, oy, P; };                 // ox == INT_MIN: not anchored yet
 struct CpRec { int ix[ESLAM_MAX_CP], iy[ESLAM_MAX_CP]; double h[ESLAM_MAX_CP], zv[ESLAM_MAX_CP]; };
 
-template <bool TAP, bool PATCH>
-__device__ __forceinline__ void contact_eval(const ContactSet& cs, const MapParams& M, const MapTile& mt,
+template <bool TAP, bool PATCH, class CS>
+__device__ __forceinline__ void contact_eval(const CS& cs, const MapParams& M, const MapTile& mt,
                                              const em::dbl2* htab, double inv_corr,
                                              double x, double y, double z, double s, double c, double mv,
                                              PoseEval& out, int32_t* tap_cells, double* tap_cp,
@@ -702,7 +704,7 @@ __global__ void __launch_bounds__(1024, 1) k_project_bin(const __grid_constant__
     for (int b = tid; b < F.nb; b += 1024) hist[b] = 0;
     __syncthreads();
     const unsigned long long i = (unsigned long long)blockIdx.x * 1024 + tid;
-    int bin = -1, rank = 0; bool defer = false;
+    int bin = -1, rank = 0; bool flagged = false;
     if (i < C.n) {
         double x = C.st.f[cur][F_X][i], y = C.st.f[cur][F_Y][i], zs = C.st.f[cur][F_ZS][i];
         if (DO_PROJECT) {
@@ -717,30 +719,28 @@ __global__ void __launch_bounds__(1024, 1) k_project_bin(const __grid_constant__
         // has room for that), its bin, and whether its footprint is inside that bin's tile
         const uint64_t ux = em::d2u(em::fma_(x, C.map.inv_sx, C.map.c0x)), uy = em::d2u(em::fma_(y, C.map.inv_sy, C.map.c0y));
         const int cx = (int)(uint32_t)ux >> IDX_FRAC_BITS, cy = (int)(uint32_t)uy >> IDX_FRAC_BITS;
-        bool ok = (((uint32_t)(ux >> 32) - 0x4217FFFFu) <= 1u) & (((uint32_t)(uy >> 32) - 0x4217FFFFu) <= 1u) &
-                  ((unsigned)cx < (unsigned)C.map.W) & ((unsigned)cy < (unsigned)C.map.H) &
-                  (((uint32_t)(em::d2u(mv) >> 52) - 923u) < 199u);       // measVar inside rsqrt_core's range
-        if (ok) {
-            const int b = (cy / F.bsy) * F.nbx + cx / F.bsx;
+        // in the grid and inside the fixed-point range: the particle has a bin (its tile, clamped into the grid, holds every
+        // in-grid cell of its footprint).  Inside the core and measVar inside rsqrt_core's range: the lean evaluation applies;
+        // otherwise the particle is flagged and evaluated by contact_eval from the same tile (map border) or through L2.
+        const bool placed = (((uint32_t)(ux >> 32) - 0x4217FFFFu) <= 1u) & (((uint32_t)(uy >> 32) - 0x4217FFFFu) <= 1u) &
+                            ((unsigned)cx < (unsigned)C.map.W) & ((unsigned)cy < (unsigned)C.map.H);
+        bool ok = placed & (((uint32_t)(em::d2u(mv) >> 52) - 923u) < 199u);   // measVar inside rsqrt_core's range
+        int b = 0;
+        if (placed) {
+            b = (cy / F.bsy) * F.nbx + cx / F.bsx;
             int x0, y0; bin_origin(C.map, F, b, x0, y0);
-            ok = ((unsigned)(cx - x0 - F.margin) < (unsigned)(C.map.tile_w - 2 * F.margin)) &
+            ok = ok & ((unsigned)(cx - x0 - F.margin) < (unsigned)(C.map.tile_w - 2 * F.margin)) &
                  ((unsigned)(cy - y0 - F.margin) < (unsigned)(C.map.tile_h - 2 * F.margin));
-            if (ok) { bin = b; rank = atomicAdd(&hist[b], 1); }
         }
-        defer = !ok;
+        bin = b; rank = atomicAdd(&hist[b], 1);
+        flagged = !ok;
     }
-    // particles the lean kernel cannot take (map border, out of range): the generic kernel's list
-    const unsigned m = __ballot_sync(0xffffffffu, defer);
-    if (m) {
-        unsigned slot = 0;
-        if (lane == (__ffs(m) - 1)) slot = atomicAdd(&C.sc->defer_count, (unsigned)__popc(m));
-        slot = __shfl_sync(0xffffffffu, slot, __ffs(m) - 1);
-        if (defer) C.defer_list[slot + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
-    }
+    const unsigned m = __ballot_sync(0xffffffffu, flagged);
+    if (m && lane == (__ffs(m) - 1)) atomicAdd(&C.sc->defer_count, (unsigned)__popc(m));   // diagnostics only
     __syncthreads();
     for (int b = tid; b < F.nb; b += 1024) { const int c = hist[b]; if (c > 0) gbase[b] = atomicAdd(&bin_count[b], c); }
     __syncthreads();
-    if (i < C.n) keys[i] = make_uint2((unsigned)bin, bin >= 0 ? (unsigned)(gbase[bin] + rank) : 0u);
+    if (i < C.n) keys[i] = make_uint2((unsigned)bin | (flagged ? 0x80000000u : 0u), (unsigned)(gbase[bin] + rank));
 }
 
 // bin-sorted particle list, the offset of every bin in it, and the bin each CTA of the lean kernel starts on
@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(1024, 1) k_bin_scatter(const int* __restrict__
     if (tid == 1023) offs[MAX_BINS] = eo;
     __syncthreads();
     const unsigned long long i = (unsigned long long)blockIdx.x * 1024 + tid;
-    if (i < n) { const uint2 k = keys[i]; if ((int)k.x >= 0) list[offs[k.x] + k.y] = (uint32_t)i; }
+    if (i < n) { const uint2 k = keys[i]; list[offs[k.x & 0x7FFFFFFFu] + k.y] = (uint32_t)i | (k.x & 0x80000000u); }   // bit 31: flagged
     if (blockIdx.x == 0) {
         for (int b = tid; b < nb; b += 1024) bin_offs[b] = offs[b];
         const unsigned M = offs[MAX_BINS];
@@ -910,6 +910,21 @@ __device__ __forceinline__ bool lean_eval(const FastContacts& F, const MapParams
     return EXACT || (border_min >= 2048u && gate_min > F.gate_span);
 }
 
+// a flagged particle (footprint over the map border, out-of-range values): ContactModel::evaluatePose as the generic kernel
+// does it -- tile first, L2 otherwise, exact cell index, the gate as written -- on the compact contact list.  Out of line.
+__device__ __noinline__ void lean_generic_eval(const FastParams* P, const LeanTile* T, const float2* tile, const em::dbl2* htab, int cur,
+                                               unsigned long long i, PoseEval* out) {
+    const WeightCommon& C = P->c;
+    const double x = C.st.f[cur][F_X][i], y = C.st.f[cur][F_Y][i], th = C.st.f[cur][F_TH][i];
+    const double z = C.st.f[cur][F_Z][i], zs = C.st.f[cur][F_ZS][i];
+    double s, c; em::sincos_(th, s, c);
+    const double mv = zs * zs + C.mp.merr2;
+    if (mv == 0) atomicOr(&C.sc->error_flags, ERR_ZERO_VARIANCE_BIT);   // src/ContactModel.cpp:122-123
+    MapTile mt; mt.s = tile; mt.x0 = T->x0; mt.y0 = T->y0; mt.w = C.map.tile_w; mt.h = C.map.tile_h;
+    PatchRef pr; pr.cells = nullptr; pr.ox = INT_MIN; pr.oy = 0; pr.P = 0;
+    contact_eval<false, false>(P->fc, C.map, mt, htab, C.mp.inv_corr, x, y, z, s, c, mv, *out, nullptr, nullptr, pr, nullptr);
+}
+
 // the whole particle again with exact decisions (~2e-4 of the particles); out of line so that it costs the lean loop no registers
 __device__ __noinline__ void lean_redo_exact(const FastParams* P, const LeanTile* T, uint32_t htab_sa, int cur,
                                              unsigned long long i, PoseEval* out) {
@@ -978,11 +993,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_weight_lean(const __grid_constan
                 if (ch >= nch) break;
                 const unsigned k = (ch << 5) + lane;
                 if (k < cnt) {
-                    const unsigned long long i = list[base + k];
+                    const uint32_t entry = list[base + k];
+                    const unsigned long long i = entry & 0x7FFFFFFFu;
                     const double z = C.st.f[cur][F_Z][i], zs = C.st.f[cur][F_ZS][i];
                     const double zs2 = zs * zs;
                     PoseEval ev;
-                    {
+                    if (entry >> 31) lean_generic_eval(&P, &T, tile, htab, cur, i, &ev);
+                    else {
                         const double x = C.st.f[cur][F_X][i], y = C.st.f[cur][F_Y][i], th = C.st.f[cur][F_TH][i];
                         double s, c; em::sincos_(th, s, c);              // :279-282
                         if (!lean_eval<false, 2>(P.fc, C.map, T, htab_sa, C.mp.inv_corr, x, y, s, c, z, zs2 + C.mp.merr2 /* :290 */, ev))

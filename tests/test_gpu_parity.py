@@ -195,6 +195,37 @@ def test_lean_and_generic_weight_kernels_agree(gpu, monkeypatch):
         assert_particles_equal(lean.getParticles(), generic.getParticles())
 
 
+def test_lean_path_at_the_map_border(gpu, oracle, monkeypatch):
+    """A cloud wider than the map (C2: 25.6 m, sigma 8 m): particles near the border and outside are flagged by the
+    binning and evaluated by contact_eval inside the lean kernel; everything must still be bit-identical to the oracle
+    and to the generic kernel."""
+    n = 4096
+    cfg = dict(min_effective=n + 1)
+    g = gpu(abi.default_config(**cfg))
+    o = oracle.OraclePoseEstimator(abi.default_config(**cfg), policy=oracle.SHARED)
+    monkeypatch.setenv("ESLAM_GPU_NO_FAST", "1")
+    generic = gpu(abi.default_config(**cfg))
+    contacts, step = synthetic.setup_filter(generic, "C2", n=n)
+    monkeypatch.delenv("ESLAM_GPU_NO_FAST")
+    for f in (g, o):
+        synthetic.setup_filter(f, "C2", n=n)
+    for f in (g, o, generic):
+        f.init(n, (0.0, 0.0, 0.0), (8.0, 8.0, 0.3), synthetic.terrain_height(0, 0) + 0.19, 1.001)
+    for i in range(3):
+        monkeypatch.setenv("ESLAM_GPU_NO_FAST", "1")
+        rc = generic.stepFused(step, contacts)
+        monkeypatch.delenv("ESLAM_GPU_NO_FAST")
+        ra = g.stepFused(step, contacts)
+        o.project(step)
+        rb = o.update(contacts)
+        assert ra.as_dict() == rb.as_dict() == rc.as_dict(), "step %d" % i
+        pc = g.pathCounters()
+        assert pc["lean"] == n and n // 20 < pc["deferred"] < n, pc      # a good share is flagged, not all
+        assert np.array_equal(g.getAncestors(), o.getAncestors())
+        assert_particles_equal(g.getParticles(), o.getParticles())
+        assert_particles_equal(g.getParticles(), generic.getParticles())
+
+
 def test_fused_step_equals_project_then_update(gpu):
     g1, g2 = gpu(abi.default_config(min_effective=10001)), gpu(abi.default_config(min_effective=10001))
     contacts, step = synthetic.setup_filter(g1, "C2")
