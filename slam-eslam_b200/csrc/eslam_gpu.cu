@@ -36,7 +36,6 @@ struct eslam_gpu_ctx {
     DevScalars* sc_async;                         // pinned mirror refreshed after every update on a side stream (never waited for)
     cudaStream_t side; cudaEvent_t side_ev;
     uint32_t* ancestors; double* cdf;
-    uint32_t* defer_list;                         // particles the lean weight kernel hands to the generic one (n entries)
     double* hint; unsigned hint_n;                // per-CTA sums of x, y (tile placement hint), entries written by the last update
     unsigned* ticket;                             // "last CTA" counter of k_resample_local
     bool last_lean;                               // the last update went through the lean path
@@ -150,7 +149,7 @@ static void free_particles(eslam_gpu_ctx* ctx) {
         for (int f = 0; f < 7; ++f) dfree(ctx->st.f[b][f]);
         for (int f = 0; f < 2; ++f) dfree(ctx->st.b[b][f]);
     }
-    dfree(ctx->ancestors); dfree(ctx->cdf); dfree(ctx->defer_list); dfree(ctx->keys); dfree(ctx->bin_list);
+    dfree(ctx->ancestors); dfree(ctx->cdf); dfree(ctx->keys); dfree(ctx->bin_list);
     for (int b = 0; b < 2; ++b) { dfree(ctx->patch[b]); dfree(ctx->porigin[b]); }
     const bool sh = ctx->g_part_a != ctx->l_part_a;
     if (sh) { dfree(ctx->xchg); ctx->g_part_a = nullptr; ctx->g_tile_sum = nullptr; ctx->g_pack = nullptr;
@@ -231,7 +230,7 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
             for (int f = 0; f < 7; ++f) CK(dalloc(&ctx->st.f[b][f], n));
             for (int f = 0; f < 2; ++f) CK(dalloc(&ctx->st.b[b][f], n));
         }
-        CK(dalloc(&ctx->ancestors, n)); CK(dalloc(&ctx->cdf, n)); CK(dalloc(&ctx->defer_list, n));
+        CK(dalloc(&ctx->ancestors, n)); CK(dalloc(&ctx->cdf, n));
         CK(dalloc(&ctx->keys, n)); CK(dalloc(&ctx->bin_list, n));
         if (ctx->cfg.patch_size > 0) {
             const size_t pp = (size_t)ctx->cfg.patch_size * ctx->cfg.patch_size;
@@ -398,7 +397,7 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     if (shard) ctx->shard = *shard;
     ctx->comm = nullptr; ctx->has_comm = false;
     ctx->device = device; ctx->launches = 0; ctx->n = ctx->cap = 0; ctx->t_local = ctx->t_global = ctx->t_cap = 0;
-    ctx->ancestors = nullptr; ctx->cdf = nullptr; ctx->defer_list = nullptr; ctx->hint = nullptr; ctx->hint_n = 0;
+    ctx->ancestors = nullptr; ctx->cdf = nullptr; ctx->hint = nullptr; ctx->hint_n = 0;
     ctx->grid_sane = false;
     ctx->last_lean = false; ctx->ticket = nullptr;
     ctx->timing = getenv("ESLAM_GPU_TIMING") != nullptr; ctx->marks_used = 0;
@@ -552,11 +551,10 @@ int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int he
         }
     }
     const int bytes = (int)weight_smem_bytes(ctx);
-    CK(cudaFuncSetAttribute(k_project_weight<true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_project_weight<false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_project_weight<true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_project_weight<false, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_project_weight<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_project_weight<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_project_weight<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_project_weight<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_project_weight<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_weight_lean<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_weight_lean<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -652,7 +650,7 @@ static void fill_weight_params(eslam_gpu_ctx* ctx, WeightParams* P, const eslam_
     P->patch_size = ctx->cfg.patch_size > 0 ? ctx->cfg.patch_size : 0;
     P->use_tma = ctx->has_tmap && !getenv("ESLAM_GPU_NO_TMA");
     P->tmap = ctx->d_tmap;
-    P->defer_list = ctx->defer_list; P->hint = ctx->hint;
+    P->hint = ctx->hint;
     for (int b = 0; b < 2; ++b) { P->patch[b] = ctx->patch[b]; P->porigin[b] = ctx->porigin[b]; }
     if (step) {
         P->yaw = step->yaw; P->z_delta = step->z_delta; P->z_var = step->z_var;
@@ -673,7 +671,7 @@ static bool fill_fast_params(eslam_gpu_ctx* ctx, FastParams* F, const WeightPara
     memset(F, 0, sizeof(*F));
     WeightCommon& c = F->c;
     c.st = P.st; c.sc = P.sc; c.map = P.map; c.mp = P.mp; c.htab = P.htab; c.n = P.n; c.base = P.base;
-    c.project_step = P.project_step; c.use_tma = P.use_tma; c.tmap = P.tmap; c.defer_list = P.defer_list; c.hint = P.hint;
+    c.project_step = P.project_step; c.use_tma = P.use_tma; c.tmap = P.tmap; c.hint = P.hint;
     c.yaw = P.yaw; c.z_delta = P.z_delta; c.z_var = P.z_var;
     for (int i = 0; i < 3; ++i) { c.dmean[i] = P.dmean[i]; c.dsigma[i] = P.dsigma[i]; }
     FastContacts& fc = F->fc;
@@ -922,11 +920,11 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
         ctx->hint_n = 0;
     } else {
         if (step_or_null) {
-            if (patches) CK(launch_pdl(ctx, (k_project_weight<true, true, true, false>), grid, WT_THREADS, smem, P));
-            else CK(launch_pdl(ctx, (k_project_weight<true, true, false, false>), grid, WT_THREADS, smem, P));
+            if (patches) CK(launch_pdl(ctx, (k_project_weight<true, true, true>), grid, WT_THREADS, smem, P));
+            else CK(launch_pdl(ctx, (k_project_weight<true, true, false>), grid, WT_THREADS, smem, P));
             ctx->project_step++;
-        } else if (patches) CK(launch_pdl(ctx, (k_project_weight<false, true, true, false>), grid, WT_THREADS, smem, P));
-        else CK(launch_pdl(ctx, (k_project_weight<false, true, false, false>), grid, WT_THREADS, smem, P));
+        } else if (patches) CK(launch_pdl(ctx, (k_project_weight<false, true, true>), grid, WT_THREADS, smem, P));
+        else CK(launch_pdl(ctx, (k_project_weight<false, true, false>), grid, WT_THREADS, smem, P));
         LAUNCHED();
         ctx->hint_n = grid;
         if (ev1) CK(cudaEventRecord(ev1, ctx->stream));
@@ -995,7 +993,7 @@ int eslam_gpu_project(eslam_gpu_ctx* ctx, const eslam_gpu_step* step) {
     if (!step) return ESLAM_ERR_INVALID;
     WeightParams P;
     fill_weight_params(ctx, &P, step, nullptr);
-    k_project_weight<true, false, false, false><<<weight_grid(ctx), WT_THREADS, 0, ctx->stream>>>(P);
+    k_project_weight<true, false, false><<<weight_grid(ctx), WT_THREADS, 0, ctx->stream>>>(P);
     ctx->project_step++;
     LAUNCHED();
     return ESLAM_OK;

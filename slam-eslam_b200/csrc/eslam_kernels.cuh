@@ -60,7 +60,7 @@ struct DevScalars {              // device-resident scalars of one context
     int n_boundaries;
     int pool_count;              // boundary-element pool allocator (reset by k_reduce_b)
     unsigned int fallbacks;      // times the sequential CDF fallback ran
-    unsigned int defer_count;    // particles the lean weight kernel handed to the generic one (live counter)
+    unsigned int defer_count;    // particles the binning flagged for contact_eval (map border, out-of-range values; live counter)
     unsigned int defer_last;     // its value at the end of the last update (diagnostics)
 };
 
@@ -117,7 +117,6 @@ struct WeightCommon {
     uint32_t project_step;
     int use_tma;                 // the map tile is staged by one TMA bulk tensor copy (tmap valid)
     const CUtensorMap* tmap;     // device copy of the 2-D tensor map of the elevation grid (8-byte cells, box = the tile)
-    uint32_t* defer_list;        // particles the lean kernel could not decide (order irrelevant)
     double* hint;                // [gridDim.x][2]: sums of x and y over the particles a CTA handled (tile placement hint)
     double yaw, z_delta, z_var, dmean[3], dsigma[3];
 };
@@ -134,7 +133,6 @@ struct WeightParams {
     int use_tma;                 // the map tile is staged by one TMA bulk tensor copy (tmap valid)
     const CUtensorMap* tmap;     // device copy of the 2-D tensor map of the elevation grid (8-byte cells, box = the tile)
     float2* patch[2]; int* porigin[2];   // double buffered with the particle state: [N][P][P] cells, [N][2] origins
-    uint32_t* defer_list;        // LIST mode: the particles to evaluate (count = sc->defer_count)
     double* hint;                // [gridDim.x][2]: sums of x and y over the particles a CTA handled (tile placement hint)
     double yaw, z_delta, z_var, dmean[3], dsigma[3];
     ContactSet cs;
@@ -1028,9 +1026,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_weight_lean(const __grid_constan
 }
 
 // ---- the generic path ---------------------------------------------------------------------------------------------
-// Any particle, any map (tile + L2 fallback, exact cell index, per-particle patches, C_global2local).  LIST: evaluate
-// the particles the lean kernel handed over (already projected); otherwise all particles.
-template <bool DO_PROJECT, bool DO_WEIGHT, bool PATCH, bool LIST>
+// Any particle, any map (tile + L2 fallback, exact cell index, per-particle patches, C_global2local).
+template <bool DO_PROJECT, bool DO_WEIGHT, bool PATCH>
 __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_constant__ WeightParams P) {
     pdl_start();
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1039,9 +1036,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_c
     const int tid = threadIdx.x, lane = tid & 31;
     const DevScalars* sc = P.sc;
     const int cur = sc->cur;
-    const unsigned long long count = LIST ? (unsigned long long)sc->defer_count : P.n;
+    const unsigned long long count = P.n;
     const unsigned long long n_chunks = (count + 31) >> 5;
-    if (LIST && (unsigned long long)blockIdx.x >= n_chunks) return;     // nothing for this CTA (its warp 0 would be the first to get work)
     MapTile mt; mt.s = nullptr; mt.w = 0; mt.h = 0; mt.x0 = 0; mt.y0 = 0;
     if (DO_WEIGHT) mt = stage_tile_and_table(P.map, P.use_tma, P.tmap, P.htab, smem_raw);
     double spread = 0.0;
@@ -1053,7 +1049,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_c
     for (unsigned long long ch = first_chunk(); ch < n_chunks; ch += chunk_stride()) {
         const unsigned long long k = (ch << 5) + lane;
         if (k >= count) continue;
-        const unsigned long long i = LIST ? (unsigned long long)P.defer_list[k] : k;
+        const unsigned long long i = k;
         double x = X[i], y = Y[i], th = TH[i], z = Z[i], zs = ZS[i], w = WG[i];
         if (DO_PROJECT) {                                                        // :196-237
             project_particle(P, P.base + i, spread, x, y, th, z, zs, w);
@@ -1081,7 +1077,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_c
             finish_particle(P, cur, i, ev, z, zs2, w);
         }
     }
-    if (!LIST && DO_WEIGHT) write_hint(hx, hy, red, P.hint);
+    if (DO_WEIGHT) write_hint(hx, hy, red, P.hint);
 }
 
 // ------------------------------------------------------------------------------------------------ loop A partials
@@ -1510,15 +1506,32 @@ __global__ void __launch_bounds__(1024, 1) k_chain(ChainPack pk, unsigned n_tile
     const unsigned tiles_per_rank = pk.tiles_per_rank;
     extern __shared__ __align__(16) unsigned char chain_raw[];
     ChainSmem& cs = *reinterpret_cast<ChainSmem*>(chain_raw);
-    __shared__ int sh_i[1024];
-    __shared__ SegE sh_e[1024];
+    __shared__ int sh_i[64];             // [0,32): warp totals, [32,64): their inclusive scan
+    __shared__ SegE sh_e[64];
     __shared__ int s_total, s_bad, s_go;
     const unsigned tid = threadIdx.x;
     if (decide) {
-        for (unsigned i = tid; i < n_tiles; i += blockDim.x) scratch_a[i] = pk.tile_sq(i);
-        __syncthreads();
-        const double eff = block_tree_reduce(scratch_a, scratch_b, n_tiles, reinterpret_cast<double*>(chain_raw),
-                                             reinterpret_cast<double*>(chain_raw) + TREE_SMEM);
+        double eff;
+        if (n_tiles > 1 && ((n_tiles + 1) >> 1) <= TREE_SMEM) {
+            // first level of the tree straight from the pack, the rest in shared memory (same tree as block_tree_reduce)
+            double* ta = reinterpret_cast<double*>(chain_raw); double* tb = ta + TREE_SMEM;
+            unsigned m = (n_tiles + 1) >> 1;
+            for (unsigned i = tid; i < m; i += blockDim.x) ta[i] = (2 * i + 1 < n_tiles) ? pk.tile_sq(2 * i) + pk.tile_sq(2 * i + 1) : pk.tile_sq(2 * i);
+            __syncthreads();
+            while (m > 1) {
+                const unsigned h = (m + 1) >> 1;
+                for (unsigned i = tid; i < h; i += blockDim.x) tb[i] = (2 * i + 1 < m) ? ta[2 * i] + ta[2 * i + 1] : ta[2 * i];
+                __syncthreads();
+                double* t = ta; ta = tb; tb = t; m = h;
+            }
+            eff = ta[0];
+            __syncthreads();
+        } else {
+            for (unsigned i = tid; i < n_tiles; i += blockDim.x) scratch_a[i] = pk.tile_sq(i);
+            __syncthreads();
+            eff = block_tree_reduce(scratch_a, scratch_b, n_tiles, reinterpret_cast<double*>(chain_raw),
+                                    reinterpret_cast<double*>(chain_raw) + TREE_SMEM);
+        }
         if (tid == 0) {
             const double ess = 1.0 / eff;                                             // src/ParticleFilter.hpp:69
             sc->ess = ess;
@@ -1546,21 +1559,32 @@ __global__ void __launch_bounds__(1024, 1) k_chain(ChainPack pk, unsigned n_tile
         } else { e.head = -1; e.f.b = D.head_b; e.f.d0 = D.head_d0; e.f.d1 = D.head_d1; e.f.pad = D.pad; }
         agg = sege_combine(agg, e);
     }
-    sh_i[tid] = cnt; sh_e[tid] = agg;
     if (bad) atomicOr(&s_bad, 1);
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        int ci = 0; SegE ce; ce.f = segf_identity(); ce.head = -1;
-        const bool has = tid >= (unsigned)o;
-        if (has) { ci = sh_i[tid - o]; ce = sh_e[tid - o]; }
-        __syncthreads();
-        if (has) { sh_i[tid] += ci; sh_e[tid] = sege_combine(ce, sh_e[tid]); }
-        __syncthreads();
+    // inclusive scan over the 1024 threads: inside the warp by shuffles, across the 32 warp totals by warp 0
+    const unsigned lane = tid & 31, warp = tid >> 5;
+    int inc_c = cnt; SegE inc_e = agg;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const SegE v = sege_shfl_up(inc_e, o); const int cv = __shfl_up_sync(0xffffffffu, inc_c, o);
+        if (lane >= (unsigned)o) { inc_e = sege_combine(v, inc_e); inc_c += cv; }
     }
-    if (tid == 1023) s_total = sh_i[1023];
-    int run_c = sh_i[tid] - cnt;
-    SegE run_e; run_e.f = segf_identity(); run_e.head = -1;
-    if (tid > 0) run_e = sh_e[tid - 1];
+    if (lane == 31) { sh_i[warp] = inc_c; sh_e[warp] = inc_e; }
+    __syncthreads();
+    if (warp == 0) {
+        int wc = sh_i[lane]; SegE we = sh_e[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const SegE v = sege_shfl_up(we, o); const int cv = __shfl_up_sync(0xffffffffu, wc, o);
+            if (lane >= (unsigned)o) { we = sege_combine(v, we); wc += cv; }
+        }
+        sh_i[32 + lane] = wc; sh_e[32 + lane] = we;                      // inclusive over warps
+    }
+    __syncthreads();
+    if (tid == 0) s_total = sh_i[32 + 31];
+    // exclusive value of this thread: (all earlier warps) o (earlier lanes of this warp)
+    SegE run_e = sege_shfl_up(inc_e, 1); int run_c = __shfl_up_sync(0xffffffffu, inc_c, 1);
+    if (lane == 0) { run_e.f = segf_identity(); run_e.head = -1; run_c = 0; }
+    if (warp > 0) { run_e = sege_combine(sh_e[32 + warp - 1], run_e); run_c += sh_i[32 + warp - 1]; }
     __syncthreads();
     const int total = s_total;
     if (total > MAX_BND_TOTAL) { if (tid == 0) s_bad = 1; }
