@@ -1137,13 +1137,30 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_a(const TilePartA* part, uns
     __shared__ unsigned long long redull[64];
     __shared__ double tree_a[TREE_SMEM], tree_b[TREE_SMEM / 2];
     double mx = 0; unsigned long long cnt = 0, pts = 0;
+    const bool direct = n_tiles > 1 && ((n_tiles + 1) >> 1) <= TREE_SMEM;   // first tree level straight from the partials
     for (unsigned i = threadIdx.x; i < n_tiles; i += blockDim.x) {
         const TilePartA p = part[i];
-        scratch_a[i] = p.sum_pw;
+        if (!direct) scratch_a[i] = p.sum_pw;
         mx = fmax(mx, p.max_w); cnt += p.cnt; pts += p.pts;
     }
-    __syncthreads();
-    const double sum_pw = block_tree_reduce(scratch_a, scratch_b, n_tiles, tree_a, tree_b);
+    double sum_pw;
+    if (direct) {
+        double *ta = tree_a, *tb = tree_b;
+        unsigned m = (n_tiles + 1) >> 1;
+        for (unsigned i = threadIdx.x; i < m; i += blockDim.x) ta[i] = (2 * i + 1 < n_tiles) ? part[2 * i].sum_pw + part[2 * i + 1].sum_pw : part[2 * i].sum_pw;
+        __syncthreads();
+        while (m > 1) {
+            const unsigned h = (m + 1) >> 1;
+            for (unsigned i = threadIdx.x; i < h; i += blockDim.x) tb[i] = (2 * i + 1 < m) ? ta[2 * i] + ta[2 * i + 1] : ta[2 * i];
+            __syncthreads();
+            double* t = ta; ta = tb; tb = t; m = h;
+        }
+        sum_pw = ta[0];
+        __syncthreads();
+    } else {
+        __syncthreads();
+        sum_pw = block_tree_reduce(scratch_a, scratch_b, n_tiles, tree_a, tree_b);
+    }
     mx = warp_max(mx);
     for (int o = 1; o < 32; o <<= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); pts += __shfl_xor_sync(0xffffffffu, pts, o); }
     __syncthreads();
@@ -1217,14 +1234,32 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_b(const double* tile_sum, un
                                                       double* tile_prefix, int normalise, const unsigned* xflags, unsigned epoch, int world) {
     pdl_start();
     peer_wait(xflags, epoch, world);
-    __shared__ double sh[1024];
+    __shared__ double sh[64];
     __shared__ double tree_a[TREE_SMEM], tree_b[TREE_SMEM / 2];
-    for (unsigned i = threadIdx.x; i < n_tiles; i += blockDim.x) scratch_a[i] = tile_sum[i];
-    __syncthreads();
-    const double total = block_tree_reduce(scratch_a, scratch_b, n_tiles, tree_a, tree_b);
+    double total;
+    if (n_tiles > 1 && ((n_tiles + 1) >> 1) <= TREE_SMEM) {
+        // the tree straight from the tile sums (no copy through global scratch); same tree as block_tree_reduce
+        double *ta = tree_a, *tb = tree_b;
+        unsigned m = (n_tiles + 1) >> 1;
+        for (unsigned i = threadIdx.x; i < m; i += blockDim.x) ta[i] = (2 * i + 1 < n_tiles) ? tile_sum[2 * i] + tile_sum[2 * i + 1] : tile_sum[2 * i];
+        __syncthreads();
+        while (m > 1) {
+            const unsigned h = (m + 1) >> 1;
+            for (unsigned i = threadIdx.x; i < h; i += blockDim.x) tb[i] = (2 * i + 1 < m) ? ta[2 * i] + ta[2 * i + 1] : ta[2 * i];
+            __syncthreads();
+            double* t = ta; ta = tb; tb = t; m = h;
+        }
+        total = ta[0];
+        __syncthreads();
+    } else {
+        for (unsigned i = threadIdx.x; i < n_tiles; i += blockDim.x) scratch_a[i] = tile_sum[i];
+        __syncthreads();
+        total = block_tree_reduce(scratch_a, scratch_b, n_tiles, tree_a, tree_b);
+    }
     const int uniform = normalise && (total <= 0.0);                                 // :51 (Q8)
     if (threadIdx.x == 0) { sc->sum_w = total; sc->uniform = uniform; sc->pool_count = 0; }
-    // exclusive scan of the per-tile masses (approximate is enough: only used to classify elements)
+    // exclusive scan of the per-tile masses (approximate is enough: only used to classify elements; k_norm_scan and k_cdf
+    // read the same values)
     const unsigned per = (n_tiles + blockDim.x - 1) / blockDim.x;
     const unsigned lo = threadIdx.x * per, hi = min(lo + per, n_tiles);
     auto mass = [&](unsigned t) -> double {
@@ -1233,15 +1268,20 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_b(const double* tile_sum, un
     };
     double local = 0;
     for (unsigned t = lo; t < hi; ++t) local += mass(t);
-    sh[threadIdx.x] = local;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (unsigned)o) inc += v; }
+    if (lane == 31) sh[warp] = inc;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const double v = (threadIdx.x >= (unsigned)o) ? sh[threadIdx.x - o] : 0.0;
-        __syncthreads();
-        sh[threadIdx.x] += v;
-        __syncthreads();
+    if (warp == 0) {
+        double w = sh[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= (unsigned)o) w += v; }
+        sh[32 + lane] = w;
     }
-    double run = sh[threadIdx.x] - local;
+    __syncthreads();
+    double run = (inc - local) + (warp ? sh[32 + warp - 1] : 0.0);
     for (unsigned t = lo; t < hi; ++t) { tile_prefix[t] = run; run += mass(t); }
 }
 
