@@ -180,6 +180,8 @@ def main():
     from slam_eslam_b200 import GpuPoseEstimator, abi, synthetic, dist
     w = synthetic.WORKLOADS[args.workload]
     n_local, c = w["n"], w["c"]
+    if args.workload == "C5":                                            # 16M particles in total, sharded over the ranks
+        n_local = (w["n"] // world) // 1024 * 1024
     torch.cuda.set_device(local_rank)
     comm = dist.init(world, rank, local_rank) if world > 1 else None
     n_global = n_local * world
