@@ -1260,29 +1260,32 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_b(const double* tile_sum, un
     if (threadIdx.x == 0) { sc->sum_w = total; sc->uniform = uniform; sc->pool_count = 0; }
     // exclusive scan of the per-tile masses (approximate is enough: only used to classify elements; k_norm_scan and k_cdf
     // read the same values)
-    const unsigned per = (n_tiles + blockDim.x - 1) / blockDim.x;
-    const unsigned lo = threadIdx.x * per, hi = min(lo + per, n_tiles);
     auto mass = [&](unsigned t) -> double {
         if (uniform) { const unsigned long long c = min((unsigned long long)TILE, n - (unsigned long long)t * TILE); return (double)c / (double)n; }
         return normalise ? tile_sum[t] / total : tile_sum[t];
     };
-    double local = 0;
-    for (unsigned t = lo; t < hi; ++t) local += mass(t);
+    // rounds of 1024 tiles, one per thread (coalesced): block exclusive scan by shuffles, a carry from round to round
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double inc = local;
+    double carry = 0.0;
+    for (unsigned r0 = 0; r0 < n_tiles; r0 += 1024) {
+        const unsigned t = r0 + threadIdx.x;
+        const double local = t < n_tiles ? mass(t) : 0.0;
+        double inc = local;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (unsigned)o) inc += v; }
-    if (lane == 31) sh[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        double w = sh[lane];
+        for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (unsigned)o) inc += v; }
+        if (lane == 31) sh[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            double w = sh[lane];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= (unsigned)o) w += v; }
-        sh[32 + lane] = w;
+            for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= (unsigned)o) w += v; }
+            sh[32 + lane] = w;
+        }
+        __syncthreads();
+        if (t < n_tiles) tile_prefix[t] = carry + ((warp ? sh[32 + warp - 1] : 0.0) + (inc - local));
+        carry += sh[32 + 31];                                            // every thread keeps the same carry
+        __syncthreads();
     }
-    __syncthreads();
-    double run = (inc - local) + (warp ? sh[32 + warp - 1] : 0.0);
-    for (unsigned t = lo; t < hi; ++t) { tile_prefix[t] = run; run += mass(t); }
 }
 
 // ------------------------------------------------------------------------------------------------ exact running sum
@@ -1584,73 +1587,72 @@ __global__ void __launch_bounds__(1024, 1) k_chain(ChainPack pk, unsigned n_tile
     __syncthreads();
     if (!s_go) return;
 
-    // exclusive prefix of boundary counts + segmented exclusive scan of tile functions
-    const unsigned per = (n_tiles + blockDim.x - 1) / blockDim.x;
-    const unsigned lo = tid * per, hi = min(lo + per, n_tiles);
-    int cnt = 0; SegE agg; agg.f = segf_identity(); agg.head = -1; int bad = 0;
-    for (unsigned t = lo; t < hi; ++t) {
-        const TileDesc& D = pk.desc(t);
-        if (D.overflow) bad = 1;
-        cnt += D.n_bnd;
-        SegE e;
-        if (D.n_bnd > 0 && !D.overflow) {
-            const BndEntry& L = pk.pool(t / tiles_per_rank)[D.bnd_base + D.n_bnd - 1];
-            e.head = (int)t; e.f.b = L.b; e.f.d0 = L.d0; e.f.d1 = L.d1; e.f.pad = 0;
-        } else { e.head = -1; e.f.b = D.head_b; e.f.d0 = D.head_d0; e.f.d1 = D.head_d1; e.f.pad = D.pad; }
-        agg = sege_combine(agg, e);
-    }
-    if (bad) atomicOr(&s_bad, 1);
-    // inclusive scan over the 1024 threads: inside the warp by shuffles, across the 32 warp totals by warp 0
+    // Rounds of 1024 tiles, one tile per thread (coalesced, independent loads): per round an exclusive scan of the boundary
+    // counts and a segmented exclusive scan of the tile functions (shuffles inside the warp, warp 0 across the warp totals),
+    // continued from round to round by a carry.  Each thread then places its tile's boundary elements and segment
+    // functions into the chain arrays straight away.
     const unsigned lane = tid & 31, warp = tid >> 5;
-    int inc_c = cnt; SegE inc_e = agg;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const SegE v = sege_shfl_up(inc_e, o); const int cv = __shfl_up_sync(0xffffffffu, inc_c, o);
-        if (lane >= (unsigned)o) { inc_e = sege_combine(v, inc_e); inc_c += cv; }
-    }
-    if (lane == 31) { sh_i[warp] = inc_c; sh_e[warp] = inc_e; }
+    __shared__ int s_carry_c; __shared__ SegE s_carry_e;
+    if (tid == 0) { s_carry_c = 0; s_carry_e.f = segf_identity(); s_carry_e.head = -1; }
     __syncthreads();
-    if (warp == 0) {
-        int wc = sh_i[lane]; SegE we = sh_e[lane];
+    for (unsigned r0 = 0; r0 < n_tiles; r0 += 1024) {
+        const unsigned t = r0 + tid;
+        const bool have = t < n_tiles;
+        TileDesc D; D.n_bnd = 0; D.overflow = 0; D.head_b = BIN_NONE; D.pad = 0; D.head_d0 = 0; D.head_d1 = 0; D.bnd_base = 0; D.pad2 = 0;
+        if (have) D = pk.desc(t);
+        const BndEntry* B = pk.pool(have ? t / tiles_per_rank : 0) + D.bnd_base;
+        if (D.overflow) atomicOr(&s_bad, 1);
+        const int cnt = D.overflow ? 0 : D.n_bnd;
+        SegE e;                                                          // what the tile does to the running function
+        if (cnt > 0) { const BndEntry& Lb = B[cnt - 1]; e.head = (int)t; e.f.b = Lb.b; e.f.d0 = Lb.d0; e.f.d1 = Lb.d1; e.f.pad = 0; }
+        else { e.head = -1; e.f.b = D.head_b; e.f.d0 = D.head_d0; e.f.d1 = D.head_d1; e.f.pad = D.pad; }
+        int inc_c = cnt; SegE inc_e = e;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const SegE v = sege_shfl_up(we, o); const int cv = __shfl_up_sync(0xffffffffu, wc, o);
-            if (lane >= (unsigned)o) { we = sege_combine(v, we); wc += cv; }
+            const SegE v = sege_shfl_up(inc_e, o); const int cv = __shfl_up_sync(0xffffffffu, inc_c, o);
+            if (lane >= (unsigned)o) { inc_e = sege_combine(v, inc_e); inc_c += cv; }
         }
-        sh_i[32 + lane] = wc; sh_e[32 + lane] = we;                      // inclusive over warps
+        if (lane == 31) { sh_i[warp] = inc_c; sh_e[warp] = inc_e; }
+        __syncthreads();
+        if (warp == 0) {
+            int wc = sh_i[lane]; SegE we = sh_e[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const SegE v = sege_shfl_up(we, o); const int cv = __shfl_up_sync(0xffffffffu, wc, o);
+                if (lane >= (unsigned)o) { we = sege_combine(v, we); wc += cv; }
+            }
+            sh_i[32 + lane] = wc; sh_e[32 + lane] = we;                  // inclusive over warps
+        }
+        __syncthreads();
+        // exclusive value of this thread: carry o (all earlier warps) o (earlier lanes of this warp)
+        SegE run_e = sege_shfl_up(inc_e, 1); int run_c = __shfl_up_sync(0xffffffffu, inc_c, 1);
+        if (lane == 0) { run_e.f = segf_identity(); run_e.head = -1; run_c = 0; }
+        if (warp > 0) { run_e = sege_combine(sh_e[32 + warp - 1], run_e); run_c += sh_i[32 + warp - 1]; }
+        run_e = sege_combine(s_carry_e, run_e); run_c += s_carry_c;
+        const SegE round_e = sh_e[32 + 31]; const int round_c = sh_i[32 + 31];
+        if (have) {
+            tile_bofs[t] = run_c; tile_pre[t] = run_e.f;
+            // boundary k = run_c + j: weight, and the function of the segment that follows it
+            for (int j = 0; j < cnt; ++j) {
+                if (run_c + j < MAX_BND_TOTAL) {
+                    cs.bw[run_c + j] = B[j].w;
+                    if (j + 1 < cnt) { SegF f; f.b = B[j].b; f.d0 = B[j].d0; f.d1 = B[j].d1; f.pad = 0; cs.seg[run_c + j] = f; }
+                }
+            }
+            if (cnt > 0 && run_c > 0 && run_c - 1 < MAX_BND_TOTAL) {
+                // segment after boundary run_c-1 ends with this tile's head piece
+                SegF hf; hf.b = D.head_b; hf.d0 = D.head_d0; hf.d1 = D.head_d1; hf.pad = D.pad;
+                cs.seg[run_c - 1] = segf_compose(run_e.f, hf);
+            }
+        }
+        __syncthreads();                                                 // everyone has read the carry and the round totals
+        if (tid == 0) { s_carry_e = sege_combine(s_carry_e, round_e); s_carry_c += round_c; }
+        __syncthreads();
     }
-    __syncthreads();
-    if (tid == 0) s_total = sh_i[32 + 31];
-    // exclusive value of this thread: (all earlier warps) o (earlier lanes of this warp)
-    SegE run_e = sege_shfl_up(inc_e, 1); int run_c = __shfl_up_sync(0xffffffffu, inc_c, 1);
-    if (lane == 0) { run_e.f = segf_identity(); run_e.head = -1; run_c = 0; }
-    if (warp > 0) { run_e = sege_combine(sh_e[32 + warp - 1], run_e); run_c += sh_i[32 + warp - 1]; }
-    __syncthreads();
-    const int total = s_total;
-    if (total > MAX_BND_TOTAL) { if (tid == 0) s_bad = 1; }
+    const int total = s_carry_c;
+    if (tid == 0 && total > MAX_BND_TOTAL) s_bad = 1;
     __syncthreads();
     if (s_bad) { if (tid == 0) { atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT); sc->n_boundaries = total; } return; }
-    for (unsigned t = lo; t < hi; ++t) {
-        const TileDesc& D = pk.desc(t);
-        tile_bofs[t] = run_c; tile_pre[t] = run_e.f;
-        // boundary k = run_c + j: weight, and the function of the segment that follows it
-        const BndEntry* B = pk.pool(t / tiles_per_rank) + D.bnd_base;
-        for (int j = 0; j < D.n_bnd; ++j) {
-            cs.bw[run_c + j] = B[j].w;
-            if (j + 1 < D.n_bnd) { SegF f; f.b = B[j].b; f.d0 = B[j].d0; f.d1 = B[j].d1; f.pad = 0; cs.seg[run_c + j] = f; }
-        }
-        if (D.n_bnd > 0 && run_c > 0) {
-            // segment after boundary run_c-1 ends with this tile's head piece
-            SegF hf; hf.b = D.head_b; hf.d0 = D.head_d0; hf.d1 = D.head_d1; hf.pad = D.pad;
-            cs.seg[run_c - 1] = segf_compose(run_e.f, hf);
-        }
-        SegE e;
-        if (D.n_bnd > 0) { const BndEntry& L = B[D.n_bnd - 1]; e.head = (int)t; e.f.b = L.b; e.f.d0 = L.d0; e.f.d1 = L.d1; e.f.pad = 0; }
-        else { e.head = -1; e.f.b = D.head_b; e.f.d0 = D.head_d0; e.f.d1 = D.head_d1; e.f.pad = D.pad; }
-        run_e = sege_combine(run_e, e);
-        run_c += D.n_bnd;
-    }
-    __syncthreads();
     if (tid == 0) {
         // the sequential part: one real fp64 add per boundary element, one integer add per segment
         double S = 0.0; int b2 = 0;
@@ -1666,7 +1668,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(ChainPack pk, unsigned n_tile
     if (s_bad) return;
     for (unsigned k = tid; k < (unsigned)total; k += blockDim.x) sb_out[k] = cs.bw[k];
     int b3 = 0;
-    for (unsigned t = lo; t < hi; ++t) {
+    for (unsigned t = tid; t < n_tiles; t += blockDim.x) {               // (each thread reads back what it wrote above)
         const int ofs = tile_bofs[t];
         const double S0 = ofs > 0 ? cs.bw[ofs - 1] : 0.0;
         tile_sin[t] = segf_apply(S0, tile_pre[t], b3);

@@ -65,6 +65,7 @@ WORKLOADS = {
     "C3": dict(n=1048576, c=64, grid=2048, sigma_xy=2.0),
     "C4": dict(n=100000, c=64, grid=4096, sigma_xy=2.0),
     "C5": dict(n=16777216, c=64, grid=4096, sigma_xy=2.0),
+    "C3x8": dict(n=8388608, c=64, grid=2048, sigma_xy=2.0),   # 8192 tiles on one GPU: what the single-CTA kernels see at 8 ranks
 }
 
 
