@@ -267,6 +267,13 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
         ctx->cap = n; ctx->t_cap = (unsigned)t;
     }
     ctx->n = n; ctx->t_local = (unsigned)((n + TILE - 1) / TILE); ctx->t_global = ctx->t_local * G;
+    if (G == 1) {                                                       // one GPU: the "peer" table maps this context's own buffers
+        ctx->peers.cdf[0] = ctx->cdf;
+        for (int b = 0; b < 2; ++b) {
+            for (int f = 0; f < 7; ++f) ctx->peers.f[0][b][f] = ctx->st.f[b][f];
+            for (int f = 0; f < 2; ++f) ctx->peers.b[0][b][f] = ctx->st.b[b][f];
+        }
+    }
     if (G > 1 && !ctx->has_peers && !getenv("ESLAM_GPU_NO_P2P")) return setup_peers(ctx);
     return ESLAM_OK;
 }
@@ -856,11 +863,9 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
         // from being overwritten)
         XCH(3, nullptr, 0, 0);
         const ModelParams mp = model_params(ctx);
-        CK(launch_pdl(ctx, k_resample_p2p, (unsigned)((n + 255) / 256), 256, 0, ctx->st, ctx->sc, ctx->tile_sin, TG, T, n, ng, base_index(ctx),
-                                                                            mp.k0, mp.k1, ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC,
-                                                                            ctx->ancestors, ctx->peers, XFLAGS(3), XEPOCH(3), XWORLD()));
-        LAUNCHED();
-        CK(launch_pdl(ctx, k_after_resample, 1, 1, 0, ctx->sc));
+        CK(launch_pdl(ctx, k_resample_local, (unsigned)((n + 1023) / 1024), 1024, 0, ctx->st, ctx->sc, ctx->tile_sin, TG, T, n, ng, base_index(ctx),
+                                                                             mp.k0, mp.k1, ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC,
+                                                                             ctx->ancestors, ctx->ticket, ctx->peers, XFLAGS(3), XEPOCH(3), XWORLD()));
         LAUNCHED();
         return ESLAM_OK;
     }
@@ -870,9 +875,9 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     const ModelParams mp = model_params(ctx);
     if (ctx->cfg.patch_size <= 0 && !getenv("ESLAM_GPU_NO_LOCAL_RESAMPLE")) {
         // search in shared memory, copy and buffer swap in one kernel
-        CK(launch_pdl(ctx, k_resample_local, (unsigned)((n + 1023) / 1024), 1024, 0, ctx->st, ctx->sc, ctx->cdf, ctx->tile_sin, T, n, mp.k0, mp.k1,
+        CK(launch_pdl(ctx, k_resample_local, (unsigned)((n + 1023) / 1024), 1024, 0, ctx->st, ctx->sc, ctx->tile_sin, T, T, n, n, 0ull, mp.k0, mp.k1,
                                                                               ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC,
-                                                                              ctx->ancestors, ctx->ticket));
+                                                                              ctx->ancestors, ctx->ticket, ctx->peers, (const unsigned*)nullptr, 0u, 1));
         LAUNCHED();
         return ESLAM_OK;
     }

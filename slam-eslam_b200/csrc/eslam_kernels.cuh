@@ -1770,24 +1770,37 @@ __global__ void __launch_bounds__(256) k_resample(StateBufs st, const DevScalars
     }
 }
 
-// One-GPU variant with the search in shared memory.  A CTA owns 1024 consecutive strata; their draws lie in
-// [k0/N, (k0+1024)/N), so their ancestors lie in the tiles from the last one starting below k0/N to the last one starting
-// below (k0+1024)/N: with balanced weights one or two tiles.  When that is at most RS_TILES tiles the CTA copies their exact
-// running sums into shared memory (coalesced) and every thread searches there; otherwise the two-level global search runs.
-// Fused with the copy (:104) and with xi_k.swap(xi_kp) (:107): the last CTA to finish flips the current buffer.
+// Resampling with the search in shared memory, on one GPU and sharded (exact-global mode) alike.  A CTA owns 1024
+// consecutive strata; their draws lie in [k0/N, (k0+1024)/N), so their ancestors lie in the tiles from the last one
+// starting below k0/N to the last one starting below (k0+1024)/N: with balanced weights one or two tiles.  When that is at
+// most RS_TILES tiles the CTA copies their exact running sums into shared memory -- coalesced, from the rank that owns each
+// tile, over NVLink when that is a peer -- and every thread searches there; otherwise the two-level search runs on global
+// (peer) memory.  The ancestor's state is copied straight from the owner's current buffers (:104).  Fused with
+// xi_k.swap(xi_kp) (:107): the last CTA to finish flips the current buffer.  tile_start holds the exact running sum before
+// every tile of every rank (k_chain); peers maps every rank's running-sum and state buffers (own pointers on one GPU).
 #define RS_TILES 3
-__global__ void __launch_bounds__(1024, 2) k_resample_local(StateBufs st, DevScalars* sc, const double* __restrict__ cdf,
-                                                            const double* __restrict__ tile_start, unsigned n_tiles,
-                                                            unsigned long long n, uint32_t k0key, uint32_t k1key, int systematic,
-                                                            uint32_t* ancestors, unsigned* ticket) {
+struct PeerTable {
+    const double* cdf[ESLAM_MAX_RANKS];
+    const double* f[ESLAM_MAX_RANKS][2][7];
+    const uint8_t* b[ESLAM_MAX_RANKS][2][2];
+};
+
+__global__ void __launch_bounds__(1024, 2) k_resample_local(StateBufs st, DevScalars* sc, const double* __restrict__ tile_start,
+                                                            unsigned n_tiles, unsigned tiles_per_rank, unsigned long long n,
+                                                            unsigned long long n_global, unsigned long long base, uint32_t k0key,
+                                                            uint32_t k1key, int systematic, uint32_t* ancestors, unsigned* ticket,
+                                                            const __grid_constant__ PeerTable peers, const unsigned* xflags,
+                                                            unsigned epoch, int world) {
     pdl_start();
     __shared__ double s_cdf[RS_TILES * TILE];
     if (!sc->do_resample) return;
+    if (world > 1 && (sc->error_flags & ERR_CDF_FALLBACK_BIT)) return;   // reported through the update status; state is left as is
+    peer_wait(xflags, epoch, world);                                     // every rank's running sum is final before anyone reads a peer
     const unsigned tid = threadIdx.x;
-    const unsigned long long kb = (unsigned long long)blockIdx.x * 1024, k = kb + tid;
+    const unsigned long long kb = (unsigned long long)blockIdx.x * 1024, k = kb + tid;   // local stratum
     // the tile starts are non-decreasing, so "the last tile starting below thr" is a count: one coalesced read of the table and
     // two block-wide counts instead of two dependent binary searches.  thr_lo / thr_hi bound every sum_r of this CTA.
-    const double thr_lo = (double)kb / (double)n, thr_hi = (double)(kb + 1024ull) / (double)n;
+    const double thr_lo = (double)(base + kb) / (double)n_global, thr_hi = (double)(base + kb + 1024ull) / (double)n_global;
     unsigned c_lo = 0, c_hi = 0;
     for (unsigned t0 = 0; t0 < n_tiles; t0 += 1024) {
         const double ts = (t0 + tid < n_tiles) ? __ldg(&tile_start[t0 + tid]) : 1.7e308;
@@ -1796,37 +1809,44 @@ __global__ void __launch_bounds__(1024, 2) k_resample_local(StateBufs st, DevSca
     }
     const unsigned t_lo = c_lo == 0 ? 0u : c_lo - 1, t_hi = c_hi == 0 ? 0u : c_hi - 1;
     const bool in_smem = (t_hi - t_lo) < RS_TILES;
-    const unsigned long long w0 = (unsigned long long)t_lo * TILE;
-    const unsigned long long w1 = min(((unsigned long long)t_hi + 1) * TILE, n);   // window [w0, w1)
+    const unsigned long long g0 = (unsigned long long)t_lo * TILE;                        // window [g0, g1) of global elements
+    const unsigned long long g1 = min(((unsigned long long)t_hi + 1) * TILE, n_global);
     if (in_smem) {
-        for (unsigned long long j = w0 + tid; j < w1; j += 1024) s_cdf[j - w0] = cdf[j];
+        for (unsigned long long j = g0 + tid; j < g1; j += 1024) {
+            const unsigned q = (unsigned)(j / n);                                         // owner of element j
+            s_cdf[j - g0] = peers.cdf[q][j - (unsigned long long)q * n];
+        }
         __syncthreads();
     }
     if (k < n) {
-        const unsigned long long gk = systematic ? 0ull : k;
+        const unsigned long long gk = systematic ? 0ull : base + k;
         const em::Philox4 r = em::philox4x32_10((uint32_t)gk, sc->resample_step, 0, stream_word(em::STREAM_RESAMPLE, gk), k0key, k1key);
         const double u = em::u01(r.v[0], r.v[1]);
-        const double sum_r = ((double)k + u) / (double)n;                            // :98
-        unsigned long long a;
+        const double sum_r = ((double)(base + k) + u) / (double)n_global;                 // :98
+        unsigned long long a;                                                             // global index of the ancestor
         if (in_smem) {
-            unsigned lo = 0, hi = (unsigned)(w1 - w0);                               // first element with !(cdf < sum_r)
+            unsigned lo = 0, hi = (unsigned)(g1 - g0);                                    // first element with !(cdf < sum_r)
             while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (s_cdf[mid] < sum_r) lo = mid + 1; else hi = mid; }
-            a = w0 + lo;
+            a = g0 + lo;
         } else {
             unsigned tlo = 0, thi = n_tiles;
             while (tlo < thi) { const unsigned mid = (tlo + thi) >> 1; if (__ldg(&tile_start[mid]) < sum_r) tlo = mid + 1; else thi = mid; }
             const unsigned t = tlo == 0 ? 0 : tlo - 1;
-            unsigned long long lo = (unsigned long long)t * TILE, hi = min(lo + TILE, n);
-            while (lo < hi) { const unsigned long long mid = (lo + hi) >> 1; if (__ldg(&cdf[mid]) < sum_r) lo = mid + 1; else hi = mid; }
-            a = lo;
+            const unsigned q = t / tiles_per_rank;
+            const double* cdf_q = peers.cdf[q];
+            unsigned long long lo = (unsigned long long)(t - q * tiles_per_rank) * TILE, hi = min(lo + TILE, n);   // owner-local
+            while (lo < hi) { const unsigned long long mid = (lo + hi) >> 1; if (cdf_q[mid] < sum_r) lo = mid + 1; else hi = mid; }
+            a = (unsigned long long)q * n + lo;           // lo == n: the first element of the next rank (its tile start is >= sum_r)
         }
-        if (a >= n) a = n - 1;               // the reference walks off the end here; we stop at the last particle
+        if (a >= n_global) a = n_global - 1;              // the reference walks off the end here; we stop at the last particle
         ancestors[k] = (uint32_t)a;
+        const unsigned q = (unsigned)(a / n);
+        const unsigned long long la = a - (unsigned long long)q * n;
         const int cur = sc->cur, nxt = cur ^ 1;
 #pragma unroll
-        for (int f = 0; f < 7; ++f) st.f[nxt][f][k] = st.f[cur][f][a];               // :104 copy keeps the weight (Q3)
+        for (int f = 0; f < 7; ++f) st.f[nxt][f][k] = peers.f[q][cur][f][la];             // :104 copy keeps the weight (Q3)
 #pragma unroll
-        for (int f = 0; f < 2; ++f) st.b[nxt][f][k] = st.b[cur][f][a];
+        for (int f = 0; f < 2; ++f) st.b[nxt][f][k] = peers.b[q][cur][f][la];
     }
     // xi_k.swap(xi_kp) :107 by the last CTA (every CTA has read sc->cur by then)
     __syncthreads();
@@ -1834,56 +1854,6 @@ __global__ void __launch_bounds__(1024, 2) k_resample_local(StateBufs st, DevSca
         __threadfence();
         if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0; sc->cur ^= 1; sc->resample_step += 1; }
     }
-}
-
-// Sharded resampling over NVLink peer memory (exact-global mode).  Every rank holds, after the all-gathered k_chain, the
-// exact running sum before every 1024-tile of EVERY rank (tile_start, global).  Stratum k of this rank searches that
-// table, then searches inside the one tile that holds its ancestor -- reading the owner's running sum through its
-// peer-mapped pointer -- and copies the ancestor's state straight from the owner's current buffers.  No host step, no
-// staging: remote ancestors cost NVLink reads, local ones (the vast majority when weights are balanced) HBM reads.
-struct PeerTable {
-    const double* cdf[ESLAM_MAX_RANKS];
-    const double* f[ESLAM_MAX_RANKS][2][7];
-    const uint8_t* b[ESLAM_MAX_RANKS][2][2];
-};
-
-__global__ void __launch_bounds__(256) k_resample_p2p(StateBufs st, DevScalars* sc, const double* __restrict__ tile_start,
-                                                      unsigned n_tiles_global, unsigned tiles_per_rank, unsigned long long n,
-                                                      unsigned long long n_global, unsigned long long base, uint32_t k0,
-                                                      uint32_t k1, int systematic, uint32_t* ancestors,
-                                                      const __grid_constant__ PeerTable peers, const unsigned* xflags,
-                                                      unsigned epoch, int world) {
-    pdl_start();
-    if (!sc->do_resample) return;
-    if (sc->error_flags & ERR_CDF_FALLBACK_BIT) return;     // reported through the update status; state is left as is
-    peer_wait(xflags, epoch, world);                        // every rank's running sum is final before anyone reads a peer
-    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const unsigned long long gk = systematic ? 0ull : base + k;
-    const em::Philox4 r = em::philox4x32_10((uint32_t)gk, sc->resample_step, 0, stream_word(em::STREAM_RESAMPLE, gk), k0, k1);
-    const double u = em::u01(r.v[0], r.v[1]);
-    const double sum_r = ((double)(base + k) + u) / (double)n_global;                // :98
-    unsigned tlo = 0, thi = n_tiles_global;                                          // first tile with !(start < sum_r)
-    while (tlo < thi) { const unsigned mid = (tlo + thi) >> 1; if (__ldg(&tile_start[mid]) < sum_r) tlo = mid + 1; else thi = mid; }
-    const unsigned t = tlo == 0 ? 0 : tlo - 1;
-    const unsigned q = t / tiles_per_rank;                                           // owner of the ancestor
-    const double* cdf_q = peers.cdf[q];
-    unsigned long long lo = (unsigned long long)(t - q * tiles_per_rank) * TILE, hi = min(lo + TILE, n);   // owner-local
-    while (lo < hi) {
-        const unsigned long long mid = (lo + hi) >> 1;
-        if (cdf_q[mid] < sum_r) lo = mid + 1; else hi = mid;
-    }
-    unsigned owner = q;
-    if (lo >= n) {                                  // past the end of the owner's tile range
-        if (q + 1 < (unsigned)(n_global / n)) { owner = q + 1; lo = 0; }   // cannot happen (tile_start[t+1] >= sum_r); kept safe
-        else lo = n - 1;                            // the reference walks off the end here; we stop at the last particle
-    }
-    ancestors[k] = (uint32_t)((unsigned long long)owner * n + lo);
-    const int cur = sc->cur, nxt = cur ^ 1;
-#pragma unroll
-    for (int f = 0; f < 7; ++f) st.f[nxt][f][k] = peers.f[owner][cur][f][lo];        // :104 copy keeps the weight (Q3)
-#pragma unroll
-    for (int f = 0; f < 2; ++f) st.b[nxt][f][k] = peers.b[owner][cur][f][lo];
 }
 
 // cloneMaps (src/PoseEstimator.cpp:31-45): every copy of a particle owns a copy of its map patch. One warp per particle.
