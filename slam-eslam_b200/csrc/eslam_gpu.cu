@@ -831,6 +831,9 @@ static int resample_exchange(eslam_gpu_ctx* ctx) {
 
 // normalise + (optional) resample tail shared by update / normalize_weights / resample.
 // mode: 0 = do_resample := force, 1 = decide from ESS (update), 2 = ESS only
+#ifndef RS_CTA
+#define RS_CTA 1024               // strata (threads) per CTA of k_resample_local (512 measured the same)
+#endif
 static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int mode, int force) {
     const unsigned T = ctx->t_local, TG = ctx->t_global;
     const uint64_t n = ctx->n, ng = global_count(ctx);
@@ -863,7 +866,7 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
         // from being overwritten)
         XCH(3, nullptr, 0, 0);
         const ModelParams mp = model_params(ctx);
-        CK(launch_pdl(ctx, k_resample_local, (unsigned)((n + 1023) / 1024), 1024, 0, ctx->st, ctx->sc, ctx->tile_sin, TG, T, n, ng, base_index(ctx),
+        CK(launch_pdl(ctx, k_resample_local<RS_CTA>, (unsigned)((n + RS_CTA - 1) / RS_CTA), RS_CTA, 0, ctx->st, ctx->sc, ctx->tile_sin, TG, T, n, ng, base_index(ctx),
                                                                              mp.k0, mp.k1, ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC,
                                                                              ctx->ancestors, ctx->ticket, ctx->peers, XFLAGS(3), XEPOCH(3), XWORLD()));
         LAUNCHED();
@@ -875,7 +878,7 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     const ModelParams mp = model_params(ctx);
     if (ctx->cfg.patch_size <= 0 && !getenv("ESLAM_GPU_NO_LOCAL_RESAMPLE")) {
         // search in shared memory, copy and buffer swap in one kernel
-        CK(launch_pdl(ctx, k_resample_local, (unsigned)((n + 1023) / 1024), 1024, 0, ctx->st, ctx->sc, ctx->tile_sin, T, T, n, n, 0ull, mp.k0, mp.k1,
+        CK(launch_pdl(ctx, k_resample_local<RS_CTA>, (unsigned)((n + RS_CTA - 1) / RS_CTA), RS_CTA, 0, ctx->st, ctx->sc, ctx->tile_sin, T, T, n, n, 0ull, mp.k0, mp.k1,
                                                                               ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC,
                                                                               ctx->ancestors, ctx->ticket, ctx->peers, (const unsigned*)nullptr, 0u, 1));
         LAUNCHED();

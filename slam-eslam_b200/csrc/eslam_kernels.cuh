@@ -1770,8 +1770,8 @@ __global__ void __launch_bounds__(256) k_resample(StateBufs st, const DevScalars
     }
 }
 
-// Resampling with the search in shared memory, on one GPU and sharded (exact-global mode) alike.  A CTA owns 1024
-// consecutive strata; their draws lie in [k0/N, (k0+1024)/N), so their ancestors lie in the tiles from the last one
+// Resampling with the search in shared memory, on one GPU and sharded (exact-global mode) alike.  A CTA owns RS_THREADS
+// consecutive strata; their draws lie in [k0/N, (k0+RS_THREADS)/N), so their ancestors lie in the tiles from the last one
 // starting below k0/N to the last one starting below (k0+1024)/N: with balanced weights one or two tiles.  When that is at
 // most RS_TILES tiles the CTA copies their exact running sums into shared memory -- coalesced, from the rank that owns each
 // tile, over NVLink when that is a peer -- and every thread searches there; otherwise the two-level search runs on global
@@ -1785,7 +1785,8 @@ struct PeerTable {
     const uint8_t* b[ESLAM_MAX_RANKS][2][2];
 };
 
-__global__ void __launch_bounds__(1024, 2) k_resample_local(StateBufs st, DevScalars* sc, const double* __restrict__ tile_start,
+template <int RS_THREADS>
+__global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_local(StateBufs st, DevScalars* sc, const double* __restrict__ tile_start,
                                                             unsigned n_tiles, unsigned tiles_per_rank, unsigned long long n,
                                                             unsigned long long n_global, unsigned long long base, uint32_t k0key,
                                                             uint32_t k1key, int systematic, uint32_t* ancestors, unsigned* ticket,
@@ -1797,12 +1798,12 @@ __global__ void __launch_bounds__(1024, 2) k_resample_local(StateBufs st, DevSca
     if (world > 1 && (sc->error_flags & ERR_CDF_FALLBACK_BIT)) return;   // reported through the update status; state is left as is
     peer_wait(xflags, epoch, world);                                     // every rank's running sum is final before anyone reads a peer
     const unsigned tid = threadIdx.x;
-    const unsigned long long kb = (unsigned long long)blockIdx.x * 1024, k = kb + tid;   // local stratum
+    const unsigned long long kb = (unsigned long long)blockIdx.x * RS_THREADS, k = kb + tid;   // local stratum
     // the tile starts are non-decreasing, so "the last tile starting below thr" is a count: one coalesced read of the table and
     // two block-wide counts instead of two dependent binary searches.  thr_lo / thr_hi bound every sum_r of this CTA.
-    const double thr_lo = (double)(base + kb) / (double)n_global, thr_hi = (double)(base + kb + 1024ull) / (double)n_global;
+    const double thr_lo = (double)(base + kb) / (double)n_global, thr_hi = (double)(base + kb + (unsigned long long)RS_THREADS) / (double)n_global;
     unsigned c_lo = 0, c_hi = 0;
-    for (unsigned t0 = 0; t0 < n_tiles; t0 += 1024) {
+    for (unsigned t0 = 0; t0 < n_tiles; t0 += RS_THREADS) {
         const double ts = (t0 + tid < n_tiles) ? __ldg(&tile_start[t0 + tid]) : 1.7e308;
         c_lo += (unsigned)__syncthreads_count(ts < thr_lo);
         c_hi += (unsigned)__syncthreads_count(ts < thr_hi);
@@ -1812,7 +1813,7 @@ __global__ void __launch_bounds__(1024, 2) k_resample_local(StateBufs st, DevSca
     const unsigned long long g0 = (unsigned long long)t_lo * TILE;                        // window [g0, g1) of global elements
     const unsigned long long g1 = min(((unsigned long long)t_hi + 1) * TILE, n_global);
     if (in_smem) {
-        for (unsigned long long j = g0 + tid; j < g1; j += 1024) {
+        for (unsigned long long j = g0 + tid; j < g1; j += RS_THREADS) {
             const unsigned q = (unsigned)(j / n);                                         // owner of element j
             s_cdf[j - g0] = peers.cdf[q][j - (unsigned long long)q * n];
         }
