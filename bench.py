@@ -24,6 +24,9 @@ sys.path.insert(0, ROOT)
 # profiles/ (workload, lean path) -> bytes
 NCU_DRAM_BYTES_PER_LAUNCH = {("C3", True): 61.7e6}
 
+KIND_TEXT = {"reference": "the reference's own PoseEstimator / ContactModel sources compiled against stand-in dependency headers "
+                          "(dense-grid map, Philox noise)",
+             "port": "LITERAL oracle port (oracle/_ref not built)"}
 METRIC = "particle-updates/sec"
 UNIT = "particle-updates/s"
 
@@ -89,11 +92,23 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def cpu_kind():
+    """"reference": oracle/_ref/libeslam_ref.so, the reference's own src/{ContactModel,PoseEstimator}.cpp compiled unmodified
+    against stand-in dependency headers (oracle/ref/, oracle/ref_shim/; prebuilt in the build container, it travels with the
+    snapshot).  "port": the LITERAL oracle, when that library is not there."""
+    from oracle import ref_binding
+    return "reference" if ref_binding.available() else "port"
+
+
 def _oracle_shard(workload, n, steps, warmup, out, k):
     """One independent CPU filter of n particles (the C call releases the GIL, so shards run on separate cores)."""
-    from oracle import binding
+    from oracle import binding, ref_binding
     from slam_eslam_b200 import abi, synthetic
-    f = binding.OraclePoseEstimator(abi.default_config(min_effective=n + 1), policy=binding.LITERAL)
+    cfg = abi.default_config(min_effective=n + 1)
+    if cpu_kind() == "reference":
+        f = ref_binding.RefPoseEstimator(cfg, debug=False)
+    else:
+        f = binding.OraclePoseEstimator(cfg, policy=binding.LITERAL)
     contacts, step = synthetic.setup_filter(f, workload, n=n)
     for _ in range(warmup):
         f.project(step); f.update(contacts)
@@ -101,10 +116,11 @@ def _oracle_shard(workload, n, steps, warmup, out, k):
 
 
 def time_oracle(workload, n_total, steps, warmup, threads):
-    """The reference's CPU filter (the oracle port, LITERAL policy: libm, reference expression order) on `threads` host
-    threads.  The reference itself is single-threaded (its only OpenMP loop is racy, src/PoseEstimator.cpp:272-327), so
-    threads > 1 runs that many independent filters of n_total/threads particles side by side: an upper bound for what a
-    particle-parallel CPU port could do ("restatement-parallel").  Returns particle-updates/s."""
+    """The reference's CPU filter (its own compiled sources when oracle/_ref is there, else the LITERAL oracle port: the two
+    are bit-identical, tests/test_reference_parity.py) on `threads` host threads.  The reference itself is single-threaded
+    (its only OpenMP loop is racy, src/PoseEstimator.cpp:272-327), so threads > 1 runs that many independent filters of
+    n_total/threads particles side by side: an upper bound for what a particle-parallel CPU build of it could do.  The map
+    behind its lookups is the dense stand-in grid, cheaper than envire's MLS map.  Returns particle-updates/s."""
     from slam_eslam_b200 import synthetic
     w = synthetic.WORKLOADS[workload]
     n = max(1, n_total // threads)
@@ -125,8 +141,8 @@ def time_oracle(workload, n_total, steps, warmup, threads):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU filter on this box's host cores.  The reference itself cannot be built
-    (no boost / Eigen / envire / odometry here), so this is the oracle port."""
+    """--impl reference: the reference's CPU filter on this box's host cores -- eslam::PoseEstimator::project + update from
+    the reference's own sources (oracle/_ref/libeslam_ref.so, see cpu_kind), on all host threads."""
     if rank != 0:
         return
     from slam_eslam_b200 import synthetic
@@ -134,15 +150,16 @@ def run_reference(args, rank, world):
     threads = max(1, min(os.cpu_count() or 1, 64))     # every filter holds its own copy of the map
     n_sample = min(w["n"], args.cpu_particles * threads)
     value, dt, n = time_oracle(args.workload, n_sample, args.steps, args.warmup, threads)
+    kind = cpu_kind()
     sample = ("%d independent CPU filters x %d particles x %d contact points per step (%d of the workload's %d particles; same "
-              "terrain, contacts, odometry; forced resampling)" % (threads, n, w["c"], n * threads, w["n"]))
+              "terrain, contacts, odometry; forced resampling); %s" % (threads, n, w["c"], n * threads, w["n"], KIND_TEXT[kind]))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "particles": w["n"], "contact_points": w["c"], "grid": w["grid"],
                    "resample": "stratified, every step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -151,9 +168,10 @@ def cpu_baseline(args, w):
     """The single-threaded CPU filter, as the reference runs it, on a bounded sample of the workload."""
     n_sample = min(w["n"], args.cpu_particles)
     value, dt, n = time_oracle(args.workload, n_sample, 3, 1, 1)
-    return {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "3 steps of %d of %d particles x %d contact points, LITERAL oracle, 1 thread like the reference (host has %d cores)"
-                      % (n, w["n"], w["c"], os.cpu_count())}
+    kind = cpu_kind()
+    return {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "3 steps of %d of %d particles x %d contact points, 1 thread like the reference (host has %d cores); %s"
+                      % (n, w["n"], w["c"], os.cpu_count(), KIND_TEXT[kind])}
 
 
 def main():

@@ -419,3 +419,71 @@ def test_millions_of_particles_resample_stage(gpu, n):
     assert np.all(lo < (k + 1.0) / n) and np.all(cdf[anc] >= k / n)
     assert g.debugCounters()["fallbacks"] == 0
     assert g.normalizeWeights() == pytest.approx(1.0 / np.sum((w[anc] / w[anc].sum()) ** 2), rel=1e-12)
+
+
+# ---------------------------------------------------------------------------------- against the reference's own code
+def _gold():
+    import os
+    import sys
+    from helpers import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    import make_reference_golden as gold
+    return gold, np.load(os.path.join(GOLDEN, "reference_trajectories.npz"))
+
+
+@pytest.mark.parametrize("case", ["c1_default", "c1_forced"])
+def test_gpu_against_reference_golden_trajectories(gpu, case):
+    """tests/golden/reference_trajectories.npz holds outputs of the reference's OWN compiled sources (oracle/ref/).  north_star's
+    bars against them: resampled ancestor indices bit-exact at every resampling step of the trajectory; poses within 1e-6 m /
+    1e-6 rad; normalised weights within 1e-5 relative; flags and fused-contact counts identical."""
+    gold, G = _gold()
+    spec = gold.CASES[case]
+    got = gold.run_case(lambda cfg: gpu(cfg), spec)
+    want = {k.split("/", 1)[1]: G[k] for k in G.files if k.startswith(case + "/")}
+    assert np.array_equal(got["resampled"], want["resampled"])
+    assert np.array_equal(got["ancestors"], want["ancestors"]) and want["ancestors"].shape[0] >= 1
+    for i in spec["keep"]:
+        for k in ("x", "y", "theta", "zpos", "zsigma"):
+            np.testing.assert_allclose(got["%s_%d" % (k, i)], want["%s_%d" % (k, i)], rtol=0, atol=1e-6, err_msg="%s step %d" % (k, i))
+        for k in ("weight", "mprob"):
+            np.testing.assert_allclose(got["%s_%d" % (k, i)], want["%s_%d" % (k, i)], rtol=1e-5, atol=1e-300, err_msg="%s step %d" % (k, i))
+        for k in ("floating", "n_found"):
+            assert np.array_equal(got["%s_%d" % (k, i)], want["%s_%d" % (k, i)])
+    keep = ~np.isnan(want["ess"])
+    np.testing.assert_allclose(got["ess"][keep], want["ess"][keep], rtol=1e-5)
+    np.testing.assert_allclose(got["centroid"], want["centroid"], rtol=0, atol=1e-6)
+    assert got["best_index"][0] == want["best_index"][0]
+
+
+def test_gpu_against_live_reference_c2(gpu):
+    """The reference's compiled filter itself (oracle/_ref/libeslam_ref.so, prebuilt in the build container) next to the GPU
+    on C2 (10 000 particles x 16 contact points), resampling every step: ancestors bit-exact, floats within north_star's bars;
+    then the ContactModel seam on 20 000 random poses: map-cell indices bit-exact."""
+    from oracle import ref_binding
+    if not ref_binding.available():
+        pytest.skip("oracle/_ref/libeslam_ref.so did not travel")
+    cfg = dict(min_effective=10001)
+    g = gpu(abi.default_config(**cfg))
+    r = ref_binding.RefPoseEstimator(abi.default_config(**cfg), debug=True)
+    contacts, step = synthetic.setup_filter(g, "C2")
+    synthetic.setup_filter(r, "C2")
+    for i in range(8):
+        g.project(step); r.project(step)
+        ra, rb = g.update(contacts), r.update(contacts)
+        assert ra.resampled == rb.resampled == 1
+        assert np.array_equal(g.getAncestors(), r.getAncestors()), "ancestors differ from the reference at step %d" % i
+        a, b = g.getParticles(), r.getParticles()
+        for k in ("x", "y", "theta", "zpos", "zsigma"):
+            np.testing.assert_allclose(a[k], b[k], rtol=0, atol=1e-6, err_msg=k)
+        np.testing.assert_allclose(a["weight"], b["weight"], rtol=1e-5, atol=1e-300)
+        assert np.array_equal(a["floating"], b["floating"]) and np.array_equal(a["n_found"], b["n_found"])
+    rng = np.random.default_rng(5)
+    n = 20000
+    x, y = rng.uniform(-13.0, 13.0, n), rng.uniform(-13.0, 13.0, n)       # the 512^2 grid spans +-12.8 m: some poses hang over the border
+    th, z, mv = rng.uniform(-4, 4, n), rng.normal(0.19, 0.15, n), rng.uniform(0.01, 1.2, n)
+    a, b = g.evaluatePoses(x, y, th, z, mv, contacts), r.evaluatePoses(x, y, th, z, mv, contacts)
+    assert np.array_equal(a["cell_index"], b["cell_index"])
+    assert np.array_equal(a["ok"], b["ok"]) and np.array_equal(a["n_contacts"], b["n_contacts"])
+    ok = a["ok"].astype(bool)
+    np.testing.assert_allclose(a["weight"][ok], b["weight"][ok], rtol=1e-5, atol=1e-300)
+    np.testing.assert_allclose(a["z_delta"][ok], b["z_delta"][ok], rtol=0, atol=1e-6)

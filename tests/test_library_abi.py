@@ -73,6 +73,6 @@ def test_product_does_not_reference_the_oracle():
             for f in files:
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".inc")):
                     text = open(os.path.join(dirpath, f), errors="ignore").read()
-                    if re.search(r"#include\s*[\"<][^\">]*oracle|import\s+oracle|from\s+oracle|libeslam_oracle", text):
+                    if re.search(r"#include\s*[\"<][^\">]*oracle|import\s+oracle|from\s+oracle|libeslam_oracle|libeslam_ref|ref_shim", text):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
