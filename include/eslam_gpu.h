@@ -32,6 +32,17 @@ enum {
 enum { ESLAM_RESAMPLE_STRATIFIED = 0,   /* reference: src/ParticleFilter.hpp:85-108 */
        ESLAM_RESAMPLE_SYSTEMATIC = 1 }; /* north_star: one uniform for all strata */
 
+/* How a SHARDED filter (particles split into equal contiguous shards, one per GPU) resamples (north_star):
+ *   EXACT_GLOBAL  : one stratified walk over all particles; ancestors may lie on any shard and are identical to the
+ *                   one-GPU / reference run.  The parity mode and the default.
+ *   LOCAL_MIGRATE : every shard resamples its own slots from its own particles (stratum k of shard g draws
+ *                   (k + u)/n_s * W_g on the shard's own left-to-right running sum, W_g its total); particles cross shards
+ *                   only in a step where some shard has collapsed -- its share of the total weight fell below
+ *                   migrate_min_share of the fair share 1/G, or its own effective sample size W_g^2 / sum w^2 fell below
+ *                   migrate_min_ess * n_s -- and that step resamples exact-globally (the migration).  Statistically a
+ *                   valid particle filter, but not index-identical to the reference: defined by the oracle. */
+enum { ESLAM_SHARD_EXACT_GLOBAL = 0, ESLAM_SHARD_LOCAL_MIGRATE = 1 };
+
 /* Hot-path fields of eslam::Configuration / ContactModelConfiguration
  * (src/Configuration.hpp:51-111).  eslam_gpu_default_config() fills the reference defaults. */
 typedef struct eslam_gpu_config {
@@ -52,6 +63,11 @@ typedef struct eslam_gpu_config {
     int32_t use_hash;                    /* SurfaceHash attached: disables spreading, src/PoseEstimator.cpp:224 */
     int32_t resample_mode;               /* ESLAM_RESAMPLE_* */
     int32_t patch_size;                  /* 0: shared map only; P>0: per-particle PxP map patches */
+    int32_t shard_mode;                  /* ESLAM_SHARD_* (only matters with more than one shard) */
+    double migrate_min_share;            /* LOCAL_MIGRATE: migrate when a shard's weight share * G falls below this (default 0.25) */
+    double migrate_min_ess;              /* LOCAL_MIGRATE: ... or its own ESS / n_s falls below this (default 0.05) */
+    int32_t virtual_shards;              /* > 1 on an unsharded context: treat the particles as that many logical shards (the
+                                            shard logic on one GPU; results identical to the same number of real shards) */
     int32_t reserved;
 } eslam_gpu_config;
 

@@ -147,6 +147,7 @@ struct eslam_oracle_ctx {
     std::vector<double> cdf;
     double max_weight = 0;                       // src/PoseEstimator.hpp:154
     uint32_t project_step = 0, resample_step = 0;
+    int migrate = 1;                             // LOCAL_MIGRATE: 1 = the next resampling is exact-global (set by shard_decision)
     // contact model state (src/ContactModel.hpp:35-47)
     std::vector<eslam_gpu_contact> contactPoints;
     std::vector<ContactPoint> contact_points;
@@ -618,6 +619,74 @@ struct eslam_oracle_ctx {
         return ESLAM_OK;
     }
 
+    // --- sharded resampling, LOCAL_MIGRATE mode (north_star / SURVEY.md §8e; no reference code behind it: this IS the definition,
+    //     include/eslam_gpu.h ESLAM_SHARD_LOCAL_MIGRATE).  The oracle holds all N particles; the G logical shards are the
+    //     contiguous ranges [g n_s, (g+1) n_s).
+    int logical_shards() const {
+        if (cfg.shard_mode != ESLAM_SHARD_LOCAL_MIGRATE) return 1;
+        const int G = shard.world > 1 ? shard.world : cfg.virtual_shards;
+        return (G > 1 && xi_k.size() % ((size_t)G * 1024) == 0) ? G : 1;    // shards are whole 1024-particle tiles
+    }
+    // decided on the weights as they are BEFORE normalisation (what every rank holds after the exchange of the per-tile sums):
+    // migrate = some shard's share of the total weight, times G, is below migrate_min_share, or its own effective sample
+    // size W_g^2 / sum w^2 is below migrate_min_ess n_s.  A non-positive total (uniform reset, Q8) never migrates.
+    template <class A>
+    void shard_decision() {
+        const int G = logical_shards();
+        migrate = 1;
+        if (G <= 1) return;
+        const size_t ns = xi_k.size() / G;
+        std::vector<double> w(xi_k.size());
+        for (size_t i = 0; i < xi_k.size(); i++) w[i] = xi_k[i].weight;
+        const double total = A::sum(w);
+        migrate = 0;
+        if (total <= 0.0) return;
+        for (int g = 0; g < G; g++) {
+            std::vector<double> ws(w.begin() + g * ns, w.begin() + (g + 1) * ns), qs(ns);
+            for (size_t i = 0; i < ns; i++) qs[i] = ws[i] * ws[i];
+            const double Wg = A::sum(ws), Qg = A::sum(qs);
+            const double share = (Wg / total) * (double)G;
+            const double essg = (Wg * Wg) / Qg;
+            if (share < cfg.migrate_min_share || essg < cfg.migrate_min_ess * (double)ns) migrate = 1;
+        }
+    }
+    // every shard walks its own strata over its own left-to-right running sum (restarted at 0), scaled by the shard's total
+    int resample_local(int G) {
+        if (xi_k.empty()) return ESLAM_ERR_EMPTY;
+        const size_t N = xi_k.size(), ns = N / G;
+        std::vector<PoseParticle> xi_kp;
+        ancestors.assign(N, 0);
+        cdf.assign(N, 0.0);
+        for (int g = 0; g < G; g++) {
+            const size_t o = (size_t)g * ns;
+            double s = xi_k[o].weight; cdf[o] = s;
+            for (size_t i = 1; i < ns; i++) { s += xi_k[o + i].weight; cdf[o + i] = s; }
+            const double Wg = s;
+            size_t idx = 0;
+            double sum_w = xi_k[o].weight;
+            for (size_t k = 0; k < ns; ++k) {
+                em::Philox4 r = noise.draw(o + k, resample_step, 0, em::STREAM_RESAMPLE);
+                const double u = em::u01(r.v[0], r.v[1]);
+                const double sum_r = (((double)k + u) / (double)ns) * Wg;
+                while (sum_w < sum_r) {
+                    if (idx + 1 >= ns) break;
+                    ++idx;
+                    sum_w += xi_k[o + idx].weight;
+                }
+                xi_kp.push_back(xi_k[o + idx]);                 // copies keep their weight, as in the global walk (Q3)
+                ancestors[o + k] = (uint32_t)(o + idx);
+            }
+        }
+        xi_k.swap(xi_kp);
+        resample_step++;
+        return ESLAM_OK;
+    }
+    int resample_any() {
+        const int G = logical_shards();
+        if (G > 1 && !migrate && cfg.resample_mode == ESLAM_RESAMPLE_STRATIFIED) return resample_local(G);
+        return resample_stratified(xi_k.size());
+    }
+
     // --- PoseEstimator::update  src/PoseEstimator.cpp:244-255
     template <class A>
     int update(const eslam_gpu_contact* pts, int n_pts, eslam_gpu_update_result* res) {
@@ -626,10 +695,11 @@ struct eslam_oracle_ctx {
         int st = updateWeights<A>(&local);                      // :247
         if (st != ESLAM_OK) { if (res) { *res = local; res->status = st; } return st; }
         double sum = 0;
+        shard_decision<A>();
         double eff = normalizeWeights<A>(&sum);                 // :248
         local.ess = eff; local.weights_sum = sum; local.resampled = 0;
         if (eff < cfg.min_effective) {                          // :249
-            st = resample_stratified(xi_k.size());              // :251
+            st = resample_any();                                // :251 (resample_stratified(N) unless LOCAL_MIGRATE says otherwise)
             local.resampled = 1;
         }
         local.status = st;
@@ -768,7 +838,9 @@ int eslam_oracle_normalize_weights(eslam_oracle_ctx* ctx, double* ess) {
 
 int eslam_oracle_resample(eslam_oracle_ctx* ctx) {
     if (!ctx) return ESLAM_ERR_INVALID;
-    return ctx->resample_stratified(ctx->xi_k.size());
+    if (ctx->xi_k.empty()) return ESLAM_ERR_EMPTY;
+    DISPATCH(ctx, ctx->shard_decision<Literal>(), ctx->shard_decision<Shared>());   // on the weights as they are
+    return ctx->resample_any();
 }
 
 int eslam_oracle_get_ancestors(eslam_oracle_ctx* ctx, uint32_t* a) {

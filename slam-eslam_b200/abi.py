@@ -14,6 +14,7 @@ MAX_CONTACTS = 128
 MAX_CP = 8
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_ENVIRONMENT, ERR_ZERO_VARIANCE, ERR_EMPTY, ERR_COMM = range(7)
 RESAMPLE_STRATIFIED, RESAMPLE_SYSTEMATIC = 0, 1
+SHARD_EXACT_GLOBAL, SHARD_LOCAL_MIGRATE = 0, 1
 
 ERROR_TEXT = {
     ERR_INVALID: "invalid argument",
@@ -34,7 +35,9 @@ class Config(C.Structure):
         ("min_contacts", C.c_uint64), ("contact_likelihood_correction", C.c_double),
         ("contact_point_radius", C.c_double),
         ("use_slip_update", C.c_int32), ("use_shape_update", C.c_int32), ("use_hash", C.c_int32),
-        ("resample_mode", C.c_int32), ("patch_size", C.c_int32), ("reserved", C.c_int32),
+        ("resample_mode", C.c_int32), ("patch_size", C.c_int32), ("shard_mode", C.c_int32),
+        ("migrate_min_share", C.c_double), ("migrate_min_ess", C.c_double),
+        ("virtual_shards", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -44,7 +47,8 @@ def default_config(**overrides):
                spread_translation_factor=0.1, spread_rotation_factor=0.05, slip_factor=0.05,
                max_yaw_deviation=15 * math.pi / 180.0, min_contacts=3, contact_likelihood_correction=0.33,
                contact_point_radius=0.01, use_slip_update=0, use_shape_update=1, use_hash=0,
-               resample_mode=RESAMPLE_STRATIFIED, patch_size=0, reserved=0)
+               resample_mode=RESAMPLE_STRATIFIED, patch_size=0, shard_mode=SHARD_EXACT_GLOBAL,
+               migrate_min_share=0.25, migrate_min_ess=0.05, virtual_shards=0, reserved=0)
     for k, v in overrides.items():
         if not hasattr(c, k):
             raise AttributeError(k)

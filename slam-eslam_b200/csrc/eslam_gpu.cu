@@ -45,7 +45,8 @@ struct eslam_gpu_ctx {
     float2* patch[2]; int* porigin[2];            // per-particle map patches (cfg.patch_size > 0), double buffered
     // per-tile arrays: l_* cover the local tiles, g_* all tiles of all ranks (aliases of l_* when world == 1)
     unsigned t_local, t_global, t_cap;
-    TilePartA *l_part_a, *g_part_a; double *l_tile_sum, *g_tile_sum, *l_tile_sq, *g_tile_sq;
+    TilePartA *l_part_a, *g_part_a; double2 *l_tile_sum, *g_tile_sum; double *l_tile_sq, *g_tile_sq;   // tile sums: {sum w, sum w^2}
+    double* shard_tot;                            // LOCAL_MIGRATE: exact total of every logical shard held here (k_chain -> k_resample_local)
     TileDesc *l_desc; BndEntry *l_pool;           // l_tile_sq, l_desc, l_pool point into l_pack
     unsigned char *l_pack, *g_pack; size_t pack_bytes;   // [sum w^2 per tile | tile descriptors | boundary pool] per rank: one all-gather
     double *l_cent, *g_cent, *l_best_w, *g_best_w; unsigned long long *l_best_idx, *g_best_idx;
@@ -157,7 +158,7 @@ static void free_particles(eslam_gpu_ctx* ctx) {
     dfree(ctx->l_part_a); dfree(ctx->l_tile_sum); dfree(ctx->l_pack);
     ctx->l_tile_sq = nullptr; ctx->l_desc = nullptr; ctx->l_pool = nullptr; ctx->g_pack = nullptr;
     dfree(ctx->l_cent); dfree(ctx->l_best_w); dfree(ctx->l_best_idx);
-    ctx->g_part_a = nullptr; ctx->g_tile_sum = ctx->g_tile_sq = nullptr;
+    ctx->g_part_a = nullptr; ctx->g_tile_sum = nullptr; ctx->g_tile_sq = nullptr;
     ctx->g_cent = ctx->g_best_w = nullptr; ctx->g_best_idx = nullptr;
     dfree(ctx->tile_prefix); dfree(ctx->scratch_a); dfree(ctx->scratch_b); dfree(ctx->tile_sin); dfree(ctx->sb);
     dfree(ctx->tile_bofs); dfree(ctx->tile_pre);
@@ -246,12 +247,12 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
         CK(dalloc(&ctx->l_cent, 5 * t)); CK(dalloc(&ctx->l_best_w, t)); CK(dalloc(&ctx->l_best_idx, t));
         if (G > 1) {
             auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-            ctx->x_part = 0; ctx->x_sum = up(tg * sizeof(TilePartA)); ctx->x_pack = ctx->x_sum + up(tg * sizeof(double));
+            ctx->x_part = 0; ctx->x_sum = up(tg * sizeof(TilePartA)); ctx->x_pack = ctx->x_sum + up(tg * sizeof(double2));
             ctx->x_flags = ctx->x_pack + up(ctx->pack_bytes * G); ctx->x_bytes = ctx->x_flags + 4 * ESLAM_MAX_RANKS * sizeof(unsigned);
             CK(dalloc(&ctx->xchg, ctx->x_bytes));
             CK(cudaMemsetAsync(ctx->xchg, 0, ctx->x_bytes, ctx->stream));
             ctx->g_part_a = reinterpret_cast<TilePartA*>(ctx->xchg + ctx->x_part);
-            ctx->g_tile_sum = reinterpret_cast<double*>(ctx->xchg + ctx->x_sum);
+            ctx->g_tile_sum = reinterpret_cast<double2*>(ctx->xchg + ctx->x_sum);
             ctx->g_pack = ctx->xchg + ctx->x_pack;
             memset(ctx->x_epoch, 0, sizeof(ctx->x_epoch));
             CK(dalloc(&ctx->g_cent, 5 * tg)); CK(dalloc(&ctx->g_best_w, tg)); CK(dalloc(&ctx->g_best_idx, tg));
@@ -281,6 +282,23 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
 static inline uint64_t global_count(const eslam_gpu_ctx* ctx) { return sharded(ctx) ? ctx->shard.global_count : ctx->n; }
 static inline uint64_t base_index(const eslam_gpu_ctx* ctx) { return sharded(ctx) ? (uint64_t)ctx->shard.rank * ctx->n : 0; }
 static inline unsigned tile_ofs(const eslam_gpu_ctx* ctx) { return sharded(ctx) ? (unsigned)ctx->shard.rank * ctx->t_local : 0; }
+// LOCAL_MIGRATE sharding: the logical shards are the ranks of a sharded filter, or cfg.virtual_shards equal parts of an
+// unsharded context (the same logic on one GPU; identical results).  Inert (mode 0) with one shard or in EXACT_GLOBAL mode.
+static ShardPlan shard_plan(const eslam_gpu_ctx* ctx) {
+    ShardPlan sp; memset(&sp, 0, sizeof(sp));
+    if (ctx->cfg.shard_mode != ESLAM_SHARD_LOCAL_MIGRATE || ctx->cfg.resample_mode != ESLAM_RESAMPLE_STRATIFIED) return sp;
+    unsigned G = 1, first = 0, count = 1;
+    if (sharded(ctx)) { G = (unsigned)ctx->shard.world; first = (unsigned)ctx->shard.rank; }
+    else if (ctx->cfg.virtual_shards > 1 && ctx->cfg.virtual_shards <= ESLAM_MAX_SHARDS && ctx->n % ((uint64_t)ctx->cfg.virtual_shards * TILE) == 0) {
+        G = (unsigned)ctx->cfg.virtual_shards; count = G;
+    }
+    if (G <= 1) return sp;
+    sp.mode = 1; sp.n_shards = G; sp.first = first; sp.count = count;
+    sp.tiles_per_shard = ctx->t_global / G; sp.n_shard = (unsigned long long)sp.tiles_per_shard * TILE;
+    sp.min_share = ctx->cfg.migrate_min_share; sp.min_ess = ctx->cfg.migrate_min_ess;
+    sp.shard_tot = ctx->shard_tot;
+    return sp;
+}
 static inline double scan_eps(const eslam_gpu_ctx* ctx) {
     // |sequential fp64 running sum - approximate parallel prefix| <= N 2^-53 (relative); 8x margin, floor 2^-40
     const double e = ldexp((double)global_count(ctx), -50);
@@ -391,6 +409,7 @@ void eslam_gpu_default_config(eslam_gpu_config* c) {
     c->min_contacts = 3; c->contact_likelihood_correction = 0.33; c->contact_point_radius = 0.01;   // :55-59
     c->use_slip_update = 0; c->use_shape_update = 1; c->use_hash = 0;
     c->resample_mode = ESLAM_RESAMPLE_STRATIFIED; c->patch_size = 0;
+    c->shard_mode = ESLAM_SHARD_EXACT_GLOBAL; c->migrate_min_share = 0.25; c->migrate_min_ess = 0.05; c->virtual_shards = 0;
 }
 
 int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_shard* shard, eslam_gpu_ctx** out) {
@@ -413,7 +432,7 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     ctx->lean_threads = getenv("ESLAM_GPU_LEAN_THREADS") ? atoi(getenv("ESLAM_GPU_LEAN_THREADS")) : 1024;
     ctx->bin_count = nullptr; ctx->keys = nullptr; ctx->bin_list = nullptr; ctx->bin_offs = nullptr; ctx->bin_next = nullptr; ctx->cta_bin = nullptr;
     for (int b = 0; b < 2; ++b) { ctx->patch[b] = nullptr; ctx->porigin[b] = nullptr; }
-    ctx->l_part_a = ctx->g_part_a = nullptr; ctx->l_tile_sum = ctx->g_tile_sum = ctx->l_tile_sq = ctx->g_tile_sq = nullptr;
+    ctx->l_part_a = ctx->g_part_a = nullptr; ctx->l_tile_sum = ctx->g_tile_sum = nullptr; ctx->l_tile_sq = ctx->g_tile_sq = nullptr; ctx->shard_tot = nullptr;
     ctx->l_desc = nullptr; ctx->l_pool = nullptr; ctx->l_pack = ctx->g_pack = nullptr; ctx->pack_bytes = 0;
     ctx->l_cent = ctx->g_cent = ctx->l_best_w = ctx->g_best_w = nullptr; ctx->l_best_idx = ctx->g_best_idx = nullptr;
     ctx->tile_prefix = ctx->scratch_a = ctx->scratch_b = ctx->tile_sin = ctx->sb = nullptr;
@@ -438,6 +457,7 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->side_ev, cudaEventDisableTiming));
     CK(dalloc(&ctx->ticket, 1)); CK(cudaMemsetAsync(ctx->ticket, 0, sizeof(unsigned), ctx->stream));
+    CK(dalloc(&ctx->shard_tot, (size_t)ESLAM_MAX_SHARDS)); CK(cudaMemsetAsync(ctx->shard_tot, 0, ESLAM_MAX_SHARDS * sizeof(double), ctx->stream));
     CK(dalloc(&ctx->bin_count, (size_t)MAX_BINS)); CK(dalloc(&ctx->bin_offs, (size_t)MAX_BINS)); CK(dalloc(&ctx->bin_next, (size_t)MAX_BINS));
     CK(dalloc(&ctx->cta_bin, (size_t)ctx->sm_count));
     CK(cudaMemsetAsync(ctx->bin_count, 0, MAX_BINS * sizeof(int), ctx->stream));
@@ -841,8 +861,9 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     if (apply_loop_b) CK(launch_pdl(ctx, k_loop_b<true>, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, ctx->l_tile_sum));
     else CK(launch_pdl(ctx, k_loop_b<false>, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, ctx->l_tile_sum));
     LAUNCHED();
-    XCH(1, ctx->l_tile_sum, ctx->x_sum, T * sizeof(double));
-    CK(launch_pdl(ctx, k_reduce_b, 1, 1024, 0, ctx->g_tile_sum, TG, ng, ctx->sc, ctx->scratch_a, ctx->scratch_b, ctx->tile_prefix, normalise,
+    XCH(1, ctx->l_tile_sum, ctx->x_sum, T * sizeof(double2));
+    const ShardPlan sp = shard_plan(ctx);
+    CK(launch_pdl(ctx, k_reduce_b, 1, 1024, 0, ctx->g_tile_sum, TG, ng, ctx->sc, ctx->scratch_a, ctx->scratch_b, ctx->tile_prefix, normalise, sp,
                   XFLAGS(1), XEPOCH(1), XWORLD()));
     LAUNCHED();
     CK(launch_pdl(ctx, k_norm_scan, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, ng, ctx->tile_prefix, ctx->l_tile_sq, ctx->l_desc, ctx->l_pool,
@@ -853,7 +874,7 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     const int decide = mode == 0 ? 0 : 1;
     CK(launch_pdl(ctx, k_chain, 1, 1024, sizeof(ChainSmem), pk, TG, ctx->sc, ctx->scratch_a,
                                                          ctx->scratch_b, ctx->tile_bofs, ctx->tile_pre, ctx->tile_sin, ctx->sb,
-                                                         mode == 2 ? 0ull : ctx->cfg.min_effective, decide, force,
+                                                         mode == 2 ? 0ull : ctx->cfg.min_effective, decide, force, sp,
                                                          XFLAGS(2), XEPOCH(2), XWORLD()));
     LAUNCHED();
     if (mode == 2) return ESLAM_OK;
@@ -868,7 +889,8 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
         const ModelParams mp = model_params(ctx);
         CK(launch_pdl(ctx, k_resample_local<RS_CTA>, (unsigned)((n + RS_CTA - 1) / RS_CTA), RS_CTA, 0, ctx->st, ctx->sc, ctx->tile_sin, TG, T, n, ng, base_index(ctx),
                                                                              mp.k0, mp.k1, ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC,
-                                                                             ctx->ancestors, ctx->ticket, ctx->peers, XFLAGS(3), XEPOCH(3), XWORLD()));
+                                                                             ctx->ancestors, ctx->ticket, ctx->peers, sp, tile_ofs(ctx), (unsigned)ctx->shard.rank,
+                                                                             XFLAGS(3), XEPOCH(3), XWORLD()));
         LAUNCHED();
         return ESLAM_OK;
     }
@@ -880,7 +902,7 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
         // search in shared memory, copy and buffer swap in one kernel
         CK(launch_pdl(ctx, k_resample_local<RS_CTA>, (unsigned)((n + RS_CTA - 1) / RS_CTA), RS_CTA, 0, ctx->st, ctx->sc, ctx->tile_sin, T, T, n, n, 0ull, mp.k0, mp.k1,
                                                                               ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC,
-                                                                              ctx->ancestors, ctx->ticket, ctx->peers, (const unsigned*)nullptr, 0u, 1));
+                                                                              ctx->ancestors, ctx->ticket, ctx->peers, sp, 0u, 0u, (const unsigned*)nullptr, 0u, 1));
         LAUNCHED();
         return ESLAM_OK;
     }
@@ -1065,9 +1087,10 @@ int eslam_gpu_weights_sum(eslam_gpu_ctx* ctx, double* sum) {
     if (!sum) return ESLAM_ERR_INVALID;
     k_loop_b<false><<<ctx->t_local, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->n, ctx->l_tile_sum);
     LAUNCHED();
-    XCH(1, ctx->l_tile_sum, ctx->x_sum, ctx->t_local * sizeof(double));
+    XCH(1, ctx->l_tile_sum, ctx->x_sum, ctx->t_local * sizeof(double2));
+    ShardPlan sp0; memset(&sp0, 0, sizeof(sp0));
     k_reduce_b<<<1, 1024, 0, ctx->stream>>>(ctx->g_tile_sum, ctx->t_global, global_count(ctx), ctx->sc, ctx->scratch_a, ctx->scratch_b,
-                                            ctx->tile_prefix, 0, XFLAGS(1), XEPOCH(1), XWORLD());
+                                            ctx->tile_prefix, 0, sp0, XFLAGS(1), XEPOCH(1), XWORLD());
     LAUNCHED();
     st = read_scalars(ctx);
     if (st != ESLAM_OK) return st;

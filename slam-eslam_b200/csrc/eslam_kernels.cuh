@@ -32,6 +32,7 @@ namespace em = eslam_math;
 #define MAX_BND_TOTAL 2048       // boundary elements per resample (pool + chain capacity); more -> sequential fallback
 #define BIN_NONE (-100000)       // "no binade": piece made of zero / sub-quarter-ulp weights only
 #define ESLAM_MAX_RANKS 8        // GPUs of one box
+#define ESLAM_MAX_SHARDS 64      // logical shards (ranks, or virtual shards of one context)
 #define ERR_ZERO_VARIANCE_BIT 1
 #define ERR_CDF_FALLBACK_BIT 2
 
@@ -62,6 +63,8 @@ struct DevScalars {              // device-resident scalars of one context
     unsigned int fallbacks;      // times the sequential CDF fallback ran
     unsigned int defer_count;    // particles the binning flagged for contact_eval (map border, out-of-range values; live counter)
     unsigned int defer_last;     // its value at the end of the last update (diagnostics)
+    int migrate;                 // LOCAL_MIGRATE sharding: 1 = this step resamples exact-globally (k_reduce_b decides)
+    int pad_migrate;
 };
 
 struct TilePartA {               // per-tile partials of loop A
@@ -730,8 +733,17 @@ __global__ void __launch_bounds__(1024, 1) k_project_bin(const __grid_constant__
             ok = ok & ((unsigned)(cx - x0 - F.margin) < (unsigned)(C.map.tile_w - 2 * F.margin)) &
                  ((unsigned)(cy - y0 - F.margin) < (unsigned)(C.map.tile_h - 2 * F.margin));
         }
-        bin = b; rank = atomicAdd(&hist[b], 1);
+        bin = b;
         flagged = !ok;
+    }
+    {   // rank inside the bin: one shared-memory atomic per (warp, bin) instead of one per particle (a warp's particles fall
+        // into one to three bins, so per-particle atomics on the same address serialise 32-fold)
+        const unsigned peers_m = __match_any_sync(0xffffffffu, bin);
+        const int leader = __ffs(peers_m) - 1;
+        int base_rank = 0;
+        if (lane == leader && bin >= 0) base_rank = atomicAdd(&hist[bin], __popc(peers_m));
+        base_rank = __shfl_sync(0xffffffffu, base_rank, leader);
+        rank = base_rank + __popc(peers_m & ((1u << lane) - 1u));
     }
     const unsigned m = __ballot_sync(0xffffffffu, flagged);
     if (m && lane == (__ffs(m) - 1)) atomicAdd(&C.sc->defer_count, (unsigned)__popc(m));   // diagnostics only
@@ -1184,11 +1196,21 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_a(const TilePartA* part, uns
     }
 }
 
+// LOCAL_MIGRATE sharding (include/eslam_gpu.h): the logical shards are runs of tiles_per_shard consecutive tiles of the
+// global tile index space; this context holds shards [first, first + count).  mode == 0: everything below is inert.
+struct ShardPlan {
+    int mode;                        // ESLAM_SHARD_LOCAL_MIGRATE when there is more than one logical shard, else 0
+    unsigned n_shards, tiles_per_shard, first, count;
+    unsigned long long n_shard;      // particles per shard
+    double min_share, min_ess;
+    double* shard_tot;               // [n_shards] exact left-to-right total of every local shard (written by k_chain)
+};
+
 // ------------------------------------------------------------------------------------------------ loop B + raw sums
 // weight *= mprob * pow(discount*floating_weight, 4 - cpoints.size())  (:332-345); per-tile sums of the result
 template <bool APPLY>
 __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, const DevScalars* sc, unsigned long long n,
-                                                         double* tile_sum) {
+                                                         double2* tile_sum) {
     pdl_start();
     __shared__ double red[8];
     const int cur = sc->cur;
@@ -1224,24 +1246,31 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, const Dev
         }
     }
     const double s = tile_tree_sum4(w, red);
-    if (threadIdx.x == 0) tile_sum[blockIdx.x] = s;
+    double q[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) q[j] = w[j] * w[j];
+    const double sq = tile_tree_sum4(q, red);                        // per-shard ESS of the LOCAL_MIGRATE decision (k_reduce_b)
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = make_double2(s, sq);
 }
 
 // ------------------------------------------------------------------------------------------------ reduce B (one CTA)
 // getWeightsSum (src/ParticleFilter.hpp:34-39) and approximate per-tile prefixes of the (normalised) weights
-__global__ void __launch_bounds__(1024, 1) k_reduce_b(const double* tile_sum, unsigned n_tiles, unsigned long long n,
+__global__ void __launch_bounds__(1024, 1) k_reduce_b(const double2* tile_sum2, unsigned n_tiles, unsigned long long n,
                                                       DevScalars* sc, double* scratch_a, double* scratch_b,
-                                                      double* tile_prefix, int normalise, const unsigned* xflags, unsigned epoch, int world) {
+                                                      double* tile_prefix, int normalise, const ShardPlan sp,
+                                                      const unsigned* xflags, unsigned epoch, int world) {
     pdl_start();
     peer_wait(xflags, epoch, world);
     __shared__ double sh[64];
     __shared__ double tree_a[TREE_SMEM], tree_b[TREE_SMEM / 2];
+    __shared__ int s_migrate;
+    auto tsum = [&](unsigned t) -> double { return tile_sum2[t].x; };
     double total;
     if (n_tiles > 1 && ((n_tiles + 1) >> 1) <= TREE_SMEM) {
         // the tree straight from the tile sums (no copy through global scratch); same tree as block_tree_reduce
         double *ta = tree_a, *tb = tree_b;
         unsigned m = (n_tiles + 1) >> 1;
-        for (unsigned i = threadIdx.x; i < m; i += blockDim.x) ta[i] = (2 * i + 1 < n_tiles) ? tile_sum[2 * i] + tile_sum[2 * i + 1] : tile_sum[2 * i];
+        for (unsigned i = threadIdx.x; i < m; i += blockDim.x) ta[i] = (2 * i + 1 < n_tiles) ? tsum(2 * i) + tsum(2 * i + 1) : tsum(2 * i);
         __syncthreads();
         while (m > 1) {
             const unsigned h = (m + 1) >> 1;
@@ -1252,39 +1281,69 @@ __global__ void __launch_bounds__(1024, 1) k_reduce_b(const double* tile_sum, un
         total = ta[0];
         __syncthreads();
     } else {
-        for (unsigned i = threadIdx.x; i < n_tiles; i += blockDim.x) scratch_a[i] = tile_sum[i];
+        for (unsigned i = threadIdx.x; i < n_tiles; i += blockDim.x) scratch_a[i] = tsum(i);
         __syncthreads();
         total = block_tree_reduce(scratch_a, scratch_b, n_tiles, tree_a, tree_b);
     }
     const int uniform = normalise && (total <= 0.0);                                 // :51 (Q8)
     if (threadIdx.x == 0) { sc->sum_w = total; sc->uniform = uniform; sc->pool_count = 0; }
+    // LOCAL_MIGRATE: does any shard's share of the weight or its own effective sample size collapse?  Per shard the pairwise
+    // tree over its tiles' sums of w and of w^2 (every rank holds all tiles' sums, so every rank decides the same).
+    int migrate = 1;
+    if (sp.mode) {
+        if (threadIdx.x == 0) s_migrate = 0;
+        __syncthreads();
+        if (total > 0.0) {
+            for (unsigned g = 0; g < sp.n_shards; ++g) {
+                const double2* src = tile_sum2 + (size_t)g * sp.tiles_per_shard;
+                double wq[2];
+                for (int c = 0; c < 2; ++c) {
+                    for (unsigned i = threadIdx.x; i < sp.tiles_per_shard; i += blockDim.x) scratch_a[i] = c ? src[i].y : src[i].x;
+                    __syncthreads();
+                    wq[c] = block_tree_reduce(scratch_a, scratch_b, sp.tiles_per_shard, tree_a, tree_b);
+                    __syncthreads();
+                }
+                const double share = (wq[0] / total) * (double)sp.n_shards;
+                const double essg = (wq[0] * wq[0]) / wq[1];
+                if (threadIdx.x == 0 && (share < sp.min_share || essg < sp.min_ess * (double)sp.n_shard)) s_migrate = 1;
+            }
+        }
+        __syncthreads();
+        migrate = s_migrate;
+    }
+    if (threadIdx.x == 0) sc->migrate = migrate;
+    const bool local = sp.mode && !migrate;
     // exclusive scan of the per-tile masses (approximate is enough: only used to classify elements; k_norm_scan and k_cdf
-    // read the same values)
+    // read the same values).  Local resampling: the scan restarts at every shard (the running sums there start from zero).
     auto mass = [&](unsigned t) -> double {
         if (uniform) { const unsigned long long c = min((unsigned long long)TILE, n - (unsigned long long)t * TILE); return (double)c / (double)n; }
-        return normalise ? tile_sum[t] / total : tile_sum[t];
+        return normalise ? tsum(t) / total : tsum(t);
     };
     // rounds of 1024 tiles, one per thread (coalesced): block exclusive scan by shuffles, a carry from round to round
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double carry = 0.0;
-    for (unsigned r0 = 0; r0 < n_tiles; r0 += 1024) {
-        const unsigned t = r0 + threadIdx.x;
-        const double local = t < n_tiles ? mass(t) : 0.0;
-        double inc = local;
+    const unsigned seg = local ? sp.tiles_per_shard : n_tiles;
+    for (unsigned s0 = 0; s0 < n_tiles; s0 += seg) {
+        double carry = 0.0;
+        const unsigned s1 = min(s0 + seg, n_tiles);
+        for (unsigned r0 = s0; r0 < s1; r0 += 1024) {
+            const unsigned t = r0 + threadIdx.x;
+            const double local_m = t < s1 ? mass(t) : 0.0;
+            double inc = local_m;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (unsigned)o) inc += v; }
-        if (lane == 31) sh[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            double w = sh[lane];
+            for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (unsigned)o) inc += v; }
+            if (lane == 31) sh[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                double w = sh[lane];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= (unsigned)o) w += v; }
-            sh[32 + lane] = w;
+                for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= (unsigned)o) w += v; }
+                sh[32 + lane] = w;
+            }
+            __syncthreads();
+            if (t < s1) tile_prefix[t] = carry + ((warp ? sh[32 + warp - 1] : 0.0) + (inc - local_m));
+            carry += sh[32 + 31];                                            // every thread keeps the same carry
+            __syncthreads();
         }
-        __syncthreads();
-        if (t < n_tiles) tile_prefix[t] = carry + ((warp ? sh[32 + warp - 1] : 0.0) + (inc - local));
-        carry += sh[32 + 31];                                            // every thread keeps the same carry
-        __syncthreads();
     }
 }
 
@@ -1542,7 +1601,7 @@ struct ChainPack {
 __global__ void __launch_bounds__(1024, 1) k_chain(ChainPack pk, unsigned n_tiles,
                                                    DevScalars* sc, double* scratch_a, double* scratch_b,
                                                    int* tile_bofs, SegF* tile_pre, double* tile_sin, double* sb_out,
-                                                   unsigned long long min_effective, int decide, int force,
+                                                   unsigned long long min_effective, int decide, int force, const ShardPlan sp,
                                                    const unsigned* xflags, unsigned epoch, int world) {
     pdl_start();
     peer_wait(xflags, epoch, world);
@@ -1591,89 +1650,106 @@ __global__ void __launch_bounds__(1024, 1) k_chain(ChainPack pk, unsigned n_tile
     // counts and a segmented exclusive scan of the tile functions (shuffles inside the warp, warp 0 across the warp totals),
     // continued from round to round by a carry.  Each thread then places its tile's boundary elements and segment
     // functions into the chain arrays straight away.
+    // The chain runs over one segment of tiles -- all of them (one GPU, exact-global sharding) -- or, when the shards resample
+    // locally (LOCAL_MIGRATE and no shard has collapsed), once per shard held here, each restarting from a zero sum.
     const unsigned lane = tid & 31, warp = tid >> 5;
     __shared__ int s_carry_c; __shared__ SegE s_carry_e;
-    if (tid == 0) { s_carry_c = 0; s_carry_e.f = segf_identity(); s_carry_e.head = -1; }
-    __syncthreads();
-    for (unsigned r0 = 0; r0 < n_tiles; r0 += 1024) {
-        const unsigned t = r0 + tid;
-        const bool have = t < n_tiles;
-        TileDesc D; D.n_bnd = 0; D.overflow = 0; D.head_b = BIN_NONE; D.pad = 0; D.head_d0 = 0; D.head_d1 = 0; D.bnd_base = 0; D.pad2 = 0;
-        if (have) D = pk.desc(t);
-        const BndEntry* B = pk.pool(have ? t / tiles_per_rank : 0) + D.bnd_base;
-        if (D.overflow) atomicOr(&s_bad, 1);
-        const int cnt = D.overflow ? 0 : D.n_bnd;
-        SegE e;                                                          // what the tile does to the running function
-        if (cnt > 0) { const BndEntry& Lb = B[cnt - 1]; e.head = (int)t; e.f.b = Lb.b; e.f.d0 = Lb.d0; e.f.d1 = Lb.d1; e.f.pad = 0; }
-        else { e.head = -1; e.f.b = D.head_b; e.f.d0 = D.head_d0; e.f.d1 = D.head_d1; e.f.pad = D.pad; }
-        int inc_c = cnt; SegE inc_e = e;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const SegE v = sege_shfl_up(inc_e, o); const int cv = __shfl_up_sync(0xffffffffu, inc_c, o);
-            if (lane >= (unsigned)o) { inc_e = sege_combine(v, inc_e); inc_c += cv; }
-        }
-        if (lane == 31) { sh_i[warp] = inc_c; sh_e[warp] = inc_e; }
+    const bool local = sp.mode && !sc->migrate;
+    const unsigned n_seg = local ? sp.count : 1u;
+    int bnd_base = 0;
+    for (unsigned sg = 0; sg < n_seg; ++sg) {
+        const unsigned t_begin = local ? (sp.first + sg) * sp.tiles_per_shard : 0u;
+        const unsigned t_end = local ? t_begin + sp.tiles_per_shard : n_tiles;
         __syncthreads();
-        if (warp == 0) {
-            int wc = sh_i[lane]; SegE we = sh_e[lane];
+        if (tid == 0) { s_carry_c = bnd_base; s_carry_e.f = segf_identity(); s_carry_e.head = -1; }
+        __syncthreads();
+        for (unsigned r0 = t_begin; r0 < t_end; r0 += 1024) {
+            const unsigned t = r0 + tid;
+            const bool have = t < t_end;
+            TileDesc D; D.n_bnd = 0; D.overflow = 0; D.head_b = BIN_NONE; D.pad = 0; D.head_d0 = 0; D.head_d1 = 0; D.bnd_base = 0; D.pad2 = 0;
+            if (have) D = pk.desc(t);
+            const BndEntry* B = pk.pool(have ? t / tiles_per_rank : 0) + D.bnd_base;
+            if (D.overflow) atomicOr(&s_bad, 1);
+            const int cnt = D.overflow ? 0 : D.n_bnd;
+            SegE e;                                                          // what the tile does to the running function
+            if (cnt > 0) { const BndEntry& Lb = B[cnt - 1]; e.head = (int)t; e.f.b = Lb.b; e.f.d0 = Lb.d0; e.f.d1 = Lb.d1; e.f.pad = 0; }
+            else { e.head = -1; e.f.b = D.head_b; e.f.d0 = D.head_d0; e.f.d1 = D.head_d1; e.f.pad = D.pad; }
+            int inc_c = cnt; SegE inc_e = e;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const SegE v = sege_shfl_up(we, o); const int cv = __shfl_up_sync(0xffffffffu, wc, o);
-                if (lane >= (unsigned)o) { we = sege_combine(v, we); wc += cv; }
+                const SegE v = sege_shfl_up(inc_e, o); const int cv = __shfl_up_sync(0xffffffffu, inc_c, o);
+                if (lane >= (unsigned)o) { inc_e = sege_combine(v, inc_e); inc_c += cv; }
             }
-            sh_i[32 + lane] = wc; sh_e[32 + lane] = we;                  // inclusive over warps
-        }
-        __syncthreads();
-        // exclusive value of this thread: carry o (all earlier warps) o (earlier lanes of this warp)
-        SegE run_e = sege_shfl_up(inc_e, 1); int run_c = __shfl_up_sync(0xffffffffu, inc_c, 1);
-        if (lane == 0) { run_e.f = segf_identity(); run_e.head = -1; run_c = 0; }
-        if (warp > 0) { run_e = sege_combine(sh_e[32 + warp - 1], run_e); run_c += sh_i[32 + warp - 1]; }
-        run_e = sege_combine(s_carry_e, run_e); run_c += s_carry_c;
-        const SegE round_e = sh_e[32 + 31]; const int round_c = sh_i[32 + 31];
-        if (have) {
-            tile_bofs[t] = run_c; tile_pre[t] = run_e.f;
-            // boundary k = run_c + j: weight, and the function of the segment that follows it
-            for (int j = 0; j < cnt; ++j) {
-                if (run_c + j < MAX_BND_TOTAL) {
-                    cs.bw[run_c + j] = B[j].w;
-                    if (j + 1 < cnt) { SegF f; f.b = B[j].b; f.d0 = B[j].d0; f.d1 = B[j].d1; f.pad = 0; cs.seg[run_c + j] = f; }
+            if (lane == 31) { sh_i[warp] = inc_c; sh_e[warp] = inc_e; }
+            __syncthreads();
+            if (warp == 0) {
+                int wc = sh_i[lane]; SegE we = sh_e[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const SegE v = sege_shfl_up(we, o); const int cv = __shfl_up_sync(0xffffffffu, wc, o);
+                    if (lane >= (unsigned)o) { we = sege_combine(v, we); wc += cv; }
+                }
+                sh_i[32 + lane] = wc; sh_e[32 + lane] = we;                  // inclusive over warps
+            }
+            __syncthreads();
+            // exclusive value of this thread: carry o (all earlier warps) o (earlier lanes of this warp)
+            SegE run_e = sege_shfl_up(inc_e, 1); int run_c = __shfl_up_sync(0xffffffffu, inc_c, 1);
+            if (lane == 0) { run_e.f = segf_identity(); run_e.head = -1; run_c = 0; }
+            if (warp > 0) { run_e = sege_combine(sh_e[32 + warp - 1], run_e); run_c += sh_i[32 + warp - 1]; }
+            run_e = sege_combine(s_carry_e, run_e); run_c += s_carry_c;
+            const SegE round_e = sh_e[32 + 31]; const int round_c = sh_i[32 + 31];
+            if (have) {
+                tile_bofs[t] = run_c; tile_pre[t] = run_e.f;
+                // boundary k = run_c + j: weight, and the function of the segment that follows it
+                for (int j = 0; j < cnt; ++j) {
+                    if (run_c + j < MAX_BND_TOTAL) {
+                        cs.bw[run_c + j] = B[j].w;
+                        if (j + 1 < cnt) { SegF f; f.b = B[j].b; f.d0 = B[j].d0; f.d1 = B[j].d1; f.pad = 0; cs.seg[run_c + j] = f; }
+                    }
+                }
+                if (cnt > 0 && run_c > bnd_base && run_c - 1 < MAX_BND_TOTAL) {
+                    // segment after boundary run_c-1 ends with this tile's head piece
+                    SegF hf; hf.b = D.head_b; hf.d0 = D.head_d0; hf.d1 = D.head_d1; hf.pad = D.pad;
+                    cs.seg[run_c - 1] = segf_compose(run_e.f, hf);
                 }
             }
-            if (cnt > 0 && run_c > 0 && run_c - 1 < MAX_BND_TOTAL) {
-                // segment after boundary run_c-1 ends with this tile's head piece
-                SegF hf; hf.b = D.head_b; hf.d0 = D.head_d0; hf.d1 = D.head_d1; hf.pad = D.pad;
-                cs.seg[run_c - 1] = segf_compose(run_e.f, hf);
-            }
+            __syncthreads();                                                 // everyone has read the carry and the round totals
+            if (tid == 0) { s_carry_e = sege_combine(s_carry_e, round_e); s_carry_c += round_c; }
+            __syncthreads();
         }
-        __syncthreads();                                                 // everyone has read the carry and the round totals
-        if (tid == 0) { s_carry_e = sege_combine(s_carry_e, round_e); s_carry_c += round_c; }
+        const int total = s_carry_c;
+        if (tid == 0 && total > MAX_BND_TOTAL) s_bad = 1;
         __syncthreads();
-    }
-    const int total = s_carry_c;
-    if (tid == 0 && total > MAX_BND_TOTAL) s_bad = 1;
-    __syncthreads();
-    if (s_bad) { if (tid == 0) { atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT); sc->n_boundaries = total; } return; }
-    if (tid == 0) {
-        // the sequential part: one real fp64 add per boundary element, one integer add per segment
-        double S = 0.0; int b2 = 0;
-        for (int k = 0; k < total; ++k) {
-            S = S + cs.bw[k];
-            cs.bw[k] = S;
-            if (k + 1 < total) S = segf_apply(S, cs.seg[k], b2);
+        if (s_bad) { if (tid == 0) { atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT); sc->n_boundaries = total; } return; }
+        if (tid == 0) {
+            // the sequential part: one real fp64 add per boundary element, one integer add per segment
+            double S = 0.0; int b2 = 0;
+            for (int k = bnd_base; k < total; ++k) {
+                S = S + cs.bw[k];
+                cs.bw[k] = S;
+                if (k + 1 < total) S = segf_apply(S, cs.seg[k], b2);
+            }
+            if (local) {                                                     // the shard's total: what its strata are scaled by
+                double tot = 0.0;
+                if (total > bnd_base) tot = segf_apply(cs.bw[total - 1], s_carry_e.f, b2);
+                sp.shard_tot[sp.first + sg] = tot;
+            }
+            if (b2) { s_bad = 1; atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT); }
+            sc->n_boundaries = total;
         }
-        if (b2) { s_bad = 1; atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT); }
-        sc->n_boundaries = total;
+        __syncthreads();
+        if (s_bad) return;
+        int b3 = 0;
+        for (unsigned t = t_begin + tid; t < t_end; t += blockDim.x) {      // (each thread reads back what it wrote above)
+            const int ofs = tile_bofs[t];
+            const double S0 = ofs > bnd_base ? cs.bw[ofs - 1] : 0.0;
+            tile_sin[t] = segf_apply(S0, tile_pre[t], b3);
+        }
+        if (b3) atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT);
+        bnd_base = total;
     }
     __syncthreads();
-    if (s_bad) return;
-    for (unsigned k = tid; k < (unsigned)total; k += blockDim.x) sb_out[k] = cs.bw[k];
-    int b3 = 0;
-    for (unsigned t = tid; t < n_tiles; t += blockDim.x) {               // (each thread reads back what it wrote above)
-        const int ofs = tile_bofs[t];
-        const double S0 = ofs > 0 ? cs.bw[ofs - 1] : 0.0;
-        tile_sin[t] = segf_apply(S0, tile_pre[t], b3);
-    }
-    if (b3) atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT);
+    for (unsigned k = tid; k < (unsigned)bnd_base; k += blockDim.x) sb_out[k] = cs.bw[k];
 }
 
 // exact running sum of every element: cdf[i] == the reference's sum_w after adding xi_k[i].weight
@@ -1790,8 +1866,8 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
                                                             unsigned n_tiles, unsigned tiles_per_rank, unsigned long long n,
                                                             unsigned long long n_global, unsigned long long base, uint32_t k0key,
                                                             uint32_t k1key, int systematic, uint32_t* ancestors, unsigned* ticket,
-                                                            const __grid_constant__ PeerTable peers, const unsigned* xflags,
-                                                            unsigned epoch, int world) {
+                                                            const __grid_constant__ PeerTable peers, const ShardPlan sp, unsigned tile_ofs,
+                                                            unsigned my_rank, const unsigned* xflags, unsigned epoch, int world) {
     pdl_start();
     __shared__ double s_cdf[RS_TILES * TILE];
     if (!sc->do_resample) return;
@@ -1799,9 +1875,24 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
     peer_wait(xflags, epoch, world);                                     // every rank's running sum is final before anyone reads a peer
     const unsigned tid = threadIdx.x;
     const unsigned long long kb = (unsigned long long)blockIdx.x * RS_THREADS, k = kb + tid;   // local stratum
+    // Local resampling (LOCAL_MIGRATE sharding, no shard collapsed): the CTA's strata belong to ONE logical shard held here; they
+    // walk that shard's own running sum (restarted at zero, tile starts at tile_ofs + s T_s of the table), scaled by the shard's
+    // total, and their ancestors are that shard's own particles.  Everything below runs on the rebound quantities; in the exact
+    // mode they are the arguments themselves and scale == 1.0 (a multiplication that changes no bit).
+    const bool local = sp.mode && !sc->migrate;
+    const unsigned long long n_ctx = n;                                  // particles of this context
+    unsigned long long po = 0, anc_base = 0, sbase = base + kb;          // sbase: index of the CTA's first stratum in its walk
+    unsigned q_fixed = 0; double scale = 1.0;
+    if (local) {
+        const unsigned s = (unsigned)(kb / sp.n_shard);
+        po = (unsigned long long)s * sp.n_shard; anc_base = base + po; sbase = kb - po;
+        tile_start += tile_ofs + s * sp.tiles_per_shard;
+        n_tiles = sp.tiles_per_shard; tiles_per_rank = sp.tiles_per_shard; n = sp.n_shard; n_global = sp.n_shard;
+        q_fixed = my_rank; world = 1; scale = sp.shard_tot[sp.first + s];
+    }
     // the tile starts are non-decreasing, so "the last tile starting below thr" is a count: one coalesced read of the table and
     // two block-wide counts instead of two dependent binary searches.  thr_lo / thr_hi bound every sum_r of this CTA.
-    const double thr_lo = (double)(base + kb) / (double)n_global, thr_hi = (double)(base + kb + (unsigned long long)RS_THREADS) / (double)n_global;
+    const double thr_lo = ((double)sbase / (double)n_global) * scale, thr_hi = ((double)(sbase + (unsigned long long)RS_THREADS) / (double)n_global) * scale;
     unsigned c_lo = 0, c_hi = 0;
     for (unsigned t0 = 0; t0 < n_tiles; t0 += RS_THREADS) {
         const double ts = (t0 + tid < n_tiles) ? __ldg(&tile_start[t0 + tid]) : 1.7e308;
@@ -1810,21 +1901,25 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
     }
     const unsigned t_lo = c_lo == 0 ? 0u : c_lo - 1, t_hi = c_hi == 0 ? 0u : c_hi - 1;
     const bool in_smem = (t_hi - t_lo) < RS_TILES;
-    const unsigned long long g0 = (unsigned long long)t_lo * TILE;                        // window [g0, g1) of global elements
+    const unsigned long long g0 = (unsigned long long)t_lo * TILE;                        // window [g0, g1) of the walk's elements
     const unsigned long long g1 = min(((unsigned long long)t_hi + 1) * TILE, n_global);
     if (in_smem) {
-        for (unsigned long long j = g0 + tid; j < g1; j += RS_THREADS) {
-            const unsigned q = (unsigned)(j / n);                                         // owner of element j
-            s_cdf[j - g0] = peers.cdf[q][j - (unsigned long long)q * n];
+        // tile by tile: the owner of a tile is a 32-bit quotient, uniform over the CTA (no per-element 64-bit division)
+        for (unsigned t = t_lo; t <= t_hi; ++t) {
+            const unsigned q = world > 1 ? t / tiles_per_rank : 0u;
+            const unsigned long long l0 = (unsigned long long)(t - q * tiles_per_rank) * TILE;   // owner-local start of the tile
+            const unsigned cnt = (unsigned)min((unsigned long long)TILE, n - l0);                // short only at the very end (one GPU)
+            const double* __restrict__ src = peers.cdf[world > 1 ? q : q_fixed] + po + l0;
+            for (unsigned e = tid; e < cnt; e += RS_THREADS) s_cdf[(t - t_lo) * TILE + e] = src[e];
         }
         __syncthreads();
     }
-    if (k < n) {
+    if (k < n_ctx) {
         const unsigned long long gk = systematic ? 0ull : base + k;
         const em::Philox4 r = em::philox4x32_10((uint32_t)gk, sc->resample_step, 0, stream_word(em::STREAM_RESAMPLE, gk), k0key, k1key);
         const double u = em::u01(r.v[0], r.v[1]);
-        const double sum_r = ((double)(base + k) + u) / (double)n_global;                 // :98
-        unsigned long long a;                                                             // global index of the ancestor
+        const double sum_r = (((double)(sbase + tid) + u) / (double)n_global) * scale;    // :98
+        unsigned long long a;                                                             // index of the ancestor in the walk
         if (in_smem) {
             unsigned lo = 0, hi = (unsigned)(g1 - g0);                                    // first element with !(cdf < sum_r)
             while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (s_cdf[mid] < sum_r) lo = mid + 1; else hi = mid; }
@@ -1834,20 +1929,21 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
             while (tlo < thi) { const unsigned mid = (tlo + thi) >> 1; if (__ldg(&tile_start[mid]) < sum_r) tlo = mid + 1; else thi = mid; }
             const unsigned t = tlo == 0 ? 0 : tlo - 1;
             const unsigned q = t / tiles_per_rank;
-            const double* cdf_q = peers.cdf[q];
+            const double* cdf_q = peers.cdf[world > 1 ? q : q_fixed] + po;
             unsigned long long lo = (unsigned long long)(t - q * tiles_per_rank) * TILE, hi = min(lo + TILE, n);   // owner-local
             while (lo < hi) { const unsigned long long mid = (lo + hi) >> 1; if (cdf_q[mid] < sum_r) lo = mid + 1; else hi = mid; }
             a = (unsigned long long)q * n + lo;           // lo == n: the first element of the next rank (its tile start is >= sum_r)
         }
         if (a >= n_global) a = n_global - 1;              // the reference walks off the end here; we stop at the last particle
-        ancestors[k] = (uint32_t)a;
-        const unsigned q = (unsigned)(a / n);
-        const unsigned long long la = a - (unsigned long long)q * n;
+        ancestors[k] = (uint32_t)(a + anc_base);
+        const unsigned q = world > 1 ? (unsigned)(a >> 10) / tiles_per_rank : 0u;         // owner: shards are whole tiles (TILE == 1024)
+        const unsigned long long la = a - (unsigned long long)q * n + po;
+        const unsigned qs = world > 1 ? q : q_fixed;
         const int cur = sc->cur, nxt = cur ^ 1;
 #pragma unroll
-        for (int f = 0; f < 7; ++f) st.f[nxt][f][k] = peers.f[q][cur][f][la];             // :104 copy keeps the weight (Q3)
+        for (int f = 0; f < 7; ++f) st.f[nxt][f][k] = peers.f[qs][cur][f][la];            // :104 copy keeps the weight (Q3)
 #pragma unroll
-        for (int f = 0; f < 2; ++f) st.b[nxt][f][k] = peers.b[q][cur][f][la];
+        for (int f = 0; f < 2; ++f) st.b[nxt][f][k] = peers.b[qs][cur][f][la];
     }
     // xi_k.swap(xi_kp) :107 by the last CTA (every CTA has read sc->cur by then)
     __syncthreads();

@@ -62,8 +62,38 @@ def main():
         if rank == 0:
             assert np.array_equal(c, ref.getCentroid()) and b == ref.getBestParticleIndex()
         comm.barrier()
+    # LOCAL_MIGRATE sharding: `world` real shards must reproduce one GPU running the same number of logical shards
+    # (cfg.virtual_shards), through local-walk steps and a migration step (a crushed shard)
+    cfg = dict(min_effective=n + 1, shard_mode=abi.SHARD_LOCAL_MIGRATE)
+    g = GpuPoseEstimator(abi.default_config(**cfg), device=local, shard=comm.shard(n_local))
+    comm.connect(g)
+    contacts, step = synthetic.setup_filter(g, "C2", n=n_local)
+    ref = None
     if rank == 0:
-        print("dist parity ok: %d ranks x %d particles bit-identical to one GPU" % (world, n_local))
+        ref = GpuPoseEstimator(abi.default_config(virtual_shards=world, **cfg), device=local)
+        synthetic.setup_filter(ref, "C2", n=n)
+    kinds = set()
+    for it in range(7):
+        if it == 4:
+            w = np.where(np.arange(n) < n_local, 1e-4, 1.0) / n      # shard 0 collapses: this step migrates
+            g.setParticles(weight=w[rank * n_local:(rank + 1) * n_local])
+            if ref:
+                ref.setParticles(weight=w)
+        r = g.stepFused(step, contacts)
+        allp = gather_particles(g, comm)
+        if rank == 0:
+            rr = ref.stepFused(step, contacts)
+            assert r.as_dict() == rr.as_dict(), (it, r.as_dict(), rr.as_dict())
+            q = ref.getParticles()
+            q["ancestors"] = ref.getAncestors()
+            for k in list(KEYS) + ["ancestors"]:
+                assert np.array_equal(allp[k], q[k]), "LOCAL_MIGRATE step %d: %s differs" % (it, k)
+            kinds.add("local" if np.array_equal(allp["ancestors"] // n_local, np.arange(n) // n_local) else "migrate")
+    if rank == 0:
+        assert kinds == {"local", "migrate"}, kinds
+    comm.barrier()
+    if rank == 0:
+        print("dist parity ok: %d ranks x %d particles bit-identical to one GPU (exact-global, systematic, LOCAL_MIGRATE)" % (world, n_local))
     td.destroy_process_group()
 
 

@@ -487,3 +487,49 @@ def test_gpu_against_live_reference_c2(gpu):
     ok = a["ok"].astype(bool)
     np.testing.assert_allclose(a["weight"][ok], b["weight"][ok], rtol=1e-5, atol=1e-300)
     np.testing.assert_allclose(a["z_delta"][ok], b["z_delta"][ok], rtol=0, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------- sharded resampling modes on one GPU
+@pytest.mark.parametrize("shards,n", [(4, 8192), (8, 65536)])
+def test_local_migrate_mode_bit_identical_to_oracle(gpu, oracle, shards, n):
+    """LOCAL_MIGRATE (include/eslam_gpu.h) with the particles of one GPU treated as `shards` logical shards: local walks
+    per shard while no shard has collapsed, the exact-global walk otherwise; every double, ancestors, flags identical to the
+    oracle's definition (tests/test_shard_modes.py), through trajectories that contain both kinds of step."""
+    cfg = dict(min_effective=n + 1, shard_mode=abi.SHARD_LOCAL_MIGRATE, virtual_shards=shards)
+    g, o, contacts, step = pair(gpu, oracle, "C2", n=n, **cfg)
+    ns = n // shards
+    own = np.arange(n) // ns
+    kinds = set()
+    for it in range(8):
+        if it == 4:      # crush shard 1: the next resampling must migrate
+            w = g.getParticles()["weight"].copy(); w[ns:2 * ns] *= 1e-3
+            g.setParticles(weight=w); o.setParticles(weight=w)
+        ra, rb = g.stepFused(step, contacts), (o.project(step), o.update(contacts))[1]
+        assert ra.as_dict() == rb.as_dict(), (it, ra.as_dict(), rb.as_dict())
+        a, b = g.getAncestors(), o.getAncestors()
+        assert np.array_equal(a, b), "ancestors differ at step %d" % it
+        kinds.add("local" if np.array_equal(a // ns, own) else "migrate")
+        assert_particles_equal(g.getParticles(), o.getParticles())
+    assert kinds == {"local", "migrate"}
+    assert g.debugCounters()["fallbacks"] == 0
+
+
+def test_local_migrate_resample_stage_adversarial(gpu, oracle):
+    """resample() alone in LOCAL_MIGRATE mode on weight vectors with zeros, ties, heavy particles and an all-zero shard."""
+    n, shards = 16384, 4
+    ns = n // shards
+    rng = np.random.default_rng(7)
+    zeros = np.zeros(n)
+    vectors = [rng.random(n) + 0.5, np.tile(np.r_[np.zeros(ns // 2), np.ones(ns // 2)], shards), rng.random(n) ** 8 + 1e-3,
+               np.r_[rng.random(3 * ns) + 0.5, np.zeros(ns)], np.ones(n)]
+    for thresholds in (dict(), dict(migrate_min_share=0.0, migrate_min_ess=0.0)):
+        for w in vectors:
+            cfg = dict(shard_mode=abi.SHARD_LOCAL_MIGRATE, virtual_shards=shards, **thresholds)
+            g = gpu(abi.default_config(**cfg)); o = oracle.OraclePoseEstimator(abi.default_config(**cfg), policy=oracle.SHARED)
+            for f in (g, o):
+                f.setParticles(x=np.arange(n, dtype=float), y=zeros, theta=zeros, zpos=zeros, zsigma=zeros + 1, weight=w)
+                f.normalizeWeights()
+                f.resample()
+            assert np.array_equal(g.getAncestors(), o.getAncestors())
+            assert np.array_equal(g.getCdf(), o.getCdf())
+            assert_particles_equal(g.getParticles(), o.getParticles(), keys=("x", "weight"))

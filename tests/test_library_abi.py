@@ -48,7 +48,7 @@ def test_struct_sizes_match_the_header():
     assert ctypes.sizeof(abi.Contact) == 40
     assert ctypes.sizeof(abi.Step) == 72
     assert ctypes.sizeof(abi.UpdateResult) == 56
-    assert ctypes.sizeof(abi.Config) == 120
+    assert ctypes.sizeof(abi.Config) == 144
 
 
 def test_no_cpu_fallback(lib_path):
