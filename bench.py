@@ -57,7 +57,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -177,13 +177,16 @@ def cpu_baseline(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=400)      # ~0.2 s timed: enough nvidia-smi clock samples inside the timed region
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--cpu-particles", type=int, default=131072,
                     help="particles per step of the bounded CPU sample (the oracle does ~1.4e7 particle-updates/s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-mode", default="exact", choices=["exact", "local"],
+                    help="N > 1: exact = exact-global resampling (ancestors identical to one GPU / the reference; the default and "
+                         "the parity mode); local = LOCAL_MIGRATE (per-shard resampling, exact-global migration step when a shard collapses)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -204,7 +207,8 @@ def main():
     comm = dist.init(world, rank, local_rank) if world > 1 else None
     n_global = n_local * world
     patch = 16 if args.workload == "C4" else 0                       # C4: EmbodiedSlamFilter per-particle map patches
-    cfg = abi.default_config(min_effective=n_global + 1, patch_size=patch)   # resample every step (ESS <= N always)
+    shard_mode = abi.SHARD_LOCAL_MIGRATE if args.shard_mode == "local" else abi.SHARD_EXACT_GLOBAL
+    cfg = abi.default_config(min_effective=n_global + 1, patch_size=patch, shard_mode=shard_mode)   # resample every step (ESS <= N always)
     g = GpuPoseEstimator(cfg, device=local_rank, shard=comm.shard(n_local) if comm else None)
     if comm:
         comm.connect(g)
@@ -254,7 +258,9 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "particles_per_gpu": n_local, "particles": n_global, "contact_points": c,
                    "grid": "%dx%d float2, replicated" % (w["grid"], w["grid"]), "resample": "stratified, every step", "patch_size": patch,
-                   "sharding": "contiguous particle ranges, exact-global resampling (ancestors identical to 1 GPU)" if world > 1 else "none",
+                   "sharding": ("none" if world == 1 else
+                                "contiguous particle ranges, exact-global resampling (ancestors identical to 1 GPU)" if args.shard_mode == "exact" else
+                                "contiguous particle ranges, LOCAL_MIGRATE: per-shard resampling, exact-global migration step when a shard collapses"),
                    "timing": "inputs larger than L2: particle state 2 x %.0f MB + scan buffers stream from HBM every "
                              "step; the %.0f MB map is L2-resident by design" % (n_local * 58 / 1e6, w["grid"] ** 2 * 8 / 1e6),
                    "step_algorithmic_bytes": step_bytes,
