@@ -67,6 +67,7 @@ struct eslam_gpu_ctx {
     uint32_t project_step;
     std::vector<cudaEvent_t> events;
     bool peer_exchange;                           // small per-step exchanges over peer memory instead of NCCL (ESLAM_GPU_PEER_EXCHANGE=1)
+    bool stream_resample;                         // one GPU: k_resample_stream instead of k_resample_local (default; ESLAM_GPU_STREAM_RESAMPLE=0: off)
     bool use_pdl;                                 // programmatic dependent launch between the kernels of a step (ESLAM_GPU_NO_PDL=1: off)
     bool timing; std::vector<std::pair<int, cudaEvent_t> > marks; size_t marks_used;
 };
@@ -228,10 +229,10 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
         ctx->ipc_opened.clear(); ctx->has_peers = false;
         free_particles(ctx);
         for (int b = 0; b < 2; ++b) {
-            for (int f = 0; f < 7; ++f) CK(dalloc(&ctx->st.f[b][f], n));
-            for (int f = 0; f < 2; ++f) CK(dalloc(&ctx->st.b[b][f], n));
+            for (int f = 0; f < 7; ++f) CK(dalloc(&ctx->st.f[b][f], n + 32));    // + 32: bulk copies of the last tile round their
+            for (int f = 0; f < 2; ++f) CK(dalloc(&ctx->st.b[b][f], n + 32));    //   size up to 16 bytes (k_resample_stream)
         }
-        CK(dalloc(&ctx->ancestors, n)); CK(dalloc(&ctx->cdf, n));
+        CK(dalloc(&ctx->ancestors, n)); CK(dalloc(&ctx->cdf, n + 32));
         CK(dalloc(&ctx->keys, n)); CK(dalloc(&ctx->bin_list, n));
         if (ctx->cfg.patch_size > 0) {
             const size_t pp = (size_t)ctx->cfg.patch_size * ctx->cfg.patch_size;
@@ -467,6 +468,8 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     CK(dalloc(&ctx->htab, (size_t)ESLAM_H_TABLE_ENTRIES));
     CK(cudaMemcpyAsync(ctx->htab, H_TABLE_HOST, sizeof(H_TABLE_HOST), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainSmem)));
+    CK(cudaFuncSetAttribute(k_resample_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_STREAM_SMEM));
+    ctx->stream_resample = getenv("ESLAM_GPU_STREAM_RESAMPLE") == nullptr || atoi(getenv("ESLAM_GPU_STREAM_RESAMPLE")) != 0;   // default on
     CK(cudaStreamSynchronize(ctx->stream));
     return ESLAM_OK;
 }
@@ -898,6 +901,13 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     CK(launch_pdl(ctx, k_cdf_sequential, 1, 1, 0, ctx->st, ctx->sc, n, ctx->cdf, ctx->tile_sin));
     LAUNCHED();
     const ModelParams mp = model_params(ctx);
+    if (ctx->cfg.patch_size <= 0 && ctx->stream_resample && !sp.mode) {
+        // persistent CTAs, source tiles streamed through a bulk-copy ring (see k_resample_stream)
+        CK(launch_pdl(ctx, k_resample_stream, (unsigned)ctx->sm_count, 1024, (size_t)RS_STREAM_SMEM, ctx->st, ctx->sc, ctx->cdf, ctx->tile_sin, T, n, mp.k0, mp.k1,
+                                                              ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC, ctx->ancestors, ctx->ticket));
+        LAUNCHED();
+        return ESLAM_OK;
+    }
     if (ctx->cfg.patch_size <= 0 && !getenv("ESLAM_GPU_NO_LOCAL_RESAMPLE")) {
         // search in shared memory, copy and buffer swap in one kernel
         CK(launch_pdl(ctx, k_resample_local<RS_CTA>, (unsigned)((n + RS_CTA - 1) / RS_CTA), RS_CTA, 0, ctx->st, ctx->sc, ctx->tile_sin, T, T, n, n, 0ull, mp.k0, mp.k1,

@@ -1953,6 +1953,122 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
     }
 }
 
+// Resampling as a stream (one GPU, no patches, one walk over all particles): a persistent CTA owns a run of consecutive strata
+// [K0, K1).  Strata and their ancestors advance together (the walk is monotone, src/ParticleFilter.hpp:96-105), so the CTA
+// pulls the SOURCE tiles that hold its ancestors -- exact running sum + the 58 bytes of state of 1024 particles, 66 KB -- one
+// after the other through a two-stage ring of bulk copies (cp.async.bulk + mbarrier: the copy of tile i+1 runs while tile i is
+// searched), and every source tile is read once per CTA that needs it.  For tile t the candidate strata are
+// floor(n S_t) - 2 .. floor(n S_t+1) + 2 (S_t = exact sum before the tile); a stratum belongs to the tile iff
+//   (t == 0 or S_t < sum_r) and (t last or !(cdf[last of t] < sum_r))      <=>  lower_bound(cdf, sum_r) lies in tile t
+// so every stratum is served by exactly one tile; tiles without candidates are never loaded.  Outputs leave coalesced.
+#define RS_STAGE_BYTES (8 * TILE * 8 + 2 * TILE)          // cdf + 7 doubles + 2 bytes per particle of one source tile
+#define RS_STREAM_SMEM (2 * RS_STAGE_BYTES + 64)
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(mbar) : "memory");
+}
+
+__global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevScalars* sc, const double* __restrict__ cdf,
+                                                             const double* __restrict__ tile_start, unsigned n_tiles,
+                                                             unsigned long long n, uint32_t k0key, uint32_t k1key, int systematic,
+                                                             uint32_t* ancestors, unsigned* ticket) {
+    pdl_start();
+    extern __shared__ __align__(128) unsigned char rs_raw[];
+    if (!sc->do_resample) return;
+    const unsigned tid = threadIdx.x;
+    const int cur = sc->cur, nxt = cur ^ 1;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(rs_raw);
+    const uint32_t mbar0 = smem0 + 2 * RS_STAGE_BYTES;                        // two mbarriers behind the stages
+    const unsigned long long per = (((n + gridDim.x - 1) / gridDim.x) + 31ull) & ~31ull;
+    const unsigned long long K0 = min(n, (unsigned long long)blockIdx.x * per), K1 = min(n, K0 + per);
+    if (K0 < K1) {
+        const double dn = (double)n;
+        // source tiles of this CTA: from the last tile starting below K0/n to the last one starting below K1/n (two counts)
+        const double thr_lo = (double)K0 / dn, thr_hi = (double)K1 / dn;
+        unsigned c_lo = 0, c_hi = 0;
+        for (unsigned t0 = 0; t0 < n_tiles; t0 += 1024) {
+            const double ts = (t0 + tid < n_tiles) ? __ldg(&tile_start[t0 + tid]) : 1.7e308;
+            c_lo += (unsigned)__syncthreads_count(ts < thr_lo);
+            c_hi += (unsigned)__syncthreads_count(ts < thr_hi);
+        }
+        const unsigned tA = c_lo == 0 ? 0u : c_lo - 1, tB = c_hi == 0 ? 0u : c_hi - 1;
+        if (tid == 0) { mbar_init(mbar0, 1); mbar_init(mbar0 + 8, 1); }
+        __syncthreads();
+        // candidate strata of tile t inside [K0, K1) (uniform over the CTA)
+        auto range = [&](unsigned t, unsigned long long& klo, unsigned long long& khi) {
+            klo = K0; khi = K1;
+            if (t > 0) {
+                const double f = floor(__ldg(&tile_start[t]) * dn) - 2.0;
+                if (f > (double)K0) klo = f >= (double)K1 ? K1 : (unsigned long long)f;
+            }
+            if (t + 1 < n_tiles) {
+                const double c = floor(__ldg(&tile_start[t + 1]) * dn) + 3.0;
+                if (c < (double)K1) khi = c <= (double)K0 ? K0 : (unsigned long long)c;
+            }
+            if (klo > khi) klo = khi;
+        };
+        auto issue = [&](unsigned t, int stage) {                              // one thread: 10 bulk copies onto one mbarrier
+            const unsigned long long e0 = (unsigned long long)t * TILE;
+            const unsigned cnt = (unsigned)min((unsigned long long)TILE, n - e0);
+            const uint32_t c8 = ((cnt + 1u) & ~1u) * 8u, c1 = (cnt + 15u) & ~15u;   // multiples of 16 bytes (buffers are padded)
+            const uint32_t S = smem0 + (uint32_t)stage * RS_STAGE_BYTES, mb = mbar0 + 8u * (uint32_t)stage;
+            mbar_expect_tx(mb, 8u * c8 + 2u * c1);
+            bulk_g2s(S, cdf + e0, c8, mb);
+#pragma unroll
+            for (int f = 0; f < 7; ++f) bulk_g2s(S + (uint32_t)(1 + f) * TILE * 8u, st.f[cur][f] + e0, c8, mb);
+#pragma unroll
+            for (int f = 0; f < 2; ++f) bulk_g2s(S + 8u * TILE * 8u + (uint32_t)f * TILE, st.b[cur][f] + e0, c1, mb);
+        };
+        unsigned t = tA; unsigned long long klo = 0, khi = 0;
+        while (t <= tB) { range(t, klo, khi); if (khi > klo) break; ++t; }
+        if (t <= tB && tid == 0) issue(t, 0);
+        int it = 0;
+        while (t <= tB) {
+            unsigned tn = t + 1; unsigned long long nlo = 0, nhi = 0;
+            while (tn <= tB) { range(tn, nlo, nhi); if (nhi > nlo) break; ++tn; }
+            const int stage = it & 1;
+            if (tn <= tB && tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the other stage was read (generic proxy) one iteration ago
+                issue(tn, stage ^ 1);
+            }
+            mbar_wait(mbar0 + 8u * (uint32_t)stage, (uint32_t)(it >> 1) & 1u);
+            {
+                const unsigned char* S = rs_raw + (size_t)stage * RS_STAGE_BYTES;
+                const double* s_cdf = reinterpret_cast<const double*>(S);
+                const unsigned long long e0 = (unsigned long long)t * TILE;
+                const unsigned cnt = (unsigned)min((unsigned long long)TILE, n - e0);
+                const double start = __ldg(&tile_start[t]), last = s_cdf[cnt - 1];
+                const bool first_tile = t == 0, last_tile = t + 1 == n_tiles;
+                for (unsigned long long k = klo + tid; k < khi; k += 1024) {
+                    const unsigned long long gk = systematic ? 0ull : k;
+                    const em::Philox4 r = em::philox4x32_10((uint32_t)gk, sc->resample_step, 0, stream_word(em::STREAM_RESAMPLE, gk), k0key, k1key);
+                    const double u = em::u01(r.v[0], r.v[1]);
+                    const double sum_r = ((double)k + u) / dn;                                   // :98
+                    if ((first_tile || start < sum_r) && (last_tile || !(last < sum_r))) {       // the ancestor lies in this tile
+                        unsigned lo = 0, hi = cnt;                                               // first element with !(cdf < sum_r)
+                        while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (s_cdf[mid] < sum_r) lo = mid + 1; else hi = mid; }
+                        if (lo >= cnt) lo = cnt - 1;      // the reference walks off the end here; we stop at the last particle
+                        ancestors[k] = (uint32_t)(e0 + lo);
+#pragma unroll
+                        for (int f = 0; f < 7; ++f) st.f[nxt][f][k] = reinterpret_cast<const double*>(S + (size_t)(1 + f) * TILE * 8)[lo];   // :104 (Q3)
+#pragma unroll
+                        for (int f = 0; f < 2; ++f) st.b[nxt][f][k] = (S + (size_t)8 * TILE * 8 + (size_t)f * TILE)[lo];
+                    }
+                }
+            }
+            __syncthreads();                                                   // everyone is done with this stage
+            t = tn; klo = nlo; khi = nhi; ++it;
+        }
+    }
+    // xi_k.swap(xi_kp) :107 by the last CTA (every CTA has read sc->cur by then)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0; sc->cur ^= 1; sc->resample_step += 1; }
+    }
+}
+
 // cloneMaps (src/PoseEstimator.cpp:31-45): every copy of a particle owns a copy of its map patch. One warp per particle.
 __global__ void k_gather_patches(const DevScalars* sc, unsigned long long n, const uint32_t* __restrict__ anc, int P,
                                  float2* p0, float2* p1, int* o0, int* o1) {
