@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the ncu --set full capture under
 # profiles/ (workload, lean path) -> bytes
-NCU_DRAM_BYTES_PER_LAUNCH = {("C3", True): 61.7e6}
+NCU_DRAM_BYTES_PER_LAUNCH = {("C3", True): 62.5e6}     # profiles/r01/k_weight_lean_final_ncu_raw.txt: 56.1 MB read + 6.3 MB written
 
 KIND_TEXT = {"reference": "the reference's own PoseEstimator / ContactModel sources compiled against stand-in dependency headers "
                           "(dense-grid map, Philox noise)",

@@ -1610,7 +1610,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(ChainPack pk, unsigned n_tile
     ChainSmem& cs = *reinterpret_cast<ChainSmem*>(chain_raw);
     __shared__ int sh_i[64];             // [0,32): warp totals, [32,64): their inclusive scan
     __shared__ SegE sh_e[64];
-    __shared__ int s_total, s_bad, s_go;
+    __shared__ int s_bad, s_go;
     const unsigned tid = threadIdx.x;
     if (decide) {
         double eff;
