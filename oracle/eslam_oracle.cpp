@@ -623,7 +623,7 @@ struct eslam_oracle_ctx {
     //     include/eslam_gpu.h ESLAM_SHARD_LOCAL_MIGRATE).  The oracle holds all N particles; the G logical shards are the
     //     contiguous ranges [g n_s, (g+1) n_s).
     int logical_shards() const {
-        if (cfg.shard_mode != ESLAM_SHARD_LOCAL_MIGRATE) return 1;
+        if (cfg.shard_mode != ESLAM_SHARD_LOCAL_MIGRATE || cfg.patch_size > 0) return 1;   // patches: exact-global only
         const int G = shard.world > 1 ? shard.world : cfg.virtual_shards;
         return (G > 1 && xi_k.size() % ((size_t)G * 1024) == 0) ? G : 1;    // shards are whole 1024-particle tiles
     }

@@ -287,7 +287,7 @@ static inline unsigned tile_ofs(const eslam_gpu_ctx* ctx) { return sharded(ctx) 
 // unsharded context (the same logic on one GPU; identical results).  Inert (mode 0) with one shard or in EXACT_GLOBAL mode.
 static ShardPlan shard_plan(const eslam_gpu_ctx* ctx) {
     ShardPlan sp; memset(&sp, 0, sizeof(sp));
-    if (ctx->cfg.shard_mode != ESLAM_SHARD_LOCAL_MIGRATE || ctx->cfg.resample_mode != ESLAM_RESAMPLE_STRATIFIED) return sp;
+    if (ctx->cfg.shard_mode != ESLAM_SHARD_LOCAL_MIGRATE || ctx->cfg.resample_mode != ESLAM_RESAMPLE_STRATIFIED || ctx->cfg.patch_size > 0) return sp;
     unsigned G = 1, first = 0, count = 1;
     if (sharded(ctx)) { G = (unsigned)ctx->shard.world; first = (unsigned)ctx->shard.rank; }
     else if (ctx->cfg.virtual_shards > 1 && ctx->cfg.virtual_shards <= ESLAM_MAX_SHARDS && ctx->n % ((uint64_t)ctx->cfg.virtual_shards * TILE) == 0) {
@@ -866,6 +866,10 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     LAUNCHED();
     XCH(1, ctx->l_tile_sum, ctx->x_sum, T * sizeof(double2));
     const ShardPlan sp = shard_plan(ctx);
+    if (sp.mode && sharded(ctx) && !ctx->has_peers) {
+        ctx->error = "LOCAL_MIGRATE sharding needs peer access between the GPUs (the migration step reads ancestors in place)";
+        return ESLAM_ERR_INVALID;
+    }
     CK(launch_pdl(ctx, k_reduce_b, 1, 1024, 0, ctx->g_tile_sum, TG, ng, ctx->sc, ctx->scratch_a, ctx->scratch_b, ctx->tile_prefix, normalise, sp,
                   XFLAGS(1), XEPOCH(1), XWORLD()));
     LAUNCHED();
