@@ -195,3 +195,68 @@ def test_the_references_own_unit_test_runs_against_its_own_code():
     # two groups give two fused contacts < minContacts (3): evaluatePose returns false, BOOST_REQUIRE stops the case
     assert cases["test_updatePose_group"] == (1, 1)
     assert cases["test_mapAbsence_group"] == (1, 1)
+
+
+@live
+@pytest.mark.parametrize("seed", range(12))
+def test_live_reference_fuzz_configurations(oracle, seed):
+    """Random configurations, contact sets (grouped / ungrouped / unknown and sub-threshold contact probabilities, up to 64
+    points), odometry streams, maps with many empty cells and a translated map frame (C_global2local): the compiled reference
+    and the LITERAL oracle stay bit-identical through every step, ancestors included."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.choice([64, 250, 1000]))
+    cfg = dict(seed=int(rng.integers(1, 2**31)), min_effective=int(rng.choice([n // 4, n // 2, n + 1])),
+               measurement_error=float(rng.choice([0.05, 0.1, 0.3])), discount_factor=float(rng.choice([0.8, 0.9, 1.0])),
+               spread_threshold=float(rng.choice([0.0, 0.9, 1.5])), slip_factor=float(rng.choice([0.0, 0.05, 0.6])),
+               max_yaw_deviation=float(rng.choice([0.0, 0.05, 0.26])), min_contacts=int(rng.choice([1, 2, 3, 4])),
+               contact_likelihood_correction=float(rng.choice([0.33, 1.0])), contact_point_radius=float(rng.choice([0.0, 0.01, 0.05])),
+               use_shape_update=int(rng.choice([0, 1])))
+    # map: 120 x 90 cells of 0.05-0.1 m, 15 % empty, offset so that part of the cloud hangs over the border
+    w, h = 120, 90
+    sx, sy = float(rng.choice([0.05, 0.1])), float(rng.choice([0.05, 0.08]))
+    cells = np.empty((h, w, 2), dtype=np.float32)
+    cells[..., 0] = (0.1 * rng.standard_normal((h, w))).astype(np.float32)
+    cells[..., 1] = (0.01 + 0.05 * rng.random((h, w))).astype(np.float32)
+    cells[..., 0][rng.random((h, w)) < 0.15] = np.nan
+    offset = (-w * sx / 2 + 0.3, -h * sy / 2 - 0.2)
+    g2l = None
+    if seed % 2:
+        g2l = np.array([[1, 0, 0, rng.uniform(-0.5, 0.5)], [0, 1, 0, rng.uniform(-0.5, 0.5)], [0, 0, 1, 0.0]])
+    # contacts: 4..64 points; grouped runs, some ungrouped, unknown (NaN) and sub-threshold probabilities
+    c = int(rng.choice([4, 8, 20, 64]))
+    pos = np.c_[rng.uniform(-0.4, 0.4, c), rng.uniform(-0.4, 0.4, c), rng.uniform(-0.2, 0.05, c)]
+    prob = rng.choice([0.5, 0.1, np.nan, 1.0, 0.2], size=c, p=[0.6, 0.1, 0.1, 0.1, 0.1])
+    if seed % 3 == 0:
+        gid = np.full(c, -1)
+    else:
+        gid = np.sort(rng.integers(0, 4, c))                # contiguous groups 0..3 (Q2: at most four fused contacts)
+    contacts = abi.make_contacts(pos, prob, gid)
+    r, o = _pair(oracle, **cfg)
+    for f in (r, o):
+        f.setEnvironment(cells, (sx, sy), offset, g2l=g2l)
+        f.init(n, (0.1, -0.2, 0.3), (0.8, 0.6, 0.2), 0.15, 0.5)
+    assert_particles_equal(r.getParticles(), o.getParticles(), keys=("x", "y", "theta", "zpos", "zsigma", "weight"))
+    touched = 0
+    for i in range(12):
+        step = abi.make_step(yaw=0.3 + 0.01 * i, z_delta=float(rng.normal(0, 0.002)), z_var=float(rng.choice([0.0, 2e-6, 1e-4])),
+                             delta_mean=(0.03, float(rng.normal(0, 0.005)), 0.01), delta_sigma=(0.005, 0.004, 0.002))
+        r.project(step); o.project(step)
+        ra, rb = r.update(contacts), o.update(contacts)
+        assert ra.resampled == rb.resampled, (i, cfg)
+        assert_particles_equal(r.getParticles(), o.getParticles())
+        touched += int(rb.data_particles)
+        if rb.resampled:
+            assert np.array_equal(r.getAncestors(), o.getAncestors()), (i, cfg)
+        else:
+            assert ra.ess == rb.ess and (ra.data_particles, ra.total_points) == (rb.data_particles, rb.total_points)
+    FUZZ_TOUCHED.append(touched)
+
+
+FUZZ_TOUCHED = []
+
+
+@live
+def test_live_reference_fuzz_was_not_vacuous():
+    """Most fuzz configurations must have had particles in contact with the map (a run where every particle floats compares
+    nothing of the contact model)."""
+    assert len(FUZZ_TOUCHED) == 12 and sum(1 for t in FUZZ_TOUCHED if t > 0) >= 8, FUZZ_TOUCHED
