@@ -177,7 +177,9 @@ def cpu_baseline(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)      # ~0.2 s timed: enough nvidia-smi clock samples inside the timed region
+    ap.add_argument("--steps", type=int, default=None,
+                    help="timed steps; default 400 (~0.2 s on the GPU: enough nvidia-smi clock samples inside the timed region), "
+                         "20 for --impl reference (a CPU step of the full workload takes ~0.2-0.5 s)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C3")
@@ -193,6 +195,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.warmup < 3:
         args.warmup = 3
+    if args.steps is None:
+        args.steps = 20 if args.impl == "reference" else 400
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
