@@ -6,6 +6,7 @@
 #ifndef ESLAM_REF_SHIM_BOOST_LCG
 #define ESLAM_REF_SHIM_BOOST_LCG
 #include <stdint.h>
+#include <cassert>            // boost/assert.hpp is part of what the real header pulls in
 namespace boost {
 struct minstd_rand {
     uint32_t x;

@@ -260,3 +260,20 @@ def test_live_reference_fuzz_was_not_vacuous():
     """Most fuzz configurations must have had particles in contact with the map (a run where every particle floats compares
     nothing of the contact model)."""
     assert len(FUZZ_TOUCHED) == 12 and sum(1 for t in FUZZ_TOUCHED if t > 0) >= 8, FUZZ_TOUCHED
+
+
+@pytest.mark.skipif(not ref_binding.have_sources(), reason="needs /root/reference")
+def test_the_references_particle_filter_unit_test_walks_off_the_end():
+    """test/UnitTest.cpp (ParticleFilter<State> on a toy tracker) resamples unnormalised weights; resample_stratified has no
+    bounds guard (src/ParticleFilter.hpp:99-103), so with weights summing below a stratum's draw it reads past the end of
+    xi_k.  Built with AddressSanitizer the reference's own test stops exactly there -- the behaviour SURVEY.md §8 (a14) flags,
+    and the reason the oracle and the kernels clamp the ancestor to the last particle instead of reproducing the read."""
+    out = os.path.join(os.path.dirname(ref_binding.LIB_PATH), "unit_test_asan")
+    r = subprocess.run(["make", "-s", "-C", os.path.join(os.path.dirname(ref_binding.LIB_PATH), "..", "ref"),
+                        "REF=" + ref_binding.REFERENCE, "../_ref/unit_test_asan"], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("AddressSanitizer build not available: " + r.stderr[-200:])
+    p = subprocess.run([out], capture_output=True, text=True, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+    assert p.returncode != 0
+    assert "heap-buffer-overflow" in p.stderr
+    assert re.search(r"resample_stratified.*ParticleFilter\.hpp:10[0-3]", p.stderr)
