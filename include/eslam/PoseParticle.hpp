@@ -3,6 +3,7 @@
 #ifndef ESLAM_FACADE_POSEPARTICLE_HPP
 #define ESLAM_FACADE_POSEPARTICLE_HPP
 #include <limits>
+#include <vector>
 #include "compat.hpp"
 
 namespace eslam {
@@ -33,6 +34,23 @@ struct PoseParticle {                                   // src/PoseParticle.hpp:
 };
 
 typedef PoseParticle PoseParticleGA;                    // src/PoseEstimator.hpp:108-117: the per-particle GridAccess lives on the device
+
+// The logging / transport snapshot of the filter (src/PoseParticle.hpp:88-114): what the task around the library writes
+// out every logParticlePeriod steps.  particles = getParticles() (the host mirror of the device state).
+struct PoseDistribution {
+    struct BaseAdapter {
+        enum { Dimension = 2 };
+        typedef double Scalar;
+        typedef base::Vector2d Vector;
+        typedef base::Matrix2d Matrix;
+    };
+    typedef envire::GaussianMixture<double, 2, BaseAdapter> GMM;
+    base::Time time;
+    std::vector<PoseParticle> particles;
+    GMM gmm;
+    base::Quaterniond orientation;
+    odometry::BodyContactState bodyState;
+};
 
 }  // namespace eslam
 #endif

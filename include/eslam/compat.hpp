@@ -127,7 +127,28 @@ struct Pose {
 
 template <class T> inline T unknown() { return std::numeric_limits<T>::quiet_NaN(); }
 
+struct Time {                           // base/Time.hpp: microseconds since the epoch
+    long long microseconds;
+    Time() : microseconds(0) {}
+    static Time fromMicroseconds(long long us) { Time t; t.microseconds = us; return t; }
+    bool isNull() const { return microseconds == 0; }
+};
+
+struct Matrix2d { double m[2][2]; Matrix2d() { m[0][0] = m[0][1] = m[1][0] = m[1][1] = 0; } };
+
 }  // namespace base
+
+namespace envire {
+// envire/tools/GaussianMixture.hpp as PoseDistribution names it (src/PoseParticle.hpp:88-114): a list of weighted Gaussians.
+// The reference never fills it inside this library (the Rock task that logs the distribution does).
+template <class S, int D, class Adapter> struct GaussianMixture {
+    struct Parameter {
+        S weight; typename Adapter::Vector mean; typename Adapter::Matrix cov;
+        Parameter() : weight(0) {}
+    };
+    std::vector<Parameter> params;
+};
+}  // namespace envire
 
 namespace odometry {
 

@@ -10,6 +10,16 @@ using namespace eslam;
 using namespace odometry;
 
 static int failures = 0;
+
+// compile-time check of the snapshot type (src/PoseParticle.hpp:88-114): filled the way the reference's task fills it
+static inline PoseDistribution snapshot(EmbodiedSlamFilter& f, const base::Quaterniond& q, const BodyContactState& bs) {
+    PoseDistribution pd;
+    pd.time = base::Time::fromMicroseconds(1);
+    pd.particles.assign(f.getParticles().begin(), f.getParticles().end());
+    pd.orientation = q; pd.bodyState = bs;
+    return pd;
+}
+
 #define CHECK(cond) do { if (!(cond)) { std::printf("CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #cond); failures++; } } while (0)
 #define CHECK_SMALL(v, tol) CHECK(std::fabs(v) < (tol))
 #define CHECK_CLOSE(a, b, pct) CHECK(std::fabs((a) - (b)) <= (pct) / 100.0 * std::fabs(b))
