@@ -90,3 +90,40 @@ def test_points_on_cell_borders_are_untrusted_or_exact():
         else:
             declined += 1
     assert declined > 3900                                    # on a border the kernel hands the decision to the IEEE division
+
+
+def test_trusted_lean_gate_decisions_are_the_exact_gate(oracle):
+    """The 3-sigma patch gate of MLSGrid::get, d^2 < 9 zvar, as the lean kernel takes it: on the HIGH WORD of |t|,
+    t = d * (rsqrt(zvar) / corr), against 3 / corr; a decision within one high-word step of the threshold is not trusted
+    (fill_fast_params: gate_lo = hi(3/corr) - 1, gate_span = 2).  Trusted decisions must equal the gate as written."""
+    RSQRT = 6
+    corr = 0.33
+    inv_corr = 1.0 / corr
+    T = 3.0 * inv_corr
+
+    def hi(x):
+        return struct.unpack("<Q", struct.pack("<d", x))[0] >> 32
+    gate_lo, gate_span = hi(T) - 1, 2
+    rng = np.random.default_rng(13)
+    untrusted = flips_if_trusted_blindly = 0
+    n = 40000
+    for i in range(n):
+        zvar = float(10.0 ** rng.uniform(-4, 1))
+        if i % 2:
+            d = 3.0 * math.sqrt(zvar) * (1.0 + rng.choice([-1.0, 1.0]) * 10.0 ** rng.uniform(-16, -3))   # around the threshold
+        else:
+            d = float(rng.normal(0.0, 4.0 * math.sqrt(zvar)))
+        if rng.random() < 0.5:
+            d = -d
+        qc = oracle.math_fn(RSQRT, zvar) * inv_corr
+        t = d * qc
+        dlt = ((hi(t) & 0x7FFFFFFF) - gate_lo) & 0xFFFFFFFF
+        inside = dlt >= 0x80000000
+        trusted = dlt > gate_span
+        exact = d * d < 9.0 * zvar
+        if not trusted:
+            untrusted += 1
+            flips_if_trusted_blindly += int(inside != exact)
+            continue
+        assert inside == exact, (d, zvar, t, dlt)
+    assert 0 < untrusted < n // 2          # only the draws placed within ~1e-6 of the threshold are declined
