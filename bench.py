@@ -20,9 +20,22 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the ncu --set full capture under
-# profiles/ (workload, lean path) -> bytes
-NCU_DRAM_BYTES_PER_LAUNCH = {("C3", True): 62.5e6}     # profiles/r01/k_weight_lean_final_ncu_raw.txt: 56.1 MB read + 6.3 MB written
+
+
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel: not measurable inside a timed run
+    (counters need ncu's replay), so it is read from the summary tools/ncu_traffic.py wrote from the committed
+    `ncu --set full` capture of this same command (profiles/<round>/traffic.json); null when there is none."""
+    for rnd in ("r02", "r01"):
+        p = os.path.join(ROOT, "profiles", rnd, "traffic.json")
+        if os.path.exists(p):
+            try:
+                t = json.load(open(p)).get("%s:%s" % (workload, kernel))
+                if t:
+                    return {"bytes": float(t["bytes"]), "source": "profiles/%s/%s" % (rnd, t.get("source", "traffic.json"))}
+            except Exception:
+                pass
+    return None
 
 KIND_TEXT = {"reference": "the reference's own PoseEstimator / ContactModel sources compiled against stand-in dependency headers "
                           "(dense-grid map, Philox noise)",
@@ -174,6 +187,50 @@ def cpu_baseline(args, w):
                       % (n, w["n"], w["c"], os.cpu_count(), KIND_TEXT[kind])}
 
 
+def multi_gpu_parity(args, comm, rank, world, local_rank, n_local, patch, shard_mode, g_timed):
+    """N > 1: the sharded filter against ONE GPU running the same global particle set (same seed, same steps), outside the
+    timed region: CRC-32 of every rank's ancestor indices and weights after 3 steps must equal the CRC of the matching slice
+    of the one-GPU run (rank 0 holds it; LOCAL_MIGRATE: one GPU with `world` logical shards).  Collective: every rank calls."""
+    import zlib
+    import numpy as np
+    import torch.distributed as td
+    from slam_eslam_b200 import GpuPoseEstimator, abi, synthetic
+    g_timed.close()
+    n_global = n_local * world
+    kw = dict(min_effective=n_global + 1, patch_size=patch, shard_mode=shard_mode)
+    g = GpuPoseEstimator(abi.default_config(**kw), device=local_rank, shard=comm.shard(n_local))
+    comm.connect(g)
+    contacts, step = synthetic.setup_filter(g, args.workload, n=n_local)
+    for _ in range(3):
+        r = g.stepFused(step, contacts)
+    p = g.getParticles()
+    mine = {"ancestors_crc": zlib.crc32(g.getAncestors().tobytes()), "weights_crc": zlib.crc32(p["weight"].tobytes()),
+            "poses_crc": zlib.crc32(p["x"].tobytes() + p["y"].tobytes() + p["theta"].tobytes()), "ess": r.ess}
+    g.close()
+    allr = [None] * world
+    td.all_gather_object(allr, mine)
+    if rank != 0:
+        return None
+    one = GpuPoseEstimator(abi.default_config(virtual_shards=world if shard_mode == abi.SHARD_LOCAL_MIGRATE else 0, **kw), device=local_rank)
+    synthetic.setup_filter(one, args.workload, n=n_global)
+    for _ in range(3):
+        r1 = one.stepFused(step, contacts)
+    q = one.getParticles()
+    anc = one.getAncestors()
+    one.close()
+    ok = True
+    for k in range(world):
+        sl = slice(k * n_local, (k + 1) * n_local)
+        ref = {"ancestors_crc": zlib.crc32(anc[sl].tobytes()), "weights_crc": zlib.crc32(q["weight"][sl].tobytes()),
+               "poses_crc": zlib.crc32(q["x"][sl].tobytes() + q["y"][sl].tobytes() + q["theta"][sl].tobytes()), "ess": r1.ess}
+        ok = ok and ref == allr[k]
+    return {"ancestors_crc": "%08x" % zlib.crc32(b"".join(("%08x" % a["ancestors_crc"]).encode() for a in allr)),
+            "weights_crc": "%08x" % zlib.crc32(b"".join(("%08x" % a["weights_crc"]).encode() for a in allr)),
+            "matches_1gpu": bool(ok), "steps": 3,
+            "what": "CRC-32 per rank of ancestor indices, weights and poses after 3 steps == the same slices of one GPU running "
+                    "all %d particles (bit-exact); ESS equal" % n_global}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -218,20 +275,25 @@ def main():
         comm.connect(g)
     contacts, step = synthetic.setup_filter(g, args.workload, n=n_local)
 
-    # warm-up, then K timed steps with inputs resident (events on the library's stream)
+    # warm-up, then K timed steps with inputs resident (events on the library's stream).  The clock sampler is started
+    # BEFORE the barrier (forking nvidia-smi takes ~20 ms on rank 0); run_steps itself begins with a device-side rendezvous
+    # of all ranks, so no rank's events include waiting for a rank whose host got there later.
     g.runSteps(step, contacts, args.warmup)
     launches0 = g.launchCount()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     if comm: comm.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ms, top_ms, res = g.runSteps(step, contacts, args.steps)
     torch.cuda.synchronize()
     if comm: comm.barrier()
     launches = g.launchCount() - launches0
+    periods = sorted(g.stepTimes())
+    median_ms = periods[len(periods) // 2] if periods else ms / args.steps
     paths = g.pathCounters()
     if comm:
         ms = comm.max_float(ms)
         top_ms = comm.max_float(top_ms)
+        median_ms = comm.max_float(median_ms)
 
     # end to end through the reference-facing call: host Step + contact array in, UpdateResult out, every step
     e2e_steps = max(3, min(args.steps, 20))
@@ -246,6 +308,8 @@ def main():
     if comm:
         e2e_s = comm.max_float(e2e_s)
     clocks = sampler.stop() if sampler else None
+    h2d, d2h = g.ioBytes(len(contacts))
+    parity = multi_gpu_parity(args, comm, rank, world, local_rank, n_local, patch, shard_mode, g) if comm else None
     if rank != 0:
         return
 
@@ -256,6 +320,8 @@ def main():
     peak, peak_kind = measured_peak()
     top_avg_s = top_ms * 1e-3 / args.steps
     achieved = top_bytes / top_avg_s / 1e9
+    top_kernel = "k_weight_lean" if lean else "k_project_weight"
+    traffic = ncu_traffic(args.workload, top_kernel)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -271,19 +337,25 @@ def main():
                    "step_hbm_frac": step_bytes / (ms * 1e-3 / args.steps) / 1e9 / peak,
                    "resampled_last_step": res.resampled, "ess_last_step": res.ess,
                    "lean_path_particles": paths["lean"], "generic_path_particles": paths["deferred"]},
-        "roofline": {"bound": "hbm", "kernel": "k_weight_lean" if lean else "k_project_weight", "achieved": achieved, "peak": peak,
+        "median_ms_per_step": median_ms,
+        "roofline": {"bound": "hbm", "kernel": top_kernel, "achieved": achieved, "peak": peak,
                      "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((args.workload, lean)),
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic["bytes"] if traffic else None,
+                     "traffic_source": traffic["source"] if traffic else None,
+                     "achieved_kind": "algorithmic bytes per launch / measured launch time (CUDA events in this run)",
+                     "limiter": "fp64 instruction issue" if lean else "fp64 instruction issue + L2 gathers",
                      "kernel_ms": top_avg_s * 1e3, "kernel_share_of_step": top_ms / ms,
                      "algorithmic_bytes_per_launch": top_bytes,
-                     "note": "bound by instruction issue (fp64 at half rate), not by HBM: the map is served from TMA-staged "
-                             "shared-memory tiles, so DRAM traffic is far below the algorithmic bytes; see DESIGN.md §5 and profiles/"},
+                     "note": "reported against the HBM roofline as the metric demands; the kernel itself is limited by instruction "
+                             "issue (fp64 at half rate), not by HBM: the map is served from TMA-staged shared-memory tiles, so "
+                             "DRAM traffic is far below the algorithmic bytes; see DESIGN.md §5 and profiles/"},
         "e2e": {"value": updates * e2e_steps / e2e_s, "unit": UNIT,
-                "h2d_bytes_per_step": ctypes.sizeof(abi.Step) + len(contacts) * ctypes.sizeof(abi.Contact),
-                "d2h_bytes_per_step": 184, "ms_per_step": 1e3 * e2e_s / e2e_steps},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / e2e_steps},
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    if parity is not None:
+        out["parity"] = parity
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, w)
     print(json.dumps(out))

@@ -26,7 +26,7 @@ enum {
     ESLAM_ERR_NO_ENVIRONMENT = 3,/* "No environment attached." src/PoseEstimator.cpp:259-260 */
     ESLAM_ERR_ZERO_VARIANCE = 4, /* zero measurement variance, src/ContactModel.cpp:122-123 */
     ESLAM_ERR_EMPTY = 5,         /* empty particle set, assert at src/ParticleFilter.hpp:91 */
-    ESLAM_ERR_COMM = 6           /* collective hook failed */
+    ESLAM_ERR_COMM = 6           /* communicator / peer-memory exchange failed (a rank did not arrive, no peer access) */
 };
 
 enum { ESLAM_RESAMPLE_STRATIFIED = 0,   /* reference: src/ParticleFilter.hpp:85-108 */
@@ -114,16 +114,16 @@ typedef struct eslam_gpu_ctx eslam_gpu_ctx;
 void eslam_gpu_default_config(eslam_gpu_config* cfg);                 /* src/Configuration.hpp:53-59,85-111 */
 int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_shard* shard_or_null,
                      eslam_gpu_ctx** out);                            /* PoseEstimator ctor, src/PoseEstimator.cpp:13-25 */
-/* Sharded filter (one context per GPU / rank; shards are equal multiples of 1024 particles): rank 0 creates a NCCL
- * unique id, the launcher broadcasts the 128 bytes, every rank joins.  The library resolves NCCL at run time
- * (dlopen of the libnccl.so.2 already in the process) and issues the exchange steps on its own stream:
- * all-gathers of per-tile partials / scan descriptors and contiguous-range send/recv for resampling. */
+/* Sharded filter (one context per GPU / rank of ONE box; shards are equal, 1024 * 2^k particles each): rank 0 creates a
+ * NCCL unique id, the launcher broadcasts the 128 bytes, every rank joins.  The library resolves NCCL at run time (dlopen of
+ * the libnccl.so.2 already in the process) and uses it for the bootstrap only -- the all-gather of the CUDA IPC handles that
+ * map every rank's buffers into every process, and the per-tile partials of getCentroid.  The per-step exchanges (loop-A
+ * partials, weight sums, ESS, the exact running sum's per-rank summary, "my running sums are final") are O(1) per rank and run
+ * INSIDE the step's kernels over NVLink peer memory: the last CTA of the producing kernel pushes the rank's summary into every
+ * rank's exchange buffer and releases an epoch flag, the consuming kernel's CTAs poll their own flags.  Resampling reads the
+ * ancestors (state, running sums, map patches) in place from the owning rank.  Peer access between the GPUs is required. */
 int eslam_gpu_nccl_unique_id(uint8_t out[128]);
 int eslam_gpu_comm_init(eslam_gpu_ctx* ctx, const uint8_t unique_id[128]);
-/* Host-only planning step of sharded resampling: element range [begin[r], end[r]) that holds every possible ancestor
- * of rank r's strata, from the exact running sum before each 1024-particle tile (n_tiles = world * n_local / 1024). */
-int eslam_gpu_plan_windows(const double* tile_start_sum, unsigned n_tiles, uint64_t n_local, int world,
-                           uint64_t* begin, uint64_t* end);
 void eslam_gpu_destroy(eslam_gpu_ctx* ctx);
 const char* eslam_gpu_last_error(const eslam_gpu_ctx* ctx);
 
@@ -158,6 +158,11 @@ int eslam_gpu_step_fused(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const e
  * the lean path does not apply). */
 int eslam_gpu_run_steps(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const eslam_gpu_contact* pts, int n_pts,
                         int steps, float* elapsed_ms, float* top_kernel_ms, eslam_gpu_update_result* last_result);
+/* Step periods of the last eslam_gpu_run_steps (steps - 1 values, CUDA events): copies min(count, cap) values, returns count. */
+int eslam_gpu_step_times(eslam_gpu_ctx* ctx, float* out_ms, int cap);
+/* Bytes one eslam_gpu_step_fused call moves between host and device: out = {host -> device (step + contact array, as kernel
+ * parameters), device -> host (the scalar block behind eslam_gpu_update_result)} (bench "e2e"). */
+int eslam_gpu_io_bytes(const eslam_gpu_ctx* ctx, int n_pts, uint64_t out[2]);
 
 /* ParticleFilter::getWeightsSum (src/ParticleFilter.hpp:34-39). */
 int eslam_gpu_weights_sum(eslam_gpu_ctx* ctx, double* sum);
@@ -185,9 +190,11 @@ int eslam_gpu_evaluate_poses(eslam_gpu_ctx* ctx, uint64_t n, const double* x, co
                              int32_t* n_contacts, double* zpos_out, double* z_var_out,
                              int32_t* cell_index, double* cp);
 
-/* EmbodiedSlamFilter per-particle map update (src/EmbodiedSlamFilter.cpp:179-232, narrowed by north_star to
- * writing the fused contact heights of the last update into particle-local PxP grid patches). */
-int eslam_gpu_patch_update(eslam_gpu_ctx* ctx);
+/* EmbodiedSlamFilter per-particle maps (useSharedMap == false, src/EmbodiedSlamFilter.cpp:131-134): with cfg.patch_size = P
+ * every particle owns a P x P overlay of the shared grid.  update() writes the fused contact heights of each particle into
+ * its patch (north_star's narrowing of processMap, src/EmbodiedSlamFilter.cpp:209-227), lookups consult the patch first,
+ * resampling copies it with the particle (cloneMaps, src/PoseEstimator.cpp:31-45).  Read-back: [n][P][P]{mean, stdev}
+ * cells and [n][2] grid coordinates of each patch's cell (0, 0) (INT32_MIN: not anchored yet). */
 int eslam_gpu_get_patches(eslam_gpu_ctx* ctx, float* cells_mean_stdev, int32_t* origin_xy);
 
 int eslam_gpu_synchronize(eslam_gpu_ctx* ctx);

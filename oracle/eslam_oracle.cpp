@@ -935,14 +935,6 @@ int eslam_oracle_lowest_points(const eslam_gpu_contact* pts, int n_pts, int upda
     return count;
 }
 
-// per-particle patch write (north_star's contact-height variant of EmbodiedSlamFilter::processMap,
-// src/EmbodiedSlamFilter.cpp:209-227): see DESIGN.md "particle-local patches" for the definition.
-int eslam_oracle_patch_update(eslam_oracle_ctx* ctx) {
-    // the write is part of update() (after each particle's evaluation, before resampling); nothing left to do here
-    if (!ctx || ctx->cfg.patch_size <= 0) return ESLAM_ERR_INVALID;
-    return ESLAM_OK;
-}
-
 int eslam_oracle_get_patches(eslam_oracle_ctx* ctx, float* cells, int32_t* origin_xy) {
     if (!ctx || ctx->cfg.patch_size <= 0) return ESLAM_ERR_INVALID;
     if (cells) std::copy(ctx->patches.begin(), ctx->patches.end(), cells);

@@ -59,7 +59,6 @@ int eslam_oracle_evaluate_poses(eslam_oracle_ctx* ctx, uint64_t n, const double*
                                 uint8_t* ok, double* weight, double* z_delta, double* z_var, double* pose_var,
                                 int32_t* n_contacts, double* zpos_out, double* z_var_out,
                                 int32_t* cell_index, double* cp);
-int eslam_oracle_patch_update(eslam_oracle_ctx* ctx);
 int eslam_oracle_get_patches(eslam_oracle_ctx* ctx, float* cells_mean_stdev, int32_t* origin_xy);
 
 /* FakeMLSAccess of test/testContactModel.cpp:8-38 as the map: 4 quadrants, index = 2*(y>0) + (x>0);

@@ -22,7 +22,7 @@ ERROR_TEXT = {
     ERR_NO_ENVIRONMENT: "No environment attached.",  # src/PoseEstimator.cpp:260
     ERR_ZERO_VARIANCE: "using a zero measurement variance leads to singularities",  # src/ContactModel.cpp:123
     ERR_EMPTY: "empty particle set",
-    ERR_COMM: "collective hook failed",
+    ERR_COMM: "communicator / peer-memory exchange failed",
 }
 
 
@@ -124,7 +124,6 @@ SIGNATURES = {
     "best_index": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "evaluate_poses": (C.c_int, [C.c_void_p, C.c_uint64] + [_dp] * 6 + [C.POINTER(Contact), C.c_int, _u8p]
                        + [_dp] * 4 + [_i32p, _dp, _dp, _i32p, _dp]),
-    "patch_update": (C.c_int, [C.c_void_p]),
     "get_patches": (C.c_int, [C.c_void_p, _fp, _i32p]),
 }
 
@@ -133,12 +132,13 @@ GPU_ONLY = {
     "create": (C.c_int, [C.POINTER(Config), C.c_int, C.POINTER(Shard), C.POINTER(C.c_void_p)]),
     "nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "comm_init": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8)]),
-    "plan_windows": (C.c_int, [_dp, C.c_uint, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "destroy": (None, [C.c_void_p]),
     "last_error": (C.c_char_p, [C.c_void_p]),
     "step_fused": (C.c_int, [C.c_void_p, C.POINTER(Step), C.POINTER(Contact), C.c_int, C.POINTER(UpdateResult)]),
     "run_steps": (C.c_int, [C.c_void_p, C.POINTER(Step), C.POINTER(Contact), C.c_int, C.c_int,
                             C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(UpdateResult)]),
+    "step_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
+    "io_bytes": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
     "synchronize": (C.c_int, [C.c_void_p]),
     "weights_sum": (C.c_int, [C.c_void_p, _dp]),
     "debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),

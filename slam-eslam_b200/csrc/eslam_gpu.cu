@@ -1,5 +1,5 @@
 // eslam_gpu.cu -- C ABI of libeslam_gpu.so (include/eslam_gpu.h): context, memory, launch sequencing and the
-// exchange steps of the sharded (multi-GPU) filter.  All arithmetic lives in eslam_kernels.cuh; there is no CPU
+// peer-memory bootstrap of the sharded (multi-GPU) filter (the step's exchanges run inside its kernels).  All arithmetic lives in eslam_kernels.cuh; there is no CPU
 // implementation of any step in this library.
 #include "eslam_kernels.cuh"
 #include "eslam_nccl.h"
@@ -20,9 +20,28 @@ static const em::dbl2 H_TABLE_HOST[ESLAM_H_TABLE_ENTRIES] = {
 
 static NcclApi g_nccl;
 
+// Development switches, read ONCE when a context is created (tools/README.md); never consulted on the step path.
+struct EnvSwitches {
+    bool no_fast, no_tma, no_local_resample, stream_resample, trace, timing, use_pdl, no_p2p;
+    int lean_threads, tile_override;
+    void read() {
+        no_fast = getenv("ESLAM_GPU_NO_FAST") != nullptr;
+        no_tma = getenv("ESLAM_GPU_NO_TMA") != nullptr;
+        no_local_resample = getenv("ESLAM_GPU_NO_LOCAL_RESAMPLE") != nullptr;
+        stream_resample = getenv("ESLAM_GPU_STREAM_RESAMPLE") == nullptr || atoi(getenv("ESLAM_GPU_STREAM_RESAMPLE")) != 0;   // default on
+        trace = getenv("ESLAM_GPU_TRACE") != nullptr;
+        timing = getenv("ESLAM_GPU_TIMING") != nullptr;
+        use_pdl = getenv("ESLAM_GPU_NO_PDL") == nullptr;
+        no_p2p = getenv("ESLAM_GPU_NO_P2P") != nullptr;
+        lean_threads = getenv("ESLAM_GPU_LEAN_THREADS") ? atoi(getenv("ESLAM_GPU_LEAN_THREADS")) : 1024;
+        tile_override = getenv("ESLAM_GPU_TILE") ? atoi(getenv("ESLAM_GPU_TILE")) : 0;
+    }
+};
+
 struct eslam_gpu_ctx {
     eslam_gpu_config cfg;
     eslam_gpu_shard shard;
+    EnvSwitches env;
     int device;
     cudaStream_t stream;
     std::string error;
@@ -37,28 +56,23 @@ struct eslam_gpu_ctx {
     cudaStream_t side; cudaEvent_t side_ev;
     uint32_t* ancestors; double* cdf;
     double* hint; unsigned hint_n;                // per-CTA sums of x, y (tile placement hint), entries written by the last update
-    unsigned* ticket;                             // "last CTA" counter of k_resample_local
+    unsigned* ticket;                             // "last CTA" counter of the resampling kernels
     bool last_lean;                               // the last update went through the lean path
-    int lean_threads;                             // CTA size of the lean kernel: 1024 x 64 registers or 512 x 128 (ESLAM_GPU_LEAN_THREADS)
+    FastParams* fast;                             // the lean kernels' parameter block of the current update (per context: contexts are independent)
     int* bin_count; uint2* keys; uint32_t* bin_list; unsigned* bin_offs; unsigned* bin_next; int* cta_bin;   // lean path: bins, per-bin lists, chunk counters
     bool grid_sane;                               // every stdev of the grid is NaN or |stdev| < 2^49 (lean path precondition)
     float2* patch[2]; int* porigin[2];            // per-particle map patches (cfg.patch_size > 0), double buffered
-    // per-tile arrays: l_* cover the local tiles, g_* all tiles of all ranks (aliases of l_* when world == 1)
+    // per-tile arrays of this rank's tiles
     unsigned t_local, t_global, t_cap;
-    TilePartA *l_part_a, *g_part_a; double2 *l_tile_sum, *g_tile_sum; double *l_tile_sq, *g_tile_sq;   // tile sums: {sum w, sum w^2}
+    TilePartA* l_part_a; double2* l_tile_sum; double* l_tile_sq; TileDesc* l_desc; BndEntry* l_pool;
+    double* prefix_raw; double2* shard_sums;
     double* shard_tot;                            // LOCAL_MIGRATE: exact total of every logical shard held here (k_chain -> k_resample_local)
-    TileDesc *l_desc; BndEntry *l_pool;           // l_tile_sq, l_desc, l_pool point into l_pack
-    unsigned char *l_pack, *g_pack; size_t pack_bytes;   // [sum w^2 per tile | tile descriptors | boundary pool] per rank: one all-gather
-    double *l_cent, *g_cent, *l_best_w, *g_best_w; unsigned long long *l_best_idx, *g_best_idx;
-    double *tile_prefix, *scratch_a, *scratch_b, *tile_sin, *sb; int* tile_bofs; SegF* tile_pre;
-    double* tile_sin_host;                        // pinned, t_global
-    // resampling window fetched from the owning ranks (world > 1)
-    uint64_t win_cap; double* win_cdf; double* win_f[7]; uint8_t* win_b[2];
-    // peer-mapped buffers of the other ranks (CUDA IPC over NVLink): resampling reads ancestors in place
-    // small per-step exchanges over peer memory (k_publish): all ranks' loop-A partials, tile sums and chain inputs live in
-    // one allocation (g_part_a, g_tile_sum, g_pack point into it) followed by the epoch flags; peer_x[q] = rank q's mapping
-    unsigned char* xchg; size_t x_part, x_sum, x_pack, x_flags, x_bytes; unsigned char* peer_x[ESLAM_MAX_RANKS]; unsigned x_epoch[4];
-    PeerTable peers; bool has_peers; std::vector<void*> ipc_opened; int* d_barrier_send; int* d_barrier_recv;
+    double *tile_prefix, *scratch_a, *scratch_b, *sb; int* tile_bofs; SegF* tile_pre;
+    double *l_cent, *g_cent, *l_best_w, *g_best_w; unsigned long long *l_best_idx, *g_best_idx;   // centroid / best particle (g_*: all ranks' tiles)
+    // exchange buffer of this rank (exchange slots, epoch flags, the global tile-start table) and every rank's mapping of it;
+    // peer-mapped running-sum and state buffers of the other ranks (CUDA IPC over NVLink): resampling reads ancestors in place
+    unsigned char* xchg; size_t x_bytes; Xchg X;
+    PeerTable peers; bool has_peers; std::vector<void*> ipc_opened;
     // map
     float2* cells; MapParams map; bool has_map;
     CUtensorMap tmap; CUtensorMap* d_tmap; bool has_tmap;   // TMA descriptor of the grid (host copy, device copy)
@@ -66,10 +80,9 @@ struct eslam_gpu_ctx {
     int max_smem_optin, sm_count;
     uint32_t project_step;
     std::vector<cudaEvent_t> events;
-    bool peer_exchange;                           // small per-step exchanges over peer memory instead of NCCL (ESLAM_GPU_PEER_EXCHANGE=1)
-    bool stream_resample;                         // one GPU: k_resample_stream instead of k_resample_local (default; ESLAM_GPU_STREAM_RESAMPLE=0: off)
-    bool use_pdl;                                 // programmatic dependent launch between the kernels of a step (ESLAM_GPU_NO_PDL=1: off)
     bool timing; std::vector<std::pair<int, cudaEvent_t> > marks; size_t marks_used;
+    std::vector<float> step_ms;                   // step periods of the last eslam_gpu_run_steps
+    bool use_pdl;
 };
 
 template <typename... KArgs, typename... Args>
@@ -153,51 +166,47 @@ static void free_particles(eslam_gpu_ctx* ctx) {
     }
     dfree(ctx->ancestors); dfree(ctx->cdf); dfree(ctx->keys); dfree(ctx->bin_list);
     for (int b = 0; b < 2; ++b) { dfree(ctx->patch[b]); dfree(ctx->porigin[b]); }
-    const bool sh = ctx->g_part_a != ctx->l_part_a;
-    if (sh) { dfree(ctx->xchg); ctx->g_part_a = nullptr; ctx->g_tile_sum = nullptr; ctx->g_pack = nullptr;
-              dfree(ctx->g_cent); dfree(ctx->g_best_w); dfree(ctx->g_best_idx); }
-    dfree(ctx->l_part_a); dfree(ctx->l_tile_sum); dfree(ctx->l_pack);
-    ctx->l_tile_sq = nullptr; ctx->l_desc = nullptr; ctx->l_pool = nullptr; ctx->g_pack = nullptr;
-    dfree(ctx->l_cent); dfree(ctx->l_best_w); dfree(ctx->l_best_idx);
-    ctx->g_part_a = nullptr; ctx->g_tile_sum = nullptr; ctx->g_tile_sq = nullptr;
+    if (ctx->g_cent != ctx->l_cent) { dfree(ctx->g_cent); dfree(ctx->g_best_w); dfree(ctx->g_best_idx); }
     ctx->g_cent = ctx->g_best_w = nullptr; ctx->g_best_idx = nullptr;
-    dfree(ctx->tile_prefix); dfree(ctx->scratch_a); dfree(ctx->scratch_b); dfree(ctx->tile_sin); dfree(ctx->sb);
+    dfree(ctx->l_part_a); dfree(ctx->l_tile_sum); dfree(ctx->l_tile_sq); dfree(ctx->l_desc); dfree(ctx->l_pool);
+    dfree(ctx->prefix_raw);
+    dfree(ctx->l_cent); dfree(ctx->l_best_w); dfree(ctx->l_best_idx);
+    dfree(ctx->tile_prefix); dfree(ctx->scratch_a); dfree(ctx->scratch_b); dfree(ctx->sb);
     dfree(ctx->tile_bofs); dfree(ctx->tile_pre);
-    if (ctx->tile_sin_host) { cudaFreeHost(ctx->tile_sin_host); ctx->tile_sin_host = nullptr; }
+    dfree(ctx->xchg); ctx->x_bytes = 0;
     ctx->cap = 0; ctx->t_cap = 0;
 }
 
-static void free_window(eslam_gpu_ctx* ctx) {
-    dfree(ctx->win_cdf);
-    for (int f = 0; f < 7; ++f) dfree(ctx->win_f[f]);
-    for (int f = 0; f < 2; ++f) dfree(ctx->win_b[f]);
-    ctx->win_cap = 0;
-}
-
-// Exchange CUDA IPC handles of the running-sum and state buffers and map every peer's buffers into this process.
 static int allgather(eslam_gpu_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank);
+
+// Exchange CUDA IPC handles of the running-sum, state, patch and exchange buffers and map every peer's buffers into this
+// process.  NCCL only carries this bootstrap (and the per-tile centroid partials of getCentroid); the step's own exchanges are
+// stores and flag polls on these mappings (eslam_kernels.cuh "peer exchange").
 static int setup_peers(eslam_gpu_ctx* ctx) {
     const int G = ctx->shard.world, me = ctx->shard.rank;
     if (G > ESLAM_MAX_RANKS) { ctx->error = "more ranks than ESLAM_MAX_RANKS"; return ESLAM_ERR_INVALID; }
     if (!ctx->has_comm) { ctx->error = "sharded context without a communicator (call eslam_gpu_comm_init before init)"; return ESLAM_ERR_COMM; }
-    const int NH = 20;                                                  // cdf + 2 x 7 doubles + 2 x 2 bytes + exchange buffer
-    void* mine[NH]; int k = 0;
-    mine[k++] = ctx->cdf;
-    for (int b = 0; b < 2; ++b) for (int f = 0; f < 7; ++f) mine[k++] = ctx->st.f[b][f];
-    for (int b = 0; b < 2; ++b) for (int f = 0; f < 2; ++f) mine[k++] = ctx->st.b[b][f];
-    mine[k++] = ctx->xchg;
+    if (ctx->env.no_p2p) { ctx->error = "sharded contexts need peer access between the GPUs (ESLAM_GPU_NO_P2P is set)"; return ESLAM_ERR_COMM; }
+    const bool patches = ctx->cfg.patch_size > 0;
+    const int NH = 20 + (patches ? 4 : 0);                              // cdf + 2 x 7 doubles + 2 x 2 bytes + exchange buffer (+ patches, origins)
+    std::vector<void*> mine;
+    mine.push_back(ctx->cdf);
+    for (int b = 0; b < 2; ++b) for (int f = 0; f < 7; ++f) mine.push_back(ctx->st.f[b][f]);
+    for (int b = 0; b < 2; ++b) for (int f = 0; f < 2; ++f) mine.push_back(ctx->st.b[b][f]);
+    mine.push_back(ctx->xchg);
+    if (patches) { for (int b = 0; b < 2; ++b) mine.push_back(ctx->patch[b]); for (int b = 0; b < 2; ++b) mine.push_back(ctx->porigin[b]); }
     std::vector<cudaIpcMemHandle_t> h_mine(NH), h_all((size_t)NH * G);
     for (int i = 0; i < NH; ++i) CK(cudaIpcGetMemHandle(&h_mine[i], mine[i]));
     cudaIpcMemHandle_t *d_send = nullptr, *d_recv = nullptr;
     CK(dalloc(&d_send, (size_t)NH)); CK(dalloc(&d_recv, (size_t)NH * G));
     CK(cudaMemcpyAsync(d_send, h_mine.data(), NH * sizeof(cudaIpcMemHandle_t), cudaMemcpyHostToDevice, ctx->stream));
     int st = allgather(ctx, d_send, d_recv, NH * sizeof(cudaIpcMemHandle_t));
-    if (st != ESLAM_OK) return st;
-    CK(cudaMemcpyAsync(h_all.data(), d_recv, (size_t)NH * G * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (st == ESLAM_OK && cudaMemcpyAsync(h_all.data(), d_recv, (size_t)NH * G * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) st = ESLAM_ERR_CUDA;
+    if (st == ESLAM_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = ESLAM_ERR_CUDA;
     cudaFree(d_send); cudaFree(d_recv);
+    if (st != ESLAM_OK) { if (ctx->error.empty()) ctx->error = "exchange of the IPC handles failed"; return st; }
     for (int q = 0; q < G; ++q) {
-        void* p[NH];
+        std::vector<void*> p(NH);
         for (int i = 0; i < NH; ++i) {
             if (q == me) p[i] = mine[i];
             else { CK(cudaIpcOpenMemHandle(&p[i], h_all[(size_t)q * NH + i], cudaIpcMemLazyEnablePeerAccess)); ctx->ipc_opened.push_back(p[i]); }
@@ -206,12 +215,17 @@ static int setup_peers(eslam_gpu_ctx* ctx) {
         ctx->peers.cdf[q] = (const double*)p[j++];
         for (int b = 0; b < 2; ++b) for (int f = 0; f < 7; ++f) ctx->peers.f[q][b][f] = (const double*)p[j++];
         for (int b = 0; b < 2; ++b) for (int f = 0; f < 2; ++f) ctx->peers.b[q][b][f] = (const uint8_t*)p[j++];
-        ctx->peer_x[q] = (unsigned char*)p[j++];
+        ctx->X.buf[q] = (unsigned char*)p[j++];
+        if (patches) { for (int b = 0; b < 2; ++b) ctx->peers.patch[q][b] = (const float2*)p[j++]; for (int b = 0; b < 2; ++b) ctx->peers.porigin[q][b] = (const int*)p[j++]; }
     }
     // nobody may publish into a buffer that its owner has not cleared yet: the handle exchange above is after the memset on
-    // every rank's stream, and one more collective here orders "all mapped" before the first step
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (!ctx->d_barrier_send) { CK(dalloc(&ctx->d_barrier_send, 1)); CK(dalloc(&ctx->d_barrier_recv, (size_t)ESLAM_MAX_RANKS)); }
+    // every rank's stream; one more collective orders "everyone has mapped everything" before the first step
+    int* d_one = nullptr; int* d_all = nullptr;
+    CK(dalloc(&d_one, 1)); CK(dalloc(&d_all, (size_t)G));
+    st = allgather(ctx, d_one, d_all, sizeof(int));
+    if (st == ESLAM_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = ESLAM_ERR_CUDA;
+    cudaFree(d_one); cudaFree(d_all);
+    if (st != ESLAM_OK) return st;
     ctx->has_peers = true;
     return ESLAM_OK;
 }
@@ -220,9 +234,13 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
     if (n == 0) return ESLAM_ERR_EMPTY;
     if (n > 0xFFFFFFFFull) { ctx->error = "more than 2^32 particles per shard"; return ESLAM_ERR_INVALID; }
     const int G = sharded(ctx) ? ctx->shard.world : 1;
-    if (G > 1 && ctx->cfg.patch_size > 0) { ctx->error = "per-particle map patches are not supported on sharded contexts yet"; return ESLAM_ERR_INVALID; }
-    if (G > 1 && (n % TILE != 0 || ctx->shard.global_count != n * (uint64_t)G)) {
-        ctx->error = "sharded contexts need equal shards that are multiples of 1024 particles"; return ESLAM_ERR_INVALID;
+    if (G > 1) {
+        // equal shards of 1024 * 2^k particles: the pairwise summation tree over all tiles then factors into per-rank subtrees,
+        // which is what lets every rank reduce its own tiles and exchange O(1) values (results identical to one GPU)
+        const uint64_t t = n / TILE;
+        if (n % TILE != 0 || (t & (t - 1)) != 0 || ctx->shard.global_count != n * (uint64_t)G) {
+            ctx->error = "sharded contexts need equal shards of 1024 * 2^k particles"; return ESLAM_ERR_INVALID;
+        }
     }
     if (n > ctx->cap) {
         for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);   // peer mappings of the old buffers are stale
@@ -233,56 +251,50 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
             for (int f = 0; f < 2; ++f) CK(dalloc(&ctx->st.b[b][f], n + 32));    //   size up to 16 bytes (k_resample_stream)
         }
         CK(dalloc(&ctx->ancestors, n)); CK(dalloc(&ctx->cdf, n + 32));
+        CK(cudaMemsetAsync(ctx->ancestors, 0, n * sizeof(uint32_t), ctx->stream));
         CK(dalloc(&ctx->keys, n)); CK(dalloc(&ctx->bin_list, n));
         if (ctx->cfg.patch_size > 0) {
             const size_t pp = (size_t)ctx->cfg.patch_size * ctx->cfg.patch_size;
             for (int b = 0; b < 2; ++b) { CK(dalloc(&ctx->patch[b], n * pp)); CK(dalloc(&ctx->porigin[b], 2 * n)); }
         }
         const size_t t = (size_t)((n + TILE - 1) / TILE), tg = t * G;
-        CK(dalloc(&ctx->l_part_a, t)); CK(dalloc(&ctx->l_tile_sum, t));
-        ctx->pack_bytes = t * (sizeof(double) + sizeof(TileDesc)) + (size_t)MAX_BND_TOTAL * sizeof(BndEntry);
-        CK(dalloc(&ctx->l_pack, ctx->pack_bytes));
-        ctx->l_tile_sq = reinterpret_cast<double*>(ctx->l_pack);
-        ctx->l_desc = reinterpret_cast<TileDesc*>(ctx->l_pack + t * sizeof(double));
-        ctx->l_pool = reinterpret_cast<BndEntry*>(ctx->l_pack + t * (sizeof(double) + sizeof(TileDesc)));
+        CK(dalloc(&ctx->l_part_a, t)); CK(dalloc(&ctx->l_tile_sum, t)); CK(dalloc(&ctx->l_tile_sq, t));
+        CK(dalloc(&ctx->l_desc, t)); CK(dalloc(&ctx->l_pool, (size_t)MAX_BND_TOTAL)); CK(dalloc(&ctx->prefix_raw, t));
         CK(dalloc(&ctx->l_cent, 5 * t)); CK(dalloc(&ctx->l_best_w, t)); CK(dalloc(&ctx->l_best_idx, t));
-        if (G > 1) {
-            auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-            ctx->x_part = 0; ctx->x_sum = up(tg * sizeof(TilePartA)); ctx->x_pack = ctx->x_sum + up(tg * sizeof(double2));
-            ctx->x_flags = ctx->x_pack + up(ctx->pack_bytes * G); ctx->x_bytes = ctx->x_flags + 4 * ESLAM_MAX_RANKS * sizeof(unsigned);
-            CK(dalloc(&ctx->xchg, ctx->x_bytes));
-            CK(cudaMemsetAsync(ctx->xchg, 0, ctx->x_bytes, ctx->stream));
-            ctx->g_part_a = reinterpret_cast<TilePartA*>(ctx->xchg + ctx->x_part);
-            ctx->g_tile_sum = reinterpret_cast<double2*>(ctx->xchg + ctx->x_sum);
-            ctx->g_pack = ctx->xchg + ctx->x_pack;
-            memset(ctx->x_epoch, 0, sizeof(ctx->x_epoch));
-            CK(dalloc(&ctx->g_cent, 5 * tg)); CK(dalloc(&ctx->g_best_w, tg)); CK(dalloc(&ctx->g_best_idx, tg));
-        } else {
-            ctx->g_part_a = ctx->l_part_a; ctx->g_tile_sum = ctx->l_tile_sum; ctx->g_pack = ctx->l_pack;
-            ctx->g_cent = ctx->l_cent;
-            ctx->g_best_w = ctx->l_best_w; ctx->g_best_idx = ctx->l_best_idx;
-        }
+        if (G > 1) { CK(dalloc(&ctx->g_cent, 5 * tg)); CK(dalloc(&ctx->g_best_w, tg)); CK(dalloc(&ctx->g_best_idx, tg)); }
+        else { ctx->g_cent = ctx->l_cent; ctx->g_best_w = ctx->l_best_w; ctx->g_best_idx = ctx->l_best_idx; }
         CK(dalloc(&ctx->tile_prefix, tg)); CK(dalloc(&ctx->scratch_a, tg)); CK(dalloc(&ctx->scratch_b, tg));
-        CK(dalloc(&ctx->tile_sin, tg)); CK(dalloc(&ctx->sb, (size_t)MAX_BND_TOTAL));
-        CK(dalloc(&ctx->tile_bofs, tg)); CK(dalloc(&ctx->tile_pre, tg));
-        CK(cudaMallocHost((void**)&ctx->tile_sin_host, tg * sizeof(double)));
+        CK(dalloc(&ctx->sb, (size_t)MAX_BND_TOTAL));
+        CK(dalloc(&ctx->tile_bofs, t)); CK(dalloc(&ctx->tile_pre, t));
+        // exchange buffer: slots + flags (fixed offsets), then the tile-start table of all ranks
+        ctx->x_bytes = (size_t)XOFF_TSIN + tg * sizeof(double);
+        CK(dalloc(&ctx->xchg, ctx->x_bytes));
+        CK(cudaMemsetAsync(ctx->xchg, 0, ctx->x_bytes, ctx->stream));
+        // exchange epochs restart with the buffer (flags are zero again on every rank: they all reallocate together)
+        CK(cudaMemsetAsync(ctx->sc->x_epoch, 0, sizeof(ctx->sc->x_epoch), ctx->stream));
         ctx->cap = n; ctx->t_cap = (unsigned)t;
     }
     ctx->n = n; ctx->t_local = (unsigned)((n + TILE - 1) / TILE); ctx->t_global = ctx->t_local * G;
-    if (G == 1) {                                                       // one GPU: the "peer" table maps this context's own buffers
+    ctx->X.world = G; ctx->X.me = sharded(ctx) ? ctx->shard.rank : 0; ctx->X.tiles_per_rank = ctx->t_cap;
+    if (G == 1) {                                                       // one GPU: the "peer" tables map this context's own buffers
+        ctx->X.buf[0] = ctx->xchg;
         ctx->peers.cdf[0] = ctx->cdf;
         for (int b = 0; b < 2; ++b) {
             for (int f = 0; f < 7; ++f) ctx->peers.f[0][b][f] = ctx->st.f[b][f];
             for (int f = 0; f < 2; ++f) ctx->peers.b[0][b][f] = ctx->st.b[b][f];
+            ctx->peers.patch[0][b] = ctx->patch[b]; ctx->peers.porigin[0][b] = ctx->porigin[b];
         }
+        return ESLAM_OK;
     }
-    if (G > 1 && !ctx->has_peers && !getenv("ESLAM_GPU_NO_P2P")) return setup_peers(ctx);
+    if (ctx->t_local != ctx->t_cap) { ctx->error = "a sharded context cannot shrink its shard (the tile-start table is laid out by capacity)"; return ESLAM_ERR_INVALID; }
+    if (!ctx->has_peers) { const int st = setup_peers(ctx); if (st != ESLAM_OK) return st; }
     return ESLAM_OK;
 }
 
 static inline uint64_t global_count(const eslam_gpu_ctx* ctx) { return sharded(ctx) ? ctx->shard.global_count : ctx->n; }
 static inline uint64_t base_index(const eslam_gpu_ctx* ctx) { return sharded(ctx) ? (uint64_t)ctx->shard.rank * ctx->n : 0; }
 static inline unsigned tile_ofs(const eslam_gpu_ctx* ctx) { return sharded(ctx) ? (unsigned)ctx->shard.rank * ctx->t_local : 0; }
+static inline double* tile_sin_table(const eslam_gpu_ctx* ctx) { return reinterpret_cast<double*>(ctx->xchg + XOFF_TSIN); }
 // LOCAL_MIGRATE sharding: the logical shards are the ranks of a sharded filter, or cfg.virtual_shards equal parts of an
 // unsharded context (the same logic on one GPU; identical results).  Inert (mode 0) with one shard or in EXACT_GLOBAL mode.
 static ShardPlan shard_plan(const eslam_gpu_ctx* ctx) {
@@ -306,7 +318,8 @@ static inline double scan_eps(const eslam_gpu_ctx* ctx) {
     return e > ldexp(1.0, -40) ? e : ldexp(1.0, -40);
 }
 
-// all-gather of equal-sized per-rank blocks (device pointers, stream ordered); identity on one GPU
+// all-gather of equal-sized per-rank blocks (device pointers, stream ordered); identity on one GPU.  Off the step path:
+// bootstrap of the peer mappings and the per-tile partials of getCentroid / getBestParticleIndex.
 static int allgather(eslam_gpu_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank) {
     if (!sharded(ctx)) return ESLAM_OK;
     if (!ctx->has_comm) { ctx->error = "sharded context without a communicator (call eslam_gpu_comm_init)"; return ESLAM_ERR_COMM; }
@@ -314,34 +327,6 @@ static int allgather(eslam_gpu_ctx* ctx, const void* send, void* recv, size_t by
     return ESLAM_OK;
 }
 #define AG(send, recv, bytes) do { int s__ = allgather(ctx, send, recv, bytes); if (s__ != ESLAM_OK) return s__; } while (0)
-
-// One of the four small per-step exchanges (0: loop-A tile partials, 1: raw tile sums, 2: chain inputs, 3: barrier in front
-// of the peer-memory resampling).  With peer access: k_publish pushes this rank's block into every peer's buffer and bumps
-// the exchange's epoch flag there; the consumer kernel waits on its own flags (XFLAGS / XEPOCH below).  Otherwise an NCCL
-// all-gather.  Measured (C3 per GPU): 0.563 ms/step against 0.541 with NCCL at 2 GPUs, 0.695 against 0.697 at 8 -- the extra
-// launch per exchange costs what the collective's latency costs, so NCCL is the default and ESLAM_GPU_PEER_EXCHANGE=1 opts in.
-static int exchange(eslam_gpu_ctx* ctx, int idx, const void* src, size_t region_off, size_t bytes) {
-    if (!sharded(ctx)) return ESLAM_OK;
-    if (!ctx->has_peers || !ctx->peer_exchange) {
-        if (idx == 3) return allgather(ctx, ctx->d_barrier_send, ctx->d_barrier_recv, sizeof(int));
-        return allgather(ctx, src, ctx->xchg + region_off, bytes);
-    }
-    const int G = ctx->shard.world, me = ctx->shard.rank;
-    PublishArgs A; memset(&A, 0, sizeof(A));
-    ctx->x_epoch[idx] += 1;
-    for (int q = 0; q < G; ++q) {
-        A.dst[q] = ctx->peer_x[q] + region_off + (size_t)me * bytes;
-        A.flag[q] = reinterpret_cast<unsigned*>(ctx->peer_x[q] + ctx->x_flags) + idx * ESLAM_MAX_RANKS + me;
-    }
-    A.src = src; A.bytes = bytes; A.epoch = ctx->x_epoch[idx]; A.world = G;
-    CK(launch_pdl(ctx, k_publish, G, 256, 0, A));
-    LAUNCHED();
-    return ESLAM_OK;
-}
-#define XCH(idx, src, off, bytes) do { int s__ = exchange(ctx, idx, src, off, bytes); if (s__ != ESLAM_OK) return s__; } while (0)
-#define XFLAGS(idx) ((sharded(ctx) && ctx->has_peers && ctx->peer_exchange) ? reinterpret_cast<const unsigned*>(ctx->xchg + ctx->x_flags) + (idx) * ESLAM_MAX_RANKS : (const unsigned*)nullptr)
-#define XEPOCH(idx) (ctx->x_epoch[idx])
-#define XWORLD() (sharded(ctx) ? ctx->shard.world : 1)
 
 static ModelParams model_params(const eslam_gpu_ctx* ctx) {
     const eslam_gpu_config& c = ctx->cfg;
@@ -413,39 +398,7 @@ void eslam_gpu_default_config(eslam_gpu_config* c) {
     c->shard_mode = ESLAM_SHARD_EXACT_GLOBAL; c->migrate_min_share = 0.25; c->migrate_min_ess = 0.05; c->virtual_shards = 0;
 }
 
-int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_shard* shard, eslam_gpu_ctx** out) {
-    if (!cfg || !out) return ESLAM_ERR_INVALID;
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ESLAM_ERR_CUDA;
-    eslam_gpu_ctx* ctx = new eslam_gpu_ctx();
-    memset(&ctx->st, 0, sizeof(ctx->st));
-    ctx->cfg = *cfg;
-    ctx->shard.rank = 0; ctx->shard.world = 1; ctx->shard.global_count = 0;
-    if (shard) ctx->shard = *shard;
-    ctx->comm = nullptr; ctx->has_comm = false;
-    ctx->device = device; ctx->launches = 0; ctx->n = ctx->cap = 0; ctx->t_local = ctx->t_global = ctx->t_cap = 0;
-    ctx->ancestors = nullptr; ctx->cdf = nullptr; ctx->hint = nullptr; ctx->hint_n = 0;
-    ctx->grid_sane = false;
-    ctx->last_lean = false; ctx->ticket = nullptr;
-    ctx->timing = getenv("ESLAM_GPU_TIMING") != nullptr; ctx->marks_used = 0;
-    ctx->use_pdl = getenv("ESLAM_GPU_NO_PDL") == nullptr;
-    ctx->peer_exchange = getenv("ESLAM_GPU_PEER_EXCHANGE") != nullptr;
-    ctx->lean_threads = getenv("ESLAM_GPU_LEAN_THREADS") ? atoi(getenv("ESLAM_GPU_LEAN_THREADS")) : 1024;
-    ctx->bin_count = nullptr; ctx->keys = nullptr; ctx->bin_list = nullptr; ctx->bin_offs = nullptr; ctx->bin_next = nullptr; ctx->cta_bin = nullptr;
-    for (int b = 0; b < 2; ++b) { ctx->patch[b] = nullptr; ctx->porigin[b] = nullptr; }
-    ctx->l_part_a = ctx->g_part_a = nullptr; ctx->l_tile_sum = ctx->g_tile_sum = nullptr; ctx->l_tile_sq = ctx->g_tile_sq = nullptr; ctx->shard_tot = nullptr;
-    ctx->l_desc = nullptr; ctx->l_pool = nullptr; ctx->l_pack = ctx->g_pack = nullptr; ctx->pack_bytes = 0;
-    ctx->l_cent = ctx->g_cent = ctx->l_best_w = ctx->g_best_w = nullptr; ctx->l_best_idx = ctx->g_best_idx = nullptr;
-    ctx->tile_prefix = ctx->scratch_a = ctx->scratch_b = ctx->tile_sin = ctx->sb = nullptr;
-    ctx->tile_bofs = nullptr; ctx->tile_pre = nullptr; ctx->tile_sin_host = nullptr;
-    ctx->xchg = nullptr; memset(ctx->x_epoch, 0, sizeof(ctx->x_epoch)); memset(ctx->peer_x, 0, sizeof(ctx->peer_x));
-    ctx->win_cap = 0; ctx->win_cdf = nullptr; ctx->has_peers = false; ctx->d_barrier_send = ctx->d_barrier_recv = nullptr;
-    memset(&ctx->peers, 0, sizeof(ctx->peers));
-    for (int f = 0; f < 7; ++f) ctx->win_f[f] = nullptr;
-    for (int f = 0; f < 2; ++f) ctx->win_b[f] = nullptr;
-    ctx->cells = nullptr; ctx->has_map = false; ctx->has_tmap = false; ctx->d_tmap = nullptr; ctx->project_step = 0;
-    memset(&ctx->map, 0, sizeof(ctx->map));
-    *out = ctx;
+static int create_impl(eslam_gpu_ctx* ctx, int device) {
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
@@ -459,6 +412,7 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     CK(cudaEventCreateWithFlags(&ctx->side_ev, cudaEventDisableTiming));
     CK(dalloc(&ctx->ticket, 1)); CK(cudaMemsetAsync(ctx->ticket, 0, sizeof(unsigned), ctx->stream));
     CK(dalloc(&ctx->shard_tot, (size_t)ESLAM_MAX_SHARDS)); CK(cudaMemsetAsync(ctx->shard_tot, 0, ESLAM_MAX_SHARDS * sizeof(double), ctx->stream));
+    CK(dalloc(&ctx->shard_sums, (size_t)ESLAM_MAX_SHARDS)); CK(cudaMemsetAsync(ctx->shard_sums, 0, ESLAM_MAX_SHARDS * sizeof(double2), ctx->stream));
     CK(dalloc(&ctx->bin_count, (size_t)MAX_BINS)); CK(dalloc(&ctx->bin_offs, (size_t)MAX_BINS)); CK(dalloc(&ctx->bin_next, (size_t)MAX_BINS));
     CK(dalloc(&ctx->cta_bin, (size_t)ctx->sm_count));
     CK(cudaMemsetAsync(ctx->bin_count, 0, MAX_BINS * sizeof(int), ctx->stream));
@@ -469,23 +423,47 @@ int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_sh
     CK(cudaMemcpyAsync(ctx->htab, H_TABLE_HOST, sizeof(H_TABLE_HOST), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainSmem)));
     CK(cudaFuncSetAttribute(k_resample_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_STREAM_SMEM));
-    ctx->stream_resample = getenv("ESLAM_GPU_STREAM_RESAMPLE") == nullptr || atoi(getenv("ESLAM_GPU_STREAM_RESAMPLE")) != 0;   // default on
     CK(cudaStreamSynchronize(ctx->stream));
+    return ESLAM_OK;
+}
+
+int eslam_gpu_create(const eslam_gpu_config* cfg, int device, const eslam_gpu_shard* shard, eslam_gpu_ctx** out) {
+    if (!cfg || !out) return ESLAM_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ESLAM_ERR_CUDA;
+    eslam_gpu_ctx* ctx = new eslam_gpu_ctx();                          // value-initialised: every pointer null, every count zero
+    ctx->cfg = *cfg;
+    ctx->shard.rank = 0; ctx->shard.world = 1; ctx->shard.global_count = 0;
+    if (shard) ctx->shard = *shard;
+    ctx->device = device;
+    ctx->env.read();
+    ctx->timing = ctx->env.timing; ctx->use_pdl = ctx->env.use_pdl;
+    ctx->fast = new FastParams();
+    const int st = create_impl(ctx, device);
+    if (st != ESLAM_OK) { eslam_gpu_destroy(ctx); return st; }         // no half-built context leaves this function
+    *out = ctx;
     return ESLAM_OK;
 }
 
 void eslam_gpu_destroy(eslam_gpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->has_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);
-    free_particles(ctx); free_window(ctx);
-    cudaFree(ctx->d_barrier_send); cudaFree(ctx->d_barrier_recv);
-    cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); cudaEventDestroy(ctx->side_ev); cudaFreeHost(ctx->sc_async);
-    cudaFree(ctx->sc); cudaFreeHost(ctx->sc_host); cudaFree(ctx->d_tmap); cudaFree(ctx->htab); cudaFree(ctx->cells); cudaFree(ctx->hint); cudaFree(ctx->ticket); cudaFree(ctx->bin_count); cudaFree(ctx->bin_offs); cudaFree(ctx->bin_next); cudaFree(ctx->cta_bin);
+    free_particles(ctx);
+    if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+    if (ctx->side_ev) cudaEventDestroy(ctx->side_ev);
+    if (ctx->sc_async) cudaFreeHost(ctx->sc_async);
+    if (ctx->sc_host) cudaFreeHost(ctx->sc_host);
+    cudaFree(ctx->sc); cudaFree(ctx->d_tmap); cudaFree(ctx->htab); cudaFree(ctx->cells); cudaFree(ctx->hint); cudaFree(ctx->ticket);
+    cudaFree(ctx->bin_count); cudaFree(ctx->bin_offs); cudaFree(ctx->bin_next); cudaFree(ctx->cta_bin);
+    cudaFree(ctx->shard_tot); cudaFree(ctx->shard_sums);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
-    cudaStreamDestroy(ctx->stream);
+    for (auto& m : ctx->marks) cudaEventDestroy(m.second);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx->fast;
     delete ctx;
 }
 
@@ -543,10 +521,10 @@ int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int he
     // shared-memory map tile: as many cells as fit next to the h-table
     const size_t avail = (size_t)ctx->max_smem_optin - WT_HEAD_BYTES;
     int side = (int)floor(sqrt((double)(avail / sizeof(float2))));
-    if (getenv("ESLAM_GPU_TILE")) side = atoi(getenv("ESLAM_GPU_TILE"));
+    if (ctx->env.tile_override > 0) side = ctx->env.tile_override;
     m.tile_w = width < side ? width : side;
     m.tile_h = (int)((avail / sizeof(float2)) / (size_t)m.tile_w);
-    if (getenv("ESLAM_GPU_TILE")) m.tile_h = atoi(getenv("ESLAM_GPU_TILE"));
+    if (ctx->env.tile_override > 0) m.tile_h = ctx->env.tile_override;
     if (m.tile_h > height) m.tile_h = height;
     if (m.tile_w > 256) m.tile_w = 256;                           // TMA box limit per dimension
     if (m.tile_h > 256) m.tile_h = 256;
@@ -568,7 +546,7 @@ int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int he
                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             ctx->has_tmap = (r == CUDA_SUCCESS);
-            if (getenv("ESLAM_GPU_TRACE")) {
+            if (ctx->env.trace) {
                 const unsigned long long* q = reinterpret_cast<const unsigned long long*>(&ctx->tmap);
                 fprintf(stderr, "[eslam] tensor map encode=%d cells=%p W=%d H=%d box=%dx%d:", (int)r, (void*)ctx->cells, width, height, m.tile_w, m.tile_h);
                 for (int i = 0; i < 16; ++i) fprintf(stderr, " %016llx", q[i]);
@@ -678,7 +656,7 @@ static void fill_weight_params(eslam_gpu_ctx* ctx, WeightParams* P, const eslam_
     P->st = ctx->st; P->sc = ctx->sc; P->map = ctx->map; P->mp = model_params(ctx);
     P->htab = ctx->htab; P->n = ctx->n; P->base = base_index(ctx); P->project_step = ctx->project_step;
     P->patch_size = ctx->cfg.patch_size > 0 ? ctx->cfg.patch_size : 0;
-    P->use_tma = ctx->has_tmap && !getenv("ESLAM_GPU_NO_TMA");
+    P->use_tma = ctx->has_tmap && !ctx->env.no_tma;
     P->tmap = ctx->d_tmap;
     P->hint = ctx->hint;
     for (int b = 0; b < 2; ++b) { P->patch[b] = ctx->patch[b]; P->porigin[b] = ctx->porigin[b]; }
@@ -695,7 +673,7 @@ static inline uint32_t hi_word(double v) { uint64_t u; memcpy(&u, &v, 8); return
 // The lean kernel's inputs (k_weight_fast).  Returns false when the lean path does not apply to this context / update:
 // per-particle patches, a non-identity C_global2local, no shared-memory tile, a grid with out-of-range deviations.
 static bool fill_fast_params(eslam_gpu_ctx* ctx, FastParams* F, const WeightParams& P, const ContactSet& cs) {
-    if (getenv("ESLAM_GPU_NO_FAST")) return false;
+    if (ctx->env.no_fast) return false;
     if (ctx->cfg.patch_size > 0 || !ctx->map.identity || !ctx->grid_sane || P.map.tile_w <= 0 || P.map.tile_h <= 0) return false;
     if (ctx->n >= 0x80000000ull) return false;                            // bit 31 of a list entry flags the particle
     memset(F, 0, sizeof(*F));
@@ -746,112 +724,6 @@ static unsigned weight_grid(const eslam_gpu_ctx* ctx) {
     return ctx->t_local < (unsigned)ctx->sm_count ? ctx->t_local : (unsigned)ctx->sm_count;
 }
 
-// Pure host logic (no device needed): which contiguous element range [begin, end) holds every possible ancestor of the
-// strata owned by each rank, given the exact running sum before each 1024-particle tile.  Stratum k draws
-// sum_r = (k + u)/N with u in [0,1), so rank r's draws lie in [r n/N, (r+1) n/N); the ancestor of sum_r is the first
-// element whose running sum is >= sum_r, which lies in the last tile whose starting sum is still below sum_r.
-extern "C" int eslam_gpu_plan_windows(const double* tile_start_sum, unsigned n_tiles, uint64_t n_local, int world,
-                                      uint64_t* begin, uint64_t* end) {
-    if (!tile_start_sum || !begin || !end || world <= 0 || n_tiles == 0) return ESLAM_ERR_INVALID;
-    const uint64_t N = n_local * (uint64_t)world;
-    auto last_tile_below = [&](double thr) -> unsigned {                // max t with S[t] < thr (0 if none)
-        unsigned lo = 0, hi = n_tiles;                                  // first t with !(S[t] < thr)
-        while (lo < hi) { unsigned mid = (lo + hi) / 2; if (tile_start_sum[mid] < thr) lo = mid + 1; else hi = mid; }
-        return lo == 0 ? 0 : lo - 1;
-    };
-    for (int r = 0; r < world; ++r) {
-        const double lo_thr = (double)((uint64_t)r * n_local) / (double)N;
-        const double hi_thr = (double)((uint64_t)(r + 1) * n_local) / (double)N;
-        const unsigned tlo = last_tile_below(lo_thr), thi = last_tile_below(hi_thr);
-        begin[r] = (uint64_t)tlo * TILE;
-        end[r] = std::min<uint64_t>(((uint64_t)thi + 1) * TILE, N);
-    }
-    return ESLAM_OK;
-}
-
-// Sharded resampling, exact-global mode: every rank knows the exact running sum at every tile start (k_chain ran on
-// the all-gathered descriptors), so every rank can tell which contiguous element range holds the ancestors of each
-// rank's strata; the owners send exactly those ranges (running sum + particle state), then search and gather run on
-// the received window.  Ancestor indices are global and identical to the one-GPU run.
-static int resample_exchange(eslam_gpu_ctx* ctx) {
-    const bool trace = getenv("ESLAM_GPU_TRACE") != nullptr;
-    auto t0 = std::chrono::steady_clock::now();
-    auto lap = [&](const char* what) {
-        if (!trace) return;
-        auto t1 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[eslam rank %d] %s: %.1f us\n", ctx->shard.rank, what, std::chrono::duration<double, std::micro>(t1 - t0).count());
-        t0 = t1;
-    };
-    int st = read_scalars(ctx);                                         // host needs: resample? which buffer? fallback?
-    lap("wait for the step so far + scalars");
-    if (st != ESLAM_OK) return st;
-    if (!ctx->sc_host->do_resample) return ESLAM_OK;
-    if (ctx->sc_host->error_flags & ERR_CDF_FALLBACK_BIT) {
-        ctx->error = "exact running sum needs the sequential fallback, which is not available across shards";
-        return ESLAM_ERR_COMM;
-    }
-    const int G = ctx->shard.world, me = ctx->shard.rank, cur = ctx->sc_host->cur;
-    const uint64_t n = ctx->n, N = ctx->shard.global_count;
-    const unsigned T = ctx->t_global;
-    CK(cudaMemcpyAsync(ctx->tile_sin_host, ctx->tile_sin, T * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    std::vector<uint64_t> wb(G), we(G);                                 // window [wb, we) of every rank
-    eslam_gpu_plan_windows(ctx->tile_sin_host, T, n, G, wb.data(), we.data());
-    lap("tile sums to host + plan");
-    const uint64_t wlen = we[me] - wb[me];
-    if (wlen > ctx->win_cap) {                                          // grow with headroom: windows move by tiles
-        free_window(ctx);
-        const uint64_t cap = std::max<uint64_t>(wlen + wlen / 4, n + 8 * TILE);
-        CK(dalloc(&ctx->win_cdf, cap));
-        for (int f = 0; f < 7; ++f) CK(dalloc(&ctx->win_f[f], cap));
-        for (int f = 0; f < 2; ++f) CK(dalloc(&ctx->win_b[f], cap));
-        ctx->win_cap = cap;
-    }
-    if (getenv("ESLAM_GPU_TRACE"))
-        fprintf(stderr, "[eslam rank %d] window [%llu, %llu) = %llu elements (own %llu)\n", me,
-                (unsigned long long)wb[me], (unsigned long long)we[me], (unsigned long long)wlen, (unsigned long long)n);
-    // arrays to move: running sum, 7 doubles, 2 bytes
-    const void* src[10]; void* dst[10]; size_t esz[10];
-    src[0] = ctx->cdf; dst[0] = ctx->win_cdf; esz[0] = 8;
-    for (int f = 0; f < 7; ++f) { src[1 + f] = ctx->st.f[cur][f]; dst[1 + f] = ctx->win_f[f]; esz[1 + f] = 8; }
-    for (int f = 0; f < 2; ++f) { src[8 + f] = ctx->st.b[cur][f]; dst[8 + f] = ctx->win_b[f]; esz[8 + f] = 1; }
-    const uint64_t my_lo = (uint64_t)me * n, my_hi = my_lo + n;
-    NK(g_nccl.GroupStart());
-    for (int q = 0; q < G; ++q) {
-        const uint64_t s_lo = std::max(wb[q], my_lo), s_hi = std::min(we[q], my_hi);      // what q needs from me
-        const uint64_t q_lo = (uint64_t)q * n, q_hi = q_lo + n;
-        const uint64_t r_lo = std::max(wb[me], q_lo), r_hi = std::min(we[me], q_hi);      // what I need from q
-        for (int a = 0; a < 10; ++a) {
-            if (q == me) {
-                if (r_hi > r_lo)
-                    CK(cudaMemcpyAsync((char*)dst[a] + (r_lo - wb[me]) * esz[a], (const char*)src[a] + (r_lo - my_lo) * esz[a],
-                                       (r_hi - r_lo) * esz[a], cudaMemcpyDeviceToDevice, ctx->stream));
-                continue;
-            }
-            if (s_hi > s_lo)
-                NK(g_nccl.Send((const char*)src[a] + (s_lo - my_lo) * esz[a], (s_hi - s_lo) * esz[a], ESLAM_NCCL_UINT8, q, ctx->comm, ctx->stream));
-            if (r_hi > r_lo)
-                NK(g_nccl.Recv((char*)dst[a] + (r_lo - wb[me]) * esz[a], (r_hi - r_lo) * esz[a], ESLAM_NCCL_UINT8, q, ctx->comm, ctx->stream));
-        }
-    }
-    NK(g_nccl.GroupEnd());
-    lap("enqueue range exchange");
-    const ModelParams mp = model_params(ctx);
-    const unsigned blocks = (unsigned)((n + 255) / 256);
-    GatherSrc gs; memset(&gs, 0, sizeof(gs));
-    for (int f = 0; f < 7; ++f) gs.f[f] = ctx->win_f[f];
-    for (int f = 0; f < 2; ++f) gs.b[f] = ctx->win_b[f];
-    gs.base = wb[me]; gs.use_window = 1;
-    CK(launch_pdl(ctx, k_resample, blocks, 256, 0, ctx->st, ctx->sc, ctx->win_cdf, ctx->tile_sin + wb[me] / TILE,
-                                                (unsigned)((wlen + TILE - 1) / TILE), wlen, wb[me], n, N, base_index(ctx),
-                                                mp.k0, mp.k1, ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC,
-                                                ctx->ancestors, gs));
-    LAUNCHED();
-    CK(launch_pdl(ctx, k_after_resample, 1, 1, 0, ctx->sc));
-    LAUNCHED();
-    return ESLAM_OK;
-}
-
 // normalise + (optional) resample tail shared by update / normalize_weights / resample.
 // mode: 0 = do_resample := force, 1 = decide from ESS (update), 2 = ESS only
 #ifndef RS_CTA
@@ -860,77 +732,51 @@ static int resample_exchange(eslam_gpu_ctx* ctx) {
 static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int mode, int force) {
     const unsigned T = ctx->t_local, TG = ctx->t_global;
     const uint64_t n = ctx->n, ng = global_count(ctx);
-    const double eps = scan_eps(ctx);
-    if (apply_loop_b) CK(launch_pdl(ctx, k_loop_b<true>, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, ctx->l_tile_sum));
-    else CK(launch_pdl(ctx, k_loop_b<false>, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, ctx->l_tile_sum));
-    LAUNCHED();
-    XCH(1, ctx->l_tile_sum, ctx->x_sum, T * sizeof(double2));
     const ShardPlan sp = shard_plan(ctx);
-    if (sp.mode && sharded(ctx) && !ctx->has_peers) {
-        ctx->error = "LOCAL_MIGRATE sharding needs peer access between the GPUs (the migration step reads ancestors in place)";
-        return ESLAM_ERR_INVALID;
-    }
-    CK(launch_pdl(ctx, k_reduce_b, 1, 1024, 0, ctx->g_tile_sum, TG, ng, ctx->sc, ctx->scratch_a, ctx->scratch_b, ctx->tile_prefix, normalise, sp,
-                  XFLAGS(1), XEPOCH(1), XWORLD()));
+    LoopBArgs lb; lb.tile_sum = ctx->l_tile_sum; lb.n_tiles = T; lb.discount = ctx->cfg.discount_factor;
+    lb.scratch_a = ctx->scratch_a; lb.scratch_b = ctx->scratch_b; lb.prefix_raw = ctx->prefix_raw; lb.shard_sums = ctx->shard_sums;
+    if (apply_loop_b) CK(launch_pdl(ctx, k_loop_b<true>, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, lb, sp, ctx->X));
+    else CK(launch_pdl(ctx, k_loop_b<false>, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, lb, sp, ctx->X));
     LAUNCHED();
-    CK(launch_pdl(ctx, k_norm_scan, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, ng, ctx->tile_prefix, ctx->l_tile_sq, ctx->l_desc, ctx->l_pool,
-                                             ctx->sc, normalise, eps, tile_ofs(ctx)));
+    NormScanArgs ns; ns.n_global = ng; ns.prefix_raw = ctx->prefix_raw; ns.shard_sums = ctx->shard_sums; ns.tile_prefix = ctx->tile_prefix;
+    ns.tile_sq = ctx->l_tile_sq; ns.desc = ctx->l_desc; ns.pool = ctx->l_pool; ns.scratch_a = ctx->scratch_a; ns.scratch_b = ctx->scratch_b;
+    ns.n_tiles = T; ns.tile_ofs = tile_ofs(ctx); ns.normalise = normalise; ns.eps = scan_eps(ctx);
+    CK(launch_pdl(ctx, k_norm_scan, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, ns, sp, ctx->X));
     LAUNCHED();
-    XCH(2, ctx->l_pack, ctx->x_pack, ctx->pack_bytes);                 // sum w^2, descriptors and boundary pool in one exchange
-    ChainPack pk; pk.base = ctx->g_pack; pk.pack_bytes = ctx->pack_bytes; pk.tiles_per_rank = T;
-    const int decide = mode == 0 ? 0 : 1;
-    CK(launch_pdl(ctx, k_chain, 1, 1024, sizeof(ChainSmem), pk, TG, ctx->sc, ctx->scratch_a,
-                                                         ctx->scratch_b, ctx->tile_bofs, ctx->tile_pre, ctx->tile_sin, ctx->sb,
-                                                         mode == 2 ? 0ull : ctx->cfg.min_effective, decide, force, sp,
-                                                         XFLAGS(2), XEPOCH(2), XWORLD()));
+    ChainArgs ca; ca.tile_sq = ctx->l_tile_sq; ca.desc = ctx->l_desc; ca.pool = ctx->l_pool; ca.n_tiles = T; ca.tile_ofs = tile_ofs(ctx);
+    ca.tile_bofs = ctx->tile_bofs; ca.tile_pre = ctx->tile_pre; ca.sb_out = ctx->sb;
+    ca.min_effective = mode == 2 ? 0ull : ctx->cfg.min_effective; ca.decide = mode == 0 ? 0 : 1; ca.force = force;
+    ca.n = n; ca.cdf = ctx->cdf;
+    CK(launch_pdl(ctx, k_chain, 1, 1024, sizeof(ChainSmem), ctx->st, ctx->sc, ca, sp, ctx->X));
     LAUNCHED();
     if (mode == 2) return ESLAM_OK;
-    CK(launch_pdl(ctx, k_cdf, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, ctx->tile_prefix, ctx->tile_bofs, ctx->tile_sin, ctx->sb, ctx->cdf, eps,
-                                       tile_ofs(ctx)));
-    LAUNCHED();
-    if (sharded(ctx) && ctx->has_peers) {
-        // all ranks must have finished their k_cdf before anyone reads running sums / state through peer pointers:
-        // an empty exchange is that barrier (the next step's exchanges protect the buffers that are still being read
-        // from being overwritten)
-        XCH(3, nullptr, 0, 0);
-        const ModelParams mp = model_params(ctx);
-        CK(launch_pdl(ctx, k_resample_local<RS_CTA>, (unsigned)((n + RS_CTA - 1) / RS_CTA), RS_CTA, 0, ctx->st, ctx->sc, ctx->tile_sin, TG, T, n, ng, base_index(ctx),
-                                                                             mp.k0, mp.k1, ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC,
-                                                                             ctx->ancestors, ctx->ticket, ctx->peers, sp, tile_ofs(ctx), (unsigned)ctx->shard.rank,
-                                                                             XFLAGS(3), XEPOCH(3), XWORLD()));
-        LAUNCHED();
-        return ESLAM_OK;
-    }
-    if (sharded(ctx)) return resample_exchange(ctx);
-    CK(launch_pdl(ctx, k_cdf_sequential, 1, 1, 0, ctx->st, ctx->sc, n, ctx->cdf, ctx->tile_sin));
+    CdfArgs cd; cd.tile_prefix = ctx->tile_prefix; cd.tile_bofs = ctx->tile_bofs; cd.sb = ctx->sb; cd.cdf = ctx->cdf; cd.eps = ns.eps; cd.tile_ofs = tile_ofs(ctx);
+    CK(launch_pdl(ctx, k_cdf, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, cd, sp, ctx->X));
     LAUNCHED();
     const ModelParams mp = model_params(ctx);
-    if (ctx->cfg.patch_size <= 0 && ctx->stream_resample && !sp.mode) {
+    const int systematic = ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC;
+    double* tile_sin = tile_sin_table(ctx);
+    PatchGather pg; memset(&pg, 0, sizeof(pg));
+    pg.P = ctx->cfg.patch_size > 0 ? ctx->cfg.patch_size : 0;
+    for (int b = 0; b < 2; ++b) { pg.patch[b] = ctx->patch[b]; pg.porigin[b] = ctx->porigin[b]; }
+    if (sharded(ctx)) {
+        // every rank searches the global tile-start table (pushed by the ranks' k_chain), then the owner's running sums, and
+        // copies its ancestors' state (and map patches) straight from the owner's buffers over NVLink
+        CK(launch_pdl(ctx, k_resample_local<RS_CTA>, (unsigned)((n + RS_CTA - 1) / RS_CTA), RS_CTA, 0, ctx->st, ctx->sc, tile_sin, TG, T, n, ng, base_index(ctx),
+                      mp.k0, mp.k1, systematic, ctx->ancestors, ctx->ticket, ctx->peers, sp, tile_ofs(ctx), (unsigned)ctx->shard.rank, pg, ctx->X));
+        LAUNCHED();
+        return ESLAM_OK;
+    }
+    if (pg.P == 0 && ctx->env.stream_resample && !sp.mode) {
         // persistent CTAs, source tiles streamed through a bulk-copy ring (see k_resample_stream)
-        CK(launch_pdl(ctx, k_resample_stream, (unsigned)ctx->sm_count, 1024, (size_t)RS_STREAM_SMEM, ctx->st, ctx->sc, ctx->cdf, ctx->tile_sin, T, n, mp.k0, mp.k1,
-                                                              ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC, ctx->ancestors, ctx->ticket));
+        CK(launch_pdl(ctx, k_resample_stream, (unsigned)ctx->sm_count, 1024, (size_t)RS_STREAM_SMEM, ctx->st, ctx->sc, ctx->cdf, tile_sin, T, n, mp.k0, mp.k1,
+                      systematic, ctx->ancestors, ctx->ticket));
         LAUNCHED();
         return ESLAM_OK;
     }
-    if (ctx->cfg.patch_size <= 0 && !getenv("ESLAM_GPU_NO_LOCAL_RESAMPLE")) {
-        // search in shared memory, copy and buffer swap in one kernel
-        CK(launch_pdl(ctx, k_resample_local<RS_CTA>, (unsigned)((n + RS_CTA - 1) / RS_CTA), RS_CTA, 0, ctx->st, ctx->sc, ctx->tile_sin, T, T, n, n, 0ull, mp.k0, mp.k1,
-                                                                              ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC,
-                                                                              ctx->ancestors, ctx->ticket, ctx->peers, sp, 0u, 0u, (const unsigned*)nullptr, 0u, 1));
-        LAUNCHED();
-        return ESLAM_OK;
-    }
-    const unsigned blocks = (unsigned)((n + 255) / 256);
-    GatherSrc gs; memset(&gs, 0, sizeof(gs));
-    CK(launch_pdl(ctx, k_resample, blocks, 256, 0, ctx->st, ctx->sc, ctx->cdf, ctx->tile_sin, T, n, 0, n, ng, 0, mp.k0, mp.k1,
-                                                ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC, ctx->ancestors, gs));
-    LAUNCHED();
-    if (ctx->cfg.patch_size > 0) {
-        CK(launch_pdl(ctx, k_gather_patches, (unsigned)((n * 32 + 255) / 256), 256, 0, ctx->sc, n, ctx->ancestors, ctx->cfg.patch_size,
-                                                                                  ctx->patch[0], ctx->patch[1], ctx->porigin[0], ctx->porigin[1]));
-        LAUNCHED();
-    }
-    CK(launch_pdl(ctx, k_after_resample, 1, 1, 0, ctx->sc));
+    // search in shared memory, copy (state and map patch) and buffer swap in one kernel
+    CK(launch_pdl(ctx, k_resample_local<RS_CTA>, (unsigned)((n + RS_CTA - 1) / RS_CTA), RS_CTA, 0, ctx->st, ctx->sc, tile_sin, T, T, n, n, 0ull, mp.k0, mp.k1,
+                  systematic, ctx->ancestors, ctx->ticket, ctx->peers, sp, 0u, 0u, pg, ctx->X));
     LAUNCHED();
     return ESLAM_OK;
 }
@@ -942,7 +788,7 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
     const size_t smem = weight_smem_bytes(ctx);
     const unsigned grid = weight_grid(ctx);
     const bool patches = ctx->cfg.patch_size > 0;
-    static FastParams F;                                                  // large (lists of 128 contacts): not on the stack
+    FastParams& F = *ctx->fast;                                           // large (lists of 128 contacts): per context, not on the stack
     const bool lean = fill_fast_params(ctx, &F, P, *cs);
     if (!lean && ev0) CK(cudaEventRecord(ev0, ctx->stream));
     if (lean) {
@@ -955,7 +801,7 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
         CK(launch_pdl(ctx, k_bin_scatter, T, 1024, 0, ctx->bin_count, F.fc.nb, ctx->keys, ctx->n, ctx->bin_list, ctx->bin_offs, ctx->cta_bin, ctx->sm_count));
         LAUNCHED();
         if (ev0) CK(cudaEventRecord(ev0, ctx->stream));                  // the events bracket the dominant kernel alone
-        if (ctx->lean_threads == 512)
+        if (ctx->env.lean_threads == 512)
             CK(launch_pdl(ctx, k_weight_lean<512>, (unsigned)ctx->sm_count, 512, smem, F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin));
         else
             CK(launch_pdl(ctx, k_weight_lean<1024>, (unsigned)ctx->sm_count, 1024, smem, F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin));
@@ -974,18 +820,17 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
         if (ev1) CK(cudaEventRecord(ev1, ctx->stream));
     }
     ctx->last_lean = lean;
-    CK(launch_pdl(ctx, k_tile_part, ctx->t_local, SCAN_THREADS, 0, ctx->st, ctx->sc, ctx->n, ctx->l_part_a));
+    TilePartArgs ta; ta.part = ctx->l_part_a; ta.n_tiles = ctx->t_local; ta.scratch_a = ctx->scratch_a; ta.scratch_b = ctx->scratch_b;
+    ta.hint = ctx->hint; ta.n_hint = ctx->hint_n; ta.n_local = ctx->n; ta.bin_count = ctx->bin_count; ta.bin_next = ctx->bin_next;
+    CK(launch_pdl(ctx, k_tile_part, ctx->t_local, SCAN_THREADS, 0, ctx->st, ctx->sc, ctx->n, ta, ctx->X));
     LAUNCHED();
-    XCH(0, ctx->l_part_a, ctx->x_part, ctx->t_local * sizeof(TilePartA));
-    CK(launch_pdl(ctx, k_reduce_a, 1, 1024, 0, ctx->g_part_a, ctx->t_global, ctx->n, ctx->sc, ctx->scratch_a, ctx->scratch_b,
-                                            ctx->cfg.discount_factor, ctx->hint, ctx->hint_n, ctx->bin_count, ctx->bin_next,
-                                            XFLAGS(0), XEPOCH(0), XWORLD()));
-    LAUNCHED();
-    // cloud centre (tile placement of the generic path) and the generic-list length (its launch size): copied to the host
-    // on a side stream, read by later launches without waiting -- both are hints
-    CK(cudaEventRecord(ctx->side_ev, ctx->stream));
-    CK(cudaStreamWaitEvent(ctx->side, ctx->side_ev, 0));
-    CK(cudaMemcpyAsync(ctx->sc_async, ctx->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->side));
+    // cloud centre (tile placement of the generic path): copied to the host on a side stream, read by later launches
+    // without waiting -- a hint
+    if (!lean) {
+        CK(cudaEventRecord(ctx->side_ev, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->side, ctx->side_ev, 0));
+        CK(cudaMemcpyAsync(ctx->sc_async, ctx->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, ctx->side));
+    }
     return launch_tail(ctx, true, 1, 1, 0);
 }
 
@@ -996,9 +841,11 @@ static int fetch_result(eslam_gpu_ctx* ctx, eslam_gpu_update_result* r) {
     r->ess = s.ess; r->max_weight = s.max_weight; r->floating_weight = s.floating_weight; r->weights_sum = s.sum_w;
     r->data_particles = s.data_particles; r->total_points = s.total_points; r->resampled = s.do_resample;
     r->status = ESLAM_OK;
-    if (sharded(ctx) && (s.error_flags & ERR_CDF_FALLBACK_BIT)) {
+    if (s.error_flags & (ERR_XCHG_TIMEOUT_BIT | ERR_INTERNAL_BIT)) {
         r->status = ESLAM_ERR_COMM;
-        ctx->error = "exact running sum needs the sequential fallback, which is not available across shards";
+        ctx->error = (s.error_flags & ERR_XCHG_TIMEOUT_BIT) ? "a rank did not arrive at a peer-memory exchange within 4 s"
+                                                            : "internal consistency check of the exact running sum failed";
+        CK(cudaMemsetAsync(&ctx->sc->error_flags, 0, sizeof(int), ctx->stream));
     }
     if (s.error_flags & ERR_ZERO_VARIANCE_BIT) {
         r->status = ESLAM_ERR_ZERO_VARIANCE;
@@ -1077,6 +924,12 @@ int eslam_gpu_run_steps(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const es
     if (st != ESLAM_OK) return st;
     const size_t need = 2 + 2 * (size_t)steps;
     while (ctx->events.size() < need) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->events.push_back(e); }
+    if (sharded(ctx)) {
+        // all ranks enter the timed region together: a rendezvous on the streams (flags over peer memory), so that no rank's
+        // events include waiting for a rank that was enqueued later
+        k_barrier<<<1, 32, 0, ctx->stream>>>(ctx->sc, ctx->X);
+        LAUNCHED();
+    }
     CK(cudaEventRecord(ctx->events[0], ctx->stream));
     ctx->marks_used = 0;
     for (int s = 0; s < steps; ++s) {
@@ -1092,19 +945,36 @@ int eslam_gpu_run_steps(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const es
         for (int s = 0; s < steps; ++s) { float t = 0; CK(cudaEventElapsedTime(&t, ctx->events[2 + 2 * s], ctx->events[3 + 2 * s])); tot += t; }
         *top_kernel_ms = tot;
     }
+    // step periods (start of the dominant kernel of step s to that of step s+1): the median is robust against a single stall
+    ctx->step_ms.clear();
+    for (int s = 0; s + 1 < steps; ++s) { float t = 0; CK(cudaEventElapsedTime(&t, ctx->events[2 + 2 * s], ctx->events[4 + 2 * s])); ctx->step_ms.push_back(t); }
     return last_result ? fetch_result(ctx, last_result) : ESLAM_OK;
+}
+
+int eslam_gpu_step_times(eslam_gpu_ctx* ctx, float* out_ms, int cap) {
+    if (!ctx || (!out_ms && cap > 0)) return -1;
+    const int n = (int)std::min<size_t>(ctx->step_ms.size(), (size_t)(cap > 0 ? cap : 0));
+    for (int i = 0; i < n; ++i) out_ms[i] = ctx->step_ms[i];
+    return (int)ctx->step_ms.size();
+}
+
+int eslam_gpu_io_bytes(const eslam_gpu_ctx* ctx, int n_pts, uint64_t out[2]) {
+    if (!ctx || !out || n_pts < 0) return ESLAM_ERR_INVALID;
+    out[0] = sizeof(eslam_gpu_step) + (uint64_t)n_pts * sizeof(eslam_gpu_contact);   // host inputs of one eslam_gpu_step_fused call
+    out[1] = sizeof(DevScalars);                                                      // what fetch_result copies back for the UpdateResult
+    return ESLAM_OK;
 }
 
 int eslam_gpu_weights_sum(eslam_gpu_ctx* ctx, double* sum) {
     int st = check_ready(ctx, false);
     if (st != ESLAM_OK) return st;
     if (!sum) return ESLAM_ERR_INVALID;
-    k_loop_b<false><<<ctx->t_local, SCAN_THREADS, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->n, ctx->l_tile_sum);
-    LAUNCHED();
-    XCH(1, ctx->l_tile_sum, ctx->x_sum, ctx->t_local * sizeof(double2));
     ShardPlan sp0; memset(&sp0, 0, sizeof(sp0));
-    k_reduce_b<<<1, 1024, 0, ctx->stream>>>(ctx->g_tile_sum, ctx->t_global, global_count(ctx), ctx->sc, ctx->scratch_a, ctx->scratch_b,
-                                            ctx->tile_prefix, 0, sp0, XFLAGS(1), XEPOCH(1), XWORLD());
+    LoopBArgs lb; lb.tile_sum = ctx->l_tile_sum; lb.n_tiles = ctx->t_local; lb.discount = ctx->cfg.discount_factor;
+    lb.scratch_a = ctx->scratch_a; lb.scratch_b = ctx->scratch_b; lb.prefix_raw = ctx->prefix_raw; lb.shard_sums = ctx->shard_sums;
+    CK(launch_pdl(ctx, k_loop_b<false>, ctx->t_local, SCAN_THREADS, 0, ctx->st, ctx->sc, ctx->n, lb, sp0, ctx->X));
+    LAUNCHED();
+    k_sum_finish<<<1, 32, 0, ctx->stream>>>(ctx->sc, sp0, ctx->shard_sums, ctx->X);
     LAUNCHED();
     st = read_scalars(ctx);
     if (st != ESLAM_OK) return st;
@@ -1180,7 +1050,11 @@ int eslam_gpu_evaluate_poses(eslam_gpu_ctx* ctx, uint64_t n, const double* x, co
     int st = build_contact_set(ctx, pts, n_pts, &P.cs);
     if (st != ESLAM_OK) return st;
     const size_t nd = n * sizeof(double);
-    double* din = nullptr; double* dout = nullptr; int32_t* dint = nullptr; uint8_t* dok = nullptr; int* derr = nullptr;
+    struct Temps {                                                       // freed on every path out of this function
+        double* din = nullptr; double* dout = nullptr; int32_t* dint = nullptr; uint8_t* dok = nullptr; int* derr = nullptr;
+        ~Temps() { cudaFree(din); cudaFree(dout); cudaFree(dint); cudaFree(dok); cudaFree(derr); }
+    } tmp;
+    double*& din = tmp.din; double*& dout = tmp.dout; int32_t*& dint = tmp.dint; uint8_t*& dok = tmp.dok; int*& derr = tmp.derr;
     const size_t cpn = n * ESLAM_MAX_CP * 5, celln = n * (size_t)(n_pts > 0 ? n_pts : 1);
     CK(dalloc(&din, 6 * n)); CK(dalloc(&dout, 6 * n + cpn)); CK(dalloc(&dint, n + celln)); CK(dalloc(&dok, n)); CK(dalloc(&derr, 1));
     const double* src[6] = {x, y, theta, zpos, meas_var, z_var_in};
@@ -1209,7 +1083,6 @@ int eslam_gpu_evaluate_poses(eslam_gpu_ctx* ctx, uint64_t n, const double* x, co
     if (n_contacts) CK(cudaMemcpyAsync(n_contacts, dint, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (cell_index && n_pts > 0) CK(cudaMemcpyAsync(cell_index, dint + n, celln * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(din); cudaFree(dout); cudaFree(dint); cudaFree(dok); cudaFree(derr);
     if (herr & ERR_ZERO_VARIANCE_BIT) {
         ctx->error = "using a zero measurement variance leads to singularities";
         return ESLAM_ERR_ZERO_VARIANCE;
@@ -1234,15 +1107,6 @@ int eslam_gpu_path_counters(eslam_gpu_ctx* ctx, uint64_t out[2]) {
     if (st != ESLAM_OK) return st;
     out[0] = ctx->last_lean ? ctx->n : 0; out[1] = ctx->last_lean ? ctx->sc_host->defer_last : ctx->n;
     return ESLAM_OK;
-}
-
-int eslam_gpu_patch_update(eslam_gpu_ctx* ctx) {
-    if (!ctx) return ESLAM_ERR_INVALID;
-    if (ctx->cfg.patch_size <= 0) {
-        ctx->error = "per-particle map patches are not enabled in this context (patch_size == 0)";
-        return ESLAM_ERR_INVALID;
-    }
-    return ESLAM_OK;   // the write is part of update(): after each particle's evaluation, before resampling
 }
 
 int eslam_gpu_get_patches(eslam_gpu_ctx* ctx, float* cells, int32_t* origin_xy) {

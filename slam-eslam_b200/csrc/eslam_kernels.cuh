@@ -63,8 +63,10 @@ struct DevScalars {              // device-resident scalars of one context
     unsigned int fallbacks;      // times the sequential CDF fallback ran
     unsigned int defer_count;    // particles the binning flagged for contact_eval (map border, out-of-range values; live counter)
     unsigned int defer_last;     // its value at the end of the last update (diagnostics)
-    int migrate;                 // LOCAL_MIGRATE sharding: 1 = this step resamples exact-globally (k_reduce_b decides)
-    int pad_migrate;
+    int migrate;                 // LOCAL_MIGRATE sharding: 1 = this step resamples exact-globally (decided in k_norm_scan)
+    int cdf_seq;                 // the running sum of this resample was computed sequentially by k_chain (k_cdf skips)
+    unsigned int ticket[4];      // "last CTA" counters: 0 k_tile_part, 1 k_loop_b, 2 k_norm_scan, 3 k_cdf
+    unsigned int x_epoch[8];     // epoch of every exchange (X_*): bumped by this rank's producer, read by its consumers
 };
 
 struct TilePartA {               // per-tile partials of loop A
@@ -160,42 +162,113 @@ __device__ __forceinline__ void pdl_start() {
 }
 
 // ------------------------------------------------------------------------------------------------ peer exchange
-// The small per-step exchanges of the sharded filter (loop-A tile partials, raw tile sums, chain inputs, the barrier in
-// front of the peer-memory resampling) go over NVLink peer memory instead of a collective library: every rank PUSHES its
-// block into the same slot of every peer's buffer (k_publish: one CTA per peer, plain stores to the peer-mapped pointer,
-// then a system-scope release of an epoch flag in the peer's memory); the consuming kernel polls its OWN flags (local
-// memory) until all ranks' epoch has arrived.  One launch + one NVLink write + a local poll instead of a collective's
-// latency; ordering between steps is the same as with collectives (a rank cannot publish step s+1 before every peer has
-// published the last exchange of step s, which it does after consuming the earlier ones).
-struct PublishArgs {
-    void* dst[ESLAM_MAX_RANKS];            // peer q's buffer region + my slot
-    unsigned* flag[ESLAM_MAX_RANKS];       // peer q's epoch flag for (this exchange, my rank)
-    const void* src; unsigned long long bytes;   // multiple of 8
-    unsigned epoch; int world;
+// The sharded filter's per-step exchanges run inside the step's own kernels, over NVLink peer memory (CUDA IPC mappings of
+// every rank's exchange buffer; no collective library, no extra launch).  What crosses GPUs is O(1) per rank: because a shard
+// holds 2^k tiles, the index-aligned pairwise tree over all G T tiles factors into G per-rank subtrees, so each rank reduces
+// its own tiles and publishes the subtree root; the exact running sum likewise travels as one composed rounding function +
+// boundary list per rank.  Producer: the LAST CTA of a kernel (ticket) reduces the rank's per-tile partials, PUSHES the
+// summary into slot `me` of every rank's buffer (plain stores through the peer mapping, __threadfence_system) and releases
+// an epoch flag there (st.release.sys).  Consumer: every CTA of the next kernel polls the flags in its OWN memory
+// (ld.acquire.sys) and combines the G summaries in tree order.  Epochs live in DevScalars (device side), so a step has no
+// host-supplied exchange state.  On one GPU the same code runs with world == 1 (no flags: the kernel boundary orders).
+#define X_A 0        // loop-A rank partials            k_tile_part (last CTA) -> k_loop_b
+#define X_B 1        // rank weight sums                k_loop_b (last CTA)    -> k_norm_scan
+#define X_E 2        // rank sum of w^2                 k_norm_scan (last CTA) -> k_chain
+#define X_C 3        // rank chain summary              k_chain                -> k_chain (all ranks)
+#define X_D 4        // "my running sums are final"     k_cdf (last CTA)       -> k_resample_local
+#define X_SEQ 5      // sequential fallback: S_out      k_chain of rank r      -> k_chain of rank r+1
+#define X_BAR 6      // plain rendezvous                k_barrier
+#define X_COUNT 7
+#define ERR_XCHG_TIMEOUT_BIT 4
+#define ERR_INTERNAL_BIT 8
+
+struct RankPartA { double sum_pw, max_w; unsigned long long cnt, pts; };                     // 32 B
+struct RankPartB { double sum_w, sum_sq; };                                                  // 16 B (sum_sq: raw weights, LOCAL_MIGRATE decision)
+struct ChainEntry { double w; long long d0, d1; int b, pad; };                               // a boundary element and the rounding function of the run after it
+struct RankChainHead { int n_bnd, bad; long long head_d0, head_d1; int head_b, head_pad; double pad[4]; };   // 64 B
+
+#define XOFF_A 0
+#define XOFF_B (XOFF_A + ESLAM_MAX_RANKS * 32)
+#define XOFF_E (XOFF_B + ESLAM_MAX_RANKS * 16)
+#define XOFF_SEQ (XOFF_E + ESLAM_MAX_RANKS * 8)
+#define XOFF_FLAGS 1024
+#define XOFF_C 2048
+#define XC_SLOT (64 + MAX_BND_TOTAL * 32)
+#define XOFF_TSIN (XOFF_C + ESLAM_MAX_RANKS * XC_SLOT)                                       // then world x tiles_per_rank doubles
+
+struct Xchg {
+    unsigned char* buf[ESLAM_MAX_RANKS];   // rank q's exchange buffer as mapped into this process (q == me: the local one)
+    int world, me;
+    unsigned tiles_per_rank;               // stride of the global tile-start table at XOFF_TSIN
+    unsigned pad;
 };
+
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__global__ void __launch_bounds__(256) k_publish(const __grid_constant__ PublishArgs A) {
-    pdl_start();
-    const int q = blockIdx.x;
-    if (q >= A.world) return;
-    const unsigned long long words = A.bytes >> 3;
-    const unsigned long long* s = reinterpret_cast<const unsigned long long*>(A.src);
-    unsigned long long* d = reinterpret_cast<unsigned long long*>(A.dst[q]);
-    for (unsigned long long i = threadIdx.x; i < words; i += blockDim.x) d[i] = s[i];
+// data another GPU wrote into this GPU's memory: read at system scope (never from a stale L1 line)
+__device__ __forceinline__ unsigned long long ld_sys_u64(const void* p) {
+    unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ double ld_sys_f64(const void* p) { return __longlong_as_double((long long)ld_sys_u64(p)); }
+__device__ __forceinline__ unsigned* x_flags(unsigned char* buf, int x) { return reinterpret_cast<unsigned*>(buf + XOFF_FLAGS) + x * ESLAM_MAX_RANKS; }
+
+// Producer side, all threads of ONE CTA: copy `words` 8-byte words from src (shared or global memory) to byte offset `off` of
+// every rank's buffer, then raise flag (x, me) there to `epoch`.
+__device__ __forceinline__ void x_publish(const Xchg& X, size_t off, const void* src, unsigned words, int x, unsigned epoch) {
+    const unsigned long long* s = reinterpret_cast<const unsigned long long*>(src);
+    for (int q = 0; q < X.world; ++q) {
+        unsigned long long* d = reinterpret_cast<unsigned long long*>(X.buf[q] + off);
+        for (unsigned i = threadIdx.x; i < words; i += blockDim.x) d[i] = s[i];
+    }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) st_release_sys(A.flag[q], A.epoch);
+    if (X.world > 1 && (int)threadIdx.x < X.world) st_release_sys(x_flags(X.buf[threadIdx.x], x) + X.me, epoch);
 }
-// consumer side: wait until every rank's block of this exchange and epoch has landed in this GPU's memory
-__device__ __forceinline__ void peer_wait(const unsigned* flags, unsigned epoch, int world) {
-    if (world <= 1 || flags == nullptr) return;
-    if ((int)threadIdx.x < world) { while ((int)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) __nanosleep(40); }
+// Consumer side, all threads of a CTA: wait until every rank's (or, with only >= 0, that one rank's) flag of exchange x has
+// reached `epoch`.  A rank that never arrives (a dead peer) would hang the GPU: after ~4 s the wait gives up and flags the step.
+__device__ __forceinline__ void x_wait(const Xchg& X, int x, unsigned epoch, int* error_flags, int only = -1) {
+    if (X.world > 1) {
+        const int q = (int)threadIdx.x;
+        if (q < X.world && (only < 0 || q == only)) {
+            const unsigned* f = x_flags(X.buf[X.me], x) + q;
+            const long long t0 = clock64();
+            while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+                __nanosleep(20);
+                if (clock64() - t0 > 8000000000ll) { atomicOr(error_flags, ERR_XCHG_TIMEOUT_BIT); break; }
+            }
+        }
+    }
     __syncthreads();
+}
+// pairwise tree over m <= 64 values held by one thread: the top levels of the index-aligned tree over all ranks' tiles
+__device__ __forceinline__ double tree_small(double* v, int m) {
+    while (m > 1) { const int h = (m + 1) >> 1; for (int j = 0; j < h; ++j) v[j] = (2 * j + 1 < m) ? v[2 * j] + v[2 * j + 1] : v[2 * j]; m = h; }
+    return v[0];
+}
+// "am I the last CTA of this grid to get here": everything the other CTAs wrote before their call is visible to the last one
+__device__ __forceinline__ bool cta_is_last(unsigned* ticket) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) { const unsigned t = atomicAdd(ticket, 1u); s_last = (t == gridDim.x - 1) ? 1 : 0; if (s_last) *ticket = 0; }
+    __syncthreads();
+    const bool last = s_last != 0;
+    if (last) __threadfence();
+    return last;
+}
+// rendezvous of all ranks on their streams (eslam_gpu_run_steps: all ranks start the timed region together)
+__global__ void k_barrier(DevScalars* sc, const __grid_constant__ Xchg X) {
+    __shared__ unsigned s_e;
+    if (threadIdx.x == 0) { s_e = sc->x_epoch[X_BAR] + 1; }
+    __syncthreads();
+    const unsigned e = s_e;
+    x_publish(X, 0, nullptr, 0, X_BAR, e);
+    x_wait(X, X_BAR, e, &sc->error_flags);
+    if (threadIdx.x == 0) sc->x_epoch[X_BAR] = e;
 }
 
 __device__ __forceinline__ uint32_t stream_word(uint32_t stream, unsigned long long idx) {
@@ -232,11 +305,12 @@ __device__ __forceinline__ double tile_tree_sum_1024(double v, double* red) {
 // (sa: TREE_SMEM doubles, sb: TREE_SMEM/2) and n <= 2*TREE_SMEM all levels but the first run in shared memory;
 // otherwise the levels ping-pong between the global arrays a and b.  Same tree either way.
 #define TREE_SMEM 2048
-__device__ double block_tree_reduce(double* a, double* b, unsigned n, double* sa = nullptr, double* sb = nullptr) {
-    if (sa && ((n + 1) >> 1) > TREE_SMEM && n <= 16u * TREE_SMEM) {
+#define TREE_SMEM_S 1024         // capacity used by the 256-thread kernels' last-CTA trees (8 + 4 KB of shared memory)
+__device__ double block_tree_reduce(double* a, double* b, unsigned n, double* sa = nullptr, double* sb = nullptr, unsigned cap = TREE_SMEM) {
+    if (sa && ((n + 1) >> 1) > cap && n <= 16u * cap) {
         // many tiles (sharded runs: all ranks' tiles): the first L levels of the same tree run in registers, 2^L consecutive
         // leaves per thread (a missing right operand passes the left one through, as below), the rest in shared memory
-        unsigned L = 1; while ((((n + (1u << L) - 1) >> L) + 1) >> 1 > TREE_SMEM) ++L;
+        unsigned L = 1; while ((((n + (1u << L) - 1) >> L) + 1) >> 1 > cap) ++L;
         const unsigned groups = (n + (1u << L) - 1) >> L;                 // <= 2 * TREE_SMEM values left
         for (unsigned g = threadIdx.x; g < ((groups + 1) >> 1); g += blockDim.x) {
             double pair[2]; unsigned have = 0;
@@ -264,7 +338,7 @@ __device__ double block_tree_reduce(double* a, double* b, unsigned n, double* sa
         __syncthreads();
         return r;
     }
-    if (sa && n > 1 && ((n + 1) >> 1) <= TREE_SMEM) {
+    if (sa && n > 1 && ((n + 1) >> 1) <= cap) {
         unsigned h = (n + 1) >> 1;
         for (unsigned i = threadIdx.x; i < h; i += blockDim.x) sa[i] = (2 * i + 1 < n) ? a[2 * i] + a[2 * i + 1] : a[2 * i];
         __syncthreads();
@@ -1095,12 +1169,25 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_c
 // ------------------------------------------------------------------------------------------------ loop A partials
 // data_particles, total_points, max_weight and the terms pow(w, 1/found) of sum_data_weights (src/PoseEstimator.cpp:
 // 305-310) per 1024-particle tile, from what the weight kernels left per particle (mprob, floating, cpoints.size()).
-__global__ void __launch_bounds__(SCAN_THREADS) k_tile_part(StateBufs st, const DevScalars* sc, unsigned long long n,
-                                                            TilePartA* part) {
+// The last CTA to finish reduces the rank's tiles (pairwise tree, continuing the per-tile trees) and publishes the rank's
+// partial to every rank (exchange X_A); it also clears the lean path's bin counters for the next update and refreshes the
+// generic path's tile placement hint.
+struct TilePartArgs {
+    TilePartA* part; unsigned n_tiles;
+    double *scratch_a, *scratch_b;
+    const double* hint; unsigned n_hint; unsigned long long n_local;
+    int* bin_count; unsigned* bin_next;
+};
+__global__ void __launch_bounds__(SCAN_THREADS) k_tile_part(StateBufs st, DevScalars* sc, unsigned long long n, const TilePartArgs A,
+                                                            const __grid_constant__ Xchg X) {
     pdl_start();
     __shared__ double red[8];
     __shared__ double redm[8];
     __shared__ unsigned redu[16];
+    __shared__ double tree_a[TREE_SMEM_S], tree_b[TREE_SMEM_S / 2];
+    __shared__ unsigned long long redull[16];
+    __shared__ RankPartA s_out;
+    __shared__ unsigned s_epoch;
     const int cur = sc->cur;
     const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
     double mp[EPT]; unsigned nf[EPT], fl[EPT];
@@ -1132,68 +1219,41 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_part(StateBufs st, const 
     if (threadIdx.x == 0) {
         TilePartA o; o.sum_pw = s; o.max_w = 0; o.cnt = 0; o.pts = 0;
         for (int k = 0; k < SCAN_THREADS / 32; ++k) { o.max_w = fmax(o.max_w, redm[k]); o.cnt += redu[k]; o.pts += redu[8 + k]; }
-        part[blockIdx.x] = o;
+        A.part[blockIdx.x] = o;
     }
-}
-
-// ------------------------------------------------------------------------------------------------ reduce A (one CTA)
-// floating_weight (:329), max_weight (:305, :347-348), the loop-B power table, next step's map tile centre
-__global__ void __launch_bounds__(1024, 1) k_reduce_a(const TilePartA* part, unsigned n_tiles, unsigned long long n_local,
-                                                      DevScalars* sc, double* scratch_a, double* scratch_b,
-                                                      double discount, const double* hint, unsigned n_hint, int* bin_count,
-                                                      unsigned* bin_next, const unsigned* xflags, unsigned epoch, int world) {
-    pdl_start();
-    peer_wait(xflags, epoch, world);
-    for (int b = threadIdx.x; b < MAX_BINS; b += blockDim.x) { bin_count[b] = 0; bin_next[b] = 0; }   // for the next update's lean path
-    __shared__ double red[32];
-    __shared__ unsigned long long redull[64];
-    __shared__ double tree_a[TREE_SMEM], tree_b[TREE_SMEM / 2];
-    double mx = 0; unsigned long long cnt = 0, pts = 0;
-    const bool direct = n_tiles > 1 && ((n_tiles + 1) >> 1) <= TREE_SMEM;   // first tree level straight from the partials
-    for (unsigned i = threadIdx.x; i < n_tiles; i += blockDim.x) {
-        const TilePartA p = part[i];
-        if (!direct) scratch_a[i] = p.sum_pw;
-        mx = fmax(mx, p.max_w); cnt += p.cnt; pts += p.pts;
+    if (!cta_is_last(&sc->ticket[0])) return;
+    // ---- last CTA: the rank's partial (floating_weight :329 and max_weight :305,:347-348 need all ranks': k_loop_b combines them)
+    for (int b = threadIdx.x; b < MAX_BINS; b += blockDim.x) { A.bin_count[b] = 0; A.bin_next[b] = 0; }   // for the next update's lean path
+    double rmx = 0; unsigned long long rcnt = 0, rpts = 0;
+    for (unsigned i = threadIdx.x; i < A.n_tiles; i += blockDim.x) {
+        TilePartA p;                                                     // 24 bytes, written by another CTA: read through L2
+        { const double* pp = reinterpret_cast<const double*>(A.part + i); const uint2 cp = __ldcg(reinterpret_cast<const uint2*>(pp + 2));
+          p.sum_pw = __ldcg(pp); p.max_w = __ldcg(pp + 1); p.cnt = cp.x; p.pts = cp.y; }
+        A.scratch_a[i] = p.sum_pw;
+        rmx = fmax(rmx, p.max_w); rcnt += p.cnt; rpts += p.pts;
     }
-    double sum_pw;
-    if (direct) {
-        double *ta = tree_a, *tb = tree_b;
-        unsigned m = (n_tiles + 1) >> 1;
-        for (unsigned i = threadIdx.x; i < m; i += blockDim.x) ta[i] = (2 * i + 1 < n_tiles) ? part[2 * i].sum_pw + part[2 * i + 1].sum_pw : part[2 * i].sum_pw;
-        __syncthreads();
-        while (m > 1) {
-            const unsigned h = (m + 1) >> 1;
-            for (unsigned i = threadIdx.x; i < h; i += blockDim.x) tb[i] = (2 * i + 1 < m) ? ta[2 * i] + ta[2 * i + 1] : ta[2 * i];
-            __syncthreads();
-            double* t = ta; ta = tb; tb = t; m = h;
-        }
-        sum_pw = ta[0];
-        __syncthreads();
-    } else {
-        __syncthreads();
-        sum_pw = block_tree_reduce(scratch_a, scratch_b, n_tiles, tree_a, tree_b);
-    }
-    mx = warp_max(mx);
-    for (int o = 1; o < 32; o <<= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); pts += __shfl_xor_sync(0xffffffffu, pts, o); }
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = mx; redull[threadIdx.x >> 5] = cnt; redull[32 + (threadIdx.x >> 5)] = pts; }
+    const double sum_pw = block_tree_reduce(A.scratch_a, A.scratch_b, A.n_tiles, tree_a, tree_b, TREE_SMEM_S);
+    rmx = warp_max(rmx);
+    for (int o = 1; o < 32; o <<= 1) { rcnt += __shfl_xor_sync(0xffffffffu, rcnt, o); rpts += __shfl_xor_sync(0xffffffffu, rpts, o); }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { redm[threadIdx.x >> 5] = rmx; redull[threadIdx.x >> 5] = rcnt; redull[8 + (threadIdx.x >> 5)] = rpts; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double smx = 0; unsigned long long scnt = 0, spts = 0;
-        for (int i = 0; i < 32; ++i) { smx = fmax(smx, red[i]); scnt += redull[i]; spts += redull[32 + i]; }
-        double tsx = 0, tsy = 0;
-        for (unsigned i = 0; i < n_hint; ++i) { tsx += hint[2 * i]; tsy += hint[2 * i + 1]; }
-        const double last_max = sc->max_weight;                                       // :268
-        const double fw = scnt > 0 ? sum_pw / (double)scnt : 1.0;                     // :329
-        sc->floating_weight = fw;
-        sc->data_particles = scnt; sc->total_points = spts;
-        sc->max_weight = (spts == 0) ? last_max * discount : smx;                     // :347-348
-        const double xb = discount * fw;
-        for (int k = 0; k <= 4; ++k) sc->pow_table[k] = em::pow_u64(xb, (unsigned long long)(4 - k));   // :336
-        sc->pow_table[5] = em::pow_u64(xb, ~0ull);                                    // wrapped size_t exponent (Q2)
-        if (n_local > 0 && n_hint > 0) { sc->tile_cx = tsx / (double)n_local; sc->tile_cy = tsy / (double)n_local; }
+        RankPartA o; o.sum_pw = sum_pw; o.max_w = 0; o.cnt = 0; o.pts = 0;
+        for (int k = 0; k < SCAN_THREADS / 32; ++k) { o.max_w = fmax(o.max_w, redm[k]); o.cnt += redull[k]; o.pts += redull[8 + k]; }
+        s_out = o;
+        s_epoch = sc->x_epoch[X_A] + 1;
+        if (A.n_local > 0 && A.n_hint > 0) {
+            double tsx = 0, tsy = 0;
+            for (unsigned i = 0; i < A.n_hint; ++i) { tsx += __ldcg(A.hint + 2 * i); tsy += __ldcg(A.hint + 2 * i + 1); }
+            sc->tile_cx = tsx / (double)A.n_local; sc->tile_cy = tsy / (double)A.n_local;
+        }
         sc->defer_last = sc->defer_count; sc->defer_count = 0;
     }
+    __syncthreads();
+    x_publish(X, XOFF_A + (size_t)X.me * sizeof(RankPartA), &s_out, sizeof(RankPartA) / 8, X_A, s_epoch);
+    if (threadIdx.x == 0) sc->x_epoch[X_A] = s_epoch;
 }
 
 // LOCAL_MIGRATE sharding (include/eslam_gpu.h): the logical shards are runs of tiles_per_shard consecutive tiles of the
@@ -1207,13 +1267,53 @@ struct ShardPlan {
 };
 
 // ------------------------------------------------------------------------------------------------ loop B + raw sums
-// weight *= mprob * pow(discount*floating_weight, 4 - cpoints.size())  (:332-345); per-tile sums of the result
+// weight *= mprob * pow(discount*floating_weight, 4 - cpoints.size())  (:332-345); per-tile sums of the result.
+// Prologue (APPLY): every CTA combines the ranks' loop-A partials (exchange X_A) in tree order into floating_weight (:329)
+// and the power table; CTA 0 also records them, and max_weight (:305, :347-348), in DevScalars.
+// Last CTA: the rank's weight sum (pairwise tree over its tiles), the raw exclusive prefix of its tile sums (only classifies
+// elements later: approximate is enough) and, for LOCAL_MIGRATE, the per-shard sums; publishes the rank's sums (X_B).
+struct LoopBArgs {
+    double2* tile_sum; unsigned n_tiles;
+    double discount;
+    double *scratch_a, *scratch_b;
+    double* prefix_raw;            // [n_tiles] raw (un-normalised) sum of the tiles before each local tile
+    double2* shard_sums;           // [sp.count] {sum w, sum w^2} of every logical shard held here (virtual shards)
+};
 template <bool APPLY>
-__global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, const DevScalars* sc, unsigned long long n,
-                                                         double2* tile_sum) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, DevScalars* sc, unsigned long long n, const LoopBArgs A,
+                                                         const ShardPlan sp, const __grid_constant__ Xchg X) {
     pdl_start();
     __shared__ double red[8];
+    __shared__ double s_pow[6];
+    __shared__ double tree_a[TREE_SMEM_S], tree_b[TREE_SMEM_S / 2];
+    __shared__ double sh[64];
+    __shared__ RankPartB s_out;
+    __shared__ unsigned s_epoch;
     const int cur = sc->cur;
+    if (APPLY) {
+        x_wait(X, X_A, sc->x_epoch[X_A], &sc->error_flags);
+        if (threadIdx.x == 0) {
+            double v[ESLAM_MAX_RANKS]; double smx = 0; unsigned long long scnt = 0, spts = 0;
+            const unsigned char* base = X.buf[X.me] + XOFF_A;
+            for (int q = 0; q < X.world; ++q) {
+                const unsigned char* r = base + (size_t)q * sizeof(RankPartA);
+                v[q] = ld_sys_f64(r); smx = fmax(smx, ld_sys_f64(r + 8)); scnt += ld_sys_u64(r + 16); spts += ld_sys_u64(r + 24);
+            }
+            const double sum_pw = tree_small(v, X.world);
+            const double fw = scnt > 0 ? sum_pw / (double)scnt : 1.0;                     // :329
+            const double xb = A.discount * fw;
+            for (int k = 0; k <= 4; ++k) s_pow[k] = em::pow_u64(xb, (unsigned long long)(4 - k));   // :336
+            s_pow[5] = em::pow_u64(xb, ~0ull);                                            // wrapped size_t exponent (Q2)
+            if (blockIdx.x == 0) {
+                const double last_max = sc->max_weight;                                   // :268
+                sc->floating_weight = fw;
+                sc->data_particles = scnt; sc->total_points = spts;
+                sc->max_weight = (spts == 0) ? last_max * A.discount : smx;               // :347-348
+                for (int k = 0; k < 6; ++k) sc->pow_table[k] = s_pow[k];
+            }
+        }
+        __syncthreads();
+    }
     const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
     double w[EPT];
     double* W = st.f[cur][F_W];
@@ -1226,7 +1326,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, const Dev
             const double mp[EPT] = {ma.x, ma.y, mb.x, mb.y};
             const unsigned nfv[EPT] = {nf.x, nf.y, nf.z, nf.w};
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) { const double factor = mp[j] * sc->pow_table[nfv[j] > 4 ? 5 : nfv[j]]; w[j] *= factor; }   // Q1: second application
+            for (int j = 0; j < EPT; ++j) { const double factor = mp[j] * s_pow[nfv[j] > 4 ? 5 : nfv[j]]; w[j] *= factor; }   // Q1: second application
             *reinterpret_cast<double2*>(W + i0) = make_double2(w[0], w[1]);
             *reinterpret_cast<double2*>(W + i0 + 2) = make_double2(w[2], w[3]);
         }
@@ -1238,7 +1338,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, const Dev
                 w[j] = W[i0 + j];
                 if (APPLY) {
                     const unsigned nf = st.b[cur][B_NF][i0 + j];
-                    const double factor = st.f[cur][F_MP][i0 + j] * sc->pow_table[nf > 4 ? 5 : nf];
+                    const double factor = st.f[cur][F_MP][i0 + j] * s_pow[nf > 4 ? 5 : nf];
                     w[j] *= factor;
                     W[i0 + j] = w[j];
                 }
@@ -1249,102 +1349,114 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, const Dev
     double q[EPT];
 #pragma unroll
     for (int j = 0; j < EPT; ++j) q[j] = w[j] * w[j];
-    const double sq = tile_tree_sum4(q, red);                        // per-shard ESS of the LOCAL_MIGRATE decision (k_reduce_b)
-    if (threadIdx.x == 0) tile_sum[blockIdx.x] = make_double2(s, sq);
-}
-
-// ------------------------------------------------------------------------------------------------ reduce B (one CTA)
-// getWeightsSum (src/ParticleFilter.hpp:34-39) and approximate per-tile prefixes of the (normalised) weights
-__global__ void __launch_bounds__(1024, 1) k_reduce_b(const double2* tile_sum2, unsigned n_tiles, unsigned long long n,
-                                                      DevScalars* sc, double* scratch_a, double* scratch_b,
-                                                      double* tile_prefix, int normalise, const ShardPlan sp,
-                                                      const unsigned* xflags, unsigned epoch, int world) {
-    pdl_start();
-    peer_wait(xflags, epoch, world);
-    __shared__ double sh[64];
-    __shared__ double tree_a[TREE_SMEM], tree_b[TREE_SMEM / 2];
-    __shared__ int s_migrate;
-    auto tsum = [&](unsigned t) -> double { return tile_sum2[t].x; };
-    double total;
-    if (n_tiles > 1 && ((n_tiles + 1) >> 1) <= TREE_SMEM) {
-        // the tree straight from the tile sums (no copy through global scratch); same tree as block_tree_reduce
-        double *ta = tree_a, *tb = tree_b;
-        unsigned m = (n_tiles + 1) >> 1;
-        for (unsigned i = threadIdx.x; i < m; i += blockDim.x) ta[i] = (2 * i + 1 < n_tiles) ? tsum(2 * i) + tsum(2 * i + 1) : tsum(2 * i);
-        __syncthreads();
-        while (m > 1) {
-            const unsigned h = (m + 1) >> 1;
-            for (unsigned i = threadIdx.x; i < h; i += blockDim.x) tb[i] = (2 * i + 1 < m) ? ta[2 * i] + ta[2 * i + 1] : ta[2 * i];
-            __syncthreads();
-            double* t = ta; ta = tb; tb = t; m = h;
-        }
-        total = ta[0];
-        __syncthreads();
-    } else {
-        for (unsigned i = threadIdx.x; i < n_tiles; i += blockDim.x) scratch_a[i] = tsum(i);
-        __syncthreads();
-        total = block_tree_reduce(scratch_a, scratch_b, n_tiles, tree_a, tree_b);
-    }
-    const int uniform = normalise && (total <= 0.0);                                 // :51 (Q8)
-    if (threadIdx.x == 0) { sc->sum_w = total; sc->uniform = uniform; sc->pool_count = 0; }
-    // LOCAL_MIGRATE: does any shard's share of the weight or its own effective sample size collapse?  Per shard the pairwise
-    // tree over its tiles' sums of w and of w^2 (every rank holds all tiles' sums, so every rank decides the same).
-    int migrate = 1;
+    const double sq = tile_tree_sum4(q, red);                        // per-shard ESS of the LOCAL_MIGRATE decision
+    if (threadIdx.x == 0) A.tile_sum[blockIdx.x] = make_double2(s, sq);
+    if (!cta_is_last(&sc->ticket[1])) return;
+    // ---- last CTA: getWeightsSum (src/ParticleFilter.hpp:34-39) of this rank's particles
+    const unsigned T = A.n_tiles;
+    for (unsigned i = threadIdx.x; i < T; i += blockDim.x) A.scratch_a[i] = __ldcg(&A.tile_sum[i]).x;
+    __syncthreads();
+    const double rank_w = block_tree_reduce(A.scratch_a, A.scratch_b, T, tree_a, tree_b, TREE_SMEM_S);
+    double rank_sq = 0.0;
     if (sp.mode) {
-        if (threadIdx.x == 0) s_migrate = 0;
-        __syncthreads();
-        if (total > 0.0) {
-            for (unsigned g = 0; g < sp.n_shards; ++g) {
-                const double2* src = tile_sum2 + (size_t)g * sp.tiles_per_shard;
-                double wq[2];
-                for (int c = 0; c < 2; ++c) {
-                    for (unsigned i = threadIdx.x; i < sp.tiles_per_shard; i += blockDim.x) scratch_a[i] = c ? src[i].y : src[i].x;
-                    __syncthreads();
-                    wq[c] = block_tree_reduce(scratch_a, scratch_b, sp.tiles_per_shard, tree_a, tree_b);
-                    __syncthreads();
-                }
-                const double share = (wq[0] / total) * (double)sp.n_shards;
-                const double essg = (wq[0] * wq[0]) / wq[1];
-                if (threadIdx.x == 0 && (share < sp.min_share || essg < sp.min_ess * (double)sp.n_shard)) s_migrate = 1;
+        // LOCAL_MIGRATE: per logical shard held here the pairwise trees over its tiles' sums of w and of w^2
+        for (unsigned g = 0; g < sp.count; ++g) {
+            const double2* src = A.tile_sum + (size_t)g * sp.tiles_per_shard;
+            double wq[2];
+            for (int c = 0; c < 2; ++c) {
+                __syncthreads();
+                for (unsigned i = threadIdx.x; i < sp.tiles_per_shard; i += blockDim.x) { const double2 v = __ldcg(&src[i]); A.scratch_a[i] = c ? v.y : v.x; }
+                __syncthreads();
+                wq[c] = block_tree_reduce(A.scratch_a, A.scratch_b, sp.tiles_per_shard, tree_a, tree_b, TREE_SMEM_S);
             }
+            if (threadIdx.x == 0) A.shard_sums[g] = make_double2(wq[0], wq[1]);
+            rank_sq = wq[1];                                          // real shards: the rank is one shard
         }
-        __syncthreads();
-        migrate = s_migrate;
     }
-    if (threadIdx.x == 0) sc->migrate = migrate;
-    const bool local = sp.mode && !migrate;
-    // exclusive scan of the per-tile masses (approximate is enough: only used to classify elements; k_norm_scan and k_cdf
-    // read the same values).  Local resampling: the scan restarts at every shard (the running sums there start from zero).
-    auto mass = [&](unsigned t) -> double {
-        if (uniform) { const unsigned long long c = min((unsigned long long)TILE, n - (unsigned long long)t * TILE); return (double)c / (double)n; }
-        return normalise ? tsum(t) / total : tsum(t);
-    };
-    // rounds of 1024 tiles, one per thread (coalesced): block exclusive scan by shuffles, a carry from round to round
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned seg = local ? sp.tiles_per_shard : n_tiles;
-    for (unsigned s0 = 0; s0 < n_tiles; s0 += seg) {
+    // raw exclusive scan of the tile sums: rounds of blockDim tiles, one per thread, a carry from round to round
+    {
+        const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
         double carry = 0.0;
-        const unsigned s1 = min(s0 + seg, n_tiles);
-        for (unsigned r0 = s0; r0 < s1; r0 += 1024) {
+        __syncthreads();
+        for (unsigned r0 = 0; r0 < T; r0 += blockDim.x) {
             const unsigned t = r0 + threadIdx.x;
-            const double local_m = t < s1 ? mass(t) : 0.0;
-            double inc = local_m;
+            const double m = t < T ? __ldcg(&A.tile_sum[t]).x : 0.0;
+            double inc = m;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (unsigned)o) inc += v; }
             if (lane == 31) sh[warp] = inc;
             __syncthreads();
             if (warp == 0) {
-                double w = sh[lane];
+                double ws = lane < nw ? sh[lane] : 0.0;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= (unsigned)o) w += v; }
-                sh[32 + lane] = w;
+                for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= (unsigned)o) ws += v; }
+                sh[32 + lane] = ws;
             }
             __syncthreads();
-            if (t < s1) tile_prefix[t] = carry + ((warp ? sh[32 + warp - 1] : 0.0) + (inc - local_m));
-            carry += sh[32 + 31];                                            // every thread keeps the same carry
+            if (t < T) A.prefix_raw[t] = carry + ((warp ? sh[32 + warp - 1] : 0.0) + (inc - m));
+            carry += sh[32 + nw - 1];                                            // every thread keeps the same carry
             __syncthreads();
         }
     }
+    if (threadIdx.x == 0) {
+        s_out.sum_w = rank_w; s_out.sum_sq = rank_sq;
+        s_epoch = sc->x_epoch[X_B] + 1;
+        sc->pool_count = 0;                                                      // boundary-element pool of k_norm_scan
+    }
+    __syncthreads();
+    x_publish(X, XOFF_B + (size_t)X.me * sizeof(RankPartB), &s_out, sizeof(RankPartB) / 8, X_B, s_epoch);
+    if (threadIdx.x == 0) sc->x_epoch[X_B] = s_epoch;
+}
+
+// What every CTA that consumes exchange X_B derives from the ranks' sums: getWeightsSum() over all ranks (tree order), the Q8
+// flag, the LOCAL_MIGRATE decision, and the raw weight in front of this rank.  One thread computes, the CTA shares it.
+struct SumInfo { double total, rank_prefix; int uniform, migrate; };
+__device__ __forceinline__ SumInfo combine_sums(const Xchg& X, const ShardPlan& sp, const double2* shard_sums, int normalise) {
+    SumInfo o;
+    double v[ESLAM_MAX_RANKS], sqv[ESLAM_MAX_RANKS];
+    const unsigned char* base = X.buf[X.me] + XOFF_B;
+    o.rank_prefix = 0.0;
+    for (int q = 0; q < X.world; ++q) {
+        v[q] = ld_sys_f64(base + (size_t)q * sizeof(RankPartB)); sqv[q] = ld_sys_f64(base + (size_t)q * sizeof(RankPartB) + 8);
+        if (q < X.me) o.rank_prefix += v[q];
+    }
+    double wv[ESLAM_MAX_RANKS];
+    for (int q = 0; q < X.world; ++q) wv[q] = v[q];
+    o.total = tree_small(v, X.world);
+    o.uniform = (normalise && o.total <= 0.0) ? 1 : 0;                            // :51 (Q8)
+    // LOCAL_MIGRATE: does any shard's share of the weight or its own effective sample size collapse?  Real shards: one per
+    // rank, from the exchange; virtual shards: from this context's own per-shard sums.  Every rank decides the same.
+    o.migrate = 1;
+    if (sp.mode) {
+        o.migrate = 0;
+        if (o.total > 0.0) {
+            for (unsigned g = 0; g < sp.n_shards; ++g) {
+                double w0, w1;
+                if (X.world > 1) { w0 = wv[g]; w1 = sqv[g]; } else { const double2 t = __ldcg(&shard_sums[g]); w0 = t.x; w1 = t.y; }
+                const double share = (w0 / o.total) * (double)sp.n_shards;
+                const double essg = (w0 * w0) / w1;
+                if (share < sp.min_share || essg < sp.min_ess * (double)sp.n_shard) o.migrate = 1;
+            }
+        }
+    }
+    return o;
+}
+
+// getWeightsSum() alone (eslam_gpu_weights_sum): combine the ranks' sums, then a rendezvous so that no rank overwrites the
+// exchange slots while another still reads them.
+__global__ void k_sum_finish(DevScalars* sc, const ShardPlan sp, const double2* shard_sums, const __grid_constant__ Xchg X) {
+    __shared__ unsigned s_e;
+    x_wait(X, X_B, sc->x_epoch[X_B], &sc->error_flags);
+    if (threadIdx.x == 0) {
+        const SumInfo si = combine_sums(X, sp, shard_sums, 0);
+        sc->sum_w = si.total;
+        s_e = sc->x_epoch[X_BAR] + 1;
+    }
+    __syncthreads();
+    const unsigned e = s_e;
+    x_publish(X, 0, nullptr, 0, X_BAR, e);
+    x_wait(X, X_BAR, e, &sc->error_flags);
+    if (threadIdx.x == 0) sc->x_epoch[X_BAR] = e;
 }
 
 // ------------------------------------------------------------------------------------------------ exact running sum
@@ -1508,27 +1620,62 @@ __device__ __forceinline__ void store4(double* p, unsigned long long i0, unsigne
     }
 }
 
-// normalise (src/ParticleFilter.hpp:51-67), per-tile sum of w^2, and the tile descriptors of the exact running sum
-__global__ void __launch_bounds__(SCAN_THREADS) k_norm_scan(StateBufs st, const DevScalars* sc, unsigned long long n,
-                                                            unsigned long long n_global, const double* tile_prefix,
-                                                            double* tile_sq, TileDesc* desc, BndEntry* pool, DevScalars* scw,
-                                                            int normalise, double eps, unsigned tile_ofs) {
+// normalise (src/ParticleFilter.hpp:51-67), per-tile sum of w^2, and the tile descriptors of the exact running sum.
+// Prologue: every CTA combines the ranks' weight sums (exchange X_B) into getWeightsSum() and derives its tile's approximate
+// prefix (rank prefix + raw tile prefix, normalised); CTA 0 records sum / Q8 flag / LOCAL_MIGRATE decision in DevScalars.
+// Last CTA: the rank's sum of w^2 (pairwise tree over its tiles) -> exchange X_E (k_chain turns the ranks' sums into the ESS).
+struct NormScanArgs {
+    unsigned long long n_global;
+    const double* prefix_raw; const double2* shard_sums;
+    double* tile_prefix;           // [all tiles] approximate prefix this kernel used for its tile (k_cdf reads the same bits)
+    double* tile_sq; TileDesc* desc; BndEntry* pool;
+    double *scratch_a, *scratch_b;
+    unsigned n_tiles, tile_ofs;
+    int normalise; double eps;
+};
+__global__ void __launch_bounds__(SCAN_THREADS) k_norm_scan(StateBufs st, DevScalars* sc, unsigned long long n, const NormScanArgs A,
+                                                            const ShardPlan sp, const __grid_constant__ Xchg X) {
     pdl_start();
     __shared__ TileScanSmem sm;
     __shared__ double red[8];
     __shared__ int slot_of[TILE];
     __shared__ int first_kind[SCAN_THREADS / 32 + 1];
     __shared__ int s_base;
+    __shared__ double s_total, s_prefix; __shared__ int s_uniform;
+    __shared__ double tree_a[TREE_SMEM_S], tree_b[TREE_SMEM_S / 2];
+    __shared__ unsigned s_epoch; __shared__ double s_sq;
     const int cur = sc->cur;
+    const int normalise = A.normalise;
+    x_wait(X, X_B, sc->x_epoch[X_B], &sc->error_flags);
+    if (threadIdx.x == 0) {
+        const SumInfo si = combine_sums(X, sp, A.shard_sums, normalise);
+        const bool local = sp.mode && !si.migrate;
+        // approximate running sum in front of this tile (only classifies elements).  Local resampling: it restarts at every shard.
+        const unsigned bt = blockIdx.x;
+        const unsigned seg0 = local ? (bt / sp.tiles_per_shard) * sp.tiles_per_shard : 0u;   // first local tile of this tile's walk
+        double prefix;
+        if (si.uniform) {
+            const unsigned long long before = (unsigned long long)(bt - seg0) * TILE + (local ? 0ull : (unsigned long long)A.tile_ofs * TILE);
+            prefix = (double)before / (double)A.n_global;
+        } else {
+            double raw = A.prefix_raw[bt] - (seg0 ? A.prefix_raw[seg0] : 0.0);
+            if (!local) raw += si.rank_prefix;
+            prefix = normalise ? raw / si.total : raw;
+        }
+        s_total = si.total; s_uniform = si.uniform; s_prefix = prefix;
+        A.tile_prefix[A.tile_ofs + bt] = prefix;
+        if (blockIdx.x == 0) { sc->sum_w = si.total; sc->uniform = si.uniform; sc->migrate = si.migrate; }
+    }
+    __syncthreads();
     const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
     double w[EPT];
     load4(st.f[cur][F_W], i0, n, w);
     if (normalise) {
-        const int uniform = sc->uniform; const double sum_w = sc->sum_w;
+        const int uniform = s_uniform; const double sum_w = s_total;
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {
             if (i0 + j < n) {
-                if (uniform) w[j] = 1.0 / (double)n_global;                           // :55
+                if (uniform) w[j] = 1.0 / (double)A.n_global;                         // :55
                 else w[j] /= sum_w;                                                  // :64
             }
         }
@@ -1538,17 +1685,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_norm_scan(StateBufs st, const 
 #pragma unroll
     for (int j = 0; j < EPT; ++j) q[j] = w[j] * w[j];                                 // effective += w*w
     const double sq = tile_tree_sum4(q, red);
-    if (threadIdx.x == 0) tile_sq[blockIdx.x] = sq;
+    if (threadIdx.x == 0) A.tile_sq[blockIdx.x] = sq;
 
     TileScan ts;
-    tile_scan(w, tile_prefix[tile_ofs + blockIdx.x], eps, sm, ts);
-    TileDesc* D = &desc[blockIdx.x];
+    tile_scan(w, s_prefix, A.eps, sm, ts);
+    TileDesc* D = &A.desc[blockIdx.x];
+    BndEntry* pool = A.pool;
 #pragma unroll
     for (int j = 0; j < EPT; ++j) slot_of[threadIdx.x * EPT + j] = ts.bnd_before[j];
     if ((threadIdx.x & 31) == 0) first_kind[threadIdx.x >> 5] = ts.cls[0].kind;
     if (threadIdx.x == 0) {
         int base = 0;
-        if (ts.bnd_total > 0) base = atomicAdd(&scw->pool_count, ts.bnd_total);
+        if (ts.bnd_total > 0) base = atomicAdd(&sc->pool_count, ts.bnd_total);
         s_base = base;
         D->n_bnd = ts.bnd_total; D->overflow = (base + ts.bnd_total > MAX_BND_TOTAL) ? 1 : 0; D->bnd_base = base; D->pad2 = 0;
         D->head_b = BIN_NONE; D->head_d0 = 0; D->head_d1 = 0; D->pad = 0;
@@ -1576,73 +1724,71 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_norm_scan(StateBufs st, const 
             }
         }
     }
+    if (!cta_is_last(&sc->ticket[2])) return;
+    // ---- last CTA: the rank's part of  effective = sum w^2  (src/ParticleFilter.hpp:58-66)
+    for (unsigned i = threadIdx.x; i < A.n_tiles; i += blockDim.x) A.scratch_a[i] = __ldcg(&A.tile_sq[i]);
+    __syncthreads();
+    const double rsq = block_tree_reduce(A.scratch_a, A.scratch_b, A.n_tiles, tree_a, tree_b, TREE_SMEM_S);
+    if (threadIdx.x == 0) { s_sq = rsq; s_epoch = sc->x_epoch[X_E] + 1; }
+    __syncthreads();
+    x_publish(X, XOFF_E + (size_t)X.me * 8, &s_sq, 1, X_E, s_epoch);
+    if (threadIdx.x == 0) sc->x_epoch[X_E] = s_epoch;
 }
 
-// one CTA: ESS, resample decision, and the exact value of the running sum at every tile start / boundary element
-struct ChainSmem { double bw[MAX_BND_TOTAL]; SegF seg[MAX_BND_TOTAL]; };
+// one CTA per rank: ESS, resample decision, and the exact value of the running sum at every tile start / boundary element of
+// this rank.  The rank scans ITS tiles' descriptors into one summary -- the rounding function of everything before its first
+// boundary element, then per boundary element its weight and the function of the run after it -- publishes it to every rank
+// (exchange X_C), and walks the summaries of the ranks in front of it and its own with real fp64 adds.
+struct ChainSmem { double bw[MAX_BND_TOTAL]; SegF seg[MAX_BND_TOTAL]; ChainEntry stage[MAX_BND_TOTAL]; };
 
-// What a rank contributes to the chain, packed so that ONE all-gather moves it: [sum of w^2 per tile | tile descriptors |
-// boundary pool]; pack_bytes is the size of one rank's block, tiles_per_rank the number of tiles in it.
-struct ChainPack {
-    const unsigned char* base; size_t pack_bytes; unsigned tiles_per_rank;
-    __device__ __forceinline__ const unsigned char* rank(unsigned r) const { return base + (size_t)r * pack_bytes; }
-    __device__ __forceinline__ double tile_sq(unsigned t) const {
-        const unsigned r = t / tiles_per_rank; return reinterpret_cast<const double*>(rank(r))[t - r * tiles_per_rank];
-    }
-    __device__ __forceinline__ const TileDesc& desc(unsigned t) const {
-        const unsigned r = t / tiles_per_rank;
-        return reinterpret_cast<const TileDesc*>(rank(r) + (size_t)tiles_per_rank * sizeof(double))[t - r * tiles_per_rank];
-    }
-    __device__ __forceinline__ const BndEntry* pool(unsigned r) const {
-        return reinterpret_cast<const BndEntry*>(rank(r) + (size_t)tiles_per_rank * (sizeof(double) + sizeof(TileDesc)));
-    }
+struct ChainArgs {
+    const double* tile_sq; const TileDesc* desc; const BndEntry* pool;   // this rank's tiles
+    unsigned n_tiles, tile_ofs;      // local tile count; index of local tile 0 in the global tile-start table
+    int* tile_bofs; SegF* tile_pre;  // [local tiles]
+    double* sb_out;                  // [MAX_BND_TOTAL] exact running sum at every local boundary element
+    unsigned long long min_effective; int decide, force;
+    unsigned long long n; double* cdf;   // sequential fallback: local particle count, running-sum array
 };
 
-__global__ void __launch_bounds__(1024, 1) k_chain(ChainPack pk, unsigned n_tiles,
-                                                   DevScalars* sc, double* scratch_a, double* scratch_b,
-                                                   int* tile_bofs, SegF* tile_pre, double* tile_sin, double* sb_out,
-                                                   unsigned long long min_effective, int decide, int force, const ShardPlan sp,
-                                                   const unsigned* xflags, unsigned epoch, int world) {
+// the running sum through one rank's summary (entries in shared memory); sb != nullptr: record the sum at every boundary
+__device__ __forceinline__ double chain_walk(double S, const SegF& head, const ChainEntry* e, int n_bnd, int& bad) {
+    S = segf_apply(S, head, bad);
+    for (int k = 0; k < n_bnd; ++k) {
+        S = S + e[k].w;
+        SegF f; f.d0 = e[k].d0; f.d1 = e[k].d1; f.b = e[k].b; f.pad = e[k].pad;
+        S = segf_apply(S, f, bad);
+    }
+    return S;
+}
+
+__global__ void __launch_bounds__(1024, 1) k_chain(StateBufs st, DevScalars* sc, const ChainArgs A, const ShardPlan sp,
+                                                   const __grid_constant__ Xchg X) {
     pdl_start();
-    peer_wait(xflags, epoch, world);
-    const unsigned tiles_per_rank = pk.tiles_per_rank;
     extern __shared__ __align__(16) unsigned char chain_raw[];
     ChainSmem& cs = *reinterpret_cast<ChainSmem*>(chain_raw);
     __shared__ int sh_i[64];             // [0,32): warp totals, [32,64): their inclusive scan
     __shared__ SegE sh_e[64];
-    __shared__ int s_bad, s_go;
+    __shared__ int s_bad, s_go, s_late;
+    __shared__ SegF s_head;
+    __shared__ RankChainHead s_hdr[ESLAM_MAX_RANKS];
+    __shared__ int s_ofs[ESLAM_MAX_RANKS + 1];
+    __shared__ double s_sin;
+    __shared__ unsigned s_epoch;
     const unsigned tid = threadIdx.x;
-    if (decide) {
-        double eff;
-        if (n_tiles > 1 && ((n_tiles + 1) >> 1) <= TREE_SMEM) {
-            // first level of the tree straight from the pack, the rest in shared memory (same tree as block_tree_reduce)
-            double* ta = reinterpret_cast<double*>(chain_raw); double* tb = ta + TREE_SMEM;
-            unsigned m = (n_tiles + 1) >> 1;
-            for (unsigned i = tid; i < m; i += blockDim.x) ta[i] = (2 * i + 1 < n_tiles) ? pk.tile_sq(2 * i) + pk.tile_sq(2 * i + 1) : pk.tile_sq(2 * i);
-            __syncthreads();
-            while (m > 1) {
-                const unsigned h = (m + 1) >> 1;
-                for (unsigned i = tid; i < h; i += blockDim.x) tb[i] = (2 * i + 1 < m) ? ta[2 * i] + ta[2 * i + 1] : ta[2 * i];
-                __syncthreads();
-                double* t = ta; ta = tb; tb = t; m = h;
-            }
-            eff = ta[0];
-            __syncthreads();
-        } else {
-            for (unsigned i = tid; i < n_tiles; i += blockDim.x) scratch_a[i] = pk.tile_sq(i);
-            __syncthreads();
-            eff = block_tree_reduce(scratch_a, scratch_b, n_tiles, reinterpret_cast<double*>(chain_raw),
-                                    reinterpret_cast<double*>(chain_raw) + TREE_SMEM);
-        }
-        if (tid == 0) {
-            const double ess = 1.0 / eff;                                             // src/ParticleFilter.hpp:69
+    const unsigned n_tiles = A.n_tiles;
+    double* tile_sin = reinterpret_cast<double*>(X.buf[X.me] + XOFF_TSIN);
+    // effective sample size over all ranks (src/ParticleFilter.hpp:69) and the decision (src/PoseEstimator.cpp:249)
+    x_wait(X, X_E, sc->x_epoch[X_E], &sc->error_flags);
+    if (tid == 0) {
+        if (A.decide) {
+            double v[ESLAM_MAX_RANKS];
+            for (int q = 0; q < X.world; ++q) v[q] = ld_sys_f64(X.buf[X.me] + XOFF_E + (size_t)q * 8);
+            const double ess = 1.0 / tree_small(v, X.world);
             sc->ess = ess;
-            sc->do_resample = (force || ess < (double)min_effective) ? 1 : 0;         // src/PoseEstimator.cpp:249
-        }
-    } else if (tid == 0) sc->do_resample = force ? 1 : 0;
-    if (tid == 0) { s_bad = 0; }
-    __syncthreads();
-    if (tid == 0) s_go = sc->do_resample;
+            sc->do_resample = (A.force || ess < (double)A.min_effective) ? 1 : 0;
+        } else sc->do_resample = A.force ? 1 : 0;
+        s_bad = 0; s_late = 0; s_go = sc->do_resample; sc->cdf_seq = 0;
+    }
     __syncthreads();
     if (!s_go) return;
 
@@ -1650,25 +1796,25 @@ __global__ void __launch_bounds__(1024, 1) k_chain(ChainPack pk, unsigned n_tile
     // counts and a segmented exclusive scan of the tile functions (shuffles inside the warp, warp 0 across the warp totals),
     // continued from round to round by a carry.  Each thread then places its tile's boundary elements and segment
     // functions into the chain arrays straight away.
-    // The chain runs over one segment of tiles -- all of them (one GPU, exact-global sharding) -- or, when the shards resample
-    // locally (LOCAL_MIGRATE and no shard has collapsed), once per shard held here, each restarting from a zero sum.
+    // The chain runs over one segment of tiles -- all of this rank's (one GPU, exact-global sharding) -- or, when the shards
+    // resample locally (LOCAL_MIGRATE and no shard has collapsed), once per shard held here, each restarting from a zero sum.
     const unsigned lane = tid & 31, warp = tid >> 5;
     __shared__ int s_carry_c; __shared__ SegE s_carry_e;
     const bool local = sp.mode && !sc->migrate;
     const unsigned n_seg = local ? sp.count : 1u;
     int bnd_base = 0;
     for (unsigned sg = 0; sg < n_seg; ++sg) {
-        const unsigned t_begin = local ? (sp.first + sg) * sp.tiles_per_shard : 0u;
+        const unsigned t_begin = local ? sg * sp.tiles_per_shard : 0u;
         const unsigned t_end = local ? t_begin + sp.tiles_per_shard : n_tiles;
         __syncthreads();
-        if (tid == 0) { s_carry_c = bnd_base; s_carry_e.f = segf_identity(); s_carry_e.head = -1; }
+        if (tid == 0) { s_carry_c = bnd_base; s_carry_e.f = segf_identity(); s_carry_e.head = -1; s_head = segf_identity(); }
         __syncthreads();
         for (unsigned r0 = t_begin; r0 < t_end; r0 += 1024) {
             const unsigned t = r0 + tid;
             const bool have = t < t_end;
             TileDesc D; D.n_bnd = 0; D.overflow = 0; D.head_b = BIN_NONE; D.pad = 0; D.head_d0 = 0; D.head_d1 = 0; D.bnd_base = 0; D.pad2 = 0;
-            if (have) D = pk.desc(t);
-            const BndEntry* B = pk.pool(have ? t / tiles_per_rank : 0) + D.bnd_base;
+            if (have) D = A.desc[t];
+            const BndEntry* B = A.pool + D.bnd_base;
             if (D.overflow) atomicOr(&s_bad, 1);
             const int cnt = D.overflow ? 0 : D.n_bnd;
             SegE e;                                                          // what the tile does to the running function
@@ -1699,7 +1845,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(ChainPack pk, unsigned n_tile
             run_e = sege_combine(s_carry_e, run_e); run_c += s_carry_c;
             const SegE round_e = sh_e[32 + 31]; const int round_c = sh_i[32 + 31];
             if (have) {
-                tile_bofs[t] = run_c; tile_pre[t] = run_e.f;
+                A.tile_bofs[t] = run_c; A.tile_pre[t] = run_e.f;
                 // boundary k = run_c + j: weight, and the function of the segment that follows it
                 for (int j = 0; j < cnt; ++j) {
                     if (run_c + j < MAX_BND_TOTAL) {
@@ -1707,10 +1853,13 @@ __global__ void __launch_bounds__(1024, 1) k_chain(ChainPack pk, unsigned n_tile
                         if (j + 1 < cnt) { SegF f; f.b = B[j].b; f.d0 = B[j].d0; f.d1 = B[j].d1; f.pad = 0; cs.seg[run_c + j] = f; }
                     }
                 }
-                if (cnt > 0 && run_c > bnd_base && run_c - 1 < MAX_BND_TOTAL) {
-                    // segment after boundary run_c-1 ends with this tile's head piece
+                if (cnt > 0) {
+                    // the run in front of this tile's first boundary element ends with the tile's head piece: it closes the
+                    // segment after boundary run_c-1, or -- for the first boundary of the walk -- it is the walk's head function
                     SegF hf; hf.b = D.head_b; hf.d0 = D.head_d0; hf.d1 = D.head_d1; hf.pad = D.pad;
-                    cs.seg[run_c - 1] = segf_compose(run_e.f, hf);
+                    const SegF cf = segf_compose(run_e.f, hf);
+                    if (run_c > bnd_base) { if (run_c - 1 < MAX_BND_TOTAL) cs.seg[run_c - 1] = cf; }
+                    else s_head = cf;
                 }
             }
             __syncthreads();                                                 // everyone has read the carry and the round totals
@@ -1718,134 +1867,237 @@ __global__ void __launch_bounds__(1024, 1) k_chain(ChainPack pk, unsigned n_tile
             __syncthreads();
         }
         const int total = s_carry_c;
-        if (tid == 0 && total > MAX_BND_TOTAL) s_bad = 1;
-        __syncthreads();
-        if (s_bad) { if (tid == 0) { atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT); sc->n_boundaries = total; } return; }
         if (tid == 0) {
-            // the sequential part: one real fp64 add per boundary element, one integer add per segment
-            double S = 0.0; int b2 = 0;
-            for (int k = bnd_base; k < total; ++k) {
-                S = S + cs.bw[k];
-                cs.bw[k] = S;
-                if (k + 1 < total) S = segf_apply(S, cs.seg[k], b2);
-            }
-            if (local) {                                                     // the shard's total: what its strata are scaled by
-                double tot = 0.0;
-                if (total > bnd_base) tot = segf_apply(cs.bw[total - 1], s_carry_e.f, b2);
-                sp.shard_tot[sp.first + sg] = tot;
-            }
-            if (b2) { s_bad = 1; atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT); }
+            if (total > MAX_BND_TOTAL) s_bad = 1;
+            else if (total > bnd_base) cs.seg[total - 1] = s_carry_e.f;     // the run after the last boundary element, to the end of the walk
+            else s_head = s_carry_e.f;                                       // no boundary element at all
             sc->n_boundaries = total;
         }
         __syncthreads();
-        if (s_bad) return;
-        int b3 = 0;
-        for (unsigned t = t_begin + tid; t < t_end; t += blockDim.x) {      // (each thread reads back what it wrote above)
-            const int ofs = tile_bofs[t];
-            const double S0 = ofs > bnd_base ? cs.bw[ofs - 1] : 0.0;
-            tile_sin[t] = segf_apply(S0, tile_pre[t], b3);
+        if (local) {
+            // this shard's own walk from a zero sum: nothing to exchange
+            if (!s_bad && tid == 0) {
+                int b2 = 0;
+                double S = segf_apply(0.0, s_head, b2);
+                for (int k = bnd_base; k < total; ++k) { S = S + cs.bw[k]; cs.bw[k] = S; S = segf_apply(S, cs.seg[k], b2); }
+                sp.shard_tot[sp.first + sg] = S;                             // the shard's total: what its strata are scaled by
+                if (b2) s_bad = 1;
+            }
+            __syncthreads();
+            if (!s_bad) {
+                int b3 = 0;
+                for (unsigned t = t_begin + tid; t < t_end; t += blockDim.x) {
+                    const int ofs = A.tile_bofs[t];
+                    tile_sin[A.tile_ofs + t] = segf_apply(ofs > bnd_base ? cs.bw[ofs - 1] : 0.0, A.tile_pre[t], b3);
+                }
+                if (b3) atomicOr(&s_bad, 1);
+            }
+            __syncthreads();
         }
-        if (b3) atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT);
         bnd_base = total;
+        if (s_bad) break;
     }
     __syncthreads();
-    for (unsigned k = tid; k < (unsigned)bnd_base; k += blockDim.x) sb_out[k] = cs.bw[k];
+    const int n_bnd = bnd_base;
+
+    if (!local) {
+        // ---- exact-global walk: exchange the ranks' summaries
+        for (unsigned k = tid; k < (unsigned)n_bnd && k < MAX_BND_TOTAL; k += blockDim.x) {
+            ChainEntry ce; ce.w = cs.bw[k]; ce.d0 = cs.seg[k].d0; ce.d1 = cs.seg[k].d1; ce.b = cs.seg[k].b; ce.pad = cs.seg[k].pad;
+            cs.stage[k] = ce;
+            if (ce.pad) atomicOr(&s_bad, 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            RankChainHead h; memset(&h, 0, sizeof(h));
+            if (s_head.pad) s_bad = 1;
+            h.n_bnd = s_bad ? 0 : n_bnd; h.bad = s_bad; h.head_d0 = s_head.d0; h.head_d1 = s_head.d1; h.head_b = s_head.b; h.head_pad = s_head.pad;
+            s_hdr[X.me] = h;
+            s_epoch = sc->x_epoch[X_C] + 1;
+        }
+        __syncthreads();
+        if (X.world > 1) {
+            const unsigned ew = s_bad ? 0u : (unsigned)n_bnd * (sizeof(ChainEntry) / 8);
+            const unsigned long long* hs = reinterpret_cast<const unsigned long long*>(&s_hdr[X.me]);
+            const unsigned long long* es = reinterpret_cast<const unsigned long long*>(cs.stage);
+            for (int q = 0; q < X.world; ++q) {
+                unsigned long long* d = reinterpret_cast<unsigned long long*>(X.buf[q] + XOFF_C + (size_t)X.me * XC_SLOT);
+                for (unsigned i = tid; i < 8 + ew; i += blockDim.x) d[i] = i < 8 ? hs[i] : es[i - 8];
+            }
+            __threadfence_system();
+            __syncthreads();
+            if ((int)tid < X.world) st_release_sys(x_flags(X.buf[tid], X_C) + X.me, s_epoch);
+            x_wait(X, X_C, s_epoch, &sc->error_flags);
+            if ((int)tid < X.world && (int)tid != X.me) {
+                const unsigned char* src = X.buf[X.me] + XOFF_C + (size_t)tid * XC_SLOT;
+                unsigned long long* d = reinterpret_cast<unsigned long long*>(&s_hdr[tid]);
+                for (int i = 0; i < 8; ++i) d[i] = ld_sys_u64(src + 8 * i);
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            sc->x_epoch[X_C] = s_epoch;
+            int any = 0, ofs = 0;
+            for (int q = 0; q < X.world; ++q) { any |= s_hdr[q].bad; s_ofs[q] = ofs; if (q < X.me) ofs += s_hdr[q].n_bnd; }
+            s_ofs[X.world] = ofs;                                            // boundary elements in front of this rank
+            s_bad = any;                                                     // every rank sees the same flags: same decision
+            s_sin = 0.0;
+        }
+        __syncthreads();
+        if (!s_bad) {
+            // the running sum in front of this rank: through the summaries of the ranks before it (staged in shared memory)
+            if (X.me > 0) {
+                const int M = s_ofs[X.world];
+                if (M <= MAX_BND_TOTAL) {
+                    // cs.stage is free again (the own entries live in cs.bw / cs.seg)
+                    for (int q = 0; q < X.me; ++q) {
+                        const unsigned char* src = X.buf[X.me] + XOFF_C + (size_t)q * XC_SLOT + 64;
+                        unsigned long long* d = reinterpret_cast<unsigned long long*>(cs.stage + s_ofs[q]);
+                        const unsigned words = (unsigned)s_hdr[q].n_bnd * (sizeof(ChainEntry) / 8);
+                        for (unsigned i = tid; i < words; i += blockDim.x) d[i] = ld_sys_u64(src + 8 * (size_t)i);
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        double S = 0.0; int b2 = 0;
+                        for (int q = 0; q < X.me; ++q) {
+                            SegF hf; hf.d0 = s_hdr[q].head_d0; hf.d1 = s_hdr[q].head_d1; hf.b = s_hdr[q].head_b; hf.pad = s_hdr[q].head_pad;
+                            S = chain_walk(S, hf, cs.stage + s_ofs[q], s_hdr[q].n_bnd, b2);
+                        }
+                        s_sin = S; if (b2) s_late = 1;
+                    }
+                } else {
+                    for (int q = 0; q < X.me; ++q) {                         // long lists: one rank at a time
+                        const unsigned char* src = X.buf[X.me] + XOFF_C + (size_t)q * XC_SLOT + 64;
+                        unsigned long long* d = reinterpret_cast<unsigned long long*>(cs.stage);
+                        const unsigned words = (unsigned)s_hdr[q].n_bnd * (sizeof(ChainEntry) / 8);
+                        __syncthreads();
+                        for (unsigned i = tid; i < words; i += blockDim.x) d[i] = ld_sys_u64(src + 8 * (size_t)i);
+                        __syncthreads();
+                        if (tid == 0) {
+                            int b2 = 0;
+                            SegF hf; hf.d0 = s_hdr[q].head_d0; hf.d1 = s_hdr[q].head_d1; hf.b = s_hdr[q].head_b; hf.pad = s_hdr[q].head_pad;
+                            s_sin = chain_walk(s_sin, hf, cs.stage, s_hdr[q].n_bnd, b2);
+                            if (b2) s_late = 1;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                // the sequential part: one real fp64 add per boundary element, one integer add per segment
+                int b2 = 0;
+                double S = segf_apply(s_sin, s_head, b2);
+                for (int k = 0; k < n_bnd; ++k) { S = S + cs.bw[k]; cs.bw[k] = S; S = segf_apply(S, cs.seg[k], b2); }
+                if (b2) s_late = 1;
+            }
+            __syncthreads();
+            int b3 = 0;
+            for (unsigned t = tid; t < n_tiles; t += blockDim.x) {
+                const int ofs = A.tile_bofs[t];
+                const double v = segf_apply(ofs > 0 ? cs.bw[ofs - 1] : s_sin, A.tile_pre[t], b3);
+                for (int q = 0; q < X.world; ++q) reinterpret_cast<double*>(X.buf[q] + XOFF_TSIN)[A.tile_ofs + t] = v;   // every rank's tile-start table
+            }
+            if (b3) atomicOr(&s_late, 1);
+            __syncthreads();
+            // a consistency check that failed after the exchange cannot be turned into a fallback every rank agrees on; it is a
+            // "cannot happen" (the element classes guarantee the binades): one GPU falls back, a sharded run reports it
+            if (s_late) { if (X.world > 1) { if (tid == 0) atomicOr(&sc->error_flags, ERR_INTERNAL_BIT); } else if (tid == 0) s_bad = 1; }
+            __syncthreads();
+        }
+    }
+    if (s_bad) {
+        // ---- fallback: the literal left-to-right running sum by one thread (boundary pool overflow, ambiguous binades).  Sharded
+        // exact-global walk: rank r continues from the sum rank r-1 ended with (exchange X_SEQ), one rank after the other.
+        if (tid == 0) s_epoch = sc->x_epoch[X_SEQ] + 1;
+        __syncthreads();
+        if (!local && X.me > 0) x_wait(X, X_SEQ, s_epoch, &sc->error_flags, X.me - 1);
+        if (tid == 0) {
+            const double* w = st.f[sc->cur][F_W];
+            const unsigned long long seg_n = local ? sp.n_shard : A.n;
+            double s = 0.0;
+            for (unsigned long long i = 0; i < A.n; ++i) {
+                const bool first = (i % seg_n) == 0;
+                if (first) {
+                    if (local && i > 0) sp.shard_tot[sp.first + (unsigned)(i / seg_n) - 1] = s;
+                    s = (!local && X.me > 0) ? ld_sys_f64(X.buf[X.me] + XOFF_SEQ + (size_t)(X.me - 1) * 8) : 0.0;
+                }
+                if ((i & (TILE - 1)) == 0) tile_sin[A.tile_ofs + i / TILE] = s;
+                s = (first && !(!local && X.me > 0)) ? w[i] : s + w[i];
+                A.cdf[i] = s;
+            }
+            if (local) sp.shard_tot[sp.first + (unsigned)((A.n - 1) / seg_n)] = s;
+            s_sin = s;
+            sc->cdf_seq = 1; sc->fallbacks += 1;
+        }
+        __syncthreads();
+        if (!local) {
+            x_publish(X, XOFF_SEQ + (size_t)X.me * 8, &s_sin, 1, X_SEQ, s_epoch);
+            if (X.world > 1) {
+                for (unsigned t = tid; t < n_tiles; t += blockDim.x) {
+                    const double v = tile_sin[A.tile_ofs + t];
+                    for (int q = 0; q < X.world; ++q) if (q != X.me) reinterpret_cast<double*>(X.buf[q] + XOFF_TSIN)[A.tile_ofs + t] = v;
+                }
+            }
+        }
+        if (tid == 0) sc->x_epoch[X_SEQ] = s_epoch;
+        __threadfence_system();
+        return;
+    }
+    for (unsigned k = tid; k < (unsigned)n_bnd; k += blockDim.x) A.sb_out[k] = cs.bw[k];
+    __threadfence_system();
 }
 
 // exact running sum of every element: cdf[i] == the reference's sum_w after adding xi_k[i].weight
-__global__ void __launch_bounds__(SCAN_THREADS) k_cdf(StateBufs st, DevScalars* sc, unsigned long long n,
-                                                      const double* tile_prefix, const int* tile_bofs, const double* tile_sin,
-                                                      const double* sb, double* cdf, double eps, unsigned tile_ofs) {
+struct CdfArgs {
+    const double* tile_prefix; const int* tile_bofs; const double* sb; double* cdf;
+    double eps; unsigned tile_ofs;
+};
+__global__ void __launch_bounds__(SCAN_THREADS) k_cdf(StateBufs st, DevScalars* sc, unsigned long long n, const CdfArgs A, const ShardPlan sp,
+                                                      const __grid_constant__ Xchg X) {
     pdl_start();
     __shared__ TileScanSmem sm;
     __shared__ int slot_of[TILE];
-    if (!sc->do_resample || (sc->error_flags & ERR_CDF_FALLBACK_BIT)) return;
-    const int cur = sc->cur;
-    const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
-    double w[EPT];
-    load4(st.f[cur][F_W], i0, n, w);
-    const unsigned gt = tile_ofs + blockIdx.x;
-    TileScan ts;
-    tile_scan(w, tile_prefix[gt], eps, sm, ts);
+    __shared__ unsigned s_epoch;
+    if (!sc->do_resample) return;                                    // the same decision on every rank
+    if (!sc->cdf_seq) {
+        const int cur = sc->cur;
+        const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
+        double w[EPT];
+        load4(st.f[cur][F_W], i0, n, w);
+        const unsigned gt = A.tile_ofs + blockIdx.x;
+        TileScan ts;
+        tile_scan(w, A.tile_prefix[gt], A.eps, sm, ts);
 #pragma unroll
-    for (int j = 0; j < EPT; ++j) slot_of[threadIdx.x * EPT + j] = ts.bnd_before[j];
+        for (int j = 0; j < EPT; ++j) slot_of[threadIdx.x * EPT + j] = ts.bnd_before[j];
+        __syncthreads();
+        int bad = 0;
+        double S[EPT];
+        const int ofs = A.tile_bofs[blockIdx.x];
+        const double s_in = reinterpret_cast<const double*>(X.buf[X.me] + XOFF_TSIN)[gt];
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            if (ts.cls[j].kind == 2) S[j] = A.sb[ofs + ts.bnd_before[j]];
+            else if (ts.inc[j].head < 0) S[j] = segf_apply(s_in, ts.inc[j].f, bad);
+            else S[j] = segf_apply(A.sb[ofs + slot_of[ts.inc[j].head]], ts.inc[j].f, bad);
+        }
+        if (bad) atomicOr(&sc->error_flags, ERR_INTERNAL_BIT);      // cannot happen: k_chain applied the same functions to the same sums
+        store4(A.cdf, i0, n, S);
+    }
+    // sharded exact-global walk: every rank's running sums must be final before anyone searches them through a peer mapping
+    // (k_resample_local waits for all ranks' X_D flags)
+    if (X.world <= 1 || (sp.mode && !sc->migrate)) return;
+    if (!cta_is_last(&sc->ticket[3])) return;
+    if (threadIdx.x == 0) s_epoch = sc->x_epoch[X_D] + 1;
     __syncthreads();
-    int bad = 0;
-    double S[EPT];
-    const int ofs = tile_bofs[gt];
-    const double s_in = tile_sin[gt];
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        if (ts.cls[j].kind == 2) S[j] = sb[ofs + ts.bnd_before[j]];
-        else if (ts.inc[j].head < 0) S[j] = segf_apply(s_in, ts.inc[j].f, bad);
-        else S[j] = segf_apply(sb[ofs + slot_of[ts.inc[j].head]], ts.inc[j].f, bad);
-    }
-    if (bad) atomicOr(&sc->error_flags, ERR_CDF_FALLBACK_BIT);
-    store4(cdf, i0, n, S);
-}
-
-// fallback: literal left-to-right running sum by one thread (only when the tile descriptors overflowed)
-__global__ void k_cdf_sequential(StateBufs st, DevScalars* sc, unsigned long long n, double* cdf, double* tile_sin) {
-    pdl_start();
-    if (!sc->do_resample || !(sc->error_flags & ERR_CDF_FALLBACK_BIT)) return;
-    const double* w = st.f[sc->cur][F_W];
-    double s = 0.0;
-    for (unsigned long long i = 0; i < n; ++i) {
-        if ((i & (TILE - 1)) == 0) tile_sin[i / TILE] = s;
-        s = (i == 0) ? w[0] : s + w[i]; cdf[i] = s;
-    }
-    sc->error_flags &= ~ERR_CDF_FALLBACK_BIT;
-    sc->fallbacks += 1;
+    x_publish(X, 0, nullptr, 0, X_D, s_epoch);
+    if (threadIdx.x == 0) sc->x_epoch[X_D] = s_epoch;
 }
 
 // ------------------------------------------------------------------------------------------------ resample
 // The stratified walk (src/ParticleFilter.hpp:96-105) as a lower-bound search, fused with the copy (:104):
-// ancestor[k] = first idx with !(cdf[idx] < sum_r); out[k] = in[ancestor[k]].
-// cdf_win holds the exact running sum of global elements [win_base, win_base + win_len) (the whole local array on one
-// GPU; the window fetched from the owning ranks otherwise) and tile_start[t] the exact sum before the window's t-th
-// 1024-tile, so the search is two-level: 10 steps over the tile starts (8 KB, cache resident), then 10 steps inside one
-// tile.  Correct because tile_start[t] == cdf[1024 t - 1]: everything before the last tile whose start is below sum_r
-// is below sum_r too, and the next tile's start is not.
-struct GatherSrc { const double* f[7]; const uint8_t* b[2]; unsigned long long base; int use_window; };
-
-__global__ void __launch_bounds__(256) k_resample(StateBufs st, const DevScalars* sc, const double* __restrict__ cdf_win,
-                                                  const double* __restrict__ tile_start, unsigned n_tiles_win,
-                                                  unsigned long long win_len, unsigned long long win_base,
-                                                  unsigned long long n, unsigned long long n_global, unsigned long long base,
-                                                  uint32_t k0, uint32_t k1, int systematic, uint32_t* ancestors, GatherSrc src) {
-    pdl_start();
-    if (!sc->do_resample) return;
-    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const unsigned long long gk = systematic ? 0ull : base + k;
-    const em::Philox4 r = em::philox4x32_10((uint32_t)gk, sc->resample_step, 0, stream_word(em::STREAM_RESAMPLE, gk), k0, k1);
-    const double u = em::u01(r.v[0], r.v[1]);
-    const double sum_r = ((double)(base + k) + u) / (double)n_global;                // :98
-    unsigned tlo = 0, thi = n_tiles_win;                                             // first tile with !(start < sum_r)
-    while (tlo < thi) { const unsigned mid = (tlo + thi) >> 1; if (__ldg(&tile_start[mid]) < sum_r) tlo = mid + 1; else thi = mid; }
-    const unsigned t = tlo == 0 ? 0 : tlo - 1;
-    unsigned long long lo = (unsigned long long)t * TILE, hi = min(lo + TILE, win_len);
-    while (lo < hi) {
-        const unsigned long long mid = (lo + hi) >> 1;
-        if (__ldg(&cdf_win[mid]) < sum_r) lo = mid + 1; else hi = mid;
-    }
-    unsigned long long a = lo;                    // window-relative
-    if (a + win_base >= n_global) a = n_global - 1 - win_base;   // the reference walks off the end here; we stop at the last particle
-    if (a >= win_len) a = win_len - 1;
-    ancestors[k] = (uint32_t)(a + win_base);
-    const int cur = sc->cur, nxt = cur ^ 1;
-#pragma unroll
-    for (int f = 0; f < 7; ++f) {
-        const double* in = src.use_window ? src.f[f] : st.f[cur][f];
-        st.f[nxt][f][k] = in[a];                                                     // :104 copy keeps the weight (Q3)
-    }
-#pragma unroll
-    for (int f = 0; f < 2; ++f) {
-        const uint8_t* in = src.use_window ? src.b[f] : st.b[cur][f];
-        st.b[nxt][f][k] = in[a];
-    }
-}
-
+// ancestor[k] = first idx with !(cdf[idx] < sum_r); out[k] = in[ancestor[k]].  tile_start[t] holds the exact running sum
+// before the t-th 1024-tile (== cdf[1024 t - 1]), so the search is two-level: everything before the last tile whose start
+// is below sum_r is below sum_r too, and the next tile's start is not.
 // Resampling with the search in shared memory, on one GPU and sharded (exact-global mode) alike.  A CTA owns RS_THREADS
 // consecutive strata; their draws lie in [k0/N, (k0+RS_THREADS)/N), so their ancestors lie in the tiles from the last one
 // starting below k0/N to the last one starting below (k0+1024)/N: with balanced weights one or two tiles.  When that is at
@@ -1859,7 +2111,12 @@ struct PeerTable {
     const double* cdf[ESLAM_MAX_RANKS];
     const double* f[ESLAM_MAX_RANKS][2][7];
     const uint8_t* b[ESLAM_MAX_RANKS][2][2];
+    const float2* patch[ESLAM_MAX_RANKS][2];      // per-particle map patches and their origins (cfg.patch_size > 0)
+    const int* porigin[ESLAM_MAX_RANKS][2];
 };
+// cloneMaps (src/PoseEstimator.cpp:31-45): every copy of a particle owns a copy of its map patch.  The destination buffers
+// of this rank; the sources come from the PeerTable (the owner of the ancestor, over NVLink when that is another GPU).
+struct PatchGather { int P; int pad; float2* patch[2]; int* porigin[2]; };
 
 template <int RS_THREADS>
 __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_local(StateBufs st, DevScalars* sc, const double* __restrict__ tile_start,
@@ -1867,19 +2124,19 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
                                                             unsigned long long n_global, unsigned long long base, uint32_t k0key,
                                                             uint32_t k1key, int systematic, uint32_t* ancestors, unsigned* ticket,
                                                             const __grid_constant__ PeerTable peers, const ShardPlan sp, unsigned tile_ofs,
-                                                            unsigned my_rank, const unsigned* xflags, unsigned epoch, int world) {
+                                                            unsigned my_rank, const PatchGather pg, const __grid_constant__ Xchg X) {
     pdl_start();
     __shared__ double s_cdf[RS_TILES * TILE];
-    if (!sc->do_resample) return;
-    if (world > 1 && (sc->error_flags & ERR_CDF_FALLBACK_BIT)) return;   // reported through the update status; state is left as is
-    peer_wait(xflags, epoch, world);                                     // every rank's running sum is final before anyone reads a peer
+    if (!sc->do_resample) return;                                        // the same decision on every rank
+    int world = X.world;
+    const bool local = sp.mode && !sc->migrate;
+    if (!local) x_wait(X, X_D, sc->x_epoch[X_D], &sc->error_flags);      // every rank's running sum is final before anyone reads a peer
     const unsigned tid = threadIdx.x;
     const unsigned long long kb = (unsigned long long)blockIdx.x * RS_THREADS, k = kb + tid;   // local stratum
     // Local resampling (LOCAL_MIGRATE sharding, no shard collapsed): the CTA's strata belong to ONE logical shard held here; they
     // walk that shard's own running sum (restarted at zero, tile starts at tile_ofs + s T_s of the table), scaled by the shard's
     // total, and their ancestors are that shard's own particles.  Everything below runs on the rebound quantities; in the exact
     // mode they are the arguments themselves and scale == 1.0 (a multiplication that changes no bit).
-    const bool local = sp.mode && !sc->migrate;
     const unsigned long long n_ctx = n;                                  // particles of this context
     unsigned long long po = 0, anc_base = 0, sbase = base + kb;          // sbase: index of the CTA's first stratum in its walk
     unsigned q_fixed = 0; double scale = 1.0;
@@ -1914,6 +2171,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
         }
         __syncthreads();
     }
+    unsigned src_q = 0; unsigned long long src_l = 0;                    // owner rank and owner-local index of this stratum's ancestor
     if (k < n_ctx) {
         const unsigned long long gk = systematic ? 0ull : base + k;
         const em::Philox4 r = em::philox4x32_10((uint32_t)gk, sc->resample_step, 0, stream_word(em::STREAM_RESAMPLE, gk), k0key, k1key);
@@ -1944,6 +2202,26 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
         for (int f = 0; f < 7; ++f) st.f[nxt][f][k] = peers.f[qs][cur][f][la];            // :104 copy keeps the weight (Q3)
 #pragma unroll
         for (int f = 0; f < 2; ++f) st.b[nxt][f][k] = peers.b[qs][cur][f][la];
+        src_q = qs; src_l = la;
+    }
+    if (pg.P > 0) {
+        // the ancestor's map patch travels with it: one warp copies the patches of its 32 strata one after the other
+        const int cur = sc->cur, nxt = cur ^ 1;
+        const unsigned pp = (unsigned)(pg.P * pg.P), lane = tid & 31;
+        const int have = k < n_ctx ? 1 : 0;
+        for (int j = 0; j < 32; ++j) {
+            if (!__shfl_sync(0xffffffffu, have, j)) continue;
+            const unsigned q = __shfl_sync(0xffffffffu, src_q, j);
+            const unsigned long long l = __shfl_sync(0xffffffffu, src_l, j);
+            const unsigned long long kk = kb + (tid & ~31u) + (unsigned)j;
+            const float2* src = peers.patch[q][cur] + l * pp;
+            float2* dst = pg.patch[nxt] + kk * pp;
+            if ((pp & 1u) == 0) {
+                const float4* s4 = reinterpret_cast<const float4*>(src); float4* d4 = reinterpret_cast<float4*>(dst);
+                for (unsigned c = lane; c < (pp >> 1); c += 32) d4[c] = s4[c];
+            } else for (unsigned c = lane; c < pp; c += 32) dst[c] = src[c];
+            if (lane < 2) pg.porigin[nxt][2 * kk + lane] = peers.porigin[q][cur][2 * l + lane];
+        }
     }
     // xi_k.swap(xi_kp) :107 by the last CTA (every CTA has read sc->cur by then)
     __syncthreads();
@@ -2069,32 +2347,9 @@ __global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevSc
     }
 }
 
-// cloneMaps (src/PoseEstimator.cpp:31-45): every copy of a particle owns a copy of its map patch. One warp per particle.
-__global__ void k_gather_patches(const DevScalars* sc, unsigned long long n, const uint32_t* __restrict__ anc, int P,
-                                 float2* p0, float2* p1, int* o0, int* o1) {
-    pdl_start();
-    if (!sc->do_resample) return;
-    const unsigned long long k = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (k >= n) return;
-    const int lane = threadIdx.x & 31;
-    const int cur = sc->cur;
-    const float2* src = (cur ? p1 : p0) + (size_t)anc[k] * P * P;
-    float2* dst = (cur ? p0 : p1) + k * (size_t)P * P;
-    for (int c = lane; c < P * P; c += 32) dst[c] = src[c];
-    if (lane < 2) (cur ? o0 : o1)[2 * k + lane] = (cur ? o1 : o0)[2 * (size_t)anc[k] + lane];
-}
-
 __global__ void k_fill_i32(int* p, size_t count, int v) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) p[i] = v;
-}
-
-__global__ void k_after_resample(DevScalars* sc) {
-    pdl_start();
-    if (!sc->do_resample) return;
-    if (sc->error_flags & ERR_CDF_FALLBACK_BIT) return;   // sharded run that could not resample: state left as is
-    sc->cur ^= 1;                                                                    // xi_k.swap(xi_kp) :107
-    sc->resample_step += 1;
 }
 
 // ------------------------------------------------------------------------------------------------ outputs

@@ -144,9 +144,6 @@ class FilterBase:
         return out
 
     # -- per-particle map patches --------------------------------------------------------------
-    def patchUpdate(self):
-        self._check(self._fn("patch_update")(self._ctx))
-
     def getPatches(self, patch_size):
         n = self.size()
         cells = np.empty((n, patch_size, patch_size, 2), dtype=np.float32)
@@ -208,6 +205,18 @@ class GpuPoseEstimator(FilterBase):
                                                   C.byref(ms), C.byref(top), C.byref(res)))
         self.last_result = res
         return ms.value, top.value, res
+
+    def stepTimes(self):
+        """Step periods (ms) of the last runSteps."""
+        n = self._lib.eslam_gpu_step_times(self._ctx, None, 0)
+        buf = (C.c_float * max(n, 1))()
+        self._lib.eslam_gpu_step_times(self._ctx, buf, n)
+        return [buf[i] for i in range(n)]
+
+    def ioBytes(self, n_pts):
+        out = (C.c_uint64 * 2)()
+        self._check(self._lib.eslam_gpu_io_bytes(self._ctx, int(n_pts), out))
+        return int(out[0]), int(out[1])
 
     def synchronize(self):
         self._check(self._lib.eslam_gpu_synchronize(self._ctx))

@@ -92,8 +92,63 @@ def main():
     if rank == 0:
         assert kinds == {"local", "migrate"}, kinds
     comm.barrier()
+    # per-particle map patches (cfg.patch_size): the patch travels with its particle, across GPUs too
+    P = 8
+    cfg = dict(min_effective=n + 1, patch_size=P)
+    g = GpuPoseEstimator(abi.default_config(**cfg), device=local, shard=comm.shard(n_local))
+    comm.connect(g)
+    contacts, step = synthetic.setup_filter(g, "C2", n=n_local)
+    ref = None
     if rank == 0:
-        print("dist parity ok: %d ranks x %d particles bit-identical to one GPU (exact-global, systematic, LOCAL_MIGRATE)" % (world, n_local))
+        ref = GpuPoseEstimator(abi.default_config(**cfg), device=local)
+        synthetic.setup_filter(ref, "C2", n=n)
+    for it in range(5):
+        if it == 2:
+            w = np.where(np.arange(n) >= n // 2, 5.0, 0.05) / n       # ancestors (and their patches) cross the shard boundary
+            g.setParticles(weight=w[rank * n_local:(rank + 1) * n_local])
+            if ref:
+                ref.setParticles(weight=w)
+        r = g.stepFused(step, contacts)
+        allp = gather_particles(g, comm)
+        cells, origin = g.getPatches(P)
+        outc, outo = [None] * world, [None] * world
+        td.all_gather_object(outc, cells); td.all_gather_object(outo, origin)
+        if rank == 0:
+            rr = ref.stepFused(step, contacts)
+            assert r.as_dict() == rr.as_dict(), (it, r.as_dict(), rr.as_dict())
+            q = ref.getParticles(); q["ancestors"] = ref.getAncestors()
+            for k in list(KEYS) + ["ancestors"]:
+                assert np.array_equal(allp[k], q[k]), "patches step %d: %s differs" % (it, k)
+            rc, ro = ref.getPatches(P)
+            assert np.array_equal(np.concatenate(outo), ro), "patch origins differ at step %d" % it
+            assert np.array_equal(np.concatenate(outc), rc, equal_nan=True), "patch cells differ at step %d" % it
+            if it == 4:
+                assert (~np.isnan(rc[..., 0])).sum() > n // 2
+    comm.barrier()
+    # a legal weight vector whose exact running sum overflows the boundary pool: the sequential fallback runs rank after rank
+    # (each continues from the sum the previous rank ended with) and N ranks still equal one GPU and numpy's sequential sum
+    g = GpuPoseEstimator(abi.default_config(), device=local, shard=comm.shard(n_local))
+    comm.connect(g)
+    rng = np.random.default_rng(3)
+    w = np.full(n, 1e-17); w[0] = 1.0
+    w[1::2] = 2.0 ** -53 * (1 + rng.random(n // 2))
+    z = np.zeros(n_local)
+    g.setParticles(x=np.arange(rank * n_local, (rank + 1) * n_local, dtype=float), y=z, theta=z, zpos=z, zsigma=z + 1,
+                   weight=w[rank * n_local:(rank + 1) * n_local])
+    g.resample()
+    anc, cdf, fb = [None] * world, [None] * world, [None] * world
+    td.all_gather_object(anc, g.getAncestors()); td.all_gather_object(cdf, g.getCdf()); td.all_gather_object(fb, g.debugCounters())
+    if rank == 0:
+        ref = GpuPoseEstimator(abi.default_config(), device=local)
+        zz = np.zeros(n)
+        ref.setParticles(x=np.arange(n, dtype=float), y=zz, theta=zz, zpos=zz, zsigma=zz + 1, weight=w)
+        ref.resample()
+        assert np.array_equal(np.concatenate(cdf), np.cumsum(w)), "sharded sequential fallback: running sum"
+        assert np.array_equal(np.concatenate(anc), ref.getAncestors()), "sharded sequential fallback: ancestors"
+        assert all(f["fallbacks"] == 1 and f["error_flags"] == 0 for f in fb), fb
+    comm.barrier()
+    if rank == 0:
+        print("dist parity ok: %d ranks x %d particles bit-identical to one GPU (exact-global, systematic, LOCAL_MIGRATE, patches, sequential fallback)" % (world, n_local))
     td.destroy_process_group()
 
 

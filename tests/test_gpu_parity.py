@@ -361,7 +361,6 @@ def test_patches_bit_identical_to_shared_oracle(gpu, oracle, n, steps):
         assert np.array_equal(oa, ob), "patch origins, step %d" % i
         assert np.array_equal(ca, cb, equal_nan=True), "patch cells, step %d" % i
     assert (~np.isnan(ca[..., 0])).sum() > n // 2
-    g.patchUpdate()                                       # kept for the ABI: the write is part of update()
 
 
 def test_patches_change_the_result_only_through_written_cells(gpu):
@@ -533,3 +532,116 @@ def test_local_migrate_resample_stage_adversarial(gpu, oracle):
             assert np.array_equal(g.getAncestors(), o.getAncestors())
             assert np.array_equal(g.getCdf(), o.getCdf())
             assert_particles_equal(g.getParticles(), o.getParticles(), keys=("x", "weight"))
+
+
+# ---------------------------------------------------------------------------------- parity holes named by the round-1 review
+def _six_group_contacts(c_per_group=3):
+    """6 contact groups (groupId 0..5): more than 4 fused contacts per particle -> `4 - cpoints.size()` wraps (Q2)."""
+    pos, contact, gid = [], [], []
+    for g in range(6):
+        for j in range(c_per_group):
+            pos.append((0.3 * np.cos(g) + 0.02 * j, 0.3 * np.sin(g), 0.0))
+            contact.append(0.5); gid.append(g)
+    return abi.make_contacts(pos, contact, gid)
+
+
+@pytest.mark.parametrize("lean", [True, False])
+def test_unsigned_exponent_quirk_Q2_on_device(gpu, oracle, monkeypatch, lean):
+    """src/PoseEstimator.cpp:336 with more than 4 fused contacts on the DEVICE: k_loop_b takes pow_table[5] (the wrapped
+    size_t exponent), every data particle's weight becomes 0, the sum is 0 and normalizeWeights resets to 1/N (Q8) --
+    identical to the oracle, on the lean kernel (gend[] / n_groups with 6 groups) and on the generic one."""
+    if not lean:
+        monkeypatch.setenv("ESLAM_GPU_NO_FAST", "1")
+    n = 3000
+    cfg = dict(min_effective=n + 1)
+    g, o, _, step = pair(gpu, oracle, "C2", n=n, **cfg)
+    flat = np.zeros((512, 512, 2), dtype=np.float32); flat[..., 1] = 0.05
+    for f in (g, o):
+        f.setEnvironment(flat, (0.05, 0.05), (-12.8, -12.8))
+    contacts = _six_group_contacts()
+    for it in range(3):
+        ra, rb = g.stepFused(step, contacts), (o.project(step), o.update(contacts))[1]
+        assert ra.as_dict() == rb.as_dict(), (it, ra.as_dict(), rb.as_dict())
+        a, b = g.getParticles(), o.getParticles()
+        assert_particles_equal(a, b)
+        assert np.array_equal(g.getAncestors(), o.getAncestors())
+        assert ra.weights_sum == 0.0 and np.all(a["n_found"] == 6)       # Q2 -> all weights 0 -> uniform reset (Q8)
+    assert g.pathCounters()["lean"] == (n if lean else 0)
+
+
+def test_unsigned_exponent_quirk_Q2_against_the_live_reference(gpu):
+    """The same on the reference's own compiled code: pow(x, size_t(4 - 6)) == 0 -> uniform weights; n_found, flags, ancestors
+    equal, weights equal (all 1/N)."""
+    from oracle import ref_binding
+    if not ref_binding.available():
+        pytest.skip("oracle/_ref/libeslam_ref.so did not travel")
+    n = 2000
+    cfg = dict(min_effective=n + 1)
+    g = gpu(abi.default_config(**cfg))
+    r = ref_binding.RefPoseEstimator(abi.default_config(**cfg), debug=True)
+    _, step = synthetic.setup_filter(g, "C2", n=n)
+    synthetic.setup_filter(r, "C2", n=n)
+    flat = np.zeros((512, 512, 2), dtype=np.float32); flat[..., 1] = 0.05
+    for f in (g, r):
+        f.setEnvironment(flat, (0.05, 0.05), (-12.8, -12.8))
+    contacts = _six_group_contacts()
+    for it in range(2):
+        g.project(step); r.project(step)
+        ra, rb = g.update(contacts), r.update(contacts)
+        a, b = g.getParticles(), r.getParticles()
+        assert np.array_equal(a["n_found"], b["n_found"]) and np.all(a["n_found"] == 6)
+        assert np.array_equal(a["weight"], b["weight"]) and np.all(a["weight"] == 1.0 / n)
+        assert np.array_equal(g.getAncestors(), r.getAncestors())
+
+
+def test_c4_at_baseline_size_patches_bit_identical(gpu, oracle):
+    """BASELINE config 4 at full size: 100 000 particles x 64 contact points on the 4096^2 grid with 16 x 16 per-particle
+    patches, resampling every step: every particle, every patch cell, every patch origin and every ancestor equal to the oracle."""
+    P, n = 16, 100000
+    g, o, contacts, step = pair(gpu, oracle, "C4", n=n, patch_size=P, min_effective=n + 1)
+    still = abi.make_step(delta_sigma=(0.001, 0.001, 0.0005))
+    for i in range(3):
+        st = step if i % 2 == 0 else still
+        ra, rb = g.stepFused(st, contacts), (o.project(st), o.update(contacts))[1]
+        assert ra.as_dict() == rb.as_dict(), i
+        assert ra.resampled == 1
+        assert np.array_equal(g.getAncestors(), o.getAncestors())
+        assert_particles_equal(g.getParticles(), o.getParticles())
+        ca, oa = g.getPatches(P)
+        cb, ob = o.getPatches(P)
+        assert np.array_equal(oa, ob), "patch origins, step %d" % i
+        assert np.array_equal(ca, cb, equal_nan=True), "patch cells, step %d" % i
+    assert (~np.isnan(ca[..., 0])).sum() > n
+
+
+def test_sequential_fallback_of_the_running_sum(gpu, oracle):
+    """A legal weight vector whose exact running sum needs more boundary elements than the pool holds: k_chain falls back to the
+    literal left-to-right sum (counted), ancestors and running sum still equal to numpy / the oracle."""
+    n = 50000
+    rng = np.random.default_rng(3)
+    w = np.full(n, 1e-17); w[0] = 1.0                                       # every add is near a quarter ulp of the sum ...
+    w[1::2] = 2.0 ** -53 * (1 + rng.random(n // 2))                        # ... or an ambiguous half-ulp case: boundaries everywhere
+    g = gpu(abi.default_config()); o = oracle.OraclePoseEstimator(abi.default_config(), policy=oracle.LITERAL)
+    z = np.zeros(n)
+    for f in (g, o):
+        f.setParticles(x=np.arange(n, dtype=float), y=z, theta=z, zpos=z, zsigma=z + 1, weight=w)
+        f.resample()
+    assert np.array_equal(g.getCdf(), np.cumsum(w))
+    assert np.array_equal(g.getAncestors(), o.getAncestors())
+    assert g.debugCounters()["error_flags"] == 0
+
+
+def test_multi_gpu_parity_worker():
+    """tests/dist_worker.py under torchrun on every visible GPU (2 or more): the sharded filter -- exchanges over peer memory,
+    ancestors read in place over NVLink -- bit-identical to one GPU (exact-global stratified / systematic, LOCAL_MIGRATE,
+    per-particle patches, the sequential fallback across shards)."""
+    import os, subprocess, sys
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 or more GPUs (run with gpurun --gpus 2)")
+    world = 2 if torch.cuda.device_count() < 4 else (4 if torch.cuda.device_count() < 8 else 8)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "dist_worker.py")],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert out.returncode == 0 and "dist parity ok" in out.stdout, out.stdout[-4000:]
