@@ -224,9 +224,10 @@ __device__ __forceinline__ void x_publish(const Xchg& X, size_t off, const void*
         unsigned long long* d = reinterpret_cast<unsigned long long*>(X.buf[q] + off);
         for (unsigned i = threadIdx.x; i < words; i += blockDim.x) d[i] = s[i];
     }
+    if (X.world <= 1) return;                              // one GPU: the kernel boundary orders producer and consumers
     __threadfence_system();
     __syncthreads();
-    if (X.world > 1 && (int)threadIdx.x < X.world) st_release_sys(x_flags(X.buf[threadIdx.x], x) + X.me, epoch);
+    if ((int)threadIdx.x < X.world) st_release_sys(x_flags(X.buf[threadIdx.x], x) + X.me, epoch);
 }
 // Consumer side, all threads of a CTA: wait until every rank's (or, with only >= 0, that one rank's) flag of exchange x has
 // reached `epoch`.  A rank that never arrives (a dead peer) would hang the GPU: after ~4 s the wait gives up and flags the step.
@@ -380,6 +381,33 @@ __device__ __forceinline__ double tile_tree_sum4(const double v[EPT], double* re
     r += __shfl_xor_sync(0xffffffffu, r, 2);
     r += __shfl_xor_sync(0xffffffffu, r, 4);
     return r;
+}
+
+// Pairwise tree over n per-tile values in global memory (written by other CTAs: read through L2), continuing the per-tile
+// trees; all threads of ONE CTA of SCAN_THREADS threads.  The index-aligned tree over 1024 consecutive leaves is what
+// tile_tree_sum4 computes from registers (a missing right operand passes the left one through == adding +0.0, exact), so a
+// rank's 2^k <= 1024 tiles take one call; more tiles go 1024 at a time and their roots through the same tree once more.
+// Same tree, same bits as block_tree_reduce.  red: >= 8 doubles of shared memory, scratch: >= ceil(n/1024) doubles.
+__device__ __forceinline__ double rank_tree_sum(const double* vals, unsigned stride_doubles, unsigned n, double* red, double* scratch) {
+    auto chunk = [&](const double* base, unsigned stride, unsigned count) -> double {
+        double v[EPT];
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) { const unsigned i = threadIdx.x * EPT + j; v[j] = i < count ? __ldcg(base + (size_t)i * stride) : 0.0; }
+        return tile_tree_sum4(v, red);
+    };
+    const double* src = vals; unsigned stride = stride_doubles, count = n;
+    while (count > TILE) {                                 // 1024 values at a time; the roots go through the same tree again
+        const unsigned chunks = (count + TILE - 1) / TILE;
+        for (unsigned c = 0; c < chunks; ++c) {
+            const double r = chunk(src + (size_t)c * TILE * stride, stride, min((unsigned)TILE, count - c * TILE));
+            __syncthreads();                               // everyone has read chunk c (scratch[c] may be one of its inputs)
+            if (threadIdx.x == 0) scratch[c] = r;
+        }
+        __threadfence_block();
+        __syncthreads();
+        src = scratch; stride = 1; count = chunks;
+    }
+    return chunk(src, stride, count);
 }
 
 // ------------------------------------------------------------------------------------------------ map lookup
@@ -1184,7 +1212,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_part(StateBufs st, DevSca
     __shared__ double red[8];
     __shared__ double redm[8];
     __shared__ unsigned redu[16];
-    __shared__ double tree_a[TREE_SMEM_S], tree_b[TREE_SMEM_S / 2];
     __shared__ unsigned long long redull[16];
     __shared__ RankPartA s_out;
     __shared__ unsigned s_epoch;
@@ -1226,14 +1253,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_part(StateBufs st, DevSca
     for (int b = threadIdx.x; b < MAX_BINS; b += blockDim.x) { A.bin_count[b] = 0; A.bin_next[b] = 0; }   // for the next update's lean path
     double rmx = 0; unsigned long long rcnt = 0, rpts = 0;
     for (unsigned i = threadIdx.x; i < A.n_tiles; i += blockDim.x) {
-        TilePartA p;                                                     // 24 bytes, written by another CTA: read through L2
-        { const double* pp = reinterpret_cast<const double*>(A.part + i); const uint2 cp = __ldcg(reinterpret_cast<const uint2*>(pp + 2));
-          p.sum_pw = __ldcg(pp); p.max_w = __ldcg(pp + 1); p.cnt = cp.x; p.pts = cp.y; }
-        A.scratch_a[i] = p.sum_pw;
-        rmx = fmax(rmx, p.max_w); rcnt += p.cnt; rpts += p.pts;
+        const double* pp = reinterpret_cast<const double*>(A.part + i);   // 24 bytes, written by another CTA: read through L2
+        const uint2 cp = __ldcg(reinterpret_cast<const uint2*>(pp + 2));
+        rmx = fmax(rmx, __ldcg(pp + 1)); rcnt += cp.x; rpts += cp.y;
     }
-    __syncthreads();
-    const double sum_pw = block_tree_reduce(A.scratch_a, A.scratch_b, A.n_tiles, tree_a, tree_b, TREE_SMEM_S);
+    const double sum_pw = rank_tree_sum(reinterpret_cast<const double*>(A.part), sizeof(TilePartA) / 8, A.n_tiles, red, A.scratch_a);
     rmx = warp_max(rmx);
     for (int o = 1; o < 32; o <<= 1) { rcnt += __shfl_xor_sync(0xffffffffu, rcnt, o); rpts += __shfl_xor_sync(0xffffffffu, rpts, o); }
     __syncthreads();
@@ -1285,11 +1309,32 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, DevScalar
     pdl_start();
     __shared__ double red[8];
     __shared__ double s_pow[6];
-    __shared__ double tree_a[TREE_SMEM_S], tree_b[TREE_SMEM_S / 2];
     __shared__ double sh[64];
     __shared__ RankPartB s_out;
     __shared__ unsigned s_epoch;
     const int cur = sc->cur;
+    // this tile's weights (and mprob, cpoints.size()) are on their way while the CTA waits for the ranks' loop-A partials
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
+    double w[EPT], mp[EPT]; unsigned nfv[EPT];
+    double* W = st.f[cur][F_W];
+    const bool full = i0 + EPT <= n;
+    if (full) {
+        const double2 a = *reinterpret_cast<const double2*>(W + i0), b = *reinterpret_cast<const double2*>(W + i0 + 2);
+        w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
+        if (APPLY) {
+            const double2 ma = *reinterpret_cast<const double2*>(st.f[cur][F_MP] + i0), mb = *reinterpret_cast<const double2*>(st.f[cur][F_MP] + i0 + 2);
+            const uchar4 nf = *reinterpret_cast<const uchar4*>(st.b[cur][B_NF] + i0);
+            mp[0] = ma.x; mp[1] = ma.y; mp[2] = mb.x; mp[3] = mb.y;
+            nfv[0] = nf.x; nfv[1] = nf.y; nfv[2] = nf.z; nfv[3] = nf.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            const bool in = i0 + j < n;
+            w[j] = in ? W[i0 + j] : 0.0;
+            if (APPLY) { mp[j] = in ? st.f[cur][F_MP][i0 + j] : 0.0; nfv[j] = in ? st.b[cur][B_NF][i0 + j] : 0u; }
+        }
+    }
     if (APPLY) {
         x_wait(X, X_A, sc->x_epoch[X_A], &sc->error_flags);
         if (threadIdx.x == 0) {
@@ -1313,36 +1358,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, DevScalar
             }
         }
         __syncthreads();
-    }
-    const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
-    double w[EPT];
-    double* W = st.f[cur][F_W];
-    if (i0 + EPT <= n) {
-        const double2 a = *reinterpret_cast<const double2*>(W + i0), b = *reinterpret_cast<const double2*>(W + i0 + 2);
-        w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
-        if (APPLY) {
-            const double2 ma = *reinterpret_cast<const double2*>(st.f[cur][F_MP] + i0), mb = *reinterpret_cast<const double2*>(st.f[cur][F_MP] + i0 + 2);
-            const uchar4 nf = *reinterpret_cast<const uchar4*>(st.b[cur][B_NF] + i0);
-            const double mp[EPT] = {ma.x, ma.y, mb.x, mb.y};
-            const unsigned nfv[EPT] = {nf.x, nf.y, nf.z, nf.w};
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) { const double factor = mp[j] * s_pow[nfv[j] > 4 ? 5 : nfv[j]]; w[j] *= factor; }   // Q1: second application
+        for (int j = 0; j < EPT; ++j) { const double factor = mp[j] * s_pow[nfv[j] > 4 ? 5 : nfv[j]]; w[j] *= factor; }   // Q1: second application
+        if (full) {
             *reinterpret_cast<double2*>(W + i0) = make_double2(w[0], w[1]);
             *reinterpret_cast<double2*>(W + i0 + 2) = make_double2(w[2], w[3]);
-        }
-    } else {
+        } else {
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-            w[j] = 0.0;
-            if (i0 + j < n) {
-                w[j] = W[i0 + j];
-                if (APPLY) {
-                    const unsigned nf = st.b[cur][B_NF][i0 + j];
-                    const double factor = st.f[cur][F_MP][i0 + j] * s_pow[nf > 4 ? 5 : nf];
-                    w[j] *= factor;
-                    W[i0 + j] = w[j];
-                }
-            }
+            for (int j = 0; j < EPT; ++j) if (i0 + j < n) W[i0 + j] = w[j];
         }
     }
     const double s = tile_tree_sum4(w, red);
@@ -1354,23 +1377,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, DevScalar
     if (!cta_is_last(&sc->ticket[1])) return;
     // ---- last CTA: getWeightsSum (src/ParticleFilter.hpp:34-39) of this rank's particles
     const unsigned T = A.n_tiles;
-    for (unsigned i = threadIdx.x; i < T; i += blockDim.x) A.scratch_a[i] = __ldcg(&A.tile_sum[i]).x;
-    __syncthreads();
-    const double rank_w = block_tree_reduce(A.scratch_a, A.scratch_b, T, tree_a, tree_b, TREE_SMEM_S);
+    const double rank_w = rank_tree_sum(reinterpret_cast<const double*>(A.tile_sum), 2, T, red, A.scratch_a);
     double rank_sq = 0.0;
     if (sp.mode) {
         // LOCAL_MIGRATE: per logical shard held here the pairwise trees over its tiles' sums of w and of w^2
         for (unsigned g = 0; g < sp.count; ++g) {
-            const double2* src = A.tile_sum + (size_t)g * sp.tiles_per_shard;
-            double wq[2];
-            for (int c = 0; c < 2; ++c) {
-                __syncthreads();
-                for (unsigned i = threadIdx.x; i < sp.tiles_per_shard; i += blockDim.x) { const double2 v = __ldcg(&src[i]); A.scratch_a[i] = c ? v.y : v.x; }
-                __syncthreads();
-                wq[c] = block_tree_reduce(A.scratch_a, A.scratch_b, sp.tiles_per_shard, tree_a, tree_b, TREE_SMEM_S);
-            }
-            if (threadIdx.x == 0) A.shard_sums[g] = make_double2(wq[0], wq[1]);
-            rank_sq = wq[1];                                          // real shards: the rank is one shard
+            const double* src = reinterpret_cast<const double*>(A.tile_sum + (size_t)g * sp.tiles_per_shard);
+            const double w0 = rank_tree_sum(src, 2, sp.tiles_per_shard, red, A.scratch_a);
+            __syncthreads();
+            const double w1 = rank_tree_sum(src + 1, 2, sp.tiles_per_shard, red, A.scratch_a);
+            __syncthreads();
+            if (threadIdx.x == 0) A.shard_sums[g] = make_double2(w0, w1);
+            rank_sq = w1;                                             // real shards: the rank is one shard
         }
     }
     // raw exclusive scan of the tile sums: rounds of blockDim tiles, one per thread, a carry from round to round
@@ -1411,7 +1429,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, DevScalar
 // What every CTA that consumes exchange X_B derives from the ranks' sums: getWeightsSum() over all ranks (tree order), the Q8
 // flag, the LOCAL_MIGRATE decision, and the raw weight in front of this rank.  One thread computes, the CTA shares it.
 struct SumInfo { double total, rank_prefix; int uniform, migrate; };
-__device__ __forceinline__ SumInfo combine_sums(const Xchg& X, const ShardPlan& sp, const double2* shard_sums, int normalise) {
+__device__ __noinline__ SumInfo combine_sums(const Xchg& X, const ShardPlan& sp, const double2* shard_sums, int normalise) {
     SumInfo o;
     double v[ESLAM_MAX_RANKS], sqv[ESLAM_MAX_RANKS];
     const unsigned char* base = X.buf[X.me] + XOFF_B;
@@ -1633,7 +1651,7 @@ struct NormScanArgs {
     unsigned n_tiles, tile_ofs;
     int normalise; double eps;
 };
-__global__ void __launch_bounds__(SCAN_THREADS) k_norm_scan(StateBufs st, DevScalars* sc, unsigned long long n, const NormScanArgs A,
+__global__ void __launch_bounds__(SCAN_THREADS, 4) k_norm_scan(StateBufs st, DevScalars* sc, unsigned long long n, const NormScanArgs A,
                                                             const ShardPlan sp, const __grid_constant__ Xchg X) {
     pdl_start();
     __shared__ TileScanSmem sm;
@@ -1642,10 +1660,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_norm_scan(StateBufs st, DevSca
     __shared__ int first_kind[SCAN_THREADS / 32 + 1];
     __shared__ int s_base;
     __shared__ double s_total, s_prefix; __shared__ int s_uniform;
-    __shared__ double tree_a[TREE_SMEM_S], tree_b[TREE_SMEM_S / 2];
     __shared__ unsigned s_epoch; __shared__ double s_sq;
     const int cur = sc->cur;
     const int normalise = A.normalise;
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
+    double w[EPT];
+    load4(st.f[cur][F_W], i0, n, w);                                 // on its way while the CTA waits for the ranks' sums
     x_wait(X, X_B, sc->x_epoch[X_B], &sc->error_flags);
     if (threadIdx.x == 0) {
         const SumInfo si = combine_sums(X, sp, A.shard_sums, normalise);
@@ -1667,9 +1687,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_norm_scan(StateBufs st, DevSca
         if (blockIdx.x == 0) { sc->sum_w = si.total; sc->uniform = si.uniform; sc->migrate = si.migrate; }
     }
     __syncthreads();
-    const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
-    double w[EPT];
-    load4(st.f[cur][F_W], i0, n, w);
     if (normalise) {
         const int uniform = s_uniform; const double sum_w = s_total;
 #pragma unroll
@@ -1726,9 +1743,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_norm_scan(StateBufs st, DevSca
     }
     if (!cta_is_last(&sc->ticket[2])) return;
     // ---- last CTA: the rank's part of  effective = sum w^2  (src/ParticleFilter.hpp:58-66)
-    for (unsigned i = threadIdx.x; i < A.n_tiles; i += blockDim.x) A.scratch_a[i] = __ldcg(&A.tile_sq[i]);
-    __syncthreads();
-    const double rsq = block_tree_reduce(A.scratch_a, A.scratch_b, A.n_tiles, tree_a, tree_b, TREE_SMEM_S);
+    const double rsq = rank_tree_sum(A.tile_sq, 1, A.n_tiles, red, A.scratch_a);
     if (threadIdx.x == 0) { s_sq = rsq; s_epoch = sc->x_epoch[X_E] + 1; }
     __syncthreads();
     x_publish(X, XOFF_E + (size_t)X.me * 8, &s_sq, 1, X_E, s_epoch);
