@@ -759,18 +759,21 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     PatchGather pg; memset(&pg, 0, sizeof(pg));
     pg.P = ctx->cfg.patch_size > 0 ? ctx->cfg.patch_size : 0;
     for (int b = 0; b < 2; ++b) { pg.patch[b] = ctx->patch[b]; pg.porigin[b] = ctx->porigin[b]; }
-    if (sharded(ctx)) {
-        // every rank searches the global tile-start table (pushed by the ranks' k_chain), then the owner's running sums, and
-        // copies its ancestors' state (and map patches) straight from the owner's buffers over NVLink
-        CK(launch_pdl(ctx, k_resample_local<RS_CTA>, (unsigned)((n + RS_CTA - 1) / RS_CTA), RS_CTA, 0, ctx->st, ctx->sc, tile_sin, TG, T, n, ng, base_index(ctx),
-                      mp.k0, mp.k1, systematic, ctx->ancestors, ctx->ticket, ctx->peers, sp, tile_ofs(ctx), (unsigned)ctx->shard.rank, pg, ctx->X));
+    if (pg.P == 0 && ctx->env.stream_resample && !sp.mode) {
+        // persistent CTAs, source tiles streamed through a bulk-copy ring from the rank that owns them: own memory or a peer's
+        // over NVLink (see k_resample_stream); sharded: tile starts from the global table the ranks' k_chain pushed
+        StreamArgs sa; sa.tile_start = tile_sin; sa.n_tiles = TG; sa.tiles_per_rank = T; sa.n = n; sa.n_global = ng; sa.base = base_index(ctx);
+        sa.k0key = mp.k0; sa.k1key = mp.k1; sa.systematic = systematic; sa.ancestors = ctx->ancestors; sa.ticket = ctx->ticket;
+        sa.my_rank = sharded(ctx) ? (unsigned)ctx->shard.rank : 0u;
+        CK(launch_pdl(ctx, k_resample_stream, (unsigned)ctx->sm_count, 1024, (size_t)RS_STREAM_SMEM, ctx->st, ctx->sc, sa, ctx->peers, ctx->X));
         LAUNCHED();
         return ESLAM_OK;
     }
-    if (pg.P == 0 && ctx->env.stream_resample && !sp.mode) {
-        // persistent CTAs, source tiles streamed through a bulk-copy ring (see k_resample_stream)
-        CK(launch_pdl(ctx, k_resample_stream, (unsigned)ctx->sm_count, 1024, (size_t)RS_STREAM_SMEM, ctx->st, ctx->sc, ctx->cdf, tile_sin, T, n, mp.k0, mp.k1,
-                      systematic, ctx->ancestors, ctx->ticket));
+    if (sharded(ctx)) {
+        // per-particle patches, LOCAL_MIGRATE: every rank searches the global tile-start table (pushed by the ranks' k_chain), then
+        // the owner's running sums, and copies its ancestors' state (and map patches) straight from the owner's buffers over NVLink
+        CK(launch_pdl(ctx, k_resample_local<RS_CTA>, (unsigned)((n + RS_CTA - 1) / RS_CTA), RS_CTA, 0, ctx->st, ctx->sc, tile_sin, TG, T, n, ng, base_index(ctx),
+                      mp.k0, mp.k1, systematic, ctx->ancestors, ctx->ticket, ctx->peers, sp, tile_ofs(ctx), (unsigned)ctx->shard.rank, pg, ctx->X));
         LAUNCHED();
         return ESLAM_OK;
     }

@@ -67,6 +67,9 @@ struct DevScalars {              // device-resident scalars of one context
     int cdf_seq;                 // the running sum of this resample was computed sequentially by k_chain (k_cdf skips)
     unsigned int ticket[4];      // "last CTA" counters: 0 k_tile_part, 1 k_loop_b, 2 k_norm_scan, 3 k_cdf
     unsigned int x_epoch[8];     // epoch of every exchange (X_*): bumped by this rank's producer, read by its consumers
+    int rank_start_valid;        // rank_start[] below holds the exact running sum in front of every rank (k_chain, exact-global walk)
+    int pad_rs;
+    double rank_start[9];        // [q] = running sum before rank q's first particle, [world] = the total (ESLAM_MAX_RANKS + 1 entries)
 };
 
 struct TilePartA {               // per-tile partials of loop A
@@ -173,28 +176,34 @@ __device__ __forceinline__ void pdl_start() {
 // host-supplied exchange state.  On one GPU the same code runs with world == 1 (no flags: the kernel boundary orders).
 #define X_A 0        // loop-A rank partials            k_tile_part (last CTA) -> k_loop_b
 #define X_B 1        // rank weight sums                k_loop_b (last CTA)    -> k_norm_scan
-#define X_E 2        // rank sum of w^2                 k_norm_scan (last CTA) -> k_chain
-#define X_C 3        // rank chain summary              k_chain                -> k_chain (all ranks)
-#define X_D 4        // "my running sums are final"     k_cdf (last CTA)       -> k_resample_local
-#define X_SEQ 5      // sequential fallback: S_out      k_chain of rank r      -> k_chain of rank r+1
-#define X_BAR 6      // plain rendezvous                k_barrier
-#define X_COUNT 7
+#define X_C 2        // rank sum of w^2 + chain summary k_chain                -> k_chain (all ranks)
+#define X_D 3        // "my running sums are final"     k_resample_local CTA 0 -> the CTAs that read this rank
+#define X_SEQ 4      // sequential fallback: S_out      k_chain of rank r      -> k_chain of rank r+1
+#define X_BAR 5      // plain rendezvous                k_barrier
+#define X_COUNT 6
 #define ERR_XCHG_TIMEOUT_BIT 4
 #define ERR_INTERNAL_BIT 8
 
-struct RankPartA { double sum_pw, max_w; unsigned long long cnt, pts; };                     // 32 B
-struct RankPartB { double sum_w, sum_sq; };                                                  // 16 B (sum_sq: raw weights, LOCAL_MIGRATE decision)
-struct ChainEntry { double w; long long d0, d1; int b, pad; };                               // a boundary element and the rounding function of the run after it
-struct RankChainHead { int n_bnd, bad; long long head_d0, head_d1; int head_b, head_pad; double pad[4]; };   // 64 B
+// Payloads travel as "LL words" (the low-latency protocol of collective libraries): 8 bytes = {32 bits of payload, 32-bit
+// epoch}.  An aligned 8-byte store is atomic, so a word whose epoch matches carries valid payload: no fence, no separate
+// flag, one NVLink write of latency.  Epoch 0 never occurs (buffers start zeroed).  Only X_D / X_BAR, which order bulk data
+// written by whole grids, are release/acquire flags.
+struct RankPartA { double sum_pw, max_w; unsigned long long cnt, pts; };                     // 8 payload words
+struct RankPartB { double sum_w, sum_sq; };                                                  // 4 words (sum_sq: raw weights, LOCAL_MIGRATE decision)
+struct ChainEntry { double w; long long d0, d1; int b, pad; };                               // 8 words: a boundary element and the rounding function of the run after it
+struct RankChainHead { double sum_sq; int n_bnd, bad; long long head_d0, head_d1; int head_b, head_pad; double pad[3]; };   // 16 words
 
-#define XOFF_A 0
-#define XOFF_B (XOFF_A + ESLAM_MAX_RANKS * 32)
-#define XOFF_E (XOFF_B + ESLAM_MAX_RANKS * 16)
-#define XOFF_SEQ (XOFF_E + ESLAM_MAX_RANKS * 8)
-#define XOFF_FLAGS 1024
+#define XA_WORDS 8
+#define XB_WORDS 4
+#define XH_WORDS 16
+#define XE_WORDS 8
+#define XOFF_A 0                                               // ESLAM_MAX_RANKS slots of XA_WORDS LL words
+#define XOFF_B (XOFF_A + ESLAM_MAX_RANKS * XA_WORDS * 8)
+#define XOFF_SEQ (XOFF_B + ESLAM_MAX_RANKS * XB_WORDS * 8)
+#define XOFF_FLAGS (XOFF_SEQ + ESLAM_MAX_RANKS * 2 * 8)
 #define XOFF_C 2048
-#define XC_SLOT (64 + MAX_BND_TOTAL * 32)
-#define XOFF_TSIN (XOFF_C + ESLAM_MAX_RANKS * XC_SLOT)                                       // then world x tiles_per_rank doubles
+#define XC_SLOT ((XH_WORDS + MAX_BND_TOTAL * XE_WORDS) * 8)    // header + entries of one rank, as LL words
+#define XOFF_TSIN (XOFF_C + ESLAM_MAX_RANKS * XC_SLOT)         // then world x tiles_per_rank doubles
 
 struct Xchg {
     unsigned char* buf[ESLAM_MAX_RANKS];   // rank q's exchange buffer as mapped into this process (q == me: the local one)
@@ -209,32 +218,56 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// data another GPU wrote into this GPU's memory: read at system scope (never from a stale L1 line)
 __device__ __forceinline__ unsigned long long ld_sys_u64(const void* p) {
     unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
 }
-__device__ __forceinline__ double ld_sys_f64(const void* p) { return __longlong_as_double((long long)ld_sys_u64(p)); }
+__device__ __forceinline__ void st_sys_u64(void* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned* x_flags(unsigned char* buf, int x) { return reinterpret_cast<unsigned*>(buf + XOFF_FLAGS) + x * ESLAM_MAX_RANKS; }
 
-// Producer side, all threads of ONE CTA: copy `words` 8-byte words from src (shared or global memory) to byte offset `off` of
-// every rank's buffer, then raise flag (x, me) there to `epoch`.
-__device__ __forceinline__ void x_publish(const Xchg& X, size_t off, const void* src, unsigned words, int x, unsigned epoch) {
-    const unsigned long long* s = reinterpret_cast<const unsigned long long*>(src);
-    for (int q = 0; q < X.world; ++q) {
-        unsigned long long* d = reinterpret_cast<unsigned long long*>(X.buf[q] + off);
-        for (unsigned i = threadIdx.x; i < words; i += blockDim.x) d[i] = s[i];
+// Producer, any number of threads of one CTA: `words` 32-bit payload words from src (shared / global / local memory) become
+// LL words at byte offset `off` of EVERY rank's buffer.  Threads stride over (rank, word).
+__device__ __forceinline__ void ll_publish(const Xchg& X, size_t off, const void* src, unsigned words, unsigned epoch) {
+    const unsigned* s = reinterpret_cast<const unsigned*>(src);
+    const unsigned total = words * (unsigned)X.world;
+    for (unsigned i = threadIdx.x; i < total; i += blockDim.x) {
+        const unsigned q = i / words, k = i - q * words;
+        st_sys_u64(X.buf[q] + off + (size_t)k * 8, ((unsigned long long)epoch << 32) | s[k]);
     }
-    if (X.world <= 1) return;                              // one GPU: the kernel boundary orders producer and consumers
+}
+// Consumer, one thread: LL word at p of this GPU's own memory, once its epoch has arrived.  A rank that never arrives (a dead
+// peer) would hang the GPU: after ~4 s the wait gives up and flags the step.
+__device__ __forceinline__ unsigned ll_read(const unsigned char* p, unsigned epoch, int* error_flags) {
+    unsigned long long v = ld_sys_u64(p);
+    if ((unsigned)(v >> 32) != epoch) {
+        const long long t0 = clock64();
+        do {
+            __nanosleep(20);
+            v = ld_sys_u64(p);
+            if (clock64() - t0 > 8000000000ll) { atomicOr(error_flags, ERR_XCHG_TIMEOUT_BIT); break; }
+        } while ((unsigned)(v >> 32) != epoch);
+    }
+    return (unsigned)v;
+}
+// Consumer, all threads of a CTA: slot `words` payload words of every rank (slots `words` LL words apart at `off` of the own
+// buffer) into dst[rank * words + k] (shared memory), then a barrier.
+__device__ __forceinline__ void ll_gather(const Xchg& X, size_t off, unsigned words, unsigned epoch, unsigned* dst, int* error_flags) {
+    const unsigned total = words * (unsigned)X.world;
+    for (unsigned i = threadIdx.x; i < total; i += blockDim.x) dst[i] = ll_read(X.buf[X.me] + off + (size_t)i * 8, epoch, error_flags);
+    __syncthreads();
+}
+// Release / acquire flags for the exchanges that order bulk data (X_D, X_BAR): all threads of ONE CTA call.
+__device__ __forceinline__ void x_signal(const Xchg& X, int x, unsigned epoch) {
+    if (X.world <= 1) return;
     __threadfence_system();
     __syncthreads();
     if ((int)threadIdx.x < X.world) st_release_sys(x_flags(X.buf[threadIdx.x], x) + X.me, epoch);
 }
-// Consumer side, all threads of a CTA: wait until every rank's (or, with only >= 0, that one rank's) flag of exchange x has
-// reached `epoch`.  A rank that never arrives (a dead peer) would hang the GPU: after ~4 s the wait gives up and flags the step.
-__device__ __forceinline__ void x_wait(const Xchg& X, int x, unsigned epoch, int* error_flags, int only = -1) {
+__device__ __forceinline__ void x_wait(const Xchg& X, int x, unsigned epoch, int* error_flags) {
     if (X.world > 1) {
         const int q = (int)threadIdx.x;
-        if (q < X.world && (only < 0 || q == only)) {
+        if (q < X.world) {
             const unsigned* f = x_flags(X.buf[X.me], x) + q;
             const long long t0 = clock64();
             while ((int)(ld_acquire_sys(f) - epoch) < 0) {
@@ -267,7 +300,7 @@ __global__ void k_barrier(DevScalars* sc, const __grid_constant__ Xchg X) {
     if (threadIdx.x == 0) { s_e = sc->x_epoch[X_BAR] + 1; }
     __syncthreads();
     const unsigned e = s_e;
-    x_publish(X, 0, nullptr, 0, X_BAR, e);
+    x_signal(X, X_BAR, e);
     x_wait(X, X_BAR, e, &sc->error_flags);
     if (threadIdx.x == 0) sc->x_epoch[X_BAR] = e;
 }
@@ -408,6 +441,24 @@ __device__ __forceinline__ double rank_tree_sum(const double* vals, unsigned str
         src = scratch; stride = 1; count = chunks;
     }
     return chunk(src, stride, count);
+}
+
+// the same for ONE CTA of 1024 threads (one value per thread and chunk); red: >= 32 doubles
+__device__ __forceinline__ double rank_tree_sum_1024(const double* vals, unsigned n, double* red, double* scratch) {
+    const double* src = vals; unsigned count = n;
+    while (count > TILE) {
+        const unsigned chunks = (count + TILE - 1) / TILE;
+        for (unsigned c = 0; c < chunks; ++c) {
+            const unsigned i = c * TILE + threadIdx.x;
+            const double r = tile_tree_sum_1024(i < count ? __ldcg(src + i) : 0.0, red);
+            __syncthreads();
+            if (threadIdx.x == 0) scratch[c] = r;
+        }
+        __threadfence_block();
+        __syncthreads();
+        src = scratch; count = chunks;
+    }
+    return tile_tree_sum_1024(threadIdx.x < count ? __ldcg(src + threadIdx.x) : 0.0, red);
 }
 
 // ------------------------------------------------------------------------------------------------ map lookup
@@ -1276,7 +1327,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_part(StateBufs st, DevSca
         sc->defer_last = sc->defer_count; sc->defer_count = 0;
     }
     __syncthreads();
-    x_publish(X, XOFF_A + (size_t)X.me * sizeof(RankPartA), &s_out, sizeof(RankPartA) / 8, X_A, s_epoch);
+    ll_publish(X, XOFF_A + (size_t)X.me * XA_WORDS * 8, &s_out, XA_WORDS, s_epoch);
     if (threadIdx.x == 0) sc->x_epoch[X_A] = s_epoch;
 }
 
@@ -1309,6 +1360,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, DevScalar
     pdl_start();
     __shared__ double red[8];
     __shared__ double s_pow[6];
+    __shared__ __align__(8) unsigned s_in[ESLAM_MAX_RANKS * XA_WORDS];
     __shared__ double sh[64];
     __shared__ RankPartB s_out;
     __shared__ unsigned s_epoch;
@@ -1336,13 +1388,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, DevScalar
         }
     }
     if (APPLY) {
-        x_wait(X, X_A, sc->x_epoch[X_A], &sc->error_flags);
+        ll_gather(X, XOFF_A, XA_WORDS, sc->x_epoch[X_A], s_in, &sc->error_flags);
         if (threadIdx.x == 0) {
             double v[ESLAM_MAX_RANKS]; double smx = 0; unsigned long long scnt = 0, spts = 0;
-            const unsigned char* base = X.buf[X.me] + XOFF_A;
             for (int q = 0; q < X.world; ++q) {
-                const unsigned char* r = base + (size_t)q * sizeof(RankPartA);
-                v[q] = ld_sys_f64(r); smx = fmax(smx, ld_sys_f64(r + 8)); scnt += ld_sys_u64(r + 16); spts += ld_sys_u64(r + 24);
+                const RankPartA r = *reinterpret_cast<const RankPartA*>(s_in + q * XA_WORDS);
+                v[q] = r.sum_pw; smx = fmax(smx, r.max_w); scnt += r.cnt; spts += r.pts;
             }
             const double sum_pw = tree_small(v, X.world);
             const double fw = scnt > 0 ? sum_pw / (double)scnt : 1.0;                     // :329
@@ -1422,20 +1473,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_loop_b(StateBufs st, DevScalar
         sc->pool_count = 0;                                                      // boundary-element pool of k_norm_scan
     }
     __syncthreads();
-    x_publish(X, XOFF_B + (size_t)X.me * sizeof(RankPartB), &s_out, sizeof(RankPartB) / 8, X_B, s_epoch);
+    ll_publish(X, XOFF_B + (size_t)X.me * XB_WORDS * 8, &s_out, XB_WORDS, s_epoch);
     if (threadIdx.x == 0) sc->x_epoch[X_B] = s_epoch;
 }
 
 // What every CTA that consumes exchange X_B derives from the ranks' sums: getWeightsSum() over all ranks (tree order), the Q8
 // flag, the LOCAL_MIGRATE decision, and the raw weight in front of this rank.  One thread computes, the CTA shares it.
 struct SumInfo { double total, rank_prefix; int uniform, migrate; };
-__device__ __noinline__ SumInfo combine_sums(const Xchg& X, const ShardPlan& sp, const double2* shard_sums, int normalise) {
+__device__ __noinline__ SumInfo combine_sums(const Xchg& X, const unsigned* gathered, const ShardPlan& sp, const double2* shard_sums, int normalise) {
     SumInfo o;
     double v[ESLAM_MAX_RANKS], sqv[ESLAM_MAX_RANKS];
-    const unsigned char* base = X.buf[X.me] + XOFF_B;
     o.rank_prefix = 0.0;
     for (int q = 0; q < X.world; ++q) {
-        v[q] = ld_sys_f64(base + (size_t)q * sizeof(RankPartB)); sqv[q] = ld_sys_f64(base + (size_t)q * sizeof(RankPartB) + 8);
+        const RankPartB r = *reinterpret_cast<const RankPartB*>(gathered + q * XB_WORDS);
+        v[q] = r.sum_w; sqv[q] = r.sum_sq;
         if (q < X.me) o.rank_prefix += v[q];
     }
     double wv[ESLAM_MAX_RANKS];
@@ -1464,15 +1515,16 @@ __device__ __noinline__ SumInfo combine_sums(const Xchg& X, const ShardPlan& sp,
 // exchange slots while another still reads them.
 __global__ void k_sum_finish(DevScalars* sc, const ShardPlan sp, const double2* shard_sums, const __grid_constant__ Xchg X) {
     __shared__ unsigned s_e;
-    x_wait(X, X_B, sc->x_epoch[X_B], &sc->error_flags);
+    __shared__ __align__(8) unsigned s_in[ESLAM_MAX_RANKS * XB_WORDS];
+    ll_gather(X, XOFF_B, XB_WORDS, sc->x_epoch[X_B], s_in, &sc->error_flags);
     if (threadIdx.x == 0) {
-        const SumInfo si = combine_sums(X, sp, shard_sums, 0);
+        const SumInfo si = combine_sums(X, s_in, sp, shard_sums, 0);
         sc->sum_w = si.total;
         s_e = sc->x_epoch[X_BAR] + 1;
     }
     __syncthreads();
     const unsigned e = s_e;
-    x_publish(X, 0, nullptr, 0, X_BAR, e);
+    x_signal(X, X_BAR, e);
     x_wait(X, X_BAR, e, &sc->error_flags);
     if (threadIdx.x == 0) sc->x_epoch[X_BAR] = e;
 }
@@ -1641,7 +1693,6 @@ __device__ __forceinline__ void store4(double* p, unsigned long long i0, unsigne
 // normalise (src/ParticleFilter.hpp:51-67), per-tile sum of w^2, and the tile descriptors of the exact running sum.
 // Prologue: every CTA combines the ranks' weight sums (exchange X_B) into getWeightsSum() and derives its tile's approximate
 // prefix (rank prefix + raw tile prefix, normalised); CTA 0 records sum / Q8 flag / LOCAL_MIGRATE decision in DevScalars.
-// Last CTA: the rank's sum of w^2 (pairwise tree over its tiles) -> exchange X_E (k_chain turns the ranks' sums into the ESS).
 struct NormScanArgs {
     unsigned long long n_global;
     const double* prefix_raw; const double2* shard_sums;
@@ -1660,15 +1711,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_norm_scan(StateBufs st, Dev
     __shared__ int first_kind[SCAN_THREADS / 32 + 1];
     __shared__ int s_base;
     __shared__ double s_total, s_prefix; __shared__ int s_uniform;
-    __shared__ unsigned s_epoch; __shared__ double s_sq;
+    __shared__ __align__(8) unsigned s_in[ESLAM_MAX_RANKS * XB_WORDS];
     const int cur = sc->cur;
     const int normalise = A.normalise;
     const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
     double w[EPT];
     load4(st.f[cur][F_W], i0, n, w);                                 // on its way while the CTA waits for the ranks' sums
-    x_wait(X, X_B, sc->x_epoch[X_B], &sc->error_flags);
+    ll_gather(X, XOFF_B, XB_WORDS, sc->x_epoch[X_B], s_in, &sc->error_flags);
     if (threadIdx.x == 0) {
-        const SumInfo si = combine_sums(X, sp, A.shard_sums, normalise);
+        const SumInfo si = combine_sums(X, s_in, sp, A.shard_sums, normalise);
         const bool local = sp.mode && !si.migrate;
         // approximate running sum in front of this tile (only classifies elements).  Local resampling: it restarts at every shard.
         const unsigned bt = blockIdx.x;
@@ -1741,13 +1792,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_norm_scan(StateBufs st, Dev
             }
         }
     }
-    if (!cta_is_last(&sc->ticket[2])) return;
-    // ---- last CTA: the rank's part of  effective = sum w^2  (src/ParticleFilter.hpp:58-66)
-    const double rsq = rank_tree_sum(A.tile_sq, 1, A.n_tiles, red, A.scratch_a);
-    if (threadIdx.x == 0) { s_sq = rsq; s_epoch = sc->x_epoch[X_E] + 1; }
-    __syncthreads();
-    x_publish(X, XOFF_E + (size_t)X.me * 8, &s_sq, 1, X_E, s_epoch);
-    if (threadIdx.x == 0) sc->x_epoch[X_E] = s_epoch;
 }
 
 // one CTA per rank: ESS, resample decision, and the exact value of the running sum at every tile start / boundary element of
@@ -1785,27 +1829,20 @@ __global__ void __launch_bounds__(1024, 1) k_chain(StateBufs st, DevScalars* sc,
     __shared__ SegE sh_e[64];
     __shared__ int s_bad, s_go, s_late;
     __shared__ SegF s_head;
-    __shared__ RankChainHead s_hdr[ESLAM_MAX_RANKS];
+    __shared__ __align__(8) RankChainHead s_hdr[ESLAM_MAX_RANKS];
     __shared__ int s_ofs[ESLAM_MAX_RANKS + 1];
-    __shared__ double s_sin;
+    __shared__ double s_sin, cs_own_start;
     __shared__ unsigned s_epoch;
+    __shared__ double red[32];
     const unsigned tid = threadIdx.x;
     const unsigned n_tiles = A.n_tiles;
     double* tile_sin = reinterpret_cast<double*>(X.buf[X.me] + XOFF_TSIN);
-    // effective sample size over all ranks (src/ParticleFilter.hpp:69) and the decision (src/PoseEstimator.cpp:249)
-    x_wait(X, X_E, sc->x_epoch[X_E], &sc->error_flags);
-    if (tid == 0) {
-        if (A.decide) {
-            double v[ESLAM_MAX_RANKS];
-            for (int q = 0; q < X.world; ++q) v[q] = ld_sys_f64(X.buf[X.me] + XOFF_E + (size_t)q * 8);
-            const double ess = 1.0 / tree_small(v, X.world);
-            sc->ess = ess;
-            sc->do_resample = (A.force || ess < (double)A.min_effective) ? 1 : 0;
-        } else sc->do_resample = A.force ? 1 : 0;
-        s_bad = 0; s_late = 0; s_go = sc->do_resample; sc->cdf_seq = 0;
-    }
+    // this rank's part of  effective = sum w^2  (src/ParticleFilter.hpp:58-66): pairwise tree over its tiles
+    const double rank_sq = rank_tree_sum_1024(A.tile_sq, n_tiles, red, A.sb_out);
+    if (tid == 0) { s_bad = 0; s_late = 0; sc->cdf_seq = 0; s_epoch = sc->x_epoch[X_C] + 1; s_head = segf_identity(); }
     __syncthreads();
-    if (!s_go) return;
+    // is a resampling possible at all in this call (every rank answers the same)?  Otherwise only the ESS is exchanged.
+    const bool want_chain = A.force || (A.decide && A.min_effective > 0);
 
     // Rounds of 1024 tiles, one tile per thread (coalesced, independent loads): per round an exclusive scan of the boundary
     // counts and a segmented exclusive scan of the tile functions (shuffles inside the warp, warp 0 across the warp totals),
@@ -1816,7 +1853,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(StateBufs st, DevScalars* sc,
     const unsigned lane = tid & 31, warp = tid >> 5;
     __shared__ int s_carry_c; __shared__ SegE s_carry_e;
     const bool local = sp.mode && !sc->migrate;
-    const unsigned n_seg = local ? sp.count : 1u;
+    const unsigned n_seg = !want_chain ? 0u : (local ? sp.count : 1u);
     int bnd_base = 0;
     for (unsigned sg = 0; sg < n_seg; ++sg) {
         const unsigned t_begin = local ? sg * sp.tiles_per_shard : 0u;
@@ -1915,129 +1952,142 @@ __global__ void __launch_bounds__(1024, 1) k_chain(StateBufs st, DevScalars* sc,
     __syncthreads();
     const int n_bnd = bnd_base;
 
-    if (!local) {
-        // ---- exact-global walk: exchange the ranks' summaries
+    // ---- exchange: every rank's sum of w^2 (-> ESS, the decision) and, for the exact-global walk, its chain summary
+    const bool send_entries = want_chain && !local;
+    if (send_entries) {
         for (unsigned k = tid; k < (unsigned)n_bnd && k < MAX_BND_TOTAL; k += blockDim.x) {
             ChainEntry ce; ce.w = cs.bw[k]; ce.d0 = cs.seg[k].d0; ce.d1 = cs.seg[k].d1; ce.b = cs.seg[k].b; ce.pad = cs.seg[k].pad;
             cs.stage[k] = ce;
             if (ce.pad) atomicOr(&s_bad, 1);
         }
         __syncthreads();
-        if (tid == 0) {
-            RankChainHead h; memset(&h, 0, sizeof(h));
-            if (s_head.pad) s_bad = 1;
-            h.n_bnd = s_bad ? 0 : n_bnd; h.bad = s_bad; h.head_d0 = s_head.d0; h.head_d1 = s_head.d1; h.head_b = s_head.b; h.head_pad = s_head.pad;
-            s_hdr[X.me] = h;
-            s_epoch = sc->x_epoch[X_C] + 1;
+    }
+    if (tid == 0) {
+        RankChainHead h; memset(&h, 0, sizeof(h));
+        if (s_head.pad) s_bad = 1;
+        h.sum_sq = rank_sq;
+        h.n_bnd = (send_entries && !s_bad) ? n_bnd : 0; h.bad = send_entries ? s_bad : 0;
+        h.head_d0 = s_head.d0; h.head_d1 = s_head.d1; h.head_b = s_head.b; h.head_pad = s_head.pad;
+        s_hdr[X.me] = h;
+    }
+    __syncthreads();
+    {
+        const size_t slot = XOFF_C + (size_t)X.me * XC_SLOT;
+        ll_publish(X, slot, &s_hdr[X.me], XH_WORDS, s_epoch);
+        if (X.world > 1 && s_hdr[X.me].n_bnd > 0) ll_publish(X, slot + XH_WORDS * 8, cs.stage, (unsigned)s_hdr[X.me].n_bnd * XE_WORDS, s_epoch);
+        __syncthreads();                                   // the own header in shared memory is complete before it is overwritten below
+        // headers of all ranks (the own one travels the same way)
+        unsigned* hw = reinterpret_cast<unsigned*>(s_hdr);
+        for (unsigned i = tid; i < (unsigned)X.world * XH_WORDS; i += blockDim.x) {
+            const unsigned q = i / XH_WORDS, k = i - q * XH_WORDS;
+            hw[q * (sizeof(RankChainHead) / 4) + k] = ll_read(X.buf[X.me] + XOFF_C + (size_t)q * XC_SLOT + (size_t)k * 8, s_epoch, &sc->error_flags);
         }
         __syncthreads();
-        if (X.world > 1) {
-            const unsigned ew = s_bad ? 0u : (unsigned)n_bnd * (sizeof(ChainEntry) / 8);
-            const unsigned long long* hs = reinterpret_cast<const unsigned long long*>(&s_hdr[X.me]);
-            const unsigned long long* es = reinterpret_cast<const unsigned long long*>(cs.stage);
+    }
+    if (tid == 0) {
+        sc->x_epoch[X_C] = s_epoch;
+        // effective sample size over all ranks (src/ParticleFilter.hpp:69) and the decision (src/PoseEstimator.cpp:249)
+        if (A.decide) {
+            double v[ESLAM_MAX_RANKS];
+            for (int q = 0; q < X.world; ++q) v[q] = s_hdr[q].sum_sq;
+            const double ess = 1.0 / tree_small(v, X.world);
+            sc->ess = ess;
+            sc->do_resample = (A.force || ess < (double)A.min_effective) ? 1 : 0;
+        } else sc->do_resample = A.force ? 1 : 0;
+        s_go = sc->do_resample;
+        int any = 0, ofs = 0;
+        for (int q = 0; q < X.world; ++q) { any |= s_hdr[q].bad; s_ofs[q] = ofs; if (q != X.me) ofs += s_hdr[q].n_bnd; }
+        s_ofs[X.world] = ofs;                                            // boundary elements of all the other ranks
+        if (!local) s_bad = any;                                         // every rank sees the same flags: same decision
+        s_sin = 0.0;
+        sc->rank_start_valid = 0;
+    }
+    __syncthreads();
+    if (!s_go) return;
+
+    if (!local && !s_bad) {
+        // The walk: through the summaries of ALL ranks in order (the other ranks' entries polled into shared memory, the own
+        // ones already there), one real fp64 add per boundary element, one integer add per run.  It yields the running sum in
+        // front of every rank (rank_start: lets the resampling kernel tell which ranks hold its ancestors) and, inside the own
+        // rank, at every boundary element.
+        const int M = s_ofs[X.world];
+        const bool at_once = M <= MAX_BND_TOTAL;                         // cs.stage is free again (the own entries live in cs.bw / cs.seg)
+        if (at_once) {
             for (int q = 0; q < X.world; ++q) {
-                unsigned long long* d = reinterpret_cast<unsigned long long*>(X.buf[q] + XOFF_C + (size_t)X.me * XC_SLOT);
-                for (unsigned i = tid; i < 8 + ew; i += blockDim.x) d[i] = i < 8 ? hs[i] : es[i - 8];
-            }
-            __threadfence_system();
-            __syncthreads();
-            if ((int)tid < X.world) st_release_sys(x_flags(X.buf[tid], X_C) + X.me, s_epoch);
-            x_wait(X, X_C, s_epoch, &sc->error_flags);
-            if ((int)tid < X.world && (int)tid != X.me) {
-                const unsigned char* src = X.buf[X.me] + XOFF_C + (size_t)tid * XC_SLOT;
-                unsigned long long* d = reinterpret_cast<unsigned long long*>(&s_hdr[tid]);
-                for (int i = 0; i < 8; ++i) d[i] = ld_sys_u64(src + 8 * i);
+                if (q == X.me) continue;
+                const unsigned char* src = X.buf[X.me] + XOFF_C + (size_t)q * XC_SLOT + XH_WORDS * 8;
+                unsigned* d = reinterpret_cast<unsigned*>(cs.stage + s_ofs[q]);
+                const unsigned words = (unsigned)s_hdr[q].n_bnd * XE_WORDS;
+                for (unsigned i = tid; i < words; i += blockDim.x) d[i] = ll_read(src + (size_t)i * 8, s_epoch, &sc->error_flags);
             }
             __syncthreads();
         }
-        if (tid == 0) {
-            sc->x_epoch[X_C] = s_epoch;
-            int any = 0, ofs = 0;
-            for (int q = 0; q < X.world; ++q) { any |= s_hdr[q].bad; s_ofs[q] = ofs; if (q < X.me) ofs += s_hdr[q].n_bnd; }
-            s_ofs[X.world] = ofs;                                            // boundary elements in front of this rank
-            s_bad = any;                                                     // every rank sees the same flags: same decision
-            s_sin = 0.0;
-        }
-        __syncthreads();
-        if (!s_bad) {
-            // the running sum in front of this rank: through the summaries of the ranks before it (staged in shared memory)
-            if (X.me > 0) {
-                const int M = s_ofs[X.world];
-                if (M <= MAX_BND_TOTAL) {
-                    // cs.stage is free again (the own entries live in cs.bw / cs.seg)
-                    for (int q = 0; q < X.me; ++q) {
-                        const unsigned char* src = X.buf[X.me] + XOFF_C + (size_t)q * XC_SLOT + 64;
-                        unsigned long long* d = reinterpret_cast<unsigned long long*>(cs.stage + s_ofs[q]);
-                        const unsigned words = (unsigned)s_hdr[q].n_bnd * (sizeof(ChainEntry) / 8);
-                        for (unsigned i = tid; i < words; i += blockDim.x) d[i] = ld_sys_u64(src + 8 * (size_t)i);
-                    }
-                    __syncthreads();
-                    if (tid == 0) {
-                        double S = 0.0; int b2 = 0;
-                        for (int q = 0; q < X.me; ++q) {
-                            SegF hf; hf.d0 = s_hdr[q].head_d0; hf.d1 = s_hdr[q].head_d1; hf.b = s_hdr[q].head_b; hf.pad = s_hdr[q].head_pad;
-                            S = chain_walk(S, hf, cs.stage + s_ofs[q], s_hdr[q].n_bnd, b2);
-                        }
-                        s_sin = S; if (b2) s_late = 1;
-                    }
-                } else {
-                    for (int q = 0; q < X.me; ++q) {                         // long lists: one rank at a time
-                        const unsigned char* src = X.buf[X.me] + XOFF_C + (size_t)q * XC_SLOT + 64;
-                        unsigned long long* d = reinterpret_cast<unsigned long long*>(cs.stage);
-                        const unsigned words = (unsigned)s_hdr[q].n_bnd * (sizeof(ChainEntry) / 8);
-                        __syncthreads();
-                        for (unsigned i = tid; i < words; i += blockDim.x) d[i] = ld_sys_u64(src + 8 * (size_t)i);
-                        __syncthreads();
-                        if (tid == 0) {
-                            int b2 = 0;
-                            SegF hf; hf.d0 = s_hdr[q].head_d0; hf.d1 = s_hdr[q].head_d1; hf.b = s_hdr[q].head_b; hf.pad = s_hdr[q].head_pad;
-                            s_sin = chain_walk(s_sin, hf, cs.stage, s_hdr[q].n_bnd, b2);
-                            if (b2) s_late = 1;
-                        }
-                    }
-                }
+        for (int q = 0; q < X.world; ++q) {
+            if (!at_once && q != X.me) {                                 // long lists: one rank at a time
+                const unsigned char* src = X.buf[X.me] + XOFF_C + (size_t)q * XC_SLOT + XH_WORDS * 8;
+                unsigned* d = reinterpret_cast<unsigned*>(cs.stage);
+                const unsigned words = (unsigned)s_hdr[q].n_bnd * XE_WORDS;
+                __syncthreads();
+                for (unsigned i = tid; i < words; i += blockDim.x) d[i] = ll_read(src + (size_t)i * 8, s_epoch, &sc->error_flags);
                 __syncthreads();
             }
             if (tid == 0) {
-                // the sequential part: one real fp64 add per boundary element, one integer add per segment
                 int b2 = 0;
-                double S = segf_apply(s_sin, s_head, b2);
-                for (int k = 0; k < n_bnd; ++k) { S = S + cs.bw[k]; cs.bw[k] = S; S = segf_apply(S, cs.seg[k], b2); }
+                double S = s_sin;
+                sc->rank_start[q] = S;
+                if (q == X.me) {
+                    cs_own_start = S;
+                    S = segf_apply(S, s_head, b2);
+                    for (int k = 0; k < n_bnd; ++k) { S = S + cs.bw[k]; cs.bw[k] = S; S = segf_apply(S, cs.seg[k], b2); }
+                } else {
+                    SegF hf; hf.d0 = s_hdr[q].head_d0; hf.d1 = s_hdr[q].head_d1; hf.b = s_hdr[q].head_b; hf.pad = s_hdr[q].head_pad;
+                    S = chain_walk(S, hf, cs.stage + (at_once ? s_ofs[q] : 0), s_hdr[q].n_bnd, b2);
+                }
+                s_sin = S;
                 if (b2) s_late = 1;
+                if (q + 1 == X.world) { sc->rank_start[X.world] = S; sc->rank_start_valid = 1; }
             }
-            __syncthreads();
-            int b3 = 0;
-            for (unsigned t = tid; t < n_tiles; t += blockDim.x) {
-                const int ofs = A.tile_bofs[t];
-                const double v = segf_apply(ofs > 0 ? cs.bw[ofs - 1] : s_sin, A.tile_pre[t], b3);
-                for (int q = 0; q < X.world; ++q) reinterpret_cast<double*>(X.buf[q] + XOFF_TSIN)[A.tile_ofs + t] = v;   // every rank's tile-start table
-            }
-            if (b3) atomicOr(&s_late, 1);
-            __syncthreads();
-            // a consistency check that failed after the exchange cannot be turned into a fallback every rank agrees on; it is a
-            // "cannot happen" (the element classes guarantee the binades): one GPU falls back, a sharded run reports it
-            if (s_late) { if (X.world > 1) { if (tid == 0) atomicOr(&sc->error_flags, ERR_INTERNAL_BIT); } else if (tid == 0) s_bad = 1; }
-            __syncthreads();
         }
+        __syncthreads();
+        if (tid == 0) s_sin = cs_own_start;                              // the running sum in front of this rank
+        __syncthreads();
+        int b3 = 0;
+        for (unsigned t = tid; t < n_tiles; t += blockDim.x) {
+            const int ofs = A.tile_bofs[t];
+            const double v = segf_apply(ofs > 0 ? cs.bw[ofs - 1] : s_sin, A.tile_pre[t], b3);
+            for (int q = 0; q < X.world; ++q) reinterpret_cast<double*>(X.buf[q] + XOFF_TSIN)[A.tile_ofs + t] = v;   // every rank's tile-start table
+        }
+        if (b3) atomicOr(&s_late, 1);
+        __syncthreads();
+        // a consistency check that failed after the exchange cannot be turned into a fallback every rank agrees on; it is a
+        // "cannot happen" (the element classes guarantee the binades): one GPU falls back, a sharded run reports it
+        if (s_late) { if (X.world > 1) { if (tid == 0) atomicOr(&sc->error_flags, ERR_INTERNAL_BIT); } else if (tid == 0) s_bad = 1; }
+        __syncthreads();
     }
     if (s_bad) {
         // ---- fallback: the literal left-to-right running sum by one thread (boundary pool overflow, ambiguous binades).  Sharded
         // exact-global walk: rank r continues from the sum rank r-1 ended with (exchange X_SEQ), one rank after the other.
-        if (tid == 0) s_epoch = sc->x_epoch[X_SEQ] + 1;
-        __syncthreads();
-        if (!local && X.me > 0) x_wait(X, X_SEQ, s_epoch, &sc->error_flags, X.me - 1);
         if (tid == 0) {
+            const unsigned e = sc->x_epoch[X_SEQ] + 1;
+            s_epoch = e;
+            double s_in = 0.0;
+            if (!local && X.me > 0) {                                    // the sum the rank in front ended with
+                const unsigned char* p = X.buf[X.me] + XOFF_SEQ + (size_t)(X.me - 1) * 16;
+                const unsigned lo = ll_read(p, e, &sc->error_flags), hi = ll_read(p + 8, e, &sc->error_flags);
+                s_in = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+            }
             const double* w = st.f[sc->cur][F_W];
             const unsigned long long seg_n = local ? sp.n_shard : A.n;
+            const bool continues = !local && X.me > 0;
             double s = 0.0;
             for (unsigned long long i = 0; i < A.n; ++i) {
                 const bool first = (i % seg_n) == 0;
                 if (first) {
                     if (local && i > 0) sp.shard_tot[sp.first + (unsigned)(i / seg_n) - 1] = s;
-                    s = (!local && X.me > 0) ? ld_sys_f64(X.buf[X.me] + XOFF_SEQ + (size_t)(X.me - 1) * 8) : 0.0;
+                    s = continues ? s_in : 0.0;
                 }
                 if ((i & (TILE - 1)) == 0) tile_sin[A.tile_ofs + i / TILE] = s;
-                s = (first && !(!local && X.me > 0)) ? w[i] : s + w[i];
+                s = (first && !continues) ? w[i] : s + w[i];
                 A.cdf[i] = s;
             }
             if (local) sp.shard_tot[sp.first + (unsigned)((A.n - 1) / seg_n)] = s;
@@ -2046,7 +2096,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(StateBufs st, DevScalars* sc,
         }
         __syncthreads();
         if (!local) {
-            x_publish(X, XOFF_SEQ + (size_t)X.me * 8, &s_sin, 1, X_SEQ, s_epoch);
+            ll_publish(X, XOFF_SEQ + (size_t)X.me * 16, &s_sin, 2, s_epoch);
             if (X.world > 1) {
                 for (unsigned t = tid; t < n_tiles; t += blockDim.x) {
                     const double v = tile_sin[A.tile_ofs + t];
@@ -2054,6 +2104,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(StateBufs st, DevScalars* sc,
                 }
             }
         }
+        __syncthreads();
         if (tid == 0) sc->x_epoch[X_SEQ] = s_epoch;
         __threadfence_system();
         return;
@@ -2072,7 +2123,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_cdf(StateBufs st, DevScalars* 
     pdl_start();
     __shared__ TileScanSmem sm;
     __shared__ int slot_of[TILE];
-    __shared__ unsigned s_epoch;
     if (!sc->do_resample) return;                                    // the same decision on every rank
     if (!sc->cdf_seq) {
         const int cur = sc->cur;
@@ -2098,14 +2148,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_cdf(StateBufs st, DevScalars* 
         if (bad) atomicOr(&sc->error_flags, ERR_INTERNAL_BIT);      // cannot happen: k_chain applied the same functions to the same sums
         store4(A.cdf, i0, n, S);
     }
-    // sharded exact-global walk: every rank's running sums must be final before anyone searches them through a peer mapping
-    // (k_resample_local waits for all ranks' X_D flags)
-    if (X.world <= 1 || (sp.mode && !sc->migrate)) return;
-    if (!cta_is_last(&sc->ticket[3])) return;
-    if (threadIdx.x == 0) s_epoch = sc->x_epoch[X_D] + 1;
-    __syncthreads();
-    x_publish(X, 0, nullptr, 0, X_D, s_epoch);
-    if (threadIdx.x == 0) sc->x_epoch[X_D] = s_epoch;
 }
 
 // ------------------------------------------------------------------------------------------------ resample
@@ -2145,8 +2187,11 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
     if (!sc->do_resample) return;                                        // the same decision on every rank
     int world = X.world;
     const bool local = sp.mode && !sc->migrate;
-    if (!local) x_wait(X, X_D, sc->x_epoch[X_D], &sc->error_flags);      // every rank's running sum is final before anyone reads a peer
     const unsigned tid = threadIdx.x;
+    // "my running sums are final" (this kernel runs after this rank's k_cdf): CTA 0 tells every rank, so that the signal
+    // travels while the other CTAs work.  Epoch = number of this resampling (equal on every rank).
+    const unsigned xd_epoch = sc->resample_step + 1u;
+    if (!local && blockIdx.x == 0) x_signal(X, X_D, xd_epoch);
     const unsigned long long kb = (unsigned long long)blockIdx.x * RS_THREADS, k = kb + tid;   // local stratum
     // Local resampling (LOCAL_MIGRATE sharding, no shard collapsed): the CTA's strata belong to ONE logical shard held here; they
     // walk that shard's own running sum (restarted at zero, tile starts at tile_ofs + s T_s of the table), scaled by the shard's
@@ -2165,12 +2210,36 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
     // the tile starts are non-decreasing, so "the last tile starting below thr" is a count: one coalesced read of the table and
     // two block-wide counts instead of two dependent binary searches.  thr_lo / thr_hi bound every sum_r of this CTA.
     const double thr_lo = ((double)sbase / (double)n_global) * scale, thr_hi = ((double)(sbase + (unsigned long long)RS_THREADS) / (double)n_global) * scale;
+    // Sharded exact-global walk: which ranks can hold this CTA's ancestors?  From the running sum in front of every rank
+    // (k_chain): ranks q_a .. q_b.  Only their part of the tile-start table is searched, and the CTA waits only for those of
+    // them that are other GPUs (their k_chain has pushed their tile starts, their k_cdf has finished) -- with balanced
+    // weights that is nobody for all but the CTAs at the ends of the shard.
+    unsigned t_first = 0, t_count = n_tiles;                             // slice of the table to count over
+    if (world > 1) {
+        unsigned q_a = 0, q_b = (unsigned)world - 1;
+        if (sc->rank_start_valid) {
+            unsigned ca = 0, cb = 0;
+            for (int q = 0; q < world; ++q) { const double rs = sc->rank_start[q]; ca += rs < thr_lo; cb += rs < thr_hi; }
+            q_a = ca ? ca - 1 : 0; q_b = cb ? cb - 1 : 0;
+        }
+        t_first = q_a * tiles_per_rank; t_count = (q_b - q_a + 1) * tiles_per_rank;
+        if (tid < (unsigned)world && tid >= q_a && tid <= q_b && tid != my_rank) {
+            const unsigned* f = x_flags(X.buf[X.me], X_D) + tid;
+            const long long t0 = clock64();
+            while ((int)(ld_acquire_sys(f) - xd_epoch) < 0) {
+                __nanosleep(20);
+                if (clock64() - t0 > 8000000000ll) { atomicOr(&sc->error_flags, ERR_XCHG_TIMEOUT_BIT); break; }
+            }
+        }
+        __syncthreads();
+    }
     unsigned c_lo = 0, c_hi = 0;
-    for (unsigned t0 = 0; t0 < n_tiles; t0 += RS_THREADS) {
-        const double ts = (t0 + tid < n_tiles) ? __ldg(&tile_start[t0 + tid]) : 1.7e308;
+    for (unsigned t0 = 0; t0 < t_count; t0 += RS_THREADS) {
+        const double ts = (t0 + tid < t_count) ? __ldcg(&tile_start[t_first + t0 + tid]) : 1.7e308;
         c_lo += (unsigned)__syncthreads_count(ts < thr_lo);
         c_hi += (unsigned)__syncthreads_count(ts < thr_hi);
     }
+    c_lo += t_first; c_hi += t_first;                                    // the tiles in front of the slice all start below thr_lo
     const unsigned t_lo = c_lo == 0 ? 0u : c_lo - 1, t_hi = c_hi == 0 ? 0u : c_hi - 1;
     const bool in_smem = (t_hi - t_lo) < RS_TILES;
     const unsigned long long g0 = (unsigned long long)t_lo * TILE;                        // window [g0, g1) of the walk's elements
@@ -2198,8 +2267,8 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
             while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (s_cdf[mid] < sum_r) lo = mid + 1; else hi = mid; }
             a = g0 + lo;
         } else {
-            unsigned tlo = 0, thi = n_tiles;
-            while (tlo < thi) { const unsigned mid = (tlo + thi) >> 1; if (__ldg(&tile_start[mid]) < sum_r) tlo = mid + 1; else thi = mid; }
+            unsigned tlo = t_lo, thi = min(t_hi + 1, n_tiles);               // the first tile that does not start below sum_r lies in (t_lo, t_hi + 1]
+            while (tlo < thi) { const unsigned mid = (tlo + thi) >> 1; if (__ldcg(&tile_start[mid]) < sum_r) tlo = mid + 1; else thi = mid; }
             const unsigned t = tlo == 0 ? 0 : tlo - 1;
             const unsigned q = t / tiles_per_rank;
             const double* cdf_q = peers.cdf[world > 1 ? q : q_fixed] + po;
@@ -2246,14 +2315,18 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
     }
 }
 
-// Resampling as a stream (one GPU, no patches, one walk over all particles): a persistent CTA owns a run of consecutive strata
-// [K0, K1).  Strata and their ancestors advance together (the walk is monotone, src/ParticleFilter.hpp:96-105), so the CTA
-// pulls the SOURCE tiles that hold its ancestors -- exact running sum + the 58 bytes of state of 1024 particles, 66 KB -- one
-// after the other through a two-stage ring of bulk copies (cp.async.bulk + mbarrier: the copy of tile i+1 runs while tile i is
-// searched), and every source tile is read once per CTA that needs it.  For tile t the candidate strata are
-// floor(n S_t) - 2 .. floor(n S_t+1) + 2 (S_t = exact sum before the tile); a stratum belongs to the tile iff
+// Resampling as a stream (no patches, one walk over all particles; one GPU or the exact-global walk of a sharded filter): a
+// persistent CTA owns a run of consecutive strata [K0, K1) of this rank.  Strata and their ancestors advance together (the
+// walk is monotone, src/ParticleFilter.hpp:96-105), so the CTA pulls the SOURCE tiles that hold its ancestors -- exact running
+// sum + the 58 bytes of state of 1024 particles, 66 KB -- one after the other through a two-stage ring of bulk copies
+// (cp.async.bulk + mbarrier: the copy of tile i+1 runs while tile i is searched), from the rank that owns each tile: its own
+// memory or a peer's over NVLink.  Every source tile is read once per CTA that needs it.  For tile t the candidate strata are
+// floor(N S_t) - 2 .. floor(N S_t+1) + 2 (S_t = exact sum before the tile); a stratum belongs to the tile iff
 //   (t == 0 or S_t < sum_r) and (t last or !(cdf[last of t] < sum_r))      <=>  lower_bound(cdf, sum_r) lies in tile t
 // so every stratum is served by exactly one tile; tiles without candidates are never loaded.  Outputs leave coalesced.
+// Sharded: the running sum in front of every rank (k_chain) tells which ranks can hold the CTA's ancestors; it searches only
+// their part of the tile-start table and waits only for those of them that are other GPUs ("my running sums are final", X_D,
+// signalled by CTA 0 of this same kernel on every rank) -- with balanced weights only the CTAs at the ends of a shard wait.
 #define RS_STAGE_BYTES (8 * TILE * 8 + 2 * TILE)          // cdf + 7 doubles + 2 bytes per particle of one source tile
 #define RS_STREAM_SMEM (2 * RS_STAGE_BYTES + 64)
 
@@ -2262,56 +2335,98 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(mbar) : "memory");
 }
 
-__global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevScalars* sc, const double* __restrict__ cdf,
-                                                             const double* __restrict__ tile_start, unsigned n_tiles,
-                                                             unsigned long long n, uint32_t k0key, uint32_t k1key, int systematic,
-                                                             uint32_t* ancestors, unsigned* ticket) {
+struct StreamArgs {
+    const double* tile_start;          // exact running sum before every tile of every rank (global tile index)
+    unsigned n_tiles, tiles_per_rank;  // tiles of all ranks, of one rank
+    unsigned long long n, n_global, base;   // strata (= particles) of this rank, of all ranks, global index of local stratum 0
+    uint32_t k0key, k1key; int systematic;
+    uint32_t* ancestors; unsigned* ticket;
+    unsigned my_rank;
+};
+
+__global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevScalars* sc, const StreamArgs A,
+                                                             const __grid_constant__ PeerTable peers, const __grid_constant__ Xchg X) {
     pdl_start();
     extern __shared__ __align__(128) unsigned char rs_raw[];
-    if (!sc->do_resample) return;
+    if (!sc->do_resample) return;                                              // the same decision on every rank
     const unsigned tid = threadIdx.x;
     const int cur = sc->cur, nxt = cur ^ 1;
+    const unsigned long long n = A.n, base = A.base;
+    const unsigned T = A.tiles_per_rank;
+    const int world = X.world;
+    const unsigned xd_epoch = sc->resample_step + 1u;                          // number of this resampling: equal on every rank
+    if (blockIdx.x == 0) x_signal(X, X_D, xd_epoch);                           // this rank's k_cdf has finished (stream order)
     const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(rs_raw);
     const uint32_t mbar0 = smem0 + 2 * RS_STAGE_BYTES;                        // two mbarriers behind the stages
     const unsigned long long per = (((n + gridDim.x - 1) / gridDim.x) + 31ull) & ~31ull;
     const unsigned long long K0 = min(n, (unsigned long long)blockIdx.x * per), K1 = min(n, K0 + per);
     if (K0 < K1) {
-        const double dn = (double)n;
-        // source tiles of this CTA: from the last tile starting below K0/n to the last one starting below K1/n (two counts)
-        const double thr_lo = (double)K0 / dn, thr_hi = (double)K1 / dn;
+        const double dn = (double)A.n_global;
+        const double thr_lo = (double)(base + K0) / dn, thr_hi = (double)(base + K1) / dn;
+        // ranks that can hold this CTA's ancestors, and the wait for those that are other GPUs
+        unsigned t_first = 0, t_count = A.n_tiles;
+        if (world > 1) {
+            unsigned q_a = 0, q_b = (unsigned)world - 1;
+            if (sc->rank_start_valid) {
+                unsigned ca = 0, cb = 0;
+                for (int q = 0; q < world; ++q) { const double rs = sc->rank_start[q]; ca += rs < thr_lo; cb += rs < thr_hi; }
+                q_a = ca ? ca - 1 : 0; q_b = cb ? cb - 1 : 0;
+            }
+            t_first = q_a * T; t_count = (q_b - q_a + 1) * T;
+            if (tid < (unsigned)world && tid >= q_a && tid <= q_b && tid != A.my_rank) {
+                const unsigned* f = x_flags(X.buf[X.me], X_D) + tid;
+                const long long t0 = clock64();
+                while ((int)(ld_acquire_sys(f) - xd_epoch) < 0) {
+                    __nanosleep(20);
+                    if (clock64() - t0 > 8000000000ll) { atomicOr(&sc->error_flags, ERR_XCHG_TIMEOUT_BIT); break; }
+                }
+            }
+            __syncthreads();
+        }
+        // source tiles of this CTA: from the last tile starting below K0/N to the last one starting below K1/N (two counts)
         unsigned c_lo = 0, c_hi = 0;
-        for (unsigned t0 = 0; t0 < n_tiles; t0 += 1024) {
-            const double ts = (t0 + tid < n_tiles) ? __ldg(&tile_start[t0 + tid]) : 1.7e308;
+        for (unsigned t0 = 0; t0 < t_count; t0 += 1024) {
+            const double ts = (t0 + tid < t_count) ? __ldcg(&A.tile_start[t_first + t0 + tid]) : 1.7e308;
             c_lo += (unsigned)__syncthreads_count(ts < thr_lo);
             c_hi += (unsigned)__syncthreads_count(ts < thr_hi);
         }
+        c_lo += t_first; c_hi += t_first;                                      // the tiles in front of the slice all start below thr_lo
         const unsigned tA = c_lo == 0 ? 0u : c_lo - 1, tB = c_hi == 0 ? 0u : c_hi - 1;
         if (tid == 0) { mbar_init(mbar0, 1); mbar_init(mbar0 + 8, 1); }
         __syncthreads();
-        // candidate strata of tile t inside [K0, K1) (uniform over the CTA)
+        // exact running sum before tile t.  The first tile of a rank: from the walk's rank starts (this rank's own memory) --
+        // the table entry is pushed by that rank, which this CTA has not necessarily waited for (t may be one past its slice)
+        const bool rs_valid = world > 1 && sc->rank_start_valid;
+        auto tstart = [&](unsigned t) -> double {
+            if (rs_valid) { const unsigned q = t / T; if (q * T == t) return sc->rank_start[q]; }
+            return __ldcg(&A.tile_start[t]);
+        };
+        // candidate strata of tile t inside [K0, K1) (local stratum numbers; uniform over the CTA)
+        const double dbase = (double)base;
         auto range = [&](unsigned t, unsigned long long& klo, unsigned long long& khi) {
             klo = K0; khi = K1;
             if (t > 0) {
-                const double f = floor(__ldg(&tile_start[t]) * dn) - 2.0;
+                const double f = floor(tstart(t) * dn) - 2.0 - dbase;
                 if (f > (double)K0) klo = f >= (double)K1 ? K1 : (unsigned long long)f;
             }
-            if (t + 1 < n_tiles) {
-                const double c = floor(__ldg(&tile_start[t + 1]) * dn) + 3.0;
+            if (t + 1 < A.n_tiles) {
+                const double c = floor(tstart(t + 1) * dn) + 3.0 - dbase;
                 if (c < (double)K1) khi = c <= (double)K0 ? K0 : (unsigned long long)c;
             }
             if (klo > khi) klo = khi;
         };
         auto issue = [&](unsigned t, int stage) {                              // one thread: 10 bulk copies onto one mbarrier
-            const unsigned long long e0 = (unsigned long long)t * TILE;
+            const unsigned q = world > 1 ? t / T : 0u;
+            const unsigned long long e0 = (unsigned long long)(t - q * T) * TILE;          // owner-local first element
             const unsigned cnt = (unsigned)min((unsigned long long)TILE, n - e0);
             const uint32_t c8 = ((cnt + 1u) & ~1u) * 8u, c1 = (cnt + 15u) & ~15u;   // multiples of 16 bytes (buffers are padded)
             const uint32_t S = smem0 + (uint32_t)stage * RS_STAGE_BYTES, mb = mbar0 + 8u * (uint32_t)stage;
             mbar_expect_tx(mb, 8u * c8 + 2u * c1);
-            bulk_g2s(S, cdf + e0, c8, mb);
+            bulk_g2s(S, peers.cdf[q] + e0, c8, mb);
 #pragma unroll
-            for (int f = 0; f < 7; ++f) bulk_g2s(S + (uint32_t)(1 + f) * TILE * 8u, st.f[cur][f] + e0, c8, mb);
+            for (int f = 0; f < 7; ++f) bulk_g2s(S + (uint32_t)(1 + f) * TILE * 8u, peers.f[q][cur][f] + e0, c8, mb);
 #pragma unroll
-            for (int f = 0; f < 2; ++f) bulk_g2s(S + 8u * TILE * 8u + (uint32_t)f * TILE, st.b[cur][f] + e0, c1, mb);
+            for (int f = 0; f < 2; ++f) bulk_g2s(S + 8u * TILE * 8u + (uint32_t)f * TILE, peers.b[q][cur][f] + e0, c1, mb);
         };
         unsigned t = tA; unsigned long long klo = 0, khi = 0;
         while (t <= tB) { range(t, klo, khi); if (khi > klo) break; ++t; }
@@ -2329,20 +2444,22 @@ __global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevSc
             {
                 const unsigned char* S = rs_raw + (size_t)stage * RS_STAGE_BYTES;
                 const double* s_cdf = reinterpret_cast<const double*>(S);
-                const unsigned long long e0 = (unsigned long long)t * TILE;
+                const unsigned q = world > 1 ? t / T : 0u;
+                const unsigned long long e0 = (unsigned long long)(t - q * T) * TILE;
                 const unsigned cnt = (unsigned)min((unsigned long long)TILE, n - e0);
-                const double start = __ldg(&tile_start[t]), last = s_cdf[cnt - 1];
-                const bool first_tile = t == 0, last_tile = t + 1 == n_tiles;
+                const unsigned long long g0 = (unsigned long long)q * n + e0;  // global index of the tile's first element
+                const double start = tstart(t), last = s_cdf[cnt - 1];
+                const bool first_tile = t == 0, last_tile = t + 1 == A.n_tiles;
                 for (unsigned long long k = klo + tid; k < khi; k += 1024) {
-                    const unsigned long long gk = systematic ? 0ull : k;
-                    const em::Philox4 r = em::philox4x32_10((uint32_t)gk, sc->resample_step, 0, stream_word(em::STREAM_RESAMPLE, gk), k0key, k1key);
+                    const unsigned long long gk = A.systematic ? 0ull : base + k;
+                    const em::Philox4 r = em::philox4x32_10((uint32_t)gk, sc->resample_step, 0, stream_word(em::STREAM_RESAMPLE, gk), A.k0key, A.k1key);
                     const double u = em::u01(r.v[0], r.v[1]);
-                    const double sum_r = ((double)k + u) / dn;                                   // :98
+                    const double sum_r = ((double)(base + k) + u) / dn;                          // :98
                     if ((first_tile || start < sum_r) && (last_tile || !(last < sum_r))) {       // the ancestor lies in this tile
                         unsigned lo = 0, hi = cnt;                                               // first element with !(cdf < sum_r)
                         while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (s_cdf[mid] < sum_r) lo = mid + 1; else hi = mid; }
                         if (lo >= cnt) lo = cnt - 1;      // the reference walks off the end here; we stop at the last particle
-                        ancestors[k] = (uint32_t)(e0 + lo);
+                        A.ancestors[k] = (uint32_t)(g0 + lo);
 #pragma unroll
                         for (int f = 0; f < 7; ++f) st.f[nxt][f][k] = reinterpret_cast<const double*>(S + (size_t)(1 + f) * TILE * 8)[lo];   // :104 (Q3)
 #pragma unroll
@@ -2358,7 +2475,7 @@ __global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevSc
     __syncthreads();
     if (tid == 0) {
         __threadfence();
-        if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0; sc->cur ^= 1; sc->resample_step += 1; }
+        if (atomicAdd(A.ticket, 1u) == gridDim.x - 1) { *A.ticket = 0; sc->cur ^= 1; sc->resample_step += 1; }
     }
 }
 
