@@ -170,6 +170,11 @@ int eslam_gpu_weights_sum(eslam_gpu_ctx* ctx, double* sum);
 int eslam_gpu_normalize_weights(eslam_gpu_ctx* ctx, double* ess);
 /* ParticleFilter::resample -> resample_stratified(N) (src/ParticleFilter.hpp:72-108). */
 int eslam_gpu_resample(eslam_gpu_ctx* ctx);
+/* ParticleFilter::resample_stratified(samples) / resample_multinomial(samples) (src/ParticleFilter.hpp:85-147) with a sample
+ * count of their own: the set has `samples` particles afterwards (at most the capacity the context was initialised with; not
+ * on sharded contexts).  multinomial != 0: one uniform per sample, the first particle whose running sum reaches it, weights
+ * reset to 1 / old size (:140); a draw above the total weight takes the last particle (the reference drops that sample). */
+int eslam_gpu_resample_n(eslam_gpu_ctx* ctx, uint64_t samples, int multinomial);
 /* parity taps: ancestor index of every particle after the last resample; the exact running-sum CDF. */
 int eslam_gpu_get_ancestors(eslam_gpu_ctx* ctx, uint32_t* ancestors);
 int eslam_gpu_get_cdf(eslam_gpu_ctx* ctx, double* cdf);
@@ -196,6 +201,28 @@ int eslam_gpu_evaluate_poses(eslam_gpu_ctx* ctx, uint64_t n, const double* x, co
  * resampling copies it with the particle (cloneMaps, src/PoseEstimator.cpp:31-45).  Read-back: [n][P][P]{mean, stdev}
  * cells and [n][2] grid coordinates of each patch's cell (0, 0) (INT32_MIN: not anchored yet). */
 int eslam_gpu_get_patches(eslam_gpu_ctx* ctx, float* cells_mean_stdev, int32_t* origin_xy);
+
+/* EmbodiedSlamFilter::processMap(scanMap, match, update) (src/EmbodiedSlamFilter.cpp:179-232) in per-particle-map mode
+ * (cfg.patch_size > 0).  The scan is what envire's MLSProjection leaves in scanMap (:137-176, out of scope): a dense grid in the
+ * yaw-compensated body frame, cell (i, j) centred on offset + (i + 0.5, j + 0.5) * scale, {mean, stdev}, NaN = no surface.
+ * Per particle: C_s2p = Translation(x, y, 0) * AngleAxis(theta, Z) (:190-193,:209), offsetPatch(zPos, zSigma) (:212);
+ *   match  != 0: weight = MLSGrid::match(scan, C_s2p, offset, sampling = 10, sigma = 0.2); p.weight *= pow(weight, 0.1) (:214-221)
+ *   update != 0: MLSGrid::merge(scan, C_s2p, offset) into the particle's own patch (:222-227).
+ * envire's match / merge are not vendored: include/eslam_gpu.h's definition is the one of oracle/eslam_oracle.cpp::process_map
+ * (merge: every scan surface, row-major, Kalman-merged in float into the patch cell its centre falls in; match: 10 evenly
+ * strided scan surfaces looked up in the particle's map -- patch first, then the shared grid, 3-sigma gate -- weight = mean of
+ * exp(-d^2 / (2 sigma^2)) over the hits, 1 without a hit). */
+typedef struct eslam_gpu_scan {
+    const float* cells_mean_stdev; int32_t width, height;
+    double scale_x, scale_y, offset_x, offset_y;
+} eslam_gpu_scan;
+int eslam_gpu_process_map(eslam_gpu_ctx* ctx, const eslam_gpu_scan* scan, int match, int update);
+
+/* The mixture part of eslam::PoseDistribution (src/PoseParticle.hpp:88-114; the Rock task around the library logs particles +
+ * a Gaussian mixture over the poses): weighted mean and covariance of the particles' (x, y) as ONE Gaussian, reduced on the
+ * device over all shards (pairwise trees: the result does not depend on the number of GPUs).  cov is row major. */
+typedef struct eslam_gpu_gaussian2d { double weight; double mean[2]; double cov[4]; } eslam_gpu_gaussian2d;
+int eslam_gpu_pose_moments(eslam_gpu_ctx* ctx, eslam_gpu_gaussian2d* out);
 
 int eslam_gpu_synchronize(eslam_gpu_ctx* ctx);
 /* diagnostics of the exact running-sum machinery: out = {sequential-fallback runs, boundary elements of the last

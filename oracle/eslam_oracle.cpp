@@ -396,6 +396,113 @@ struct eslam_oracle_ctx {
         }
     }
 
+    // --- EmbodiedSlamFilter::processMap(scanMap, match, update)  src/EmbodiedSlamFilter.cpp:179-232, per-particle-map mode.
+    //     The scan (MLSProjection's output in the yaw-compensated body frame, :137-176) arrives as a dense grid; per particle:
+    //     C_s2p = Translation(x, y, 0) * AngleAxis(theta, Z) (:190-193,:209), offsetPatch(zPos, zSigma) (:212),
+    //     match -> p.weight *= pow(weight, 0.1) (:214-221), merge (:222-227).  envire's MLSGrid::match / merge are not
+    //     vendored (parity unpinned); THIS is their definition for the dense single-surface grid:
+    //       merge : every scan cell with a surface, in row-major order: its centre goes through C_s2p into the particle's map
+    //               cell; {mean + zPos, sqrt(stdev^2 + zSigma^2)} is Kalman-merged (float) into that cell of the particle's
+    //               patch (anchored on the particle's own cell at its first write; cells outside the patch are dropped);
+    //       match : `sampling` scan cells with a surface, evenly strided through the row-major list; each is looked up in
+    //               the particle's map as it was before this scan's merge (patch first, then the shared grid, 3-sigma gate
+    //               on the offset height); weight = mean over the hits of exp(-d^2 / (2 sigma^2)), 1 without any hit,
+    //               returned as float like upstream.
+    struct ScanCell { double x, y; float mean, stdev; };
+    std::vector<ScanCell> scan_cells;
+    template <class A>
+    void patch_merge(size_t i, int ix, int iy, float zm, float sd, double px, double py) {
+        const int P = cfg.patch_size;
+        int32_t* org = &patch_origin[2 * i];
+        if (org[0] == INT32_MIN) {                              // anchor the patch on the particle's own cell
+            int cx, cy;
+            double gx = px, gy = py;
+            if (!grid.identity) { const double* g = grid.g2l; gx = em::fma_(g[0], px, em::fma_(g[1], py, g[3])); gy = em::fma_(g[4], px, em::fma_(g[5], py, g[7])); }
+            if (!em::cell_index_exact(gx, grid.ox, grid.sx, grid.w, cx) || !em::cell_index_exact(gy, grid.oy, grid.sy, grid.h, cy)) return;
+            org[0] = cx - P / 2; org[1] = cy - P / 2;
+        }
+        const int lx = ix - org[0], ly = iy - org[1];
+        if (lx < 0 || lx >= P || ly < 0 || ly >= P) return;
+        float* cell = &patches[(i * P * P + (size_t)ly * P + lx) * 2];
+        if (std::isnan(cell[0]) || std::isnan(cell[1])) { cell[0] = zm; cell[1] = sd; }
+        else {                                                  // Kalman merge of two height estimates
+            const float v0 = cell[1] * cell[1], v1 = sd * sd;
+            const float kg = v0 / (v0 + v1);
+            cell[0] = cell[0] + kg * (zm - cell[0]);
+            cell[1] = std::sqrt((1.0f - kg) * v0);
+        }
+    }
+    template <class A>
+    int process_map(const eslam_gpu_scan* scan, int match, int update) {
+        if (cfg.patch_size <= 0 || patches.empty()) return ESLAM_ERR_INVALID;
+        if (!grid.attached) return ESLAM_ERR_NO_ENVIRONMENT;
+        scan_cells.clear();
+        for (int j = 0; j < scan->height; j++)
+            for (int k = 0; k < scan->width; k++) {
+                const float m = scan->cells_mean_stdev[2 * ((size_t)j * scan->width + k)], sd = scan->cells_mean_stdev[2 * ((size_t)j * scan->width + k) + 1];
+                if (std::isnan(m) || std::isnan(sd)) continue;
+                ScanCell c; c.x = scan->offset_x + (k + 0.5) * scan->scale_x; c.y = scan->offset_y + (j + 0.5) * scan->scale_y; c.mean = m; c.stdev = sd;
+                scan_cells.push_back(c);
+            }
+        const size_t M = scan_cells.size();
+        const size_t sampling = 10; const double sigma = 0.2, visualWeighting = 0.1;   // src/EmbodiedSlamFilter.cpp:216-220
+        const size_t n_samples = std::min(sampling, M);
+        for (size_t i = 0; i < xi_k.size(); i++) {
+            PoseParticle& p(xi_k[i]);
+            double s, c; A::sincos(p.orientation, s, c);        // :190-193
+            const double ox = p.px, oy = p.py;
+            if (match && n_samples > 0) {                       // :214-221
+                double wsum = 0; size_t hits = 0;
+                for (size_t j = 0; j < n_samples; j++) {
+                    const ScanCell& sc_ = scan_cells[j * M / n_samples];
+                    Vec3 w; w.x = em::fma_(c, sc_.x, em::fma_(-s, sc_.y, ox)); w.y = em::fma_(s, sc_.x, em::fma_(c, sc_.y, oy));
+                    w.z = (double)sc_.mean + p.zPos;
+                    const double qvar = (double)sc_.stdev * (double)sc_.stdev + p.zSigma * p.zSigma;
+                    SurfacePatch patch = {w.z, A::sqrt(qvar)};
+                    int cix, ciy;
+                    if (map_get<A>(w, patch, qvar, nullptr, (long)i, &cix, &ciy)) {
+                        const double d = w.z - patch.mean;
+                        wsum += A::exp(-(d * d) / (2.0 * sigma * sigma));
+                        hits++;
+                    }
+                }
+                const float weight = hits ? (float)(wsum / (double)hits) : 1.0f;
+                p.weight *= A::shared ? em::exp_(visualWeighting * em::log_((double)weight)) : std::pow((double)weight, visualWeighting);   // :220
+            }
+            if (update) {                                       // :222-227
+                for (size_t j = 0; j < M; j++) {
+                    const ScanCell& sc_ = scan_cells[j];
+                    const double wx = em::fma_(c, sc_.x, em::fma_(-s, sc_.y, ox)), wy = em::fma_(s, sc_.x, em::fma_(c, sc_.y, oy));
+                    double gx = wx, gy = wy;
+                    if (!grid.identity) { const double* g = grid.g2l; gx = em::fma_(g[0], wx, em::fma_(g[1], wy, g[3])); gy = em::fma_(g[4], wx, em::fma_(g[5], wy, g[7])); }
+                    int ix, iy;
+                    if (!em::cell_index_exact(gx, grid.ox, grid.sx, grid.w, ix) || !em::cell_index_exact(gy, grid.oy, grid.sy, grid.h, iy)) continue;
+                    const float zm = (float)((double)sc_.mean + p.zPos);
+                    const float sd = (float)A::sqrt((double)sc_.stdev * (double)sc_.stdev + p.zSigma * p.zSigma);
+                    patch_merge<A>(i, ix, iy, zm, sd, ox, oy);
+                }
+            }
+        }
+        return ESLAM_OK;
+    }
+
+    // --- weighted mean and covariance of the particles' (x, y): the single-component mixture a PoseDistribution carries
+    //     (src/PoseParticle.hpp:88-114); sums in the policy's order
+    template <class A>
+    void pose_moments(eslam_gpu_gaussian2d* out) {
+        const size_t n = xi_k.size();
+        std::vector<double> w(n), wx(n), wy(n);
+        for (size_t i = 0; i < n; i++) { w[i] = xi_k[i].weight; wx[i] = xi_k[i].px * w[i]; wy[i] = xi_k[i].py * w[i]; }
+        const double W = A::sum(w), mx = A::sum(wx) / W, my = A::sum(wy) / W;
+        std::vector<double> cxx(n), cxy(n), cyy(n);
+        for (size_t i = 0; i < n; i++) {
+            const double dx = xi_k[i].px - mx, dy = xi_k[i].py - my;
+            cxx[i] = w[i] * dx * dx; cxy[i] = w[i] * dx * dy; cyy[i] = w[i] * dy * dy;
+        }
+        out->weight = W; out->mean[0] = mx; out->mean[1] = my;
+        out->cov[0] = A::sum(cxx) / W; out->cov[1] = out->cov[2] = A::sum(cxy) / W; out->cov[3] = A::sum(cyy) / W;
+    }
+
     // --- ContactModel::updateZPositionEstimate  src/ContactModel.cpp:319-340
     bool updateZPositionEstimate(double& z_pos, double& z_var) {
         const double pose_var = m_poseVar / contact_points.size();      // :321
@@ -608,13 +715,46 @@ struct eslam_oracle_ctx {
         xi_k.swap(xi_kp);                                       // :107
         if (cfg.patch_size > 0 && !patches.empty()) {           // cloneMaps, src/PoseEstimator.cpp:31-45: maps travel with copies
             const size_t cells = (size_t)cfg.patch_size * cfg.patch_size * 2;
-            std::vector<float> np(patches.size()); std::vector<int32_t> no(patch_origin.size());
+            std::vector<float> np(samples * cells); std::vector<int32_t> no(2 * samples);
             for (size_t k = 0; k < samples; k++) {
                 std::memcpy(&np[k * cells], &patches[ancestors[k] * cells], cells * sizeof(float));
                 no[2 * k] = patch_origin[2 * ancestors[k]]; no[2 * k + 1] = patch_origin[2 * ancestors[k] + 1];
             }
             patches.swap(np); patch_origin.swap(no);
         }
+        resample_step++;
+        return ESLAM_OK;
+    }
+    // --- ParticleFilter::resample_multinomial(samples)  src/ParticleFilter.hpp:120-147 (unused by the filter itself)
+    int resample_multinomial(size_t samples) {
+        if (xi_k.empty()) return ESLAM_ERR_EMPTY;               // assert :126
+        std::vector<PoseParticle> xi_kp;
+        ancestors.assign(samples, 0);
+        cdf.assign(xi_k.size(), 0.0);
+        { double s = xi_k[0].weight; cdf[0] = s; for (size_t i = 1; i < xi_k.size(); i++) { s += xi_k[i].weight; cdf[i] = s; } }
+        for (size_t n = 0; n < samples; n++) {                  // :129
+            em::Philox4 r = noise.draw(n, resample_step, 0, em::STREAM_RESAMPLE);
+            const double r_n = em::u01(r.v[0], r.v[1]);         // :132
+            double sum = 0; size_t pick = xi_k.size() - 1;      // the reference drops a draw above the total (:134-143 finds nothing);
+            for (size_t i = 0; i < xi_k.size(); i++) {          //  we keep the set size and take the last particle
+                sum = i == 0 ? xi_k[0].weight : sum + xi_k[i].weight;   // :136
+                if (r_n <= sum) { pick = i; break; }            // :137
+            }
+            PoseParticle p(xi_k[pick]);                         // :139
+            p.weight = 1.0 / xi_k.size();                       // :140
+            xi_kp.push_back(p);
+            ancestors[n] = (uint32_t)pick;
+        }
+        if (cfg.patch_size > 0 && !patches.empty()) {
+            const size_t cells = (size_t)cfg.patch_size * cfg.patch_size * 2;
+            std::vector<float> np(samples * cells); std::vector<int32_t> no(2 * samples);
+            for (size_t k = 0; k < samples; k++) {
+                std::memcpy(&np[k * cells], &patches[ancestors[k] * cells], cells * sizeof(float));
+                no[2 * k] = patch_origin[2 * ancestors[k]]; no[2 * k + 1] = patch_origin[2 * ancestors[k] + 1];
+            }
+            patches.swap(np); patch_origin.swap(no);
+        }
+        xi_k.swap(xi_kp);                                       // :146
         resample_step++;
         return ESLAM_OK;
     }
@@ -784,6 +924,11 @@ int eslam_oracle_set_particles(eslam_oracle_ctx* ctx, uint64_t n, const double* 
     if (ctx->xi_k.size() != n) {
         PoseParticle p; std::memset(&p, 0, sizeof(p)); p.floating = true;
         ctx->xi_k.assign(n, p);
+        if (ctx->cfg.patch_size > 0) {                          // a fresh set: empty maps, like eslam_gpu_set_particles
+            const size_t cells = (size_t)ctx->cfg.patch_size * ctx->cfg.patch_size * 2;
+            ctx->patches.assign(n * cells, std::numeric_limits<float>::quiet_NaN());
+            ctx->patch_origin.assign(2 * n, INT32_MIN);
+        }
     }
     for (uint64_t i = 0; i < n; i++) {
         PoseParticle& p = ctx->xi_k[i];
@@ -841,6 +986,12 @@ int eslam_oracle_resample(eslam_oracle_ctx* ctx) {
     if (ctx->xi_k.empty()) return ESLAM_ERR_EMPTY;
     DISPATCH(ctx, ctx->shard_decision<Literal>(), ctx->shard_decision<Shared>());   // on the weights as they are
     return ctx->resample_any();
+}
+
+int eslam_oracle_resample_n(eslam_oracle_ctx* ctx, uint64_t samples, int multinomial) {
+    if (!ctx || samples == 0) return ESLAM_ERR_INVALID;
+    if (ctx->xi_k.empty()) return ESLAM_ERR_EMPTY;
+    return multinomial ? ctx->resample_multinomial((size_t)samples) : ctx->resample_stratified((size_t)samples);
 }
 
 int eslam_oracle_get_ancestors(eslam_oracle_ctx* ctx, uint32_t* a) {
@@ -933,6 +1084,19 @@ int eslam_oracle_lowest_points(const eslam_gpu_contact* pts, int n_pts, int upda
     }
     if (contact_out) for (int i = 0; i < n_pts; i++) contact_out[i] = contactPoints[i].contact;
     return count;
+}
+
+int eslam_oracle_process_map(eslam_oracle_ctx* ctx, const eslam_gpu_scan* scan, int match, int update) {
+    if (!ctx || !scan || !scan->cells_mean_stdev || scan->width <= 0 || scan->height <= 0) return ESLAM_ERR_INVALID;
+    if (ctx->xi_k.empty()) return ESLAM_ERR_EMPTY;
+    return DISPATCH(ctx, ctx->process_map<Literal>(scan, match, update), ctx->process_map<Shared>(scan, match, update));
+}
+
+int eslam_oracle_pose_moments(eslam_oracle_ctx* ctx, eslam_gpu_gaussian2d* out) {
+    if (!ctx || !out) return ESLAM_ERR_INVALID;
+    if (ctx->xi_k.empty()) return ESLAM_ERR_EMPTY;
+    DISPATCH(ctx, ctx->pose_moments<Literal>(out), ctx->pose_moments<Shared>(out));
+    return ESLAM_OK;
 }
 
 int eslam_oracle_get_patches(eslam_oracle_ctx* ctx, float* cells, int32_t* origin_xy) {

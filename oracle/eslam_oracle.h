@@ -49,6 +49,7 @@ int eslam_oracle_project(eslam_oracle_ctx* ctx, const eslam_gpu_step* step);
 int eslam_oracle_update(eslam_oracle_ctx* ctx, const eslam_gpu_contact* pts, int n_pts, eslam_gpu_update_result* result);
 int eslam_oracle_normalize_weights(eslam_oracle_ctx* ctx, double* ess);
 int eslam_oracle_resample(eslam_oracle_ctx* ctx);
+int eslam_oracle_resample_n(eslam_oracle_ctx* ctx, uint64_t samples, int multinomial);
 int eslam_oracle_get_ancestors(eslam_oracle_ctx* ctx, uint32_t* ancestors);
 int eslam_oracle_get_cdf(eslam_oracle_ctx* ctx, double* cdf);
 int eslam_oracle_centroid(eslam_oracle_ctx* ctx, double out[4]);
@@ -60,6 +61,8 @@ int eslam_oracle_evaluate_poses(eslam_oracle_ctx* ctx, uint64_t n, const double*
                                 int32_t* n_contacts, double* zpos_out, double* z_var_out,
                                 int32_t* cell_index, double* cp);
 int eslam_oracle_get_patches(eslam_oracle_ctx* ctx, float* cells_mean_stdev, int32_t* origin_xy);
+int eslam_oracle_process_map(eslam_oracle_ctx* ctx, const eslam_gpu_scan* scan, int match, int update);
+int eslam_oracle_pose_moments(eslam_oracle_ctx* ctx, eslam_gpu_gaussian2d* out);
 
 /* FakeMLSAccess of test/testContactModel.cpp:8-38 as the map: 4 quadrants, index = 2*(y>0) + (x>0);
  * res may be NULL (all present).  Replaces the grid for evaluate_poses; queried points are recorded. */

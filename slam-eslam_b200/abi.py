@@ -70,6 +70,15 @@ class Contact(C.Structure):
                 ("group_id", C.c_int32), ("pad", C.c_int32)]
 
 
+class Scan(C.Structure):
+    _fields_ = [("cells", C.POINTER(C.c_float)), ("width", C.c_int32), ("height", C.c_int32),
+                ("scale_x", C.c_double), ("scale_y", C.c_double), ("offset_x", C.c_double), ("offset_y", C.c_double)]
+
+
+class Gaussian2d(C.Structure):
+    _fields_ = [("weight", C.c_double), ("mean", C.c_double * 2), ("cov", C.c_double * 4)]
+
+
 class UpdateResult(C.Structure):
     _fields_ = [("ess", C.c_double), ("max_weight", C.c_double), ("floating_weight", C.c_double),
                 ("weights_sum", C.c_double), ("data_particles", C.c_uint64), ("total_points", C.c_uint64),
@@ -118,6 +127,7 @@ SIGNATURES = {
     "update": (C.c_int, [C.c_void_p, C.POINTER(Contact), C.c_int, C.POINTER(UpdateResult)]),
     "normalize_weights": (C.c_int, [C.c_void_p, _dp]),
     "resample": (C.c_int, [C.c_void_p]),
+    "resample_n": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int]),
     "get_ancestors": (C.c_int, [C.c_void_p, _u32p]),
     "get_cdf": (C.c_int, [C.c_void_p, _dp]),
     "centroid": (C.c_int, [C.c_void_p, _dp]),
@@ -125,6 +135,8 @@ SIGNATURES = {
     "evaluate_poses": (C.c_int, [C.c_void_p, C.c_uint64] + [_dp] * 6 + [C.POINTER(Contact), C.c_int, _u8p]
                        + [_dp] * 4 + [_i32p, _dp, _dp, _i32p, _dp]),
     "get_patches": (C.c_int, [C.c_void_p, _fp, _i32p]),
+    "process_map": (C.c_int, [C.c_void_p, C.POINTER(Scan), C.c_int, C.c_int]),
+    "pose_moments": (C.c_int, [C.c_void_p, C.POINTER(Gaussian2d)]),
 }
 
 GPU_ONLY = {

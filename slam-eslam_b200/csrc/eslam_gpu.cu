@@ -75,6 +75,7 @@ struct eslam_gpu_ctx {
     PeerTable peers; bool has_peers; std::vector<void*> ipc_opened;
     // map
     float2* cells; MapParams map; bool has_map;
+    void* scan_cells; size_t scan_cap;                // processMap: the scan's surfaces on the device
     CUtensorMap tmap; CUtensorMap* d_tmap; bool has_tmap;   // TMA descriptor of the grid (host copy, device copy)
     em::dbl2* htab;
     int max_smem_optin, sm_count;
@@ -459,7 +460,7 @@ void eslam_gpu_destroy(eslam_gpu_ctx* ctx) {
     if (ctx->sc_host) cudaFreeHost(ctx->sc_host);
     cudaFree(ctx->sc); cudaFree(ctx->d_tmap); cudaFree(ctx->htab); cudaFree(ctx->cells); cudaFree(ctx->hint); cudaFree(ctx->ticket);
     cudaFree(ctx->bin_count); cudaFree(ctx->bin_offs); cudaFree(ctx->bin_next); cudaFree(ctx->cta_bin);
-    cudaFree(ctx->shard_tot); cudaFree(ctx->shard_sums);
+    cudaFree(ctx->shard_tot); cudaFree(ctx->shard_sums); cudaFree(ctx->scan_cells);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     for (auto& m : ctx->marks) cudaEventDestroy(m.second);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -729,7 +730,7 @@ static unsigned weight_grid(const eslam_gpu_ctx* ctx) {
 #ifndef RS_CTA
 #define RS_CTA 1024               // strata (threads) per CTA of k_resample_local (512 measured the same)
 #endif
-static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int mode, int force) {
+static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int mode, int force, bool cdf_only = false) {
     const unsigned T = ctx->t_local, TG = ctx->t_global;
     const uint64_t n = ctx->n, ng = global_count(ctx);
     const ShardPlan sp = shard_plan(ctx);
@@ -753,6 +754,7 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     CdfArgs cd; cd.tile_prefix = ctx->tile_prefix; cd.tile_bofs = ctx->tile_bofs; cd.sb = ctx->sb; cd.cdf = ctx->cdf; cd.eps = ns.eps; cd.tile_ofs = tile_ofs(ctx);
     CK(launch_pdl(ctx, k_cdf, T, SCAN_THREADS, 0, ctx->st, ctx->sc, n, cd, sp, ctx->X));
     LAUNCHED();
+    if (cdf_only) return ESLAM_OK;                                        // the caller walks the running sum itself
     const ModelParams mp = model_params(ctx);
     const int systematic = ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC;
     double* tile_sin = tile_sin_table(ctx);
@@ -1000,6 +1002,33 @@ int eslam_gpu_resample(eslam_gpu_ctx* ctx) {
     return launch_tail(ctx, false, 0, 0, 1);
 }
 
+int eslam_gpu_resample_n(eslam_gpu_ctx* ctx, uint64_t samples, int multinomial) {
+    int st = check_ready(ctx, false);
+    if (st != ESLAM_OK) return st;
+    if (samples == 0) return ESLAM_ERR_INVALID;
+    if (sharded(ctx)) { ctx->error = "resample_stratified(samples) / resample_multinomial are not available on sharded contexts"; return ESLAM_ERR_INVALID; }
+    if (samples > ctx->cap) { ctx->error = "more samples than the capacity the context was initialised with"; return ESLAM_ERR_INVALID; }
+    if (samples == ctx->n && !multinomial) return launch_tail(ctx, false, 0, 0, 1);   // resample(): the step's own kernels
+    eslam_gpu_config saved = ctx->cfg;
+    ctx->cfg.shard_mode = ESLAM_SHARD_EXACT_GLOBAL;                       // one walk over all particles
+    st = launch_tail(ctx, false, 0, 0, 1, true);                          // exact running sum of the weights as they are
+    ctx->cfg = saved;
+    if (st != ESLAM_OK) return st;
+    const ModelParams mp = model_params(ctx);
+    ResampleNArgs A; memset(&A, 0, sizeof(A));
+    A.cdf = ctx->cdf; A.tile_start = tile_sin_table(ctx); A.n_tiles = ctx->t_local; A.n = ctx->n; A.samples = samples;
+    A.k0key = mp.k0; A.k1key = mp.k1; A.systematic = ctx->cfg.resample_mode == ESLAM_RESAMPLE_SYSTEMATIC; A.multinomial = multinomial;
+    A.ancestors = ctx->ancestors; A.P = ctx->cfg.patch_size > 0 ? ctx->cfg.patch_size : 0;
+    for (int b = 0; b < 2; ++b) { A.patch[b] = ctx->patch[b]; A.porigin[b] = ctx->porigin[b]; }
+    k_resample_n<<<(unsigned)((samples + 255) / 256), 256, 0, ctx->stream>>>(ctx->st, ctx->sc, A);
+    LAUNCHED();
+    k_after_resample_n<<<1, 1, 0, ctx->stream>>>(ctx->sc);
+    LAUNCHED();
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n = samples; ctx->t_local = (unsigned)((samples + TILE - 1) / TILE); ctx->t_global = ctx->t_local;
+    return ESLAM_OK;
+}
+
 int eslam_gpu_get_ancestors(eslam_gpu_ctx* ctx, uint32_t* a) {
     int st = check_ready(ctx, false);
     if (st != ESLAM_OK) return st;
@@ -1109,6 +1138,67 @@ int eslam_gpu_path_counters(eslam_gpu_ctx* ctx, uint64_t out[2]) {
     int st = read_scalars(ctx);
     if (st != ESLAM_OK) return st;
     out[0] = ctx->last_lean ? ctx->n : 0; out[1] = ctx->last_lean ? ctx->sc_host->defer_last : ctx->n;
+    return ESLAM_OK;
+}
+
+int eslam_gpu_process_map(eslam_gpu_ctx* ctx, const eslam_gpu_scan* scan, int match, int update) {
+    int st = check_ready(ctx, true);
+    if (st != ESLAM_OK) return st;
+    if (!scan || !scan->cells_mean_stdev || scan->width <= 0 || scan->height <= 0) return ESLAM_ERR_INVALID;
+    if (ctx->cfg.patch_size <= 0) {
+        ctx->error = "processMap needs per-particle maps (patch_size > 0: EmbodiedSlamFilter::init with useSharedMap == false)";
+        return ESLAM_ERR_INVALID;
+    }
+    // the scan cells that hold a surface, in row-major order, with their centres in the scan frame
+    std::vector<ScanCell> cells;
+    cells.reserve((size_t)scan->width * scan->height);
+    for (int j = 0; j < scan->height; ++j)
+        for (int k = 0; k < scan->width; ++k) {
+            const float m = scan->cells_mean_stdev[2 * ((size_t)j * scan->width + k)], sd = scan->cells_mean_stdev[2 * ((size_t)j * scan->width + k) + 1];
+            if (m != m || sd != sd) continue;
+            ScanCell c; c.x = scan->offset_x + (k + 0.5) * scan->scale_x; c.y = scan->offset_y + (j + 0.5) * scan->scale_y; c.mean = m; c.stdev = sd;
+            cells.push_back(c);
+        }
+    if (cells.empty()) return ESLAM_OK;
+    if (cells.size() > ctx->scan_cap) {
+        cudaFree(ctx->scan_cells); ctx->scan_cells = nullptr; ctx->scan_cap = 0;
+        CK(cudaMalloc((void**)&ctx->scan_cells, cells.size() * sizeof(ScanCell)));
+        ctx->scan_cap = cells.size();
+    }
+    CK(cudaMemcpyAsync(ctx->scan_cells, cells.data(), cells.size() * sizeof(ScanCell), cudaMemcpyHostToDevice, ctx->stream));
+    ProcessMapArgs A; memset(&A, 0, sizeof(A));
+    const double sigma = 0.2;                                            // src/EmbodiedSlamFilter.cpp:216-217
+    A.cells = reinterpret_cast<const ScanCell*>(ctx->scan_cells); A.n_cells = (unsigned)cells.size();
+    A.n_samples = (unsigned)std::min<size_t>(10, cells.size());          // sampling = 10  :216
+    A.match = match; A.update = update; A.P = ctx->cfg.patch_size;
+    A.two_sigma2 = 2.0 * sigma * sigma; A.visual = 0.1;                  // visualWeighting :219
+    for (int b = 0; b < 2; ++b) { A.patch[b] = ctx->patch[b]; A.porigin[b] = ctx->porigin[b]; }
+    A.grid = ctx->cells; A.map = ctx->map;
+    k_process_map<<<(unsigned)((ctx->n * 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->n, A);
+    LAUNCHED();
+    CK(cudaStreamSynchronize(ctx->stream));                              // `cells` (host) is borrowed until the copy has run
+    return ESLAM_OK;
+}
+
+int eslam_gpu_pose_moments(eslam_gpu_ctx* ctx, eslam_gpu_gaussian2d* out) {
+    int st = check_ready(ctx, false);
+    if (st != ESLAM_OK) return st;
+    if (!out) return ESLAM_ERR_INVALID;
+    st = launch_centroid(ctx);                                           // sums of w x, w y, ..., w over all shards
+    if (st != ESLAM_OK) return st;
+    const double W = ctx->sc_host->centroid[4];
+    const double mx = ctx->sc_host->centroid[0] / W, my = ctx->sc_host->centroid[1] / W;
+    k_moment_tiles<<<ctx->t_local, 1024, 0, ctx->stream>>>(ctx->st, ctx->sc, ctx->n, mx, my, ctx->l_cent);
+    LAUNCHED();
+    AG(ctx->l_cent, ctx->g_cent, ctx->t_local * 5 * sizeof(double));
+    k_centroid_final<<<1, 1024, 0, ctx->stream>>>(ctx->g_cent, ctx->t_global, ctx->scratch_a, ctx->scratch_b, ctx->g_best_idx,
+                                                  ctx->g_best_w, ctx->sc);
+    LAUNCHED();
+    st = read_scalars(ctx);
+    if (st != ESLAM_OK) return st;
+    const double* c = ctx->sc_host->centroid;
+    out->weight = W; out->mean[0] = mx; out->mean[1] = my;
+    out->cov[0] = c[0] / W; out->cov[1] = out->cov[2] = c[1] / W; out->cov[3] = c[2] / W;
     return ESLAM_OK;
 }
 

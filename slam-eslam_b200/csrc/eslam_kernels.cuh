@@ -2479,6 +2479,182 @@ __global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevSc
     }
 }
 
+// ------------------------------------------------------------------------------------------------ processMap
+// EmbodiedSlamFilter::processMap(scanMap, match, update) (src/EmbodiedSlamFilter.cpp:179-232) in per-particle-map mode: one
+// warp per particle.  match: lane j evaluates the j-th sampled scan surface against the particle's map (patch first, then the
+// shared grid, 3-sigma gate), lane 0 adds the hits in sample order; p.weight *= pow(weight, 0.1) (:214-221).  merge: the scan
+// surfaces go through C_s2p 32 at a time in row-major order; lanes whose surfaces fall into the SAME patch cell apply their
+// Kalman merges one after the other in lane order, so every cell sees its merges in the order of the sequential loop
+// (:222-227).  Definition of match / merge: include/eslam_gpu.h eslam_gpu_process_map.
+struct ScanCell { double x, y; float mean, stdev; };   // centre of a scan cell with a surface (scan frame), its {mean, stdev}
+struct ProcessMapArgs {
+    const ScanCell* cells; unsigned n_cells, n_samples;
+    int match, update, P;
+    double two_sigma2, visual;
+    float2* patch[2]; int* porigin[2];
+    const float2* grid; MapParams map;
+};
+
+__device__ __forceinline__ void patch_merge_cell(float2* cell, float zm, float sd) {
+    float2 cv = *cell;
+    if (!(cv.x == cv.x) || !(cv.y == cv.y)) { cv.x = zm; cv.y = sd; }
+    else {                                                               // Kalman merge of two height estimates (float)
+        const float v0 = cv.y * cv.y, v1 = sd * sd;
+        const float kg = __fdiv_rn(v0, v0 + v1);
+        cv.x = cv.x + kg * (zm - cv.x);
+        cv.y = __fsqrt_rn((1.0f - kg) * v0);
+    }
+    *cell = cv;
+}
+
+__global__ void __launch_bounds__(256) k_process_map(StateBufs st, DevScalars* sc, unsigned long long n, const ProcessMapArgs A) {
+    const unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;                                                  // whole warps leave together
+    const unsigned lane = threadIdx.x & 31;
+    const int cur = sc->cur, P = A.P;
+    const MapParams& M = A.map;
+    const double x = st.f[cur][F_X][i], y = st.f[cur][F_Y][i], th = st.f[cur][F_TH][i];
+    const double zpos = st.f[cur][F_Z][i], zs = st.f[cur][F_ZS][i];
+    double s, c; em::sincos_(th, s, c);                                  // :190-193
+    float2* patch = A.patch[cur] + i * (size_t)P * P;
+    int* origin = A.porigin[cur] + 2 * i;
+    int ox = origin[0], oy = origin[1];
+    if (A.match && A.n_samples > 0) {                                    // :214-221
+        double wj = 0.0; int hit = 0;
+        if (lane < A.n_samples) {
+            const ScanCell q = A.cells[(unsigned long long)lane * A.n_cells / A.n_samples];
+            const double wx = em::fma_(c, q.x, em::fma_(-s, q.y, x)), wy = em::fma_(s, q.x, em::fma_(c, q.y, y));
+            const double wz = (double)q.mean + zpos;
+            const double qvar = (double)q.stdev * (double)q.stdev + zs * zs;
+            double gx = wx, gy = wy;
+            if (!M.identity) {
+                gx = em::fma_(M.g2l[0], wx, em::fma_(M.g2l[1], wy, em::fma_(M.g2l[2], wz, M.g2l[3])));
+                gy = em::fma_(M.g2l[4], wx, em::fma_(M.g2l[5], wy, em::fma_(M.g2l[6], wz, M.g2l[7])));
+            }
+            int ix, iy;
+            if (em::cell_index_exact(gx, M.ox, M.sx, M.W, ix) && em::cell_index_exact(gy, M.oy, M.sy, M.H, iy)) {
+                float2 cell = A.grid[(size_t)iy * M.W + ix];
+                bool found = false;
+                const unsigned lx = (unsigned)(ix - ox), ly = (unsigned)(iy - oy);
+                if (ox != INT_MIN && lx < (unsigned)P && ly < (unsigned)P) {     // the particle's own map first
+                    const float2 pc = patch[ly * P + lx];
+                    if (pc.x == pc.x && pc.y == pc.y) {
+                        const double dp = wz - (double)pc.x;
+                        if (dp * dp < 9.0 * ((double)pc.y * (double)pc.y + qvar)) { cell = pc; found = true; }
+                    }
+                }
+                if (!found && cell.x == cell.x && cell.y == cell.y) {
+                    const double d0 = wz - (double)cell.x;
+                    const double zvar = (double)cell.y * (double)cell.y + qvar;
+                    found = d0 * d0 < 9.0 * zvar;
+                }
+                if (found) { const double d = wz - (double)cell.x; wj = em::exp_(-(d * d) / A.two_sigma2); hit = 1; }
+            }
+        }
+        double wsum = 0.0; unsigned hits = 0;
+        for (unsigned j = 0; j < A.n_samples; ++j) {                     // in sample order (every lane keeps the same sums)
+            const double v = __shfl_sync(0xffffffffu, wj, j); const int h = __shfl_sync(0xffffffffu, hit, j);
+            if (h) { wsum += v; hits++; }
+        }
+        if (lane == 0) {
+            const float weight = hits ? (float)(wsum / (double)hits) : 1.0f;
+            st.f[cur][F_W][i] *= em::exp_(A.visual * em::log_((double)weight));   // pow(weight, visualWeighting) :220
+        }
+    }
+    if (!A.update) return;
+    for (unsigned b0 = 0; b0 < A.n_cells; b0 += 32) {                    // :222-227
+        const unsigned k = b0 + lane;
+        bool valid = false; int ix = 0, iy = 0; float zm = 0.f, sd = 0.f;
+        if (k < A.n_cells) {
+            const ScanCell q = A.cells[k];
+            const double wx = em::fma_(c, q.x, em::fma_(-s, q.y, x)), wy = em::fma_(s, q.x, em::fma_(c, q.y, y));
+            double gx = wx, gy = wy;
+            if (!M.identity) {
+                gx = em::fma_(M.g2l[0], wx, em::fma_(M.g2l[1], wy, M.g2l[3]));
+                gy = em::fma_(M.g2l[4], wx, em::fma_(M.g2l[5], wy, M.g2l[7]));
+            }
+            valid = em::cell_index_exact(gx, M.ox, M.sx, M.W, ix) && em::cell_index_exact(gy, M.oy, M.sy, M.H, iy);
+            zm = (float)((double)q.mean + zpos);
+            sd = (float)em::sqrt_((double)q.stdev * (double)q.stdev + zs * zs);
+        }
+        if (ox == INT_MIN && __any_sync(0xffffffffu, valid)) {           // anchor the patch on the particle's own cell
+            int ax = 0, ay = 0; bool ok = false;
+            if (lane == 0) {
+                double gx = x, gy = y;
+                if (!M.identity) { gx = em::fma_(M.g2l[0], x, em::fma_(M.g2l[1], y, M.g2l[3])); gy = em::fma_(M.g2l[4], x, em::fma_(M.g2l[5], y, M.g2l[7])); }
+                ok = em::cell_index_exact(gx, M.ox, M.sx, M.W, ax) && em::cell_index_exact(gy, M.oy, M.sy, M.H, ay);
+                if (ok) { origin[0] = ax - P / 2; origin[1] = ay - P / 2; }
+            }
+            ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+            if (ok) { ox = __shfl_sync(0xffffffffu, ax, 0) - P / 2; oy = __shfl_sync(0xffffffffu, ay, 0) - P / 2; }
+        }
+        const unsigned lx = (unsigned)(ix - ox), ly = (unsigned)(iy - oy);
+        const bool act = valid && ox != INT_MIN && lx < (unsigned)P && ly < (unsigned)P;
+        const unsigned target = act ? ly * (unsigned)P + lx : 0x80000000u | lane;
+        const unsigned grp = __match_any_sync(0xffffffffu, target);
+        const unsigned rank = __popc(grp & ((1u << lane) - 1u));
+        unsigned max_rank = act ? rank : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) max_rank = max(max_rank, __shfl_xor_sync(0xffffffffu, max_rank, o));
+        for (unsigned r = 0; r <= max_rank; ++r) {
+            if (act && rank == r) patch_merge_cell(patch + target, zm, sd);
+            __syncwarp();
+        }
+    }
+}
+
+// second moments of (x, y) about the weighted mean: per-tile sums of w dx^2, w dx dy, w dy^2 (eslam_gpu_pose_moments)
+__global__ void __launch_bounds__(1024, 1) k_moment_tiles(StateBufs st, const DevScalars* sc, unsigned long long n, double mx, double my,
+                                                          double* part /* n_tiles x 5 */) {
+    __shared__ double red[32];
+    const int cur = sc->cur;
+    const unsigned long long i = (unsigned long long)blockIdx.x * TILE + threadIdx.x;
+    double cxx = 0, cxy = 0, cyy = 0;
+    if (i < n) {
+        const double w = st.f[cur][F_W][i], dx = st.f[cur][F_X][i] - mx, dy = st.f[cur][F_Y][i] - my;
+        cxx = w * dx * dx; cxy = w * dx * dy; cyy = w * dy * dy;
+    }
+    const double a = tile_tree_sum_1024(cxx, red), b = tile_tree_sum_1024(cxy, red), c = tile_tree_sum_1024(cyy, red);
+    if (threadIdx.x == 0) { double* o = part + (size_t)blockIdx.x * 5; o[0] = a; o[1] = b; o[2] = c; o[3] = 0; o[4] = 0; }
+}
+
+// ParticleFilter::resample_stratified(samples) / resample_multinomial(samples) (src/ParticleFilter.hpp:85-147) with a sample count
+// of their own (one GPU, off the step path): one thread per sample, two-level lower-bound search of the exact running sum (tile
+// starts, then the tile), copy of the ancestor (state and map patch).  Multinomial: one uniform per sample, weight 1 / old size.
+struct ResampleNArgs {
+    const double* cdf; const double* tile_start; unsigned n_tiles;
+    unsigned long long n, samples; uint32_t k0key, k1key; int systematic, multinomial;
+    uint32_t* ancestors; int P; float2* patch[2]; int* porigin[2];
+};
+__global__ void __launch_bounds__(256) k_resample_n(StateBufs st, const DevScalars* sc, const ResampleNArgs A) {
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.samples) return;
+    const int cur = sc->cur, nxt = cur ^ 1;
+    const unsigned long long gk = (A.systematic && !A.multinomial) ? 0ull : k;
+    const em::Philox4 r = em::philox4x32_10((uint32_t)gk, sc->resample_step, 0, stream_word(em::STREAM_RESAMPLE, gk), A.k0key, A.k1key);
+    const double u = em::u01(r.v[0], r.v[1]);
+    const double sum_r = A.multinomial ? u : ((double)k + u) / (double)A.samples;    // :132 / :98
+    unsigned tlo = 0, thi = A.n_tiles;                                               // first tile with !(start < sum_r)
+    while (tlo < thi) { const unsigned mid = (tlo + thi) >> 1; if (__ldg(&A.tile_start[mid]) < sum_r) tlo = mid + 1; else thi = mid; }
+    const unsigned t = tlo == 0 ? 0 : tlo - 1;
+    unsigned long long lo = (unsigned long long)t * TILE, hi = min(lo + TILE, A.n);
+    while (lo < hi) { const unsigned long long mid = (lo + hi) >> 1; if (__ldg(&A.cdf[mid]) < sum_r) lo = mid + 1; else hi = mid; }   // :99-103 / :137
+    const unsigned long long a = lo >= A.n ? A.n - 1 : lo;
+    A.ancestors[k] = (uint32_t)a;
+#pragma unroll
+    for (int f = 0; f < 7; ++f) st.f[nxt][f][k] = st.f[cur][f][a];                   // :104 / :139
+    if (A.multinomial) st.f[nxt][F_W][k] = 1.0 / (double)A.n;                        // :140
+#pragma unroll
+    for (int f = 0; f < 2; ++f) st.b[nxt][f][k] = st.b[cur][f][a];
+    if (A.P > 0) {
+        const size_t pp = (size_t)A.P * A.P;
+        const float2* src = A.patch[cur] + a * pp; float2* dst = A.patch[nxt] + k * pp;
+        for (size_t c = 0; c < pp; ++c) dst[c] = src[c];
+        A.porigin[nxt][2 * k] = A.porigin[cur][2 * a]; A.porigin[nxt][2 * k + 1] = A.porigin[cur][2 * a + 1];
+    }
+}
+__global__ void k_after_resample_n(DevScalars* sc) { sc->cur ^= 1; sc->resample_step += 1; }   // xi_k.swap(xi_kp) :107 / :146
+
 __global__ void k_fill_i32(int* p, size_t count, int v) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) p[i] = v;

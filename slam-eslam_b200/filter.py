@@ -103,6 +103,14 @@ class FilterBase:
     def resample(self):
         self._check(self._fn("resample")(self._ctx))
 
+    def resampleStratified(self, samples):
+        """ParticleFilter::resample_stratified(samples) (src/ParticleFilter.hpp:85-108)."""
+        self._check(self._fn("resample_n")(self._ctx, int(samples), 0))
+
+    def resampleMultinomial(self, samples):
+        """ParticleFilter::resample_multinomial(samples) (src/ParticleFilter.hpp:120-147)."""
+        self._check(self._fn("resample_n")(self._ctx, int(samples), 1))
+
     def getAncestors(self):
         a = np.empty(self.size(), dtype=np.uint32)
         self._check(self._fn("get_ancestors")(self._ctx, a.ctypes.data_as(C.POINTER(C.c_uint32))))
@@ -144,6 +152,22 @@ class FilterBase:
         return out
 
     # -- per-particle map patches --------------------------------------------------------------
+    def processMap(self, scan_cells, scale, offset, match=True, update=True):
+        """EmbodiedSlamFilter::processMap (src/EmbodiedSlamFilter.cpp:179-232) with the scan as a dense grid:
+        scan_cells[h, w, 2] float32 {mean, stdev} in the yaw-compensated body frame (NaN mean = no surface)."""
+        cells = np.ascontiguousarray(scan_cells, dtype=np.float32)
+        h, w, two = cells.shape
+        assert two == 2
+        scan = abi.Scan(cells=cells.ctypes.data_as(C.POINTER(C.c_float)), width=w, height=h, scale_x=float(scale[0]),
+                        scale_y=float(scale[1]), offset_x=float(offset[0]), offset_y=float(offset[1]))
+        self._check(self._fn("process_map")(self._ctx, C.byref(scan), 1 if match else 0, 1 if update else 0))
+
+    def poseMoments(self):
+        """Weighted mean / covariance of (x, y): the one-component mixture of a PoseDistribution (src/PoseParticle.hpp:88-114)."""
+        g = abi.Gaussian2d()
+        self._check(self._fn("pose_moments")(self._ctx, C.byref(g)))
+        return dict(weight=g.weight, mean=np.array(list(g.mean)), cov=np.array(list(g.cov)).reshape(2, 2))
+
     def getPatches(self, patch_size):
         n = self.size()
         cells = np.empty((n, patch_size, patch_size, 2), dtype=np.float32)

@@ -645,3 +645,62 @@ def test_multi_gpu_parity_worker():
                           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "dist_worker.py")],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert out.returncode == 0 and "dist parity ok" in out.stdout, out.stdout[-4000:]
+
+
+# ---------------------------------------------------------------------------------- processMap proper, PoseDistribution moments
+def test_process_map_bit_identical_to_shared_oracle(gpu, oracle):
+    """EmbodiedSlamFilter::processMap(scanMap, match, update) (src/EmbodiedSlamFilter.cpp:179-232): scan merges into every
+    particle's own map and the match weight, interleaved with contact updates and resampling (maps travel with their
+    particles): every weight, every patch cell, every origin identical to the oracle's definition."""
+    P, n = 16, 3000
+    g, o, contacts, step = pair(gpu, oracle, "C1", n=n, patch_size=P, min_effective=n + 1)
+    rng = np.random.default_rng(11)
+    for it in range(5):
+        scan = np.zeros((9, 13, 2), dtype=np.float32)
+        scan[..., 0] = rng.normal(-0.19, 0.03, scan.shape[:2]); scan[..., 1] = 0.01 + 0.02 * rng.random(scan.shape[:2])
+        scan[rng.random(scan.shape[:2]) < 0.15, 0] = np.nan
+        args = (scan, (0.04, 0.06), (-0.2 + 0.05 * it, -0.25))
+        for f in (g, o):
+            f.processMap(*args, match=it > 0, update=it != 3)
+        assert_particles_equal(g.getParticles(), o.getParticles())
+        ca, oa = g.getPatches(P)
+        cb, ob = o.getPatches(P)
+        assert np.array_equal(oa, ob), "patch origins after processMap %d" % it
+        assert np.array_equal(ca, cb, equal_nan=True), "patch cells after processMap %d" % it
+        ra, rb = g.stepFused(step, contacts), (o.project(step), o.update(contacts))[1]
+        assert ra.as_dict() == rb.as_dict(), it
+        assert np.array_equal(g.getAncestors(), o.getAncestors())
+    assert (~np.isnan(ca[..., 0])).reshape(n, -1).sum(axis=1).min() > 10
+    m, mo = g.poseMoments(), o.poseMoments()
+    assert m["weight"] == mo["weight"] and np.array_equal(m["mean"], mo["mean"]) and np.array_equal(m["cov"], mo["cov"])
+
+
+def test_process_map_needs_per_particle_maps(gpu):
+    g = gpu(abi.default_config())
+    synthetic.setup_filter(g, "C1")
+    with pytest.raises(RuntimeError, match="per-particle maps"):
+        g.processMap(np.zeros((2, 2, 2), dtype=np.float32), (0.05, 0.05), (0, 0))
+
+
+@pytest.mark.parametrize("multinomial", [False, True])
+@pytest.mark.parametrize("samples", [700, 5000])
+def test_resample_with_a_sample_count_of_its_own(gpu, oracle, multinomial, samples):
+    """ParticleFilter::resample_stratified(samples) / resample_multinomial(samples) (src/ParticleFilter.hpp:85-147): the set has
+    `samples` particles afterwards; ancestors and copies identical to the oracle (multinomial: weights reset to 1 / old size)."""
+    n = 5000
+    rng = np.random.default_rng(4)
+    w = rng.random(n) ** 3
+    z = np.zeros(n)
+    out = []
+    for f in (gpu(abi.default_config()), oracle.OraclePoseEstimator(abi.default_config(), policy=oracle.SHARED)):
+        f.setParticles(x=np.arange(n, dtype=float), y=z, theta=z, zpos=z, zsigma=z + 1, weight=w)
+        f.normalizeWeights()
+        (f.resampleMultinomial if multinomial else f.resampleStratified)(samples)
+        assert f.size() == samples
+        out.append((f.getAncestors(), f.getParticles()))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert_particles_equal(out[0][1], out[1][1], keys=("x", "weight"))
+    if multinomial:
+        assert np.all(out[0][1]["weight"] == 1.0 / n)
+    else:
+        assert np.all(np.diff(out[0][0].astype(np.int64)) >= 0)

@@ -132,3 +132,23 @@ def test_centroid_and_best_index(oracle):
         wn = w / w.sum()
         np.testing.assert_allclose(c, [(x * wn).sum(), (y * wn).sum(), (th * wn).sum(), (z * wn).sum()], rtol=1e-12)
         np.testing.assert_allclose(f.getParticles()["weight"], wn, rtol=1e-14)   # getCentroid re-normalises (:356)
+
+
+def test_resample_variants_with_a_sample_count(oracle):
+    """src/ParticleFilter.hpp:85-147: resample_stratified(samples) keeps the ancestors' weights (Q3) and changes the set size;
+    resample_multinomial(samples) resets the weights to 1 / old size; both pick particles in proportion to their weight."""
+    n = 400
+    w = np.zeros(n); w[100] = 0.75; w[300] = 0.25
+    z = np.zeros(n)
+    for policy in (oracle.LITERAL, oracle.SHARED):
+        for multinomial in (False, True):
+            f = oracle.OraclePoseEstimator(abi.default_config(), policy=policy)
+            f.setParticles(x=np.arange(n, dtype=float), y=z, theta=z, zpos=z, zsigma=z + 1, weight=w)
+            (f.resampleMultinomial if multinomial else f.resampleStratified)(1000)
+            assert f.size() == 1000
+            anc = f.getAncestors()
+            assert set(anc.tolist()) == {100, 300}
+            frac = (anc == 100).mean()
+            assert abs(frac - 0.75) < (0.06 if multinomial else 0.002)
+            wt = f.getParticles()["weight"]
+            assert np.all(wt == 1.0 / n) if multinomial else np.array_equal(wt, w[anc])
