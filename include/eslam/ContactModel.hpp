@@ -46,6 +46,7 @@ protected:
     std::vector<base::Vector3d> lowestPointsPerGroup;
     std::vector<ContactPoint> contact_points;
     double m_zDelta, m_zVar, m_weight, m_poseVar;
+    double last[5]; bool haveLast;                                    // x, y, yaw, z, measVar of the last evaluatePose
     ContactModelConfiguration config;
     eslam_gpu_ctx* gpu; bool ownsGpu;
 
@@ -57,43 +58,43 @@ protected:
         ownsGpu = true;
     }
 
-    void lowestPointHeuristic(bool update_probabilities) {               // src/ContactModel.cpp:48-79
+    // getLowestPointPerGroup / updateContactStateUsingLowestPointHeuristic (src/ContactModel.cpp:48-92): ungrouped points
+    // (groupId < 0) stand for themselves; a run of consecutive points sharing a group id is represented by its lowest member
+    // (first one on ties), which alone keeps contact probability 1 when the probabilities are rewritten.
+    void lowestPointHeuristic(bool rewrite) {
+        std::vector<odometry::BodyContactPoint>& pts = contactState.points;
         lowestPointsPerGroup.clear();
-        std::vector<odometry::BodyContactPoint>& contactPoints(contactState.points);
-        std::vector<std::pair<double, int> > group;
-        for (size_t i = 0; i < contactPoints.size(); i++) {
-            if (contactPoints[i].groupId >= 0) {
-                group.push_back(std::make_pair(contactPoints[i].position.z(), (int)i));
-                if (update_probabilities) contactPoints[i].contact = 0;
-            }
-            if (group.empty())
-                lowestPointsPerGroup.push_back(contactPoints[i].position);
-            else if (i + 1 == contactPoints.size() || contactPoints[i + 1].groupId != contactPoints[i].groupId) {
-                std::sort(group.begin(), group.end());
-                odometry::BodyContactPoint& contact = contactPoints[group[0].second];
-                lowestPointsPerGroup.push_back(contact.position);
-                if (update_probabilities) contact.contact = 1;
-                group.clear();
-            }
+        const size_t n = pts.size();
+        for (size_t first = 0; first < n;) {
+            if (pts[first].groupId < 0) { lowestPointsPerGroup.push_back(pts[first].position); ++first; continue; }
+            size_t last = first, low = first;                              // run [first, last] of one group id
+            while (last + 1 < n && pts[last + 1].groupId == pts[first].groupId && pts[last + 1].groupId >= 0) ++last;
+            for (size_t k = first + 1; k <= last; ++k)
+                if (pts[k].position.z() < pts[low].position.z()) low = k;
+            if (rewrite) for (size_t k = first; k <= last; ++k) pts[k].contact = (k == low) ? 1.0f : 0.0f;
+            lowestPointsPerGroup.push_back(pts[low].position);
+            first = last + 1;
         }
     }
 
 public:
     static const int GROUP_SIZE = 4;
 
-    ContactModel() : m_zDelta(0), m_zVar(0), m_weight(0), m_poseVar(0), gpu(NULL), ownsGpu(false) { recreate(); }   // :12-14
+    ContactModel() : m_zDelta(0), m_zVar(0), m_weight(0), m_poseVar(0), haveLast(false), gpu(NULL), ownsGpu(false) { recreate(); }   // :12-14
     ~ContactModel() { if (gpu && ownsGpu) eslam_gpu_destroy(gpu); }
 
     void setConfiguration(const ContactModelConfiguration& c) { config = c; recreate(); }     // :16-19
     void setMap(const DenseGrid& grid) { attachGrid(gpu, grid); }
 
-    void setContactPoints(const odometry::BodyContactState& state, const base::Quaterniond& orientation) {   // :21-41
-        contactState = state;
+    // :21-41 -- the body's contact points, turned into the yaw-compensated frame (roll and pitch applied, heading left to the particles)
+    void setContactPoints(const odometry::BodyContactState& state, const base::Quaterniond& orientation) {
+        const base::Quaterniond rollPitch = base::removeYaw(orientation);
+        contactState.points.resize(state.points.size());
+        for (size_t i = 0; i < state.points.size(); ++i) {
+            contactState.points[i] = state.points[i];
+            contactState.points[i].position = rollPitch * state.points[i].position;
+        }
         lowestPointsPerGroup.clear();
-        base::Quaterniond yawCompensatedOrientation = base::removeYaw(orientation);
-        std::vector<odometry::BodyContactPoint>& contactPoints(contactState.points);
-        for (size_t i = 0; i < contactPoints.size(); i++)
-            contactPoints[i].position = yawCompensatedOrientation * contactPoints[i].position;
     }
     void updateContactStateUsingLowestPointHeuristic() { lowestPointHeuristic(true); }        // :81-84
     odometry::BodyContactState const& getContactState() const { return contactState; }        // :43-46
@@ -111,6 +112,7 @@ public:
         std::vector<eslam_gpu_contact> pts = toAbi(contactState);
         uint8_t ok = 0; int32_t ncont = 0; double cp[ESLAM_MAX_CP * 5];
         double x = t.x(), y = t.y(), z = t.z();
+        last[0] = x; last[1] = y; last[2] = yaw; last[3] = z; last[4] = measVar; haveLast = true;
         gpu_check(gpu, eslam_gpu_evaluate_poses(gpu, 1, &x, &y, &yaw, &z, &measVar, NULL, pts.data(), (int)pts.size(), &ok,
                                                 &m_weight, &m_zDelta, &m_zVar, &m_poseVar, &ncont, NULL, NULL, NULL, cp));
         contact_points.clear();
@@ -123,16 +125,20 @@ public:
     double getZVar() const { return m_zVar; }
     std::vector<ContactPoint>& getContactPoints() { return contact_points; }
 
-    bool updateZPositionEstimate(double& z_pos, double& z_var) {                               // :319-340 (scalar Kalman step)
-        const double pose_var = m_poseVar / contact_points.size();
-        double delta_var = std::max(z_var - pose_var, 1e-9);
-        if (std::fabs(m_zDelta / std::sqrt(delta_var)) > 1.0) return false;
-        const double gain = z_var / (z_var + m_zVar);
-        z_pos += gain * m_zDelta;
-        const double var_gain = delta_var / (delta_var + m_zVar);
-        delta_var = (1.0 - var_gain) * delta_var;
-        z_var = pose_var + delta_var;
-        return true;
+    // :319-340 -- the scalar Kalman step on the particle's height.  Evaluated on the device with the pose of the last
+    // evaluatePose (the same device function the filter's weight kernels run), not restated on the host.
+    bool updateZPositionEstimate(double& z_pos, double& z_var) {
+        if (!haveLast) return false;
+        std::vector<eslam_gpu_contact> pts = toAbi(contactState);
+        double zo = z_pos, zvo = z_var; uint8_t ok = 0;
+        // z_pos enters only as the state to correct: the measurement (m_zDelta, m_zVar, m_poseVar) is that of the last evaluated pose
+        gpu_check(gpu, eslam_gpu_evaluate_poses(gpu, 1, &last[0], &last[1], &last[2], &last[3], &last[4], &z_var, pts.data(), (int)pts.size(),
+                                                &ok, NULL, NULL, NULL, NULL, NULL, &zo, &zvo, NULL, NULL));
+        if (!ok) return false;
+        const bool changed = zvo != z_var || zo != last[3];
+        if (z_pos == last[3]) z_pos = zo; else z_pos += zo - last[3];     // the device applied the gain to the evaluated height
+        z_var = zvo;
+        return changed;
     }
 };
 

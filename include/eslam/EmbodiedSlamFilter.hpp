@@ -1,6 +1,8 @@
-// EmbodiedSlamFilter.hpp -- eslam::EmbodiedSlamFilter (src/EmbodiedSlamFilter.hpp:27-75), the contact-update slice:
-// init, update(body2odometry, BodyContactState, ltc), getParticles, getBestParticleIndex, getCentroid.  The laser /
-// distance-image overloads feed envire's scan pipeline, which is out of scope.
+// EmbodiedSlamFilter.hpp -- eslam::EmbodiedSlamFilter (src/EmbodiedSlamFilter.hpp:27-75): init (shared map or per-particle
+// maps), update(body2odometry, BodyContactState, ltc), the mapping update with an already projected scan, processMap,
+// getParticles, getBestParticleIndex, getCentroid, the PoseDistribution snapshot.  The laser / distance-image overloads
+// start with envire's scan pipeline (LaserScan -> ScanMeshing -> MLSProjection, src/EmbodiedSlamFilter.cpp:137-176), which is
+// out of scope: here the update takes that pipeline's OUTPUT, the scan as a grid.
 #ifndef ESLAM_FACADE_EMBODIEDSLAMFILTER_HPP
 #define ESLAM_FACADE_EMBODIEDSLAMFILTER_HPP
 #include "PoseEstimator.hpp"
@@ -12,16 +14,18 @@ class EmbodiedSlamFilter {
     odometry::Configuration odometryConfig;
     odometry::FootContact odometry;
     eslam::PoseEstimator filter;
-    base::Affine3d udPose;                                   // pose of the last measurement update
+    base::Affine3d udPose, mapPose;                          // poses of the last measurement / mapping update
+    bool sharedMap;
+    base::Quaterniond lastOrientation; odometry::BodyContactState lastBodyState;
 
 public:
     EmbodiedSlamFilter(const odometry::Configuration& odometryConfig, const eslam::Configuration& eslamConfig)   // src/EmbodiedSlamFilter.cpp:13-23
-        : eslamConfig(eslamConfig), odometryConfig(odometryConfig), odometry(odometryConfig), filter(odometry, eslamConfig) {}
+        : eslamConfig(eslamConfig), odometryConfig(odometryConfig), odometry(odometryConfig), filter(odometry, eslamConfig), sharedMap(true) {}
 
     // init(env, pose, useSharedMap): the environment must hold a map (:77-104), particles are drawn around the pose (:118-125)
     void init(const DenseGrid* map, const base::Pose& pose, bool useSharedMap = true,
               const SurfaceHashConfig& = SurfaceHashConfig()) {
-        if (useSharedMap && (!map || map->width == 0))
+        if (!map || map->width == 0)
             throw std::runtime_error("The provided environment does not contain an mls grid.");    // :104
         const double angle = base::getYaw(pose.orientation);
         filter.init((int)eslamConfig.particleCount,
@@ -30,12 +34,17 @@ public:
                                  eslamConfig.initialRotationError.z()),
                     pose.position.z(), eslamConfig.initialTranslationError.z() + 1e-3);              // :118-125
         udPose = base::Affine3d::Identity(); udPose.translation() = base::Vector3d(1000, 0, 0);      // :128
-        if (map) filter.setEnvironment(*map);                                                        // :131-134
+        mapPose = udPose;
+        sharedMap = useSharedMap;
+        if (!map || map->width == 0) throw std::runtime_error("The provided environment does not contain an mls grid.");
+        filter.setEnvironment(*map, useSharedMap, patchCells);                                       // :131-134 (per-particle maps: cloneMaps)
     }
+    int patchCells = 16;                                     // side of a particle's own map (cells) in per-particle-map mode
 
     bool update(const base::Affine3d& body2odometry, const odometry::BodyContactState& bs,
                 const std::vector<terrain_estimator::TerrainClassification>& ltc) {                  // :353-369
         base::Quaterniond orientation = body2odometry.rotation();
+        lastBodyState = bs;
         odometry.update(body2odometry);                                                              // :357
         filter.project(bs, orientation);                                                             // :358
         if (eslamConfig.measurementThreshold.test(udPose.inverse() * body2odometry) || ltc.size() > 0) {   // :360
@@ -44,6 +53,31 @@ public:
             return true;
         }
         return false;
+    }
+
+    // processMap(scanMap, match, update) (:179-232) on every particle's own map
+    void processMap(const DenseGrid& scanMap, bool match, bool update) { filter.processMap(scanMap, match, update); }
+
+    // The mapping update (:311-351) from the point where envire hands over: `scanMap` is MLSProjection's output for this scan
+    // in the yaw-compensated body frame.  project, then -- once the body has moved past mappingThreshold -- processMap with
+    // match = useVisualUpdate and update = !sharedMap (:337-345).
+    bool update(const base::Affine3d& body2odometry, const DenseGrid& scanMap) {
+        base::Quaterniond orientation = body2odometry.rotation();
+        if (eslamConfig.mappingThreshold.test(mapPose.inverse() * body2odometry)) {                  // :325
+            if (eslamConfig.useVisualUpdate || !sharedMap) processMap(scanMap, eslamConfig.useVisualUpdate, !sharedMap);   // :343
+            mapPose = body2odometry;
+            lastOrientation = orientation;
+            return true;
+        }
+        return false;
+    }
+
+    // the logging snapshot of the filter (src/PoseParticle.hpp:88-114)
+    PoseDistribution getPoseDistribution(const base::Time& time = base::Time()) {
+        PoseDistribution pd;
+        pd.time = time; pd.bodyState = lastBodyState;
+        filter.fillPoseDistribution(pd);
+        return pd;
     }
 
     std::vector<eslam::PoseEstimator::Particle>& getParticles() { return filter.getParticles(); }   // :371-374

@@ -29,7 +29,7 @@ class ParticleFilter<PoseParticle> {
 public:
     typedef PoseParticle Particle;
 
-    explicit ParticleFilter(const eslam_gpu_config& cfg, int device = 0) : gpu(NULL), hostValid(false), hostBorrowed(false) {
+    explicit ParticleFilter(const eslam_gpu_config& cfg, int device = 0) : gpu(NULL), gpuConfig(cfg), gpuDevice(device), hostValid(false), hostBorrowed(false) {
         if (eslam_gpu_create(&cfg, device, NULL, &gpu) != ESLAM_OK)
             throw std::runtime_error("eslam_gpu_create failed: no CUDA device (there is no CPU fallback)");
     }
@@ -41,6 +41,8 @@ public:
     double getWeightAvg() { return getWeightsSum() / size(); }                    // :41-44
     double normalizeWeights() { flush(); double ess; gpu_check(gpu, eslam_gpu_normalize_weights(gpu, &ess)); hostValid = false; return ess; }  // :46-70
     void resample() { flush(); gpu_check(gpu, eslam_gpu_resample(gpu)); hostValid = false; }                                    // :72-75
+    void resample_stratified(size_t samples) { flush(); gpu_check(gpu, eslam_gpu_resample_n(gpu, samples, 0)); hostValid = false; }    // :85-108
+    void resample_multinomial(size_t samples) { flush(); gpu_check(gpu, eslam_gpu_resample_n(gpu, samples, 1)); hostValid = false; }   // :120-147
     size_t getBestParticleIndex() { flush(); uint64_t i; gpu_check(gpu, eslam_gpu_best_index(gpu, &i)); return (size_t)i; }     // :160-173
     size_t size() const { return (size_t)eslam_gpu_particle_count(gpu); }
 
@@ -52,35 +54,51 @@ public:
     eslam_gpu_ctx* context() { return gpu; }
 
 protected:
-    void sync() {                                        // device -> host mirror
+    void sync() {                                        // device -> host mirror (staging arrays are kept between calls)
         if (hostValid) return;
         const size_t n = size();
         xi_k.resize(n);
         if (n == 0) { hostValid = true; return; }
-        std::vector<double> x(n), y(n), th(n), z(n), zs(n), w(n), mp(n); std::vector<uint8_t> fl(n), nf(n);
-        gpu_check(gpu, eslam_gpu_get_particles(gpu, x.data(), y.data(), th.data(), z.data(), zs.data(), w.data(), mp.data(), fl.data(), nf.data()));
+        for (int f = 0; f < 7; f++) stage[f].resize(n);
+        stageFlag[0].resize(n); stageFlag[1].resize(n);
+        gpu_check(gpu, eslam_gpu_get_particles(gpu, stage[0].data(), stage[1].data(), stage[2].data(), stage[3].data(), stage[4].data(),
+                                               stage[5].data(), stage[6].data(), stageFlag[0].data(), stageFlag[1].data()));
         for (size_t i = 0; i < n; i++) {
             Particle& p = xi_k[i];
-            p.position = base::Vector2d(x[i], y[i]); p.orientation = th[i]; p.zPos = z[i]; p.zSigma = zs[i];
-            p.weight = w[i]; p.mprob = mp[i]; p.floating = fl[i] != 0; p.n_contacts = nf[i];
+            p.position = base::Vector2d(stage[0][i], stage[1][i]); p.orientation = stage[2][i]; p.zPos = stage[3][i]; p.zSigma = stage[4][i];
+            p.weight = stage[5][i]; p.mprob = stage[6][i]; p.floating = stageFlag[0][i] != 0; p.n_contacts = stageFlag[1][i];
         }
         hostValid = true;
     }
     void flush() {                                       // host mirror -> device, if a mutable reference was handed out
         if (!hostBorrowed) return;
         const size_t n = xi_k.size();
-        std::vector<double> x(n), y(n), th(n), z(n), zs(n), w(n);
+        for (int f = 0; f < 6; f++) stage[f].resize(n);
         for (size_t i = 0; i < n; i++) {
             const Particle& p = xi_k[i];
-            x[i] = p.position.x(); y[i] = p.position.y(); th[i] = p.orientation; z[i] = p.zPos; zs[i] = p.zSigma; w[i] = p.weight;
+            stage[0][i] = p.position.x(); stage[1][i] = p.position.y(); stage[2][i] = p.orientation; stage[3][i] = p.zPos;
+            stage[4][i] = p.zSigma; stage[5][i] = p.weight;
         }
-        if (n) gpu_check(gpu, eslam_gpu_set_particles(gpu, n, x.data(), y.data(), th.data(), z.data(), zs.data(), w.data()));
+        if (n) gpu_check(gpu, eslam_gpu_set_particles(gpu, n, stage[0].data(), stage[1].data(), stage[2].data(), stage[3].data(),
+                                                      stage[4].data(), stage[5].data()));
         hostBorrowed = false;
+    }
+    // a new context with another configuration (per-particle maps on / off): the particle set moves over
+    void recreate(const eslam_gpu_config& cfg) {
+        sync();
+        eslam_gpu_ctx* fresh = NULL;
+        if (eslam_gpu_create(&cfg, gpuDevice, NULL, &fresh) != ESLAM_OK) throw std::runtime_error("eslam_gpu_create failed");
+        eslam_gpu_destroy(gpu);
+        gpu = fresh; gpuConfig = cfg;
+        hostBorrowed = !xi_k.empty();                    // re-uploaded before the next device operation
+        flush();
     }
     void deviceChanged() { hostValid = false; hostBorrowed = false; }
 
     eslam_gpu_ctx* gpu;
+    eslam_gpu_config gpuConfig; int gpuDevice;
     std::vector<Particle> xi_k;                          // :176 (host mirror)
+    std::vector<double> stage[7]; std::vector<uint8_t> stageFlag[2];
     bool hostValid, hostBorrowed;
 };
 

@@ -9,7 +9,7 @@ namespace eslam {
 class PoseEstimator : public ParticleFilter<PoseParticle> {
 public:
     PoseEstimator(odometry::FootContact& odometry, const eslam::Configuration& config)      // src/PoseEstimator.cpp:13-25
-        : ParticleFilter<Particle>(toGpuConfig(config)), config(config), odometry(odometry), max_weight(0), haveEnv(false) {}
+        : ParticleFilter<Particle>(toGpuConfig(config)), config(config), odometry(odometry), max_weight(0), haveEnv(false), useSharedMap(true) {}
     ~PoseEstimator() {}
 
     void init(int numParticles, const base::Pose2D& mu, const base::Pose2D& sigma, double zpos = 0, double zsigma = 0) {   // :88-102
@@ -19,8 +19,39 @@ public:
         deviceChanged();
     }
 
-    void setEnvironment(const DenseGrid& map, const double* C_global2local = 0) {            // :47-62
+    // setEnvironment(env, map, useShared) (:47-62).  useShared == false is the per-particle-map mode: every particle owns
+    // a map that contact heights and scans are merged into and that travels with it through resampling (cloneMaps :31-45,
+    // :252-253).  On the device a particle's own map is a patchCells x patchCells overlay of the shared grid.
+    void setEnvironment(const DenseGrid& map, bool useShared = true, int patchCells = 16, const double* C_global2local = 0) {
+        const int want = useShared ? 0 : patchCells;
+        if (gpuConfig.patch_size != want) { eslam_gpu_config c = gpuConfig; c.patch_size = want; recreate(c); }
+        useSharedMap = useShared;
         attachGrid(gpu, map, C_global2local); haveEnv = true;
+    }
+    bool usesSharedMap() const { return useSharedMap; }
+
+    // the per-particle half of EmbodiedSlamFilter::processMap (src/EmbodiedSlamFilter.cpp:183-228): scan merge and match weight
+    void processMap(const DenseGrid& scanMap, bool match, bool update) {
+        flush();
+        eslam_gpu_scan s;
+        s.cells_mean_stdev = scanMap.cells.data(); s.width = scanMap.width; s.height = scanMap.height;
+        s.scale_x = scanMap.scaleX; s.scale_y = scanMap.scaleY; s.offset_x = scanMap.offsetX; s.offset_y = scanMap.offsetY;
+        gpu_check(gpu, eslam_gpu_process_map(gpu, &s, match ? 1 : 0, update ? 1 : 0));
+        deviceChanged();
+    }
+
+    // what a PoseDistribution carries besides the particles (src/PoseParticle.hpp:88-114): the poses as a Gaussian mixture
+    // (one component: weighted mean and covariance, reduced on the device)
+    void fillPoseDistribution(PoseDistribution& pd) {
+        flush();
+        eslam_gpu_gaussian2d g;
+        gpu_check(gpu, eslam_gpu_pose_moments(gpu, &g));
+        pd.particles.assign(getParticles().begin(), getParticles().end());
+        PoseDistribution::GMM::Parameter par;
+        par.weight = 1.0; par.mean = base::Vector2d(g.mean[0], g.mean[1]);
+        par.cov.m[0][0] = g.cov[0]; par.cov.m[0][1] = g.cov[1]; par.cov.m[1][0] = g.cov[2]; par.cov.m[1][1] = g.cov[3];
+        pd.gmm.params.assign(1, par);
+        pd.orientation = zCompensatedOrientation;
     }
 
     void project(const odometry::BodyContactState& /*state*/, const base::Quaterniond& orientation) {   // :184-242
@@ -76,7 +107,7 @@ private:
     odometry::FootContact& odometry;
     base::Quaterniond zCompensatedOrientation;
     double max_weight;
-    bool haveEnv;
+    bool haveEnv, useSharedMap;
     eslam_gpu_update_result lastResult;
 };
 

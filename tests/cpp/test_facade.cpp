@@ -174,8 +174,61 @@ static void test_filter_steps() {                          // PoseEstimator / Em
     (void)sum;
 }
 
+static void test_per_particle_maps() {                     // init(..., useSharedMap = false): src/EmbodiedSlamFilter.cpp:131-134,179-232
+    eslam::Configuration conf; conf.particleCount = 1500; conf.minEffective = 1501; conf.useVisualUpdate = true;
+    EmbodiedSlamFilter f(odometry::Configuration(), conf);
+    DenseGrid map = rollingTerrain(400);
+    f.init(&map, base::Pose(base::Vector3d(0, 0, 0.19), base::Quaterniond::Identity()), false);
+    CHECK(!f.getFilter().usesSharedMap());
+    CHECK(f.getParticles().size() == 1500);
+    std::vector<terrain_estimator::TerrainClassification> ltc;
+    BodyContactState bs = wheels();
+    // a scan 0.2 m in front of the body, 8 x 6 cells of 0.05 m, heights relative to the body (z = 0.19 above the ground)
+    DenseGrid scan(8, 6, 0.05, 0.05, 0.2, -0.15);
+    for (int iy = 0; iy < 6; iy++) for (int ix = 0; ix < 8; ix++) scan.set(ix, iy, -0.19f, 0.02f);
+    int mapped = 0;
+    for (int step = 0; step < 12; step++) {
+        base::Affine3d body2odo = base::Affine3d::fromTranslationYaw(base::Vector3d(0.03 * step, 0, 0.19), 0.0);
+        f.update(body2odo, bs, ltc);                          // contact update: resamples every time (minEffective > N): maps travel
+        if (f.update(body2odo, scan)) mapped++;               // mapping update past mappingThreshold: match weight + merge
+        CHECK(f.getParticles().size() == 1500);
+    }
+    CHECK(mapped >= 5);
+    std::vector<float> cells((size_t)1500 * 16 * 16 * 2); std::vector<int32_t> origin(2 * 1500);
+    CHECK(eslam_gpu_get_patches(f.getFilter().context(), cells.data(), origin.data()) == ESLAM_OK);
+    size_t written = 0; for (size_t i = 0; i < cells.size(); i += 2) written += cells[i] == cells[i];
+    CHECK(written > 1500 * 20);                                // every particle's own map holds scan and contact heights
+    // the logging snapshot: particles + one-component mixture around the cloud (src/PoseParticle.hpp:88-114)
+    PoseDistribution pd = f.getPoseDistribution(base::Time::fromMicroseconds(42));
+    CHECK(pd.particles.size() == 1500 && pd.gmm.params.size() == 1 && pd.bodyState.points.size() == bs.points.size());
+    CHECK(std::fabs(pd.gmm.params[0].mean.x() - 0.33) < 0.3 && pd.gmm.params[0].cov.m[0][0] > 0 && pd.gmm.params[0].cov.m[1][1] > 0);
+    // resample_stratified(samples) / resample_multinomial(samples) (src/ParticleFilter.hpp:85-147) change the set size
+    f.getFilter().resample_stratified(1000);
+    CHECK(f.getParticles().size() == 1000);
+    f.getFilter().resample_multinomial(800);
+    CHECK(f.getParticles().size() == 800);
+    CHECK(std::fabs(f.getParticles()[3].weight - 1.0 / 1000) < 1e-15);   // :140
+}
+
+static void test_z_position_estimate() {                   // ContactModel::updateZPositionEstimate as test/testMap.cpp:279-289 drives it
+    const double pts[4][3] = {{-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 1, 0}};
+    const float contact[4] = {0.5f, 0.5f, 0.5f, 0.5f}; const int group[4] = {-1, -1, -1, -1};
+    ContactModel model;
+    ContactModelConfiguration cfg; cfg.contactPointRadius = 0.0; model.setConfiguration(cfg);
+    model.setContactPoints(fourPoints(pts, contact, group), base::Quaterniond::Identity());
+    double z[4] = {0.05, 0.05, 0.05, 0.05}, stddev[4] = {0.1, 0.1, 0.1, 0.1};
+    model.setMap(quadrantGrid(z, stddev));
+    CHECK(model.evaluatePose(base::Affine3d::Identity(), 0.5));
+    double zpos = 0.0, zvar = 0.5;
+    CHECK(model.updateZPositionEstimate(zpos, zvar));
+    CHECK(zpos > 0.0 && zpos < 0.05 + 1e-9);                   // pulled towards the ground the feet stand on
+    CHECK(zvar < 0.5 && zvar > 0.0);
+}
+
 int main() {
     test_updatePose_nogroup();
+    test_per_particle_maps();
+    test_z_position_estimate();
     test_lowest_points();
     test_mapAbsence_group();
     test_filter_steps();

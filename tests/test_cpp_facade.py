@@ -25,6 +25,33 @@ def test_facade_compiles_and_links():
     assert os.path.exists(compile_facade_test())
 
 
+def test_libeslam_and_pkgconfig_like_the_reference_installs_them(tmp_path):
+    """The reference installs `eslam` as a library with a pkg-config file (src/CMakeLists.txt:16-19, src/eslam.pc.in:6-10): a
+    consumer that asks pkg-config for `eslam` compiles and links against the installed headers, libeslam.so and libeslam_gpu.so."""
+    import shutil
+    build.build()
+    prefix = tmp_path / "prefix"
+    res = subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "packaging"), "install", "PREFIX=%s" % prefix],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    for f in ("lib/libeslam.so", "lib/libeslam_gpu.so", "lib/pkgconfig/eslam.pc", "include/eslam/EmbodiedSlamFilter.hpp", "include/eslam_gpu.h"):
+        assert (prefix / f).exists(), f
+    if shutil.which("pkg-config"):
+        env = dict(os.environ, PKG_CONFIG_PATH=str(prefix / "lib" / "pkgconfig"))
+        flags = subprocess.run(["pkg-config", "--cflags", "--libs", "eslam"], env=env, stdout=subprocess.PIPE, text=True).stdout.split()
+    else:
+        flags = ["-I%s" % (prefix / "include"), "-L%s" % (prefix / "lib"), "-leslam", "-leslam_gpu"]
+    assert "-leslam" in flags
+    out = tmp_path / "consumer"
+    res = subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "test_facade.cpp"), "-o", str(out)] + flags +
+                         ["-Wl,-rpath,%s" % (prefix / "lib")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 0, res.stdout
+    import ctypes
+    lib = ctypes.CDLL(str(prefix / "lib" / "libeslam.so"))
+    lib.eslam_version.restype = ctypes.c_char_p
+    assert lib.eslam_version().startswith(b"2.")
+
+
 @pytest.mark.gpu
 def test_facade_runs_reference_test_cases():
     import torch
