@@ -23,7 +23,7 @@ static NcclApi g_nccl;
 // Development switches, read ONCE when a context is created (tools/README.md); never consulted on the step path.
 struct EnvSwitches {
     bool no_fast, no_tma, no_local_resample, stream_resample, trace, timing, use_pdl, no_p2p;
-    int lean_threads, tile_override;
+    int lean_threads, tile_override, graph;
     void read() {
         no_fast = getenv("ESLAM_GPU_NO_FAST") != nullptr;
         no_tma = getenv("ESLAM_GPU_NO_TMA") != nullptr;
@@ -34,6 +34,7 @@ struct EnvSwitches {
         use_pdl = getenv("ESLAM_GPU_NO_PDL") == nullptr;
         no_p2p = getenv("ESLAM_GPU_NO_P2P") != nullptr;
         lean_threads = getenv("ESLAM_GPU_LEAN_THREADS") ? atoi(getenv("ESLAM_GPU_LEAN_THREADS")) : 1024;
+        graph = getenv("ESLAM_GPU_GRAPH") ? atoi(getenv("ESLAM_GPU_GRAPH")) : -1;   // -1: by size, 0: never, 1: always
         tile_override = getenv("ESLAM_GPU_TILE") ? atoi(getenv("ESLAM_GPU_TILE")) : 0;
     }
 };
@@ -79,12 +80,23 @@ struct eslam_gpu_ctx {
     CUtensorMap tmap; CUtensorMap* d_tmap; bool has_tmap;   // TMA descriptor of the grid (host copy, device copy)
     em::dbl2* htab;
     int max_smem_optin, sm_count;
-    uint32_t project_step;
     std::vector<cudaEvent_t> events;
     bool timing; std::vector<std::pair<int, cudaEvent_t> > marks; size_t marks_used;
     std::vector<float> step_ms;                   // step periods of the last eslam_gpu_run_steps
+    // The fused step (project + update) as ONE CUDA graph with programmatic edges, for launch-bound sizes: the step's decisions
+    // (resample?, which buffer, Philox step, exchange epochs) all live on the device, so a captured step is replayable; what
+    // changes from call to call -- odometry step and contact points -- lives in the parameters of three kernel nodes, which
+    // are updated in place (cudaGraphExecKernelNodeSetParams).
+    struct StepGraph {
+        cudaGraph_t graph; cudaGraphExec_t exec; cudaGraphNode_t n_project, n_scatter, n_lean;
+        bool valid, failed; uint64_t n; int nb, lean_threads; unsigned kernels;
+        eslam_gpu_step step; ContactSet cs; cudaEvent_t ev0, ev1;
+    } sg;
+    bool capturing;
     bool use_pdl;
 };
+
+static void graph_drop(eslam_gpu_ctx* ctx);
 
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(eslam_gpu_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
@@ -243,6 +255,7 @@ static int ensure_capacity(eslam_gpu_ctx* ctx, uint64_t n) {
             ctx->error = "sharded contexts need equal shards of 1024 * 2^k particles"; return ESLAM_ERR_INVALID;
         }
     }
+    if (n != ctx->n) graph_drop(ctx);                                   // the captured step holds the old sizes / buffers
     if (n > ctx->cap) {
         for (void* p : ctx->ipc_opened) cudaIpcCloseMemHandle(p);   // peer mappings of the old buffers are stale
         ctx->ipc_opened.clear(); ctx->has_peers = false;
@@ -461,6 +474,8 @@ void eslam_gpu_destroy(eslam_gpu_ctx* ctx) {
     cudaFree(ctx->sc); cudaFree(ctx->d_tmap); cudaFree(ctx->htab); cudaFree(ctx->cells); cudaFree(ctx->hint); cudaFree(ctx->ticket);
     cudaFree(ctx->bin_count); cudaFree(ctx->bin_offs); cudaFree(ctx->bin_next); cudaFree(ctx->cta_bin);
     cudaFree(ctx->shard_tot); cudaFree(ctx->shard_sums); cudaFree(ctx->scan_cells);
+    graph_drop(ctx);
+    if (ctx->sg.ev0) { cudaEventDestroy(ctx->sg.ev0); cudaEventDestroy(ctx->sg.ev1); }
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     for (auto& m : ctx->marks) cudaEventDestroy(m.second);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -504,6 +519,7 @@ int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int he
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->cells); ctx->cells = nullptr;
+    graph_drop(ctx);                                                      // the captured step holds the old grid's pointers
     const size_t count = (size_t)width * height;
     CK(dalloc(&ctx->cells, count));
     CK(cudaMemcpyAsync(ctx->cells, cells, count * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
@@ -583,7 +599,6 @@ int eslam_gpu_init_gaussian(eslam_gpu_ctx* ctx, uint64_t n, const double mu[3], 
     *ctx->sc_async = init;
     *ctx->sc_host = init;
     CK(cudaMemcpyAsync(ctx->sc, ctx->sc_host, sizeof(DevScalars), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->project_step = 0;
     st = reset_patches(ctx);
     if (st != ESLAM_OK) return st;
     const ModelParams mp = model_params(ctx);
@@ -655,7 +670,7 @@ static void place_tile(const eslam_gpu_ctx* ctx, MapParams* m) {
 static void fill_weight_params(eslam_gpu_ctx* ctx, WeightParams* P, const eslam_gpu_step* step, const ContactSet* cs) {
     memset(P, 0, sizeof(*P));
     P->st = ctx->st; P->sc = ctx->sc; P->map = ctx->map; P->mp = model_params(ctx);
-    P->htab = ctx->htab; P->n = ctx->n; P->base = base_index(ctx); P->project_step = ctx->project_step;
+    P->htab = ctx->htab; P->n = ctx->n; P->base = base_index(ctx);
     P->patch_size = ctx->cfg.patch_size > 0 ? ctx->cfg.patch_size : 0;
     P->use_tma = ctx->has_tmap && !ctx->env.no_tma;
     P->tmap = ctx->d_tmap;
@@ -680,7 +695,7 @@ static bool fill_fast_params(eslam_gpu_ctx* ctx, FastParams* F, const WeightPara
     memset(F, 0, sizeof(*F));
     WeightCommon& c = F->c;
     c.st = P.st; c.sc = P.sc; c.map = P.map; c.mp = P.mp; c.htab = P.htab; c.n = P.n; c.base = P.base;
-    c.project_step = P.project_step; c.use_tma = P.use_tma; c.tmap = P.tmap; c.hint = P.hint;
+    c.use_tma = P.use_tma; c.tmap = P.tmap; c.hint = P.hint;
     c.yaw = P.yaw; c.z_delta = P.z_delta; c.z_var = P.z_var;
     for (int i = 0; i < 3; ++i) { c.dmean[i] = P.dmean[i]; c.dsigma[i] = P.dsigma[i]; }
     FastContacts& fc = F->fc;
@@ -761,7 +776,7 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     PatchGather pg; memset(&pg, 0, sizeof(pg));
     pg.P = ctx->cfg.patch_size > 0 ? ctx->cfg.patch_size : 0;
     for (int b = 0; b < 2; ++b) { pg.patch[b] = ctx->patch[b]; pg.porigin[b] = ctx->porigin[b]; }
-    if (pg.P == 0 && ctx->env.stream_resample && !sp.mode) {
+    if (ctx->env.stream_resample && !sp.mode) {
         // persistent CTAs, source tiles streamed through a bulk-copy ring from the rank that owns them: own memory or a peer's
         // over NVLink (see k_resample_stream); sharded: tile starts from the global table the ranks' k_chain pushed
         StreamArgs sa; sa.tile_start = tile_sin; sa.n_tiles = TG; sa.tiles_per_rank = T; sa.n = n; sa.n_global = ng; sa.base = base_index(ctx);
@@ -769,20 +784,23 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
         sa.my_rank = sharded(ctx) ? (unsigned)ctx->shard.rank : 0u;
         CK(launch_pdl(ctx, k_resample_stream, (unsigned)ctx->sm_count, 1024, (size_t)RS_STREAM_SMEM, ctx->st, ctx->sc, sa, ctx->peers, ctx->X));
         LAUNCHED();
-        return ESLAM_OK;
-    }
-    if (sharded(ctx)) {
-        // per-particle patches, LOCAL_MIGRATE: every rank searches the global tile-start table (pushed by the ranks' k_chain), then
-        // the owner's running sums, and copies its ancestors' state (and map patches) straight from the owner's buffers over NVLink
+    } else if (sharded(ctx)) {
+        // LOCAL_MIGRATE: every rank searches the global tile-start table (pushed by the ranks' k_chain), then the owner's running
+        // sums, and copies its ancestors' state straight from the owner's buffers over NVLink
         CK(launch_pdl(ctx, k_resample_local<RS_CTA>, (unsigned)((n + RS_CTA - 1) / RS_CTA), RS_CTA, 0, ctx->st, ctx->sc, tile_sin, TG, T, n, ng, base_index(ctx),
-                      mp.k0, mp.k1, systematic, ctx->ancestors, ctx->ticket, ctx->peers, sp, tile_ofs(ctx), (unsigned)ctx->shard.rank, pg, ctx->X));
+                      mp.k0, mp.k1, systematic, ctx->ancestors, ctx->ticket, ctx->peers, sp, tile_ofs(ctx), (unsigned)ctx->shard.rank, ctx->X));
         LAUNCHED();
-        return ESLAM_OK;
+    } else {
+        // search in shared memory, copy and buffer swap in one kernel (virtual shards, ESLAM_GPU_STREAM_RESAMPLE=0)
+        CK(launch_pdl(ctx, k_resample_local<RS_CTA>, (unsigned)((n + RS_CTA - 1) / RS_CTA), RS_CTA, 0, ctx->st, ctx->sc, tile_sin, T, T, n, n, 0ull, mp.k0, mp.k1,
+                      systematic, ctx->ancestors, ctx->ticket, ctx->peers, sp, 0u, 0u, ctx->X));
+        LAUNCHED();
     }
-    // search in shared memory, copy (state and map patch) and buffer swap in one kernel
-    CK(launch_pdl(ctx, k_resample_local<RS_CTA>, (unsigned)((n + RS_CTA - 1) / RS_CTA), RS_CTA, 0, ctx->st, ctx->sc, tile_sin, T, T, n, n, 0ull, mp.k0, mp.k1,
-                  systematic, ctx->ancestors, ctx->ticket, ctx->peers, sp, 0u, 0u, pg, ctx->X));
-    LAUNCHED();
+    if (pg.P > 0) {
+        // cloneMaps: the maps follow their particles (the state buffers are swapped already)
+        CK(launch_pdl(ctx, k_gather_patches, (unsigned)((n * 32 + 255) / 256), 256, 0, ctx->sc, n, n, ctx->ancestors, pg, ctx->peers));
+        LAUNCHED();
+    }
     return ESLAM_OK;
 }
 
@@ -800,24 +818,24 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
         // bin the particles by map tile, evaluate bin by bin from shared memory (particles whose footprint leaves the map or
         // whose values are out of range are flagged and go through contact_eval inside the same kernel)
         const unsigned T = ctx->t_local;
-        if (step_or_null) { CK(launch_pdl(ctx, k_project_bin<true>, T, 1024, 0, F, ctx->bin_count, ctx->keys)); ctx->project_step++; }
+        if (step_or_null) CK(launch_pdl(ctx, k_project_bin<true>, T, 1024, 0, F, ctx->bin_count, ctx->keys));
         else CK(launch_pdl(ctx, k_project_bin<false>, T, 1024, 0, F, ctx->bin_count, ctx->keys));
         LAUNCHED();
-        CK(launch_pdl(ctx, k_bin_scatter, T, 1024, 0, ctx->bin_count, F.fc.nb, ctx->keys, ctx->n, ctx->bin_list, ctx->bin_offs, ctx->cta_bin, ctx->sm_count));
+        CK(launch_pdl(ctx, k_bin_scatter, T, 1024, 0, ctx->bin_count, F.fc.nb, ctx->keys, ctx->n, ctx->bin_list, ctx->bin_offs, ctx->cta_bin, ctx->sm_count, ctx->sc,
+                      step_or_null ? 1 : 0));
         LAUNCHED();
-        if (ev0) CK(cudaEventRecord(ev0, ctx->stream));                  // the events bracket the dominant kernel alone
+        if (ev0) CK(cudaEventRecordWithFlags(ev0, ctx->stream, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));   // the events bracket the dominant kernel alone
         if (ctx->env.lean_threads == 512)
             CK(launch_pdl(ctx, k_weight_lean<512>, (unsigned)ctx->sm_count, 512, smem, F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin));
         else
             CK(launch_pdl(ctx, k_weight_lean<1024>, (unsigned)ctx->sm_count, 1024, smem, F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin));
         LAUNCHED();
-        if (ev1) CK(cudaEventRecord(ev1, ctx->stream));
+        if (ev1) CK(cudaEventRecordWithFlags(ev1, ctx->stream, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
         ctx->hint_n = 0;
     } else {
         if (step_or_null) {
             if (patches) CK(launch_pdl(ctx, (k_project_weight<true, true, true>), grid, WT_THREADS, smem, P));
             else CK(launch_pdl(ctx, (k_project_weight<true, true, false>), grid, WT_THREADS, smem, P));
-            ctx->project_step++;
         } else if (patches) CK(launch_pdl(ctx, (k_project_weight<false, true, true>), grid, WT_THREADS, smem, P));
         else CK(launch_pdl(ctx, (k_project_weight<false, true, false>), grid, WT_THREADS, smem, P));
         LAUNCHED();
@@ -827,6 +845,7 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
     ctx->last_lean = lean;
     TilePartArgs ta; ta.part = ctx->l_part_a; ta.n_tiles = ctx->t_local; ta.scratch_a = ctx->scratch_a; ta.scratch_b = ctx->scratch_b;
     ta.hint = ctx->hint; ta.n_hint = ctx->hint_n; ta.n_local = ctx->n; ta.bin_count = ctx->bin_count; ta.bin_next = ctx->bin_next;
+    ta.bump_project = (!lean && step_or_null) ? 1 : 0;
     CK(launch_pdl(ctx, k_tile_part, ctx->t_local, SCAN_THREADS, 0, ctx->st, ctx->sc, ctx->n, ta, ctx->X));
     LAUNCHED();
     // cloud centre (tile placement of the generic path): copied to the host on a side stream, read by later launches
@@ -890,7 +909,8 @@ int eslam_gpu_project(eslam_gpu_ctx* ctx, const eslam_gpu_step* step) {
     WeightParams P;
     fill_weight_params(ctx, &P, step, nullptr);
     k_project_weight<true, false, false><<<weight_grid(ctx), WT_THREADS, 0, ctx->stream>>>(P);
-    ctx->project_step++;
+    LAUNCHED();
+    k_bump_project<<<1, 1, 0, ctx->stream>>>(ctx->sc);
     LAUNCHED();
     return ESLAM_OK;
 }
@@ -906,6 +926,85 @@ int eslam_gpu_update(eslam_gpu_ctx* ctx, const eslam_gpu_contact* pts, int n_pts
     return result ? fetch_result(ctx, result) : ESLAM_OK;
 }
 
+}  // extern "C"
+
+static void graph_drop(eslam_gpu_ctx* ctx) {
+    if (ctx->sg.exec) cudaGraphExecDestroy(ctx->sg.exec);
+    if (ctx->sg.graph) cudaGraphDestroy(ctx->sg.graph);
+    ctx->sg.exec = nullptr; ctx->sg.graph = nullptr; ctx->sg.valid = false;
+}
+
+// launch-bound sizes only: with a million particles the step's ~9 launches hide behind 0.4 ms of kernels
+static bool graph_wanted(const eslam_gpu_ctx* ctx) {
+    if (ctx->timing || ctx->sg.failed || ctx->env.graph == 0) return false;
+    if (ctx->env.graph == 1) return true;
+    return ctx->n <= 262144;
+}
+
+// One fused step through the graph: capture on first use (or when the step's structure changed), afterwards update the three
+// parameter blocks that carry the call's inputs and launch.  Returns ESLAM_OK with *done = false when the graph does not apply
+// (the generic kernel, a failed capture): the caller launches the kernels directly.
+static int graph_step(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const ContactSet* cs, bool* done, bool launch = true) {
+    *done = false;
+    eslam_gpu_ctx::StepGraph& G = ctx->sg;
+    WeightParams P;
+    fill_weight_params(ctx, &P, step, cs);
+    FastParams& F = *ctx->fast;
+    if (!fill_fast_params(ctx, &F, P, *cs)) return ESLAM_OK;              // generic path: tile placement is a host-side hint per launch
+    if (G.valid && (G.n != ctx->n || G.nb != F.fc.nb || G.lean_threads != ctx->env.lean_threads)) graph_drop(ctx);
+    if (!G.valid) {
+        if (!G.ev0) { CK(cudaEventCreate(&G.ev0)); CK(cudaEventCreate(&G.ev1)); }
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); G.failed = true; return ESLAM_OK; }
+        ctx->capturing = true;
+        const uint64_t before = ctx->launches;
+        const int st = launch_update(ctx, step, cs, G.ev0, G.ev1);
+        ctx->capturing = false;
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        G.kernels = (unsigned)(ctx->launches - before); ctx->launches = before;
+        if (st != ESLAM_OK || e != cudaSuccess || !g) { cudaGetLastError(); if (g) cudaGraphDestroy(g); G.failed = true; return st; }
+        G.graph = g;
+        if (cudaGraphInstantiate(&G.exec, G.graph, 0) != cudaSuccess) { cudaGetLastError(); graph_drop(ctx); G.failed = true; return ESLAM_OK; }
+        // the nodes whose parameters carry the call's inputs
+        size_t nn = 0; CK(cudaGraphGetNodes(G.graph, nullptr, &nn));
+        std::vector<cudaGraphNode_t> nodes(nn); CK(cudaGraphGetNodes(G.graph, nodes.data(), &nn));
+        G.n_project = G.n_scatter = G.n_lean = nullptr;
+        for (size_t i = 0; i < nn; ++i) {
+            cudaGraphNodeType ty; CK(cudaGraphNodeGetType(nodes[i], &ty));
+            if (ty != cudaGraphNodeTypeKernel) continue;
+            cudaKernelNodeParams kp; CK(cudaGraphKernelNodeGetParams(nodes[i], &kp));
+            if (kp.func == (void*)k_project_bin<true>) G.n_project = nodes[i];
+            else if (kp.func == (void*)k_bin_scatter) G.n_scatter = nodes[i];
+            else if (kp.func == (void*)k_weight_lean<1024> || kp.func == (void*)k_weight_lean<512>) G.n_lean = nodes[i];
+        }
+        if (!G.n_project || !G.n_scatter || !G.n_lean) { graph_drop(ctx); G.failed = true; return ESLAM_OK; }
+        G.valid = true; G.n = ctx->n; G.nb = F.fc.nb; G.lean_threads = ctx->env.lean_threads; G.step = *step; G.cs = *cs;
+    } else if (memcmp(&G.step, step, sizeof(*step)) != 0 || memcmp(&G.cs, cs, sizeof(*cs)) != 0) {
+        // new odometry step / contact points: the three kernels that take them
+        cudaKernelNodeParams kp;
+        int nb = F.fc.nb, n_cta = ctx->sm_count, did = 1; unsigned long long n = ctx->n;
+        void* a_project[] = {&F, &ctx->bin_count, &ctx->keys};
+        CK(cudaGraphKernelNodeGetParams(G.n_project, &kp)); kp.kernelParams = a_project; kp.extra = nullptr;
+        CK(cudaGraphExecKernelNodeSetParams(G.exec, G.n_project, &kp));
+        void* a_scatter[] = {&ctx->bin_count, &nb, &ctx->keys, &n, &ctx->bin_list, &ctx->bin_offs, &ctx->cta_bin, &n_cta, &ctx->sc, &did};
+        CK(cudaGraphKernelNodeGetParams(G.n_scatter, &kp)); kp.kernelParams = a_scatter; kp.extra = nullptr;
+        CK(cudaGraphExecKernelNodeSetParams(G.exec, G.n_scatter, &kp));
+        void* a_lean[] = {&F, &ctx->bin_list, &ctx->bin_count, &ctx->bin_offs, &ctx->bin_next, &ctx->cta_bin};
+        CK(cudaGraphKernelNodeGetParams(G.n_lean, &kp)); kp.kernelParams = a_lean; kp.extra = nullptr;
+        CK(cudaGraphExecKernelNodeSetParams(G.exec, G.n_lean, &kp));
+        G.step = *step; G.cs = *cs;
+    }
+    *done = true;
+    if (!launch) return ESLAM_OK;                                          // prepared (captured, parameters current): nothing has run
+    CK(cudaGraphLaunch(G.exec, ctx->stream));
+    ctx->launches += G.kernels;
+    ctx->last_lean = true; ctx->hint_n = 0;
+    return ESLAM_OK;
+}
+
+extern "C" {
+
 int eslam_gpu_step_fused(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const eslam_gpu_contact* pts, int n_pts,
                          eslam_gpu_update_result* result) {
     int st = check_ready(ctx, true);
@@ -914,7 +1013,9 @@ int eslam_gpu_step_fused(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const e
     ContactSet cs;
     st = build_contact_set(ctx, pts, n_pts, &cs);
     if (st != ESLAM_OK) return st;
-    st = launch_update(ctx, step, &cs, nullptr, nullptr);
+    bool done = false;
+    if (graph_wanted(ctx)) { st = graph_step(ctx, step, &cs, &done); if (st != ESLAM_OK) return st; }
+    if (!done) st = launch_update(ctx, step, &cs, nullptr, nullptr);
     if (st != ESLAM_OK) return st;
     return result ? fetch_result(ctx, result) : ESLAM_OK;
 }
@@ -935,8 +1036,22 @@ int eslam_gpu_run_steps(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const es
         k_barrier<<<1, 32, 0, ctx->stream>>>(ctx->sc, ctx->X);
         LAUNCHED();
     }
+    bool graphed = false;
+    if (graph_wanted(ctx)) { st = graph_step(ctx, step, &cs, &graphed, false); if (st != ESLAM_OK) return st; }   // capture outside the timed region
     CK(cudaEventRecord(ctx->events[0], ctx->stream));
     ctx->marks_used = 0;
+    if (graphed) {
+        // launch-bound sizes: every step is one graph launch.  The graph holds ONE pair of events around the dominant kernel
+        // (re-recorded by every replay), so its time is that of the last step, scaled to the run; step periods: the mean.
+        for (int s = 0; s < steps; ++s) { bool done = false; st = graph_step(ctx, step, &cs, &done); if (st != ESLAM_OK) return st; }
+        CK(cudaEventRecord(ctx->events[1], ctx->stream));
+        CK(cudaEventSynchronize(ctx->events[1]));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->events[0], ctx->events[1]));
+        if (elapsed_ms) *elapsed_ms = ms;
+        if (top_kernel_ms) { float t = 0; CK(cudaEventElapsedTime(&t, ctx->sg.ev0, ctx->sg.ev1)); *top_kernel_ms = t * (float)steps; }
+        ctx->step_ms.assign((size_t)(steps > 1 ? steps - 1 : 0), ms / (float)steps);
+        return last_result ? fetch_result(ctx, last_result) : ESLAM_OK;
+    }
     for (int s = 0; s < steps; ++s) {
         st = launch_update(ctx, step, &cs, ctx->events[2 + 2 * s], ctx->events[3 + 2 * s]);
         if (st != ESLAM_OK) return st;
@@ -1025,6 +1140,7 @@ int eslam_gpu_resample_n(eslam_gpu_ctx* ctx, uint64_t samples, int multinomial) 
     k_after_resample_n<<<1, 1, 0, ctx->stream>>>(ctx->sc);
     LAUNCHED();
     CK(cudaStreamSynchronize(ctx->stream));
+    graph_drop(ctx);
     ctx->n = samples; ctx->t_local = (unsigned)((samples + TILE - 1) / TILE); ctx->t_global = ctx->t_local;
     return ESLAM_OK;
 }

@@ -67,8 +67,8 @@ struct DevScalars {              // device-resident scalars of one context
     int cdf_seq;                 // the running sum of this resample was computed sequentially by k_chain (k_cdf skips)
     unsigned int ticket[4];      // "last CTA" counters: 0 k_tile_part, 1 k_loop_b, 2 k_norm_scan, 3 k_cdf
     unsigned int x_epoch[8];     // epoch of every exchange (X_*): bumped by this rank's producer, read by its consumers
+    unsigned int project_step;   // Philox counter word of project: projects done so far (device side: a captured step is replayable)
     int rank_start_valid;        // rank_start[] below holds the exact running sum in front of every rank (k_chain, exact-global walk)
-    int pad_rs;
     double rank_start[9];        // [q] = running sum before rank q's first particle, [world] = the total (ESLAM_MAX_RANKS + 1 entries)
 };
 
@@ -122,8 +122,8 @@ struct WeightCommon {
     MapParams map; ModelParams mp;
     const em::dbl2* htab;
     unsigned long long n, base;  // local particle count, global index of local particle 0
-    uint32_t project_step;
     int use_tma;                 // the map tile is staged by one TMA bulk tensor copy (tmap valid)
+    int pad_tma;
     const CUtensorMap* tmap;     // device copy of the 2-D tensor map of the elevation grid (8-byte cells, box = the tile)
     double* hint;                // [gridDim.x][2]: sums of x and y over the particles a CTA handled (tile placement hint)
     double yaw, z_delta, z_var, dmean[3], dsigma[3];
@@ -136,7 +136,7 @@ struct WeightParams {
     MapParams map; ModelParams mp;
     const em::dbl2* htab;
     unsigned long long n, base;  // local particle count, global index of local particle 0
-    uint32_t project_step;
+    int bump_project;            // k_tile_part: this update contained a project on the generic kernel -> count it
     int patch_size;              // P (0: no per-particle patches)
     int use_tma;                 // the map tile is staged by one TMA bulk tensor copy (tmap valid)
     const CUtensorMap* tmap;     // device copy of the 2-D tensor map of the elevation grid (8-byte cells, box = the tile)
@@ -755,16 +755,16 @@ __device__ __forceinline__ MapTile stage_tile_and_table(const MapParams& M, int 
 
 // PoseEstimator::project for one particle (src/PoseEstimator.cpp:196-237)
 template <class PP>
-__device__ __forceinline__ void project_particle(const PP& P, unsigned long long gi, double spread, double& x, double& y,
+__device__ __forceinline__ void project_particle(const PP& P, uint32_t pstep, unsigned long long gi, double spread, double& x, double& y,
                                                  double& th, double& z, double& zs, double& w) {
     const uint32_t sw = stream_word(em::STREAM_PROJECT, gi);
     double n0, n1, n2, unused;
-    normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 0, sw, P.mp.k0, P.mp.k1), n0, n1);
-    normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 1, sw, P.mp.k0, P.mp.k1), n2, unused);
+    normal_pair(em::philox4x32_10((uint32_t)gi, pstep, 0, sw, P.mp.k0, P.mp.k1), n0, n1);
+    normal_pair(em::philox4x32_10((uint32_t)gi, pstep, 1, sw, P.mp.k0, P.mp.k1), n2, unused);
     const double dx = P.dmean[0] + P.dsigma[0] * n0;                     // :198
     double dy = P.dmean[1] + P.dsigma[1] * n1;
     const double dth = P.dmean[2] + P.dsigma[2] * n2;
-    const em::Philox4 u = em::philox4x32_10((uint32_t)gi, P.project_step, 2, sw, P.mp.k0, P.mp.k1);
+    const em::Philox4 u = em::philox4x32_10((uint32_t)gi, pstep, 2, sw, P.mp.k0, P.mp.k1);
     if (em::u01(u.v[0], u.v[1]) < P.mp.slip_factor) dy *= em::u01(u.v[2], u.v[3]);   // :199-202
     double s, c; em::sincos_(th, s, c);
     x += c * dx - s * dy;                                                // :205
@@ -778,8 +778,8 @@ __device__ __forceinline__ void project_particle(const PP& P, unsigned long long
     if (spread > 0 && !P.mp.use_hash) {                                  // :224-236
         const double trans_fac = P.mp.spread_tf * spread, rot_fac = P.mp.spread_rf * spread;
         double sx, sy, sth;
-        normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 3, sw, P.mp.k0, P.mp.k1), sx, sy);
-        normal_pair(em::philox4x32_10((uint32_t)gi, P.project_step, 4, sw, P.mp.k0, P.mp.k1), sth, unused);
+        normal_pair(em::philox4x32_10((uint32_t)gi, pstep, 3, sw, P.mp.k0, P.mp.k1), sx, sy);
+        normal_pair(em::philox4x32_10((uint32_t)gi, pstep, 4, sw, P.mp.k0, P.mp.k1), sth, unused);
         x += sx * trans_fac + 0.0;
         y += sy * trans_fac + 0.0;
         th += sth * rot_fac + 0.0;
@@ -864,7 +864,7 @@ __global__ void __launch_bounds__(1024, 1) k_project_bin(const __grid_constant__
         if (DO_PROJECT) {
             double th = C.st.f[cur][F_TH][i], z = C.st.f[cur][F_Z][i], w = C.st.f[cur][F_W][i];
             const double spread = weighting_function(C.sc->max_weight, 0.0, C.mp.spread_thr, 0.0);   // :194
-            project_particle(C, C.base + i, spread, x, y, th, z, zs, w);
+            project_particle(C, C.sc->project_step, C.base + i, spread, x, y, th, z, zs, w);
             C.st.f[cur][F_X][i] = x; C.st.f[cur][F_Y][i] = y; C.st.f[cur][F_TH][i] = th;
             C.st.f[cur][F_Z][i] = z; C.st.f[cur][F_ZS][i] = zs; C.st.f[cur][F_W][i] = w;   // everything project changed
         }
@@ -910,8 +910,9 @@ __global__ void __launch_bounds__(1024, 1) k_project_bin(const __grid_constant__
 // (CTA c starts where sorted position c*M/G lies: CTAs per bin in proportion to the bin's particles)
 __global__ void __launch_bounds__(1024, 1) k_bin_scatter(const int* __restrict__ bin_count, int nb, const uint2* __restrict__ keys,
                                                          unsigned long long n, uint32_t* __restrict__ list, unsigned* __restrict__ bin_offs,
-                                                         int* __restrict__ cta_bin, int n_cta) {
+                                                         int* __restrict__ cta_bin, int n_cta, DevScalars* sc, int did_project) {
     pdl_start();
+    if (did_project && blockIdx.x == 0 && threadIdx.x == 0) sc->project_step += 1;   // k_project_bin has finished: its project is counted
     __shared__ unsigned offs[MAX_BINS + 1];
     __shared__ unsigned wsum[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1207,6 +1208,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_c
     if (DO_WEIGHT) mt = stage_tile_and_table(P.map, P.use_tma, P.tmap, P.htab, smem_raw);
     double spread = 0.0;
     if (DO_PROJECT) spread = weighting_function(sc->max_weight, 0.0, P.mp.spread_thr, 0.0);   // :194
+    const uint32_t pstep = sc->project_step;
 
     double* X = P.st.f[cur][F_X]; double* Y = P.st.f[cur][F_Y]; double* TH = P.st.f[cur][F_TH];
     double* Z = P.st.f[cur][F_Z]; double* ZS = P.st.f[cur][F_ZS]; double* WG = P.st.f[cur][F_W];
@@ -1217,7 +1219,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) k_project_weight(const __grid_c
         const unsigned long long i = k;
         double x = X[i], y = Y[i], th = TH[i], z = Z[i], zs = ZS[i], w = WG[i];
         if (DO_PROJECT) {                                                        // :196-237
-            project_particle(P, P.base + i, spread, x, y, th, z, zs, w);
+            project_particle(P, pstep, P.base + i, spread, x, y, th, z, zs, w);
             X[i] = x; Y[i] = y; TH[i] = th; Z[i] = z; ZS[i] = zs; WG[i] = w;     // everything project changed
         }
         hx += x; hy += y;
@@ -1256,6 +1258,7 @@ struct TilePartArgs {
     double *scratch_a, *scratch_b;
     const double* hint; unsigned n_hint; unsigned long long n_local;
     int* bin_count; unsigned* bin_next;
+    int bump_project;              // this update projected on the generic kernel: count the project (device-side Philox step)
 };
 __global__ void __launch_bounds__(SCAN_THREADS) k_tile_part(StateBufs st, DevScalars* sc, unsigned long long n, const TilePartArgs A,
                                                             const __grid_constant__ Xchg X) {
@@ -1267,6 +1270,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tile_part(StateBufs st, DevSca
     __shared__ RankPartA s_out;
     __shared__ unsigned s_epoch;
     const int cur = sc->cur;
+    if (A.bump_project && blockIdx.x == 0 && threadIdx.x == 0) sc->project_step += 1;
     const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
     double mp[EPT]; unsigned nf[EPT], fl[EPT];
     if (i0 + EPT <= n) {
@@ -1971,7 +1975,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(StateBufs st, DevScalars* sc,
         s_hdr[X.me] = h;
     }
     __syncthreads();
-    {
+    if (X.world > 1) {
         const size_t slot = XOFF_C + (size_t)X.me * XC_SLOT;
         ll_publish(X, slot, &s_hdr[X.me], XH_WORDS, s_epoch);
         if (X.world > 1 && s_hdr[X.me].n_bnd > 0) ll_publish(X, slot + XH_WORDS * 8, cs.stage, (unsigned)s_hdr[X.me].n_bnd * XE_WORDS, s_epoch);
@@ -2181,7 +2185,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
                                                             unsigned long long n_global, unsigned long long base, uint32_t k0key,
                                                             uint32_t k1key, int systematic, uint32_t* ancestors, unsigned* ticket,
                                                             const __grid_constant__ PeerTable peers, const ShardPlan sp, unsigned tile_ofs,
-                                                            unsigned my_rank, const PatchGather pg, const __grid_constant__ Xchg X) {
+                                                            unsigned my_rank, const __grid_constant__ Xchg X) {
     pdl_start();
     __shared__ double s_cdf[RS_TILES * TILE];
     if (!sc->do_resample) return;                                        // the same decision on every rank
@@ -2255,7 +2259,6 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
         }
         __syncthreads();
     }
-    unsigned src_q = 0; unsigned long long src_l = 0;                    // owner rank and owner-local index of this stratum's ancestor
     if (k < n_ctx) {
         const unsigned long long gk = systematic ? 0ull : base + k;
         const em::Philox4 r = em::philox4x32_10((uint32_t)gk, sc->resample_step, 0, stream_word(em::STREAM_RESAMPLE, gk), k0key, k1key);
@@ -2286,26 +2289,6 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
         for (int f = 0; f < 7; ++f) st.f[nxt][f][k] = peers.f[qs][cur][f][la];            // :104 copy keeps the weight (Q3)
 #pragma unroll
         for (int f = 0; f < 2; ++f) st.b[nxt][f][k] = peers.b[qs][cur][f][la];
-        src_q = qs; src_l = la;
-    }
-    if (pg.P > 0) {
-        // the ancestor's map patch travels with it: one warp copies the patches of its 32 strata one after the other
-        const int cur = sc->cur, nxt = cur ^ 1;
-        const unsigned pp = (unsigned)(pg.P * pg.P), lane = tid & 31;
-        const int have = k < n_ctx ? 1 : 0;
-        for (int j = 0; j < 32; ++j) {
-            if (!__shfl_sync(0xffffffffu, have, j)) continue;
-            const unsigned q = __shfl_sync(0xffffffffu, src_q, j);
-            const unsigned long long l = __shfl_sync(0xffffffffu, src_l, j);
-            const unsigned long long kk = kb + (tid & ~31u) + (unsigned)j;
-            const float2* src = peers.patch[q][cur] + l * pp;
-            float2* dst = pg.patch[nxt] + kk * pp;
-            if ((pp & 1u) == 0) {
-                const float4* s4 = reinterpret_cast<const float4*>(src); float4* d4 = reinterpret_cast<float4*>(dst);
-                for (unsigned c = lane; c < (pp >> 1); c += 32) d4[c] = s4[c];
-            } else for (unsigned c = lane; c < pp; c += 32) dst[c] = src[c];
-            if (lane < 2) pg.porigin[nxt][2 * kk + lane] = peers.porigin[q][cur][2 * l + lane];
-        }
     }
     // xi_k.swap(xi_kp) :107 by the last CTA (every CTA has read sc->cur by then)
     __syncthreads();
@@ -2477,6 +2460,39 @@ __global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevSc
         __threadfence();
         if (atomicAdd(A.ticket, 1u) == gridDim.x - 1) { *A.ticket = 0; sc->cur ^= 1; sc->resample_step += 1; }
     }
+}
+
+// cloneMaps (src/PoseEstimator.cpp:31-45, :252-253): every copy of a particle owns a copy of its map.  Runs after the
+// resampling kernel (which has swapped the state buffers: sc->cur is the NEW buffer): one warp per particle copies the
+// ancestor's patch and origin from the old buffer of the rank that owns the ancestor (a peer's memory over NVLink when that is
+// another GPU; its old buffer stays untouched until its next resampling, which cannot start before this rank's next k_chain).
+__global__ void __launch_bounds__(256) k_gather_patches(const DevScalars* sc, unsigned long long n, unsigned long long n_per_rank,
+                                                        const uint32_t* __restrict__ anc, const PatchGather pg,
+                                                        const __grid_constant__ PeerTable peers) {
+    pdl_start();
+    if (!sc->do_resample) return;
+    const unsigned long long k = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n) return;
+    const unsigned lane = threadIdx.x & 31;
+    const int now = sc->cur, old = now ^ 1;
+    const unsigned long long a = anc[k];
+    const unsigned q = (unsigned)(a / n_per_rank);
+    const unsigned long long la = a - (unsigned long long)q * n_per_rank;
+    const unsigned pp = (unsigned)(pg.P * pg.P);
+    const float2* src = peers.patch[q][old] + la * pp;
+    float2* dst = pg.patch[now] + k * pp;
+    if ((pp & 1u) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src); float4* d4 = reinterpret_cast<float4*>(dst);
+        const unsigned m = pp >> 1;
+        for (unsigned c0 = 0; c0 < m; c0 += 128) {                        // four 16-byte loads in flight per lane
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const unsigned c = c0 + j * 32 + lane; if (c < m) v[j] = s4[c]; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const unsigned c = c0 + j * 32 + lane; if (c < m) d4[c] = v[j]; }
+        }
+    } else for (unsigned c = lane; c < pp; c += 32) dst[c] = src[c];
+    if (lane < 2) pg.porigin[now][2 * k + lane] = peers.porigin[q][old][2 * la + lane];
 }
 
 // ------------------------------------------------------------------------------------------------ processMap
@@ -2654,6 +2670,8 @@ __global__ void __launch_bounds__(256) k_resample_n(StateBufs st, const DevScala
     }
 }
 __global__ void k_after_resample_n(DevScalars* sc) { sc->cur ^= 1; sc->resample_step += 1; }   // xi_k.swap(xi_kp) :107 / :146
+
+__global__ void k_bump_project(DevScalars* sc) { sc->project_step += 1; }   // eslam_gpu_project alone: count the project
 
 __global__ void k_fill_i32(int* p, size_t count, int v) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
