@@ -17,7 +17,7 @@ struct UpdateThreshold {                        // src/Configuration.hpp:12-30
     double distance, angle;
 };
 
-struct SurfaceHashConfig {                      // :32-49 (relocaliser: out of scope, the flag only disables spreading)
+struct SurfaceHashConfig {                      // :32-49
     SurfaceHashConfig() : useHash(false), period(10), percentage(0.05), avgFactor(0.1), slopeBins(20), angularSteps(16) {}
     bool useHash; size_t period; double percentage, avgFactor; size_t slopeBins, angularSteps;
 };

@@ -16,6 +16,7 @@ class EmbodiedSlamFilter {
     eslam::PoseEstimator filter;
     base::Affine3d udPose, mapPose;                          // poses of the last measurement / mapping update
     bool sharedMap;
+    SurfaceHash hash;                                        // :70
     base::Quaterniond lastOrientation; odometry::BodyContactState lastBodyState;
 
 public:
@@ -24,7 +25,15 @@ public:
 
     // init(env, pose, useSharedMap): the environment must hold a map (:77-104), particles are drawn around the pose (:118-125)
     void init(const DenseGrid* map, const base::Pose& pose, bool useSharedMap = true,
-              const SurfaceHashConfig& = SurfaceHashConfig()) {
+              const SurfaceHashConfig& hashConfig = SurfaceHashConfig()) {
+        if (hashConfig.useHash && useSharedMap && map && map->width > 0) {                             // :93-98,:109-114
+            hash.setConfiguration(hashConfig); hash.create();
+            filter.setEnvironment(*map, true, patchCells);
+            filter.init((int)eslamConfig.particleCount, &hash);
+            udPose = base::Affine3d::Identity(); udPose.translation() = base::Vector3d(1000, 0, 0); mapPose = udPose;
+            sharedMap = true;
+            return;
+        }
         if (!map || map->width == 0)
             throw std::runtime_error("The provided environment does not contain an mls grid.");    // :104
         const double angle = base::getYaw(pose.orientation);

@@ -3,13 +3,15 @@
 #ifndef ESLAM_FACADE_POSEESTIMATOR_HPP
 #define ESLAM_FACADE_POSEESTIMATOR_HPP
 #include "ContactModel.hpp"
+#include "SurfaceHash.hpp"
 
 namespace eslam {
 
 class PoseEstimator : public ParticleFilter<PoseParticle> {
 public:
     PoseEstimator(odometry::FootContact& odometry, const eslam::Configuration& config)      // src/PoseEstimator.cpp:13-25
-        : ParticleFilter<Particle>(toGpuConfig(config)), config(config), odometry(odometry), max_weight(0), haveEnv(false), useSharedMap(true) {}
+        : ParticleFilter<Particle>(toGpuConfig(config)), config(config), odometry(odometry), max_weight(0), haveEnv(false), useSharedMap(true),
+          hash(0), hashCalls(0) {}
     ~PoseEstimator() {}
 
     void init(int numParticles, const base::Pose2D& mu, const base::Pose2D& sigma, double zpos = 0, double zsigma = 0) {   // :88-102
@@ -22,7 +24,21 @@ public:
     // setEnvironment(env, map, useShared) (:47-62).  useShared == false is the per-particle-map mode: every particle owns
     // a map that contact heights and scans are merged into and that travels with it through resampling (cloneMaps :31-45,
     // :252-253).  On the device a particle's own map is a patchCells x patchCells overlay of the shared grid.
+    // init(numParticles, hash) (:75-86): every particle a candidate pose drawn from the surface hash; project() then re-seeds the
+    // lowest-weight particles from it every hash period (:239-241, sampleFromHash :130-182) and stops spreading (:224)
+    void init(int numParticles, SurfaceHash* h) {
+        if (!h || !h->created) throw std::runtime_error("could not sample from pose hash.");           // :84
+        if (!gpuConfig.use_hash) { eslam_gpu_config c = gpuConfig; c.use_hash = 1; recreate(c); if (haveEnv) attachGrid(gpu, envGrid); }
+        gpu_check(gpu, eslam_gpu_hash_create(gpu, (int)h->config.slopeBins, (int)h->config.angularSteps));
+        const int st = eslam_gpu_init_from_hash(gpu, (uint64_t)numParticles);
+        if (st == ESLAM_ERR_EMPTY) throw std::runtime_error("could not sample from pose hash.");         // :84
+        gpu_check(gpu, st);
+        hash = h; hashCalls = 0;
+        deviceChanged();
+    }
+
     void setEnvironment(const DenseGrid& map, bool useShared = true, int patchCells = 16, const double* C_global2local = 0) {
+        envGrid = map;
         const int want = useShared ? 0 : patchCells;
         if (gpuConfig.patch_size != want) { eslam_gpu_config c = gpuConfig; c.patch_size = want; recreate(c); }
         useSharedMap = useShared;
@@ -54,7 +70,7 @@ public:
         pd.orientation = zCompensatedOrientation;
     }
 
-    void project(const odometry::BodyContactState& /*state*/, const base::Quaterniond& orientation) {   // :184-242
+    void project(const odometry::BodyContactState& state, const base::Quaterniond& orientation) {   // :184-242
         flush();
         eslam_gpu_step s;
         s.yaw = base::getYaw(orientation);                                                   // :186
@@ -66,6 +82,11 @@ public:
         for (int i = 0; i < 3; i++) s.delta_sigma[i] = odometry.getSampleSigma()[i];        // :198
         gpu_check(gpu, eslam_gpu_project(gpu, &s));
         deviceChanged();
+        if (hash && ((hashCalls++) % hash->config.period) == 0) {                              // :239-241
+            contactModel.setContactPoints(state, orientation);                               // :137
+            std::vector<eslam_gpu_contact> pts = toAbi(contactModel.getContactState());
+            gpu_check(gpu, eslam_gpu_sample_from_hash(gpu, hash->config.percentage, hash->config.avgFactor, pts.data(), (int)pts.size(), NULL));
+        }
     }
 
     void update(const odometry::BodyContactState& state, const base::Quaterniond& orientation,
@@ -108,6 +129,8 @@ private:
     base::Quaterniond zCompensatedOrientation;
     double max_weight;
     bool haveEnv, useSharedMap;
+    DenseGrid envGrid;                                   // kept to re-attach the map when the context is recreated
+    SurfaceHash* hash; size_t hashCalls;                 // :148, the call counter of :239
     eslam_gpu_update_result lastResult;
 };
 

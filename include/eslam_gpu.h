@@ -224,6 +224,26 @@ int eslam_gpu_process_map(eslam_gpu_ctx* ctx, const eslam_gpu_scan* scan, int ma
 typedef struct eslam_gpu_gaussian2d { double weight; double mean[2]; double cov[4]; } eslam_gpu_gaussian2d;
 int eslam_gpu_pose_moments(eslam_gpu_ctx* ctx, eslam_gpu_gaussian2d* out);
 
+/* SurfaceHash, the relocaliser (src/SurfaceHash.hpp:113-232): for every grid cell and each of `angular_steps` headings the
+ * least-squares plane under a 4-point footprint gives (slope_x, slope_y); candidate poses are bucketed by slope
+ * (slope_bins x slope_bins over [-1, 1]^2).  Built on the device from the attached grid (identity map frame).
+ *   eslam_gpu_hash_create       SurfaceHash::create (:155-231)
+ *   eslam_gpu_hash_info         size of the table, candidates per bucket (slope_bins^2 counts; either pointer may be NULL)
+ *   eslam_gpu_hash_get          parity tap: candidates [first, first + count) in creation order (heading, row, column)
+ *   eslam_gpu_init_from_hash    PoseEstimator::init(numParticles, hash) (src/PoseEstimator.cpp:75-86); ESLAM_ERR_EMPTY =
+ *                               "could not sample from pose hash." (:84)
+ *   eslam_gpu_sample_from_hash  PoseEstimator::sampleFromHash (src/PoseEstimator.cpp:130-182), which project() calls every
+ *                               hash period (:239-241): the replace_percentage * relevance^3 lowest-weight particles become
+ *                               candidates whose slopes match the plane through the lowest contact point of every group;
+ *                               their weight is getWeightAvg() * avg_factor * relevance^3, zSigma 0.5.  pts as for update().
+ * The reference draws with libc rand(); here the draws come from the Philox stream (noise is unpinned either way). */
+int eslam_gpu_hash_create(eslam_gpu_ctx* ctx, int slope_bins, int angular_steps);
+int eslam_gpu_hash_info(eslam_gpu_ctx* ctx, uint64_t* n_poses, uint32_t* bucket_counts);
+int eslam_gpu_hash_get(eslam_gpu_ctx* ctx, uint64_t first, uint64_t count, double* x, double* y, double* theta, double* z, int32_t* bucket);
+int eslam_gpu_init_from_hash(eslam_gpu_ctx* ctx, uint64_t n);
+int eslam_gpu_sample_from_hash(eslam_gpu_ctx* ctx, double replace_percentage, double avg_factor, const eslam_gpu_contact* pts, int n_pts,
+                               uint64_t* replaced);
+
 int eslam_gpu_synchronize(eslam_gpu_ctx* ctx);
 /* diagnostics of the exact running-sum machinery: out = {sequential-fallback runs, boundary elements of the last
  * resample, pending error flags, resamples done} */

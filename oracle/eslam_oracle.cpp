@@ -132,6 +132,8 @@ struct Noise {
 
 }  // namespace
 
+extern "C" int eslam_oracle_lowest_points(const eslam_gpu_contact* pts, int n_pts, int update_probabilities, double* lowest_xyz, float* contact_out);
+
 // ------------------------------------------------------------------------------------------------
 // The filter
 // ------------------------------------------------------------------------------------------------
@@ -157,6 +159,9 @@ struct eslam_oracle_ctx {
     double sh_d1 = 0, sh_d2 = 0, sh_A = 0;
     // per-particle patches
     std::vector<float> patches; std::vector<int32_t> patch_origin;
+    // SurfaceHash (src/SurfaceHash.hpp:113-232)
+    struct HashPose { uint16_t m, n; uint8_t a; uint16_t bucket; double z; };
+    std::vector<HashPose> hash_poses; std::vector<uint32_t> hash_by_bucket, hash_offs; int hash_bins = 0, hash_steps = 0; uint32_t hash_step = 0;
 
     eslam_oracle_ctx(const eslam_gpu_config& c, int pol) : cfg(c), policy(pol), noise(c.seed) {
         shard.rank = 0; shard.world = 1; shard.global_count = 0;
@@ -483,6 +488,113 @@ struct eslam_oracle_ctx {
                 }
             }
         }
+        return ESLAM_OK;
+    }
+
+    // --- SurfaceHash::create (src/SurfaceHash.hpp:155-231): for every heading a of `steps` and every grid cell the least-squares
+    //     plane under a 4-point footprint (base 0.5 m) -> (slope_x, slope_y) -> bucket; candidate pose = cell centre, heading
+    //     a 2 pi / steps, z = mean height + 0.18.  Kept as in the reference: the footprint is rotated BEFORE it is used, i.e. by
+    //     (a + 1) steps while the stored heading is a steps (:177-181); the plane is fitted over the UNROTATED footprint
+    //     coordinates (:199).  Defined here (the reference reads uninitialised indices there): a footprint point outside the
+    //     grid is skipped.  Order of the candidates: heading, then grid row, then column.
+    int hash_create(int bins, int steps) {
+        if (!grid.attached || !grid.identity || bins <= 0 || bins > 255 || steps <= 0 || steps > 255 || grid.w > 65535 || grid.h > 65535) return ESLAM_ERR_INVALID;
+        hash_bins = bins; hash_steps = steps; hash_poses.clear();
+        for (int a = 0; a < steps; a++) {
+            const double rot = (a + 1) * 2.0 * M_PI / steps;
+            double s, c; em::sincos_(rot, s, c);
+            double rx[4], ry[4], fx[4], fy[4];
+            for (int i = 0; i < 4; i++) { em::hash_footprint(i, fx[i], fy[i]); rx[i] = c * fx[i] - s * fy[i]; ry[i] = s * fx[i] + c * fy[i]; }
+            for (int n = 0; n < grid.h; n++)
+                for (int m = 0; m < grid.w; m++) {
+                    const double x = grid.ox + (m + 0.5) * grid.sx, y = grid.oy + (n + 0.5) * grid.sy;   // fromGrid :189
+                    double gx[4], gy[4], gz[4], mean_z = 0; int cnt = 0;
+                    for (int i = 0; i < 4; i++) {                                                          // :193-206
+                        int ix, iy;
+                        if (!em::cell_index_exact(x + rx[i], grid.ox, grid.sx, grid.w, ix) || !em::cell_index_exact(y + ry[i], grid.oy, grid.sy, grid.h, iy)) continue;
+                        const float mean = grid.cells[2 * ((size_t)iy * grid.w + ix)], sd = grid.cells[2 * ((size_t)iy * grid.w + ix) + 1];
+                        if (std::isnan(mean) || std::isnan(sd)) continue;
+                        gx[cnt] = fx[i]; gy[cnt] = fy[i]; gz[cnt] = (double)mean; mean_z += (double)mean; cnt++;
+                    }
+                    if (cnt < 3) continue;                                                                 // :209
+                    mean_z /= cnt;
+                    double slx, sly;
+                    if (!em::surface_slopes(gx, gy, gz, cnt, slx, sly)) continue;                          // :211-212
+                    HashPose hp; hp.m = (uint16_t)m; hp.n = (uint16_t)n; hp.a = (uint8_t)a;
+                    hp.bucket = (uint16_t)(em::slope_bucket(slx, bins) * bins + em::slope_bucket(sly, bins));   // :218
+                    hp.z = mean_z + 0.18;                                                                  // :216
+                    hash_poses.push_back(hp);
+                }
+        }
+        // the buckets: candidate indices grouped by bucket, creation order inside a bucket
+        hash_offs.assign((size_t)bins * bins + 1, 0);
+        for (size_t i = 0; i < hash_poses.size(); i++) hash_offs[hash_poses[i].bucket + 1]++;
+        for (size_t b = 0; b < (size_t)bins * bins; b++) hash_offs[b + 1] += hash_offs[b];
+        hash_by_bucket.resize(hash_poses.size());
+        std::vector<uint32_t> fill(hash_offs.begin(), hash_offs.end() - 1);
+        for (size_t i = 0; i < hash_poses.size(); i++) hash_by_bucket[fill[hash_poses[i].bucket]++] = (uint32_t)i;
+        return ESLAM_OK;
+    }
+    void hash_pose(const HashPose& hp, double& x, double& y, double& theta) const {
+        x = grid.ox + (hp.m + 0.5) * grid.sx; y = grid.oy + (hp.n + 0.5) * grid.sy;
+        theta = hp.a * 2.0 * M_PI / hash_steps;                                                             // :175
+    }
+    // --- PoseEstimator::init(numParticles, hash) (src/PoseEstimator.cpp:75-86): every particle a uniformly drawn candidate
+    //     (SurfaceHash::sample :129-133 uses libc rand(); here the Philox stream STREAM_HASH, counter = particle index)
+    int init_from_hash(uint64_t n) {
+        if (hash_poses.empty()) return ESLAM_ERR_EMPTY;                                                     // "could not sample from pose hash." :84
+        PoseParticle p; std::memset(&p, 0, sizeof(p)); p.floating = true;
+        xi_k.assign(n, p);
+        for (uint64_t i = 0; i < n; i++) {
+            const em::Philox4 r = noise.draw(i, 0xFFFFFFFFu, 0, em::STREAM_HASH);
+            const size_t idx = std::min((size_t)(em::u01(r.v[0], r.v[1]) * (double)hash_poses.size()), hash_poses.size() - 1);
+            double th; hash_pose(hash_poses[idx], xi_k[i].px, xi_k[i].py, th);
+            xi_k[i].orientation = th; xi_k[i].zPos = hash_poses[idx].z;                                     // PoseParticle(position, orientation, zpos): zSigma 0, weight 0
+        }
+        if (cfg.patch_size > 0) {
+            const size_t cells = (size_t)cfg.patch_size * cfg.patch_size * 2;
+            patches.assign(n * cells, std::numeric_limits<float>::quiet_NaN()); patch_origin.assign(2 * n, INT32_MIN);
+        }
+        max_weight = 0; project_step = 0; resample_step = 0; hash_step = 0;
+        return ESLAM_OK;
+    }
+    // --- PoseEstimator::sampleFromHash (src/PoseEstimator.cpp:130-182): the lowest-weight particles are replaced by candidates
+    //     whose surface slopes match what the body's lowest contact points see
+    template <class A>
+    int sample_from_hash(double replace_percentage, double avg_factor, const eslam_gpu_contact* pts, int n_pts, uint64_t* replaced) {
+        if (replaced) *replaced = 0;
+        if (hash_poses.empty() || xi_k.empty()) return ESLAM_ERR_EMPTY;
+        std::vector<double> low((size_t)n_pts * 3);
+        const int nl = eslam_oracle_lowest_points(pts, n_pts, 0, low.data(), nullptr);                     // :139-140
+        std::vector<double> lx(nl), ly(nl), lz(nl);
+        for (int i = 0; i < nl; i++) { lx[i] = low[3 * i]; ly[i] = low[3 * i + 1]; lz[i] = low[3 * i + 2]; }
+        double slx = 0, sly = 0;
+        if (nl < 3 || !em::surface_slopes(lx.data(), ly.data(), lz.data(), nl, slx, sly)) { hash_step++; return ESLAM_OK; }   // :143-144
+        const int b = em::slope_bucket(slx, hash_bins) * hash_bins + em::slope_bucket(sly, hash_bins);
+        const size_t in_bucket = hash_offs[b + 1] - hash_offs[b];
+        const double relevance = 1.0 - 1.0 * in_bucket / hash_poses.size();                                 // getRelevance :139-144
+        const double relevance_factor = relevance * relevance * relevance;                                  // pow(., 3) :156
+        size_t replace_count = (size_t)(xi_k.size() * replace_percentage * relevance_factor);               // :157
+        if (relevance_factor < 0.8) replace_count = 0;                                                      // :158-159
+        std::vector<double> w(xi_k.size());
+        for (size_t i = 0; i < xi_k.size(); i++) w[i] = xi_k[i].weight;
+        const double weight = (A::sum(w) / xi_k.size()) * avg_factor * relevance_factor;                   // :162 getWeightAvg()
+        typedef std::pair<float, unsigned long> weight_index;                                               // :147-153
+        std::vector<weight_index> widxs(xi_k.size());
+        for (size_t i = 0; i < xi_k.size(); i++) widxs[i] = weight_index((float)xi_k[i].weight, i);
+        std::stable_sort(widxs.begin(), widxs.end(), [](const weight_index& l, const weight_index& r) { return l.first < r.first; });
+        uint64_t done = 0;
+        for (size_t i = 0; i < replace_count && in_bucket > 0; i++) {                                       // :164-180 (sample(params) == NULL: nothing)
+            const em::Philox4 r = noise.draw(i, hash_step, 1, em::STREAM_HASH);
+            const size_t k = std::min((size_t)(em::u01(r.v[0], r.v[1]) * (double)in_bucket), in_bucket - 1);
+            const HashPose& hp = hash_poses[hash_by_bucket[hash_offs[b] + k]];
+            PoseParticle& pose = xi_k[widxs[i].second];
+            double th; hash_pose(hp, pose.px, pose.py, th);
+            pose.orientation = th; pose.zPos = hp.z; pose.zSigma = 0.5; pose.floating = true; pose.weight = weight;   // :170-175
+            done++;
+        }
+        hash_step++;
+        if (replaced) *replaced = done;
         return ESLAM_OK;
     }
 
@@ -1097,6 +1209,40 @@ int eslam_oracle_pose_moments(eslam_oracle_ctx* ctx, eslam_gpu_gaussian2d* out) 
     if (ctx->xi_k.empty()) return ESLAM_ERR_EMPTY;
     DISPATCH(ctx, ctx->pose_moments<Literal>(out), ctx->pose_moments<Shared>(out));
     return ESLAM_OK;
+}
+
+int eslam_oracle_hash_create(eslam_oracle_ctx* ctx, int slope_bins, int angular_steps) {
+    if (!ctx) return ESLAM_ERR_INVALID;
+    return ctx->hash_create(slope_bins, angular_steps);
+}
+int eslam_oracle_hash_info(eslam_oracle_ctx* ctx, uint64_t* n_poses, uint32_t* bucket_counts) {
+    if (!ctx) return ESLAM_ERR_INVALID;
+    if (n_poses) *n_poses = ctx->hash_poses.size();
+    if (bucket_counts && !ctx->hash_offs.empty()) for (size_t b = 0; b + 1 < ctx->hash_offs.size(); b++) bucket_counts[b] = ctx->hash_offs[b + 1] - ctx->hash_offs[b];
+    return ESLAM_OK;
+}
+int eslam_oracle_hash_get(eslam_oracle_ctx* ctx, uint64_t first, uint64_t count, double* x, double* y, double* theta, double* z, int32_t* bucket) {
+    if (!ctx || first + count > ctx->hash_poses.size()) return ESLAM_ERR_INVALID;
+    for (uint64_t i = 0; i < count; i++) {
+        const eslam_oracle_ctx::HashPose& hp = ctx->hash_poses[first + i];
+        double px, py, th; ctx->hash_pose(hp, px, py, th);
+        if (x) x[i] = px;
+        if (y) y[i] = py;
+        if (theta) theta[i] = th;
+        if (z) z[i] = hp.z;
+        if (bucket) bucket[i] = hp.bucket;
+    }
+    return ESLAM_OK;
+}
+int eslam_oracle_init_from_hash(eslam_oracle_ctx* ctx, uint64_t n) {
+    if (!ctx || n == 0) return ESLAM_ERR_INVALID;
+    return ctx->init_from_hash(n);
+}
+int eslam_oracle_sample_from_hash(eslam_oracle_ctx* ctx, double replace_percentage, double avg_factor, const eslam_gpu_contact* pts, int n_pts,
+                                  uint64_t* replaced) {
+    if (!ctx || !pts || n_pts < 0 || n_pts > ESLAM_MAX_CONTACTS) return ESLAM_ERR_INVALID;
+    return DISPATCH(ctx, ctx->sample_from_hash<Literal>(replace_percentage, avg_factor, pts, n_pts, replaced),
+                    ctx->sample_from_hash<Shared>(replace_percentage, avg_factor, pts, n_pts, replaced));
 }
 
 int eslam_oracle_get_patches(eslam_oracle_ctx* ctx, float* cells, int32_t* origin_xy) {

@@ -63,6 +63,12 @@ int eslam_oracle_evaluate_poses(eslam_oracle_ctx* ctx, uint64_t n, const double*
 int eslam_oracle_get_patches(eslam_oracle_ctx* ctx, float* cells_mean_stdev, int32_t* origin_xy);
 int eslam_oracle_process_map(eslam_oracle_ctx* ctx, const eslam_gpu_scan* scan, int match, int update);
 int eslam_oracle_pose_moments(eslam_oracle_ctx* ctx, eslam_gpu_gaussian2d* out);
+int eslam_oracle_hash_create(eslam_oracle_ctx* ctx, int slope_bins, int angular_steps);
+int eslam_oracle_hash_info(eslam_oracle_ctx* ctx, uint64_t* n_poses, uint32_t* bucket_counts);
+int eslam_oracle_hash_get(eslam_oracle_ctx* ctx, uint64_t first, uint64_t count, double* x, double* y, double* theta, double* z, int32_t* bucket);
+int eslam_oracle_init_from_hash(eslam_oracle_ctx* ctx, uint64_t n);
+int eslam_oracle_sample_from_hash(eslam_oracle_ctx* ctx, double replace_percentage, double avg_factor, const eslam_gpu_contact* pts, int n_pts,
+                                  uint64_t* replaced);
 
 /* FakeMLSAccess of test/testContactModel.cpp:8-38 as the map: 4 quadrants, index = 2*(y>0) + (x>0);
  * res may be NULL (all present).  Replaces the grid for evaluate_poses; queried points are recorded. */

@@ -137,6 +137,11 @@ SIGNATURES = {
     "get_patches": (C.c_int, [C.c_void_p, _fp, _i32p]),
     "process_map": (C.c_int, [C.c_void_p, C.POINTER(Scan), C.c_int, C.c_int]),
     "pose_moments": (C.c_int, [C.c_void_p, C.POINTER(Gaussian2d)]),
+    "hash_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "hash_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), _u32p]),
+    "hash_get": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, _dp, _dp, _dp, _dp, _i32p]),
+    "init_from_hash": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "sample_from_hash": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.POINTER(Contact), C.c_int, C.POINTER(C.c_uint64)]),
 }
 
 GPU_ONLY = {

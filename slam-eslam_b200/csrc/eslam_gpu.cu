@@ -2,6 +2,7 @@
 // peer-memory bootstrap of the sharded (multi-GPU) filter (the step's exchanges run inside its kernels).  All arithmetic lives in eslam_kernels.cuh; there is no CPU
 // implementation of any step in this library.
 #include "eslam_kernels.cuh"
+#include "eslam_hash.cuh"
 #include "eslam_nccl.h"
 
 #include <math.h>
@@ -77,6 +78,9 @@ struct eslam_gpu_ctx {
     // map
     float2* cells; MapParams map; bool has_map;
     void* scan_cells; size_t scan_cap;                // processMap: the scan's surfaces on the device
+    // SurfaceHash: candidate poses (creation order), their indices grouped by slope bucket, per-bucket counts / offsets (host)
+    HashPose* hash_poses; unsigned* hash_by_bucket; unsigned hash_n; int hash_bins, hash_steps; uint32_t hash_step;
+    std::vector<unsigned> hash_counts, hash_offs;
     CUtensorMap tmap; CUtensorMap* d_tmap; bool has_tmap;   // TMA descriptor of the grid (host copy, device copy)
     em::dbl2* htab;
     int max_smem_optin, sm_count;
@@ -473,7 +477,7 @@ void eslam_gpu_destroy(eslam_gpu_ctx* ctx) {
     if (ctx->sc_host) cudaFreeHost(ctx->sc_host);
     cudaFree(ctx->sc); cudaFree(ctx->d_tmap); cudaFree(ctx->htab); cudaFree(ctx->cells); cudaFree(ctx->hint); cudaFree(ctx->ticket);
     cudaFree(ctx->bin_count); cudaFree(ctx->bin_offs); cudaFree(ctx->bin_next); cudaFree(ctx->cta_bin);
-    cudaFree(ctx->shard_tot); cudaFree(ctx->shard_sums); cudaFree(ctx->scan_cells);
+    cudaFree(ctx->shard_tot); cudaFree(ctx->shard_sums); cudaFree(ctx->scan_cells); cudaFree(ctx->hash_poses); cudaFree(ctx->hash_by_bucket);
     graph_drop(ctx);
     if (ctx->sg.ev0) { cudaEventDestroy(ctx->sg.ev0); cudaEventDestroy(ctx->sg.ev1); }
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
@@ -1315,6 +1319,167 @@ int eslam_gpu_pose_moments(eslam_gpu_ctx* ctx, eslam_gpu_gaussian2d* out) {
     const double* c = ctx->sc_host->centroid;
     out->weight = W; out->mean[0] = mx; out->mean[1] = my;
     out->cov[0] = c[0] / W; out->cov[1] = out->cov[2] = c[1] / W; out->cov[3] = c[2] / W;
+    return ESLAM_OK;
+}
+
+// ---- SurfaceHash (src/SurfaceHash.hpp:113-232; src/PoseEstimator.cpp:75-86,130-182)
+int eslam_gpu_hash_create(eslam_gpu_ctx* ctx, int slope_bins, int angular_steps) {
+    if (!ctx) return ESLAM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->has_map) { ctx->error = "No environment attached."; return ESLAM_ERR_NO_ENVIRONMENT; }
+    if (!ctx->map.identity || slope_bins <= 0 || slope_bins > 255 || angular_steps <= 0 || angular_steps > 255 || ctx->map.W > 65535 || ctx->map.H > 65535) {
+        ctx->error = "SurfaceHash needs an identity map frame, at most 255 slope bins / headings and a grid of at most 65535 cells a side";
+        return ESLAM_ERR_INVALID;
+    }
+    cudaFree(ctx->hash_poses); cudaFree(ctx->hash_by_bucket); ctx->hash_poses = nullptr; ctx->hash_by_bucket = nullptr; ctx->hash_n = 0;
+    ctx->hash_bins = slope_bins; ctx->hash_steps = angular_steps; ctx->hash_step = 0;
+    HashArgs A; A.map = ctx->map; A.bins = slope_bins; A.steps = angular_steps;
+    const unsigned rows = (unsigned)angular_steps * (unsigned)ctx->map.H, nb = (unsigned)slope_bins * slope_bins;
+    struct Temps { unsigned *cnt = nullptr, *offs = nullptr, *bcnt = nullptr, *idx = nullptr; unsigned short *keys = nullptr, *keys2 = nullptr; void* tmp = nullptr;
+                   ~Temps() { cudaFree(cnt); cudaFree(offs); cudaFree(bcnt); cudaFree(idx); cudaFree(keys); cudaFree(keys2); cudaFree(tmp); } } T;
+    CK(dalloc(&T.cnt, (size_t)rows + 1)); CK(dalloc(&T.offs, (size_t)rows + 1)); CK(dalloc(&T.bcnt, (size_t)nb));
+    CK(cudaMemsetAsync(T.cnt, 0, (rows + 1) * sizeof(unsigned), ctx->stream));
+    CK(cudaMemsetAsync(T.bcnt, 0, nb * sizeof(unsigned), ctx->stream));
+    k_hash_rows<false><<<rows, 256, 0, ctx->stream>>>(A, T.cnt, nullptr, nullptr, nullptr);
+    LAUNCHED();
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, T.cnt, T.offs, (int)rows + 1, ctx->stream);
+    CK(cudaMalloc(&T.tmp, tb));
+    cub::DeviceScan::ExclusiveSum(T.tmp, tb, T.cnt, T.offs, (int)rows + 1, ctx->stream);
+    unsigned total = 0;
+    CK(cudaMemcpyAsync(&total, T.offs + rows, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->hash_counts.assign(nb, 0); ctx->hash_offs.assign(nb + 1, 0);
+    if (total == 0) return ESLAM_OK;
+    CK(dalloc(&ctx->hash_poses, (size_t)total)); CK(dalloc(&ctx->hash_by_bucket, (size_t)total));
+    k_hash_rows<true><<<rows, 256, 0, ctx->stream>>>(A, nullptr, T.offs, ctx->hash_poses, T.bcnt);
+    LAUNCHED();
+    // candidate indices grouped by bucket, creation order inside a bucket: a stable sort of (bucket, index)
+    CK(dalloc(&T.keys, (size_t)total)); CK(dalloc(&T.keys2, (size_t)total)); CK(dalloc(&T.idx, (size_t)total));
+    k_hash_keys<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->hash_poses, total, T.keys, T.idx);
+    LAUNCHED();
+    cudaFree(T.tmp); T.tmp = nullptr; tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, T.keys, T.keys2, T.idx, ctx->hash_by_bucket, (int)total, 0, 16, ctx->stream);
+    CK(cudaMalloc(&T.tmp, tb));
+    cub::DeviceRadixSort::SortPairs(T.tmp, tb, T.keys, T.keys2, T.idx, ctx->hash_by_bucket, (int)total, 0, 16, ctx->stream);
+    CK(cudaMemcpyAsync(ctx->hash_counts.data(), T.bcnt, nb * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    for (unsigned b = 0; b < nb; ++b) ctx->hash_offs[b + 1] = ctx->hash_offs[b] + ctx->hash_counts[b];
+    ctx->hash_n = total;
+    return ESLAM_OK;
+}
+
+int eslam_gpu_hash_info(eslam_gpu_ctx* ctx, uint64_t* n_poses, uint32_t* bucket_counts) {
+    if (!ctx) return ESLAM_ERR_INVALID;
+    if (n_poses) *n_poses = ctx->hash_n;
+    if (bucket_counts) for (size_t b = 0; b < ctx->hash_counts.size(); ++b) bucket_counts[b] = ctx->hash_counts[b];
+    return ESLAM_OK;
+}
+
+int eslam_gpu_hash_get(eslam_gpu_ctx* ctx, uint64_t first, uint64_t count, double* x, double* y, double* theta, double* z, int32_t* bucket) {
+    if (!ctx || first + count > ctx->hash_n) return ESLAM_ERR_INVALID;
+    if (count == 0) return ESLAM_OK;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<HashPose> h(count);
+    CK(cudaMemcpyAsync(h.data(), ctx->hash_poses + first, count * sizeof(HashPose), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const MapParams& M = ctx->map;
+    for (uint64_t i = 0; i < count; ++i) {
+        if (x) x[i] = M.ox + (h[i].m + 0.5) * M.sx;
+        if (y) y[i] = M.oy + (h[i].n + 0.5) * M.sy;
+        if (theta) theta[i] = h[i].a * 2.0 * M_PI / ctx->hash_steps;
+        if (z) z[i] = h[i].z;
+        if (bucket) bucket[i] = h[i].bucket;
+    }
+    return ESLAM_OK;
+}
+
+int eslam_gpu_init_from_hash(eslam_gpu_ctx* ctx, uint64_t n) {
+    if (!ctx || n == 0) return ESLAM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->hash_n == 0) { ctx->error = "could not sample from pose hash."; return ESLAM_ERR_EMPTY; }   // src/PoseEstimator.cpp:84
+    int st = ensure_capacity(ctx, n);
+    if (st != ESLAM_OK) return st;
+    DevScalars init; memset(&init, 0, sizeof(init));
+    CK(cudaStreamSynchronize(ctx->side));
+    *ctx->sc_async = init; *ctx->sc_host = init;
+    CK(cudaMemcpyAsync(ctx->sc, ctx->sc_host, sizeof(DevScalars), cudaMemcpyHostToDevice, ctx->stream));
+    if (sharded(ctx)) CK(cudaMemsetAsync(ctx->xchg, 0, ctx->x_bytes, ctx->stream));   // the exchange epochs restart with the scalars
+    st = reset_patches(ctx);
+    if (st != ESLAM_OK) return st;
+    ctx->hash_step = 0;
+    const ModelParams mp = model_params(ctx);
+    k_init_from_hash<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->st, ctx->sc, n, base_index(ctx), mp.k0, mp.k1, ctx->hash_poses, ctx->hash_n,
+                                                                          ctx->map, ctx->hash_steps);
+    LAUNCHED();
+    CK(cudaStreamSynchronize(ctx->stream));
+    return ESLAM_OK;
+}
+
+}  // extern "C"
+
+// ContactModel::lowestPointHeuristic (src/ContactModel.cpp:48-79) on the rotated contact points: ungrouped points stand for
+// themselves, a run of one group id is represented by its lowest member (the first one on ties)
+static int lowest_points_per_group(const eslam_gpu_contact* pts, int n, double* lx, double* ly, double* lz) {
+    int count = 0;
+    for (int first = 0; first < n;) {
+        int low = first, last = first;
+        if (pts[first].group_id >= 0) {
+            while (last + 1 < n && pts[last + 1].group_id == pts[first].group_id) ++last;
+            for (int k = first + 1; k <= last; ++k) if (pts[k].position[2] < pts[low].position[2]) low = k;
+        }
+        lx[count] = pts[low].position[0]; ly[count] = pts[low].position[1]; lz[count] = pts[low].position[2]; ++count;
+        first = last + 1;
+    }
+    return count;
+}
+
+extern "C" {
+
+int eslam_gpu_sample_from_hash(eslam_gpu_ctx* ctx, double replace_percentage, double avg_factor, const eslam_gpu_contact* pts, int n_pts,
+                               uint64_t* replaced) {
+    if (replaced) *replaced = 0;
+    int st = check_ready(ctx, false);
+    if (st != ESLAM_OK) return st;
+    if (!pts || n_pts < 0 || n_pts > ESLAM_MAX_CONTACTS) return ESLAM_ERR_INVALID;
+    if (sharded(ctx)) { ctx->error = "sampleFromHash is not available on sharded contexts"; return ESLAM_ERR_INVALID; }
+    if (ctx->hash_n == 0) { ctx->error = "no pose hash (eslam_gpu_hash_create)"; return ESLAM_ERR_EMPTY; }
+    double lx[ESLAM_MAX_CONTACTS], ly[ESLAM_MAX_CONTACTS], lz[ESLAM_MAX_CONTACTS];
+    const int nl = lowest_points_per_group(pts, n_pts, lx, ly, lz);                   // src/PoseEstimator.cpp:139-140
+    double slx = 0, sly = 0;
+    const uint32_t hstep = ctx->hash_step++;
+    if (nl < 3 || !em::surface_slopes(lx, ly, lz, nl, slx, sly)) return ESLAM_OK;     // :143-144
+    const int b = em::slope_bucket(slx, ctx->hash_bins) * ctx->hash_bins + em::slope_bucket(sly, ctx->hash_bins);
+    const unsigned in_bucket = ctx->hash_counts[b];
+    const double relevance = 1.0 - 1.0 * in_bucket / ctx->hash_n;                     // SurfaceHash::getRelevance :139-144
+    const double relevance_factor = relevance * relevance * relevance;                // pow(., 3) :156
+    size_t replace_count = (size_t)(ctx->n * replace_percentage * relevance_factor);  // :157
+    if (relevance_factor < 0.8) replace_count = 0;                                    // :158-159
+    if (replace_count == 0 || in_bucket == 0) return ESLAM_OK;                        // nothing to replace / sample(params) == NULL
+    if (replace_count > ctx->n) replace_count = (size_t)ctx->n;
+    double sum = 0;
+    st = eslam_gpu_weights_sum(ctx, &sum);                                            // getWeightAvg() :162
+    if (st != ESLAM_OK) return st;
+    const double weight = (sum / (double)ctx->n) * avg_factor * relevance_factor;
+    // the particles by ascending weight (as float, ties by index: std::sort of pair<float, index> :147-153)
+    const unsigned n = (unsigned)ctx->n;
+    struct Temps { float *k = nullptr, *k2 = nullptr; unsigned *i = nullptr, *i2 = nullptr; void* tmp = nullptr;
+                   ~Temps() { cudaFree(k); cudaFree(k2); cudaFree(i); cudaFree(i2); cudaFree(tmp); } } T;
+    CK(dalloc(&T.k, (size_t)n)); CK(dalloc(&T.k2, (size_t)n)); CK(dalloc(&T.i, (size_t)n)); CK(dalloc(&T.i2, (size_t)n));
+    k_weight_keys<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->st, ctx->sc, n, T.k, T.i);
+    LAUNCHED();
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, T.k, T.k2, T.i, T.i2, (int)n, 0, 32, ctx->stream);
+    CK(cudaMalloc(&T.tmp, tb));
+    cub::DeviceRadixSort::SortPairs(T.tmp, tb, T.k, T.k2, T.i, T.i2, (int)n, 0, 32, ctx->stream);
+    const ModelParams mp = model_params(ctx);
+    k_hash_replace<<<(unsigned)((replace_count + 255) / 256), 256, 0, ctx->stream>>>(ctx->st, ctx->sc, T.i2, (unsigned)replace_count, mp.k0, mp.k1, hstep,
+                                                                                     ctx->hash_poses, ctx->hash_by_bucket, ctx->hash_offs[b], in_bucket,
+                                                                                     ctx->map, ctx->hash_steps, weight);
+    LAUNCHED();
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (replaced) *replaced = replace_count;
     return ESLAM_OK;
 }
 

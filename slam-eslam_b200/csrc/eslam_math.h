@@ -112,7 +112,7 @@ ESLAM_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c
 }
 
 // RNG streams (counter word 3).  Counter layout: (index, step, slot, stream); key = seed.
-enum { STREAM_INIT = 0, STREAM_PROJECT = 1, STREAM_RESAMPLE = 2, STREAM_TERRAIN = 3 };
+enum { STREAM_INIT = 0, STREAM_PROJECT = 1, STREAM_RESAMPLE = 2, STREAM_TERRAIN = 3, STREAM_HASH = 4 };
 
 // [0,1): 53 bits, like boost::uniform_real<>(0,1) over a full-range engine
 ESLAM_HD double u01(uint32_t hi, uint32_t lo) {
@@ -393,6 +393,46 @@ ESLAM_HD bool cell_index_exact(double x, double offset, double scale, int n, int
     double q = floor((x - offset) / scale);
     if (!(q >= 0.0 && q < (double)n)) return false;
     idx = (int)q; return true;
+}
+
+// ---------------------------------------------------------------- SurfaceHash (src/SurfaceHash.hpp)
+// SurfaceParam::fromPoints (:60-110): least-squares plane z = sx x + sy y + c through n >= 3 points; the normal equations
+// [[xx xy x] [xy yy y] [x y n]] r = (xz yz z) solved by LDL^T (the reference calls Eigen's pivoting LDLT: the same solution up
+// to rounding -- Eigen is not vendored).  Returns false for a singular system (collinear points).
+ESLAM_HD bool surface_slopes(const double* px, const double* py, const double* pz, int n, double& slope_x, double& slope_y) {
+    double x = 0, y = 0, z = 0, xx = 0, yy = 0, xy = 0, xz = 0, yz = 0;
+    for (int i = 0; i < n; ++i) {
+        x += px[i]; y += py[i]; z += pz[i];
+        xx += px[i] * px[i]; yy += py[i] * py[i]; xy += px[i] * py[i]; xz += px[i] * pz[i]; yz += py[i] * pz[i];
+    }
+    const double d0 = xx;
+    if (!(d0 > 0.0)) return false;
+    const double l10 = xy / d0, l20 = x / d0;
+    const double d1 = yy - l10 * xy;
+    if (!(d1 > 0.0)) return false;
+    const double l21 = (y - l20 * xy) / d1;
+    const double d2 = ((double)n - l20 * x) - l21 * l21 * d1;
+    if (!(d2 > 0.0)) return false;
+    // forward: L w = b;  diagonal;  backward: L^T r = w / d
+    const double w0 = xz, w1 = yz - l10 * w0, w2 = (z - l20 * w0) - l21 * w1;
+    const double r2 = w2 / d2;
+    const double r1 = w1 / d1 - l21 * r2;
+    const double r0 = (w0 / d0 - l10 * r1) - l20 * r2;
+    slope_x = r0; slope_y = r1;
+    return true;
+}
+// Buckets::bucketIndex (:26-30) for the slope hash: count buckets over [-1, 1]; NaN -> bucket 0
+ESLAM_HD int slope_bucket(double value, int count) {
+    const double v = (value - (-1.0)) / (1.0 - (-1.0)) * (double)count;
+    if (!(v > 0.0)) return 0;
+    if (v >= (double)count) return count - 1;
+    return (int)v;
+}
+// the 4-point footprint of SurfaceHash::create (:162-168): base 0.5 m
+ESLAM_HD void hash_footprint(int i, double& x, double& y) {
+    const double b = 0.5;
+    x = (i & 1) ? -b / 2.0 : b / 2.0;
+    y = (i & 2) ? -b : 0.0;
 }
 
 }  // namespace eslam_math

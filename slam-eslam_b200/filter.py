@@ -168,6 +168,35 @@ class FilterBase:
         self._check(self._fn("pose_moments")(self._ctx, C.byref(g)))
         return dict(weight=g.weight, mean=np.array(list(g.mean)), cov=np.array(list(g.cov)).reshape(2, 2))
 
+    # -- SurfaceHash (src/SurfaceHash.hpp, src/PoseEstimator.cpp:75-86,130-182) -------------------
+    def hashCreate(self, slope_bins=20, angular_steps=16):
+        """SurfaceHash::create on the attached grid (SurfaceHashConfig defaults: 20 slope bins, 16 headings)."""
+        self._check(self._fn("hash_create")(self._ctx, int(slope_bins), int(angular_steps)))
+        self._hash_bins = int(slope_bins)
+
+    def hashInfo(self):
+        n = C.c_uint64()
+        counts = np.zeros(self._hash_bins ** 2, dtype=np.uint32)
+        self._check(self._fn("hash_info")(self._ctx, C.byref(n), counts.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return int(n.value), counts
+
+    def hashGet(self, first, count):
+        out = {k: np.zeros(count) for k in ("x", "y", "theta", "z")}
+        out["bucket"] = np.zeros(count, dtype=np.int32)
+        self._check(self._fn("hash_get")(self._ctx, int(first), int(count), _dp(out["x"]), _dp(out["y"]), _dp(out["theta"]), _dp(out["z"]),
+                                         out["bucket"].ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def initFromHash(self, n):
+        """PoseEstimator::init(numParticles, hash) (src/PoseEstimator.cpp:75-86)."""
+        self._check(self._fn("init_from_hash")(self._ctx, int(n)))
+
+    def sampleFromHash(self, contacts, replace_percentage=0.05, avg_factor=0.1):
+        """PoseEstimator::sampleFromHash (src/PoseEstimator.cpp:130-182); returns the number of replaced particles."""
+        r = C.c_uint64()
+        self._check(self._fn("sample_from_hash")(self._ctx, float(replace_percentage), float(avg_factor), contacts, len(contacts), C.byref(r)))
+        return int(r.value)
+
     def getPatches(self, patch_size):
         n = self.size()
         cells = np.empty((n, patch_size, patch_size, 2), dtype=np.float32)

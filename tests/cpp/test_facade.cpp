@@ -210,6 +210,31 @@ static void test_per_particle_maps() {                     // init(..., useShare
     CHECK(std::fabs(f.getParticles()[3].weight - 1.0 / 1000) < 1e-15);   // :140
 }
 
+static void test_surface_hash() {                          // init(env, pose, true, hashConfig with useHash): src/EmbodiedSlamFilter.cpp:93-98,109-114
+    eslam::Configuration conf; conf.particleCount = 3000; conf.minEffective = 3001;
+    SurfaceHashConfig hc; hc.useHash = true; hc.period = 3;
+    EmbodiedSlamFilter f(odometry::Configuration(), conf);
+    DenseGrid map = rollingTerrain(200);
+    f.init(&map, base::Pose(base::Vector3d(0, 0, 0.19), base::Quaterniond::Identity()), true, hc);
+    CHECK(f.getParticles().size() == 3000);
+    double minx = 1e9, maxx = -1e9;
+    for (size_t i = 0; i < 3000; i++) { minx = std::fmin(minx, f.getParticles()[i].position.x()); maxx = std::fmax(maxx, f.getParticles()[i].position.x()); }
+    CHECK(maxx - minx > 5.0);                                 // seeded all over the 10 m map, not around the start pose
+    CHECK(f.getParticles()[0].zSigma == 0.0 && f.getParticles()[0].weight == 0.0);
+    std::vector<terrain_estimator::TerrainClassification> ltc;
+    BodyContactState bs = wheels();
+    for (int step = 0; step < 9; step++) {
+        base::Affine3d body2odo = base::Affine3d::fromTranslationYaw(base::Vector3d(0.03 * step, 0, 0.19), 0.0);
+        f.update(body2odo, bs, ltc);                          // project() re-seeds from the hash every 3rd call (:239-241)
+        CHECK(f.getParticles().size() == 3000);
+    }
+    SurfaceParam sp; std::vector<base::Vector3d> pts;        // test/UnitTest.cpp:121-143 exercises fromPoints
+    pts.push_back(base::Vector3d(0.25, 0, 0.05)); pts.push_back(base::Vector3d(-0.25, 0, -0.05));
+    pts.push_back(base::Vector3d(0.25, -0.5, 0.05)); pts.push_back(base::Vector3d(-0.25, -0.5, -0.05));
+    sp.fromPoints(pts);
+    CHECK_CLOSE(sp.slope_x, 0.2, 1e-9); CHECK_SMALL(sp.slope_y, 1e-12);
+}
+
 static void test_z_position_estimate() {                   // ContactModel::updateZPositionEstimate as test/testMap.cpp:279-289 drives it
     const double pts[4][3] = {{-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 1, 0}};
     const float contact[4] = {0.5f, 0.5f, 0.5f, 0.5f}; const int group[4] = {-1, -1, -1, -1};
@@ -228,6 +253,7 @@ static void test_z_position_estimate() {                   // ContactModel::upda
 int main() {
     test_updatePose_nogroup();
     test_per_particle_maps();
+    test_surface_hash();
     test_z_position_estimate();
     test_lowest_points();
     test_mapAbsence_group();

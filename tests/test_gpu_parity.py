@@ -704,3 +704,32 @@ def test_resample_with_a_sample_count_of_its_own(gpu, oracle, multinomial, sampl
         assert np.all(out[0][1]["weight"] == 1.0 / n)
     else:
         assert np.all(np.diff(out[0][0].astype(np.int64)) >= 0)
+
+
+# ---------------------------------------------------------------------------------- SurfaceHash, the relocaliser
+def test_surface_hash_bit_identical_to_oracle(gpu, oracle):
+    """SurfaceHash::create on the device (src/SurfaceHash.hpp:155-231), PoseEstimator::init(n, hash) (src/PoseEstimator.cpp:75-86)
+    and sampleFromHash (:130-182): the table (every candidate pose and bucket, the per-bucket counts), the seeded particle set
+    and the re-seeded one identical to the oracle's definition."""
+    n = 4000
+    g, o, contacts, step = pair(gpu, oracle, "C1", n=n, min_effective=n + 1)
+    for f in (g, o):
+        f.hashCreate(20, 16)
+    (na, ca), (nb, cb) = g.hashInfo(), o.hashInfo()
+    assert na == nb and na > 16 * 150 * 150 and np.array_equal(ca, cb)
+    ha, hb = g.hashGet(0, na), o.hashGet(0, nb)
+    for k in ha:
+        assert np.array_equal(ha[k], hb[k]), k
+    for f in (g, o):
+        f.initFromHash(n)
+    assert_particles_equal(g.getParticles(), o.getParticles())
+    total = 0
+    for it in range(4):
+        ra, rb = g.stepFused(step, contacts), (o.project(step), o.update(contacts))[1]
+        assert ra.as_dict() == rb.as_dict(), it
+        assert_particles_equal(g.getParticles(), o.getParticles())
+        ka, kb = g.sampleFromHash(contacts), o.sampleFromHash(contacts)
+        assert ka == kb
+        total += ka
+        assert_particles_equal(g.getParticles(), o.getParticles())
+    assert total > 0
