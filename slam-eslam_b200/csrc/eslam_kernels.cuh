@@ -283,16 +283,19 @@ __device__ __forceinline__ double tree_small(double* v, int m) {
     while (m > 1) { const int h = (m + 1) >> 1; for (int j = 0; j < h; ++j) v[j] = (2 * j + 1 < m) ? v[2 * j] + v[2 * j + 1] : v[2 * j]; m = h; }
     return v[0];
 }
-// "am I the last CTA of this grid to get here": everything the other CTAs wrote before their call is visible to the last one
+// "am I the last CTA of this grid to get here": what THREAD 0 of the other CTAs wrote before their call (their tile's partial)
+// is visible to the last CTA.  Thread 0 takes the ticket with a release/acquire atomic at gpu scope -- no block-wide fence: the
+// last CTA only reads what the thread-0s published.
 __device__ __forceinline__ bool cta_is_last(unsigned* ticket) {
     __shared__ int s_last;
-    __threadfence();
+    if (threadIdx.x == 0) {
+        unsigned t;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(t) : "l"(ticket) : "memory");
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
+        if (s_last) *ticket = 0;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) { const unsigned t = atomicAdd(ticket, 1u); s_last = (t == gridDim.x - 1) ? 1 : 0; if (s_last) *ticket = 0; }
-    __syncthreads();
-    const bool last = s_last != 0;
-    if (last) __threadfence();
-    return last;
+    return s_last != 0;
 }
 // rendezvous of all ranks on their streams (eslam_gpu_run_steps: all ranks start the timed region together)
 __global__ void k_barrier(DevScalars* sc, const __grid_constant__ Xchg X) {
@@ -2114,7 +2117,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(StateBufs st, DevScalars* sc,
         return;
     }
     for (unsigned k = tid; k < (unsigned)n_bnd; k += blockDim.x) A.sb_out[k] = cs.bw[k];
-    __threadfence_system();
+    if (X.world > 1) __threadfence_system();                             // the tile starts pushed to the peers land before this kernel ends
 }
 
 // exact running sum of every element: cdf[i] == the reference's sum_w after adding xi_k[i].weight
