@@ -2314,7 +2314,8 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
 // their part of the tile-start table and waits only for those of them that are other GPUs ("my running sums are final", X_D,
 // signalled by CTA 0 of this same kernel on every rank) -- with balanced weights only the CTAs at the ends of a shard wait.
 #define RS_STAGE_BYTES (8 * TILE * 8 + 2 * TILE)          // cdf + 7 doubles + 2 bytes per particle of one source tile
-#define RS_STREAM_SMEM (2 * RS_STAGE_BYTES + 64)
+#define RS_STAGES 3                                       // ring depth: two source tiles in flight while one is searched
+#define RS_STREAM_SMEM (RS_STAGES * RS_STAGE_BYTES + 64)
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -2343,7 +2344,7 @@ __global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevSc
     const unsigned xd_epoch = sc->resample_step + 1u;                          // number of this resampling: equal on every rank
     if (blockIdx.x == 0) x_signal(X, X_D, xd_epoch);                           // this rank's k_cdf has finished (stream order)
     const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(rs_raw);
-    const uint32_t mbar0 = smem0 + 2 * RS_STAGE_BYTES;                        // two mbarriers behind the stages
+    const uint32_t mbar0 = smem0 + RS_STAGES * RS_STAGE_BYTES;                // the stages' mbarriers behind them
     const unsigned long long per = (((n + gridDim.x - 1) / gridDim.x) + 31ull) & ~31ull;
     const unsigned long long K0 = min(n, (unsigned long long)blockIdx.x * per), K1 = min(n, K0 + per);
     if (K0 < K1) {
@@ -2378,7 +2379,7 @@ __global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevSc
         }
         c_lo += t_first; c_hi += t_first;                                      // the tiles in front of the slice all start below thr_lo
         const unsigned tA = c_lo == 0 ? 0u : c_lo - 1, tB = c_hi == 0 ? 0u : c_hi - 1;
-        if (tid == 0) { mbar_init(mbar0, 1); mbar_init(mbar0 + 8, 1); }
+        if (tid == 0) { for (int g = 0; g < RS_STAGES; ++g) mbar_init(mbar0 + 8u * g, 1); }
         __syncthreads();
         // exact running sum before tile t.  The first tile of a rank: from the walk's rank starts (this rank's own memory) --
         // the table entry is pushed by that rank, which this CTA has not necessarily waited for (t may be one past its slice)
@@ -2414,19 +2415,25 @@ __global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevSc
 #pragma unroll
             for (int f = 0; f < 2; ++f) bulk_g2s(S + 8u * TILE * 8u + (uint32_t)f * TILE, peers.b[q][cur][f] + e0, c1, mb);
         };
-        unsigned t = tA; unsigned long long klo = 0, khi = 0;
-        while (t <= tB) { range(t, klo, khi); if (khi > klo) break; ++t; }
-        if (t <= tB && tid == 0) issue(t, 0);
+        // the next source tile after `from` that has candidate strata (tB + 1: none)
+        auto next_tile = [&](unsigned from, unsigned long long& lo, unsigned long long& hi) -> unsigned {
+            unsigned t = from; lo = hi = 0;
+            while (t <= tB) { range(t, lo, hi); if (hi > lo) break; ++t; }
+            return t;
+        };
+        unsigned long long klo = 0, khi = 0, nlo = 0, nhi = 0, mlo = 0, mhi = 0;
+        unsigned t = next_tile(tA, klo, khi);
+        unsigned tn = t <= tB ? next_tile(t + 1, nlo, nhi) : tB + 1;
+        if (tid == 0) { if (t <= tB) issue(t, 0); if (tn <= tB) issue(tn, 1); }
         int it = 0;
         while (t <= tB) {
-            unsigned tn = t + 1; unsigned long long nlo = 0, nhi = 0;
-            while (tn <= tB) { range(tn, nlo, nhi); if (nhi > nlo) break; ++tn; }
-            const int stage = it & 1;
-            if (tn <= tB && tid == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the other stage was read (generic proxy) one iteration ago
-                issue(tn, stage ^ 1);
+            const unsigned tm = tn <= tB ? next_tile(tn + 1, mlo, mhi) : tB + 1;   // two tiles ahead
+            const int stage = it % RS_STAGES;
+            if (tm <= tB && tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // that stage was read (generic proxy) one iteration ago
+                issue(tm, (it + 2) % RS_STAGES);
             }
-            mbar_wait(mbar0 + 8u * (uint32_t)stage, (uint32_t)(it >> 1) & 1u);
+            mbar_wait(mbar0 + 8u * (uint32_t)stage, (uint32_t)(it / RS_STAGES) & 1u);
             {
                 const unsigned char* S = rs_raw + (size_t)stage * RS_STAGE_BYTES;
                 const double* s_cdf = reinterpret_cast<const double*>(S);
@@ -2454,7 +2461,7 @@ __global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevSc
                 }
             }
             __syncthreads();                                                   // everyone is done with this stage
-            t = tn; klo = nlo; khi = nhi; ++it;
+            t = tn; klo = nlo; khi = nhi; tn = tm; nlo = mlo; nhi = mhi; ++it;
         }
     }
     // xi_k.swap(xi_kp) :107 by the last CTA (every CTA has read sc->cur by then)
