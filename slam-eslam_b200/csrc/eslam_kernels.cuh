@@ -1708,6 +1708,7 @@ struct NormScanArgs {
     double *scratch_a, *scratch_b;
     unsigned n_tiles, tile_ofs;
     int normalise; double eps;
+    long long* el_d0; unsigned short* el_code;   // per element: what k_cdf needs to materialise its running sum (see k_cdf)
 };
 __global__ void __launch_bounds__(SCAN_THREADS, 4) k_norm_scan(StateBufs st, DevScalars* sc, unsigned long long n, const NormScanArgs A,
                                                             const ShardPlan sp, const __grid_constant__ Xchg X) {
@@ -1797,6 +1798,32 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) k_norm_scan(StateBufs st, Dev
                     if (e.f.pad) D->overflow = 1;
                 }
             }
+        }
+    }
+    // Per element, what k_cdf needs: the running sum after element i is  bits(base) + d0 (+ delta if base's mantissa is odd),
+    // base = the exact sum at the tile start (ref 0) or at the tile's boundary element `ref - 1` -- the composed rounding
+    // function since that point, whose two branches differ by -1, 0 or +1 (two walks that start one ulp apart stay 0, 1 or 2
+    // apart).  10 bytes per element instead of a second tile scan.
+    {
+        long long d0v[EPT]; unsigned short cv[EPT];
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            long long d0 = 0; int delta = 0; unsigned ref;
+            if (ts.cls[j].kind == 2) ref = (unsigned)ts.bnd_before[j] + 1u;
+            else {
+                const SegE& e = ts.inc[j];
+                if (e.f.b != BIN_NONE) { d0 = e.f.d0; delta = (int)(e.f.d1 - e.f.d0); }
+                ref = e.head < 0 ? 0u : (unsigned)slot_of[e.head] + 1u;
+            }
+            d0v[j] = d0; cv[j] = (unsigned short)(ref | ((unsigned)(delta + 1) << 12));
+        }
+        if (i0 + EPT <= n) {
+            *reinterpret_cast<longlong2*>(A.el_d0 + i0) = make_longlong2(d0v[0], d0v[1]);
+            *reinterpret_cast<longlong2*>(A.el_d0 + i0 + 2) = make_longlong2(d0v[2], d0v[3]);
+            *reinterpret_cast<ushort4*>(A.el_code + i0) = make_ushort4(cv[0], cv[1], cv[2], cv[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) if (i0 + j < n) { A.el_d0[i0 + j] = d0v[j]; A.el_code[i0 + j] = cv[j]; }
         }
     }
 }
@@ -2120,41 +2147,39 @@ __global__ void __launch_bounds__(1024, 1) k_chain(StateBufs st, DevScalars* sc,
     if (X.world > 1) __threadfence_system();                             // the tile starts pushed to the peers land before this kernel ends
 }
 
-// exact running sum of every element: cdf[i] == the reference's sum_w after adding xi_k[i].weight
+// exact running sum of every element: cdf[i] == the reference's sum_w after adding xi_k[i].weight.  A streaming pass: the sum
+// at the element's base (tile start, or one of the tile's boundary elements: k_chain) plus the integer offset k_norm_scan left.
 struct CdfArgs {
-    const double* tile_prefix; const int* tile_bofs; const double* sb; double* cdf;
-    double eps; unsigned tile_ofs;
+    const int* tile_bofs; const double* sb; double* cdf;
+    const long long* el_d0; const unsigned short* el_code;
+    unsigned tile_ofs;
 };
-__global__ void __launch_bounds__(SCAN_THREADS) k_cdf(StateBufs st, DevScalars* sc, unsigned long long n, const CdfArgs A, const ShardPlan sp,
-                                                      const __grid_constant__ Xchg X) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_cdf(DevScalars* sc, unsigned long long n, const CdfArgs A, const __grid_constant__ Xchg X) {
     pdl_start();
-    __shared__ TileScanSmem sm;
-    __shared__ int slot_of[TILE];
-    if (!sc->do_resample) return;                                    // the same decision on every rank
-    if (!sc->cdf_seq) {
-        const int cur = sc->cur;
-        const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
-        double w[EPT];
-        load4(st.f[cur][F_W], i0, n, w);
-        const unsigned gt = A.tile_ofs + blockIdx.x;
-        TileScan ts;
-        tile_scan(w, A.tile_prefix[gt], A.eps, sm, ts);
+    if (!sc->do_resample || sc->cdf_seq) return;                     // the same decision on every rank; sequential fallback: k_chain wrote it
+    const unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * EPT;
+    if (i0 >= n) return;
+    const int ofs = A.tile_bofs[blockIdx.x];
+    const double s_in = reinterpret_cast<const double*>(X.buf[X.me] + XOFF_TSIN)[A.tile_ofs + blockIdx.x];
+    long long d0[EPT]; unsigned short code[EPT];
+    const bool full = i0 + EPT <= n;
+    if (full) {
+        const longlong2 a = *reinterpret_cast<const longlong2*>(A.el_d0 + i0), b = *reinterpret_cast<const longlong2*>(A.el_d0 + i0 + 2);
+        const ushort4 c = *reinterpret_cast<const ushort4*>(A.el_code + i0);
+        d0[0] = a.x; d0[1] = a.y; d0[2] = b.x; d0[3] = b.y; code[0] = c.x; code[1] = c.y; code[2] = c.z; code[3] = c.w;
+    } else {
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) slot_of[threadIdx.x * EPT + j] = ts.bnd_before[j];
-        __syncthreads();
-        int bad = 0;
-        double S[EPT];
-        const int ofs = A.tile_bofs[blockIdx.x];
-        const double s_in = reinterpret_cast<const double*>(X.buf[X.me] + XOFF_TSIN)[gt];
-#pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-            if (ts.cls[j].kind == 2) S[j] = A.sb[ofs + ts.bnd_before[j]];
-            else if (ts.inc[j].head < 0) S[j] = segf_apply(s_in, ts.inc[j].f, bad);
-            else S[j] = segf_apply(A.sb[ofs + slot_of[ts.inc[j].head]], ts.inc[j].f, bad);
-        }
-        if (bad) atomicOr(&sc->error_flags, ERR_INTERNAL_BIT);      // cannot happen: k_chain applied the same functions to the same sums
-        store4(A.cdf, i0, n, S);
+        for (int j = 0; j < EPT; ++j) { const bool in = i0 + j < n; d0[j] = in ? A.el_d0[i0 + j] : 0; code[j] = in ? A.el_code[i0 + j] : (unsigned short)(1u << 12); }
     }
+    double S[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        const unsigned ref = code[j] & 0xFFFu; const long long delta = (long long)((code[j] >> 12) & 3u) - 1;
+        const double base = ref ? A.sb[ofs + (int)ref - 1] : s_in;
+        const uint64_t u = em::d2u(base);
+        S[j] = em::u2d(u + (uint64_t)(d0[j] + ((u & 1) ? delta : 0)));
+    }
+    store4(A.cdf, i0, n, S);
 }
 
 // ------------------------------------------------------------------------------------------------ resample

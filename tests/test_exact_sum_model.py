@@ -142,3 +142,51 @@ def test_composition_is_associative():
                 S = S2
             if ok and l[0] != BIN_NONE:
                 assert apply(S0, l)[0] == S
+
+
+def test_branches_of_a_composed_function_differ_by_at_most_one():
+    """k_norm_scan stores, per element, d0 of the composed rounding function and d1 - d0 in two bits (k_cdf): two walks that
+    start one ulp apart are 0, 1 or 2 ulps apart ever after, so d1 - d0 is -1, 0 or +1 for ANY run of interior elements."""
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        b = int(rng.integers(-30, 0))
+        run = (BIN_NONE, 0, 0)
+        for _ in range(int(rng.integers(1, 60))):
+            # single-element functions as classify() makes them: non-tie (d0 == d1) or tie (they differ by one, by the parity of fl)
+            fl = int(rng.integers(0, 1 << 30))
+            if rng.random() < 0.5:
+                f = (b, fl, fl)
+            else:
+                f = (b, fl + (1 if fl & 1 else 0), fl + (0 if fl & 1 else 1))
+            run, bad = compose(run, f)
+            assert not bad
+            assert run[2] - run[1] in (-1, 0, 1), run
+
+
+@pytest.mark.parametrize("n", [5000])
+def test_offsets_from_a_base_reproduce_the_sequential_sum(n):
+    """What k_cdf does: running sum after element i = bits(base) + d0 (+ d1 - d0 if the base's mantissa is odd), base = the sum at
+    the last boundary element (or at the start)."""
+    rng = np.random.default_rng(n)
+    eps = max(8 * n * 2.0 ** -53, 2.0 ** -40)
+    for name, w in vectors(n, rng):
+        A = approximate_prefix(w)
+        seq = np.cumsum(w)
+        base, run = 0.0, (BIN_NONE, 0, 0)
+        for i in range(n):
+            kind, b, d0, d1 = classify(float(w[i]), float(A[i - 1]) if i else 0.0, float(A[i]), eps)
+            if kind == 2:
+                base = (seq[i - 1] if i else 0.0) + float(w[i]); run = (BIN_NONE, 0, 0)
+                got = base
+            else:
+                if kind == 1:
+                    run, bad = compose(run, (b, d0, d1))
+                    assert not bad
+                if run[0] == BIN_NONE:
+                    got = base
+                else:
+                    u = d2u(base)
+                    delta = run[2] - run[1]
+                    assert delta in (-1, 0, 1)
+                    got = u2d(u + run[1] + (delta if (u & 1) else 0))
+            assert got == seq[i], (name, i)
