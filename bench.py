@@ -44,11 +44,14 @@ METRIC = "particle-updates/sec"
 UNIT = "particle-updates/s"
 
 
-def algorithmic_bytes(n, c, lean):
-    """B_step(N, C) = N (8 C + 234).  The dominant kernel's share: k_weight_lean reads the
-    C map cells (8 C), the particle's x, y, theta, z, zSigma, weight (48) and writes z, zSigma, weight, mprob, floating,
-    n_found (34): N (8 C + 82); the generic fused project+weight kernel moves §8(d)'s N (8 C + 97)."""
-    return n * (8 * c + 234), n * (8 * c + (82 if lean else 97))
+def algorithmic_bytes(n, c, lean, patch=0):
+    """B_step(N, C) = N (8 C + 234); with per-particle P x P map patches (config C4) + 4 * 16 (read-modify-write
+    of at most 4 patch cells in the update) + 2 * P^2 * 8 (the patch read and written when the particle is resampled).
+    The dominant kernel's share: k_weight_lean reads the C map cells (8 C), the particle's x, y, theta, z, zSigma,
+    weight (48) and writes z, zSigma, weight, mprob, floating, n_found (34): N (8 C + 82); the generic fused project+weight
+    kernel moves §8(d)'s N (8 C + 97), + 4 * 16 with patches."""
+    per_patch = (4 * 16 + 2 * patch * patch * 8) if patch else 0
+    return n * (8 * c + 234 + per_patch), n * (8 * c + (82 if lean else 97) + (4 * 16 if patch else 0))
 
 
 def measured_peak():
@@ -316,7 +319,7 @@ def main():
     updates = n_global * c
     value = updates * args.steps / (ms * 1e-3)
     lean = paths["lean"] > 0
-    step_bytes, top_bytes = algorithmic_bytes(n_local, c, lean)
+    step_bytes, top_bytes = algorithmic_bytes(n_local, c, lean, patch)
     peak, peak_kind = measured_peak()
     top_avg_s = top_ms * 1e-3 / args.steps
     achieved = top_bytes / top_avg_s / 1e9
@@ -345,6 +348,8 @@ def main():
                      "achieved_kind": "algorithmic bytes per launch / measured launch time (CUDA events in this run)",
                      "limiter": "fp64 instruction issue" if lean else "fp64 instruction issue + L2 gathers",
                      "kernel_ms": top_avg_s * 1e3, "kernel_share_of_step": top_ms / ms,
+                     "kernel_ms_sampling": "CUDA events around the kernel on every 4th timed step (every step below 16 steps); "
+                                           "launch-bound sizes run as one CUDA graph: the events of its last replay",
                      "algorithmic_bytes_per_launch": top_bytes,
                      "note": "reported against the HBM roofline as the metric demands; the kernel itself is limited by instruction "
                              "issue (fp64 at half rate), not by HBM: the map is served from TMA-staged shared-memory tiles, so "

@@ -4,6 +4,7 @@
 #include "eslam_kernels.cuh"
 #include "eslam_hash.cuh"
 #include "eslam_nccl.h"
+#include <nvtx3/nvToolsExt.h>   // header-only; a range costs a few ns when no tool is attached
 
 #include <math.h>
 #include <stdio.h>
@@ -20,6 +21,9 @@ static const em::dbl2 H_TABLE_HOST[ESLAM_H_TABLE_ENTRIES] = {
 };
 
 static NcclApi g_nccl;
+
+// NVTX ranges around the entry points of the step path (what nsys / ncu group the kernels under)
+struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
 
 // Development switches, read ONCE when a context is created (tools/README.md); never consulted on the step path.
 struct EnvSwitches {
@@ -545,7 +549,11 @@ int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int he
     int side = (int)floor(sqrt((double)(avail / sizeof(float2))));
     if (ctx->env.tile_override > 0) side = ctx->env.tile_override;
     m.tile_w = width < side ? width : side;
+    // a grid at least 256 cells wide: tiles of 256 columns (the row pitch the lean kernel turns into a byte permute, and the TMA
+    // box limit), as many rows as fit (about 100: below the 128 the permute needs)
+    if (width >= 256 && ctx->env.tile_override <= 0) m.tile_w = 256;
     m.tile_h = (int)((avail / sizeof(float2)) / (size_t)m.tile_w);
+    if (m.tile_w == 256 && m.tile_h > 127) m.tile_h = 127;
     if (ctx->env.tile_override > 0) m.tile_h = ctx->env.tile_override;
     if (m.tile_h > height) m.tile_h = height;
     if (m.tile_w > 256) m.tile_w = 256;                           // TMA box limit per dimension
@@ -585,8 +593,9 @@ int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells, int width, int he
     CK(cudaFuncSetAttribute(k_project_weight<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_project_weight<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaFuncSetAttribute(k_project_weight<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_weight_lean<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    CK(cudaFuncSetAttribute(k_weight_lean<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_weight_lean<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_weight_lean<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    CK(cudaFuncSetAttribute(k_weight_lean<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->has_map = true;
     return ESLAM_OK;
@@ -729,6 +738,8 @@ static bool fill_fast_params(eslam_gpu_ctx* ctx, FastParams* F, const WeightPara
     if (fc.bsx < 8 || fc.bsy < 8) return false;
     fc.nbx = (P.map.W + fc.bsx - 1) / fc.bsx; fc.nby = (P.map.H + fc.bsy - 1) / fc.bsy;
     fc.nb = fc.nbx * fc.nby;
+    auto magic = [](uint64_t two_k, int d) { return (uint32_t)((two_k + (uint64_t)d - 1) / (uint64_t)d); };
+    fc.inv_bsx = magic(1ull << 32, fc.bsx); fc.inv_bsy = magic(1ull << 32, fc.bsy); fc.inv_nbx = magic(1ull << 31, fc.nbx);
     if (fc.nb > MAX_BINS || P.map.W > 16000 || P.map.H > 16000) return false;
     // 3-sigma gate d^2 < 9 zvar  <=>  |t| < 3/corr with t = d / (sigma corr); decided on the high word of |t|
     const double T = 3.0 * P.mp.inv_corr;
@@ -830,10 +841,13 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
                       step_or_null ? 1 : 0));
         LAUNCHED();
         if (ev0) CK(cudaEventRecordWithFlags(ev0, ctx->stream, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));   // the events bracket the dominant kernel alone
+        const bool p256 = F.c.map.tile_w == 256 && F.c.map.tile_h < 128;   // rows 256 cells apart: cell offsets by byte permute
         if (ctx->env.lean_threads == 512)
-            CK(launch_pdl(ctx, k_weight_lean<512>, (unsigned)ctx->sm_count, 512, smem, F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin));
+            CK(launch_pdl(ctx, (k_weight_lean<512, false>), (unsigned)ctx->sm_count, 512, smem, F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin));
+        else if (p256)
+            CK(launch_pdl(ctx, (k_weight_lean<1024, true>), (unsigned)ctx->sm_count, 1024, smem, F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin));
         else
-            CK(launch_pdl(ctx, k_weight_lean<1024>, (unsigned)ctx->sm_count, 1024, smem, F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin));
+            CK(launch_pdl(ctx, (k_weight_lean<1024, false>), (unsigned)ctx->sm_count, 1024, smem, F, ctx->bin_list, ctx->bin_count, ctx->bin_offs, ctx->bin_next, ctx->cta_bin));
         LAUNCHED();
         if (ev1) CK(cudaEventRecordWithFlags(ev1, ctx->stream, ctx->capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
         ctx->hint_n = 0;
@@ -908,6 +922,7 @@ static int launch_centroid(eslam_gpu_ctx* ctx) {
 extern "C" {
 
 int eslam_gpu_project(eslam_gpu_ctx* ctx, const eslam_gpu_step* step) {
+    NvtxRange nvtx_("eslam project");
     int st = check_ready(ctx, false);
     if (st != ESLAM_OK) return st;
     if (!step) return ESLAM_ERR_INVALID;
@@ -921,6 +936,7 @@ int eslam_gpu_project(eslam_gpu_ctx* ctx, const eslam_gpu_step* step) {
 }
 
 int eslam_gpu_update(eslam_gpu_ctx* ctx, const eslam_gpu_contact* pts, int n_pts, eslam_gpu_update_result* result) {
+    NvtxRange nvtx_("eslam update");
     int st = check_ready(ctx, true);
     if (st != ESLAM_OK) return st;
     ContactSet cs;
@@ -981,7 +997,7 @@ static int graph_step(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const Cont
             cudaKernelNodeParams kp; CK(cudaGraphKernelNodeGetParams(nodes[i], &kp));
             if (kp.func == (void*)k_project_bin<true>) G.n_project = nodes[i];
             else if (kp.func == (void*)k_bin_scatter) G.n_scatter = nodes[i];
-            else if (kp.func == (void*)k_weight_lean<1024> || kp.func == (void*)k_weight_lean<512>) G.n_lean = nodes[i];
+            else if (kp.func == (void*)k_weight_lean<1024, true> || kp.func == (void*)k_weight_lean<1024, false> || kp.func == (void*)k_weight_lean<512, false>) G.n_lean = nodes[i];
         }
         if (!G.n_project || !G.n_scatter || !G.n_lean) { graph_drop(ctx); G.failed = true; return ESLAM_OK; }
         G.valid = true; G.n = ctx->n; G.nb = F.fc.nb; G.lean_threads = ctx->env.lean_threads; G.step = *step; G.cs = *cs;
@@ -1012,6 +1028,7 @@ extern "C" {
 
 int eslam_gpu_step_fused(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const eslam_gpu_contact* pts, int n_pts,
                          eslam_gpu_update_result* result) {
+    NvtxRange nvtx_("eslam step (project + update)");
     int st = check_ready(ctx, true);
     if (st != ESLAM_OK) return st;
     if (!step) return ESLAM_ERR_INVALID;
@@ -1027,6 +1044,7 @@ int eslam_gpu_step_fused(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const e
 
 int eslam_gpu_run_steps(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const eslam_gpu_contact* pts, int n_pts, int steps,
                         float* elapsed_ms, float* top_kernel_ms, eslam_gpu_update_result* last_result) {
+    NvtxRange nvtx_("eslam run_steps");
     int st = check_ready(ctx, true);
     if (st != ESLAM_OK) return st;
     if (!step || steps <= 0) return ESLAM_ERR_INVALID;
@@ -1124,6 +1142,7 @@ int eslam_gpu_normalize_weights(eslam_gpu_ctx* ctx, double* ess) {
 }
 
 int eslam_gpu_resample(eslam_gpu_ctx* ctx) {
+    NvtxRange nvtx_("eslam resample");
     int st = check_ready(ctx, false);
     if (st != ESLAM_OK) return st;
     return launch_tail(ctx, false, 0, 0, 1);
@@ -1270,6 +1289,7 @@ int eslam_gpu_path_counters(eslam_gpu_ctx* ctx, uint64_t out[2]) {
 }
 
 int eslam_gpu_process_map(eslam_gpu_ctx* ctx, const eslam_gpu_scan* scan, int match, int update) {
+    NvtxRange nvtx_("eslam processMap");
     int st = check_ready(ctx, true);
     if (st != ESLAM_OK) return st;
     if (!scan || !scan->cells_mean_stdev || scan->width <= 0 || scan->height <= 0) return ESLAM_ERR_INVALID;
@@ -1332,6 +1352,7 @@ int eslam_gpu_pose_moments(eslam_gpu_ctx* ctx, eslam_gpu_gaussian2d* out) {
 
 // ---- SurfaceHash (src/SurfaceHash.hpp:113-232; src/PoseEstimator.cpp:75-86,130-182)
 int eslam_gpu_hash_create(eslam_gpu_ctx* ctx, int slope_bins, int angular_steps) {
+    NvtxRange nvtx_("eslam SurfaceHash::create");
     if (!ctx) return ESLAM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     if (!ctx->has_map) { ctx->error = "No environment attached."; return ESLAM_ERR_NO_ENVIRONMENT; }

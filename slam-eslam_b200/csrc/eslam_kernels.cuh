@@ -112,6 +112,8 @@ struct FastContacts {
     uint32_t gate_lo, gate_span; // high word of |t|: below gate_lo -> inside the gate; within [gate_lo, gate_lo+gate_span] -> undecided
     double c0x, c0y;             // 1.5*2^28 - offset/scale: cell quotient with 24 fractional bits (minus the tile origin: tile-relative)
     int bsx, bsy, nbx, nby, nb;  // bins: a lattice of tile cores (tile minus the margin on every side), bsx x bsy cells each
+    uint32_t inv_bsx, inv_bsy;   // ceil(2^32 / d), d >= 2: n / d == umulhi(n, inv) for n < 2^16 (cell numbers)
+    uint32_t inv_nbx;            // ceil(2^31 / nbx) (nbx may be 1): b / nbx == umulhi(2 b, inv) for b < 2^15
     uint8_t gend[ESLAM_MAX_CONTACTS];   // one past the last evaluated contact of each group (groups without any are dropped)
     uint8_t flags[ESLAM_MAX_CONTACTS];  // per compact contact: bit0 = 1 (evaluated), bit1 = last of its group
     double px[ESLAM_MAX_CONTACTS + 1], py[ESLAM_MAX_CONTACTS + 1], pzr[ESLAM_MAX_CONTACTS + 1];   // [n_eval] = 0: read ahead by the loop
@@ -843,7 +845,7 @@ __device__ __forceinline__ unsigned long long chunk_stride() { return (unsigned 
 #define MAX_BINS 4096
 
 __device__ __forceinline__ void bin_origin(const MapParams& M, const FastContacts& F, int b, int& x0, int& y0) {
-    const int by = b / F.nbx, bx = b - by * F.nbx;
+    const int by = (int)__umulhi((unsigned)b << 1, F.inv_nbx), bx = b - by * F.nbx;
     x0 = max(0, min(bx * F.bsx - F.margin, M.W - M.tile_w)) & ~1;        // W - tile_w is even when the lean path is on
     y0 = max(0, min(by * F.bsy - F.margin, M.H - M.tile_h));
 }
@@ -884,7 +886,7 @@ __global__ void __launch_bounds__(1024, 1) k_project_bin(const __grid_constant__
         bool ok = placed & (((uint32_t)(em::d2u(mv) >> 52) - 923u) < 199u);   // measVar inside rsqrt_core's range
         int b = 0;
         if (placed) {
-            b = (cy / F.bsy) * F.nbx + cx / F.bsx;
+            b = (int)__umulhi((unsigned)cy, F.inv_bsy) * F.nbx + (int)__umulhi((unsigned)cx, F.inv_bsx);
             int x0, y0; bin_origin(C.map, F, b, x0, y0);
             ok = ok & ((unsigned)(cx - x0 - F.margin) < (unsigned)(C.map.tile_w - 2 * F.margin)) &
                  ((unsigned)(cy - y0 - F.margin) < (unsigned)(C.map.tile_h - 2 * F.margin));
@@ -971,7 +973,15 @@ struct LeanTile { uint32_t sa; int w, x0, y0; double c0x, c0y; };
 // EXACT == false: the lean decisions; returns false when one of them was too close to its threshold to be trusted.
 // EXACT == true: every decision as contact_eval takes it (cell index through the IEEE division, the gate as
 // d^2 < 9 zvar); always returns true.  Everything that reaches the result is the same arithmetic in both.
-template <bool EXACT, int UNROLL>
+// (top byte of ky) << 8 | top byte of kx, for ky < 2^31: prmt's sign-replicating selectors (PTX ISA, prmt default mode, selector
+// bit 3) give the two zero bytes -- __byte_perm documents only three selector bits, hence the PTX
+__device__ __forceinline__ uint32_t row_col_bytes(uint32_t kx, uint32_t ky) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, 0xFF73;" : "=r"(r) : "r"(kx), "r"(ky));
+    return r;
+}
+
+template <bool EXACT, int UNROLL, bool P256>
 __device__ __forceinline__ bool lean_eval(const FastContacts& F, const MapParams& M, const LeanTile& T,
                                           uint32_t htab_sa, double inv_corr, double x, double y, double s, double c,
                                           double z, double mv, PoseEval& out) {
@@ -999,7 +1009,10 @@ __device__ __forceinline__ bool lean_eval(const FastContacts& F, const MapParams
         const uint32_t kx = (uint32_t)ux, ky = (uint32_t)uy;
         // (k + 4) << 8 drops the cell bits: below 8 << 8 when the fraction is within 4/2^24 of a cell border
         border_min = min(border_min, min(kx * 256u + 1024u, ky * 256u + 1024u));
-        cell_n = lds_f32x2(T.sa + ((ky >> 24) * (uint32_t)T.w + (kx >> 24)) * 8u);
+        // tile rows are 256 cells apart when the grid is at least that wide: the cell's offset is then (row byte, column byte), one
+        // byte permute (the tile has fewer than 128 rows, so the row byte's sign bit supplies the two zero bytes)
+        if (P256) cell_n = lds_f32x2(T.sa + (row_col_bytes(kx, ky) << 3));
+        else cell_n = lds_f32x2(T.sa + ((ky >> 24) * (uint32_t)T.w + (kx >> 24)) * 8u);
     };
     int i = 0;
     if (!EXACT) look_up(0);
@@ -1099,13 +1112,13 @@ __device__ __noinline__ void lean_redo_exact(const FastParams* P, const LeanTile
     const double x = C.st.f[cur][F_X][i], y = C.st.f[cur][F_Y][i], th = C.st.f[cur][F_TH][i];
     const double z = C.st.f[cur][F_Z][i], zs = C.st.f[cur][F_ZS][i];
     double s, c; em::sincos_(th, s, c);
-    lean_eval<true, 1>(P->fc, C.map, *T, htab_sa, C.mp.inv_corr, x, y, s, c, z, zs * zs + C.mp.merr2, *out);
+    lean_eval<true, 1, false>(P->fc, C.map, *T, htab_sa, C.mp.inv_corr, x, y, s, c, z, zs * zs + C.mp.merr2, *out);
 }
 
 // Work distribution: a chunk is 32 consecutive entries of a bin's list.  Every CTA works on one bin at a time (its tile
 // is what the CTA has in shared memory); its warps pull chunks from the bin's global counter, so all CTAs on a bin finish
 // it together.  A CTA whose bin is exhausted joins the bin with the most chunks left (restaging the tile) or exits.
-template <int THREADS>
+template <int THREADS, bool P256>
 __global__ void __launch_bounds__(THREADS, 1) k_weight_lean(const __grid_constant__ FastParams P, const uint32_t* __restrict__ list,
                                                             const int* __restrict__ bin_count, const unsigned* __restrict__ bin_offs,
                                                             unsigned* __restrict__ bin_next, const int* __restrict__ cta_bin) {
@@ -1169,7 +1182,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_weight_lean(const __grid_constan
                     else {
                         const double x = C.st.f[cur][F_X][i], y = C.st.f[cur][F_Y][i], th = C.st.f[cur][F_TH][i];
                         double s, c; em::sincos_(th, s, c);              // :279-282
-                        if (!lean_eval<false, 2>(P.fc, C.map, T, htab_sa, C.mp.inv_corr, x, y, s, c, z, zs2 + C.mp.merr2 /* :290 */, ev))
+                        if (!lean_eval<false, 2, P256>(P.fc, C.map, T, htab_sa, C.mp.inv_corr, x, y, s, c, z, zs2 + C.mp.merr2 /* :290 */, ev))
                             lean_redo_exact(&P, &T, htab_sa, cur, i, &ev);
                     }
                     finish_particle(C, cur, i, ev, z, zs2, C.st.f[cur][F_W][i]);
