@@ -12,6 +12,7 @@
 #include <string.h>
 #include <chrono>
 #include <algorithm>
+#include <atomic>
 #include <string>
 #include <utility>
 #include <vector>
@@ -27,7 +28,7 @@ struct NvtxRange { explicit NvtxRange(const char* name) { nvtxRangePushA(name); 
 
 // Development switches, read ONCE when a context is created (tools/README.md); never consulted on the step path.
 struct EnvSwitches {
-    bool no_fast, no_tma, no_local_resample, stream_resample, trace, timing, use_pdl, no_p2p;
+    bool no_fast, no_tma, no_local_resample, stream_resample, trace, timing, use_pdl, no_p2p, result_sync;
     int lean_threads, tile_override, graph;
     void read() {
         no_fast = getenv("ESLAM_GPU_NO_FAST") != nullptr;
@@ -38,6 +39,7 @@ struct EnvSwitches {
         timing = getenv("ESLAM_GPU_TIMING") != nullptr;
         use_pdl = getenv("ESLAM_GPU_NO_PDL") == nullptr;
         no_p2p = getenv("ESLAM_GPU_NO_P2P") != nullptr;
+        result_sync = getenv("ESLAM_GPU_RESULT_SYNC") != nullptr && atoi(getenv("ESLAM_GPU_RESULT_SYNC")) != 0;
         lean_threads = getenv("ESLAM_GPU_LEAN_THREADS") ? atoi(getenv("ESLAM_GPU_LEAN_THREADS")) : 1024;
         graph = getenv("ESLAM_GPU_GRAPH") ? atoi(getenv("ESLAM_GPU_GRAPH")) : -1;   // -1: by size, 0: never, 1: always
         tile_override = getenv("ESLAM_GPU_TILE") ? atoi(getenv("ESLAM_GPU_TILE")) : 0;
@@ -59,6 +61,9 @@ struct eslam_gpu_ctx {
     StateBufs st;
     DevScalars* sc; DevScalars* sc_host;          // sc_host: pinned staging
     DevScalars* sc_async;                         // pinned mirror refreshed after every update on a side stream (never waited for)
+    ResultBox* box_host; ResultBox* box_dev;      // host-mapped pinned mailbox k_chain publishes the UpdateResult into (two views)
+    unsigned long long* box_seq;                  // device-side sequence counter of the mailbox
+    uint64_t chain_launched;                      // k_chain launches so far: the sequence number the newest result will carry
     cudaStream_t side; cudaEvent_t side_ev;
     uint32_t* ancestors; double* cdf;
     long long* el_d0; unsigned short* el_code;    // per element: offset of its running sum from its base (k_norm_scan -> k_cdf)
@@ -431,6 +436,11 @@ static int create_impl(eslam_gpu_ctx* ctx, int device) {
     CK(cudaMallocHost((void**)&ctx->sc_host, sizeof(DevScalars)));
     CK(cudaMallocHost((void**)&ctx->sc_async, sizeof(DevScalars)));
     memset(ctx->sc_async, 0, sizeof(DevScalars));
+    CK(cudaHostAlloc((void**)&ctx->box_host, sizeof(ResultBox), cudaHostAllocMapped));
+    memset(ctx->box_host, 0, sizeof(ResultBox));
+    CK(cudaHostGetDevicePointer((void**)&ctx->box_dev, ctx->box_host, 0));
+    CK(cudaMalloc((void**)&ctx->box_seq, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->box_seq, 0, sizeof(unsigned long long), ctx->stream));
     CK(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->side_ev, cudaEventDisableTiming));
     CK(dalloc(&ctx->ticket, 1)); CK(cudaMemsetAsync(ctx->ticket, 0, sizeof(unsigned), ctx->stream));
@@ -479,6 +489,8 @@ void eslam_gpu_destroy(eslam_gpu_ctx* ctx) {
     if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
     if (ctx->side_ev) cudaEventDestroy(ctx->side_ev);
     if (ctx->sc_async) cudaFreeHost(ctx->sc_async);
+    if (ctx->box_host) cudaFreeHost(ctx->box_host);
+    if (ctx->box_seq) cudaFree(ctx->box_seq);
     if (ctx->sc_host) cudaFreeHost(ctx->sc_host);
     cudaFree(ctx->sc); cudaFree(ctx->d_tmap); cudaFree(ctx->htab); cudaFree(ctx->cells); cudaFree(ctx->hint); cudaFree(ctx->ticket);
     cudaFree(ctx->bin_count); cudaFree(ctx->bin_offs); cudaFree(ctx->bin_next); cudaFree(ctx->cta_bin);
@@ -778,7 +790,8 @@ static int launch_tail(eslam_gpu_ctx* ctx, bool apply_loop_b, int normalise, int
     ChainArgs ca; ca.tile_sq = ctx->l_tile_sq; ca.desc = ctx->l_desc; ca.pool = ctx->l_pool; ca.n_tiles = T; ca.tile_ofs = tile_ofs(ctx);
     ca.tile_bofs = ctx->tile_bofs; ca.tile_pre = ctx->tile_pre; ca.sb_out = ctx->sb;
     ca.min_effective = mode == 2 ? 0ull : ctx->cfg.min_effective; ca.decide = mode == 0 ? 0 : 1; ca.force = force;
-    ca.n = n; ca.cdf = ctx->cdf;
+    ca.n = n; ca.cdf = ctx->cdf; ca.box = ctx->box_dev; ca.box_seq = ctx->box_seq;
+    if (!ctx->capturing) ctx->chain_launched++;
     CK(launch_pdl(ctx, k_chain, 1, 1024, sizeof(ChainSmem), ctx->st, ctx->sc, ca, sp, ctx->X));
     LAUNCHED();
     if (mode == 2) return ESLAM_OK;
@@ -877,10 +890,31 @@ static int launch_update(eslam_gpu_ctx* ctx, const eslam_gpu_step* step_or_null,
     return launch_tail(ctx, true, 1, 1, 0);
 }
 
+// The step's UpdateResult.  k_chain publishes it into host-mapped memory the moment the resampling decision is taken; the host
+// waits for that sequence number only, so the call returns while k_cdf and the resampling kernel are still running -- they overlap
+// the caller's next step, and every later call is ordered after them on the context's stream.  Errors raised by those trailing
+// kernels (a peer that never arrived) surface in the next result.  ESLAM_GPU_RESULT_SYNC=1: wait for the whole step instead.
 static int fetch_result(eslam_gpu_ctx* ctx, eslam_gpu_update_result* r) {
-    int st = read_scalars(ctx);
-    if (st != ESLAM_OK) return st;
-    const DevScalars& s = *ctx->sc_host;
+    const uint64_t want = ctx->chain_launched;
+    volatile ResultBox* b = ctx->box_host;
+    for (unsigned spin = 1; b->seq < want; ++spin) {
+        if ((spin & 2047u) == 0) {
+            const cudaError_t e = cudaStreamQuery(ctx->stream);
+            if (e == cudaSuccess) {
+                if (b->seq >= want) break;
+                ctx->error = "the step finished without publishing its result"; return ESLAM_ERR_CUDA;
+            }
+            if (e != cudaErrorNotReady) CK(e);
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (ctx->env.result_sync) CK(cudaStreamSynchronize(ctx->stream));
+    ResultBox s;
+    s.ess = b->ess; s.max_weight = b->max_weight; s.floating_weight = b->floating_weight; s.sum_w = b->sum_w;
+    s.data_particles = b->data_particles; s.total_points = b->total_points; s.do_resample = b->do_resample; s.error_flags = b->error_flags;
     r->ess = s.ess; r->max_weight = s.max_weight; r->floating_weight = s.floating_weight; r->weights_sum = s.sum_w;
     r->data_particles = s.data_particles; r->total_points = s.total_points; r->resampled = s.do_resample;
     r->status = ESLAM_OK;
@@ -1019,7 +1053,7 @@ static int graph_step(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const Cont
     *done = true;
     if (!launch) return ESLAM_OK;                                          // prepared (captured, parameters current): nothing has run
     CK(cudaGraphLaunch(G.exec, ctx->stream));
-    ctx->launches += G.kernels;
+    ctx->launches += G.kernels; ctx->chain_launched++;
     ctx->last_lean = true; ctx->hint_n = 0;
     return ESLAM_OK;
 }
@@ -1111,7 +1145,7 @@ int eslam_gpu_step_times(eslam_gpu_ctx* ctx, float* out_ms, int cap) {
 int eslam_gpu_io_bytes(const eslam_gpu_ctx* ctx, int n_pts, uint64_t out[2]) {
     if (!ctx || !out || n_pts < 0) return ESLAM_ERR_INVALID;
     out[0] = sizeof(eslam_gpu_step) + (uint64_t)n_pts * sizeof(eslam_gpu_contact);   // host inputs of one eslam_gpu_step_fused call
-    out[1] = sizeof(DevScalars);                                                      // what fetch_result copies back for the UpdateResult
+    out[1] = sizeof(ResultBox);                                                       // what k_chain writes into host memory for the UpdateResult
     return ESLAM_OK;
 }
 

@@ -72,6 +72,15 @@ struct DevScalars {              // device-resident scalars of one context
     double rank_start[9];        // [q] = running sum before rank q's first particle, [world] = the total (ESLAM_MAX_RANKS + 1 entries)
 };
 
+// The UpdateResult of a step, written by k_chain into host-mapped pinned memory as soon as the resampling decision is taken
+// (the host reads it without a copy or a stream synchronise while k_cdf / the resampling kernel still run); seq last.
+struct ResultBox {
+    double ess, max_weight, floating_weight, sum_w;
+    unsigned long long data_particles, total_points;
+    int do_resample, error_flags;
+    unsigned long long seq;      // number of k_chain launches of this context that have published
+};
+
 struct TilePartA {               // per-tile partials of loop A
     double sum_pw, max_w;
     unsigned int cnt, pts;
@@ -1854,7 +1863,20 @@ struct ChainArgs {
     double* sb_out;                  // [MAX_BND_TOTAL] exact running sum at every local boundary element
     unsigned long long min_effective; int decide, force;
     unsigned long long n; double* cdf;   // sequential fallback: local particle count, running-sum array
+    ResultBox* box; unsigned long long* box_seq;   // host-mapped result mailbox and its device-side sequence counter
 };
+
+// Everything the caller's UpdateResult holds is final: publish it to the host (fields, system fence, then the sequence number).
+__device__ __forceinline__ void publish_result(const ChainArgs& A, DevScalars* sc) {
+    if (!A.box) return;
+    const unsigned long long q = *A.box_seq + 1; *A.box_seq = q;
+    ResultBox* b = A.box;
+    b->ess = sc->ess; b->max_weight = sc->max_weight; b->floating_weight = sc->floating_weight; b->sum_w = sc->sum_w;
+    b->data_particles = sc->data_particles; b->total_points = sc->total_points;
+    b->do_resample = sc->do_resample; b->error_flags = *(volatile int*)&sc->error_flags;
+    __threadfence_system();
+    *(volatile unsigned long long*)&b->seq = q;
+}
 
 // the running sum through one rank's summary (entries in shared memory); sb != nullptr: record the sum at every boundary
 __device__ __forceinline__ double chain_walk(double S, const SegF& head, const ChainEntry* e, int n_bnd, int& bad) {
@@ -2050,7 +2072,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain(StateBufs st, DevScalars* sc,
         sc->rank_start_valid = 0;
     }
     __syncthreads();
-    if (!s_go) return;
+    if (!s_go) { if (tid == 0) publish_result(A, sc); return; }
 
     if (!local && !s_bad) {
         // The walk: through the summaries of ALL ranks in order (the other ranks' entries polled into shared memory, the own
@@ -2111,6 +2133,9 @@ __global__ void __launch_bounds__(1024, 1) k_chain(StateBufs st, DevScalars* sc,
         if (s_late) { if (X.world > 1) { if (tid == 0) atomicOr(&sc->error_flags, ERR_INTERNAL_BIT); } else if (tid == 0) s_bad = 1; }
         __syncthreads();
     }
+    // the decision and every consistency check of the walk are in: the host may have the step's result while the running sum,
+    // the resampling copy (and a sequential fallback below) are still to run
+    if (tid == 0) publish_result(A, sc);
     if (s_bad) {
         // ---- fallback: the literal left-to-right running sum by one thread (boundary pool overflow, ambiguous binades).  Sharded
         // exact-global walk: rank r continues from the sum rank r-1 ended with (exchange X_SEQ), one rank after the other.
