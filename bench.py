@@ -299,7 +299,7 @@ def main():
         median_ms = comm.max_float(median_ms)
 
     # end to end through the reference-facing call: host Step + contact array in, UpdateResult out, every step
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 100))
     g.stepFused(step, contacts)
     if comm: comm.barrier()
     torch.cuda.synchronize()

@@ -1124,6 +1124,82 @@ __device__ __noinline__ void lean_redo_exact(const FastParams* P, const LeanTile
     lean_eval<true, 1, false>(P->fc, C.map, *T, htab_sa, C.mp.inv_corr, x, y, s, c, z, zs * zs + C.mp.merr2, *out);
 }
 
+// The same, by all 32 lanes of the warp for ONE particle (i is warp-uniform): one lane redoing 64 contacts alone keeps its warp
+// for two more chunk times, and when that happens in the last round of a bin the whole CTA (and the kernel) waits for it.
+// Lane l takes the decisions and the likelihood of contacts l, l + 32, ... exactly as lean_eval<EXACT> does per contact; the
+// running sums and the group fusion (:172-213) then run over the contacts in order, every lane the same, the per-contact
+// values fetched by shuffles.  Every lane returns the particle's PoseEval.
+__device__ __noinline__ void lean_redo_exact_warp(const FastParams* P, const LeanTile* Tp, uint32_t htab_sa, int cur,
+                                                  unsigned long long i, PoseEval* out) {
+    const WeightCommon& C = P->c; const FastContacts& F = P->fc; const MapParams& M = C.map; const LeanTile& T = *Tp;
+    const int lane = threadIdx.x & 31;
+    const double x = C.st.f[cur][F_X][i], y = C.st.f[cur][F_Y][i], th = C.st.f[cur][F_TH][i];
+    const double z = C.st.f[cur][F_Z][i], zs = C.st.f[cur][F_ZS][i];
+    double s, c; em::sincos_(th, s, c);
+    const double mv = zs * zs + C.mp.merr2, inv_corr = C.mp.inv_corr;
+    int pass = -1, n_used = 0, g = 0;
+    double acc_d = 0, acc_v = 0, acc_r = 0;
+    PoseEval ev; ev.n_found = 0; ev.d1 = 0; ev.d2 = 0; ev.A = 0; ev.poseVar = 0;
+    const int n = F.n_eval;
+    for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        double d = 0, zvar = 0, ratio = 0; int inside = 0;
+        if (j < n) {
+            const double px = F.px[j], py = F.py[j];
+            const double wz = z + F.pzr[j];                              // :147
+            const double wx = em::fma_(c, px, em::fma_(-s, py, x));
+            const double wy = em::fma_(s, px, em::fma_(c, py, y));
+            int ix = 0, iy = 0;
+            bool inb = em::cell_index_exact(wx, M.ox, M.sx, M.W, ix);
+            if (inb) inb = em::cell_index_exact(wy, M.oy, M.sy, M.H, iy);
+            const unsigned lx = (unsigned)(ix - T.x0), ly = (unsigned)(iy - T.y0);
+            inb = inb & (lx < (unsigned)M.tile_w) & (ly < (unsigned)M.tile_h);   // always true for a binned particle
+            float2 cl = make_float2(0.f, 0.f);
+            if (inb) cl = lds_f32x2(T.sa + (ly * (unsigned)M.tile_w + lx) * 8u);
+            d = wz - (double)cl.x;
+            zvar = em::fma_((double)cl.y, (double)cl.y, mv);
+            const bool hit = inb & (cl.x == cl.x) & (cl.y == cl.y) & (d * d < 9.0 * zvar);
+            if (hit) {                                                   // em::likelihood_ratio
+                const double q2 = (em::rsqrt_in_range(zvar) ? em::rsqrt_core(zvar) : 1.0 / em::sqrt_(zvar)) * inv_corr;
+                const double t2 = d * q2;
+                double hv;
+                if (em::h_in_range(t2)) {
+                    uint32_t hj; double zc; em::h_index(t2, hj, zc);
+                    double c0, c1; float c2, c3, c4, c5;
+                    lds_f64x2(htab_sa + 16u * hj, c0, c1); lds_f32x4(htab_sa + 16u * (ESLAM_H_NINT + hj), c2, c3, c4, c5);
+                    hv = em::h_poly(zc, c0, c1, c2, c3, c4, c5);
+                } else hv = h_slow_call(t2);
+                ratio = hv * q2;
+            }
+            inside = hit ? -1 : 0;
+        }
+        const int m = min(32, n - j0);
+        for (int l = 0; l < m; ++l) {
+            const double dl = __shfl_sync(0xffffffffu, d, l), vl = __shfl_sync(0xffffffffu, zvar, l), rl = __shfl_sync(0xffffffffu, ratio, l);
+            const int il = __shfl_sync(0xffffffffu, inside, l);
+            pass &= il; n_used -= pass;                                  // :154,:185,:189-190
+            acc_d = em::fma_(dl, rl, acc_d); acc_v = em::fma_(vl, rl, acc_v); acc_r += rl;
+            if (j0 + l + 1 == (int)F.gend[g]) {                          // the group's last evaluated point
+                if (n_used > 0) {                                        // :194-197
+                    if (pass && acc_r > 1e-9) {                          // :199
+                        const double ir = 1.0 / acc_r;
+                        const double zd = acc_d * ir, zv = acc_v * ir;   // :201-202
+                        ev.poseVar += zv - mv;                           // :203
+                        const double iv = 1.0 / zv;
+                        const double q = zd * iv;
+                        ev.d1 += q; ev.d2 += iv; ev.A = em::fma_(zd, q, ev.A);
+                        ev.n_found++;
+                    }
+                    pass = -1; n_used = 0;                               // :210-213 (only when valid: Q4)
+                    acc_d = acc_v = acc_r = 0;
+                }
+                ++g;
+            }
+        }
+    }
+    *out = ev;
+}
+
 // Work distribution: a chunk is 32 consecutive entries of a bin's list.  Every CTA works on one bin at a time (its tile
 // is what the CTA has in shared memory); its warps pull chunks from the bin's global counter, so all CTAs on a bin finish
 // it together.  A CTA whose bin is exhausted joins the bin with the most chunks left (restaging the tile) or exits.
@@ -1181,21 +1257,30 @@ __global__ void __launch_bounds__(THREADS, 1) k_weight_lean(const __grid_constan
                 have_first = false;
                 if (ch >= nch) break;
                 const unsigned k = (ch << 5) + lane;
-                if (k < cnt) {
-                    const uint32_t entry = list[base + k];
-                    const unsigned long long i = entry & 0x7FFFFFFFu;
-                    const double z = C.st.f[cur][F_Z][i], zs = C.st.f[cur][F_ZS][i];
-                    const double zs2 = zs * zs;
-                    PoseEval ev;
+                const bool have = k < cnt;
+                const uint32_t entry = have ? list[base + k] : 0u;
+                const unsigned long long i = entry & 0x7FFFFFFFu;
+                double z = 0, zs2 = 0;
+                PoseEval ev;
+                bool redo = false;
+                if (have) {
+                    z = C.st.f[cur][F_Z][i]; const double zs = C.st.f[cur][F_ZS][i];
+                    zs2 = zs * zs;
                     if (entry >> 31) lean_generic_eval(&P, &T, tile, htab, cur, i, &ev);
                     else {
                         const double x = C.st.f[cur][F_X][i], y = C.st.f[cur][F_Y][i], th = C.st.f[cur][F_TH][i];
                         double s, c; em::sincos_(th, s, c);              // :279-282
-                        if (!lean_eval<false, 2, P256>(P.fc, C.map, T, htab_sa, C.mp.inv_corr, x, y, s, c, z, zs2 + C.mp.merr2 /* :290 */, ev))
-                            lean_redo_exact(&P, &T, htab_sa, cur, i, &ev);
+                        redo = !lean_eval<false, 2, P256>(P.fc, C.map, T, htab_sa, C.mp.inv_corr, x, y, s, c, z, zs2 + C.mp.merr2 /* :290 */, ev);
                     }
-                    finish_particle(C, cur, i, ev, z, zs2, C.st.f[cur][F_W][i]);
                 }
+                // a decision too close to its threshold (~2e-4 of the particles): the particle again with exact decisions, by the whole warp
+                for (unsigned m = __ballot_sync(0xffffffffu, redo); m; m &= m - 1) {
+                    const int src = __ffs(m) - 1;
+                    PoseEval e2;
+                    lean_redo_exact_warp(&P, &T, htab_sa, cur, __shfl_sync(0xffffffffu, i, src), &e2);
+                    if (lane == src) ev = e2;
+                }
+                if (have) finish_particle(C, cur, i, ev, z, zs2, C.st.f[cur][F_W][i]);
             }
         }
         // everyone is done with this tile; pick the bin with the most chunks left
