@@ -22,6 +22,75 @@
 
 namespace eslam_math {
 
+// ---------------------------------------------------------------- constants of the polynomials
+// On the device a 64-bit literal costs two moves into uniform registers at every use; a __constant__ word is an operand of
+// the fp64 instruction itself (c[3][..]).  The host reads the same values as literals: ESLAM_K(name).
+#define ESLAM_K_LIST(X) \
+    X(EXP13, 1.6059043836821613e-10) \
+    X(EXP12, 2.08767569878681e-09) \
+    X(EXP11, 2.505210838544172e-08) \
+    X(EXP10, 2.755731922398589e-07) \
+    X(EXP9, 2.7557319223985893e-06) \
+    X(EXP8, 2.48015873015873e-05) \
+    X(EXP7, 0.0001984126984126984) \
+    X(EXP6, 0.001388888888888889) \
+    X(EXP5, 0.008333333333333333) \
+    X(EXP4, 0.041666666666666664) \
+    X(EXP3, 0.16666666666666666) \
+    X(L2E, 1.4426950408889634) \
+    X(LN2_HI, 6.93147180369123816490e-01) \
+    X(LN2_LO, 1.90821492927058770002e-10) \
+    X(LOG21, 0.047619047619047616) \
+    X(LOG19, 0.05263157894736842) \
+    X(LOG17, 0.058823529411764705) \
+    X(LOG15, 0.06666666666666667) \
+    X(LOG13, 0.07692307692307693) \
+    X(LOG11, 0.09090909090909091) \
+    X(LOG9, 0.1111111111111111) \
+    X(LOG7, 0.14285714285714285) \
+    X(LOG5, 0.2) \
+    X(LOG3, 0.3333333333333333) \
+    X(SQRT2, 1.4142135623730951) \
+    X(SIN19, -8.22063524662433e-18) \
+    X(SIN17, 2.8114572543455206e-15) \
+    X(SIN15, -7.647163731819816e-13) \
+    X(SIN13, 1.6059043836821613e-10) \
+    X(SIN11, -2.505210838544172e-08) \
+    X(SIN9, 2.7557319223985893e-06) \
+    X(SIN7, -0.0001984126984126984) \
+    X(SIN5, 0.008333333333333333) \
+    X(SIN3, -0.16666666666666666) \
+    X(COS20, 4.110317623312165e-19) \
+    X(COS18, -1.5619206968586225e-16) \
+    X(COS16, 4.779477332387385e-14) \
+    X(COS14, -1.1470745597729725e-11) \
+    X(COS12, 2.08767569878681e-09) \
+    X(COS10, -2.755731922398589e-07) \
+    X(COS8, 2.48015873015873e-05) \
+    X(COS6, -0.001388888888888889) \
+    X(COS4, 0.041666666666666664) \
+    X(TWO_PI, 6.283185307179586) \
+    X(TWO_OVER_PI, 0.6366197723675814) \
+    X(PIO2_1, 1.57079632673412561417e+00) \
+    X(PIO2_2, 6.07710050650619224932e-11) \
+    X(PIO2_3, 2.02226624879595063154e-21) \
+    X(RINT_MAGIC, 6755399441055744.0)
+namespace kc {
+#define ESLAM_K_HOST(n, v) constexpr double h_##n = v;
+ESLAM_K_LIST(ESLAM_K_HOST)
+#undef ESLAM_K_HOST
+#if defined(__CUDACC__)
+#define ESLAM_K_DEV(n, v) static __constant__ double d_##n = v;
+ESLAM_K_LIST(ESLAM_K_DEV)
+#undef ESLAM_K_DEV
+#endif
+}
+#if defined(__CUDA_ARCH__)
+#define ESLAM_K(n) (::eslam_math::kc::d_##n)
+#else
+#define ESLAM_K(n) (::eslam_math::kc::h_##n)
+#endif
+
 // ---------------------------------------------------------------- bit moves / fma
 ESLAM_HD uint64_t d2u(double x) {
 #if defined(__CUDA_ARCH__)
@@ -74,7 +143,7 @@ ESLAM_HD double sqrt_(double x) {
 }
 // round to nearest even integer, |x| < 2^51
 ESLAM_HD double rint_(double x) {
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52
+    const double magic = ESLAM_K(RINT_MAGIC);  // 1.5 * 2^52
     return (x + magic) - magic;
 }
 ESLAM_HD bool isnan_(double x) { return x != x; }
@@ -131,22 +200,21 @@ ESLAM_HD double exp_(double x) {
     if (isnan_(x)) return x;
     if (x > 709.782712893384) return u2d(0x7FF0000000000000ull);
     if (x < -745.2) return 0.0;
-    const double L2E = 1.4426950408889634, LN2_HI = 6.93147180369123816490e-01,
-                 LN2_LO = 1.90821492927058770002e-10;
+    const double L2E = ESLAM_K(L2E), LN2_HI = ESLAM_K(LN2_HI), LN2_LO = ESLAM_K(LN2_LO);
     double k = rint_(x * L2E);
     double r = fma_(-k, LN2_HI, x);
     r = fma_(-k, LN2_LO, r);
-    double p = 1.6059043836821613e-10;               // 1/13!
-    p = fma_(p, r, 2.08767569878681e-09);            // 1/12!
-    p = fma_(p, r, 2.505210838544172e-08);           // 1/11!
-    p = fma_(p, r, 2.755731922398589e-07);           // 1/10!
-    p = fma_(p, r, 2.7557319223985893e-06);          // 1/9!
-    p = fma_(p, r, 2.48015873015873e-05);            // 1/8!
-    p = fma_(p, r, 0.0001984126984126984);           // 1/7!
-    p = fma_(p, r, 0.001388888888888889);            // 1/6!
-    p = fma_(p, r, 0.008333333333333333);            // 1/5!
-    p = fma_(p, r, 0.041666666666666664);            // 1/4!
-    p = fma_(p, r, 0.16666666666666666);             // 1/3!
+    double p = ESLAM_K(EXP13);               // 1/13!
+    p = fma_(p, r, ESLAM_K(EXP12));            // 1/12!
+    p = fma_(p, r, ESLAM_K(EXP11));            // 1/11!
+    p = fma_(p, r, ESLAM_K(EXP10));            // 1/10!
+    p = fma_(p, r, ESLAM_K(EXP9));            // 1/9!
+    p = fma_(p, r, ESLAM_K(EXP8));            // 1/8!
+    p = fma_(p, r, ESLAM_K(EXP7));            // 1/7!
+    p = fma_(p, r, ESLAM_K(EXP6));            // 1/6!
+    p = fma_(p, r, ESLAM_K(EXP5));            // 1/5!
+    p = fma_(p, r, ESLAM_K(EXP4));            // 1/4!
+    p = fma_(p, r, ESLAM_K(EXP3));            // 1/3!
     p = fma_(p, r, 0.5);
     p = fma_(p, r, 1.0);
     p = fma_(p, r, 1.0);
@@ -168,24 +236,24 @@ ESLAM_HD double log_(double x) {
     k += (int)(u >> 52) - 1023;
     u = (u & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull;   // m in [1,2)
     double m = u2d(u);
-    if (m > 1.4142135623730951) { m *= 0.5; k += 1; }
+    if (m > ESLAM_K(SQRT2)) { m *= 0.5; k += 1; }
     double f = m - 1.0;
     double s = f / (m + 1.0);
     double z = s * s;
-    double p = 0.047619047619047616;                  // 1/21
-    p = fma_(p, z, 0.05263157894736842);              // 1/19
-    p = fma_(p, z, 0.058823529411764705);             // 1/17
-    p = fma_(p, z, 0.06666666666666667);              // 1/15
-    p = fma_(p, z, 0.07692307692307693);              // 1/13
-    p = fma_(p, z, 0.09090909090909091);              // 1/11
-    p = fma_(p, z, 0.1111111111111111);               // 1/9
-    p = fma_(p, z, 0.14285714285714285);              // 1/7
-    p = fma_(p, z, 0.2);                              // 1/5
-    p = fma_(p, z, 0.3333333333333333);               // 1/3
+    double p = ESLAM_K(LOG21);                  // 1/21
+    p = fma_(p, z, ESLAM_K(LOG19));              // 1/19
+    p = fma_(p, z, ESLAM_K(LOG17));              // 1/17
+    p = fma_(p, z, ESLAM_K(LOG15));              // 1/15
+    p = fma_(p, z, ESLAM_K(LOG13));              // 1/13
+    p = fma_(p, z, ESLAM_K(LOG11));              // 1/11
+    p = fma_(p, z, ESLAM_K(LOG9));              // 1/9
+    p = fma_(p, z, ESLAM_K(LOG7));              // 1/7
+    p = fma_(p, z, ESLAM_K(LOG5));              // 1/5
+    p = fma_(p, z, ESLAM_K(LOG3));              // 1/3
     // log m = 2s + 2s z p
     double s2 = s + s;
     double lm = fma_(s2 * z, p, s2);
-    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double LN2_HI = ESLAM_K(LN2_HI), LN2_LO = ESLAM_K(LN2_LO);
     double dk = (double)k;
     return fma_(dk, LN2_HI, fma_(dk, LN2_LO, lm));
 }
@@ -193,28 +261,28 @@ ESLAM_HD double log_(double x) {
 // ---------------------------------------------------------------- sin / cos kernels, |a| <= pi/4
 ESLAM_HD double sin_kernel(double a) {
     double z = a * a;
-    double p = -8.22063524662433e-18;                 // -1/19!
-    p = fma_(p, z, 2.8114572543455206e-15);           //  1/17!
-    p = fma_(p, z, -7.647163731819816e-13);           // -1/15!
-    p = fma_(p, z, 1.6059043836821613e-10);           //  1/13!
-    p = fma_(p, z, -2.505210838544172e-08);           // -1/11!
-    p = fma_(p, z, 2.7557319223985893e-06);           //  1/9!
-    p = fma_(p, z, -0.0001984126984126984);           // -1/7!
-    p = fma_(p, z, 0.008333333333333333);             //  1/5!
-    p = fma_(p, z, -0.16666666666666666);             // -1/3!
+    double p = ESLAM_K(SIN19);                 // -1/19!
+    p = fma_(p, z, ESLAM_K(SIN17));           // +-1/17!
+    p = fma_(p, z, ESLAM_K(SIN15));           // +-1/15!
+    p = fma_(p, z, ESLAM_K(SIN13));           // +-1/13!
+    p = fma_(p, z, ESLAM_K(SIN11));           // +-1/11!
+    p = fma_(p, z, ESLAM_K(SIN9));           // +-1/9!
+    p = fma_(p, z, ESLAM_K(SIN7));           // +-1/7!
+    p = fma_(p, z, ESLAM_K(SIN5));           // +-1/5!
+    p = fma_(p, z, ESLAM_K(SIN3));           // +-1/3!
     return fma_(a * z, p, a);
 }
 ESLAM_HD double cos_kernel(double a) {
     double z = a * a;
-    double p = 4.110317623312165e-19;                 //  1/20!
-    p = fma_(p, z, -1.5619206968586225e-16);          // -1/18!
-    p = fma_(p, z, 4.779477332387385e-14);            //  1/16!
-    p = fma_(p, z, -1.1470745597729725e-11);          // -1/14!
-    p = fma_(p, z, 2.08767569878681e-09);             //  1/12!
-    p = fma_(p, z, -2.755731922398589e-07);           // -1/10!
-    p = fma_(p, z, 2.48015873015873e-05);             //  1/8!
-    p = fma_(p, z, -0.001388888888888889);            // -1/6!
-    p = fma_(p, z, 0.041666666666666664);             //  1/4!
+    double p = ESLAM_K(COS20);                 //  1/20!
+    p = fma_(p, z, ESLAM_K(COS18));          // +-1/18!
+    p = fma_(p, z, ESLAM_K(COS16));          // +-1/16!
+    p = fma_(p, z, ESLAM_K(COS14));          // +-1/14!
+    p = fma_(p, z, ESLAM_K(COS12));          // +-1/12!
+    p = fma_(p, z, ESLAM_K(COS10));          // +-1/10!
+    p = fma_(p, z, ESLAM_K(COS8));          // +-1/8!
+    p = fma_(p, z, ESLAM_K(COS6));          // +-1/6!
+    p = fma_(p, z, ESLAM_K(COS4));          // +-1/4!
     p = fma_(p, z, -0.5);
     return fma_(z, p, 1.0);
 }
@@ -230,15 +298,14 @@ ESLAM_HD void quadrant_(int q, double sk, double ck, double& s, double& c) {
 ESLAM_HD void sincos_2pi(double u, double& s, double& c) {
     double q = rint_(u * 4.0);          // 0..4
     double r = u - q * 0.25;            // exact, |r| <= 1/8
-    double a = r * 6.283185307179586;
+    double a = r * ESLAM_K(TWO_PI);
     quadrant_((int)q, sin_kernel(a), cos_kernel(a), s, c);
 }
 // sin/cos(theta), three-part Cody-Waite reduction; full accuracy for |theta| < ~1e5,
 // graceful beyond (headings are un-wrapped sums of small deltas, src/PoseEstimator.cpp:206)
 ESLAM_HD void sincos_(double t, double& s, double& c) {
-    const double TWO_OVER_PI = 0.6366197723675814;
-    const double P1 = 1.57079632673412561417e+00, P2 = 6.07710050650619224932e-11,
-                 P3 = 2.02226624879595063154e-21;
+    const double TWO_OVER_PI = ESLAM_K(TWO_OVER_PI);
+    const double P1 = ESLAM_K(PIO2_1), P2 = ESLAM_K(PIO2_2), P3 = ESLAM_K(PIO2_3);
     double k = rint_(t * TWO_OVER_PI);
     double r = fma_(-k, P1, t);
     r = fma_(-k, P2, r);
