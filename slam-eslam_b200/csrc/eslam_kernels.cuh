@@ -2464,6 +2464,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
 #define RS_STAGE_BYTES (8 * TILE * 8 + 2 * TILE)          // cdf + 7 doubles + 2 bytes per particle of one source tile
 #define RS_STAGES 3                                       // ring depth: two source tiles in flight while one is searched
 #define RS_STREAM_SMEM (RS_STAGES * RS_STAGE_BYTES + 64)
+#define RS_TS_CACHE 128                                   // tile starts of a CTA's source tiles kept in shared memory
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -2528,14 +2529,19 @@ __global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevSc
         c_lo += t_first; c_hi += t_first;                                      // the tiles in front of the slice all start below thr_lo
         const unsigned tA = c_lo == 0 ? 0u : c_lo - 1, tB = c_hi == 0 ? 0u : c_hi - 1;
         if (tid == 0) { for (int g = 0; g < RS_STAGES; ++g) mbar_init(mbar0 + 8u * g, 1); }
-        __syncthreads();
         // exact running sum before tile t.  The first tile of a rank: from the walk's rank starts (this rank's own memory) --
         // the table entry is pushed by that rank, which this CTA has not necessarily waited for (t may be one past its slice)
         const bool rs_valid = world > 1 && sc->rank_start_valid;
-        auto tstart = [&](unsigned t) -> double {
+        auto tstart_mem = [&](unsigned t) -> double {
             if (rs_valid) { const unsigned q = t / T; if (q * T == t) return sc->rank_start[q]; }
             return __ldcg(&A.tile_start[t]);
         };
+        // the starts of the CTA's own source tiles tA .. tB + 1 are asked for again and again (candidate ranges, two tiles ahead of
+        // the ring): once into shared memory -- from global memory every look-ahead costs two dependent L2 round trips per tile
+        __shared__ double s_ts[RS_TS_CACHE];
+        for (unsigned i = tid; i < RS_TS_CACHE && tA + i < A.n_tiles && tA + i <= tB + 1; i += 1024) s_ts[i] = tstart_mem(tA + i);
+        __syncthreads();
+        auto tstart = [&](unsigned t) -> double { return (t - tA) < RS_TS_CACHE ? s_ts[t - tA] : tstart_mem(t); };
         // candidate strata of tile t inside [K0, K1) (local stratum numbers; uniform over the CTA)
         const double dbase = (double)base;
         auto range = [&](unsigned t, unsigned long long& klo, unsigned long long& khi) {
