@@ -17,6 +17,9 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line: whatever NCCL has to say (NCCL_DEBUG=VERSION/INFO prints to stdout by default) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
