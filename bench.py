@@ -351,7 +351,7 @@ def main():
                      "achieved_kind": "algorithmic bytes per launch / measured launch time (CUDA events in this run)",
                      "limiter": "fp64 instruction issue" if lean else "fp64 instruction issue + L2 gathers",
                      "kernel_ms": top_avg_s * 1e3, "kernel_share_of_step": top_ms / ms,
-                     "kernel_ms_sampling": "CUDA events around the kernel on every 4th timed step (every step below 16 steps); "
+                     "kernel_ms_sampling": "CUDA events around the kernel on every 16th timed step (every 4th below 64 steps, every step below 16); "
                                            "launch-bound sizes run as one CUDA graph: the events of its last replay",
                      "algorithmic_bytes_per_launch": top_bytes,
                      "note": "reported against the HBM roofline as the metric demands; the kernel itself is limited by instruction "

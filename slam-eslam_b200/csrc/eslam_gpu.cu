@@ -1110,9 +1110,9 @@ int eslam_gpu_run_steps(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const es
         return last_result ? fetch_result(ctx, last_result) : ESLAM_OK;
     }
     // The events around the dominant kernel sit between launches and so take the programmatic overlap away at those two
-    // places: they are recorded on every 4th step only (every step in short runs); the kernel's time is the mean over the
+    // places: they are recorded on every 16th step only (every 4th below 64 steps, every step below 16); the kernel's time is the mean over the
     // sampled steps, scaled to the run, and a step period is the time between two sampled steps divided by their distance.
-    const int every = steps >= 16 ? 4 : 1;
+    const int every = steps >= 64 ? 16 : steps >= 16 ? 4 : 1;
     for (int s = 0; s < steps; ++s) {
         const bool sampled = (s % every) == 0;
         st = launch_update(ctx, step, &cs, sampled ? ctx->events[2 + 2 * s] : nullptr, sampled ? ctx->events[3 + 2 * s] : nullptr);
