@@ -852,6 +852,7 @@ __device__ __forceinline__ unsigned long long chunk_stride() { return (unsigned 
 // An untrusted decision is taken again for that contact by lean_contact_exact (IEEE division, the gate as written):
 // results are bit-identical to the generic path by construction.
 #define MAX_BINS 4096
+#define LEAN_REDO_CAP (WT_CONTACT_BYTES / 4)   // the lean kernel's list of deferred exact evaluations lives where the generic kernel keeps its contact list
 
 __device__ __forceinline__ void bin_origin(const MapParams& M, const FastContacts& F, int b, int& x0, int& y0) {
     const int by = (int)__umulhi((unsigned)b << 1, F.inv_nbx), bx = b - by * F.nbx;
@@ -921,7 +922,7 @@ __global__ void __launch_bounds__(1024, 1) k_project_bin(const __grid_constant__
 }
 
 // bin-sorted particle list, the offset of every bin in it, and the bin each CTA of the lean kernel starts on
-// (CTA c starts where sorted position c*M/G lies: CTAs per bin in proportion to the bin's particles)
+// (one CTA per non-empty bin, the others in proportion to the bins' particles)
 __global__ void __launch_bounds__(1024, 1) k_bin_scatter(const int* __restrict__ bin_count, int nb, const uint2* __restrict__ keys,
                                                          unsigned long long n, uint32_t* __restrict__ list, unsigned* __restrict__ bin_offs,
                                                          int* __restrict__ cta_bin, int n_cta, DevScalars* sc, int did_project) {
@@ -956,11 +957,37 @@ __global__ void __launch_bounds__(1024, 1) k_bin_scatter(const int* __restrict__
     if (blockIdx.x == 0) {
         for (int b = tid; b < nb; b += 1024) bin_offs[b] = offs[b];
         const unsigned M = offs[MAX_BINS];
-        if (tid < n_cta) {
-            const unsigned p = (unsigned)(((unsigned long long)tid * M) / (unsigned)n_cta);
+        // Where the CTAs of the lean kernel start.  Every non-empty bin gets one CTA first (up to n_cta bins): a wide cloud has a
+        // fringe of small bins, and a bin nobody starts on is only reached by stealing, i.e. AFTER the big bins are exhausted --
+        // one more tile load and chunk round at the very end of the kernel.  Started at once, the small bins are done long before
+        // the big ones, whose shared queues then absorb every CTA and end the kernel at chunk granularity.  The remaining CTAs
+        // start where sorted position (i + 1/2) M / R lies: in proportion to the bins' particles.
+        unsigned nz = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nz += c[j] > 0;
+        unsigned sz = nz;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned a = __shfl_up_sync(0xffffffffu, sz, o); if (lane >= o) sz += a; }
+        __syncthreads();                                  // wsum is free again
+        if (lane == 31) wsum[warp] = sz;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned a = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned x = __shfl_up_sync(0xffffffffu, a, o); if (lane >= o) a += x; }
+            wsum[lane] = a;
+        }
+        __syncthreads();
+        unsigned r = sz - nz + (warp ? wsum[warp - 1] : 0u);                   // non-empty bins in front of this thread's four
+        const unsigned B = wsum[31];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (c[j] > 0) { if (r < (unsigned)n_cta) cta_bin[r] = tid * 4 + j; ++r; }
+        const unsigned first = B < (unsigned)n_cta ? B : (unsigned)n_cta, R = (unsigned)n_cta - first;
+        if ((unsigned)tid < R) {
+            const unsigned p = (unsigned)(((unsigned long long)(2 * tid + 1) * M) / (2ull * R));
             int lo_b = 0, hi_b = nb;                      // last bin whose offset is <= p: it holds p when it is not empty
             while (hi_b - lo_b > 1) { const int mid = (lo_b + hi_b) >> 1; if (offs[mid] <= p) lo_b = mid; else hi_b = mid; }
-            cta_bin[tid] = lo_b;
+            cta_bin[first + tid] = lo_b;
         }
     }
 }
@@ -1213,7 +1240,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_weight_lean(const __grid_constan
     em::dbl2* htab = reinterpret_cast<em::dbl2*>(smem_raw);
     const uint32_t htab_sa = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t mbar = htab_sa + HTAB_BYTES + WT_CONTACT_BYTES + 512;
-    int* s_pick = reinterpret_cast<int*>(smem_raw + HTAB_BYTES + WT_CONTACT_BYTES);          // [0] best remaining, [1] its bin, [2] the chunk claimed for the CTA (-1: none)
+    int* s_pick = reinterpret_cast<int*>(smem_raw + HTAB_BYTES + WT_CONTACT_BYTES);          // [0] best remaining, [1] its bin, [2] the chunk claimed for the CTA (-1: none), [3] entries of s_redo
+    uint32_t* s_redo = reinterpret_cast<uint32_t*>(smem_raw + HTAB_BYTES);                  // particles of this bin visit waiting for their exact evaluation
     float2* tile = reinterpret_cast<float2*>(smem_raw + WT_HEAD_BYTES);
     const int tid = threadIdx.x, lane = tid & 31;
     const int cur = C.sc->cur;
@@ -1227,7 +1255,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_weight_lean(const __grid_constan
     while (true) {
         const unsigned cnt = (unsigned)bin_count[bin], nch = (cnt + 31u) >> 5, base = bin_offs[bin];
         // one thread claims a first chunk for the CTA: the tile is only staged when there really is work left
-        if (tid == 0) { const unsigned c0 = atomicAdd(&bin_next[bin], 1u); s_pick[2] = c0 < nch ? (int)c0 : -1; }
+        if (tid == 0) { const unsigned c0 = atomicAdd(&bin_next[bin], 1u); s_pick[2] = c0 < nch ? (int)c0 : -1; s_pick[3] = 0; }
         __syncthreads();
         const int first = s_pick[2];
         if (first >= 0) {
@@ -1273,14 +1301,33 @@ __global__ void __launch_bounds__(THREADS, 1) k_weight_lean(const __grid_constan
                         redo = !lean_eval<false, 2, P256>(P.fc, C.map, T, htab_sa, C.mp.inv_corr, x, y, s, c, z, zs2 + C.mp.merr2 /* :290 */, ev);
                     }
                 }
-                // a decision too close to its threshold (~2e-4 of the particles): the particle again with exact decisions, by the whole warp
-                for (unsigned m = __ballot_sync(0xffffffffu, redo); m; m &= m - 1) {
+                // A decision too close to its threshold (~1e-4 of the particles; copies of one ancestor that fall into the same cell
+                // share it, so they come in runs): the particle is evaluated again with exact decisions, by a whole warp.  Not here --
+                // a chunk with eight of them would keep this warp for five chunk times, and the CTA with it -- but from the CTA's
+                // list once its warps have run out of chunks: one particle per warp, all warps at once.
+                bool redo_here = false;
+                if (redo) {
+                    const int slot = atomicAdd(&s_pick[3], 1);
+                    if (slot < LEAN_REDO_CAP) s_redo[slot] = (uint32_t)i; else redo_here = true;
+                }
+                for (unsigned m = __ballot_sync(0xffffffffu, redo_here); m; m &= m - 1) {   // the list is full: as before
                     const int src = __ffs(m) - 1;
                     PoseEval e2;
                     lean_redo_exact_warp(&P, &T, htab_sa, cur, __shfl_sync(0xffffffffu, i, src), &e2);
                     if (lane == src) ev = e2;
                 }
-                if (have) finish_particle(C, cur, i, ev, z, zs2, C.st.f[cur][F_W][i]);
+                if (have && (!redo || redo_here)) finish_particle(C, cur, i, ev, z, zs2, C.st.f[cur][F_W][i]);
+            }
+            __syncthreads();                                             // the CTA's list of deferred particles is complete
+            const int n_redo = min(s_pick[3], LEAN_REDO_CAP);
+            for (int r = tid >> 5; r < n_redo; r += THREADS / 32) {
+                const unsigned long long i = s_redo[r];
+                PoseEval ev;
+                lean_redo_exact_warp(&P, &T, htab_sa, cur, i, &ev);
+                if (lane == 0) {
+                    const double z = C.st.f[cur][F_Z][i], zs = C.st.f[cur][F_ZS][i];
+                    finish_particle(C, cur, i, ev, z, zs * zs, C.st.f[cur][F_W][i]);
+                }
             }
         }
         // everyone is done with this tile; pick the bin with the most chunks left
