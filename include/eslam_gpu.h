@@ -154,11 +154,12 @@ int eslam_gpu_step_fused(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const e
                          eslam_gpu_update_result* result);
 /* Enqueue `steps` identical fused steps without host synchronisation (benchmark loop; inputs stay
  * resident).  elapsed_ms (may be NULL) = CUDA-event time of the whole region on the context's stream;
- * top_kernel_ms (may be NULL) = summed event time of the dominant kernel alone (k_weight_lean; k_project_weight when
- * the lean path does not apply). */
+ * top_kernel_ms = summed event time of the dominant kernel alone (k_weight_lean; k_project_weight when the lean path
+ * does not apply), from events around it on every step; they cost the programmatic overlap at two places per step, so a
+ * run that measures the step itself passes NULL: no event then sits between its first and its last launch. */
 int eslam_gpu_run_steps(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const eslam_gpu_contact* pts, int n_pts,
                         int steps, float* elapsed_ms, float* top_kernel_ms, eslam_gpu_update_result* last_result);
-/* Step periods of the last eslam_gpu_run_steps (steps - 1 values, CUDA events): copies min(count, cap) values, returns count. */
+/* Step periods of the last eslam_gpu_run_steps that asked for top_kernel_ms (steps - 1 values, CUDA events): copies min(count, cap) values, returns count. */
 int eslam_gpu_step_times(eslam_gpu_ctx* ctx, float* out_ms, int cap);
 /* Bytes one eslam_gpu_step_fused call moves between host and device: out = {host -> device (step + contact array, as kernel
  * parameters), device -> host (the scalar block behind eslam_gpu_update_result)} (bench "e2e"). */

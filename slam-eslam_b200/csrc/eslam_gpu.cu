@@ -617,6 +617,10 @@ int eslam_gpu_init_gaussian(eslam_gpu_ctx* ctx, uint64_t n, const double mu[3], 
                             double zsigma) {
     if (!ctx || !mu || !sigma) return ESLAM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    if (sharded(ctx) && ctx->chain_launched > 0) {
+        // the exchange epochs live in the scalars this call resets, while the peers' words of the old epochs are still in the buffers
+        ctx->error = "a sharded context that has stepped cannot be re-initialised: create a new one"; return ESLAM_ERR_INVALID;
+    }
     int st = ensure_capacity(ctx, n);
     if (st != ESLAM_OK) return st;
     DevScalars init; memset(&init, 0, sizeof(init));
@@ -1110,12 +1114,12 @@ int eslam_gpu_run_steps(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const es
         return last_result ? fetch_result(ctx, last_result) : ESLAM_OK;
     }
     // The events around the dominant kernel sit between launches and so take the programmatic overlap away at those two
-    // places: they are recorded on every 16th step only (every 4th below 64 steps, every step below 16); the kernel's time is the mean over the
-    // sampled steps, scaled to the run, and a step period is the time between two sampled steps divided by their distance.
-    const int every = steps >= 64 ? 16 : steps >= 16 ? 4 : 1;
+    // places (~4 us per step): they are recorded only when the caller asks for the kernel's time (top_kernel_ms != NULL), then
+    // on every step.  A run that measures the step itself passes NULL and carries no event between its first and its last launch.
+    const bool sampling = top_kernel_ms != nullptr;
+    const int every = 1;
     for (int s = 0; s < steps; ++s) {
-        const bool sampled = (s % every) == 0;
-        st = launch_update(ctx, step, &cs, sampled ? ctx->events[2 + 2 * s] : nullptr, sampled ? ctx->events[3 + 2 * s] : nullptr);
+        st = launch_update(ctx, step, &cs, sampling ? ctx->events[2 + 2 * s] : nullptr, sampling ? ctx->events[3 + 2 * s] : nullptr);
         if (st != ESLAM_OK) return st;
     }
     CK(cudaEventRecord(ctx->events[1], ctx->stream));
@@ -1128,7 +1132,7 @@ int eslam_gpu_run_steps(eslam_gpu_ctx* ctx, const eslam_gpu_step* step, const es
         *top_kernel_ms = tot * (float)steps / (float)cnt;
     }
     ctx->step_ms.clear();
-    for (int s = 0; s + every < steps; s += every) {
+    for (int s = 0; sampling && s + every < steps; s += every) {
         float t = 0; CK(cudaEventElapsedTime(&t, ctx->events[2 + 2 * s], ctx->events[2 + 2 * (s + every)]));
         ctx->step_ms.push_back(t / (float)every);
     }

@@ -250,12 +250,13 @@ class GpuPoseEstimator(FilterBase):
             self.last_result = res
         return res
 
-    def runSteps(self, step, contacts, steps):
-        """Enqueue ``steps`` fused steps back to back; returns (elapsed_ms, top_kernel_ms, last result)."""
+    def runSteps(self, step, contacts, steps, kernel_events=True):
+        """Enqueue ``steps`` fused steps back to back; returns (elapsed_ms, top_kernel_ms, last result).  kernel_events=False:
+        no event between the first and the last launch (top_kernel_ms is 0 then)."""
         ms, top = C.c_float(), C.c_float()
         res = abi.UpdateResult()
         self._check(self._lib.eslam_gpu_run_steps(self._ctx, C.byref(step), contacts, len(contacts), int(steps),
-                                                  C.byref(ms), C.byref(top), C.byref(res)))
+                                                  C.byref(ms), C.byref(top) if kernel_events else None, C.byref(res)))
         self.last_result = res
         return ms.value, top.value, res
 
