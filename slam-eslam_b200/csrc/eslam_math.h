@@ -430,12 +430,43 @@ ESLAM_HD double likelihood_ratio_fast(double zdiff, double zvar, double inv_corr
 }
 
 // ---------------------------------------------------------------- powers
+// w^(1/3), w > 0 finite: w = m 2^(3q), m in [1, 8); z ~ m^(-1/3) from a quadratic seed (3e-3) and three division-free Newton steps
+// (z <- z + z (1 - m z^3) / 3: error 2 e^2 each), y = m z^2, one Newton step on y with the residual y^3 - m taken exactly
+// (fma).  ~1 ulp; 45 instructions against ~250 for exp(log(w) / 3): three of four contact groups found is the second most
+// frequent case of pow(weight, 1/found) after four, and one lane on the generic path makes its whole warp walk it.
+ESLAM_HD double cbrt_(double w) {
+    uint64_t u = d2u(w);
+    int bias = 0;
+    if ((u >> 52) == 0) { w *= 18014398509481984.0; u = d2u(w); bias = -18; }      // subnormal: 2^54 = (2^18)^3
+    const int e = (int)(u >> 52) - 1023;
+    const int q = (e + 3072) / 3 - 1024, r = e - 3 * q;                            // floor(e / 3), remainder 0..2
+    const double mm = u2d((u & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);     // [1, 2)
+    const double m = mm * (double)(1 << r);                                         // [1, 8), exact
+    double z = fma_(fma_(0.09202394, mm, -0.47733264), mm, 1.38237822);             // mm^(-1/3) to 3e-3
+    z *= r == 0 ? 1.0 : (r == 1 ? 0.7937005259840998 : 0.6299605249474366);         // 2^(-r/3)
+    const double third = 0.3333333333333333;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int it = 0; it < 3; ++it) {
+        const double t = (z * z) * z;
+        const double h = fma_(-m, t, 1.0);
+        z = fma_(z * third, h, z);
+    }
+    double y = (m * z) * z;
+    const double y2 = y * y, e2 = fma_(y, y, -y2);                                  // y^2 = y2 + e2 exactly
+    const double res = fma_(e2, y, fma_(y2, y, -m));                                // y^3 - m
+    y = fma_(-(res * third), z * z, y);                                             // 1 / (3 y^2) = z^2 / 3
+    return y * pow2i(q + bias);
+}
+
 // w^(1/n) as in pow(weight, 1.0/found_points) (src/PoseEstimator.cpp:309), w >= 0
 ESLAM_HD double root_n(double w, unsigned long long n) {
     if (n == 1) return w;
     if (n == 2) return sqrt_(w);
     if (n == 4) return sqrt_(sqrt_(w));
     if (w == 0.0) return 0.0;
+    if (n == 3 && w < 1.7e308) return cbrt_(w);                                     // finite (NaN / inf: the generic path)
     if (n == 0) return (w == 1.0) ? 1.0 : (w < 1.0 ? 0.0 : u2d(0x7FF0000000000000ull));  // pow(w, inf)
     return exp_(log_(w) / (double)n);
 }
