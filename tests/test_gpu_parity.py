@@ -195,6 +195,37 @@ def test_lean_and_generic_weight_kernels_agree(gpu, monkeypatch):
         assert_particles_equal(lean.getParticles(), generic.getParticles())
 
 
+def test_lean_path_when_every_particle_needs_the_exact_evaluation(gpu, monkeypatch):
+    """Particles placed ON cell borders: the fused fixed-point index of their own cell is never trusted, so every particle goes
+    through the exact re-evaluation -- the per-CTA deferred list (worked off by all warps once the bin's chunks have run out) and,
+    with more than 1024 of them per CTA, its overflow path (evaluated on the spot by the whole warp).  Bit-identical to the
+    generic kernel, which takes every decision exactly."""
+    n = 262144
+    rng = np.random.default_rng(11)
+    w = synthetic.WORKLOADS["C3"]
+    scale, off = 0.05, -w["grid"] * 0.05 / 2.0
+    x = off + rng.integers(900, 1150, n) * scale                       # on the border between two cells
+    y = rng.uniform(-3.0, 3.0, n)
+    th = rng.uniform(-3.0, 3.0, n)
+    z = np.full(n, synthetic.terrain_height(0, 0) + 0.19)
+    lean = gpu(abi.default_config(min_effective=n + 1))
+    monkeypatch.setenv("ESLAM_GPU_NO_FAST", "1")
+    generic = gpu(abi.default_config(min_effective=n + 1))
+    contacts, step = synthetic.setup_filter(generic, "C3", n=n)
+    monkeypatch.delenv("ESLAM_GPU_NO_FAST")
+    synthetic.setup_filter(lean, "C3", n=n)
+    for f in (lean, generic):
+        f.setParticles(x=x, y=y, theta=th, zpos=z, zsigma=np.full(n, 1.001), weight=np.full(n, 1.0 / n))
+    monkeypatch.setenv("ESLAM_GPU_NO_FAST", "1")
+    rb = generic.update(contacts)
+    monkeypatch.delenv("ESLAM_GPU_NO_FAST")
+    ra = lean.update(contacts)
+    assert ra.as_dict() == rb.as_dict()
+    assert lean.pathCounters()["lean"] == n
+    assert np.array_equal(lean.getAncestors(), generic.getAncestors())
+    assert_particles_equal(lean.getParticles(), generic.getParticles())
+
+
 def test_lean_path_at_the_map_border(gpu, oracle, monkeypatch):
     """A cloud wider than the map (C2: 25.6 m, sigma 8 m): particles near the border and outside are flagged by the
     binning and evaluated by contact_eval inside the lean kernel; everything must still be bit-identical to the oracle

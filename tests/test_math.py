@@ -18,13 +18,13 @@ def h_exact(t):
     return mp.npdf(t) / mp.ncdf(t)
 
 
-def max_rel(oracle, fn, ref, xs):
+def max_rel(oracle, fn, ref, xs, b=0.0):
     worst = 0.0
     for x in xs:
         r = ref(x)
         if r == 0:
             continue
-        worst = max(worst, float(abs((mp.mpf(oracle.math_fn(fn, x)) - r) / r)))
+        worst = max(worst, float(abs((mp.mpf(oracle.math_fn(fn, x, b)) - r) / r)))
     return worst
 
 
@@ -89,6 +89,17 @@ def test_powers(oracle):
     assert oracle.math_fn(POW_U64, 0.5, 3) == 0.125
     assert oracle.math_fn(POW_U64, 0.9, 2 ** 63) == 0.0          # quirk Q2: wrapped size_t exponent
     assert oracle.math_fn(POW_U64, 1.0, 2 ** 63) == 1.0
+
+
+def test_cube_root(oracle):
+    """pow(weight, 1/3) (three of four contact groups found, src/PoseEstimator.cpp:309) as a division-free cube root."""
+    rng = np.random.default_rng(8)
+    xs = np.concatenate([10 ** rng.uniform(-300, 300, 1500), rng.uniform(1e-12, 1, 1500), [1e-310, 5e-324, 1.7e307]])
+    assert max_rel(oracle, ROOT_N, lambda x: mp.cbrt(mp.mpf(x)), xs, 3) < 1.2 * 2.0 ** -53
+    for k in (1.0, 2.0, 3.0, 0.5, 1e5):
+        assert oracle.math_fn(ROOT_N, k ** 3, 3) == k                     # exact cubes come out exact
+    assert oracle.math_fn(ROOT_N, 0.0, 3) == 0.0
+    assert math.isinf(oracle.math_fn(ROOT_N, float("inf"), 3))
 
 
 def test_box_muller_moments(oracle):
