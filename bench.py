@@ -283,24 +283,30 @@ def main():
     patch = 16 if args.workload == "C4" else 0                       # C4: EmbodiedSlamFilter per-particle map patches
     shard_mode = abi.SHARD_LOCAL_MIGRATE if args.shard_mode == "local" else abi.SHARD_EXACT_GLOBAL
     cfg = abi.default_config(min_effective=n_global + 1, patch_size=patch, shard_mode=shard_mode)   # resample every step (ESS <= N always)
-    # Three passes over the SAME steps of the same trajectory (a fresh filter, W warm-up steps, then K steps each): the synthetic
-    # filter converges -- its cloud contracts from 2 m to 0.1 m within ~50 resampling steps and the weight kernel gets 10 % faster
-    # with it -- so legs measured one after the other on one filter would not see the same work.
+    # Three passes over the SAME steps of the same trajectory (the same filter re-initialised with the same seed, W warm-up steps,
+    # then K steps each): the synthetic filter converges -- its cloud contracts from 2 m to 0.1 m within ~50 resampling steps and
+    # the weight kernel gets 10 % faster with it -- so legs measured one after the other without the reset would not see the
+    # same work.
     #   1. value: K steps enqueued back to back, inputs resident, no event between the first and the last launch;
     #   2. the dominant kernel: the same K steps with CUDA events around it on every step (they cost the programmatic overlap at
     #      two places per step, ~4 us: not the pass the step time comes from);
     #   3. e2e: the same K steps (at most 100) through the reference-facing call with host inputs, the result read every step.
-    def fresh_filter():
-        f = GpuPoseEstimator(cfg, device=local_rank, shard=comm.shard(n_local) if comm else None)
-        if comm:
-            comm.connect(f)
-        cts, stp = synthetic.setup_filter(f, args.workload, n=n_local)
-        f.runSteps(stp, cts, args.warmup, kernel_events=False)
-        return f, cts, stp
+    g = GpuPoseEstimator(cfg, device=local_rank, shard=comm.shard(n_local) if comm else None)
+    if comm:
+        comm.connect(g)
+    contacts, step = synthetic.setup_filter(g, args.workload, n=n_local)
+
+    def restart():
+        """The initial cloud again and the warm-up steps; sharded: every rank is idle before any rank re-initialises."""
+        torch.cuda.synchronize()
+        if comm: comm.barrier()
+        synthetic.init_cloud(g, args.workload, n_local)
+        if comm: comm.barrier()
+        g.runSteps(step, contacts, args.warmup, kernel_events=False)
 
     # The clock sampler is started BEFORE the barrier (forking nvidia-smi takes ~20 ms on rank 0); run_steps itself begins with a
     # device-side rendezvous of all ranks, so no rank's events include waiting for a rank whose host got there later.
-    g, contacts, step = fresh_filter()
+    g.runSteps(step, contacts, args.warmup, kernel_events=False)
     launches0 = g.launchCount()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if comm: comm.barrier()
@@ -310,16 +316,14 @@ def main():
     if comm: comm.barrier()
     launches = g.launchCount() - launches0
     paths = g.pathCounters()
-    g.close()
 
-    g, contacts, step = fresh_filter()
+    restart()
     if comm: comm.barrier()
     torch.cuda.synchronize()
     ms_k, top_ms, _ = g.runSteps(step, contacts, args.steps)
     torch.cuda.synchronize()
     periods = sorted(g.stepTimes())
     median_ms = periods[len(periods) // 2] if periods else ms_k / args.steps
-    g.close()
     if comm:
         ms = comm.max_float(ms)
         top_ms = comm.max_float(top_ms)
@@ -327,7 +331,7 @@ def main():
 
     # end to end through the reference-facing call: host Step + contact array in, UpdateResult out, every step
     e2e_steps = max(3, min(args.steps, 100))
-    g, contacts, step = fresh_filter()
+    restart()
     if comm: comm.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -376,7 +380,7 @@ def main():
                      "achieved_kind": "algorithmic bytes per launch / measured launch time (CUDA events in this run)",
                      "limiter": "fp64 instruction issue" if lean else "fp64 instruction issue + L2 gathers",
                      "kernel_ms": top_avg_s * 1e3, "kernel_share_of_step": top_ms / ms,
-                     "kernel_ms_sampling": "CUDA events around the kernel on every step of a second pass over the same steps (a fresh filter, same warm-up); ms_per_step comes from a pass without them; "
+                     "kernel_ms_sampling": "CUDA events around the kernel on every step of a second pass over the same steps (the filter re-initialised, same warm-up); ms_per_step comes from a pass without them; "
                                            "launch-bound sizes run as one CUDA graph: the events of its last replay",
                      "algorithmic_bytes_per_launch": top_bytes,
                      "note": "reported against the HBM roofline as the metric demands; the kernel itself is limited by instruction "

@@ -133,7 +133,9 @@ const char* eslam_gpu_last_error(const eslam_gpu_ctx* ctx);
 int eslam_gpu_set_grid(eslam_gpu_ctx* ctx, const float* cells_mean_stdev, int width, int height,
                        double scale_x, double scale_y, double offset_x, double offset_y, const double* g2l);
 
-/* PoseEstimator::init(n, mu, sigma, zpos, zsigma) (src/PoseEstimator.cpp:88-102). n = local shard size. */
+/* PoseEstimator::init(n, mu, sigma, zpos, zsigma) (src/PoseEstimator.cpp:88-102). n = local shard size. 
+ * Sharded contexts: re-initialising after steps restarts the exchange epochs; every rank must have finished its steps before
+ * any rank calls this again, and no rank may step before all have (a barrier on either side of the call). */
 int eslam_gpu_init_gaussian(eslam_gpu_ctx* ctx, uint64_t n, const double mu[3], const double sigma[3],
                             double zpos, double zsigma);
 /* ParticleFilter::getParticles() (src/ParticleFilter.hpp:150-158) as SoA; NULL pointers are skipped. */

@@ -617,10 +617,6 @@ int eslam_gpu_init_gaussian(eslam_gpu_ctx* ctx, uint64_t n, const double mu[3], 
                             double zsigma) {
     if (!ctx || !mu || !sigma) return ESLAM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    if (sharded(ctx) && ctx->chain_launched > 0) {
-        // the exchange epochs live in the scalars this call resets, while the peers' words of the old epochs are still in the buffers
-        ctx->error = "a sharded context that has stepped cannot be re-initialised: create a new one"; return ESLAM_ERR_INVALID;
-    }
     int st = ensure_capacity(ctx, n);
     if (st != ESLAM_OK) return st;
     DevScalars init; memset(&init, 0, sizeof(init));
@@ -629,6 +625,10 @@ int eslam_gpu_init_gaussian(eslam_gpu_ctx* ctx, uint64_t n, const double mu[3], 
     *ctx->sc_async = init;
     *ctx->sc_host = init;
     CK(cudaMemcpyAsync(ctx->sc, ctx->sc_host, sizeof(DevScalars), cudaMemcpyHostToDevice, ctx->stream));
+    // Re-initialising a sharded context that has stepped: the exchange epochs restart with the scalars, so the words of the old
+    // epochs must go.  The caller's part of the contract (include/eslam_gpu.h): every rank has finished its steps before any rank
+    // re-initialises, and no rank steps before all have -- a barrier on either side.
+    if (sharded(ctx) && ctx->xchg && ctx->chain_launched > 0) CK(cudaMemsetAsync(ctx->xchg, 0, ctx->x_bytes, ctx->stream));
     st = reset_patches(ctx);
     if (st != ESLAM_OK) return st;
     const ModelParams mp = model_params(ctx);

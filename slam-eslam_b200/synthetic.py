@@ -69,11 +69,18 @@ WORKLOADS = {
 }
 
 
+def init_cloud(f, workload, n=None):
+    """The initial cloud of a workload (again): same seed, same particles."""
+    w = WORKLOADS[workload]
+    n = n or w["n"]
+    f.init(n, (0.0, 0.0, 0.0), (w["sigma_xy"], w["sigma_xy"], 0.1), terrain_height(0, 0) + 0.19, 1.001)
+
+
 def setup_filter(f, workload, n=None, force_resample=True):
     """Attach terrain and draw the initial cloud on any filter object exposing the PoseEstimator mirror API."""
     w = WORKLOADS[workload]
     n = n or w["n"]
     cells, scale, offset = make_terrain(w["grid"], w["grid"])
     f.setEnvironment(cells, scale, offset)
-    f.init(n, (0.0, 0.0, 0.0), (w["sigma_xy"], w["sigma_xy"], 0.1), terrain_height(0, 0) + 0.19, 1.001)
+    init_cloud(f, workload, n)
     return make_contact_points(w["c"]), odometry_step()
