@@ -302,11 +302,11 @@ def main():
         if comm: comm.barrier()
         synthetic.init_cloud(g, args.workload, n_local)
         if comm: comm.barrier()
-        g.runSteps(step, contacts, args.warmup, kernel_events=False)
+        if args.warmup > 0: g.runSteps(step, contacts, args.warmup, kernel_events=False)
 
     # The clock sampler is started BEFORE the barrier (forking nvidia-smi takes ~20 ms on rank 0); run_steps itself begins with a
     # device-side rendezvous of all ranks, so no rank's events include waiting for a rank whose host got there later.
-    g.runSteps(step, contacts, args.warmup, kernel_events=False)
+    if args.warmup > 0: g.runSteps(step, contacts, args.warmup, kernel_events=False)
     launches0 = g.launchCount()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if comm: comm.barrier()
