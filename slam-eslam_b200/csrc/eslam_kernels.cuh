@@ -2499,8 +2499,8 @@ __global__ void __launch_bounds__(RS_THREADS, 2048 / RS_THREADS) k_resample_loca
 // Resampling as a stream (no patches, one walk over all particles; one GPU or the exact-global walk of a sharded filter): a
 // persistent CTA owns a run of consecutive strata [K0, K1) of this rank.  Strata and their ancestors advance together (the
 // walk is monotone, src/ParticleFilter.hpp:96-105), so the CTA pulls the SOURCE tiles that hold its ancestors -- exact running
-// sum + the 58 bytes of state of 1024 particles, 66 KB -- one after the other through a two-stage ring of bulk copies
-// (cp.async.bulk + mbarrier: the copy of tile i+1 runs while tile i is searched), from the rank that owns each tile: its own
+// sum + the 58 bytes of state of 1024 particles, 66 KB -- one after the other through a three-stage ring of bulk copies
+// (cp.async.bulk + mbarrier: tiles i+1 and i+2 are on their way while tile i is searched), from the rank that owns each tile: its own
 // memory or a peer's over NVLink.  Every source tile is read once per CTA that needs it.  For tile t the candidate strata are
 // floor(N S_t) - 2 .. floor(N S_t+1) + 2 (S_t = exact sum before the tile); a stratum belongs to the tile iff
 //   (t == 0 or S_t < sum_r) and (t last or !(cdf[last of t] < sum_r))      <=>  lower_bound(cdf, sum_r) lies in tile t
