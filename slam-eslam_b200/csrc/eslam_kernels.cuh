@@ -2603,19 +2603,27 @@ __global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevSc
             }
             if (klo > khi) klo = khi;
         };
-        auto issue = [&](unsigned t, int stage) {                              // one thread: 10 bulk copies onto one mbarrier
-            const unsigned q = world > 1 ? t / T : 0u;
-            const unsigned long long e0 = (unsigned long long)(t - q * T) * TILE;          // owner-local first element
+        // A source tile is ten bulk copies (running sum, seven doubles, two bytes per particle) onto one mbarrier.  Issuing them
+        // takes ~0.1 us each -- from one thread that was 1 us per tile with everyone waiting for that thread's warp -- so thread 0
+        // arms the barrier with the byte count and, after a CTA barrier, lane 0 of warps 0..9 issues one copy each.
+        auto tile_geometry = [&](unsigned t, unsigned& q, unsigned long long& e0, uint32_t& c8, uint32_t& c1) {
+            q = world > 1 ? t / T : 0u;
+            e0 = (unsigned long long)(t - q * T) * TILE;                       // owner-local first element
             const unsigned cnt = (unsigned)min((unsigned long long)TILE, n - e0);
-            const uint32_t c8 = ((cnt + 1u) & ~1u) * 8u, c1 = (cnt + 15u) & ~15u;   // multiples of 16 bytes (buffers are padded)
-            const uint32_t S = smem0 + (uint32_t)stage * RS_STAGE_BYTES, mb = mbar0 + 8u * (uint32_t)stage;
-            mbar_expect_tx(mb, 8u * c8 + 2u * c1);
-            bulk_g2s(S, peers.cdf[q] + e0, c8, mb);
-#pragma unroll
-            for (int f = 0; f < 7; ++f) bulk_g2s(S + (uint32_t)(1 + f) * TILE * 8u, peers.f[q][cur][f] + e0, c8, mb);
-#pragma unroll
-            for (int f = 0; f < 2; ++f) bulk_g2s(S + 8u * TILE * 8u + (uint32_t)f * TILE, peers.b[q][cur][f] + e0, c1, mb);
+            c8 = ((cnt + 1u) & ~1u) * 8u; c1 = (cnt + 15u) & ~15u;             // multiples of 16 bytes (buffers are padded)
         };
+        auto arm = [&](unsigned t, int stage) {                               // one thread
+            unsigned q; unsigned long long e0; uint32_t c8, c1; tile_geometry(t, q, e0, c8, c1);
+            mbar_expect_tx(mbar0 + 8u * (uint32_t)stage, 8u * c8 + 2u * c1);
+        };
+        auto issue_part = [&](unsigned t, int stage, unsigned part) {         // part 0: running sum, 1..7: doubles, 8..9: bytes
+            unsigned q; unsigned long long e0; uint32_t c8, c1; tile_geometry(t, q, e0, c8, c1);
+            const uint32_t S = smem0 + (uint32_t)stage * RS_STAGE_BYTES, mb = mbar0 + 8u * (uint32_t)stage;
+            if (part == 0) bulk_g2s(S, peers.cdf[q] + e0, c8, mb);
+            else if (part < 8) bulk_g2s(S + part * TILE * 8u, peers.f[q][cur][part - 1] + e0, c8, mb);
+            else bulk_g2s(S + 8u * TILE * 8u + (part - 8u) * TILE, peers.b[q][cur][part - 8] + e0, c1, mb);
+        };
+        const unsigned lane = tid & 31u, warp = tid >> 5;
         // the next source tile after `from` that has candidate strata (tB + 1: none)
         auto next_tile = [&](unsigned from, unsigned long long& lo, unsigned long long& hi) -> unsigned {
             unsigned t = from; lo = hi = 0;
@@ -2625,14 +2633,20 @@ __global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevSc
         unsigned long long klo = 0, khi = 0, nlo = 0, nhi = 0, mlo = 0, mhi = 0;
         unsigned t = next_tile(tA, klo, khi);
         unsigned tn = t <= tB ? next_tile(t + 1, nlo, nhi) : tB + 1;
-        if (tid == 0) { if (t <= tB) issue(t, 0); if (tn <= tB) issue(tn, 1); }
+        if (tid == 0) { if (t <= tB) arm(t, 0); if (tn <= tB) arm(tn, 1); }
+        __syncthreads();
+        if (lane == 0 && warp < 10) { if (t <= tB) issue_part(t, 0, warp); if (tn <= tB) issue_part(tn, 1, warp); }
         int it = 0;
         while (t <= tB) {
             const unsigned tm = tn <= tB ? next_tile(tn + 1, mlo, mhi) : tB + 1;   // two tiles ahead
             const int stage = it % RS_STAGES;
-            if (tm <= tB && tid == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // that stage was read (generic proxy) one iteration ago
-                issue(tm, (it + 2) % RS_STAGES);
+            if (tm <= tB) {                                                    // uniform over the CTA
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // that stage was read (generic proxy) one iteration ago
+                    arm(tm, (it + 2) % RS_STAGES);
+                }
+                __syncthreads();
+                if (lane == 0 && warp < 10) issue_part(tm, (it + 2) % RS_STAGES, warp);
             }
             mbar_wait(mbar0 + 8u * (uint32_t)stage, (uint32_t)(it / RS_STAGES) & 1u);
             {
