@@ -2624,30 +2624,33 @@ __global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevSc
             else bulk_g2s(S + 8u * TILE * 8u + (part - 8u) * TILE, peers.b[q][cur][part - 8] + e0, c1, mb);
         };
         const unsigned lane = tid & 31u, warp = tid >> 5;
+        // the candidate ranges of the CTA's source tiles, once (thread j: tile tA + j): every thread walks them below
+        __shared__ unsigned long long s_klo[RS_TS_CACHE], s_khi[RS_TS_CACHE];
+        for (unsigned j = tid; j < RS_TS_CACHE && tA + j <= tB; j += 1024) { unsigned long long a, b; range(tA + j, a, b); s_klo[j] = a; s_khi[j] = b; }
+        __syncthreads();
         // the next source tile after `from` that has candidate strata (tB + 1: none)
         auto next_tile = [&](unsigned from, unsigned long long& lo, unsigned long long& hi) -> unsigned {
             unsigned t = from; lo = hi = 0;
-            while (t <= tB) { range(t, lo, hi); if (hi > lo) break; ++t; }
+            while (t <= tB) {
+                if (t - tA < RS_TS_CACHE) { lo = s_klo[t - tA]; hi = s_khi[t - tA]; } else range(t, lo, hi);
+                if (hi > lo) break;
+                ++t;
+            }
             return t;
         };
-        unsigned long long klo = 0, khi = 0, nlo = 0, nhi = 0, mlo = 0, mhi = 0;
+        // Three tiles ahead: t is searched, tn and tm are on their way or about to be issued.  A stage's mbarrier is armed by
+        // thread 0 BEFORE the CTA barrier that precedes the issue of its copies, so the top of an iteration only issues.
+        unsigned long long klo = 0, khi = 0, nlo = 0, nhi = 0, mlo = 0, mhi = 0, qlo = 0, qhi = 0;
         unsigned t = next_tile(tA, klo, khi);
         unsigned tn = t <= tB ? next_tile(t + 1, nlo, nhi) : tB + 1;
-        if (tid == 0) { if (t <= tB) arm(t, 0); if (tn <= tB) arm(tn, 1); }
+        unsigned tm = tn <= tB ? next_tile(tn + 1, mlo, mhi) : tB + 1;
+        if (tid == 0) { if (t <= tB) arm(t, 0); if (tn <= tB) arm(tn, 1); if (tm <= tB) arm(tm, 2); }
         __syncthreads();
         if (lane == 0 && warp < 10) { if (t <= tB) issue_part(t, 0, warp); if (tn <= tB) issue_part(tn, 1, warp); }
         int it = 0;
         while (t <= tB) {
-            const unsigned tm = tn <= tB ? next_tile(tn + 1, mlo, mhi) : tB + 1;   // two tiles ahead
             const int stage = it % RS_STAGES;
-            if (tm <= tB) {                                                    // uniform over the CTA
-                if (tid == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // that stage was read (generic proxy) one iteration ago
-                    arm(tm, (it + 2) % RS_STAGES);
-                }
-                __syncthreads();
-                if (lane == 0 && warp < 10) issue_part(tm, (it + 2) % RS_STAGES, warp);
-            }
+            if (tm <= tB && lane == 0 && warp < 10) issue_part(tm, (it + 2) % RS_STAGES, warp);   // that stage was read one iteration ago
             mbar_wait(mbar0 + 8u * (uint32_t)stage, (uint32_t)(it / RS_STAGES) & 1u);
             {
                 const unsigned char* S = rs_raw + (size_t)stage * RS_STAGE_BYTES;
@@ -2675,8 +2678,14 @@ __global__ void __launch_bounds__(1024, 1) k_resample_stream(StateBufs st, DevSc
                     }
                 }
             }
+            // the tile after tm goes into THIS stage at the top of the next iteration: found and armed before the barrier
+            const unsigned tq = tm <= tB ? next_tile(tm + 1, qlo, qhi) : tB + 1;
+            if (tid == 0 && tq <= tB) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was read through the generic proxy
+                arm(tq, stage);
+            }
             __syncthreads();                                                   // everyone is done with this stage
-            t = tn; klo = nlo; khi = nhi; tn = tm; nlo = mlo; nhi = mhi; ++it;
+            t = tn; klo = nlo; khi = nhi; tn = tm; nlo = mlo; nhi = mhi; tm = tq; mlo = qlo; mhi = qhi; ++it;
         }
     }
     // xi_k.swap(xi_kp) :107 by the last CTA (every CTA has read sc->cur by then)
